@@ -1,0 +1,135 @@
+/*
+ * oracle_api.h -- C ABI shared by the two CPU checkers of this repository.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under navigation_b200/ may include, link or load anything
+ * from oracle/.  Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference)
+ * use it, and only as the checker or the timed CPU baseline.
+ *
+ * Two shared libraries export exactly these symbols:
+ *   oracle/_ref/libnavref.so   the reference's own, unmodified hot-path sources compiled from
+ *                              /root/reference against oracle/shim (built by oracle/Makefile,
+ *                              git-ignored); glue in oracle/ref_harness.cpp.
+ *   oracle/libnavoracle.so     a from-scratch CPU restatement (oracle/navoracle.cpp) that is
+ *                              pinned against libnavref.so and the reference's golden vectors.
+ *
+ * Path A mirrors costmap_2d::LayeredCostmap + Layer plugins (costmap_2d/src/layered_costmap.cpp:79-150).
+ * Path B mirrors dwa_local_planner::DWAPlanner::findBestPath (dwa_local_planner/src/dwa_planner.cpp:292-371).
+ */
+#ifndef NAV_ORACLE_API_H_
+#define NAV_ORACLE_API_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* merge policies of CostmapLayer (costmap_2d/src/costmap_layer.cpp:62-157) */
+enum { NAVO_TRUE_OVERWRITE = 0, NAVO_OVERWRITE = 1, NAVO_MAX = 2, NAVO_ADDITION = 3, NAVO_NOTHING = 4 };
+
+/* one costmap_2d::Observation (costmap_2d/include/costmap_2d/observation.h:47-100) */
+typedef struct {
+  double origin_x, origin_y, origin_z;
+  double obstacle_range, raytrace_range;
+  const float* xyz; /* n_points * 3 float32, world frame (pcl::PointXYZ payload) */
+  int32_t n_points;
+  int32_t marking;  /* used by the marking loop  (obstacle_layer.cpp:368-410) */
+  int32_t clearing; /* used by raytraceFreespace (obstacle_layer.cpp:498-576) */
+  int32_t pad_;
+} navo_observation;
+
+/* ---- Path A ---- */
+void* navo_costmap_create(uint32_t size_x, uint32_t size_y, double resolution, double origin_x, double origin_y,
+                          int rolling_window, int track_unknown);
+void navo_costmap_destroy(void* h);
+/* layers are appended in plugin order; each call returns the layer index */
+int navo_costmap_add_grid_layer(void* h, int policy);
+int navo_costmap_add_obstacle_layer(void* h, int combination_method, int footprint_clearing,
+                                    double max_obstacle_height);
+int navo_costmap_add_inflation_layer(void* h, double inflation_radius, double cost_scaling_factor);
+/* LayeredCostmap::setFootprint (layered_costmap.cpp:163-173); xy = n (x,y) pairs in the robot frame */
+void navo_costmap_set_footprint(void* h, const double* xy, int n);
+/* overwrite the whole grid of a grid layer and flag it as updated (StaticLayer::incomingMap semantics) */
+void navo_grid_layer_set(void* h, int layer, const uint8_t* data);
+/* flag a grid layer region dirty without changing data: static_layer.cpp:263-285 bounds = map corners of (x,y,w,h) */
+void navo_grid_layer_touch(void* h, int layer, uint32_t x, uint32_t y, uint32_t w, uint32_t hgt);
+void navo_layer_set_enabled(void* h, int layer, int enabled);
+/* observations persist until replaced (ObstacleLayer::addStaticObservation, obstacle_layer.cpp:450-464) */
+void navo_obstacle_set_observations(void* h, int layer, const navo_observation* obs, int n_obs);
+void navo_inflation_set_params(void* h, int layer, double inflation_radius, double cost_scaling_factor);
+/* LayeredCostmap::updateMap; window_out = {x0, xn, y0, yn} (bx0_, bxn_, by0_, byn_) */
+void navo_costmap_update_map(void* h, double robot_x, double robot_y, double robot_yaw, int32_t window_out[4]);
+void navo_costmap_get(void* h, uint8_t* out);
+void navo_costmap_set(void* h, const uint8_t* in); /* poke the master grid (tests of stateful windowing) */
+void navo_layer_get(void* h, int layer, uint8_t* out);
+void navo_costmap_get_origin(void* h, double out[2]);
+/* InflationLayer cached tables: (R+2)*(R+2) entries each, row-major [i][j]; returns R = cell_inflation_radius_ */
+int navo_inflation_tables(void* h, int layer, uint8_t* costs_out, double* dists_out, int capacity);
+
+/* stand-alone helpers */
+/* StaticLayer::interpretValue (static_layer.cpp:149-163) over n values */
+void navo_interpret_values(const uint8_t* in, uint8_t* out, int64_t n, int track_unknown, uint8_t unknown_cost_value,
+                           uint8_t lethal_threshold, int trinary);
+/* Costmap2D::raytraceLine<MarkCell> cells, in visiting order (costmap_2d.h:359-412); returns count */
+int navo_raytrace_cells(uint32_t size_x, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, uint32_t max_length,
+                        uint32_t* offsets_out, int capacity);
+/* calculateMinAndMaxDistances (footprint.cpp:41-67) */
+void navo_footprint_radii(const double* xy, int n, double* inscribed, double* circumscribed);
+
+/* ---- Path B ---- */
+typedef struct {
+  /* base_local_planner::LocalPlannerLimits (local_planner_limits.h:43-124) */
+  double max_trans_vel, min_trans_vel, max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_rot_vel, min_rot_vel;
+  double acc_lim_x, acc_lim_y, acc_lim_theta;
+  /* DWAPlannerConfig (dwa_local_planner/cfg/DWAPlanner.cfg) */
+  double sim_time, sim_granularity, angular_sim_granularity, sim_period;
+  double path_distance_bias, goal_distance_bias, occdist_scale;
+  double forward_point_distance, cheat_factor;
+  double oscillation_reset_dist, oscillation_reset_angle;
+  double scaling_speed, max_scaling_factor;
+  int32_t vx_samples, vy_samples, vth_samples;
+  int32_t use_dwa, sum_scores, allow_unknown; /* allow_unknown: honoured by the restatement only */
+} navo_dwa_config;
+
+typedef struct {
+  double cost;       /* result_traj_.cost_ (-7 when nothing valid; dwa_planner.cpp:316) */
+  double xv, yv, thetav;
+  int32_t best_index; /* index into the enumerated sample list (x outer, y, theta inner), -1 if none */
+  int32_t n_samples;  /* number of enumerated samples */
+  int32_t n_scored;   /* samples for which generateTrajectory returned true */
+  int32_t n_points;   /* points of the winning trajectory */
+} navo_dwa_result;
+
+void navo_dwa_default_config(navo_dwa_config* cfg);
+void* navo_dwa_create(const navo_dwa_config* cfg, uint32_t size_x, uint32_t size_y, double resolution);
+void navo_dwa_destroy(void* h);
+void navo_dwa_set_costmap(void* h, const uint8_t* grid, double origin_x, double origin_y);
+/* DWAPlanner::updatePlanAndLocalCosts (dwa_planner.cpp:240-286); plan_xy = n (x,y) pairs */
+void navo_dwa_set_plan(void* h, const double pose[3], const double* plan_xy, int n);
+void navo_dwa_reset_oscillation(void* h);
+int navo_dwa_get_oscillation_mask(void* h); /* bit0 fwd_pos_only,1 fwd_neg_only,2 strafe_pos_only,3 strafe_neg_only,4 rot_pos_only,5 rot_neg_only */
+/* DWAPlanner::findBestPath.  all_costs (nullable, capacity >= n_samples): cost reported in all_explored for each
+ * enumerated sample, NaN for samples the generator rejected.  best_points (nullable): 3*capacity doubles. */
+int navo_dwa_find_best_path(void* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                            int n_footprint, navo_dwa_result* result, double* all_costs, int all_capacity,
+                            double* best_points, int points_capacity);
+/* the four MapGrid distance fields after prepare(): which = 0 path, 1 goal, 2 goal_front, 3 alignment */
+void navo_dwa_get_grid(void* h, int which, double* out);
+/* only the 4 prepare() calls (MapGrid BFS), for timing them separately */
+void navo_dwa_prepare_only(void* h);
+
+/* stand-alone Path-B helpers for the reference's golden vectors */
+/* VelocityIterator samples (velocity_iterator.h:47-96); returns count */
+int navo_velocity_samples(double vmin, double vmax, int num_samples, double* out, int capacity);
+/* LineIterator cells (line_iterator.h:38-139); xy_out = pairs; returns count */
+int navo_line_cells(int x0, int y0, int x1, int y1, int32_t* xy_out, int capacity);
+/* MapGrid BFS from explicit seed cells over a cost grid (map_grid.cpp:258-310) */
+void navo_mapgrid_bfs(const uint8_t* costs, uint32_t size_x, uint32_t size_y, const int32_t* seeds_xy, int n_seeds,
+                      int allow_unknown, double* dist_out);
+
+const char* navo_impl_name(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

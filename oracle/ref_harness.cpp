@@ -1,0 +1,702 @@
+// ref_harness.cpp -- glue that exposes the reference's OWN compiled hot-path code through oracle_api.h.
+//
+// TEST INFRASTRUCTURE ONLY.  Compiled by oracle/Makefile together with the unmodified reference sources
+// (read in place from /root/reference, never copied) into oracle/_ref/libnavref.so.
+//
+// What is reference code and what is restated here (because the enclosing reference TU needs ROS/PCL/tf):
+//   reference, unmodified: Costmap2D, Layer, LayeredCostmap, CostmapLayer (all four updateWith*),
+//       InflationLayer, raytraceLine/bresenham2D/MarkCell, setConvexPolygonCost, MapGrid, MapGridCostFunction,
+//       ObstacleCostFunction, CostmapModel, LineIterator, OscillationCostFunction, SimpleTrajectoryGenerator,
+//       VelocityIterator, SimpleScoredSamplingPlanner, Trajectory, calculateMinAndMaxDistances (via LayeredCostmap).
+//   restated in this file: ObstacleLayer::updateBounds/raytraceFreespace/updateRaytraceBounds/updateFootprint/
+//       updateCosts bodies (costmap_2d/plugins/obstacle_layer.cpp:340-448,498-610) on top of the reference's
+//       protected CostmapLayer primitives; StaticLayer::updateBounds/updateCosts non-rolling branch and
+//       interpretValue (static_layer.cpp:149-163,263-299); transformFootprint and calculateMinAndMaxDistances
+//       (footprint.cpp:41-67,106-120, that TU needs boost tokenizer + XmlRpc); DWAPlanner's wiring
+//       (dwa_planner.cpp:52-112,116-182,240-286,292-319,357).
+#include <costmap_2d/costmap_2d.h>
+#include <costmap_2d/layered_costmap.h>
+#include <costmap_2d/costmap_layer.h>
+#include <costmap_2d/inflation_layer.h>
+#include <costmap_2d/cost_values.h>
+#include <costmap_2d/costmap_math.h>
+#include <costmap_2d/observation.h>
+#include <base_local_planner/map_grid.h>
+#include <base_local_planner/map_grid_cost_function.h>
+#include <base_local_planner/obstacle_cost_function.h>
+#include <base_local_planner/oscillation_cost_function.h>
+#include <base_local_planner/simple_trajectory_generator.h>
+#include <base_local_planner/simple_scored_sampling_planner.h>
+#include <base_local_planner/velocity_iterator.h>
+#include <base_local_planner/line_iterator.h>
+#include <base_local_planner/local_planner_limits.h>
+
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <queue>
+#include <vector>
+
+#include "oracle_api.h"
+
+// ---- footprint.cpp needs boost::tokenizer/XmlRpc; its two pure functions are restated (footprint.cpp:41-67,106-120)
+namespace costmap_2d {
+void calculateMinAndMaxDistances(const std::vector<geometry_msgs::Point>& footprint, double& min_dist,
+                                 double& max_dist) {
+  min_dist = std::numeric_limits<double>::max();
+  max_dist = 0.0;
+  if (footprint.size() <= 2) return;
+  for (unsigned int i = 0; i < footprint.size() - 1; ++i) {
+    double vertex_dist = distance(0.0, 0.0, footprint[i].x, footprint[i].y);
+    double edge_dist = distanceToLine(0.0, 0.0, footprint[i].x, footprint[i].y, footprint[i + 1].x, footprint[i + 1].y);
+    min_dist = std::min(min_dist, std::min(vertex_dist, edge_dist));
+    max_dist = std::max(max_dist, std::max(vertex_dist, edge_dist));
+  }
+  double vertex_dist = distance(0.0, 0.0, footprint.back().x, footprint.back().y);
+  double edge_dist =
+      distanceToLine(0.0, 0.0, footprint.back().x, footprint.back().y, footprint.front().x, footprint.front().y);
+  min_dist = std::min(min_dist, std::min(vertex_dist, edge_dist));
+  max_dist = std::max(max_dist, std::max(vertex_dist, edge_dist));
+}
+
+void transformFootprint(double x, double y, double theta, const std::vector<geometry_msgs::Point>& footprint_spec,
+                        std::vector<geometry_msgs::Point>& oriented_footprint) {
+  oriented_footprint.clear();
+  double cos_th = cos(theta);
+  double sin_th = sin(theta);
+  for (unsigned int i = 0; i < footprint_spec.size(); ++i) {
+    geometry_msgs::Point new_pt;
+    new_pt.x = x + (footprint_spec[i].x * cos_th - footprint_spec[i].y * sin_th);
+    new_pt.y = y + (footprint_spec[i].x * sin_th + footprint_spec[i].y * cos_th);
+    oriented_footprint.push_back(new_pt);
+  }
+}
+}  // namespace costmap_2d
+
+namespace {
+
+using costmap_2d::Costmap2D;
+using costmap_2d::CostmapLayer;
+using costmap_2d::LayeredCostmap;
+
+// A CostmapLayer whose cells are supplied by the caller; merge policy selectable.  With TRUE_OVERWRITE / MAX it is
+// StaticLayer's non-rolling behaviour (static_layer.cpp:263-299).
+class GridLayer : public CostmapLayer {
+ public:
+  explicit GridLayer(int policy) : policy_(policy), x_(0), y_(0), width_(0), height_(0), has_updated_data_(false) {}
+  void onInitialize() override {
+    current_ = true;
+    enabled_ = true;
+    default_value_ = layered_costmap_->isTrackingUnknown() ? costmap_2d::NO_INFORMATION : costmap_2d::FREE_SPACE;
+    matchSize();
+  }
+  void setData(const uint8_t* data) {
+    memcpy(costmap_, data, size_t(size_x_) * size_y_);
+    x_ = y_ = 0;
+    width_ = size_x_;
+    height_ = size_y_;
+    has_updated_data_ = true;
+  }
+  void touchRegion(unsigned x, unsigned y, unsigned w, unsigned h) {
+    x_ = x; y_ = y; width_ = w; height_ = h;
+    has_updated_data_ = true;
+  }
+  void setEnabled(bool e) { enabled_ = e; }
+  void updateBounds(double, double, double, double* min_x, double* min_y, double* max_x, double* max_y) override {
+    if (!layered_costmap_->isRolling()) {
+      if (!(has_updated_data_ || has_extra_bounds_)) return;
+    }
+    useExtraBounds(min_x, min_y, max_x, max_y);
+    double wx, wy;
+    mapToWorld(x_, y_, wx, wy);
+    *min_x = std::min(wx, *min_x);
+    *min_y = std::min(wy, *min_y);
+    mapToWorld(x_ + width_, y_ + height_, wx, wy);
+    *max_x = std::max(wx, *max_x);
+    *max_y = std::max(wy, *max_y);
+    has_updated_data_ = false;
+  }
+  void updateCosts(Costmap2D& master, int min_i, int min_j, int max_i, int max_j) override {
+    switch (policy_) {
+      case NAVO_TRUE_OVERWRITE: updateWithTrueOverwrite(master, min_i, min_j, max_i, max_j); break;
+      case NAVO_OVERWRITE: updateWithOverwrite(master, min_i, min_j, max_i, max_j); break;
+      case NAVO_MAX: updateWithMax(master, min_i, min_j, max_i, max_j); break;
+      case NAVO_ADDITION: updateWithAddition(master, min_i, min_j, max_i, max_j); break;
+      default: break;
+    }
+  }
+  int policy_;
+  unsigned x_, y_, width_, height_;
+  bool has_updated_data_;
+};
+
+struct OwnedObservation {
+  double ox, oy, oz, obstacle_range, raytrace_range;
+  std::vector<float> xyz;
+  bool marking, clearing;
+};
+
+// ObstacleLayer's algorithmic part on top of the reference's CostmapLayer primitives.
+class RefObstacleLayer : public CostmapLayer {
+ public:
+  RefObstacleLayer(int combination_method, bool footprint_clearing, double max_obstacle_height)
+      : combination_method_(combination_method),
+        footprint_clearing_enabled_(footprint_clearing),
+        max_obstacle_height_(max_obstacle_height),
+        rolling_window_(false) {}
+  void onInitialize() override {  // obstacle_layer.cpp:54-66
+    rolling_window_ = layered_costmap_->isRolling();
+    default_value_ = layered_costmap_->isTrackingUnknown() ? costmap_2d::NO_INFORMATION : costmap_2d::FREE_SPACE;
+    matchSize();
+    current_ = true;
+    enabled_ = true;
+  }
+  void setEnabled(bool e) { enabled_ = e; }
+  std::vector<OwnedObservation> observations_;
+
+  void updateBounds(double robot_x, double robot_y, double robot_yaw, double* min_x, double* min_y, double* max_x,
+                    double* max_y) override {  // obstacle_layer.cpp:340-413
+    if (rolling_window_) updateOrigin(robot_x - getSizeInMetersX() / 2, robot_y - getSizeInMetersY() / 2);
+    if (!enabled_) return;
+    useExtraBounds(min_x, min_y, max_x, max_y);
+    for (size_t i = 0; i < observations_.size(); ++i)
+      if (observations_[i].clearing) raytraceFreespace(observations_[i], min_x, min_y, max_x, max_y);
+    for (size_t k = 0; k < observations_.size(); ++k) {
+      const OwnedObservation& obs = observations_[k];
+      if (!obs.marking) continue;
+      double sq_obstacle_range = obs.obstacle_range * obs.obstacle_range;
+      for (size_t i = 0; i < obs.xyz.size() / 3; ++i) {
+        double px = obs.xyz[3 * i], py = obs.xyz[3 * i + 1], pz = obs.xyz[3 * i + 2];
+        if (pz > max_obstacle_height_) continue;
+        double sq_dist = (px - obs.ox) * (px - obs.ox) + (py - obs.oy) * (py - obs.oy) + (pz - obs.oz) * (pz - obs.oz);
+        if (sq_dist >= sq_obstacle_range) continue;
+        unsigned int mx, my;
+        if (!worldToMap(px, py, mx, my)) continue;
+        costmap_[getIndex(mx, my)] = costmap_2d::LETHAL_OBSTACLE;
+        touch(px, py, min_x, min_y, max_x, max_y);
+      }
+    }
+    // updateFootprint, obstacle_layer.cpp:415-425
+    if (!footprint_clearing_enabled_) return;
+    costmap_2d::transformFootprint(robot_x, robot_y, robot_yaw, getFootprint(), transformed_footprint_);
+    for (unsigned int i = 0; i < transformed_footprint_.size(); i++)
+      touch(transformed_footprint_[i].x, transformed_footprint_[i].y, min_x, min_y, max_x, max_y);
+  }
+
+  void updateCosts(Costmap2D& master_grid, int min_i, int min_j, int max_i, int max_j) override {  // :427-448
+    if (!enabled_) return;
+    if (footprint_clearing_enabled_) setConvexPolygonCost(transformed_footprint_, costmap_2d::FREE_SPACE);
+    switch (combination_method_) {
+      case 0: updateWithOverwrite(master_grid, min_i, min_j, max_i, max_j); break;
+      case 1: updateWithMax(master_grid, min_i, min_j, max_i, max_j); break;
+      default: break;
+    }
+  }
+
+ private:
+  void raytraceFreespace(const OwnedObservation& obs, double* min_x, double* min_y, double* max_x,
+                         double* max_y) {  // obstacle_layer.cpp:498-576
+    double ox = obs.ox, oy = obs.oy;
+    unsigned int x0, y0;
+    if (!worldToMap(ox, oy, x0, y0)) return;
+    double origin_x = origin_x_, origin_y = origin_y_;
+    double map_end_x = origin_x + size_x_ * resolution_;
+    double map_end_y = origin_y + size_y_ * resolution_;
+    touch(ox, oy, min_x, min_y, max_x, max_y);
+    for (size_t i = 0; i < obs.xyz.size() / 3; ++i) {
+      double wx = obs.xyz[3 * i];
+      double wy = obs.xyz[3 * i + 1];
+      double a = wx - ox;
+      double b = wy - oy;
+      if (wx < origin_x) {
+        double t = (origin_x - ox) / a;
+        wx = origin_x;
+        wy = oy + b * t;
+      }
+      if (wy < origin_y) {
+        double t = (origin_y - oy) / b;
+        wx = ox + a * t;
+        wy = origin_y;
+      }
+      if (wx > map_end_x) {
+        double t = (map_end_x - ox) / a;
+        wx = map_end_x - .001;
+        wy = oy + b * t;
+      }
+      if (wy > map_end_y) {
+        double t = (map_end_y - oy) / b;
+        wx = ox + a * t;
+        wy = map_end_y - .001;
+      }
+      unsigned int x1, y1;
+      if (!worldToMap(wx, wy, x1, y1)) continue;
+      unsigned int cell_raytrace_range = cellDistance(obs.raytrace_range);
+      MarkCell marker(costmap_, costmap_2d::FREE_SPACE);
+      raytraceLine(marker, x0, y0, x1, y1, cell_raytrace_range);
+      // updateRaytraceBounds, obstacle_layer.cpp:602-610
+      double dx = wx - ox, dy = wy - oy;
+      double full_distance = hypot(dx, dy);
+      double scale = std::min(1.0, obs.raytrace_range / full_distance);
+      double ex = ox + dx * scale, ey = oy + dy * scale;
+      touch(ex, ey, min_x, min_y, max_x, max_y);
+    }
+  }
+  int combination_method_;
+  bool footprint_clearing_enabled_;
+  double max_obstacle_height_;
+  bool rolling_window_;
+  std::vector<geometry_msgs::Point> transformed_footprint_;
+};
+
+// exposes Costmap2D's protected raytraceLine
+class RayProbe : public Costmap2D {
+ public:
+  RayProbe(unsigned sx) : Costmap2D(sx, 1, 1.0, 0, 0) {}
+  struct Collect {
+    std::vector<unsigned>* v;
+    void operator()(unsigned off) { v->push_back(off); }
+  };
+  void trace(unsigned x0, unsigned y0, unsigned x1, unsigned y1, unsigned maxlen, std::vector<unsigned>& out) {
+    Collect c{&out};
+    raytraceLine(c, x0, y0, x1, y1, maxlen);
+  }
+};
+
+struct CostmapHandle {
+  std::unique_ptr<LayeredCostmap> lc;
+  std::vector<costmap_2d::Layer*> layers;  // owned by lc's shared_ptrs
+  std::vector<int> kinds;                  // 0 grid, 1 obstacle, 2 inflation
+  std::vector<double> infl_radius;         // per layer (only meaningful for kind 2)
+  tf::TransformListener tf;
+};
+
+std::vector<geometry_msgs::Point> toPoints(const double* xy, int n) {
+  std::vector<geometry_msgs::Point> v(n);
+  for (int i = 0; i < n; ++i) {
+    v[i].x = xy[2 * i];
+    v[i].y = xy[2 * i + 1];
+  }
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* navo_impl_name(void) { return "reference"; }
+
+void* navo_costmap_create(uint32_t size_x, uint32_t size_y, double resolution, double origin_x, double origin_y,
+                          int rolling_window, int track_unknown) {
+  CostmapHandle* h = new CostmapHandle;
+  h->lc.reset(new LayeredCostmap("map", rolling_window != 0, track_unknown != 0));
+  h->lc->resizeMap(size_x, size_y, resolution, origin_x, origin_y);
+  return h;
+}
+void navo_costmap_destroy(void* hv) { delete static_cast<CostmapHandle*>(hv); }
+
+static int addLayer(CostmapHandle* h, costmap_2d::Layer* l, int kind, const char* name) {
+  h->lc->addPlugin(boost::shared_ptr<costmap_2d::Layer>(l));
+  l->initialize(h->lc.get(), name, &h->tf);
+  h->layers.push_back(l);
+  h->kinds.push_back(kind);
+  h->infl_radius.push_back(0.0);
+  return int(h->layers.size()) - 1;
+}
+int navo_costmap_add_grid_layer(void* hv, int policy) {
+  return addLayer(static_cast<CostmapHandle*>(hv), new GridLayer(policy), 0, "grid");
+}
+int navo_costmap_add_obstacle_layer(void* hv, int combination_method, int footprint_clearing,
+                                    double max_obstacle_height) {
+  return addLayer(static_cast<CostmapHandle*>(hv),
+                  new RefObstacleLayer(combination_method, footprint_clearing != 0, max_obstacle_height), 1,
+                  "obstacles");
+}
+int navo_costmap_add_inflation_layer(void* hv, double inflation_radius, double cost_scaling_factor) {
+  CostmapHandle* h = static_cast<CostmapHandle*>(hv);
+  costmap_2d::InflationLayer* il = new costmap_2d::InflationLayer();
+  int id = addLayer(h, il, 2, "inflation");
+  il->setInflationParameters(inflation_radius, cost_scaling_factor);
+  h->infl_radius[id] = inflation_radius;
+  return id;
+}
+void navo_costmap_set_footprint(void* hv, const double* xy, int n) {
+  static_cast<CostmapHandle*>(hv)->lc->setFootprint(toPoints(xy, n));
+}
+void navo_grid_layer_set(void* hv, int layer, const uint8_t* data) {
+  static_cast<GridLayer*>(static_cast<CostmapHandle*>(hv)->layers[layer])->setData(data);
+}
+void navo_grid_layer_touch(void* hv, int layer, uint32_t x, uint32_t y, uint32_t w, uint32_t hgt) {
+  static_cast<GridLayer*>(static_cast<CostmapHandle*>(hv)->layers[layer])->touchRegion(x, y, w, hgt);
+}
+void navo_layer_set_enabled(void* hv, int layer, int enabled) {
+  CostmapHandle* h = static_cast<CostmapHandle*>(hv);
+  if (h->kinds[layer] == 0) static_cast<GridLayer*>(h->layers[layer])->setEnabled(enabled != 0);
+  if (h->kinds[layer] == 1) static_cast<RefObstacleLayer*>(h->layers[layer])->setEnabled(enabled != 0);
+}
+void navo_obstacle_set_observations(void* hv, int layer, const navo_observation* obs, int n_obs) {
+  RefObstacleLayer* ol = static_cast<RefObstacleLayer*>(static_cast<CostmapHandle*>(hv)->layers[layer]);
+  ol->observations_.clear();
+  for (int i = 0; i < n_obs; ++i) {
+    OwnedObservation o;
+    o.ox = obs[i].origin_x; o.oy = obs[i].origin_y; o.oz = obs[i].origin_z;
+    o.obstacle_range = obs[i].obstacle_range;
+    o.raytrace_range = obs[i].raytrace_range;
+    o.xyz.assign(obs[i].xyz, obs[i].xyz + 3 * size_t(obs[i].n_points));
+    o.marking = obs[i].marking != 0;
+    o.clearing = obs[i].clearing != 0;
+    ol->observations_.push_back(o);
+  }
+}
+void navo_inflation_set_params(void* hv, int layer, double inflation_radius, double cost_scaling_factor) {
+  static_cast<CostmapHandle*>(hv)->infl_radius[layer] = inflation_radius;
+  static_cast<costmap_2d::InflationLayer*>(static_cast<CostmapHandle*>(hv)->layers[layer])
+      ->setInflationParameters(inflation_radius, cost_scaling_factor);
+}
+void navo_costmap_update_map(void* hv, double rx, double ry, double ryaw, int32_t w[4]) {
+  CostmapHandle* h = static_cast<CostmapHandle*>(hv);
+  h->lc->updateMap(rx, ry, ryaw);
+  unsigned int x0, xn, y0, yn;
+  h->lc->getBounds(&x0, &xn, &y0, &yn);
+  w[0] = x0; w[1] = xn; w[2] = y0; w[3] = yn;
+}
+void navo_costmap_get(void* hv, uint8_t* out) {
+  Costmap2D* c = static_cast<CostmapHandle*>(hv)->lc->getCostmap();
+  memcpy(out, c->getCharMap(), size_t(c->getSizeInCellsX()) * c->getSizeInCellsY());
+}
+void navo_costmap_set(void* hv, const uint8_t* in) {
+  Costmap2D* c = static_cast<CostmapHandle*>(hv)->lc->getCostmap();
+  memcpy(c->getCharMap(), in, size_t(c->getSizeInCellsX()) * c->getSizeInCellsY());
+}
+void navo_layer_get(void* hv, int layer, uint8_t* out) {
+  CostmapHandle* h = static_cast<CostmapHandle*>(hv);
+  if (h->kinds[layer] == 2) return;
+  Costmap2D* c = (h->kinds[layer] == 0) ? static_cast<Costmap2D*>(static_cast<GridLayer*>(h->layers[layer]))
+                                        : static_cast<Costmap2D*>(static_cast<RefObstacleLayer*>(h->layers[layer]));
+  memcpy(out, c->getCharMap(), size_t(c->getSizeInCellsX()) * c->getSizeInCellsY());
+}
+void navo_costmap_get_origin(void* hv, double out[2]) {
+  Costmap2D* c = static_cast<CostmapHandle*>(hv)->lc->getCostmap();
+  out[0] = c->getOriginX();
+  out[1] = c->getOriginY();
+}
+int navo_inflation_tables(void* hv, int layer, uint8_t* costs_out, double* dists_out, int capacity) {
+  // The cached tables are private; they are fully determined by the public computeCost and hypot, exactly as
+  // computeCaches builds them (inflation_layer.cpp:295-328); R as matchSize computes it (:110-123).
+  CostmapHandle* h = static_cast<CostmapHandle*>(hv);
+  costmap_2d::InflationLayer* il = static_cast<costmap_2d::InflationLayer*>(h->layers[layer]);
+  int R = int(h->lc->getCostmap()->cellDistance(h->infl_radius[layer]));
+  int n = R + 2;
+  if (n * n > capacity) return R;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double d = hypot(i, j);
+      dists_out[i * n + j] = d;
+      costs_out[i * n + j] = il->computeCost(d);
+    }
+  return R;
+}
+
+void navo_interpret_values(const uint8_t* in, uint8_t* out, int64_t n, int track_unknown, uint8_t unknown_cost_value,
+                           uint8_t lethal_threshold, int trinary) {  // static_layer.cpp:149-163
+  for (int64_t i = 0; i < n; ++i) {
+    unsigned char value = in[i];
+    unsigned char r;
+    if (track_unknown && value == unknown_cost_value) r = costmap_2d::NO_INFORMATION;
+    else if (!track_unknown && value == unknown_cost_value) r = costmap_2d::FREE_SPACE;
+    else if (value >= lethal_threshold) r = costmap_2d::LETHAL_OBSTACLE;
+    else if (trinary) r = costmap_2d::FREE_SPACE;
+    else {
+      double scale = (double)value / lethal_threshold;
+      r = scale * costmap_2d::LETHAL_OBSTACLE;
+    }
+    out[i] = r;
+  }
+}
+
+int navo_raytrace_cells(uint32_t size_x, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, uint32_t max_length,
+                        uint32_t* offsets_out, int capacity) {
+  RayProbe p(size_x);
+  std::vector<unsigned> v;
+  p.trace(x0, y0, x1, y1, max_length, v);
+  for (size_t i = 0; i < v.size() && int(i) < capacity; ++i) offsets_out[i] = v[i];
+  return int(v.size());
+}
+
+void navo_footprint_radii(const double* xy, int n, double* inscribed, double* circumscribed) {
+  costmap_2d::calculateMinAndMaxDistances(toPoints(xy, n), *inscribed, *circumscribed);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ Path B
+namespace {
+
+using namespace base_local_planner;
+
+std::vector<geometry_msgs::PoseStamped> toPoses(const double* xy, int n) {
+  std::vector<geometry_msgs::PoseStamped> v(n);
+  for (int i = 0; i < n; ++i) {
+    v[i].pose.position.x = xy[2 * i];
+    v[i].pose.position.y = xy[2 * i + 1];
+  }
+  return v;
+}
+
+// DWAPlanner's wiring (dwa_planner.cpp:116-182) around the reference's critics / generator / search.
+struct DwaHandle {
+  navo_dwa_config cfg;
+  Costmap2D costmap;
+  LocalPlannerLimits limits;
+  ObstacleCostFunction obstacle_costs_;
+  MapGridCostFunction path_costs_, goal_costs_, goal_front_costs_, alignment_costs_;
+  OscillationCostFunction oscillation_costs_;
+  SimpleTrajectoryGenerator generator_;
+  SimpleScoredSamplingPlanner scored_sampling_planner_;
+  std::vector<geometry_msgs::PoseStamped> global_plan_;
+  Eigen::Vector3f vsamples_;
+  double pdist_scale_, gdist_scale_, occdist_scale_, forward_point_distance_, cheat_factor_;
+  Trajectory result_traj_;
+
+  DwaHandle(const navo_dwa_config& c, unsigned sx, unsigned sy, double res)
+      : cfg(c),
+        costmap(sx, sy, res, 0.0, 0.0, 0),
+        obstacle_costs_(&costmap),
+        path_costs_(&costmap),
+        goal_costs_(&costmap, 0.0, 0.0, true),
+        goal_front_costs_(&costmap, 0.0, 0.0, true),
+        alignment_costs_(&costmap) {
+    goal_front_costs_.setStopOnFailure(false);
+    alignment_costs_.setStopOnFailure(false);
+    oscillation_costs_.resetOscillationFlags();
+    obstacle_costs_.setSumScores(c.sum_scores != 0);
+    std::vector<TrajectoryCostFunction*> critics;
+    critics.push_back(&oscillation_costs_);
+    critics.push_back(&obstacle_costs_);
+    critics.push_back(&goal_front_costs_);
+    critics.push_back(&alignment_costs_);
+    critics.push_back(&path_costs_);
+    critics.push_back(&goal_costs_);
+    std::vector<TrajectorySampleGenerator*> generator_list;
+    generator_list.push_back(&generator_);
+    scored_sampling_planner_ = SimpleScoredSamplingPlanner(generator_list, critics);
+    cheat_factor_ = c.cheat_factor;
+    reconfigure();
+  }
+  void reconfigure() {  // dwa_planner.cpp:52-112
+    const navo_dwa_config& c = cfg;
+    limits.max_trans_vel = c.max_trans_vel; limits.min_trans_vel = c.min_trans_vel;
+    limits.max_vel_x = c.max_vel_x; limits.min_vel_x = c.min_vel_x;
+    limits.max_vel_y = c.max_vel_y; limits.min_vel_y = c.min_vel_y;
+    limits.max_rot_vel = c.max_rot_vel; limits.min_rot_vel = c.min_rot_vel;
+    limits.acc_lim_x = c.acc_lim_x; limits.acc_lim_y = c.acc_lim_y; limits.acc_lim_theta = c.acc_lim_theta;
+    generator_.setParameters(c.sim_time, c.sim_granularity, c.angular_sim_granularity, c.use_dwa != 0, c.sim_period);
+    double resolution = costmap.getResolution();
+    pdist_scale_ = c.path_distance_bias;
+    path_costs_.setScale(resolution * pdist_scale_ * 0.5);
+    alignment_costs_.setScale(resolution * pdist_scale_ * 0.5);
+    gdist_scale_ = c.goal_distance_bias;
+    goal_costs_.setScale(resolution * gdist_scale_ * 0.5);
+    goal_front_costs_.setScale(resolution * gdist_scale_ * 0.5);
+    occdist_scale_ = c.occdist_scale;
+    obstacle_costs_.setScale(resolution * occdist_scale_);
+    oscillation_costs_.setOscillationResetDist(c.oscillation_reset_dist, c.oscillation_reset_angle);
+    forward_point_distance_ = c.forward_point_distance;
+    goal_front_costs_.setXShift(forward_point_distance_);
+    alignment_costs_.setXShift(forward_point_distance_);
+    obstacle_costs_.setParams(c.max_trans_vel, c.max_scaling_factor, c.scaling_speed);
+    int vx = c.vx_samples <= 0 ? 1 : c.vx_samples;
+    int vy = c.vy_samples <= 0 ? 1 : c.vy_samples;
+    int vth = c.vth_samples <= 0 ? 1 : c.vth_samples;
+    vsamples_[0] = vx; vsamples_[1] = vy; vsamples_[2] = vth;
+  }
+};
+
+// Costmap2D keeps its origin protected; this subclass-free trick re-creates geometry through resizeMap.
+void setCostmap(Costmap2D& cm, const uint8_t* grid, double ox, double oy) {
+  unsigned sx = cm.getSizeInCellsX(), sy = cm.getSizeInCellsY();
+  if (cm.getOriginX() != ox || cm.getOriginY() != oy) {
+    // updateOrigin snaps to the grid; resizeMap sets the origin verbatim and keeps the same buffer size
+    cm.resizeMap(sx, sy, cm.getResolution(), ox, oy);
+  }
+  memcpy(cm.getCharMap(), grid, size_t(sx) * sy);
+}
+
+}  // namespace
+
+extern "C" {
+
+void navo_dwa_default_config(navo_dwa_config* c) {
+  // base_local_planner/src/local_planner_limits/__init__.py:15-45, dwa_local_planner/cfg/DWAPlanner.cfg:15-43
+  c->max_trans_vel = 0.55; c->min_trans_vel = 0.1; c->max_vel_x = 0.55; c->min_vel_x = 0.0;
+  c->max_vel_y = 0.1; c->min_vel_y = -0.1; c->max_rot_vel = 1.0; c->min_rot_vel = 0.4;
+  c->acc_lim_x = 2.5; c->acc_lim_y = 2.5; c->acc_lim_theta = 3.2;
+  c->sim_time = 1.7; c->sim_granularity = 0.025; c->angular_sim_granularity = 0.1; c->sim_period = 0.05;
+  c->path_distance_bias = 32.0; c->goal_distance_bias = 24.0; c->occdist_scale = 0.01;
+  c->forward_point_distance = 0.325; c->cheat_factor = 1.0;
+  c->oscillation_reset_dist = 0.05; c->oscillation_reset_angle = 0.2;
+  c->scaling_speed = 0.25; c->max_scaling_factor = 0.2;
+  c->vx_samples = 3; c->vy_samples = 10; c->vth_samples = 20;
+  c->use_dwa = 1; c->sum_scores = 0; c->allow_unknown = 0;
+}
+
+void* navo_dwa_create(const navo_dwa_config* cfg, uint32_t size_x, uint32_t size_y, double resolution) {
+  return new DwaHandle(*cfg, size_x, size_y, resolution);
+}
+void navo_dwa_destroy(void* hv) { delete static_cast<DwaHandle*>(hv); }
+void navo_dwa_set_costmap(void* hv, const uint8_t* grid, double ox, double oy) {
+  setCostmap(static_cast<DwaHandle*>(hv)->costmap, grid, ox, oy);
+}
+
+void navo_dwa_set_plan(void* hv, const double pose[3], const double* plan_xy, int n) {  // dwa_planner.cpp:240-286
+  DwaHandle* h = static_cast<DwaHandle*>(hv);
+  h->global_plan_ = toPoses(plan_xy, n);
+  h->path_costs_.setTargetPoses(h->global_plan_);
+  h->goal_costs_.setTargetPoses(h->global_plan_);
+  geometry_msgs::PoseStamped goal_pose = h->global_plan_.back();
+  Eigen::Vector3f pos(pose[0], pose[1], pose[2]);
+  double sq_dist = (pos[0] - goal_pose.pose.position.x) * (pos[0] - goal_pose.pose.position.x) +
+                   (pos[1] - goal_pose.pose.position.y) * (pos[1] - goal_pose.pose.position.y);
+  std::vector<geometry_msgs::PoseStamped> front_global_plan = h->global_plan_;
+  double angle_to_goal = atan2(goal_pose.pose.position.y - pos[1], goal_pose.pose.position.x - pos[0]);
+  front_global_plan.back().pose.position.x =
+      front_global_plan.back().pose.position.x + h->forward_point_distance_ * cos(angle_to_goal);
+  front_global_plan.back().pose.position.y =
+      front_global_plan.back().pose.position.y + h->forward_point_distance_ * sin(angle_to_goal);
+  h->goal_front_costs_.setTargetPoses(front_global_plan);
+  if (sq_dist > h->forward_point_distance_ * h->forward_point_distance_ * h->cheat_factor_) {
+    double resolution = h->costmap.getResolution();
+    h->alignment_costs_.setScale(resolution * h->pdist_scale_ * 0.5);
+    h->alignment_costs_.setTargetPoses(h->global_plan_);
+  } else {
+    h->alignment_costs_.setScale(0.0);
+  }
+}
+
+void navo_dwa_reset_oscillation(void* hv) { static_cast<DwaHandle*>(hv)->oscillation_costs_.resetOscillationFlags(); }
+
+int navo_dwa_get_oscillation_mask(void* hv) {
+  // the *_only_ flags are private; probe them through the public scoreTrajectory (oscillation_cost_function.cpp:166-176)
+  DwaHandle* h = static_cast<DwaHandle*>(hv);
+  const double probes[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+  int mask = 0;
+  for (int i = 0; i < 6; ++i) {
+    Trajectory t;
+    t.xv_ = probes[i][0]; t.yv_ = probes[i][1]; t.thetav_ = probes[i][2];
+    if (h->oscillation_costs_.scoreTrajectory(t) < 0) mask |= 1 << i;
+  }
+  return mask;
+}
+
+int navo_dwa_find_best_path(void* hv, const double pose[3], const double velv[3], const double* footprint_xy,
+                            int n_footprint, navo_dwa_result* result, double* all_costs, int all_capacity,
+                            double* best_points, int points_capacity) {  // dwa_planner.cpp:292-371
+  DwaHandle* h = static_cast<DwaHandle*>(hv);
+  h->obstacle_costs_.setFootprint(toPoints(footprint_xy, n_footprint));
+  Eigen::Vector3f pos(pose[0], pose[1], pose[2]);
+  Eigen::Vector3f vel(velv[0], velv[1], velv[2]);
+  geometry_msgs::PoseStamped goal_pose = h->global_plan_.back();
+  Eigen::Vector3f goal(goal_pose.pose.position.x, goal_pose.pose.position.y, 0.0f);
+  LocalPlannerLimits limits = h->limits;
+  h->generator_.initialise(pos, vel, goal, &limits, h->vsamples_);
+  h->result_traj_.cost_ = -7;
+  std::vector<Trajectory> all_explored;
+  h->scored_sampling_planner_.findBestTrajectory(h->result_traj_, &all_explored);
+
+  // Recover per-sample bookkeeping: re-enumerate the samples exactly as the generator did, and walk all_explored
+  // (which holds only samples whose generateTrajectory succeeded, in order).
+  h->generator_.initialise(pos, vel, goal, &limits, h->vsamples_);
+  int n_samples = 0, k = 0, best_index = -1;
+  bool best_found = false;
+  while (h->generator_.hasMoreTrajectories()) {
+    Trajectory t;
+    bool ok = h->generator_.nextTrajectory(t);
+    double c = std::numeric_limits<double>::quiet_NaN();
+    if (ok) {
+      c = all_explored[k].cost_;
+      // the winner is the first sample whose reported cost equals the final best cost with identical velocities
+      if (!best_found && h->result_traj_.cost_ >= 0 && c == h->result_traj_.cost_ &&
+          all_explored[k].xv_ == h->result_traj_.xv_ && all_explored[k].yv_ == h->result_traj_.yv_ &&
+          all_explored[k].thetav_ == h->result_traj_.thetav_) {
+        best_index = n_samples;
+        best_found = true;
+      }
+      ++k;
+    }
+    if (all_costs && n_samples < all_capacity) all_costs[n_samples] = c;
+    ++n_samples;
+  }
+  h->oscillation_costs_.updateOscillationFlags(pos, &h->result_traj_, limits.min_trans_vel);
+
+  result->cost = h->result_traj_.cost_;
+  result->xv = h->result_traj_.xv_;
+  result->yv = h->result_traj_.yv_;
+  result->thetav = h->result_traj_.thetav_;
+  result->best_index = best_index;
+  result->n_samples = n_samples;
+  result->n_scored = int(all_explored.size());
+  result->n_points = int(h->result_traj_.getPointsSize());
+  if (best_points) {
+    for (unsigned i = 0; i < h->result_traj_.getPointsSize() && int(i) < points_capacity; ++i)
+      h->result_traj_.getPoint(i, best_points[3 * i], best_points[3 * i + 1], best_points[3 * i + 2]);
+  }
+  return h->result_traj_.cost_ >= 0 ? 1 : 0;
+}
+
+void navo_dwa_get_grid(void* hv, int which, double* out) {
+  DwaHandle* h = static_cast<DwaHandle*>(hv);
+  MapGridCostFunction* g[4] = {&h->path_costs_, &h->goal_costs_, &h->goal_front_costs_, &h->alignment_costs_};
+  unsigned sx = h->costmap.getSizeInCellsX(), sy = h->costmap.getSizeInCellsY();
+  for (unsigned y = 0; y < sy; ++y)
+    for (unsigned x = 0; x < sx; ++x) out[size_t(y) * sx + x] = g[which]->getCellCosts(x, y);
+}
+
+void navo_dwa_prepare_only(void* hv) {
+  DwaHandle* h = static_cast<DwaHandle*>(hv);
+  h->goal_front_costs_.prepare();
+  h->alignment_costs_.prepare();
+  h->path_costs_.prepare();
+  h->goal_costs_.prepare();
+}
+
+int navo_velocity_samples(double vmin, double vmax, int num_samples, double* out, int capacity) {
+  VelocityIterator it(vmin, vmax, num_samples);
+  int n = 0;
+  for (; !it.isFinished(); it++) {
+    if (n < capacity) out[n] = it.getVelocity();
+    ++n;
+  }
+  return n;
+}
+
+int navo_line_cells(int x0, int y0, int x1, int y1, int32_t* xy_out, int capacity) {
+  int n = 0;
+  for (LineIterator line(x0, y0, x1, y1); line.isValid(); line.advance()) {
+    if (n < capacity) {
+      xy_out[2 * n] = line.getX();
+      xy_out[2 * n + 1] = line.getY();
+    }
+    ++n;
+  }
+  return n;
+}
+
+void navo_mapgrid_bfs(const uint8_t* costs, uint32_t size_x, uint32_t size_y, const int32_t* seeds_xy, int n_seeds,
+                      int /*allow_unknown*/, double* dist_out) {
+  // as base_local_planner/test/utest.cpp:104-166 drives it
+  Costmap2D cm(size_x, size_y, 1.0, 0.0, 0.0, 0);
+  memcpy(cm.getCharMap(), costs, size_t(size_x) * size_y);
+  MapGrid mg(size_x, size_y);
+  mg.resetPathDist();
+  std::queue<MapCell*> q;
+  for (int i = 0; i < n_seeds; ++i) {
+    MapCell& c = mg.getCell(seeds_xy[2 * i], seeds_xy[2 * i + 1]);
+    c.target_dist = 0.0;
+    c.target_mark = true;
+    q.push(&c);
+  }
+  mg.computeTargetDistance(q, cm);
+  for (uint32_t y = 0; y < size_y; ++y)
+    for (uint32_t x = 0; x < size_x; ++x) dist_out[size_t(y) * size_x + x] = mg(x, y).target_dist;
+}
+
+}  // extern "C"
