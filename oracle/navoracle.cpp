@@ -1,0 +1,1128 @@
+// navoracle.cpp -- CPU restatement of the two hot paths (checker for the CUDA implementation).
+//
+// TEST INFRASTRUCTURE ONLY: used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs.  Nothing under navigation_b200/ links or loads this file.
+//
+// Written from scratch as plain single-threaded C++ following the reference's algorithms; every function cites the
+// reference file:line it follows.  It is pinned (tests/test_oracle_*.py) against
+//   * the reference's own known-answer tests (costmap_2d/test/inflation_tests.cpp, obstacle_tests.cpp,
+//     base_local_planner/test/{map_grid_test,utest,line_iterator_test,velocity_iterator_test}.cpp), and
+//   * oracle/_ref/libnavref.so -- the reference's unmodified sources compiled in place -- on seeded random inputs
+//     (bit-for-bit grids, costs and selections), with golden fixtures of those runs committed under tests/golden/.
+//
+// libstdc++'s std::priority_queue is kept for inflation on purpose: the reference's output depends on its heap tie
+// order, and the same container + push order reproduces it hash-for-hash.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <queue>
+#include <vector>
+
+#include "oracle_api.h"
+
+namespace {
+
+enum : uint8_t { kFree = 0, kInscribed = 253, kLethal = 254, kNoInfo = 255 };  // cost_values.h:42-45
+
+// ------------------------------------------------------------------ Costmap2D-shaped grid (costmap_2d.cpp)
+struct Grid {
+  unsigned sx = 0, sy = 0;
+  double res = 0, ox = 0, oy = 0;
+  uint8_t def = 0;
+  std::vector<uint8_t> c;
+
+  void resize(unsigned nx, unsigned ny, double r, double x, double y) {  // resizeMap :71-85
+    sx = nx; sy = ny; res = r; ox = x; oy = y;
+    c.assign(size_t(sx) * sy, def);
+  }
+  void reset_window(unsigned x0, unsigned y0, unsigned xn, unsigned yn) {  // resetMap :93-99
+    unsigned len = xn - x0;
+    for (unsigned y = y0 * sx + x0; y < yn * sx + x0; y += sx) memset(c.data() + y, def, len);
+  }
+  bool world_to_map(double wx, double wy, unsigned& mx, unsigned& my) const {  // worldToMap :208-220
+    if (wx < ox || wy < oy) return false;
+    mx = (int)((wx - ox) / res);
+    my = (int)((wy - oy) / res);
+    return mx < sx && my < sy;
+  }
+  void map_to_world(unsigned mx, unsigned my, double& wx, double& wy) const {  // mapToWorld :202-206
+    wx = ox + (mx + 0.5) * res;
+    wy = oy + (my + 0.5) * res;
+  }
+  void world_to_map_enforce(double wx, double wy, int& mx, int& my) const {  // worldToMapEnforceBounds :228-262
+    if (wx < ox) mx = 0;
+    else if (wx > res * (sx - 1) + ox) mx = sx - 1;
+    else mx = (int)((wx - ox) / res);
+    if (wy < oy) my = 0;
+    else if (wy > res * (sy - 1) + oy) my = sy - 1;
+    else my = (int)((wy - oy) / res);
+  }
+  unsigned cell_distance(double world_dist) const {  // cellDistance :181-185
+    return (unsigned)std::max(0.0, ceil(world_dist / res));
+  }
+  double size_m_x() const { return (sx - 1 + 0.5) * res; }  // getSizeInMetersX :440-443
+  double size_m_y() const { return (sy - 1 + 0.5) * res; }
+
+  void update_origin(double nox, double noy) {  // updateOrigin :264-313
+    int cell_ox = int((nox - ox) / res), cell_oy = int((noy - oy) / res);
+    double new_grid_ox = ox + cell_ox * res, new_grid_oy = oy + cell_oy * res;
+    int isx = sx, isy = sy;
+    int llx = std::min(std::max(cell_ox, 0), isx), lly = std::min(std::max(cell_oy, 0), isy);
+    int urx = std::min(std::max(cell_ox + isx, 0), isx), ury = std::min(std::max(cell_oy + isy, 0), isy);
+    unsigned w = urx - llx, h = ury - lly;
+    std::vector<uint8_t> keep(size_t(w) * h);
+    for (unsigned r = 0; r < h; ++r) memcpy(keep.data() + size_t(r) * w, c.data() + size_t(lly + r) * sx + llx, w);
+    std::fill(c.begin(), c.end(), def);
+    ox = new_grid_ox;
+    oy = new_grid_oy;
+    int start_x = llx - cell_ox, start_y = lly - cell_oy;
+    for (unsigned r = 0; r < h; ++r) memcpy(c.data() + size_t(start_y + r) * sx + start_x, keep.data() + size_t(r) * w, w);
+  }
+};
+
+// Costmap2D::raytraceLine + bresenham2D (costmap_2d.h:359-412): calls at(offset) for each visited cell.
+template <class F>
+void raytrace_line(unsigned size_x, F at, unsigned x0, unsigned y0, unsigned x1, unsigned y1,
+                   unsigned max_length = UINT32_MAX) {
+  int dx = x1 - x0, dy = y1 - y0;
+  unsigned adx = abs(dx), ady = abs(dy);
+  int off_dx = dx > 0 ? 1 : -1;
+  int off_dy = (dy > 0 ? 1 : -1) * int(size_x);
+  unsigned offset = y0 * size_x + x0;
+  double dist = hypot(dx, dy);
+  double scale = (dist == 0.0) ? 1.0 : std::min(1.0, max_length / dist);
+  unsigned abs_da, abs_db;
+  int off_a, off_b;
+  if (adx >= ady) { abs_da = adx; abs_db = ady; off_a = off_dx; off_b = off_dy; }
+  else { abs_da = ady; abs_db = adx; off_a = off_dy; off_b = off_dx; }
+  int err = abs_da / 2;
+  unsigned end = std::min((unsigned)(scale * abs_da), abs_da);
+  for (unsigned i = 0; i < end; ++i) {
+    at(offset);
+    offset += off_a;
+    err += abs_db;
+    if ((unsigned)err >= abs_da) {
+      offset += off_b;
+      err -= abs_da;
+    }
+  }
+  at(offset);
+}
+
+struct Cell { unsigned x, y; };
+
+// Costmap2D::convexFillCells + polygonOutlineCells (costmap_2d.cpp:344-428), quirks included.
+void convex_fill_cells(unsigned size_x, const std::vector<Cell>& poly, std::vector<Cell>& cells) {
+  if (poly.size() < 3) return;
+  auto gather = [&](unsigned off) { cells.push_back(Cell{off % size_x, off / size_x}); };
+  for (size_t i = 0; i + 1 < poly.size(); ++i) raytrace_line(size_x, gather, poly[i].x, poly[i].y, poly[i + 1].x, poly[i + 1].y);
+  raytrace_line(size_x, gather, poly.back().x, poly.back().y, poly[0].x, poly[0].y);
+  // the reference's "bubble sort by x" (stable, back-stepping)
+  size_t i = 0;
+  while (i < cells.size() - 1) {
+    if (cells[i].x > cells[i + 1].x) {
+      std::swap(cells[i], cells[i + 1]);
+      if (i > 0) --i;
+    } else {
+      ++i;
+    }
+  }
+  i = 0;
+  Cell min_pt, max_pt;
+  unsigned min_x = cells[0].x, max_x = cells[cells.size() - 1].x;
+  for (unsigned x = min_x; x <= max_x; ++x) {
+    if (i >= cells.size() - 1) break;
+    if (cells[i].y < cells[i + 1].y) { min_pt = cells[i]; max_pt = cells[i + 1]; }
+    else { min_pt = cells[i + 1]; max_pt = cells[i]; }
+    i += 2;
+    while (i < cells.size() && cells[i].x == x) {
+      if (cells[i].y < min_pt.y) min_pt = cells[i];
+      else if (cells[i].y > max_pt.y) max_pt = cells[i];
+      ++i;
+    }
+    for (unsigned y = min_pt.y; y < max_pt.y; ++y) cells.push_back(Cell{x, y});
+  }
+}
+
+// costmap_math.h distance / costmap_math.cpp:32-63 distanceToLine
+double dist2d(double x0, double y0, double x1, double y1) { return hypot(x1 - x0, y1 - y0); }
+double distance_to_line(double pX, double pY, double x0, double y0, double x1, double y1) {
+  double A = pX - x0, B = pY - y0, C = x1 - x0, D = y1 - y0;
+  double dot = A * C + B * D, len_sq = C * C + D * D, param = dot / len_sq;
+  double xx, yy;
+  if (param < 0) { xx = x0; yy = y0; }
+  else if (param > 1) { xx = x1; yy = y1; }
+  else { xx = x0 + param * C; yy = y0 + param * D; }
+  return dist2d(pX, pY, xx, yy);
+}
+struct Pt { double x, y; };
+void min_max_distances(const std::vector<Pt>& fp, double& mn, double& mx) {  // footprint.cpp:41-67
+  mn = std::numeric_limits<double>::max();
+  mx = 0.0;
+  if (fp.size() <= 2) return;
+  for (size_t i = 0; i < fp.size(); ++i) {
+    const Pt& a = fp[i];
+    const Pt& b = fp[(i + 1) % fp.size()];
+    double vd = dist2d(0, 0, a.x, a.y), ed = distance_to_line(0, 0, a.x, a.y, b.x, b.y);
+    mn = std::min(mn, std::min(vd, ed));
+    mx = std::max(mx, std::max(vd, ed));
+  }
+}
+void transform_footprint(double x, double y, double th, const std::vector<Pt>& spec, std::vector<Pt>& out) {  // :106-120
+  out.clear();
+  double c = cos(th), s = sin(th);
+  for (const Pt& p : spec) out.push_back(Pt{x + (p.x * c - p.y * s), y + (p.x * s + p.y * c)});
+}
+
+// ------------------------------------------------------------------ layers
+struct Bounds { double minx, miny, maxx, maxy; };
+void touch(double x, double y, Bounds& b) {  // costmap_layer.cpp:8-14
+  b.minx = std::min(x, b.minx); b.miny = std::min(y, b.miny);
+  b.maxx = std::max(x, b.maxx); b.maxy = std::max(y, b.maxy);
+}
+
+// the four merge policies, costmap_layer.cpp:62-157
+void merge(int policy, const Grid& layer, Grid& master, int min_i, int min_j, int max_i, int max_j) {
+  unsigned span = master.sx;
+  for (int j = min_j; j < max_j; j++) {
+    unsigned it = j * span + min_i;
+    for (int i = min_i; i < max_i; i++, it++) {
+      uint8_t v = layer.c[it];
+      uint8_t& m = master.c[it];
+      switch (policy) {
+        case NAVO_TRUE_OVERWRITE: m = v; break;
+        case NAVO_OVERWRITE: if (v != kNoInfo) m = v; break;
+        case NAVO_MAX:
+          if (v == kNoInfo) break;
+          if (m == kNoInfo || m < v) m = v;
+          break;
+        case NAVO_ADDITION:
+          if (v == kNoInfo) break;
+          if (m == kNoInfo) m = v;
+          else {
+            int sum = m + v;
+            m = sum >= kInscribed ? kInscribed - 1 : sum;
+          }
+          break;
+        default: break;
+      }
+    }
+  }
+}
+
+struct Obs {
+  double ox, oy, oz, obstacle_range, raytrace_range;
+  std::vector<float> xyz;
+  bool marking, clearing;
+};
+
+struct Costmap;
+
+struct LayerBase {
+  bool enabled = true;
+  virtual ~LayerBase() {}
+  virtual void match_size(Costmap&) {}
+  virtual void update_bounds(Costmap&, double, double, double, Bounds&) {}
+  virtual void update_costs(Costmap&, int, int, int, int) {}
+  virtual void on_footprint_changed(Costmap&) {}
+  virtual Grid* grid() { return nullptr; }
+};
+
+struct Costmap {
+  Grid master;
+  bool rolling = false, track_unknown = false;
+  std::vector<std::unique_ptr<LayerBase>> layers;
+  std::vector<Pt> footprint;
+  double inscribed = 0, circumscribed = 0;
+  int bx0 = 0, bxn = 0, by0 = 0, byn = 0;
+
+  void update_map(double rx, double ry, double ryaw) {  // layered_costmap.cpp:79-150
+    if (rolling) master.update_origin(rx - master.size_m_x() / 2, ry - master.size_m_y() / 2);
+    if (layers.empty()) return;
+    Bounds b{1e30, 1e30, -1e30, -1e30};
+    for (auto& l : layers) l->update_bounds(*this, rx, ry, ryaw, b);
+    int x0, xn, y0, yn;
+    master.world_to_map_enforce(b.minx, b.miny, x0, y0);
+    master.world_to_map_enforce(b.maxx, b.maxy, xn, yn);
+    x0 = std::max(0, x0);
+    xn = std::min(int(master.sx), xn + 1);
+    y0 = std::max(0, y0);
+    yn = std::min(int(master.sy), yn + 1);
+    bx0 = x0; bxn = xn; by0 = y0; byn = yn;
+    if (xn < x0 || yn < y0) return;
+    master.reset_window(x0, y0, xn, yn);
+    for (auto& l : layers) l->update_costs(*this, x0, y0, xn, yn);
+  }
+};
+
+struct CostLayerBase : LayerBase {  // CostmapLayer (costmap_layer.h:48-151)
+  Grid g;
+  void match_size(Costmap& cm) override {
+    g.def = cm.track_unknown ? kNoInfo : kFree;
+    g.resize(cm.master.sx, cm.master.sy, cm.master.res, cm.master.ox, cm.master.oy);
+  }
+  Grid* grid() override { return &g; }
+};
+
+struct GridLayer : CostLayerBase {  // StaticLayer non-rolling branch, static_layer.cpp:263-299
+  int policy;
+  unsigned x = 0, y = 0, w = 0, h = 0;
+  bool updated = false;
+  explicit GridLayer(int p) : policy(p) {}
+  void update_bounds(Costmap& cm, double, double, double, Bounds& b) override {
+    if (!cm.rolling && !updated) return;
+    double wx, wy;
+    g.map_to_world(x, y, wx, wy);
+    b.minx = std::min(wx, b.minx);
+    b.miny = std::min(wy, b.miny);
+    g.map_to_world(x + w, y + h, wx, wy);
+    b.maxx = std::max(wx, b.maxx);
+    b.maxy = std::max(wy, b.maxy);
+    updated = false;
+  }
+  void update_costs(Costmap& cm, int a, int b_, int c_, int d) override {
+    if (!enabled) return;
+    merge(policy, g, cm.master, a, b_, c_, d);
+  }
+};
+
+struct ObstacleLayer : CostLayerBase {  // obstacle_layer.cpp:340-448, 498-610
+  int combination_method;
+  bool footprint_clearing;
+  double max_obstacle_height;
+  std::vector<Obs> obs;
+  std::vector<Pt> transformed_footprint;
+  ObstacleLayer(int cmeth, bool fc, double mh) : combination_method(cmeth), footprint_clearing(fc), max_obstacle_height(mh) {}
+
+  void raytrace_freespace(const Obs& o, Bounds& b) {  // :498-576
+    double ox = o.ox, oy = o.oy;
+    unsigned x0, y0;
+    if (!g.world_to_map(ox, oy, x0, y0)) return;
+    double origin_x = g.ox, origin_y = g.oy;
+    double map_end_x = origin_x + g.sx * g.res, map_end_y = origin_y + g.sy * g.res;
+    touch(ox, oy, b);
+    for (size_t i = 0; i < o.xyz.size() / 3; ++i) {
+      double wx = o.xyz[3 * i], wy = o.xyz[3 * i + 1];
+      double a = wx - ox, bb = wy - oy;
+      if (wx < origin_x) { double t = (origin_x - ox) / a; wx = origin_x; wy = oy + bb * t; }
+      if (wy < origin_y) { double t = (origin_y - oy) / bb; wx = ox + a * t; wy = origin_y; }
+      if (wx > map_end_x) { double t = (map_end_x - ox) / a; wx = map_end_x - .001; wy = oy + bb * t; }
+      if (wy > map_end_y) { double t = (map_end_y - oy) / bb; wx = ox + a * t; wy = map_end_y - .001; }
+      unsigned x1, y1;
+      if (!g.world_to_map(wx, wy, x1, y1)) continue;
+      unsigned cell_range = g.cell_distance(o.raytrace_range);
+      uint8_t* cells = g.c.data();
+      raytrace_line(g.sx, [cells](unsigned off) { cells[off] = kFree; }, x0, y0, x1, y1, cell_range);
+      double dx = wx - ox, dy = wy - oy;  // updateRaytraceBounds :602-610
+      double full = hypot(dx, dy);
+      double scale = std::min(1.0, o.raytrace_range / full);
+      touch(ox + dx * scale, oy + dy * scale, b);
+    }
+  }
+
+  void update_bounds(Costmap& cm, double rx, double ry, double ryaw, Bounds& b) override {  // :340-413
+    if (cm.rolling) g.update_origin(rx - g.size_m_x() / 2, ry - g.size_m_y() / 2);
+    if (!enabled) return;
+    for (const Obs& o : obs)
+      if (o.clearing) raytrace_freespace(o, b);
+    for (const Obs& o : obs) {
+      if (!o.marking) continue;
+      double sq_range = o.obstacle_range * o.obstacle_range;
+      for (size_t i = 0; i < o.xyz.size() / 3; ++i) {
+        double px = o.xyz[3 * i], py = o.xyz[3 * i + 1], pz = o.xyz[3 * i + 2];
+        if (pz > max_obstacle_height) continue;
+        double sq = (px - o.ox) * (px - o.ox) + (py - o.oy) * (py - o.oy) + (pz - o.oz) * (pz - o.oz);
+        if (sq >= sq_range) continue;
+        unsigned mx, my;
+        if (!g.world_to_map(px, py, mx, my)) continue;
+        g.c[size_t(my) * g.sx + mx] = kLethal;
+        touch(px, py, b);
+      }
+    }
+    if (!footprint_clearing) return;  // updateFootprint :415-425
+    transform_footprint(rx, ry, ryaw, cm.footprint, transformed_footprint);
+    for (const Pt& p : transformed_footprint) touch(p.x, p.y, b);
+  }
+
+  void update_costs(Costmap& cm, int a, int b_, int c_, int d) override {  // :427-448
+    if (!enabled) return;
+    if (footprint_clearing) {  // setConvexPolygonCost, costmap_2d.cpp:315-342
+      std::vector<Cell> poly, cells;
+      bool ok = true;
+      for (const Pt& p : transformed_footprint) {
+        Cell loc;
+        if (!g.world_to_map(p.x, p.y, loc.x, loc.y)) { ok = false; break; }
+        poly.push_back(loc);
+      }
+      if (ok) {
+        convex_fill_cells(g.sx, poly, cells);
+        for (const Cell& cc : cells) g.c[size_t(cc.y) * g.sx + cc.x] = kFree;
+      }
+    }
+    if (combination_method == 0) merge(NAVO_OVERWRITE, g, cm.master, a, b_, c_, d);
+    else if (combination_method == 1) merge(NAVO_MAX, g, cm.master, a, b_, c_, d);
+  }
+};
+
+struct QCell {  // CellData, inflation_layer.h:55-85
+  double distance;
+  unsigned index, x, y, sx, sy;
+};
+struct QLess {
+  bool operator()(const QCell& a, const QCell& b) const { return a.distance > b.distance; }
+};
+
+struct InflationLayer : LayerBase {  // inflation_layer.cpp
+  double radius = 0.55, weight = 10.0, inscribed = 0, res = 0;
+  unsigned R = 0;
+  bool need_reinflation = false;
+  double lminx = -std::numeric_limits<float>::max(), lminy = -std::numeric_limits<float>::max();
+  double lmaxx = std::numeric_limits<float>::max(), lmaxy = std::numeric_limits<float>::max();
+  std::vector<uint8_t> costs;  // (R+2)^2
+  std::vector<double> dists;
+  std::vector<uint8_t> seen;
+
+  uint8_t compute_cost(double d) const {  // inflation_layer.h:114-129
+    if (d == 0) return kLethal;
+    if (d * res <= inscribed) return kInscribed;
+    double factor = exp(-1.0 * weight * (d * res - inscribed));
+    return (uint8_t)((kInscribed - 1) * factor);
+  }
+  void compute_caches() {  // :295-328
+    if (R == 0) return;
+    unsigned n = R + 2;
+    costs.assign(n * n, 0);
+    dists.assign(n * n, 0);
+    for (unsigned i = 0; i < n; ++i)
+      for (unsigned j = 0; j < n; ++j) {
+        dists[i * n + j] = hypot(i, j);
+        costs[i * n + j] = compute_cost(dists[i * n + j]);
+      }
+  }
+  void set_params(Costmap& cm, double r, double w) {  // :356-370
+    if (weight != w || radius != r) {
+      radius = r;
+      R = cm.master.cell_distance(radius);
+      weight = w;
+      need_reinflation = true;
+      compute_caches();
+    }
+  }
+  void match_size(Costmap& cm) override {  // :110-123
+    res = cm.master.res;
+    R = cm.master.cell_distance(radius);
+    compute_caches();
+    seen.assign(size_t(cm.master.sx) * cm.master.sy, 0);
+  }
+  void on_footprint_changed(Costmap& cm) override {  // :160-170
+    inscribed = cm.inscribed;
+    R = cm.master.cell_distance(radius);
+    compute_caches();
+    need_reinflation = true;
+  }
+  void update_bounds(Costmap&, double, double, double, Bounds& b) override {  // :125-158
+    if (need_reinflation) {
+      lminx = b.minx; lminy = b.miny; lmaxx = b.maxx; lmaxy = b.maxy;
+      b.minx = -std::numeric_limits<float>::max();
+      b.miny = -std::numeric_limits<float>::max();
+      b.maxx = std::numeric_limits<float>::max();
+      b.maxy = std::numeric_limits<float>::max();
+      need_reinflation = false;
+    } else {
+      double tx0 = lminx, ty0 = lminy, tx1 = lmaxx, ty1 = lmaxy;
+      lminx = b.minx; lminy = b.miny; lmaxx = b.maxx; lmaxy = b.maxy;
+      b.minx = std::min(tx0, b.minx) - radius;
+      b.miny = std::min(ty0, b.miny) - radius;
+      b.maxx = std::max(tx1, b.maxx) + radius;
+      b.maxy = std::max(ty1, b.maxy) + radius;
+    }
+  }
+  void update_costs(Costmap& cm, int min_i, int min_j, int max_i, int max_j) override {  // :172-266
+    if (!enabled) return;
+    Grid& m = cm.master;
+    unsigned size_x = m.sx, size_y = m.sy;
+    if (seen.size() != size_t(size_x) * size_y) seen.resize(size_t(size_x) * size_y);
+    std::fill(seen.begin(), seen.end(), 0);
+    min_i -= R; min_j -= R; max_i += R; max_j += R;
+    min_i = std::max(0, min_i);
+    min_j = std::max(0, min_j);
+    max_i = std::min(int(size_x), max_i);
+    max_j = std::min(int(size_y), max_j);
+    std::priority_queue<QCell, std::vector<QCell>, QLess> q;
+    const unsigned n = R + 2;
+    auto enqueue = [&](unsigned index, unsigned mx, unsigned my, unsigned sx, unsigned sy) {  // :277-293
+      if (seen[index]) return;
+      unsigned dx = abs(int(mx) - int(sx)), dy = abs(int(my) - int(sy));
+      double d = dists[dx * n + dy];
+      if (d > R) return;
+      q.push(QCell{d, index, mx, my, sx, sy});
+    };
+    for (int j = min_j; j < max_j; j++)
+      for (int i = min_i; i < max_i; i++) {
+        unsigned index = j * size_x + i;
+        if (m.c[index] == kLethal) enqueue(index, i, j, i, j);
+      }
+    while (!q.empty()) {
+      QCell cur = q.top();
+      q.pop();
+      if (seen[cur.index]) continue;
+      seen[cur.index] = 1;
+      unsigned dx = abs(int(cur.x) - int(cur.sx)), dy = abs(int(cur.y) - int(cur.sy));
+      uint8_t cost = costs[dx * n + dy];
+      uint8_t old = m.c[cur.index];
+      if (old == kNoInfo && cost >= kInscribed) m.c[cur.index] = cost;
+      else m.c[cur.index] = std::max(old, cost);
+      if (cur.x > 0) enqueue(cur.index - 1, cur.x - 1, cur.y, cur.sx, cur.sy);
+      if (cur.y > 0) enqueue(cur.index - size_x, cur.x, cur.y - 1, cur.sx, cur.sy);
+      if (cur.x < size_x - 1) enqueue(cur.index + 1, cur.x + 1, cur.y, cur.sx, cur.sy);
+      if (cur.y < size_y - 1) enqueue(cur.index + size_x, cur.x, cur.y + 1, cur.sx, cur.sy);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ Path B
+struct V3f { float v[3]; float& operator[](int i) { return v[i]; } const float& operator[](int i) const { return v[i]; } };
+
+std::vector<double> velocity_samples(double mn, double mx, int n) {  // velocity_iterator.h:49-74
+  std::vector<double> s;
+  if (mn == mx) { s.push_back(mn); return s; }
+  n = std::max(2, n);
+  double step = (mx - mn) / double(std::max(1, n - 1));
+  double cur, next = mn;
+  for (int j = 0; j < n - 1; ++j) {
+    cur = next;
+    next += step;
+    s.push_back(cur);
+    if (cur < 0 && next > 0) s.push_back(0.0);
+  }
+  s.push_back(mx);
+  return s;
+}
+
+struct Traj {
+  double xv = 0, yv = 0, thv = 0, cost = -1;
+  std::vector<double> x, y, th;
+};
+
+struct LineIt {  // line_iterator.h:38-139
+  int x, y, dx, dy, cur = 0, xinc1, xinc2, yinc1, yinc2, den, num, numadd, numpixels;
+  LineIt(int x0, int y0, int x1, int y1) : x(x0), y(y0), dx(abs(x1 - x0)), dy(abs(y1 - y0)) {
+    xinc1 = xinc2 = (x1 >= x0) ? 1 : -1;
+    yinc1 = yinc2 = (y1 >= y0) ? 1 : -1;
+    if (dx >= dy) { xinc1 = 0; yinc2 = 0; den = dx; num = dx / 2; numadd = dy; numpixels = dx; }
+    else { xinc2 = 0; yinc1 = 0; den = dy; num = dy / 2; numadd = dx; numpixels = dy; }
+  }
+  bool valid() const { return cur <= numpixels; }
+  void advance() {
+    num += numadd;
+    if (num >= den) { num -= den; x += xinc1; y += yinc1; }
+    x += xinc2;
+    y += yinc2;
+    cur++;
+  }
+};
+
+// MapGrid::computeTargetDistance (map_grid.cpp:258-310) over explicit seeds; dist pre-filled with "unreachable".
+void mapgrid_bfs(const Grid& cm, bool allow_unknown, std::vector<double>& dist, std::vector<uint8_t>& mark,
+                 std::queue<unsigned>& q) {
+  const unsigned sx = cm.sx, sy = cm.sy;
+  const double obstacle = double(size_t(sx) * sy);
+  auto visit = [&](unsigned cur, unsigned chk) {
+    if (mark[chk]) return;
+    mark[chk] = 1;
+    uint8_t cost = cm.c[chk];  // updatePathCell :103-123
+    if (cost == kLethal || cost == kInscribed || (cost == kNoInfo && !allow_unknown)) {
+      dist[chk] = obstacle;
+      return;
+    }
+    double nd = dist[cur] + 1;
+    if (nd < dist[chk]) dist[chk] = nd;
+    q.push(chk);
+  };
+  while (!q.empty()) {
+    unsigned cur = q.front();
+    q.pop();
+    unsigned cx = cur % sx, cy = cur / sx;
+    if (cx > 0) visit(cur, cur - 1);
+    if (cx < sx - 1) visit(cur, cur + 1);
+    if (cy > 0) visit(cur, cur - sx);
+    if (cy < sy - 1) visit(cur, cur + sx);
+  }
+}
+
+void adjust_plan_resolution(const std::vector<Pt>& in, std::vector<Pt>& out, double resolution) {  // map_grid.cpp:135-171
+  if (in.empty()) return;
+  double last_x = in[0].x, last_y = in[0].y;
+  out.push_back(in[0]);
+  double min_sq = resolution * resolution * 4;
+  for (size_t i = 1; i < in.size(); ++i) {
+    double lx = in[i].x, ly = in[i].y;
+    double sq = (lx - last_x) * (lx - last_x) + (ly - last_y) * (ly - last_y);
+    if (sq > min_sq) {
+      int steps = ((sqrt(sq) - sqrt(min_sq)) / resolution) - 1;
+      double ddx = (lx - last_x) / steps, ddy = (ly - last_y) / steps;
+      for (int j = 1; j < steps; ++j) out.push_back(Pt{last_x + j * ddx, last_y + j * ddy});
+    }
+    out.push_back(in[i]);
+    last_x = lx;
+    last_y = ly;
+  }
+}
+
+struct MapGridCritic {  // MapGridCostFunction + MapGrid
+  bool local_goal = false, stop_on_failure = true;
+  double xshift = 0, scale = 1;
+  std::vector<Pt> target;
+  std::vector<double> dist;
+
+  void prepare(const Grid& cm, bool allow_unknown) {  // map_grid_cost_function.cpp:59-68, map_grid.cpp:127-254
+    size_t n = size_t(cm.sx) * cm.sy;
+    dist.assign(n, double(n + 1));
+    std::vector<uint8_t> mark(n, 0);
+    std::queue<unsigned> q;
+    std::vector<Pt> adj;
+    adjust_plan_resolution(target, adj, cm.res);
+    bool started = false;
+    int gx = -1, gy = -1;
+    for (size_t i = 0; i < adj.size(); ++i) {
+      unsigned mx, my;
+      if (cm.world_to_map(adj[i].x, adj[i].y, mx, my) && cm.c[size_t(my) * cm.sx + mx] != kNoInfo) {
+        if (local_goal) { gx = mx; gy = my; }
+        else {
+          unsigned id = my * cm.sx + mx;
+          dist[id] = 0.0;
+          mark[id] = 1;
+          q.push(id);
+        }
+        started = true;
+      } else if (started) {
+        break;
+      }
+    }
+    if (!started) return;
+    if (local_goal && gx >= 0 && gy >= 0) {
+      unsigned id = gy * cm.sx + gx;
+      dist[id] = 0.0;
+      mark[id] = 1;
+      q.push(id);
+    }
+    mapgrid_bfs(cm, allow_unknown, dist, mark, q);
+  }
+
+  double score(const Grid& cm, const Traj& t) const {  // map_grid_cost_function.cpp:75-129 (aggregation Last)
+    double cost = 0.0;
+    const double n = double(dist.size());
+    for (size_t i = 0; i < t.x.size(); ++i) {
+      double px = t.x[i], py = t.y[i], pth = t.th[i];
+      if (xshift != 0.0) {
+        px = px + xshift * cos(pth);
+        py = py + xshift * sin(pth);
+      }
+      unsigned cx, cy;
+      if (!cm.world_to_map(px, py, cx, cy)) return -4.0;
+      double d = dist[size_t(cy) * cm.sx + cx];
+      if (stop_on_failure) {
+        if (d == n) return -3.0;
+        if (d == n + 1) return -2.0;
+      }
+      cost = d;
+    }
+    return cost;
+  }
+};
+
+struct Dwa {
+  navo_dwa_config cfg;
+  Grid cm;
+  std::vector<Pt> plan;
+  MapGridCritic path, goal, goal_front, alignment;
+  double obstacle_scale = 0;
+  // oscillation state (oscillation_cost_function.h:78-83)
+  bool strafe_pos_only = false, strafe_neg_only = false, strafing_pos = false, strafing_neg = false;
+  bool rot_pos_only = false, rot_neg_only = false, rotating_pos = false, rotating_neg = false;
+  bool forward_pos_only = false, forward_neg_only = false, forward_pos = false, forward_neg = false;
+  V3f prev_stationary{{0, 0, 0}};
+  std::vector<Pt> footprint;
+  Traj result;
+
+  void reconfigure() {  // dwa_planner.cpp:52-112, ctor :116-182
+    double r = cm.res;
+    path.scale = alignment.scale = r * cfg.path_distance_bias * 0.5;
+    goal.scale = goal_front.scale = r * cfg.goal_distance_bias * 0.5;
+    obstacle_scale = r * cfg.occdist_scale;
+    goal.local_goal = goal_front.local_goal = true;
+    goal_front.stop_on_failure = alignment.stop_on_failure = false;
+    goal_front.xshift = alignment.xshift = cfg.forward_point_distance;
+  }
+  void reset_osc() {  // oscillation_cost_function.cpp:84-99
+    strafe_pos_only = strafe_neg_only = strafing_pos = strafing_neg = false;
+    rot_pos_only = rot_neg_only = rotating_pos = rotating_neg = false;
+    forward_pos_only = forward_neg_only = forward_pos = forward_neg = false;
+  }
+  double osc_score(const Traj& t) const {  // :166-176
+    if ((forward_pos_only && t.xv < 0.0) || (forward_neg_only && t.xv > 0.0) || (strafe_pos_only && t.yv < 0.0) ||
+        (strafe_neg_only && t.yv > 0.0) || (rot_pos_only && t.thv < 0.0) || (rot_neg_only && t.thv > 0.0))
+      return -5.0;
+    return 0.0;
+  }
+  bool set_osc_flags(const Traj& t, double min_vel_trans) {  // :101-164
+    bool flag_set = false;
+    if (t.xv < 0.0) { if (forward_pos) { forward_neg_only = true; flag_set = true; } forward_pos = false; forward_neg = true; }
+    if (t.xv > 0.0) { if (forward_neg) { forward_pos_only = true; flag_set = true; } forward_neg = false; forward_pos = true; }
+    if (fabs(t.xv) <= min_vel_trans) {
+      if (t.yv < 0) { if (strafing_pos) { strafe_neg_only = true; flag_set = true; } strafing_pos = false; strafing_neg = true; }
+      if (t.yv > 0) { if (strafing_neg) { strafe_pos_only = true; flag_set = true; } strafing_neg = false; strafing_pos = true; }
+      if (t.thv < 0) { if (rotating_pos) { rot_neg_only = true; flag_set = true; } rotating_pos = false; rotating_neg = true; }
+      if (t.thv > 0) { if (rotating_neg) { rot_pos_only = true; flag_set = true; } rotating_neg = false; rotating_pos = true; }
+    }
+    return flag_set;
+  }
+  void update_osc_flags(const V3f& pos, const Traj& t, double min_vel_trans) {  // :56-82
+    if (t.cost < 0) return;
+    if (set_osc_flags(t, min_vel_trans)) prev_stationary = pos;
+    if (forward_pos_only || forward_neg_only || strafe_pos_only || strafe_neg_only || rot_pos_only || rot_neg_only) {
+      double xd = pos[0] - prev_stationary[0], yd = pos[1] - prev_stationary[1];
+      double sq = xd * xd + yd * yd;
+      double thd = pos[2] - prev_stationary[2];
+      if (sq > cfg.oscillation_reset_dist * cfg.oscillation_reset_dist || fabs(thd) > cfg.oscillation_reset_angle) reset_osc();
+    }
+  }
+
+  // SimpleTrajectoryGenerator::initialise, simple_trajectory_generator.cpp:60-135
+  void enumerate_samples(const V3f& pos, const V3f& vel, const V3f& goal, std::vector<V3f>& out) const {
+    double max_vel_th = cfg.max_rot_vel, min_vel_th = -1.0 * max_vel_th;
+    V3f acc{{float(cfg.acc_lim_x), float(cfg.acc_lim_y), float(cfg.acc_lim_theta)}};
+    double min_vel_x = cfg.min_vel_x, max_vel_x = cfg.max_vel_x, min_vel_y = cfg.min_vel_y, max_vel_y = cfg.max_vel_y;
+    int nx = std::max(1, cfg.vx_samples), ny = std::max(1, cfg.vy_samples), nth = std::max(1, cfg.vth_samples);
+    V3f mx{{0, 0, 0}}, mn{{0, 0, 0}};
+    if (!cfg.use_dwa) {
+      double dist = hypot(goal[0] - pos[0], goal[1] - pos[1]);
+      max_vel_x = std::max(std::min(max_vel_x, dist / cfg.sim_time), min_vel_x);
+      max_vel_y = std::max(std::min(max_vel_y, dist / cfg.sim_time), min_vel_y);
+      mx[0] = std::min(max_vel_x, vel[0] + acc[0] * cfg.sim_time);
+      mx[1] = std::min(max_vel_y, vel[1] + acc[1] * cfg.sim_time);
+      mx[2] = std::min(max_vel_th, vel[2] + acc[2] * cfg.sim_time);
+      mn[0] = std::max(min_vel_x, vel[0] - acc[0] * cfg.sim_time);
+      mn[1] = std::max(min_vel_y, vel[1] - acc[1] * cfg.sim_time);
+      mn[2] = std::max(min_vel_th, vel[2] - acc[2] * cfg.sim_time);
+    } else {
+      mx[0] = std::min(max_vel_x, vel[0] + acc[0] * cfg.sim_period);
+      mx[1] = std::min(max_vel_y, vel[1] + acc[1] * cfg.sim_period);
+      mx[2] = std::min(max_vel_th, vel[2] + acc[2] * cfg.sim_period);
+      mn[0] = std::max(min_vel_x, vel[0] - acc[0] * cfg.sim_period);
+      mn[1] = std::max(min_vel_y, vel[1] - acc[1] * cfg.sim_period);
+      mn[2] = std::max(min_vel_th, vel[2] - acc[2] * cfg.sim_period);
+    }
+    std::vector<double> xs = velocity_samples(mn[0], mx[0], nx), ys = velocity_samples(mn[1], mx[1], ny),
+                        ths = velocity_samples(mn[2], mx[2], nth);
+    for (double a : xs)
+      for (double b : ys)
+        for (double c : ths) out.push_back(V3f{{float(a), float(b), float(c)}});
+  }
+
+  // generateTrajectory, simple_trajectory_generator.cpp:180-251 (+ computeNewPositions/Velocities :253-276)
+  bool generate(V3f pos, const V3f& vel, const V3f& s, Traj& t) const {
+    double vmag = hypot(s[0], s[1]);
+    const double eps = 1e-4;
+    t.cost = -1.0;
+    t.x.clear(); t.y.clear(); t.th.clear();
+    if ((cfg.min_trans_vel >= 0 && vmag + eps < cfg.min_trans_vel) && (cfg.min_rot_vel >= 0 && fabs(s[2]) + eps < cfg.min_rot_vel))
+      return false;
+    if (cfg.max_trans_vel >= 0 && vmag - eps > cfg.max_trans_vel) return false;
+    double sim_time_distance = vmag * cfg.sim_time;
+    double sim_time_angle = fabs(s[2]) * cfg.sim_time;
+    int num_steps = ceil(std::max(sim_time_distance / cfg.sim_granularity, sim_time_angle / cfg.angular_sim_granularity));
+    double dt = cfg.sim_time / num_steps;
+    V3f acc{{float(cfg.acc_lim_x), float(cfg.acc_lim_y), float(cfg.acc_lim_theta)}};
+    auto new_vel = [&](const V3f& v) {
+      V3f nv{{0, 0, 0}};
+      for (int i = 0; i < 3; ++i) {
+        if (v[i] < s[i]) nv[i] = std::min(double(s[i]), v[i] + acc[i] * dt);
+        else nv[i] = std::max(double(s[i]), v[i] - acc[i] * dt);
+      }
+      return nv;
+    };
+    V3f loop_vel;
+    const bool continued = !cfg.use_dwa;
+    if (continued) loop_vel = new_vel(vel);
+    else loop_vel = s;
+    t.xv = loop_vel[0]; t.yv = loop_vel[1]; t.thv = loop_vel[2];
+    for (int i = 0; i < num_steps; ++i) {
+      t.x.push_back(pos[0]); t.y.push_back(pos[1]); t.th.push_back(pos[2]);
+      if (continued) loop_vel = new_vel(loop_vel);
+      V3f np;
+      np[0] = pos[0] + (loop_vel[0] * cos(double(pos[2])) + loop_vel[1] * cos(M_PI_2 + pos[2])) * dt;
+      np[1] = pos[1] + (loop_vel[0] * sin(double(pos[2])) + loop_vel[1] * sin(M_PI_2 + pos[2])) * dt;
+      np[2] = pos[2] + loop_vel[2] * dt;
+      pos = np;
+    }
+    return num_steps > 0;
+  }
+
+  // CostmapModel::pointCost / lineCost / footprintCost (costmap_model.cpp:50-142) + WorldModel wrapper (world_model.h:65-86)
+  double footprint_cost(double x, double y, double th) const {
+    const bool allow_unknown = cfg.allow_unknown != 0;
+    double c = cos(th), s = sin(th);
+    unsigned cx, cy;
+    if (!cm.world_to_map(x, y, cx, cy)) return -1.0;
+    if (footprint.size() < 3) {
+      uint8_t cost = cm.c[size_t(cy) * cm.sx + cx];
+      if (cost == kLethal || cost == kInscribed || (cost == kNoInfo && !allow_unknown)) return -1.0;
+      return cost;
+    }
+    double fcost = 0.0;
+    const size_t n = footprint.size();
+    for (size_t i = 0; i < n; ++i) {
+      const Pt& a = footprint[i];
+      const Pt& b = footprint[(i + 1) % n];
+      double ax = x + (a.x * c - a.y * s), ay = y + (a.x * s + a.y * c);
+      double bx = x + (b.x * c - b.y * s), by = y + (b.x * s + b.y * c);
+      unsigned x0, y0, x1, y1;
+      if (!cm.world_to_map(ax, ay, x0, y0)) return -1.0;
+      if (!cm.world_to_map(bx, by, x1, y1)) return -1.0;
+      double line_cost = 0.0;
+      for (LineIt l(x0, y0, x1, y1); l.valid(); l.advance()) {
+        uint8_t cost = cm.c[size_t(l.y) * cm.sx + l.x];
+        if (cost == kLethal || (cost == kNoInfo && !allow_unknown)) return -1.0;
+        if (line_cost < cost) line_cost = cost;
+      }
+      fcost = std::max(line_cost, fcost);
+    }
+    return fcost;
+  }
+  double obstacle_score(const Traj& t) const {  // obstacle_cost_function.cpp:74-142
+    double cost = 0;
+    if (footprint.empty()) return -9;
+    for (size_t i = 0; i < t.x.size(); ++i) {
+      double f = footprint_cost(t.x[i], t.y[i], t.th[i]);
+      if (f < 0) return -6.0;
+      unsigned cx, cy;
+      if (!cm.world_to_map(t.x[i], t.y[i], cx, cy)) return -7.0;
+      double occ = std::max(std::max(0.0, f), double(cm.c[size_t(cy) * cm.sx + cx]));
+      if (cfg.sum_scores) cost += occ;
+      else cost = occ;
+    }
+    return cost;
+  }
+
+  // SimpleScoredSamplingPlanner::scoreTrajectory, simple_scored_sampling_planner.cpp:50-79
+  double score(const Traj& t, double best) const {
+    double total = 0;
+    for (int k = 0; k < 6; ++k) {
+      double scale, cost;
+      switch (k) {  // critic order dwa_planner.cpp:167-173
+        case 0: scale = 1.0; break;  // OscillationCostFunction keeps TrajectoryCostFunction's default scale 1.0
+        case 1: scale = obstacle_scale; break;
+        case 2: scale = goal_front.scale; break;
+        case 3: scale = alignment.scale; break;
+        case 4: scale = path.scale; break;
+        default: scale = goal.scale; break;
+      }
+      if (scale == 0) continue;
+      switch (k) {
+        case 0: cost = osc_score(t); break;
+        case 1: cost = obstacle_score(t); break;
+        case 2: cost = goal_front.score(cm, t); break;
+        case 3: cost = alignment.score(cm, t); break;
+        case 4: cost = path.score(cm, t); break;
+        default: cost = goal.score(cm, t); break;
+      }
+      if (cost < 0) { total = cost; break; }
+      if (cost != 0) cost *= scale;
+      total += cost;
+      if (best > 0 && total > best) break;
+    }
+    return total;
+  }
+
+  void prepare_all() {
+    const bool au = cfg.allow_unknown != 0;
+    goal_front.prepare(cm, au);
+    alignment.prepare(cm, au);
+    path.prepare(cm, au);
+    goal.prepare(cm, au);
+  }
+};
+
+std::vector<Pt> to_pts(const double* xy, int n) {
+  std::vector<Pt> v(n);
+  for (int i = 0; i < n; ++i) v[i] = Pt{xy[2 * i], xy[2 * i + 1]};
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* navo_impl_name(void) { return "port"; }
+
+void* navo_costmap_create(uint32_t size_x, uint32_t size_y, double resolution, double origin_x, double origin_y,
+                          int rolling_window, int track_unknown) {
+  Costmap* cm = new Costmap;
+  cm->rolling = rolling_window != 0;
+  cm->track_unknown = track_unknown != 0;
+  cm->master.def = track_unknown ? kNoInfo : kFree;
+  cm->master.resize(size_x, size_y, resolution, origin_x, origin_y);
+  return cm;
+}
+void navo_costmap_destroy(void* h) { delete static_cast<Costmap*>(h); }
+static int add_layer(Costmap* cm, LayerBase* l) {
+  cm->layers.emplace_back(l);
+  l->match_size(*cm);
+  return int(cm->layers.size()) - 1;
+}
+int navo_costmap_add_grid_layer(void* h, int policy) { return add_layer(static_cast<Costmap*>(h), new GridLayer(policy)); }
+int navo_costmap_add_obstacle_layer(void* h, int combination_method, int footprint_clearing, double max_obstacle_height) {
+  return add_layer(static_cast<Costmap*>(h), new ObstacleLayer(combination_method, footprint_clearing != 0, max_obstacle_height));
+}
+int navo_costmap_add_inflation_layer(void* h, double inflation_radius, double cost_scaling_factor) {
+  Costmap* cm = static_cast<Costmap*>(h);
+  InflationLayer* il = new InflationLayer;
+  // onInitialize: the dynamic_reconfigure server delivers the defaults (0.55, 10) first, then matchSize (:71-98)
+  il->weight = 0; il->radius = 0;
+  il->res = cm->master.res;
+  il->set_params(*cm, 0.55, 10.0);
+  il->need_reinflation = true;
+  int id = add_layer(cm, il);
+  il->set_params(*cm, inflation_radius, cost_scaling_factor);
+  return id;
+}
+void navo_costmap_set_footprint(void* h, const double* xy, int n) {  // layered_costmap.cpp:163-173
+  Costmap* cm = static_cast<Costmap*>(h);
+  cm->footprint = to_pts(xy, n);
+  min_max_distances(cm->footprint, cm->inscribed, cm->circumscribed);
+  for (auto& l : cm->layers) l->on_footprint_changed(*cm);
+}
+void navo_grid_layer_set(void* h, int layer, const uint8_t* data) {
+  GridLayer* g = static_cast<GridLayer*>(static_cast<Costmap*>(h)->layers[layer].get());
+  memcpy(g->g.c.data(), data, g->g.c.size());
+  g->x = g->y = 0; g->w = g->g.sx; g->h = g->g.sy;
+  g->updated = true;
+}
+void navo_grid_layer_touch(void* h, int layer, uint32_t x, uint32_t y, uint32_t w, uint32_t hgt) {
+  GridLayer* g = static_cast<GridLayer*>(static_cast<Costmap*>(h)->layers[layer].get());
+  g->x = x; g->y = y; g->w = w; g->h = hgt;
+  g->updated = true;
+}
+void navo_layer_set_enabled(void* h, int layer, int enabled) { static_cast<Costmap*>(h)->layers[layer]->enabled = enabled != 0; }
+void navo_obstacle_set_observations(void* h, int layer, const navo_observation* obs, int n_obs) {
+  ObstacleLayer* ol = static_cast<ObstacleLayer*>(static_cast<Costmap*>(h)->layers[layer].get());
+  ol->obs.clear();
+  for (int i = 0; i < n_obs; ++i) {
+    Obs o;
+    o.ox = obs[i].origin_x; o.oy = obs[i].origin_y; o.oz = obs[i].origin_z;
+    o.obstacle_range = obs[i].obstacle_range;
+    o.raytrace_range = obs[i].raytrace_range;
+    o.xyz.assign(obs[i].xyz, obs[i].xyz + 3 * size_t(obs[i].n_points));
+    o.marking = obs[i].marking != 0;
+    o.clearing = obs[i].clearing != 0;
+    ol->obs.push_back(std::move(o));
+  }
+}
+void navo_inflation_set_params(void* h, int layer, double inflation_radius, double cost_scaling_factor) {
+  Costmap* cm = static_cast<Costmap*>(h);
+  static_cast<InflationLayer*>(cm->layers[layer].get())->set_params(*cm, inflation_radius, cost_scaling_factor);
+}
+void navo_costmap_update_map(void* h, double rx, double ry, double ryaw, int32_t w[4]) {
+  Costmap* cm = static_cast<Costmap*>(h);
+  cm->update_map(rx, ry, ryaw);
+  w[0] = cm->bx0; w[1] = cm->bxn; w[2] = cm->by0; w[3] = cm->byn;
+}
+void navo_costmap_get(void* h, uint8_t* out) {
+  Costmap* cm = static_cast<Costmap*>(h);
+  memcpy(out, cm->master.c.data(), cm->master.c.size());
+}
+void navo_costmap_set(void* h, const uint8_t* in) {
+  Costmap* cm = static_cast<Costmap*>(h);
+  memcpy(cm->master.c.data(), in, cm->master.c.size());
+}
+void navo_layer_get(void* h, int layer, uint8_t* out) {
+  Grid* g = static_cast<Costmap*>(h)->layers[layer]->grid();
+  if (g) memcpy(out, g->c.data(), g->c.size());
+}
+void navo_costmap_get_origin(void* h, double out[2]) {
+  Costmap* cm = static_cast<Costmap*>(h);
+  out[0] = cm->master.ox;
+  out[1] = cm->master.oy;
+}
+int navo_inflation_tables(void* h, int layer, uint8_t* costs_out, double* dists_out, int capacity) {
+  InflationLayer* il = static_cast<InflationLayer*>(static_cast<Costmap*>(h)->layers[layer].get());
+  int n = il->R + 2;
+  if (n * n > capacity || il->R == 0) return il->R;
+  memcpy(costs_out, il->costs.data(), size_t(n) * n);
+  memcpy(dists_out, il->dists.data(), size_t(n) * n * sizeof(double));
+  return il->R;
+}
+
+void navo_interpret_values(const uint8_t* in, uint8_t* out, int64_t n, int track_unknown, uint8_t unknown_cost_value,
+                           uint8_t lethal_threshold, int trinary) {  // static_layer.cpp:149-163
+  for (int64_t i = 0; i < n; ++i) {
+    uint8_t v = in[i];
+    if (v == unknown_cost_value) out[i] = track_unknown ? kNoInfo : kFree;
+    else if (v >= lethal_threshold) out[i] = kLethal;
+    else if (trinary) out[i] = kFree;
+    else out[i] = (uint8_t)(((double)v / lethal_threshold) * kLethal);
+  }
+}
+
+int navo_raytrace_cells(uint32_t size_x, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, uint32_t max_length,
+                        uint32_t* offsets_out, int capacity) {
+  int n = 0;
+  raytrace_line(size_x, [&](unsigned off) { if (n < capacity) offsets_out[n] = off; ++n; }, x0, y0, x1, y1, max_length);
+  return n;
+}
+void navo_footprint_radii(const double* xy, int n, double* inscribed, double* circumscribed) {
+  min_max_distances(to_pts(xy, n), *inscribed, *circumscribed);
+}
+
+// ---- Path B
+void navo_dwa_default_config(navo_dwa_config* c) {
+  // base_local_planner/src/local_planner_limits/__init__.py:15-45, dwa_local_planner/cfg/DWAPlanner.cfg:15-43
+  c->max_trans_vel = 0.55; c->min_trans_vel = 0.1; c->max_vel_x = 0.55; c->min_vel_x = 0.0;
+  c->max_vel_y = 0.1; c->min_vel_y = -0.1; c->max_rot_vel = 1.0; c->min_rot_vel = 0.4;
+  c->acc_lim_x = 2.5; c->acc_lim_y = 2.5; c->acc_lim_theta = 3.2;
+  c->sim_time = 1.7; c->sim_granularity = 0.025; c->angular_sim_granularity = 0.1; c->sim_period = 0.05;
+  c->path_distance_bias = 32.0; c->goal_distance_bias = 24.0; c->occdist_scale = 0.01;
+  c->forward_point_distance = 0.325; c->cheat_factor = 1.0;
+  c->oscillation_reset_dist = 0.05; c->oscillation_reset_angle = 0.2;
+  c->scaling_speed = 0.25; c->max_scaling_factor = 0.2;
+  c->vx_samples = 3; c->vy_samples = 10; c->vth_samples = 20;
+  c->use_dwa = 1; c->sum_scores = 0; c->allow_unknown = 0;
+}
+void* navo_dwa_create(const navo_dwa_config* cfg, uint32_t size_x, uint32_t size_y, double resolution) {
+  Dwa* d = new Dwa;
+  d->cfg = *cfg;
+  d->cm.def = 0;
+  d->cm.resize(size_x, size_y, resolution, 0.0, 0.0);
+  d->reconfigure();
+  return d;
+}
+void navo_dwa_destroy(void* h) { delete static_cast<Dwa*>(h); }
+void navo_dwa_set_costmap(void* h, const uint8_t* grid, double origin_x, double origin_y) {
+  Dwa* d = static_cast<Dwa*>(h);
+  d->cm.ox = origin_x;
+  d->cm.oy = origin_y;
+  memcpy(d->cm.c.data(), grid, d->cm.c.size());
+}
+void navo_dwa_set_plan(void* h, const double pose[3], const double* plan_xy, int n) {  // dwa_planner.cpp:240-286
+  Dwa* d = static_cast<Dwa*>(h);
+  d->plan = to_pts(plan_xy, n);
+  d->path.target = d->plan;
+  d->goal.target = d->plan;
+  Pt g = d->plan.back();
+  V3f pos{{float(pose[0]), float(pose[1]), float(pose[2])}};
+  double sq = (pos[0] - g.x) * (pos[0] - g.x) + (pos[1] - g.y) * (pos[1] - g.y);
+  std::vector<Pt> front = d->plan;
+  double ang = atan2(g.y - pos[1], g.x - pos[0]);
+  front.back().x = front.back().x + d->cfg.forward_point_distance * cos(ang);
+  front.back().y = front.back().y + d->cfg.forward_point_distance * sin(ang);
+  d->goal_front.target = front;
+  if (sq > d->cfg.forward_point_distance * d->cfg.forward_point_distance * d->cfg.cheat_factor) {
+    d->alignment.scale = d->cm.res * d->cfg.path_distance_bias * 0.5;
+    d->alignment.target = d->plan;
+  } else {
+    d->alignment.scale = 0.0;
+  }
+}
+void navo_dwa_reset_oscillation(void* h) { static_cast<Dwa*>(h)->reset_osc(); }
+int navo_dwa_get_oscillation_mask(void* h) {
+  Dwa* d = static_cast<Dwa*>(h);
+  return int(d->forward_pos_only) | int(d->forward_neg_only) << 1 | int(d->strafe_pos_only) << 2 |
+         int(d->strafe_neg_only) << 3 | int(d->rot_pos_only) << 4 | int(d->rot_neg_only) << 5;
+}
+
+int navo_dwa_find_best_path(void* h, const double pose[3], const double velv[3], const double* footprint_xy,
+                            int n_footprint, navo_dwa_result* result, double* all_costs, int all_capacity,
+                            double* best_points, int points_capacity) {  // dwa_planner.cpp:292-371
+  Dwa* d = static_cast<Dwa*>(h);
+  d->footprint = to_pts(footprint_xy, n_footprint);
+  V3f pos{{float(pose[0]), float(pose[1]), float(pose[2])}};
+  V3f vel{{float(velv[0]), float(velv[1]), float(velv[2])}};
+  V3f goal{{float(d->plan.back().x), float(d->plan.back().y), 0.f}};
+  std::vector<V3f> samples;
+  d->enumerate_samples(pos, vel, goal, samples);
+  // findBestTrajectory, simple_scored_sampling_planner.cpp:81-142
+  d->prepare_all();
+  Traj loop, best;
+  double best_cost = -1;
+  int best_index = -1, n_scored = 0;
+  for (size_t i = 0; i < samples.size(); ++i) {
+    double reported = std::numeric_limits<double>::quiet_NaN();
+    if (d->generate(pos, vel, samples[i], loop)) {
+      double c = d->score(loop, best_cost);
+      reported = c;
+      ++n_scored;
+      if (c >= 0 && (best_cost < 0 || c < best_cost)) {
+        best_cost = c;
+        best = loop;
+        best_index = int(i);
+      }
+    }
+    if (all_costs && int(i) < all_capacity) all_costs[i] = reported;
+  }
+  // result_traj_ persists across cycles: only cost_ is reset, velocities and points stay stale when nothing is
+  // valid (dwa_planner.cpp:316, simple_scored_sampling_planner.cpp:123-134)
+  Traj& res = d->result;
+  res.cost = -7;
+  if (best_cost >= 0) {
+    res = best;
+    res.cost = best_cost;
+  }
+  d->update_osc_flags(pos, res, d->cfg.min_trans_vel);
+  result->cost = res.cost;
+  result->xv = res.xv; result->yv = res.yv; result->thetav = res.thv;
+  result->best_index = best_index;
+  result->n_samples = int(samples.size());
+  result->n_scored = n_scored;
+  result->n_points = int(res.x.size());
+  if (best_points)
+    for (size_t i = 0; i < res.x.size() && int(i) < points_capacity; ++i) {
+      best_points[3 * i] = res.x[i];
+      best_points[3 * i + 1] = res.y[i];
+      best_points[3 * i + 2] = res.th[i];
+    }
+  return best_cost >= 0 ? 1 : 0;
+}
+void navo_dwa_get_grid(void* h, int which, double* out) {
+  Dwa* d = static_cast<Dwa*>(h);
+  MapGridCritic* g[4] = {&d->path, &d->goal, &d->goal_front, &d->alignment};
+  memcpy(out, g[which]->dist.data(), g[which]->dist.size() * sizeof(double));
+}
+void navo_dwa_prepare_only(void* h) { static_cast<Dwa*>(h)->prepare_all(); }
+
+int navo_velocity_samples(double vmin, double vmax, int num_samples, double* out, int capacity) {
+  std::vector<double> s = velocity_samples(vmin, vmax, num_samples);
+  for (size_t i = 0; i < s.size() && int(i) < capacity; ++i) out[i] = s[i];
+  return int(s.size());
+}
+int navo_line_cells(int x0, int y0, int x1, int y1, int32_t* xy_out, int capacity) {
+  int n = 0;
+  for (LineIt l(x0, y0, x1, y1); l.valid(); l.advance()) {
+    if (n < capacity) { xy_out[2 * n] = l.x; xy_out[2 * n + 1] = l.y; }
+    ++n;
+  }
+  return n;
+}
+void navo_mapgrid_bfs(const uint8_t* costs, uint32_t size_x, uint32_t size_y, const int32_t* seeds_xy, int n_seeds,
+                      int allow_unknown, double* dist_out) {
+  Grid cm;
+  cm.resize(size_x, size_y, 1.0, 0, 0);
+  memcpy(cm.c.data(), costs, cm.c.size());
+  size_t n = cm.c.size();
+  std::vector<double> dist(n, double(n + 1));
+  std::vector<uint8_t> mark(n, 0);
+  std::queue<unsigned> q;
+  for (int i = 0; i < n_seeds; ++i) {
+    unsigned id = seeds_xy[2 * i + 1] * size_x + seeds_xy[2 * i];
+    dist[id] = 0.0;
+    mark[id] = 1;
+    q.push(id);
+  }
+  mapgrid_bfs(cm, allow_unknown != 0, dist, mark, q);
+  memcpy(dist_out, dist.data(), n * sizeof(double));
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+"""Loading / comparing the golden fixtures produced by tests/golden/make_golden.py (reference outputs)."""
+import glob
+import os
+import re
+
+import numpy as np
+
+import scenarios as sc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def costmap_cases():
+    out = []
+    for p in sorted(glob.glob(os.path.join(GOLDEN, "costmap_*.npz"))):
+        m = re.match(r"costmap_(tf|any)_(\d+)\.npz", os.path.basename(p))
+        out.append((m.group(1) == "tf", int(m.group(2)), p))
+    return out
+
+
+def dwa_cases():
+    return [(int(re.match(r"dwa_(\d+)\.npz", os.path.basename(p)).group(1)), p)
+            for p in sorted(glob.glob(os.path.join(GOLDEN, "dwa_*.npz")))]
+
+
+def check_costmap_case(api, tie_free, seed, path, exact=True):
+    """Returns the number of mismatching master cells over all cycles (0 = bit-exact); asserts windows/layers."""
+    g = np.load(path)
+    tr = sc.run_costmap_scenario(api, seed, tie_free=tie_free)
+    bad = 0
+    for c, (w, m, o, org) in enumerate(tr):
+        assert tuple(g[f"w{c}"]) == tuple(w), f"window differs in cycle {c}"
+        assert tuple(g[f"org{c}"]) == tuple(org), f"origin differs in cycle {c}"
+        assert np.array_equal(g[f"o{c}"], o), f"obstacle layer grid differs in cycle {c}"
+        bad += int((g[f"m{c}"] != m).sum())
+    if exact:
+        assert bad == 0, f"{bad} master cells differ from the reference"
+    return bad
+
+
+def check_dwa_case(api, grid_api, seed, path, rtol=0.0):
+    g = np.load(path)
+    out = sc.run_dwa_scenario(api, grid_api, seed)
+    for c, r in enumerate(out):
+        s = g[f"scalars{c}"]
+        ref = dict(ok=bool(s[0]), cost=s[1], xv=s[2], yv=s[3], thetav=s[4], best_index=int(s[5]), n_samples=int(s[6]),
+                   n_scored=int(s[7]), mask=int(s[8]), costs=g[f"costs{c}"], points=g[f"points{c}"],
+                   grids=[g[f"grid{c}_{k}"].astype(np.float64) for k in range(4)])
+        assert sc.dwa_results_equal(r, ref, rtol=rtol), f"seed {seed} cycle {c} differs from the reference"

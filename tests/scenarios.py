@@ -1,0 +1,185 @@
+"""Seeded random scenarios shared by the oracle-vs-reference and GPU-vs-oracle parity tests."""
+import numpy as np
+
+from oracle import pyoracle as po
+
+
+def square_footprint(half=0.325):
+    return [(half, half), (half, -half), (-half, -half), (-half, half)]
+
+
+PENTAGON = [(-0.325, -0.325), (-0.325, 0.325), (0.325, 0.325), (0.46, 0.0), (0.325, -0.325)]  # costmap_params.yaml:21
+
+
+def random_layer(rng, sy, sx, kind):
+    """kind: 'blocks' axis-aligned thick structure (tie-free), 'salt' single cells, 'values' arbitrary bytes."""
+    g = np.zeros((sy, sx), np.uint8)
+    if kind == "blocks":
+        for _ in range(max(2, sx * sy // 2500)):
+            w, h = rng.integers(3, max(4, sx // 5)), rng.integers(3, max(4, sy // 5))
+            x, y = rng.integers(0, sx - 2), rng.integers(0, sy - 2)
+            g[y:y + h, x:x + w] = 254
+    elif kind == "salt":
+        g[rng.random((sy, sx)) < 0.01] = 254
+    elif kind == "values":
+        g = rng.choice(np.array([0, 0, 0, 1, 50, 100, 128, 200, 252, 253, 254, 255], np.uint8), size=(sy, sx))
+    return g
+
+
+def random_observations(rng, sx, sy, res, ox, oy, n_obs, n_pts, spread=1.3):
+    obs = []
+    for _ in range(n_obs):
+        # origins mostly inside the map, sometimes outside (whole observation skipped for clearing)
+        o = (ox + rng.uniform(-0.1, 1.1) * sx * res, oy + rng.uniform(-0.1, 1.1) * sy * res, rng.uniform(0, 1))
+        ang = rng.uniform(0, 2 * np.pi, n_pts)
+        rad = rng.uniform(0.0, spread * max(sx, sy) * res, n_pts)
+        pts = np.stack([o[0] + rad * np.cos(ang), o[1] + rad * np.sin(ang), rng.uniform(-0.2, 2.5, n_pts)], 1)
+        obs.append(dict(origin=o, points=pts.astype(np.float32), obstacle_range=float(rng.uniform(1.0, 8.0)),
+                        raytrace_range=float(rng.uniform(1.0, 8.0)), marking=bool(rng.random() < 0.8),
+                        clearing=bool(rng.random() < 0.8)))
+    return obs
+
+
+def build_stack(api, rng, sx, sy, res, ox, oy, rolling, track_unknown, layer_kind="blocks", with_obstacle=True,
+                with_inflation=True, radius=0.55, scaling=10.0, extra_policy=None):
+    """static(TrueOverwrite|Max) [+ extra grid layer] [+ obstacle] [+ inflation]; returns (costmap, ids)."""
+    cm = api.costmap(sx, sy, res, ox, oy, rolling=rolling, track_unknown=track_unknown)
+    ids = {}
+    if not rolling:
+        ids["static"] = cm.add_grid_layer(po.TRUE_OVERWRITE if rng.random() < 0.7 else po.MAX)
+    if extra_policy is not None:
+        ids["extra"] = cm.add_grid_layer(extra_policy)
+    if with_obstacle:
+        ids["obstacle"] = cm.add_obstacle_layer(int(rng.integers(0, 2)), bool(rng.random() < 0.7), 2.0)
+    if with_inflation:
+        ids["inflation"] = cm.add_inflation_layer(radius, scaling)
+    cm.set_footprint(square_footprint())
+    return cm, ids
+
+
+def local_costmap(api, rng, n=120, res=0.05, ox=0.0, oy=0.0, style="corridor"):
+    """A C2-style local costmap (no NO_INFORMATION cells): walls/boxes inflated by the oracle itself."""
+    cm = api.costmap(n, n, res, ox, oy)
+    s = cm.add_grid_layer(po.TRUE_OVERWRITE)
+    cm.add_inflation_layer(0.55, 10.0)
+    cm.set_footprint(PENTAGON)
+    g = np.zeros((n, n), np.uint8)
+    if style == "corridor":
+        lo, hi = int(n * 0.25), int(n * 0.75)
+        g[:lo - 1, :] = 0
+        g[lo - 4:lo - 1, :] = 254
+        g[hi + 1:hi + 4, :] = 254
+        bx, by = int(rng.integers(n // 2, n - 20)), int(rng.integers(lo + 8, hi - 14))
+        g[by:by + 6, bx:bx + 6] = 254
+    elif style == "clutter":
+        for _ in range(int(rng.integers(3, 9))):
+            x, y = rng.integers(0, n - 8, 2)
+            w, h = rng.integers(2, 8, 2)
+            g[y:y + h, x:x + w] = 254
+    elif style == "empty":
+        pass
+    cm.set_grid_layer(s, g)
+    cm.update_map(0, 0, 0)
+    return cm.get()
+
+
+def dwa_scenario(rng, n=120, res=0.05, style=None):
+    """Returns dict(origin, pose, vel, plan) for a local map of n x n cells."""
+    style = style or str(rng.choice(["corridor", "clutter", "empty"]))
+    ox, oy = float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5))
+    size = n * res
+    pose = (ox + size * rng.uniform(0.2, 0.5), oy + size * rng.uniform(0.4, 0.6), float(rng.uniform(-0.6, 0.6)))
+    vel = (float(rng.uniform(0.0, 0.5)), 0.0, float(rng.uniform(-0.5, 0.5)))
+    # plan: polyline from behind the robot to beyond the map edge (so it leaves the window), some sparse gaps
+    npts = int(rng.integers(20, 200))
+    t = np.linspace(-0.1, 1.3, npts)
+    px = pose[0] + t * size * 0.7
+    py = pose[1] + 0.3 * np.sin(t * rng.uniform(1, 4)) * rng.uniform(0, 1.5)
+    return dict(style=style, origin=(ox, oy), pose=pose, vel=vel, plan=np.stack([px, py], 1))
+
+
+def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False):
+    """Multi-cycle LayeredCostmap scenario; returns per cycle (window, master, obstacle-layer grid, origin).
+
+    `api` is anything shaped like oracle.pyoracle.Api (the oracles and the CUDA binding all are).
+    tie_free=True restricts obstacle sources to thick axis-aligned blocks (no marking of single points), the class on
+    which every tie policy of the reference's priority queue gives the same grid.
+    """
+    rng = np.random.default_rng(seed)
+    sx, sy = int(rng.integers(20, max_size)), int(rng.integers(20, max_size))
+    res = float(rng.choice([0.05, 0.1, 0.25]))
+    ox, oy = float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3))
+    rolling = bool(rng.random() < 0.4)
+    tu = bool(rng.random() < 0.4)
+    kind = "blocks" if tie_free else str(rng.choice(["blocks", "salt", "values"]))
+    extra = [None, po.OVERWRITE, po.MAX, po.ADDITION][int(rng.integers(0, 4))]
+    radius = float(rng.choice([0.3, 0.55, 1.0]))
+    scaling = float(rng.choice([1.0, 10.0]))
+    cm, ids = build_stack(api, rng, sx, sy, res, ox, oy, rolling, tu, kind, radius=radius, scaling=scaling,
+                          extra_policy=extra)
+    trace = []
+    rx, ry = ox + sx * res / 2, oy + sy * res / 2
+    for cyc in range(cycles):
+        if "static" in ids and (cyc == 0 or rng.random() < 0.3):
+            cm.set_grid_layer(ids["static"], random_layer(rng, sy, sx, kind))
+        if "extra" in ids and (cyc == 0 or rng.random() < 0.5):
+            cm.set_grid_layer(ids["extra"], random_layer(rng, sy, sx, "values"))
+        obs = random_observations(rng, sx, sy, res, ox, oy, int(rng.integers(0, 4)), 40)
+        if tie_free:
+            for o in obs:
+                o["marking"] = False
+        cm.set_observations(ids["obstacle"], obs)
+        rx += rng.uniform(-0.5, 0.5)
+        ry += rng.uniform(-0.5, 0.5)
+        w = cm.update_map(rx, ry, float(rng.uniform(-3, 3)))
+        trace.append((w, cm.get().copy(), cm.get_layer(ids["obstacle"]).copy(), cm.origin()))
+    return trace
+
+
+def run_dwa_scenario(api, grid_api, seed, cycles=5):
+    """Multi-cycle DWAPlanner scenario; the local costmap is produced by `grid_api` (an oracle)."""
+    rng = np.random.default_rng(seed)
+    s = dwa_scenario(rng)
+    grid = local_costmap(grid_api, np.random.default_rng(seed + 1000), ox=s["origin"][0], oy=s["origin"][1],
+                         style=s["style"])
+    over = dict(vx_samples=int(rng.integers(1, 12)), vy_samples=int(rng.integers(1, 4)),
+                vth_samples=int(rng.integers(1, 25)))
+    if rng.random() < 0.3:
+        over.update(max_vel_y=0.0, min_vel_y=0.0)
+    if rng.random() < 0.2:
+        over.update(use_dwa=0)
+    if rng.random() < 0.2:
+        over.update(sum_scores=1)
+    if rng.random() < 0.3:
+        over.update(min_vel_x=-0.2)
+    d = api.dwa(120, 120, 0.05, **over)
+    d.set_costmap(grid, *s["origin"])
+    out = []
+    pose = np.array(s["pose"])
+    vel = np.array(s["vel"])
+    for cyc in range(cycles):
+        d.set_plan(pose, s["plan"])
+        r = d.find_best_path(pose, vel, PENTAGON)
+        r["mask"] = d.oscillation_mask()
+        r["grids"] = [d.grid(k) for k in range(4)]
+        out.append(r)
+        # alternate forward/backward so the oscillation flags latch
+        vel = np.array([r["xv"] * (-1 if cyc % 2 else 1), r["yv"], -r["thetav"]]) if r["ok"] else vel * 0
+        pose = pose + np.array([0.01 * vel[0], 0, 0.01 * vel[2]])
+    return out
+
+
+def dwa_results_equal(a, b, rtol=0.0):
+    """Exact (rtol=0) or relative comparison of two find_best_path result dicts."""
+    if (a["ok"], a["best_index"], a["n_samples"], a["n_scored"], a["mask"]) != \
+       (b["ok"], b["best_index"], b["n_samples"], b["n_scored"], b["mask"]):
+        return False
+    if not all(np.array_equal(x, y) for x, y in zip(a["grids"], b["grids"])):
+        return False
+    if rtol == 0.0:
+        return (a["cost"] == b["cost"] and (a["xv"], a["yv"], a["thetav"]) == (b["xv"], b["yv"], b["thetav"]) and
+                np.array_equal(a["costs"], b["costs"], equal_nan=True) and np.array_equal(a["points"], b["points"]))
+    ok = np.isclose(a["cost"], b["cost"], rtol=rtol, atol=0) and \
+        np.allclose(a["costs"], b["costs"], rtol=rtol, atol=0, equal_nan=True) and \
+        np.allclose(a["points"], b["points"], rtol=rtol, atol=1e-12)
+    return bool(ok)
