@@ -1,0 +1,199 @@
+/*
+ * navgpu.h -- C ABI of libnavgpu.so: B200-native (sm_100a) implementation of the ROS navigation stack's two
+ * data-parallel hot paths.  Plain pointers and sizes only; every entry point returns a status code (0 = ok) and
+ * never throws.  There is NO CPU fallback: every entry point that computes fails with NAVGPU_ERR_CUDA when no
+ * CUDA device is usable.
+ *
+ * Path A -- costmap layering + inflation.  A device-resident layered costmap replacing, per update cycle,
+ *   costmap_2d::LayeredCostmap::updateMap            costmap_2d/src/layered_costmap.cpp:79-150
+ *   Costmap2D::resetMap / updateOrigin                costmap_2d/src/costmap_2d.cpp:93-99, 264-313
+ *   CostmapLayer::updateWith{TrueOverwrite,Overwrite,Max,Addition}   costmap_2d/src/costmap_layer.cpp:62-157
+ *   StaticLayer::updateBounds/updateCosts (non-rolling) + interpretValue   plugins/static_layer.cpp:149-163,263-299
+ *   ObstacleLayer::updateBounds (raytraceFreespace + marking + footprint)  plugins/obstacle_layer.cpp:340-425,498-610
+ *   ObstacleLayer::updateCosts (setConvexPolygonCost + merge)               plugins/obstacle_layer.cpp:427-448
+ *   InflationLayer::updateBounds/updateCosts/computeCaches                  plugins/inflation_layer.cpp:125-328
+ * plus stateless "plugin seam" calls on a HOST master grid for use from inside a costmap_2d::Layer subclass
+ * (layer.h:65-72): navgpu_inflate_host, navgpu_merge_host.
+ *
+ * Path B -- DWA rollout scoring: see the navgpu_dwa_* block below (dwa_local_planner/src/dwa_planner.cpp:292-371).
+ *
+ * Threading: one CUDA stream per handle; the caller provides mutual exclusion per handle, exactly like the
+ * reference's Costmap2D::mutex_t (layered_costmap.cpp:83) and DWAPlanner::configuration_mutex_ (dwa_planner.cpp:301).
+ */
+#ifndef NAVGPU_H_
+#define NAVGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  NAVGPU_OK = 0,
+  NAVGPU_ERR_CUDA = 1,        /* no device / CUDA runtime error (message via navgpu_last_error) */
+  NAVGPU_ERR_INVALID = 2,     /* bad argument */
+  NAVGPU_ERR_UNSUPPORTED = 3, /* configuration outside what the kernels implement */
+  NAVGPU_ERR_CAPACITY = 4     /* caller-provided buffer too small */
+};
+
+/* merge policies (costmap_layer.cpp:62-157) */
+enum { NAVGPU_TRUE_OVERWRITE = 0, NAVGPU_OVERWRITE = 1, NAVGPU_MAX = 2, NAVGPU_ADDITION = 3, NAVGPU_NOTHING = 4 };
+
+/* cost_values.h:42-45 */
+enum { NAVGPU_FREE_SPACE = 0, NAVGPU_INSCRIBED = 253, NAVGPU_LETHAL = 254, NAVGPU_NO_INFORMATION = 255 };
+
+const char* navgpu_last_error(void);
+/* number of usable CUDA devices (0 when none) */
+int navgpu_device_count(void);
+/* total number of kernels launched by this library in this process (for bench.py's gpu_launches) */
+uint64_t navgpu_launch_count(void);
+
+/* one costmap_2d::Observation (observation.h:47-100); xyz = n_points * 3 float32 in the world frame */
+typedef struct {
+  double origin_x, origin_y, origin_z;
+  double obstacle_range, raytrace_range;
+  const float* xyz;
+  int32_t n_points;
+  int32_t marking;
+  int32_t clearing;
+  int32_t pad_;
+} navgpu_observation;
+
+typedef struct navgpu_costmap navgpu_costmap;
+
+/* ---- Path A: device-resident LayeredCostmap -------------------------------------------------------------- */
+/* LayeredCostmap ctor + resizeMap (layered_costmap.cpp:50-77). device = CUDA ordinal. */
+int navgpu_costmap_create(navgpu_costmap** out, uint32_t size_x, uint32_t size_y, double resolution, double origin_x,
+                          double origin_y, int rolling_window, int track_unknown, int device);
+int navgpu_costmap_destroy(navgpu_costmap* h);
+/* layers are appended in plugin order (costmap_2d_ros.cpp:115-128); *layer_out receives the index */
+int navgpu_costmap_add_grid_layer(navgpu_costmap* h, int policy, int* layer_out);
+int navgpu_costmap_add_obstacle_layer(navgpu_costmap* h, int combination_method, int footprint_clearing,
+                                      double max_obstacle_height, int* layer_out);
+int navgpu_costmap_add_inflation_layer(navgpu_costmap* h, double inflation_radius, double cost_scaling_factor,
+                                       int* layer_out);
+/* LayeredCostmap::setFootprint (layered_costmap.cpp:163-173): n (x,y) pairs, robot frame */
+int navgpu_costmap_set_footprint(navgpu_costmap* h, const double* xy, int n);
+/* whole-grid upload of a grid layer from HOST memory, marks it updated (StaticLayer::incomingMap :165-223) */
+int navgpu_grid_layer_set(navgpu_costmap* h, int layer, const uint8_t* host_data);
+/* same, from DEVICE memory (row pitch in bytes) */
+int navgpu_grid_layer_set_device(navgpu_costmap* h, int layer, const uint8_t* dev_data, uint32_t pitch);
+/* OccupancyGrid ingest on the device: interpretValue over int8 occupancy from HOST memory (static_layer.cpp:149-207) */
+int navgpu_grid_layer_set_occupancy(navgpu_costmap* h, int layer, const int8_t* host_occupancy, int track_unknown,
+                                    uint8_t unknown_cost_value, uint8_t lethal_threshold, int trinary);
+int navgpu_grid_layer_touch(navgpu_costmap* h, int layer, uint32_t x, uint32_t y, uint32_t w, uint32_t hgt);
+int navgpu_layer_set_enabled(navgpu_costmap* h, int layer, int enabled);
+/* observations persist until replaced (ObstacleLayer::addStaticObservation :450-464); copied H2D here */
+int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_observation* obs, int n_obs);
+/* InflationLayer::setInflationParameters (:356-370) */
+int navgpu_inflation_set_params(navgpu_costmap* h, int layer, double inflation_radius, double cost_scaling_factor);
+/* inflation algorithm: 0 = exact windowed nearest-lethal distance (default; equals the reference wherever its
+ * priority-queue tie order does not matter), 1 = level-synchronous nearest-source propagation */
+int navgpu_inflation_set_mode(navgpu_costmap* h, int layer, int mode);
+/* LayeredCostmap::updateMap.  Synchronous: returns after the cycle's kernels finished.
+ * window_out = {x0, xn, y0, yn} (LayeredCostmap::getBounds). */
+int navgpu_costmap_update_map(navgpu_costmap* h, double robot_x, double robot_y, double robot_yaw,
+                              int32_t window_out[4]);
+/* enqueue-only variant (no host synchronisation, no window read-back): for timing and pipelining */
+int navgpu_costmap_update_map_async(navgpu_costmap* h, double robot_x, double robot_y, double robot_yaw);
+int navgpu_costmap_synchronize(navgpu_costmap* h);
+/* the CUDA stream of this handle (cudaStream_t) so callers can record events on it */
+void* navgpu_costmap_stream(navgpu_costmap* h);
+/* master grid read-back to HOST: whole grid, or a window [x0,xn) x [y0,yn) packed row-major into out */
+int navgpu_costmap_get(navgpu_costmap* h, uint8_t* host_out);
+int navgpu_costmap_get_window(navgpu_costmap* h, int x0, int y0, int xn, int yn, uint8_t* host_out);
+int navgpu_costmap_set(navgpu_costmap* h, const uint8_t* host_in);
+int navgpu_layer_get(navgpu_costmap* h, int layer, uint8_t* host_out);
+int navgpu_costmap_get_origin(navgpu_costmap* h, double out[2]);
+/* device pointer + pitch of the master grid (for zero-copy consumers such as the Path-B scorer) */
+int navgpu_costmap_device_grid(navgpu_costmap* h, const uint8_t** dev_ptr, uint32_t* pitch);
+/* InflationLayer cached tables (computeCaches :295-328), (R+2)*(R+2) each; *radius_out = cell_inflation_radius_ */
+int navgpu_inflation_tables(navgpu_costmap* h, int layer, uint8_t* costs_out, double* dists_out, int capacity,
+                            int* radius_out);
+
+/* ---- Path A: stateless plugin-seam calls on a HOST master grid -------------------------------------------- */
+/* Drop-in body for InflationLayer::updateCosts(master, min_i, min_j, max_i, max_j) (inflation_layer.cpp:172-266):
+ * uploads the affected window, inflates on the device, writes the result back into master.  cost_table is the
+ * (R+2)*(R+2) cached_costs_ array (row-major [dx][dy]) built with the reference formula. */
+int navgpu_inflate_host(uint8_t* master, uint32_t size_x, uint32_t size_y, int min_i, int min_j, int max_i, int max_j,
+                        const uint8_t* cost_table, uint32_t cell_inflation_radius, int device);
+/* Drop-in body for CostmapLayer::updateWith* (costmap_layer.cpp:62-157) */
+int navgpu_merge_host(uint8_t* master, const uint8_t* layer, uint32_t size_x, uint32_t size_y, int min_i, int min_j,
+                      int max_i, int max_j, int policy, int device);
+/* InflationLayer::computeCost table builder (inflation_layer.h:114-129, .cpp:295-328) -- host-side, exact formula */
+int navgpu_build_cost_table(double resolution, double inscribed_radius, double inflation_radius,
+                            double cost_scaling_factor, uint8_t* costs_out, double* dists_out, int capacity,
+                            int* radius_out);
+
+/* ---- Path B: DWA rollout scoring ------------------------------------------------------------------------- */
+typedef struct {
+  /* base_local_planner::LocalPlannerLimits (local_planner_limits.h:43-124) */
+  double max_trans_vel, min_trans_vel, max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_rot_vel, min_rot_vel;
+  double acc_lim_x, acc_lim_y, acc_lim_theta;
+  /* DWAPlannerConfig (dwa_local_planner/cfg/DWAPlanner.cfg) */
+  double sim_time, sim_granularity, angular_sim_granularity, sim_period;
+  double path_distance_bias, goal_distance_bias, occdist_scale;
+  double forward_point_distance, cheat_factor;
+  double oscillation_reset_dist, oscillation_reset_angle;
+  double scaling_speed, max_scaling_factor;
+  int32_t vx_samples, vy_samples, vth_samples;
+  int32_t use_dwa, sum_scores, allow_unknown;
+} navgpu_dwa_config;
+
+typedef struct {
+  double cost; /* result_traj_.cost_; -7 when nothing valid (dwa_planner.cpp:316) */
+  double xv, yv, thetav;
+  int32_t best_index; /* index into the enumerated samples (x outer, y, theta inner); -1 if none */
+  int32_t n_samples;
+  int32_t n_scored;
+  int32_t n_points;
+} navgpu_dwa_result;
+
+typedef struct navgpu_dwa navgpu_dwa;
+
+void navgpu_dwa_default_config(navgpu_dwa_config* cfg);
+/* DWAPlanner ctor + reconfigure (dwa_planner.cpp:52-182) for a local costmap of size_x x size_y cells */
+int navgpu_dwa_create(navgpu_dwa** out, const navgpu_dwa_config* cfg, uint32_t size_x, uint32_t size_y,
+                      double resolution, int device);
+int navgpu_dwa_destroy(navgpu_dwa* h);
+int navgpu_dwa_reconfigure(navgpu_dwa* h, const navgpu_dwa_config* cfg);
+/* local costmap contents from HOST memory (what the critics read through Costmap2D*, dwa_planner.cpp:118-122) */
+int navgpu_dwa_set_costmap(navgpu_dwa* h, const uint8_t* host_grid, double origin_x, double origin_y);
+/* zero-copy: score against a device-resident grid (e.g. navgpu_costmap_device_grid of the local costmap) */
+int navgpu_dwa_set_costmap_device(navgpu_dwa* h, const uint8_t* dev_grid, uint32_t pitch, double origin_x,
+                                  double origin_y);
+/* DWAPlanner::updatePlanAndLocalCosts (dwa_planner.cpp:240-286) */
+int navgpu_dwa_set_plan(navgpu_dwa* h, const double pose[3], const double* plan_xy, int n);
+/* DWAPlanner::setPlan's oscillation reset (dwa_planner.cpp:204-207) */
+int navgpu_dwa_reset_oscillation(navgpu_dwa* h);
+int navgpu_dwa_get_oscillation_mask(navgpu_dwa* h, int* mask_out);
+/* DWAPlanner::findBestPath (dwa_planner.cpp:292-371): 4x MapGrid prepare, sample enumeration, rollout, 6 critics,
+ * argmin, oscillation-flag update.  all_costs (nullable): per enumerated sample the cost the reference reports in
+ * all_explored (NaN for samples its generator rejects).  best_points (nullable): 3*points_capacity doubles.
+ * Returns NAVGPU_OK also when no valid trajectory exists (result->cost < 0, like the reference). */
+int navgpu_dwa_find_best_path(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                              int n_footprint, navgpu_dwa_result* result, double* all_costs, int all_capacity,
+                              double* best_points, int points_capacity);
+/* sample-range sharded variant for multi-GPU sweeps: scores enumerated samples [begin, end) only and returns this
+ * shard's (cost, global index) minimum without touching the oscillation state; cost = +inf when none valid. */
+int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                           int n_footprint, int64_t begin, int64_t end, double* best_cost, int64_t* best_index,
+                           int64_t* n_samples_total);
+/* finish a sharded sweep on every rank: given the all-gathered per-rank (cost,index) minima pick the winner exactly
+ * as simple_scored_sampling_planner.cpp:111-116 would, regenerate its trajectory and update the oscillation flags */
+int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double vel[3], const double* costs,
+                              const int64_t* indices, int n_ranks, navgpu_dwa_result* result, double* best_points,
+                              int points_capacity);
+/* the four MapGrid distance fields after prepare(): which = 0 path, 1 goal, 2 goal_front, 3 alignment (fp64, host) */
+int navgpu_dwa_get_grid(navgpu_dwa* h, int which, double* host_out);
+/* enqueue one full scoring cycle without host synchronisation (timing) */
+int navgpu_dwa_find_best_path_async(navgpu_dwa* h, const double pose[3], const double vel[3],
+                                    const double* footprint_xy, int n_footprint);
+int navgpu_dwa_synchronize(navgpu_dwa* h);
+void* navgpu_dwa_stream(navgpu_dwa* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,406 @@
+"""ctypes binding of include/navgpu.h (libnavgpu.so).
+
+Shaped like the checker binding (same method names) so parity tests drive both through the same scenario code, but
+this module never imports or loads anything from oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnavgpu.so")
+
+TRUE_OVERWRITE, OVERWRITE, MAX, ADDITION, NOTHING = 0, 1, 2, 3, 4
+
+
+class NavGpuError(RuntimeError):
+    pass
+
+
+class Observation(C.Structure):
+    _fields_ = [("origin_x", C.c_double), ("origin_y", C.c_double), ("origin_z", C.c_double),
+                ("obstacle_range", C.c_double), ("raytrace_range", C.c_double),
+                ("xyz", C.POINTER(C.c_float)), ("n_points", C.c_int32), ("marking", C.c_int32),
+                ("clearing", C.c_int32), ("pad_", C.c_int32)]
+
+
+class DwaConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "max_trans_vel", "min_trans_vel", "max_vel_x", "min_vel_x", "max_vel_y", "min_vel_y", "max_rot_vel",
+        "min_rot_vel", "acc_lim_x", "acc_lim_y", "acc_lim_theta", "sim_time", "sim_granularity",
+        "angular_sim_granularity", "sim_period", "path_distance_bias", "goal_distance_bias", "occdist_scale",
+        "forward_point_distance", "cheat_factor", "oscillation_reset_dist", "oscillation_reset_angle",
+        "scaling_speed", "max_scaling_factor")] + [(n, C.c_int32) for n in (
+            "vx_samples", "vy_samples", "vth_samples", "use_dwa", "sum_scores", "allow_unknown")]
+
+
+class DwaResult(C.Structure):
+    _fields_ = [("cost", C.c_double), ("xv", C.c_double), ("yv", C.c_double), ("thetav", C.c_double),
+                ("best_index", C.c_int32), ("n_samples", C.c_int32), ("n_scored", C.c_int32),
+                ("n_points", C.c_int32)]
+
+
+_u8p = C.POINTER(C.c_uint8)
+_i8p = C.POINTER(C.c_int8)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_vpp = C.POINTER(C.c_void_p)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+# name -> (restype, argtypes); every symbol include/navgpu.h declares
+SIGNATURES = {
+    "navgpu_last_error": (C.c_char_p, []),
+    "navgpu_device_count": (C.c_int, []),
+    "navgpu_launch_count": (C.c_uint64, []),
+    "navgpu_costmap_create": (C.c_int, [_vpp, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int,
+                                        C.c_int, C.c_int]),
+    "navgpu_costmap_destroy": (C.c_int, [C.c_void_p]),
+    "navgpu_costmap_add_grid_layer": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
+    "navgpu_costmap_add_obstacle_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, _i32p]),
+    "navgpu_costmap_add_inflation_layer": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _i32p]),
+    "navgpu_costmap_set_footprint": (C.c_int, [C.c_void_p, _f64p, C.c_int]),
+    "navgpu_grid_layer_set": (C.c_int, [C.c_void_p, C.c_int, _u8p]),
+    "navgpu_grid_layer_set_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]),
+    "navgpu_grid_layer_set_occupancy": (C.c_int, [C.c_void_p, C.c_int, _i8p, C.c_int, C.c_uint8, C.c_uint8, C.c_int]),
+    "navgpu_grid_layer_touch": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "navgpu_layer_set_enabled": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "navgpu_obstacle_set_observations": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Observation), C.c_int]),
+    "navgpu_inflation_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
+    "navgpu_inflation_set_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "navgpu_costmap_update_map": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, _i32p]),
+    "navgpu_costmap_update_map_async": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
+    "navgpu_costmap_synchronize": (C.c_int, [C.c_void_p]),
+    "navgpu_costmap_stream": (C.c_void_p, [C.c_void_p]),
+    "navgpu_costmap_get": (C.c_int, [C.c_void_p, _u8p]),
+    "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
+    "navgpu_costmap_set": (C.c_int, [C.c_void_p, _u8p]),
+    "navgpu_layer_get": (C.c_int, [C.c_void_p, C.c_int, _u8p]),
+    "navgpu_costmap_get_origin": (C.c_int, [C.c_void_p, _f64p]),
+    "navgpu_costmap_device_grid": (C.c_int, [C.c_void_p, _vpp, C.POINTER(C.c_uint32)]),
+    "navgpu_inflation_tables": (C.c_int, [C.c_void_p, C.c_int, _u8p, _f64p, C.c_int, _i32p]),
+    "navgpu_inflate_host": (C.c_int, [_u8p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                      C.c_uint32, C.c_int]),
+    "navgpu_merge_host": (C.c_int, [_u8p, _u8p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int]),
+    "navgpu_build_cost_table": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double, _u8p, _f64p, C.c_int, _i32p]),
+    "navgpu_dwa_default_config": (None, [C.POINTER(DwaConfig)]),
+    "navgpu_dwa_create": (C.c_int, [_vpp, C.POINTER(DwaConfig), C.c_uint32, C.c_uint32, C.c_double, C.c_int]),
+    "navgpu_dwa_destroy": (C.c_int, [C.c_void_p]),
+    "navgpu_dwa_reconfigure": (C.c_int, [C.c_void_p, C.POINTER(DwaConfig)]),
+    "navgpu_dwa_set_costmap": (C.c_int, [C.c_void_p, _u8p, C.c_double, C.c_double]),
+    "navgpu_dwa_set_costmap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_double]),
+    "navgpu_dwa_set_plan": (C.c_int, [C.c_void_p, _f64p, _f64p, C.c_int]),
+    "navgpu_dwa_reset_oscillation": (C.c_int, [C.c_void_p]),
+    "navgpu_dwa_get_oscillation_mask": (C.c_int, [C.c_void_p, _i32p]),
+    "navgpu_dwa_find_best_path": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.POINTER(DwaResult), _f64p,
+                                            C.c_int, _f64p, C.c_int]),
+    "navgpu_dwa_score_range": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.c_int64, C.c_int64, _f64p, _i64p,
+                                         _i64p]),
+    "navgpu_dwa_finish_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, _i64p, C.c_int, C.POINTER(DwaResult),
+                                            _f64p, C.c_int]),
+    "navgpu_dwa_get_grid": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
+    "navgpu_dwa_find_best_path_async": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int]),
+    "navgpu_dwa_synchronize": (C.c_int, [C.c_void_p]),
+    "navgpu_dwa_stream": (C.c_void_p, [C.c_void_p]),
+}
+
+
+class Costmap:
+    """Device-resident LayeredCostmap (navgpu_costmap_*)."""
+
+    def __init__(self, api, size_x, size_y, resolution, origin_x=0.0, origin_y=0.0, rolling=False,
+                 track_unknown=False, device=0):
+        self.api, self.lib = api, api.lib
+        self.size_x, self.size_y, self.resolution = size_x, size_y, resolution
+        h = C.c_void_p()
+        api.check(self.lib.navgpu_costmap_create(C.byref(h), size_x, size_y, resolution, origin_x, origin_y,
+                                                 int(rolling), int(track_unknown), device))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.navgpu_costmap_destroy(self.h)
+            self.h = None
+
+    def _layer(self, rc, out):
+        self.api.check(rc)
+        return int(out.value)
+
+    def add_grid_layer(self, policy):
+        out = C.c_int32()
+        return self._layer(self.lib.navgpu_costmap_add_grid_layer(self.h, policy, C.byref(out)), out)
+
+    def add_obstacle_layer(self, combination_method=1, footprint_clearing=True, max_obstacle_height=2.0):
+        out = C.c_int32()
+        return self._layer(self.lib.navgpu_costmap_add_obstacle_layer(self.h, combination_method,
+                                                                      int(footprint_clearing), max_obstacle_height,
+                                                                      C.byref(out)), out)
+
+    def add_inflation_layer(self, inflation_radius=0.55, cost_scaling_factor=10.0):
+        out = C.c_int32()
+        return self._layer(self.lib.navgpu_costmap_add_inflation_layer(self.h, inflation_radius, cost_scaling_factor,
+                                                                       C.byref(out)), out)
+
+    def set_footprint(self, xy):
+        a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        self.api.check(self.lib.navgpu_costmap_set_footprint(self.h, _p(a, _f64p), a.shape[0]))
+
+    def set_grid_layer(self, layer, data):
+        a = np.ascontiguousarray(data, dtype=np.uint8)
+        assert a.size == self.size_x * self.size_y
+        self.api.check(self.lib.navgpu_grid_layer_set(self.h, layer, _p(a, _u8p)))
+
+    def set_grid_layer_device(self, layer, dev_ptr, pitch):
+        self.api.check(self.lib.navgpu_grid_layer_set_device(self.h, layer, C.c_void_p(dev_ptr), pitch))
+
+    def set_grid_layer_occupancy(self, layer, occupancy, track_unknown=True, unknown_cost_value=255,
+                                 lethal_threshold=100, trinary=True):
+        a = np.ascontiguousarray(occupancy, dtype=np.int8)
+        assert a.size == self.size_x * self.size_y
+        self.api.check(self.lib.navgpu_grid_layer_set_occupancy(self.h, layer, _p(a, _i8p), int(track_unknown),
+                                                                unknown_cost_value, lethal_threshold, int(trinary)))
+
+    def touch_grid_layer(self, layer, x, y, w, h):
+        self.api.check(self.lib.navgpu_grid_layer_touch(self.h, layer, x, y, w, h))
+
+    def set_enabled(self, layer, enabled):
+        self.api.check(self.lib.navgpu_layer_set_enabled(self.h, layer, int(enabled)))
+
+    def set_observations(self, layer, observations):
+        arr = (Observation * max(1, len(observations)))()
+        keep = []
+        for k, o in enumerate(observations):
+            pts = np.ascontiguousarray(o["points"], dtype=np.float32).reshape(-1, 3)
+            keep.append(pts)
+            arr[k].origin_x, arr[k].origin_y, arr[k].origin_z = [float(v) for v in o["origin"]]
+            arr[k].obstacle_range = float(o.get("obstacle_range", 2.5))
+            arr[k].raytrace_range = float(o.get("raytrace_range", 3.0))
+            arr[k].xyz = _p(pts, C.POINTER(C.c_float))
+            arr[k].n_points = pts.shape[0]
+            arr[k].marking = int(o.get("marking", True))
+            arr[k].clearing = int(o.get("clearing", True))
+        self.api.check(self.lib.navgpu_obstacle_set_observations(self.h, layer, arr, len(observations)))
+
+    def set_inflation_params(self, layer, inflation_radius, cost_scaling_factor):
+        self.api.check(self.lib.navgpu_inflation_set_params(self.h, layer, inflation_radius, cost_scaling_factor))
+
+    def set_inflation_mode(self, layer, mode):
+        self.api.check(self.lib.navgpu_inflation_set_mode(self.h, layer, mode))
+
+    def update_map(self, x=0.0, y=0.0, yaw=0.0):
+        w = np.zeros(4, dtype=np.int32)
+        self.api.check(self.lib.navgpu_costmap_update_map(self.h, x, y, yaw, _p(w, _i32p)))
+        return tuple(int(v) for v in w)
+
+    def update_map_async(self, x=0.0, y=0.0, yaw=0.0):
+        self.api.check(self.lib.navgpu_costmap_update_map_async(self.h, x, y, yaw))
+
+    def synchronize(self):
+        self.api.check(self.lib.navgpu_costmap_synchronize(self.h))
+
+    def stream(self):
+        return self.lib.navgpu_costmap_stream(self.h)
+
+    def get(self):
+        out = np.empty((self.size_y, self.size_x), dtype=np.uint8)
+        self.api.check(self.lib.navgpu_costmap_get(self.h, _p(out, _u8p)))
+        return out
+
+    def get_window(self, x0, y0, xn, yn, out=None):
+        if out is None:
+            out = np.empty((yn - y0, xn - x0), dtype=np.uint8)
+        self.api.check(self.lib.navgpu_costmap_get_window(self.h, x0, y0, xn, yn, _p(out, _u8p)))
+        return out
+
+    def set(self, grid):
+        a = np.ascontiguousarray(grid, dtype=np.uint8)
+        self.api.check(self.lib.navgpu_costmap_set(self.h, _p(a, _u8p)))
+
+    def get_layer(self, layer):
+        out = np.empty((self.size_y, self.size_x), dtype=np.uint8)
+        self.api.check(self.lib.navgpu_layer_get(self.h, layer, _p(out, _u8p)))
+        return out
+
+    def origin(self):
+        o = np.zeros(2)
+        self.api.check(self.lib.navgpu_costmap_get_origin(self.h, _p(o, _f64p)))
+        return float(o[0]), float(o[1])
+
+    def device_grid(self):
+        ptr, pitch = C.c_void_p(), C.c_uint32()
+        self.api.check(self.lib.navgpu_costmap_device_grid(self.h, C.byref(ptr), C.byref(pitch)))
+        return ptr.value, int(pitch.value)
+
+    def inflation_tables(self, layer):
+        cap = 256 * 256
+        costs = np.zeros(cap, dtype=np.uint8)
+        dists = np.zeros(cap, dtype=np.float64)
+        R = C.c_int32()
+        self.api.check(self.lib.navgpu_inflation_tables(self.h, layer, _p(costs, _u8p), _p(dists, _f64p), cap,
+                                                        C.byref(R)))
+        n = R.value + 2
+        return R.value, costs[:n * n].reshape(n, n).copy(), dists[:n * n].reshape(n, n).copy()
+
+
+class Dwa:
+    """DWAPlanner-shaped scorer (navgpu_dwa_*)."""
+
+    def __init__(self, api, size_x, size_y, resolution, device=0, **overrides):
+        self.api, self.lib = api, api.lib
+        self.size_x, self.size_y, self.resolution = size_x, size_y, resolution
+        self.cfg = DwaConfig()
+        self.lib.navgpu_dwa_default_config(C.byref(self.cfg))
+        for k, v in overrides.items():
+            setattr(self.cfg, k, v)
+        h = C.c_void_p()
+        api.check(self.lib.navgpu_dwa_create(C.byref(h), C.byref(self.cfg), size_x, size_y, resolution, device))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.navgpu_dwa_destroy(self.h)
+            self.h = None
+
+    def set_costmap(self, grid, origin_x=0.0, origin_y=0.0):
+        a = np.ascontiguousarray(grid, dtype=np.uint8)
+        assert a.size == self.size_x * self.size_y
+        self.api.check(self.lib.navgpu_dwa_set_costmap(self.h, _p(a, _u8p), origin_x, origin_y))
+
+    def set_costmap_device(self, dev_ptr, pitch, origin_x, origin_y):
+        self.api.check(self.lib.navgpu_dwa_set_costmap_device(self.h, C.c_void_p(dev_ptr), pitch, origin_x, origin_y))
+
+    def set_plan(self, pose, plan_xy):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        a = np.ascontiguousarray(plan_xy, dtype=np.float64).reshape(-1, 2)
+        self.api.check(self.lib.navgpu_dwa_set_plan(self.h, _p(p, _f64p), _p(a, _f64p), a.shape[0]))
+
+    def reset_oscillation(self):
+        self.api.check(self.lib.navgpu_dwa_reset_oscillation(self.h))
+
+    def oscillation_mask(self):
+        m = C.c_int32()
+        self.api.check(self.lib.navgpu_dwa_get_oscillation_mask(self.h, C.byref(m)))
+        return int(m.value)
+
+    def find_best_path(self, pose, vel, footprint_xy, max_samples=1 << 21, max_points=4096, want_costs=True):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        res = DwaResult()
+        costs = np.full(max_samples if want_costs else 1, np.nan)
+        pts = np.zeros((max_points, 3))
+        self.api.check(self.lib.navgpu_dwa_find_best_path(
+            self.h, _p(p, _f64p), _p(v, _f64p), _p(f, _f64p), f.shape[0], C.byref(res),
+            _p(costs, _f64p) if want_costs else None, max_samples if want_costs else 0, _p(pts, _f64p), max_points))
+        return dict(ok=res.cost >= 0, cost=res.cost, xv=res.xv, yv=res.yv, thetav=res.thetav,
+                    best_index=res.best_index, n_samples=res.n_samples, n_scored=res.n_scored,
+                    costs=costs[:res.n_samples].copy() if want_costs else None, points=pts[:res.n_points].copy())
+
+    def find_best_path_async(self, pose, vel, footprint_xy):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        self.api.check(self.lib.navgpu_dwa_find_best_path_async(self.h, _p(p, _f64p), _p(v, _f64p), _p(f, _f64p),
+                                                                f.shape[0]))
+
+    def score_range(self, pose, vel, footprint_xy, begin, end):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        cost, idx, total = C.c_double(), C.c_int64(), C.c_int64()
+        self.api.check(self.lib.navgpu_dwa_score_range(self.h, _p(p, _f64p), _p(v, _f64p), _p(f, _f64p), f.shape[0],
+                                                       begin, end, C.byref(cost), C.byref(idx), C.byref(total)))
+        return cost.value, idx.value, total.value
+
+    def finish_sharded(self, pose, vel, costs, indices, max_points=4096):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        c = np.ascontiguousarray(costs, dtype=np.float64)
+        i = np.ascontiguousarray(indices, dtype=np.int64)
+        res = DwaResult()
+        pts = np.zeros((max_points, 3))
+        self.api.check(self.lib.navgpu_dwa_finish_sharded(self.h, _p(p, _f64p), _p(v, _f64p), _p(c, _f64p), _p(i, _i64p),
+                                                          c.size, C.byref(res), _p(pts, _f64p), max_points))
+        return dict(ok=res.cost >= 0, cost=res.cost, xv=res.xv, yv=res.yv, thetav=res.thetav,
+                    best_index=res.best_index, n_samples=res.n_samples, points=pts[:res.n_points].copy())
+
+    def synchronize(self):
+        self.api.check(self.lib.navgpu_dwa_synchronize(self.h))
+
+    def stream(self):
+        return self.lib.navgpu_dwa_stream(self.h)
+
+    def grid(self, which):
+        out = np.empty((self.size_y, self.size_x), dtype=np.float64)
+        self.api.check(self.lib.navgpu_dwa_get_grid(self.h, which, _p(out, _f64p)))
+        return out
+
+
+class Api:
+    name = "cuda"
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise NavGpuError(f"{path} is missing: run `python -m navigation_b200.build` (there is no CPU fallback)")
+        self.lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(self.lib, name)
+            f.restype = res
+            f.argtypes = args
+
+    def check(self, rc):
+        if rc != 0:
+            raise NavGpuError(f"navgpu error {rc}: {self.lib.navgpu_last_error().decode(errors='replace')}")
+
+    def device_count(self):
+        return self.lib.navgpu_device_count()
+
+    def launch_count(self):
+        return int(self.lib.navgpu_launch_count())
+
+    def costmap(self, *a, **k):
+        return Costmap(self, *a, **k)
+
+    def dwa(self, *a, **k):
+        return Dwa(self, *a, **k)
+
+    def build_cost_table(self, resolution, inscribed_radius, inflation_radius, cost_scaling_factor):
+        cap = 256 * 256
+        costs = np.zeros(cap, dtype=np.uint8)
+        dists = np.zeros(cap, dtype=np.float64)
+        R = C.c_int32()
+        self.check(self.lib.navgpu_build_cost_table(resolution, inscribed_radius, inflation_radius,
+                                                    cost_scaling_factor, _p(costs, _u8p), _p(dists, _f64p), cap,
+                                                    C.byref(R)))
+        n = R.value + 2
+        return R.value, costs[:n * n].reshape(n, n).copy(), dists[:n * n].reshape(n, n).copy()
+
+    def inflate_host(self, master, min_i, min_j, max_i, max_j, cost_table, radius, device=0):
+        assert master.dtype == np.uint8 and master.flags.c_contiguous
+        t = np.ascontiguousarray(cost_table, dtype=np.uint8)
+        self.check(self.lib.navgpu_inflate_host(_p(master, _u8p), master.shape[1], master.shape[0], min_i, min_j,
+                                                max_i, max_j, _p(t, _u8p), radius, device))
+        return master
+
+    def merge_host(self, master, layer, min_i, min_j, max_i, max_j, policy, device=0):
+        assert master.dtype == np.uint8 and master.flags.c_contiguous
+        a = np.ascontiguousarray(layer, dtype=np.uint8)
+        self.check(self.lib.navgpu_merge_host(_p(master, _u8p), _p(a, _u8p), master.shape[1], master.shape[0], min_i,
+                                              min_j, max_i, max_j, policy, device))
+        return master
+
+
+_api = None
+
+
+def load():
+    global _api
+    if _api is None:
+        _api = Api()
+    return _api

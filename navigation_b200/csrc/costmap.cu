@@ -1,0 +1,894 @@
+// costmap.cu -- Path A host side: the device-resident layered costmap behind the navgpu_costmap_* C ABI.
+//
+// Mirrors costmap_2d::LayeredCostmap + its Layer plugins (reference file:line cited per function).  Everything that
+// touches grid cells runs in the kernels of costmap_kernels.cuh; the host keeps only the scalar state the reference
+// keeps in its objects (origins, parameters, cached tables, flags) and sequences the kernels of one update cycle.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "costmap_kernels.cuh"
+
+namespace navgpu {
+
+struct Pt {
+  double x, y;
+};
+
+// calculateMinAndMaxDistances, src/footprint.cpp:41-67 (pure scalar geometry, evaluated once per footprint change)
+static double dist2d(double x0, double y0, double x1, double y1) { return hypot(x1 - x0, y1 - y0); }
+static double distance_to_line(double pX, double pY, double x0, double y0, double x1, double y1) {  // costmap_math.cpp:32-63
+  double A = pX - x0, B = pY - y0, C = x1 - x0, D = y1 - y0;
+  double dot = A * C + B * D, len_sq = C * C + D * D, param = dot / len_sq;
+  double xx, yy;
+  if (param < 0) { xx = x0; yy = y0; }
+  else if (param > 1) { xx = x1; yy = y1; }
+  else { xx = x0 + param * C; yy = y0 + param * D; }
+  return dist2d(pX, pY, xx, yy);
+}
+void footprint_radii(const std::vector<Pt>& fp, double& mn, double& mx) {
+  mn = std::numeric_limits<double>::max();
+  mx = 0.0;
+  if (fp.size() <= 2) return;
+  for (size_t i = 0; i < fp.size(); ++i) {
+    const Pt& a = fp[i];
+    const Pt& b = fp[(i + 1) % fp.size()];
+    double vd = dist2d(0, 0, a.x, a.y), ed = distance_to_line(0, 0, a.x, a.y, b.x, b.y);
+    mn = std::min(mn, std::min(vd, ed));
+    mx = std::max(mx, std::max(vd, ed));
+  }
+}
+
+// InflationLayer::computeCost / computeCaches (inflation_layer.h:114-129, plugins/inflation_layer.cpp:295-328):
+// evaluated on the host with the reference formula (hypot, exp of the host libm) so the tables are bit-identical.
+struct CostTables {
+  unsigned R = 0;
+  std::vector<uint8_t> costs;  // (R+2)^2, [dx][dy]
+  std::vector<double> dists;
+  std::vector<uint8_t> by_d2;  // R*R+1: cost by squared distance
+  bool ambiguous = false;      // two (dx,dy) with equal dx^2+dy^2 but different cached cost (never seen in practice)
+};
+static uint8_t compute_cost(double distance, double resolution, double inscribed, double weight) {
+  unsigned char cost = 0;
+  if (distance == 0) cost = kLethal;
+  else if (distance * resolution <= inscribed) cost = kInscribed;
+  else {
+    double euclidean_distance = distance * resolution;
+    double factor = exp(-1.0 * weight * (euclidean_distance - inscribed));
+    cost = (unsigned char)((kInscribed - 1) * factor);
+  }
+  return cost;
+}
+void build_tables(CostTables& t, unsigned R, double resolution, double inscribed, double weight) {
+  t.R = R;
+  const unsigned n = R + 2;
+  t.costs.assign(size_t(n) * n, 0);
+  t.dists.assign(size_t(n) * n, 0.0);
+  t.by_d2.assign(size_t(R) * R + 1, 0);
+  std::vector<int> seen(size_t(R) * R + 1, 0);
+  t.ambiguous = false;
+  for (unsigned i = 0; i < n; ++i)
+    for (unsigned j = 0; j < n; ++j) {
+      double d = hypot(i, j);
+      t.dists[i * n + j] = d;
+      uint8_t c = compute_cost(d, resolution, inscribed, weight);
+      t.costs[i * n + j] = c;
+      unsigned d2 = i * i + j * j;
+      // the reference enqueues a cell only while cached_distances_ <= cell_inflation_radius_ (:284-287)
+      if (d2 <= R * R) {
+        if (d > (double)R) t.ambiguous = true;
+        if (seen[d2] && t.by_d2[d2] != c) t.ambiguous = true;
+        seen[d2] = 1;
+        t.by_d2[d2] = c;
+      } else if (!(d > (double)R)) {
+        t.ambiguous = true;
+      }
+    }
+}
+
+static unsigned cell_distance(double world_dist, double resolution) {  // Costmap2D::cellDistance, costmap_2d.cpp:181-185
+  double cells_dist = std::max(0.0, ceil(world_dist / resolution));
+  return (unsigned int)cells_dist;
+}
+
+struct HostObs {
+  double ox, oy, oz, obstacle_range, raytrace_range;
+  int first_point, n_points;
+  bool marking, clearing;
+};
+
+struct Layer {
+  int kind = 0;  // 0 grid, 1 obstacle, 2 inflation
+  bool enabled = true;
+  // cost layers (CostmapLayer): own grid with own origin
+  uint8_t* grid[2] = {nullptr, nullptr};
+  int cur = 0;
+  double ox = 0, oy = 0;
+  uint8_t def = 0;
+  // grid layer
+  int policy = 0;
+  unsigned ux = 0, uy = 0, uw = 0, uh = 0;
+  bool updated = false;
+  // obstacle layer
+  int combination_method = 1;
+  bool footprint_clearing = true;
+  double max_obstacle_height = 2.0;
+  std::vector<HostObs> obs;
+  DevObs* d_clear = nullptr;
+  DevObs* d_mark = nullptr;
+  float* d_xyz = nullptr;
+  size_t xyz_capacity = 0, obs_capacity = 0;
+  int n_clear = 0, n_mark = 0, total_rays = 0, total_marks = 0;
+  std::vector<Pt> transformed_footprint;
+  // inflation layer
+  double radius = 0, weight = 0, inscribed = 0;
+  bool need_reinflation = false;
+  int mode = 0;
+  CostTables tables;
+  uint8_t* d_cost_d2 = nullptr;
+  size_t cost_d2_capacity = 0;
+  bool tables_dirty = true;
+};
+
+}  // namespace navgpu
+
+using namespace navgpu;
+
+struct navgpu_costmap {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  unsigned sx = 0, sy = 0, pitch = 0;
+  double res = 0, ox = 0, oy = 0;
+  bool rolling = false, track_unknown = false;
+  uint8_t def = 0;
+  uint8_t* master[2] = {nullptr, nullptr};
+  int cur = 0;
+  std::vector<Layer> layers;
+  std::vector<Pt> footprint;
+  double inscribed = 0, circumscribed = 0;
+  DevBox* d_boxes = nullptr;
+  InflationBoundsState* d_infl = nullptr;
+  DevWindow* d_win = nullptr;
+  DevWindow* h_win = nullptr;  // pinned
+  int win[4] = {0, 0, 0, 0};
+  bool poly_attr_set = false;
+
+  size_t bytes() const { return size_t(pitch) * sy; }
+  Geom geom(double gox, double goy) const { return Geom{sx, sy, pitch, res, gox, goy}; }
+  double size_m_x() const { return (sx - 1 + 0.5) * res; }  // Costmap2D::getSizeInMetersX, costmap_2d.cpp:440-443
+  double size_m_y() const { return (sy - 1 + 0.5) * res; }
+};
+
+namespace {
+
+int use_device(navgpu_costmap* h) {
+  NAVGPU_CUDA(cudaSetDevice(h->device));
+  return NAVGPU_OK;
+}
+
+int alloc_grid(navgpu_costmap* h, uint8_t** p, uint8_t value) {
+  NAVGPU_CUDA(cudaMalloc(p, h->bytes()));
+  NAVGPU_CUDA(cudaMemsetAsync(*p, value, h->bytes(), h->stream));
+  return NAVGPU_OK;
+}
+
+// host mirror of Costmap2D::updateOrigin's scalar part (costmap_2d.cpp:264-275, 301-302); the cell shift runs on the
+// device (k_shift_grid) into the other buffer of the ping-pong pair.
+int roll_grid(navgpu_costmap* h, uint8_t* grid[2], int& cur, double& gox, double& goy, uint8_t def, double new_ox,
+              double new_oy) {
+  int cell_ox = int((new_ox - gox) / h->res), cell_oy = int((new_oy - goy) / h->res);
+  double new_grid_ox = gox + cell_ox * h->res, new_grid_oy = goy + cell_oy * h->res;
+  if (!grid[cur ^ 1]) NAVGPU_CUDA(cudaMalloc(&grid[cur ^ 1], h->bytes()));
+  dim3 block(256), g((h->pitch + 255) / 256, h->sy);
+  k_shift_grid<<<g, block, 0, h->stream>>>(grid[cur], grid[cur ^ 1], h->sx, h->sy, h->pitch, cell_ox, cell_oy, def);
+  NAVGPU_LAUNCHED(1);
+  cur ^= 1;
+  gox = new_grid_ox;
+  goy = new_grid_oy;
+  return NAVGPU_OK;
+}
+
+int upload_tables(navgpu_costmap* h, Layer& L) {
+  if (!L.tables_dirty) return NAVGPU_OK;
+  const unsigned R = cell_distance(L.radius, h->res);
+  build_tables(L.tables, R, h->res, L.inscribed, L.weight);
+  if (L.tables.ambiguous)
+    return fail(NAVGPU_ERR_UNSUPPORTED, "inflation cost table is not a function of squared distance for R=%u", R);
+  if (R > 254) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %u > 254", R);
+  size_t n = L.tables.by_d2.size();
+  if (n > L.cost_d2_capacity) {
+    if (L.d_cost_d2) cudaFree(L.d_cost_d2);
+    NAVGPU_CUDA(cudaMalloc(&L.d_cost_d2, n));
+    L.cost_d2_capacity = n;
+  }
+  NAVGPU_CUDA(cudaMemcpyAsync(L.d_cost_d2, L.tables.by_d2.data(), n, cudaMemcpyHostToDevice, h->stream));
+  // the table lives in pageable host memory owned by this handle; make the copy complete before it can change
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  L.tables_dirty = false;
+  return NAVGPU_OK;
+}
+
+int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2) {
+  UpdateArgs a;
+  a.master = h->master[h->cur];
+  a.sx = h->sx; a.sy = h->sy; a.pitch = h->pitch;
+  a.def = h->def;
+  a.do_reset = do_reset;
+  a.win = h->d_win;
+  a.ml = ml;
+  a.R = R;
+  a.cost_d2 = cost_d2;
+  size_t smem = update_costs_smem(R);
+  if (smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %d needs %zu B of shared memory", R, smem);
+  if (smem > 48 * 1024)
+    NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((h->sx + kTX - 1) / kTX, (h->sy + kTY - 1) / kTY);
+  k_update_costs<<<grid, kUpdateThreads, smem, h->stream>>>(a);
+  NAVGPU_LAUNCHED(1);
+  return NAVGPU_OK;
+}
+
+// One LayeredCostmap::updateMap cycle (layered_costmap.cpp:79-150), enqueued on the handle's stream.
+int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
+  NAVGPU_TRY(use_device(h));
+  // rolling window: master origin follows the robot (:86-91)
+  if (h->rolling)
+    NAVGPU_TRY(roll_grid(h, h->master, h->cur, h->ox, h->oy, h->def, rx - h->size_m_x() / 2, ry - h->size_m_y() / 2));
+  if (h->layers.empty()) return NAVGPU_OK;
+
+  // ---- updateBounds of every plugin, in order (:96-115)
+  BoundsArgs ba;
+  ba.n_layers = (int)h->layers.size();
+  ba.master = h->geom(h->ox, h->oy);
+  for (size_t li = 0; li < h->layers.size(); ++li) {
+    Layer& L = h->layers[li];
+    BoundsLayer& B = ba.layer[li];
+    B.kind = L.kind == 2 ? 2 : 0;
+    B.flag = 0;
+    B.hx0 = B.hy0 = B.hx1 = B.hy1 = 0;
+    if (L.kind == 0) {  // StaticLayer::updateBounds, non-rolling semantics (static_layer.cpp:263-285)
+      if (!h->rolling && !L.updated) continue;
+      B.flag = 1;
+      B.hx0 = L.ox + (L.ux + 0.5) * h->res;  // mapToWorld, costmap_2d.cpp:202-206
+      B.hy0 = L.oy + (L.uy + 0.5) * h->res;
+      B.hx1 = L.ox + (L.ux + L.uw + 0.5) * h->res;
+      B.hy1 = L.oy + (L.uy + L.uh + 0.5) * h->res;
+      L.updated = false;
+    } else if (L.kind == 1) {  // ObstacleLayer::updateBounds (obstacle_layer.cpp:340-413)
+      if (h->rolling)
+        NAVGPU_TRY(roll_grid(h, L.grid, L.cur, L.ox, L.oy, L.def, rx - h->size_m_x() / 2, ry - h->size_m_y() / 2));
+      if (!L.enabled) continue;
+      Geom g = h->geom(L.ox, L.oy);
+      double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
+      // raytraceFreespace touches the sensor origin once per clearing observation whose origin is on the map
+      // (:504-521); origins and geometry are host-side scalars, the per-ray end points are touched on the device
+      for (const HostObs& o : L.obs) {
+        if (!o.clearing) continue;
+        if (o.ox < L.ox || o.oy < L.oy) continue;
+        unsigned mx = (int)((o.ox - L.ox) / h->res), my = (int)((o.oy - L.oy) / h->res);
+        if (!(mx < h->sx && my < h->sy)) continue;
+        bx0 = std::min(o.ox, bx0); by0 = std::min(o.oy, by0);
+        bx1 = std::max(o.ox, bx1); by1 = std::max(o.oy, by1);
+      }
+      if (L.total_rays > 0) {  // all clearing before any marking (:362-365 then :368)
+        int warps_per_block = 8;
+        int blocks = (L.total_rays + warps_per_block - 1) / warps_per_block;
+        k_raytrace_clear<<<blocks, warps_per_block * 32, 0, h->stream>>>(L.grid[L.cur], g, L.d_clear, L.n_clear, L.d_xyz,
+                                                                        L.total_rays, h->d_boxes + li);
+        NAVGPU_LAUNCHED(1);
+      }
+      if (L.total_marks > 0) {
+        int blocks = (L.total_marks + 255) / 256;
+        k_mark_points<<<blocks, 256, 0, h->stream>>>(L.grid[L.cur], g, L.d_mark, L.n_mark, L.d_xyz, L.total_marks,
+                                                     L.max_obstacle_height, h->d_boxes + li);
+        NAVGPU_LAUNCHED(1);
+      }
+      if (L.footprint_clearing) {  // updateFootprint (:415-425) with transformFootprint (footprint.cpp:106-120)
+        L.transformed_footprint.clear();
+        double cos_th = cos(ryaw), sin_th = sin(ryaw);
+        for (const Pt& p : h->footprint)
+          L.transformed_footprint.push_back(Pt{rx + (p.x * cos_th - p.y * sin_th), ry + (p.x * sin_th + p.y * cos_th)});
+        for (const Pt& p : L.transformed_footprint) {
+          bx0 = std::min(p.x, bx0); by0 = std::min(p.y, by0);
+          bx1 = std::max(p.x, bx1); by1 = std::max(p.y, by1);
+        }
+      }
+      if (bx1 >= bx0) {
+        B.flag = 1;
+        B.hx0 = bx0; B.hy0 = by0; B.hx1 = bx1; B.hy1 = by1;
+      }
+    } else {  // InflationLayer::updateBounds runs on the device (needs the device-accumulated bounds)
+      B.flag = L.need_reinflation ? 1 : 0;
+      B.hx0 = L.radius;
+      L.need_reinflation = false;
+    }
+  }
+  k_finalize_bounds<<<1, 32, 0, h->stream>>>(ba, h->d_boxes, h->d_infl, h->d_win);
+  NAVGPU_LAUNCHED(1);
+
+  // ---- resetMap + updateCosts of every plugin, in order (:137-142), fused into as few sweeps as possible:
+  // consecutive cost layers merge in one pass, an inflation layer closes the pass.
+  MergeLayers ml;
+  ml.n = 0;
+  int do_reset = 1;
+  bool pending = true;  // the reset itself must happen even with no enabled layer
+  for (size_t li = 0; li < h->layers.size(); ++li) {
+    Layer& L = h->layers[li];
+    if (L.kind == 1 && L.enabled && L.footprint_clearing) {
+      // setConvexPolygonCost(transformed_footprint_, FREE_SPACE) on the layer's own grid (obstacle_layer.cpp:432-435)
+      PolyArgs pa;
+      pa.n = 0;
+      bool ok = L.transformed_footprint.size() <= 32;
+      if (L.transformed_footprint.size() > 32) return fail(NAVGPU_ERR_UNSUPPORTED, "footprint with more than 32 vertices");
+      long long outline = 0;
+      for (const Pt& p : L.transformed_footprint) {  // worldToMap, costmap_2d.cpp:208-220
+        if (p.x < L.ox || p.y < L.oy) { ok = false; break; }
+        unsigned mx = (int)((p.x - L.ox) / h->res), my = (int)((p.y - L.oy) / h->res);
+        if (!(mx < h->sx && my < h->sy)) { ok = false; break; }
+        pa.vx[pa.n] = (int)mx;
+        pa.vy[pa.n] = (int)my;
+        ++pa.n;
+      }
+      if (ok && pa.n >= 3) {
+        long long minx = pa.vx[0], maxx = pa.vx[0], miny = pa.vy[0], maxy = pa.vy[0];
+        for (int k = 0; k < pa.n; ++k) {
+          int k1 = (k + 1) % pa.n;
+          outline += std::max(std::abs(pa.vx[k1] - pa.vx[k]), std::abs(pa.vy[k1] - pa.vy[k])) + 1;
+          minx = std::min<long long>(minx, pa.vx[k]); maxx = std::max<long long>(maxx, pa.vx[k]);
+          miny = std::min<long long>(miny, pa.vy[k]); maxy = std::max<long long>(maxy, pa.vy[k]);
+        }
+        if (outline + (maxx - minx + 1) * (maxy - miny + 1) > kPolyMaxCells || h->sx > 65535 || h->sy > 65535)
+          return fail(NAVGPU_ERR_UNSUPPORTED, "footprint polygon covers too many cells for the device rasteriser");
+        size_t smem = 2 * kPolyMaxCells * sizeof(uint32_t);
+        if (!h->poly_attr_set) {
+          NAVGPU_CUDA(cudaFuncSetAttribute(k_polygon_clear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          h->poly_attr_set = true;
+        }
+        k_polygon_clear<<<1, 256, smem, h->stream>>>(L.grid[L.cur], h->pitch, pa, kFree);
+        NAVGPU_LAUNCHED(1);
+      }
+    }
+    if (L.kind == 0 || L.kind == 1) {
+      if (!L.enabled) continue;
+      int policy = L.kind == 0 ? L.policy
+                               : (L.combination_method == 0 ? NAVGPU_OVERWRITE
+                                                            : (L.combination_method == 1 ? NAVGPU_MAX : NAVGPU_NOTHING));
+      if (policy == NAVGPU_NOTHING) continue;
+      ml.grid[ml.n] = L.grid[L.cur];
+      ml.policy[ml.n] = policy;
+      ++ml.n;
+      pending = true;
+    } else {
+      if (!L.enabled) continue;
+      NAVGPU_TRY(upload_tables(h, L));
+      if (L.tables.R == 0) continue;  // the reference dereferences NULL tables here; we make it a no-op
+      if (!do_reset && ml.n > 0) {    // merges that read what a previous inflation wrote: keep them a separate pass
+        NAVGPU_TRY(launch_update(h, ml, 0, 0, nullptr));
+        ml.n = 0;
+      }
+      NAVGPU_TRY(launch_update(h, ml, do_reset, (int)L.tables.R, L.d_cost_d2));
+      ml.n = 0;
+      do_reset = 0;
+      pending = false;
+    }
+  }
+  if (pending) NAVGPU_TRY(launch_update(h, ml, do_reset, 0, nullptr));
+  return NAVGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* navgpu_last_error(void) { return last_error_ref().c_str(); }
+
+int navgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+uint64_t navgpu_launch_count(void) { return launch_counter().load(); }
+
+int navgpu_costmap_create(navgpu_costmap** out, uint32_t size_x, uint32_t size_y, double resolution, double origin_x,
+                          double origin_y, int rolling_window, int track_unknown, int device) {
+  if (!out || size_x == 0 || size_y == 0 || !(resolution > 0)) return fail(NAVGPU_ERR_INVALID, "bad costmap geometry");
+  if (navgpu_device_count() <= device) return fail(NAVGPU_ERR_CUDA, "no CUDA device %d (libnavgpu has no CPU fallback)", device);
+  std::unique_ptr<navgpu_costmap> h(new navgpu_costmap);
+  h->device = device;
+  NAVGPU_CUDA(cudaSetDevice(device));
+  NAVGPU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->sx = size_x; h->sy = size_y; h->pitch = grid_pitch(size_x);
+  h->res = resolution; h->ox = origin_x; h->oy = origin_y;
+  h->rolling = rolling_window != 0;
+  h->track_unknown = track_unknown != 0;
+  h->def = track_unknown ? kNoInfo : kFree;  // layered_costmap.cpp:53-56
+  NAVGPU_TRY(alloc_grid(h.get(), &h->master[0], h->def));
+  NAVGPU_CUDA(cudaMalloc(&h->d_boxes, sizeof(DevBox) * kMaxLayers));
+  NAVGPU_CUDA(cudaMalloc(&h->d_infl, sizeof(InflationBoundsState) * kMaxLayers));
+  NAVGPU_CUDA(cudaMalloc(&h->d_win, sizeof(DevWindow)));
+  NAVGPU_CUDA(cudaMallocHost(&h->h_win, sizeof(DevWindow)));
+  DevBox boxes[kMaxLayers];
+  InflationBoundsState infl[kMaxLayers];
+  for (int i = 0; i < kMaxLayers; ++i) {
+    boxes[i] = DevBox{~0ull, ~0ull, 0ull, 0ull};
+    const double fm = std::numeric_limits<float>::max();  // inflation_layer.cpp:63-66
+    infl[i] = InflationBoundsState{-fm, -fm, fm, fm};
+  }
+  NAVGPU_CUDA(cudaMemcpy(h->d_boxes, boxes, sizeof(boxes), cudaMemcpyHostToDevice));
+  NAVGPU_CUDA(cudaMemcpy(h->d_infl, infl, sizeof(infl), cudaMemcpyHostToDevice));
+  NAVGPU_CUDA(cudaMemset(h->d_win, 0, sizeof(DevWindow)));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  *out = h.release();
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_destroy(navgpu_costmap* h) {
+  if (!h) return NAVGPU_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (Layer& L : h->layers) {
+    cudaFree(L.grid[0]); cudaFree(L.grid[1]);
+    cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2);
+  }
+  cudaFree(h->master[0]); cudaFree(h->master[1]);
+  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win);
+  cudaFreeHost(h->h_win);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return NAVGPU_OK;
+}
+
+static int add_cost_layer(navgpu_costmap* h, Layer& L) {
+  // CostmapLayer::matchSize (costmap_layer.cpp:14-19): same geometry as the master, filled with the default value
+  L.def = h->track_unknown ? kNoInfo : kFree;
+  L.ox = h->ox;
+  L.oy = h->oy;
+  NAVGPU_TRY(alloc_grid(h, &L.grid[0], L.def));
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_add_grid_layer(navgpu_costmap* h, int policy, int* layer_out) {
+  if (!h || policy < 0 || policy > NAVGPU_NOTHING) return fail(NAVGPU_ERR_INVALID, "bad grid layer arguments");
+  if (h->layers.size() >= (size_t)kMaxLayers) return fail(NAVGPU_ERR_UNSUPPORTED, "more than %d layers", kMaxLayers);
+  NAVGPU_TRY(use_device(h));
+  Layer L;
+  L.kind = 0;
+  L.policy = policy;
+  NAVGPU_TRY(add_cost_layer(h, L));
+  h->layers.push_back(L);
+  if (layer_out) *layer_out = (int)h->layers.size() - 1;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_add_obstacle_layer(navgpu_costmap* h, int combination_method, int footprint_clearing,
+                                      double max_obstacle_height, int* layer_out) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  if (h->layers.size() >= (size_t)kMaxLayers) return fail(NAVGPU_ERR_UNSUPPORTED, "more than %d layers", kMaxLayers);
+  NAVGPU_TRY(use_device(h));
+  Layer L;
+  L.kind = 1;
+  L.combination_method = combination_method;
+  L.footprint_clearing = footprint_clearing != 0;
+  L.max_obstacle_height = max_obstacle_height;
+  NAVGPU_TRY(add_cost_layer(h, L));
+  h->layers.push_back(L);
+  if (layer_out) *layer_out = (int)h->layers.size() - 1;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_add_inflation_layer(navgpu_costmap* h, double inflation_radius, double cost_scaling_factor,
+                                       int* layer_out) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  if (h->layers.size() >= (size_t)kMaxLayers) return fail(NAVGPU_ERR_UNSUPPORTED, "more than %d layers", kMaxLayers);
+  Layer L;
+  L.kind = 2;
+  // onInitialize: the dynamic_reconfigure server first delivers the defaults (0.55, 10), which differ from the
+  // constructor's zeros and therefore set need_reinflation_ (inflation_layer.cpp:71-108, 356-370)
+  L.radius = inflation_radius;
+  L.weight = cost_scaling_factor;
+  L.inscribed = h->inscribed;
+  L.need_reinflation = true;
+  L.tables_dirty = true;
+  h->layers.push_back(L);
+  if (layer_out) *layer_out = (int)h->layers.size() - 1;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_set_footprint(navgpu_costmap* h, const double* xy, int n) {  // layered_costmap.cpp:163-173
+  if (!h || n < 0 || (n > 0 && !xy)) return fail(NAVGPU_ERR_INVALID, "bad footprint");
+  h->footprint.clear();
+  for (int i = 0; i < n; ++i) h->footprint.push_back(Pt{xy[2 * i], xy[2 * i + 1]});
+  footprint_radii(h->footprint, h->inscribed, h->circumscribed);
+  for (Layer& L : h->layers)
+    if (L.kind == 2) {  // InflationLayer::onFootprintChanged (:160-170)
+      L.inscribed = h->inscribed;
+      L.need_reinflation = true;
+      L.tables_dirty = true;
+    }
+  return NAVGPU_OK;
+}
+
+static Layer* get_layer(navgpu_costmap* h, int layer, int kind) {
+  if (!h || layer < 0 || layer >= (int)h->layers.size()) return nullptr;
+  Layer* L = &h->layers[layer];
+  if (kind >= 0 && L->kind != kind) return nullptr;
+  return L;
+}
+
+static void mark_whole(navgpu_costmap* h, Layer* L) {
+  L->ux = L->uy = 0;
+  L->uw = h->sx;
+  L->uh = h->sy;
+  L->updated = true;
+}
+
+int navgpu_grid_layer_set(navgpu_costmap* h, int layer, const uint8_t* host_data) {
+  Layer* L = get_layer(h, layer, 0);
+  if (!L || !host_data) return fail(NAVGPU_ERR_INVALID, "bad grid layer");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(L->grid[L->cur], h->pitch, host_data, h->sx, h->sx, h->sy, cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  mark_whole(h, L);
+  return NAVGPU_OK;
+}
+
+int navgpu_grid_layer_set_device(navgpu_costmap* h, int layer, const uint8_t* dev_data, uint32_t pitch) {
+  Layer* L = get_layer(h, layer, 0);
+  if (!L || !dev_data || pitch < h->sx) return fail(NAVGPU_ERR_INVALID, "bad grid layer");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(L->grid[L->cur], h->pitch, dev_data, pitch, h->sx, h->sy, cudaMemcpyDeviceToDevice, h->stream));
+  mark_whole(h, L);
+  return NAVGPU_OK;
+}
+
+int navgpu_grid_layer_set_occupancy(navgpu_costmap* h, int layer, const int8_t* host_occupancy, int track_unknown,
+                                    uint8_t unknown_cost_value, uint8_t lethal_threshold, int trinary) {
+  Layer* L = get_layer(h, layer, 0);
+  if (!L || !host_occupancy) return fail(NAVGPU_ERR_INVALID, "bad grid layer");
+  NAVGPU_TRY(use_device(h));
+  int8_t* d_occ = nullptr;
+  size_t n = size_t(h->sx) * h->sy;
+  NAVGPU_CUDA(cudaMallocAsync(&d_occ, n, h->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(d_occ, host_occupancy, n, cudaMemcpyHostToDevice, h->stream));
+  dim3 block(256), grid((h->sx + 255) / 256, h->sy);
+  k_interpret_occupancy<<<grid, block, 0, h->stream>>>(d_occ, L->grid[L->cur], h->sx, h->sy, h->pitch, track_unknown,
+                                                       unknown_cost_value, lethal_threshold, trinary);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaFreeAsync(d_occ, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  mark_whole(h, L);
+  return NAVGPU_OK;
+}
+
+int navgpu_grid_layer_touch(navgpu_costmap* h, int layer, uint32_t x, uint32_t y, uint32_t w, uint32_t hgt) {
+  Layer* L = get_layer(h, layer, 0);
+  if (!L) return fail(NAVGPU_ERR_INVALID, "bad grid layer");
+  L->ux = x; L->uy = y; L->uw = w; L->uh = hgt;
+  L->updated = true;
+  return NAVGPU_OK;
+}
+
+int navgpu_layer_set_enabled(navgpu_costmap* h, int layer, int enabled) {
+  Layer* L = get_layer(h, layer, -1);
+  if (!L) return fail(NAVGPU_ERR_INVALID, "bad layer");
+  if (L->kind == 2 && L->enabled != (enabled != 0)) L->need_reinflation = true;  // reconfigureCB :104-107
+  L->enabled = enabled != 0;
+  return NAVGPU_OK;
+}
+
+int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_observation* obs, int n_obs) {
+  Layer* L = get_layer(h, layer, 1);
+  if (!L || n_obs < 0 || (n_obs > 0 && !obs)) return fail(NAVGPU_ERR_INVALID, "bad obstacle layer / observations");
+  NAVGPU_TRY(use_device(h));
+  std::vector<float> xyz;
+  std::vector<DevObs> clear, mark;
+  L->obs.clear();
+  int rays = 0, marks = 0;
+  for (int i = 0; i < n_obs; ++i) {
+    if (obs[i].n_points < 0 || (obs[i].n_points > 0 && !obs[i].xyz)) return fail(NAVGPU_ERR_INVALID, "bad observation %d", i);
+    DevObs d;
+    d.ox = obs[i].origin_x; d.oy = obs[i].origin_y; d.oz = obs[i].origin_z;
+    d.obstacle_range = obs[i].obstacle_range;
+    d.raytrace_range = obs[i].raytrace_range;
+    d.first_point = (int)(xyz.size() / 3);
+    d.n_points = obs[i].n_points;
+    d.flags = (obs[i].marking ? 1 : 0) | (obs[i].clearing ? 2 : 0);
+    L->obs.push_back(HostObs{d.ox, d.oy, d.oz, d.obstacle_range, d.raytrace_range, d.first_point, d.n_points,
+                             obs[i].marking != 0, obs[i].clearing != 0});
+    xyz.insert(xyz.end(), obs[i].xyz, obs[i].xyz + 3 * size_t(obs[i].n_points));
+    if (obs[i].clearing && d.n_points > 0) {
+      d.first_ray = rays;
+      rays += d.n_points;
+      clear.push_back(d);
+    }
+    if (obs[i].marking && d.n_points > 0) {
+      d.first_ray = marks;
+      marks += d.n_points;
+      mark.push_back(d);
+    }
+  }
+  if (xyz.size() > L->xyz_capacity) {
+    if (L->d_xyz) cudaFree(L->d_xyz);
+    NAVGPU_CUDA(cudaMalloc(&L->d_xyz, xyz.size() * sizeof(float)));
+    L->xyz_capacity = xyz.size();
+  }
+  size_t need = std::max(clear.size(), mark.size());
+  if (need > L->obs_capacity) {
+    if (L->d_clear) cudaFree(L->d_clear);
+    if (L->d_mark) cudaFree(L->d_mark);
+    NAVGPU_CUDA(cudaMalloc(&L->d_clear, need * sizeof(DevObs)));
+    NAVGPU_CUDA(cudaMalloc(&L->d_mark, need * sizeof(DevObs)));
+    L->obs_capacity = need;
+  }
+  if (!xyz.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_xyz, xyz.data(), xyz.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (!clear.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_clear, clear.data(), clear.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
+  if (!mark.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_mark, mark.data(), mark.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  L->n_clear = (int)clear.size();
+  L->n_mark = (int)mark.size();
+  L->total_rays = rays;
+  L->total_marks = marks;
+  return NAVGPU_OK;
+}
+
+int navgpu_inflation_set_params(navgpu_costmap* h, int layer, double inflation_radius, double cost_scaling_factor) {
+  Layer* L = get_layer(h, layer, 2);
+  if (!L) return fail(NAVGPU_ERR_INVALID, "bad inflation layer");
+  if (L->weight != cost_scaling_factor || L->radius != inflation_radius) {  // inflation_layer.cpp:356-370
+    L->radius = inflation_radius;
+    L->weight = cost_scaling_factor;
+    L->need_reinflation = true;
+    L->tables_dirty = true;
+  }
+  return NAVGPU_OK;
+}
+
+int navgpu_inflation_set_mode(navgpu_costmap* h, int layer, int mode) {
+  Layer* L = get_layer(h, layer, 2);
+  if (!L || mode < 0 || mode > 1) return fail(NAVGPU_ERR_INVALID, "bad inflation layer / mode");
+  if (mode == 1) return fail(NAVGPU_ERR_UNSUPPORTED, "propagation mode is not built yet");
+  L->mode = mode;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_update_map_async(navgpu_costmap* h, double rx, double ry, double ryaw) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  NAVGPU_TRY(enqueue_update(h, rx, ry, ryaw));
+  NAVGPU_CUDA(cudaGetLastError());
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_synchronize(navgpu_costmap* h) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_update_map(navgpu_costmap* h, double rx, double ry, double ryaw, int32_t window_out[4]) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  NAVGPU_TRY(enqueue_update(h, rx, ry, ryaw));
+  NAVGPU_CUDA(cudaGetLastError());
+  if (!h->layers.empty())
+    NAVGPU_CUDA(cudaMemcpyAsync(h->h_win, h->d_win, sizeof(DevWindow), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  if (!h->layers.empty()) {
+    h->win[0] = h->h_win->x0; h->win[1] = h->h_win->xn; h->win[2] = h->h_win->y0; h->win[3] = h->h_win->yn;
+  }
+  if (window_out)
+    for (int i = 0; i < 4; ++i) window_out[i] = h->win[i];
+  return NAVGPU_OK;
+}
+
+void* navgpu_costmap_stream(navgpu_costmap* h) { return h ? (void*)h->stream : nullptr; }
+
+int navgpu_costmap_get_window(navgpu_costmap* h, int x0, int y0, int xn, int yn, uint8_t* host_out) {
+  if (!h || !host_out || x0 < 0 || y0 < 0 || xn > (int)h->sx || yn > (int)h->sy || xn < x0 || yn < y0)
+    return fail(NAVGPU_ERR_INVALID, "bad window");
+  if (xn == x0 || yn == y0) return NAVGPU_OK;
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(host_out, xn - x0, h->master[h->cur] + size_t(y0) * h->pitch + x0, h->pitch, xn - x0,
+                                yn - y0, cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_get(navgpu_costmap* h, uint8_t* host_out) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  return navgpu_costmap_get_window(h, 0, 0, h->sx, h->sy, host_out);
+}
+
+int navgpu_costmap_set(navgpu_costmap* h, const uint8_t* host_in) {
+  if (!h || !host_in) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(h->master[h->cur], h->pitch, host_in, h->sx, h->sx, h->sy, cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+int navgpu_layer_get(navgpu_costmap* h, int layer, uint8_t* host_out) {
+  Layer* L = get_layer(h, layer, -1);
+  if (!L || !host_out || L->kind == 2) return fail(NAVGPU_ERR_INVALID, "layer has no grid");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(host_out, h->sx, L->grid[L->cur], h->pitch, h->sx, h->sy, cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_get_origin(navgpu_costmap* h, double out[2]) {
+  if (!h || !out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  out[0] = h->ox;
+  out[1] = h->oy;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_device_grid(navgpu_costmap* h, const uint8_t** dev_ptr, uint32_t* pitch) {
+  if (!h || !dev_ptr || !pitch) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  *dev_ptr = h->master[h->cur];
+  *pitch = h->pitch;
+  return NAVGPU_OK;
+}
+
+int navgpu_inflation_tables(navgpu_costmap* h, int layer, uint8_t* costs_out, double* dists_out, int capacity,
+                            int* radius_out) {
+  Layer* L = get_layer(h, layer, 2);
+  if (!L || !radius_out) return fail(NAVGPU_ERR_INVALID, "bad inflation layer");
+  CostTables t;
+  build_tables(t, cell_distance(L->radius, h->res), h->res, L->inscribed, L->weight);
+  *radius_out = (int)t.R;
+  int n = (int)t.R + 2;
+  if (n * n > capacity) return fail(NAVGPU_ERR_CAPACITY, "table needs %d entries", n * n);
+  if (costs_out) memcpy(costs_out, t.costs.data(), size_t(n) * n);
+  if (dists_out) memcpy(dists_out, t.dists.data(), size_t(n) * n * sizeof(double));
+  return NAVGPU_OK;
+}
+
+int navgpu_build_cost_table(double resolution, double inscribed_radius, double inflation_radius,
+                            double cost_scaling_factor, uint8_t* costs_out, double* dists_out, int capacity,
+                            int* radius_out) {
+  if (!(resolution > 0) || !radius_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  CostTables t;
+  build_tables(t, cell_distance(inflation_radius, resolution), resolution, inscribed_radius, cost_scaling_factor);
+  *radius_out = (int)t.R;
+  int n = (int)t.R + 2;
+  if (n * n > capacity) return fail(NAVGPU_ERR_CAPACITY, "table needs %d entries", n * n);
+  if (costs_out) memcpy(costs_out, t.costs.data(), size_t(n) * n);
+  if (dists_out) memcpy(dists_out, t.dists.data(), size_t(n) * n * sizeof(double));
+  return NAVGPU_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stateless plugin-seam calls on a HOST master grid (include/navgpu.h): the body of a costmap_2d::Layer::updateCosts
+// override.  Rows [min_j - 2R, max_j + 2R) are staged to the device (the only rows the reference can read or write,
+// inflation_layer.cpp:203-264), processed by the same k_update_costs kernel, and copied back.
+namespace {
+
+struct SeamContext {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  uint8_t* d_master = nullptr;
+  uint8_t* d_layer = nullptr;
+  uint8_t* d_table = nullptr;
+  DevWindow* d_win = nullptr;
+  size_t cap_master = 0, cap_layer = 0, cap_table = 0;
+};
+
+int seam_context(int device, SeamContext** out) {
+  static thread_local SeamContext ctx[16];
+  if (device < 0 || device >= 16) return fail(NAVGPU_ERR_INVALID, "bad device %d", device);
+  if (navgpu_device_count() <= device) return fail(NAVGPU_ERR_CUDA, "no CUDA device %d (libnavgpu has no CPU fallback)", device);
+  SeamContext& c = ctx[device];
+  NAVGPU_CUDA(cudaSetDevice(device));
+  if (c.device < 0) {
+    NAVGPU_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    NAVGPU_CUDA(cudaMalloc(&c.d_win, sizeof(DevWindow)));
+    c.device = device;
+  }
+  *out = &c;
+  return NAVGPU_OK;
+}
+
+int ensure(uint8_t** p, size_t* cap, size_t need) {
+  if (need <= *cap) return NAVGPU_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  NAVGPU_CUDA(cudaMalloc(p, need));
+  *cap = need;
+  return NAVGPU_OK;
+}
+
+int seam_run(uint8_t* master, const uint8_t* layer, uint32_t size_x, uint32_t size_y, int min_i, int min_j, int max_i,
+             int max_j, int policy, const uint8_t* by_d2, int R, int device) {
+  SeamContext* c;
+  NAVGPU_TRY(seam_context(device, &c));
+  if (max_i <= min_i || max_j <= min_j) return NAVGPU_OK;
+  const int y_lo = std::max(0, min_j - 2 * R), y_hi = std::min((int)size_y, max_j + 2 * R);
+  if (y_hi <= y_lo) return NAVGPU_OK;
+  const unsigned rows = y_hi - y_lo, pitch = grid_pitch(size_x);
+  NAVGPU_TRY(ensure(&c->d_master, &c->cap_master, size_t(pitch) * rows));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(c->d_master, pitch, master + size_t(y_lo) * size_x, size_x, size_x, rows,
+                                cudaMemcpyHostToDevice, c->stream));
+  MergeLayers ml;
+  ml.n = 0;
+  if (layer) {
+    NAVGPU_TRY(ensure(&c->d_layer, &c->cap_layer, size_t(pitch) * rows));
+    NAVGPU_CUDA(cudaMemcpy2DAsync(c->d_layer, pitch, layer + size_t(y_lo) * size_x, size_x, size_x, rows,
+                                  cudaMemcpyHostToDevice, c->stream));
+    ml.n = 1;
+    ml.grid[0] = c->d_layer;
+    ml.policy[0] = policy;
+  }
+  if (R > 0) {
+    NAVGPU_TRY(ensure(&c->d_table, &c->cap_table, size_t(R) * R + 1));
+    NAVGPU_CUDA(cudaMemcpyAsync(c->d_table, by_d2, size_t(R) * R + 1, cudaMemcpyHostToDevice, c->stream));
+  }
+  k_set_window<<<1, 32, 0, c->stream>>>(c->d_win, min_i, max_i, min_j - y_lo, max_j - y_lo);
+  UpdateArgs a;
+  a.master = c->d_master;
+  a.sx = size_x; a.sy = rows; a.pitch = pitch;
+  a.def = 0;
+  a.do_reset = 0;
+  a.win = c->d_win;
+  a.ml = ml;
+  a.R = R;
+  a.cost_d2 = c->d_table;
+  size_t smem = update_costs_smem(R);
+  if (smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %d needs %zu B of shared memory", R, smem);
+  if (smem > 48 * 1024)
+    NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((size_x + kTX - 1) / kTX, (rows + kTY - 1) / kTY);
+  k_update_costs<<<grid, kUpdateThreads, smem, c->stream>>>(a);
+  NAVGPU_LAUNCHED(2);
+  NAVGPU_CUDA(cudaGetLastError());
+  NAVGPU_CUDA(cudaMemcpy2DAsync(master + size_t(y_lo) * size_x, size_x, c->d_master, pitch, size_x, rows,
+                                cudaMemcpyDeviceToHost, c->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(c->stream));
+  return NAVGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int navgpu_inflate_host(uint8_t* master, uint32_t size_x, uint32_t size_y, int min_i, int min_j, int max_i, int max_j,
+                        const uint8_t* cost_table, uint32_t R, int device) {
+  if (!master || !cost_table || size_x == 0 || size_y == 0) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (R == 0) return NAVGPU_OK;
+  if (R > 254) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %u > 254", R);
+  // cached_costs_[dx][dy] -> cost by squared distance; must be consistent (see build_tables)
+  const unsigned n = R + 2;
+  std::vector<uint8_t> by_d2(size_t(R) * R + 1, 0);
+  std::vector<uint8_t> seen(size_t(R) * R + 1, 0);
+  for (unsigned i = 0; i < n; ++i)
+    for (unsigned j = 0; j < n; ++j) {
+      unsigned d2 = i * i + j * j;
+      if (d2 > R * R) continue;
+      uint8_t cst = cost_table[i * n + j];
+      if (seen[d2] && by_d2[d2] != cst)
+        return fail(NAVGPU_ERR_UNSUPPORTED, "cost table is not a function of squared distance at (%u,%u)", i, j);
+      seen[d2] = 1;
+      by_d2[d2] = cst;
+    }
+  // the window the reference receives is clamped by LayeredCostmap (:117-124); clamp defensively the same way
+  min_i = std::max(0, min_i); min_j = std::max(0, min_j);
+  max_i = std::min((int)size_x, max_i); max_j = std::min((int)size_y, max_j);
+  return seam_run(master, nullptr, size_x, size_y, min_i, min_j, max_i, max_j, NAVGPU_NOTHING, by_d2.data(), (int)R, device);
+}
+
+int navgpu_merge_host(uint8_t* master, const uint8_t* layer, uint32_t size_x, uint32_t size_y, int min_i, int min_j,
+                      int max_i, int max_j, int policy, int device) {
+  if (!master || !layer || size_x == 0 || size_y == 0 || policy < 0 || policy > NAVGPU_NOTHING)
+    return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (min_i < 0 || min_j < 0 || max_i > (int)size_x || max_j > (int)size_y) return fail(NAVGPU_ERR_INVALID, "window outside the grid");
+  return seam_run(master, layer, size_x, size_y, min_i, min_j, max_i, max_j, policy, nullptr, 0, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,542 @@
+// costmap_kernels.cuh -- Path A device code: layered costmap update on the GPU (sm_100a).
+//
+// Reference semantics (file:line under /root/reference/costmap_2d) are cited next to each kernel; the host side
+// that sequences them per LayeredCostmap::updateMap is in costmap.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace navgpu {
+
+struct Geom {
+  unsigned sx, sy, pitch;
+  double res, ox, oy;
+};
+
+// Costmap2D::worldToMap, src/costmap_2d.cpp:208-220
+__device__ __forceinline__ bool world_to_map(const Geom& g, double wx, double wy, unsigned& mx, unsigned& my) {
+  if (wx < g.ox || wy < g.oy) return false;
+  mx = (unsigned)(int)((wx - g.ox) / g.res);
+  my = (unsigned)(int)((wy - g.oy) / g.res);
+  return mx < g.sx && my < g.sy;
+}
+
+__device__ __forceinline__ void box_touch_warp(DevBox* box, double x, double y, bool active) {
+  // warp-aggregated CostmapLayer::touch (src/costmap_layer.cpp:8-14): one atomic per warp and coordinate
+  unsigned long long ex_min = active ? enc_double(x) : ~0ull, ex_max = active ? enc_double(x) : 0ull;
+  unsigned long long ey_min = active ? enc_double(y) : ~0ull, ey_max = active ? enc_double(y) : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ex_min = min(ex_min, __shfl_xor_sync(0xffffffffu, ex_min, o));
+    ex_max = max(ex_max, __shfl_xor_sync(0xffffffffu, ex_max, o));
+    ey_min = min(ey_min, __shfl_xor_sync(0xffffffffu, ey_min, o));
+    ey_max = max(ey_max, __shfl_xor_sync(0xffffffffu, ey_max, o));
+  }
+  if ((threadIdx.x & 31) == 0 && ex_max != 0ull) {
+    atomicMin(&box->minx, ex_min);
+    atomicMax(&box->maxx, ex_max);
+    atomicMin(&box->miny, ey_min);
+    atomicMax(&box->maxy, ey_max);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rolling-window origin shift, Costmap2D::updateOrigin (src/costmap_2d.cpp:264-313): out of place,
+// dst(x, y) = src(x + cell_ox, y + cell_oy) where that lies inside the old grid, default elsewhere.
+__global__ void k_shift_grid(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, unsigned sx, unsigned sy,
+                             unsigned pitch, int cell_ox, int cell_oy, uint8_t def) {
+  unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned y = blockIdx.y;
+  if (x >= pitch || y >= sy) return;
+  uint8_t v = def;
+  long long ox = (long long)x + cell_ox, oy = (long long)y + cell_oy;
+  if (x < sx && ox >= 0 && ox < (long long)sx && oy >= 0 && oy < (long long)sy) v = src[(size_t)oy * pitch + ox];
+  dst[(size_t)y * pitch + x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// StaticLayer::interpretValue over an OccupancyGrid (plugins/static_layer.cpp:149-163, applied as in :196-207)
+__global__ void k_interpret_occupancy(const int8_t* __restrict__ occ, uint8_t* __restrict__ grid, unsigned sx,
+                                      unsigned sy, unsigned pitch, int track_unknown, uint8_t unknown_cost_value,
+                                      uint8_t lethal_threshold, int trinary) {
+  unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned y = blockIdx.y;
+  if (x >= sx || y >= sy) return;
+  uint8_t value = (uint8_t)occ[(size_t)y * sx + x];
+  uint8_t r;
+  if (value == unknown_cost_value) r = track_unknown ? kNoInfo : kFree;
+  else if (value >= lethal_threshold) r = kLethal;
+  else if (trinary) r = kFree;
+  else {
+    double scale = (double)value / lethal_threshold;
+    r = (uint8_t)(scale * kLethal);
+  }
+  grid[(size_t)y * pitch + x] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Observations as laid out on the device
+struct DevObs {
+  double ox, oy, oz, obstacle_range, raytrace_range;
+  int first_point, n_points;
+  int first_ray;  // prefix over clearing observations (rays) / marking observations (points), per kernel
+  int flags;      // bit0 marking, bit1 clearing
+};
+
+// ObstacleLayer::raytraceFreespace (plugins/obstacle_layer.cpp:498-576) + Costmap2D::raytraceLine / bresenham2D
+// (include/costmap_2d/costmap_2d.h:359-412) + updateRaytraceBounds (:602-610).
+// One warp per ray.  All lanes evaluate the fp64 clip (identical operation order to the reference, no FMA
+// contraction); the Bresenham walk is evaluated in closed form so the lanes write cells i, i+32, ... in parallel:
+// after i major steps the reference's error accumulator has taken floor((abs_da/2 + i*abs_db)/abs_da) minor steps.
+// All writers store FREE_SPACE, so write order between rays does not matter.
+__global__ void k_raytrace_clear(uint8_t* __restrict__ grid, Geom g, const DevObs* __restrict__ obs, int n_obs,
+                                 const float* __restrict__ xyz, int total_rays, DevBox* box) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  bool touch1 = false;
+  double t1x = 0, t1y = 0;
+  if (warp < total_rays) {
+    int k = 0;
+    while (k + 1 < n_obs && obs[k + 1].first_ray <= warp) ++k;
+    const DevObs o = obs[k];
+    const int pi = o.first_point + (warp - o.first_ray);
+    const double ox = o.ox, oy = o.oy;
+    unsigned x0, y0;
+    if (world_to_map(g, ox, oy, x0, y0)) {  // otherwise the whole observation is skipped (:507-513)
+      const double origin_x = g.ox, origin_y = g.oy;
+      const double map_end_x = origin_x + g.sx * g.res;
+      const double map_end_y = origin_y + g.sy * g.res;
+      double wx = xyz[3 * (size_t)pi], wy = xyz[3 * (size_t)pi + 1];
+      const double a = wx - ox, b = wy - oy;
+      if (wx < origin_x) {
+        double t = (origin_x - ox) / a;
+        wx = origin_x;
+        wy = oy + b * t;
+      }
+      if (wy < origin_y) {
+        double t = (origin_y - oy) / b;
+        wx = ox + a * t;
+        wy = origin_y;
+      }
+      if (wx > map_end_x) {
+        double t = (map_end_x - ox) / a;
+        wx = map_end_x - .001;
+        wy = oy + b * t;
+      }
+      if (wy > map_end_y) {
+        double t = (map_end_y - oy) / b;
+        wx = ox + a * t;
+        wy = map_end_y - .001;
+      }
+      unsigned x1, y1;
+      if (world_to_map(g, wx, wy, x1, y1)) {
+        const unsigned cell_range = (unsigned)fmax(0.0, ceil(o.raytrace_range / g.res));  // cellDistance :181-185
+        const int dx = (int)x1 - (int)x0, dy = (int)y1 - (int)y0;
+        const unsigned adx = abs(dx), ady = abs(dy);
+        const int off_dx = dx > 0 ? 1 : -1;
+        const int off_dy = (dy > 0 ? 1 : -1) * (int)g.pitch;
+        const double dist = hypot((double)dx, (double)dy);
+        const double scale = (dist == 0.0) ? 1.0 : fmin(1.0, cell_range / dist);
+        unsigned da, db;
+        int off_a, off_b;
+        if (adx >= ady) { da = adx; db = ady; off_a = off_dx; off_b = off_dy; }
+        else { da = ady; db = adx; off_a = off_dy; off_b = off_dx; }
+        const unsigned end = min((unsigned)(scale * da), da);
+        const long long start = (long long)y0 * g.pitch + x0;
+        const unsigned half = da / 2;
+        for (unsigned i = lane; i <= end; i += 32) {  // cells 0..end-1 of the loop plus the final at(offset)
+          const unsigned m = da ? (unsigned)((half + (unsigned long long)i * db) / da) : 0u;
+          grid[start + (long long)i * off_a + (long long)m * off_b] = kFree;
+        }
+        // updateRaytraceBounds
+        const double ddx = wx - ox, ddy = wy - oy;
+        const double full = hypot(ddx, ddy);
+        const double s2 = fmin(1.0, o.raytrace_range / full);
+        touch1 = true;
+        t1x = ox + ddx * s2;
+        t1y = oy + ddy * s2;
+      }
+    }
+  }
+  // every lane of a warp holds the same values; reduce across the block's warps through lane 0 only
+  box_touch_warp(box, t1x, t1y, touch1 && lane == 0);
+}
+
+// ObstacleLayer::updateBounds marking loop (plugins/obstacle_layer.cpp:368-410): one thread per point
+__global__ void k_mark_points(uint8_t* __restrict__ grid, Geom g, const DevObs* __restrict__ obs, int n_obs,
+                              const float* __restrict__ xyz, int total_points, double max_obstacle_height,
+                              DevBox* box) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool touched = false;
+  double px = 0, py = 0;
+  if (t < total_points) {
+    int k = 0;
+    while (k + 1 < n_obs && obs[k + 1].first_ray <= t) ++k;
+    const DevObs o = obs[k];
+    const int pi = o.first_point + (t - o.first_ray);
+    px = xyz[3 * (size_t)pi];
+    py = xyz[3 * (size_t)pi + 1];
+    const double pz = xyz[3 * (size_t)pi + 2];
+    if (!(pz > max_obstacle_height)) {
+      const double sq_dist = (px - o.ox) * (px - o.ox) + (py - o.oy) * (py - o.oy) + (pz - o.oz) * (pz - o.oz);
+      if (!(sq_dist >= o.obstacle_range * o.obstacle_range)) {
+        unsigned mx, my;
+        if (world_to_map(g, px, py, mx, my)) {
+          grid[(size_t)my * g.pitch + mx] = kLethal;
+          touched = true;
+        }
+      }
+    }
+  }
+  box_touch_warp(box, px, py, touched);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Costmap2D::setConvexPolygonCost -> convexFillCells -> polygonOutlineCells (src/costmap_2d.cpp:315-428).
+// One CTA.  Outline cells come from the closed-form Bresenham (parallel), the reference's back-stepping bubble sort
+// is a stable sort by x (parallel rank), and the column walk -- which in the reference iterates over the very
+// vector it appends to -- is replayed verbatim by one thread so that degenerate footprints fill identically.
+constexpr int kPolyMaxCells = 12288;
+struct PolyArgs {
+  int n;
+  int vx[32], vy[32];
+};
+__global__ void k_polygon_clear(uint8_t* __restrict__ grid, unsigned pitch, PolyArgs poly, uint8_t value) {
+  extern __shared__ uint32_t poly_smem[];
+  uint32_t* cells = poly_smem;                  // packed x | y << 16, in outline order
+  uint32_t* sorted = poly_smem + kPolyMaxCells;  // the vector convexFillCells works on
+  __shared__ int edge_first[33];
+  __shared__ int n_total;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) {
+    int acc = 0;
+    for (int k = 0; k < poly.n; ++k) {
+      const int k1 = (k + 1) % poly.n;
+      edge_first[k] = acc;
+      acc += max(abs(poly.vx[k1] - poly.vx[k]), abs(poly.vy[k1] - poly.vy[k])) + 1;
+    }
+    edge_first[poly.n] = acc;
+  }
+  __syncthreads();
+  const int n_outline = edge_first[poly.n];
+  for (int j = tid; j < n_outline; j += nt) {
+    int k = 0;
+    while (edge_first[k + 1] <= j) ++k;
+    const int i = j - edge_first[k];
+    const int k1 = (k + 1) % poly.n;
+    const int dx = poly.vx[k1] - poly.vx[k], dy = poly.vy[k1] - poly.vy[k];
+    const int adx = abs(dx), ady = abs(dy);
+    const int sxn = dx > 0 ? 1 : -1, syn = dy > 0 ? 1 : -1;
+    int x = poly.vx[k], y = poly.vy[k];
+    if (adx >= ady) {
+      const int m = adx ? (adx / 2 + i * ady) / adx : 0;
+      x += i * sxn;
+      y += m * syn;
+    } else {
+      const int m = (ady / 2 + i * adx) / ady;
+      y += i * syn;
+      x += m * sxn;
+    }
+    cells[j] = (uint32_t)x | ((uint32_t)y << 16);
+  }
+  __syncthreads();
+  for (int j = tid; j < n_outline; j += nt) {  // stable rank by x
+    const uint32_t xj = cells[j] & 0xffffu;
+    int rank = 0;
+    for (int i = 0; i < n_outline; ++i) {
+      const uint32_t xi = cells[i] & 0xffffu;
+      rank += (xi < xj) || (xi == xj && i < j);
+    }
+    sorted[rank] = cells[j];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int size = n_outline;
+    auto X = [&](int i) { return (int)(sorted[i] & 0xffffu); };
+    auto Y = [&](int i) { return (int)(sorted[i] >> 16); };
+    int i = 0;
+    const int min_x = X(0), max_x = X(size - 1);
+    for (int x = min_x; x <= max_x; ++x) {
+      if (i >= size - 1) break;
+      int min_y, max_y;
+      if (Y(i) < Y(i + 1)) { min_y = Y(i); max_y = Y(i + 1); }
+      else { min_y = Y(i + 1); max_y = Y(i); }
+      i += 2;
+      while (i < size && X(i) == x) {
+        if (Y(i) < min_y) min_y = Y(i);
+        else if (Y(i) > max_y) max_y = Y(i);
+        ++i;
+      }
+      for (int y = min_y; y < max_y && size < kPolyMaxCells; ++y) sorted[size++] = (uint32_t)x | ((uint32_t)y << 16);
+    }
+    n_total = size;
+  }
+  __syncthreads();
+  for (int j = tid; j < n_total; j += nt) {
+    const uint32_t c = sorted[j];
+    grid[(size_t)(c >> 16) * pitch + (c & 0xffffu)] = value;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bounds pass of LayeredCostmap::updateMap (src/layered_costmap.cpp:96-135): walks the layers in plugin order,
+// unions what each contributed (host-known boxes for grid layers / footprints, device-accumulated boxes for the
+// observation kernels), applies InflationLayer::updateBounds (plugins/inflation_layer.cpp:125-158) with its
+// device-resident last_* state, and converts to the cell window with worldToMapEnforceBounds (:228-262).
+constexpr int kMaxLayers = 8;
+struct BoundsLayer {
+  int kind;  // 0 union-box layer (grid / obstacle), 2 inflation
+  int flag;  // kind 0: host box present; kind 2: need_reinflation_
+  double hx0, hy0, hx1, hy1;  // host-known box contribution (kind 0), inflation_radius_ in hx0 (kind 2)
+};
+struct BoundsArgs {
+  int n_layers;
+  BoundsLayer layer[kMaxLayers];
+  Geom master;
+};
+struct InflationBoundsState {
+  double last_min_x, last_min_y, last_max_x, last_max_y;
+};
+__global__ void k_finalize_bounds(BoundsArgs a, DevBox* boxes, InflationBoundsState* infl, DevWindow* win) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double minx = 1e30, miny = 1e30, maxx = -1e30, maxy = -1e30;
+  for (int l = 0; l < a.n_layers; ++l) {
+    const BoundsLayer& L = a.layer[l];
+    if (L.kind == 0) {
+      if (L.flag) {
+        minx = fmin(minx, L.hx0); miny = fmin(miny, L.hy0);
+        maxx = fmax(maxx, L.hx1); maxy = fmax(maxy, L.hy1);
+      }
+      DevBox b = boxes[l];
+      if (b.maxx != 0ull) {  // something was touched on the device this cycle
+        minx = fmin(minx, dec_double(b.minx)); miny = fmin(miny, dec_double(b.miny));
+        maxx = fmax(maxx, dec_double(b.maxx)); maxy = fmax(maxy, dec_double(b.maxy));
+      }
+      boxes[l] = DevBox{~0ull, ~0ull, 0ull, 0ull};  // re-armed for the next cycle
+    } else if (L.kind == 2) {
+      InflationBoundsState& s = infl[l];
+      const double fmaxf_ = 3.40282346638528859811704183484516925e+38;  // std::numeric_limits<float>::max()
+      if (L.flag) {
+        s.last_min_x = minx; s.last_min_y = miny; s.last_max_x = maxx; s.last_max_y = maxy;
+        minx = -fmaxf_; miny = -fmaxf_; maxx = fmaxf_; maxy = fmaxf_;
+      } else {
+        const double tx0 = s.last_min_x, ty0 = s.last_min_y, tx1 = s.last_max_x, ty1 = s.last_max_y;
+        s.last_min_x = minx; s.last_min_y = miny; s.last_max_x = maxx; s.last_max_y = maxy;
+        minx = fmin(tx0, minx) - L.hx0;
+        miny = fmin(ty0, miny) - L.hx0;
+        maxx = fmax(tx1, maxx) + L.hx0;
+        maxy = fmax(ty1, maxy) + L.hx0;
+      }
+    }
+  }
+  const Geom& g = a.master;
+  auto enforce = [&](double w, double origin, unsigned size) -> int {
+    if (w < origin) return 0;
+    if (w > g.res * (size - 1) + origin) return (int)(size - 1);
+    return (int)((w - origin) / g.res);
+  };
+  int x0 = enforce(minx, g.ox, g.sx), y0 = enforce(miny, g.oy, g.sy);
+  int xn = enforce(maxx, g.ox, g.sx), yn = enforce(maxy, g.oy, g.sy);
+  x0 = max(0, x0);
+  xn = min((int)g.sx, xn + 1);
+  y0 = max(0, y0);
+  yn = min((int)g.sy, yn + 1);
+  win->x0 = x0; win->xn = xn; win->y0 = y0; win->yn = yn;
+  win->valid = !(xn < x0 || yn < y0);
+}
+
+__global__ void k_set_window(DevWindow* win, int x0, int xn, int y0, int yn) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    win->x0 = x0; win->xn = xn; win->y0 = y0; win->yn = yn;
+    win->valid = !(xn < x0 || yn < y0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The cost sweep of a cycle: Costmap2D::resetMap (src/costmap_2d.cpp:93-99), the CostmapLayer merge policies
+// (src/costmap_layer.cpp:62-157) of every enabled cost layer in plugin order, and InflationLayer::updateCosts
+// (plugins/inflation_layer.cpp:172-266), fused into ONE pass over the master grid.
+//
+// Inside the window a cell's pre-inflation value is a pure function of the layer grids (reset -> merges), so a tile
+// recomputes it for its halo instead of reading what a neighbouring CTA writes; outside the window it is the
+// previous master value, whose "== LETHAL" predicate inflation can never change.  Inflation is evaluated as the
+// exact windowed nearest-seed distance: seeds are the LETHAL cells of (window +- R, clamped), a cell within
+// hypot <= R of a seed gets max(old, table[d]) (NO_INFORMATION is replaced only by costs >= INSCRIBED), cells may be
+// written up to window +- 2R exactly like the reference's unclamped propagation.  d^2 = dy^2 + hx^2 with hx the
+// per-row distance to the nearest seed, taken from per-row seed bitmasks with clz/ffs.
+struct MergeLayers {
+  int n;
+  const uint8_t* grid[kMaxLayers];
+  int policy[kMaxLayers];
+};
+struct UpdateArgs {
+  uint8_t* master;
+  unsigned sx, sy, pitch;
+  uint8_t def;
+  int do_reset;
+  const DevWindow* win;
+  MergeLayers ml;
+  int R;                   // 0: no inflation in this pass
+  const uint8_t* cost_d2;  // R*R+1 entries: cost by squared cell distance
+};
+
+__device__ __forceinline__ uint8_t apply_policy(uint8_t m, uint8_t v, int policy) {
+  switch (policy) {
+    case NAVGPU_TRUE_OVERWRITE: return v;
+    case NAVGPU_OVERWRITE: return v != kNoInfo ? v : m;
+    case NAVGPU_MAX: return (v == kNoInfo) ? m : ((m == kNoInfo || m < v) ? v : m);
+    case NAVGPU_ADDITION: {
+      if (v == kNoInfo) return m;
+      if (m == kNoInfo) return v;
+      const int sum = (int)m + (int)v;
+      return sum >= kInscribed ? (uint8_t)(kInscribed - 1) : (uint8_t)sum;
+    }
+    default: return m;
+  }
+}
+
+__device__ __forceinline__ uint8_t inflate_combine(uint8_t old, uint8_t cost) {  // inflation_layer.cpp:249-254
+  if (old == kNoInfo && cost >= kInscribed) return cost;
+  return old > cost ? old : cost;
+}
+
+constexpr int kTX = 128, kTY = 32, kUpdateThreads = 256;
+
+// generic kernel: any R <= 254
+__global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const DevWindow w = *a.win;
+  if (!w.valid) return;
+  const int R = a.R;
+  const int tx0 = blockIdx.x * kTX, ty0 = blockIdx.y * kTY;
+  // affected region: the window itself, plus 2R around it when inflating
+  if (tx0 >= w.xn + 2 * R || tx0 + kTX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kTY <= w.y0 - 2 * R) return;
+
+  const int HX = (R + 7) & ~7;            // x halo rounded to the 8-cell load granularity
+  const int groups = (kTX + 2 * HX) / 8;  // 8-cell groups per region row
+  const int rows = kTY + 2 * R;
+  const int bits_pitch = (groups + 3) & ~3;  // bytes per row of the seed bitmask, whole 32-bit words
+  uint8_t* tile = smem;                                   // kTY x kTX pre-inflation values, then results
+  uint8_t* bits = tile + kTX * kTY;                       // rows x bits_pitch
+  uint8_t* hx = bits + ((rows * bits_pitch + 15) & ~15);  // rows x kTX horizontal distances
+  uint8_t* table = hx + rows * kTX;                       // R*R+1
+  const int tid = threadIdx.x;
+
+  if (R > 0)
+    for (int i = tid; i <= R * R; i += kUpdateThreads) table[i] = a.cost_d2[i];
+  // seed region: window +- R clamped to the map (inflation_layer.cpp:203-211)
+  const int sx0 = max(0, w.x0 - R), sxn = min((int)a.sx, w.xn + R);
+  const int sy0 = max(0, w.y0 - R), syn = min((int)a.sy, w.yn + R);
+  const int rx0 = tx0 - HX, ry0 = ty0 - R;
+
+  // phase 1: pre-inflation values of the region, 8 cells per item
+  for (int item = tid; item < rows * groups; item += kUpdateThreads) {
+    const int row = item / groups, grp = item - row * groups;
+    const int y = ry0 + row, x = rx0 + grp * 8;
+    uint32_t seedbits = 0;
+    const bool own_row = row >= R && row < R + kTY;
+    if (y >= 0 && y < (int)a.sy && x >= 0 && x < (int)a.sx) {
+      const size_t off = (size_t)y * a.pitch + x;
+      const bool row_in = y >= w.y0 && y < w.yn;
+      const bool any_in = row_in && x + 8 > w.x0 && x < w.xn;
+      const bool all_in = row_in && x >= w.x0 && x + 8 <= w.xn;
+      uint2 mv = make_uint2(0, 0);
+      if (!(all_in && a.do_reset)) mv = *reinterpret_cast<const uint2*>(a.master + off);
+      uint2 lv[kMaxLayers];
+      if (any_in)
+        for (int l = 0; l < a.ml.n; ++l) lv[l] = *reinterpret_cast<const uint2*>(a.ml.grid[l] + off);
+      uint2 outv = make_uint2(0, 0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cx = x + i;
+        const uint32_t mword = i < 4 ? mv.x : mv.y;
+        uint8_t v = (uint8_t)(mword >> (8 * (i & 3)));
+        const bool inwin = row_in && cx >= w.x0 && cx < w.xn;
+        if (inwin) {
+          if (a.do_reset) v = a.def;
+          for (int l = 0; l < a.ml.n; ++l) {
+            const uint32_t lword = i < 4 ? lv[l].x : lv[l].y;
+            v = apply_policy(v, (uint8_t)(lword >> (8 * (i & 3))), a.ml.policy[l]);
+          }
+        }
+        if (cx >= (int)a.sx) v = 0;
+        if (v == kLethal && cx >= sx0 && cx < sxn && y >= sy0 && y < syn) seedbits |= 1u << i;
+        if (i < 4) outv.x |= (uint32_t)v << (8 * i);
+        else outv.y |= (uint32_t)v << (8 * (i - 4));
+      }
+      if (own_row && x >= tx0 && x < tx0 + kTX)
+        *reinterpret_cast<uint2*>(tile + (row - R) * kTX + (x - tx0)) = outv;
+    } else if (own_row && x >= tx0 && x < tx0 + kTX) {
+      *reinterpret_cast<uint2*>(tile + (row - R) * kTX + (x - tx0)) = make_uint2(0, 0);
+    }
+    bits[row * bits_pitch + grp] = (uint8_t)seedbits;
+  }
+  // zero the pad bytes of each bitmask row so whole-word reads are clean
+  for (int i = tid; i < rows * (bits_pitch - groups); i += kUpdateThreads) {
+    const int row = i / (bits_pitch - groups), k = i - row * (bits_pitch - groups);
+    bits[row * bits_pitch + groups + k] = 0;
+  }
+  __syncthreads();
+
+  if (R > 0) {
+    // phase 2: horizontal distance to the nearest seed of the same row, |dx| <= R (255 = none)
+    const int nwords = bits_pitch / 4;
+    for (int item = tid; item < rows * kTX; item += kUpdateThreads) {
+      const int row = item / kTX, tx = item - row * kTX;
+      const uint32_t* wrow = reinterpret_cast<const uint32_t*>(bits + row * bits_pitch);
+      const int p = HX + tx;  // bit position of this cell in the row
+      auto word = [&](int i) -> uint32_t { return (i < 0 || i >= nwords) ? 0u : wrow[i]; };
+      auto window32 = [&](int q) -> uint32_t {  // bits q .. q+31
+        const int wi = q >> 5, sh = q & 31;
+        return __funnelshift_r(word(wi), word(wi + 1), sh);
+      };
+      int best = 255;
+      for (int base = 0; base <= R; base += 32) {
+        const uint32_t right = window32(p + base);       // bit k  <-> distance base + k
+        const uint32_t left = window32(p - base - 31);   // bit 31-k <-> distance base + k
+        int d = 255;
+        if (right) d = base + (__ffs(right) - 1);
+        if (left) d = min(d, base + __clz(left));
+        if (d != 255) { best = d; break; }
+      }
+      hx[item] = (uint8_t)(best <= R ? best : 255);
+    }
+    __syncthreads();
+
+    // phase 3: d^2 = min over dy of dy^2 + hx(y+dy)^2 ; one thread per column, 16 rows each
+    const int tx = tid & (kTX - 1), half = tid / kTX;
+    const int R2 = R * R;
+    for (int r = half * (kTY / 2); r < (half + 1) * (kTY / 2); ++r) {
+      int best = 0x7fffffff;
+      const uint8_t* col = hx + (r + R) * kTX + tx;  // row of this cell inside the region
+      for (int dy = -R; dy <= R; ++dy) {
+        const int h = col[dy * kTX];
+        const int d2 = (h == 255) ? 0x7fffffff : h * h + dy * dy;
+        best = min(best, d2);
+      }
+      if (best <= R2) {
+        uint8_t* cell = tile + r * kTX + tx;
+        *cell = inflate_combine(*cell, table[best]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // write-back: the whole tile, 16 cells per thread (unchanged cells are rewritten with their own value)
+  for (int item = tid; item < kTX * kTY / 16; item += kUpdateThreads) {
+    const int r = item / (kTX / 16), c = (item - r * (kTX / 16)) * 16;
+    const int y = ty0 + r, x = tx0 + c;
+    if (y < (int)a.sy && x < (int)a.pitch)
+      *reinterpret_cast<uint4*>(a.master + (size_t)y * a.pitch + x) = *reinterpret_cast<const uint4*>(tile + r * kTX + c);
+  }
+}
+
+inline size_t update_costs_smem(int R) {
+  const int HX = (R + 7) & ~7;
+  const int groups = (kTX + 2 * HX) / 8;
+  const int rows = kTY + 2 * R;
+  const int bits_pitch = (groups + 3) & ~3;
+  return (size_t)kTX * kTY + ((rows * bits_pitch + 15) & ~15) + (size_t)rows * kTX + (size_t)R * R + 1 + 16;
+}
+
+}  // namespace navgpu

@@ -29,3 +29,14 @@ def ref():
         else:
             pytest.skip("oracle/_ref/libnavref.so not present (needs /root/reference to build)")
     return pyoracle.load("reference")
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    """The product: navigation_b200/libnavgpu.so through its C ABI.  No fallback: a missing library or device fails."""
+    import navigation_b200
+    from navigation_b200 import build
+    build.build()
+    api = navigation_b200.load()
+    assert api.device_count() > 0, "GPU tests need a CUDA device; libnavgpu has no CPU path"
+    return api

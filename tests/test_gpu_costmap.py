@@ -1,0 +1,239 @@
+"""Path A parity: the CUDA layered costmap (through the C ABI) against the CPU checker and the reference's goldens.
+
+Bit-exact (==) everywhere except where stated: on maps whose obstacle boundaries are diagonal / point-like the
+reference's inflation depends on libstdc++'s heap tie order; there the exact-distance kernel
+may only differ by being HIGHER than the reference on a tiny fraction of cells (reference <= exact), which is what
+those tests assert, together with exact windows, origins and layer grids.
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import scenarios as sc
+import test_oracle_known_answers as ka
+from navigation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("fn", [
+    ka.test_raytracing, ka.test_raytracing2, ka.test_wave_interference, ka.test_z_threshold,
+    ka.test_dynamic_obstacles_and_multiple_additions, ka.test_adjacent_to_obstacle_can_still_move,
+    ka.test_cost_function_correctness, ka.test_priority_queue_use_correctness, ka.test_inflation, ka.test_inflation2,
+    ka.test_inflation3, ka.test_tricky_propagation], ids=lambda f: f.__name__)
+def test_reference_known_answers(cuda, fn):
+    """The reference's own gtest expectations (inflation_tests.cpp, obstacle_tests.cpp), run on the GPU."""
+    fn(cuda)
+
+
+def compare_traces(a, b, exact):
+    total = bad = 0
+    for c, (x, y) in enumerate(zip(a, b)):
+        assert x[0] == y[0], f"window differs in cycle {c}: {x[0]} vs {y[0]}"
+        assert x[3] == y[3], f"origin differs in cycle {c}"
+        assert np.array_equal(x[2], y[2]), f"obstacle layer grid differs in cycle {c}"
+        diff = x[1] != y[1]
+        if exact:
+            assert not diff.any(), f"{int(diff.sum())} master cells differ in cycle {c}"
+        else:
+            # exact-distance inflation can only be >= the reference's propagation, and only on inflated values
+            assert (x[1][diff] > y[1][diff]).all() or (y[1][diff] == 255).any(), "a differing cell is LOWER than the reference"
+        total += diff.size
+        bad += int(diff.sum())
+    return bad, total
+
+
+@pytest.mark.parametrize("seed", range(100, 130))
+def test_tie_free_scenarios_bit_exact(cuda, port, seed):
+    """Rolling/non-rolling windows, all four merge policies, ray-trace clearing, footprint clearing, stateful
+    windowed inflation over 4 cycles -- obstacle sources restricted to thick axis-aligned blocks."""
+    compare_traces(sc.run_costmap_scenario(cuda, seed, tie_free=True), sc.run_costmap_scenario(port, seed, tie_free=True), True)
+
+
+@pytest.mark.parametrize("seed", range(0, 30))
+def test_adversarial_scenarios(cuda, port, seed):
+    """Salt-and-pepper / arbitrary-valued layers and single-point marks: everything but tie-dependent inflation cells
+    must be exact; those may only be higher, and rare."""
+    bad, total = compare_traces(sc.run_costmap_scenario(cuda, seed), sc.run_costmap_scenario(port, seed), False)
+    assert bad <= max(3, 2e-3 * total), f"{bad} of {total} cells differ"
+
+
+@pytest.mark.parametrize("tie_free,seed,path", gu.costmap_cases())
+def test_golden_fixtures(cuda, tie_free, seed, path):
+    bad = gu.check_costmap_case(cuda, tie_free, seed, path, exact=tie_free)
+    assert bad <= 40
+
+
+def c1_stack(api, grid, radius=0.55):
+    cm = api.costmap(400, 400, 0.05)
+    s = cm.add_grid_layer(0)
+    o = cm.add_obstacle_layer(1, True, 2.0)
+    cm.add_inflation_layer(radius, 10.0)
+    cm.set_footprint(sc.square_footprint())
+    cm.set_grid_layer(s, grid)
+    return cm, s, o
+
+
+def test_c1_400x400_bit_exact(cuda, port):
+    """Config C1 (400x400 @0.05, inscribed 0.325, inflation 0.55 -> R=11) on the tie-free block world."""
+    g = synth.blocks_c1()
+    a, _, _ = c1_stack(cuda, g)
+    b, _, _ = c1_stack(port, g)
+    assert a.update_map(10, 10, 0) == b.update_map(10, 10, 0)
+    assert np.array_equal(a.get(), b.get())
+    # idempotent on a second (no-op window) cycle
+    assert a.update_map(10, 10, 0) == b.update_map(10, 10, 0)
+    assert np.array_equal(a.get(), b.get())
+
+
+def test_c1_adversarial_mismatch_is_rare_and_one_sided(cuda, port):
+    g = synth.blocks_c1(adversarial=True)
+    a, _, _ = c1_stack(cuda, g)
+    b, _, _ = c1_stack(port, g)
+    a.update_map(10, 10, 0)
+    b.update_map(10, 10, 0)
+    ga, gb = a.get(), b.get()
+    diff = ga != gb
+    assert diff.mean() < 5e-4 and (ga[diff] > gb[diff]).all()
+
+
+def test_inflation_radius_sweep_bit_exact(cuda, port):
+    """R from 1 to 45 cells (beyond the 32-cell fast path) on a thick-block world, including map-edge clamping."""
+    rng = np.random.default_rng(3)
+    g = sc.random_layer(rng, 150, 170, "blocks")
+    for radius in (0.05, 0.2, 0.55, 1.0, 1.6, 2.25):
+        outs = []
+        for api in (cuda, port):
+            cm = api.costmap(170, 150, 0.05)
+            s = cm.add_grid_layer(0)
+            cm.add_inflation_layer(radius, 3.0)
+            cm.set_footprint(sc.square_footprint())
+            cm.set_grid_layer(s, g)
+            cm.update_map()
+            outs.append(cm.get())
+        assert np.array_equal(outs[0], outs[1]), f"radius {radius}"
+
+
+def test_plugin_seam_inflate_and_merge_host(cuda, port):
+    """navgpu_inflate_host / navgpu_merge_host: the bodies of Layer::updateCosts overrides on a HOST master grid."""
+    rng = np.random.default_rng(11)
+    g = sc.random_layer(rng, 200, 260, "blocks")
+    cm = port.costmap(260, 200, 0.05)
+    s = cm.add_grid_layer(0)
+    il = cm.add_inflation_layer(0.55, 10.0)
+    cm.set_footprint(sc.square_footprint())
+    cm.set_grid_layer(s, g)
+    cm.update_map()
+    expect = cm.get()
+    R, costs, _ = cuda.build_cost_table(0.05, 0.325, 0.55, 10.0)
+    Rp, costs_p, _ = cm.inflation_tables(il)
+    assert R == Rp and np.array_equal(costs, costs_p)
+    master = g.copy()
+    cuda.inflate_host(master, 0, 0, 260, 200, costs, R)
+    assert np.array_equal(master, expect)
+    # windowed call: only seeds in window +- R, writes up to +- 2R, rest untouched
+    master = g.copy()
+    cuda.inflate_host(master, 100, 60, 180, 120, costs, R)
+    cm2 = port.costmap(260, 200, 0.05)
+    il2 = cm2.add_inflation_layer(0.55, 10.0)
+    cm2.set_footprint(sc.square_footprint())
+    cm2.update_map()          # consumes need_reinflation with an empty map
+    # drive the reference-shaped inflation on the window by faking a dirty grid layer region is not possible without a
+    # cost layer; emulate with numpy: exact-distance inflation restricted to seeds in window +- R
+    yy, xx = np.nonzero(g[max(0, 60 - R):120 + R, max(0, 100 - R):180 + R] == 254)
+    exp = g.copy()
+    for y, x in zip(yy + max(0, 60 - R), xx + max(0, 100 - R)):
+        y0, y1, x0, x1 = max(0, y - R), min(200, y + R + 1), max(0, x - R), min(260, x + R + 1)
+        dy, dx = np.abs(np.arange(y0, y1) - y)[:, None], np.abs(np.arange(x0, x1) - x)[None, :]
+        c = np.where(dx * dx + dy * dy <= R * R, costs[np.minimum(dx, R + 1), np.minimum(dy, R + 1)], 0).astype(np.uint8)
+        exp[y0:y1, x0:x1] = np.maximum(exp[y0:y1, x0:x1], c)
+    assert np.array_equal(master, exp)
+    for policy in range(4):
+        m = sc.random_layer(rng, 200, 260, "values")
+        lay = sc.random_layer(rng, 200, 260, "values")
+        got = cuda.merge_host(m.copy(), lay, 30, 40, 200, 150, policy)
+        cm3 = port.costmap(260, 200, 0.05, track_unknown=True)
+        l3 = cm3.add_grid_layer(policy)
+        cm3.set_grid_layer(l3, lay)
+        cm3.touch_grid_layer(l3, 30, 40, 169, 109)   # bounds -> window [30,200) x [40,150)
+        # master outside the window keeps m; inside it is reset to NO_INFORMATION first in a real cycle, so compare
+        # against numpy restatements of costmap_layer.cpp:62-157 applied to m directly
+        exp = m.copy()
+        w = (slice(40, 150), slice(30, 200))
+        mv, lv = exp[w].astype(np.int32), lay[w].astype(np.int32)
+        if policy == 0:
+            r = lv
+        elif policy == 1:
+            r = np.where(lv != 255, lv, mv)
+        elif policy == 2:
+            r = np.where(lv == 255, mv, np.where((mv == 255) | (mv < lv), lv, mv))
+        else:
+            r = np.where(lv == 255, mv, np.where(mv == 255, lv, np.where(mv + lv >= 253, 252, mv + lv)))
+        exp[w] = r.astype(np.uint8)
+        assert np.array_equal(got, exp), f"policy {policy}"
+
+
+def test_occupancy_ingest(cuda, port):
+    """StaticLayer::interpretValue on the device equals the checker for every byte and flag combination."""
+    occ = np.arange(256, dtype=np.uint8).astype(np.int8).reshape(16, 16)
+    for tu in (True, False):
+        for tri in (True, False):
+            cm = cuda.costmap(16, 16, 1.0, track_unknown=tu)
+            s = cm.add_grid_layer(0)
+            cm.set_grid_layer_occupancy(s, occ, tu, 255, 100, tri)
+            got = cm.get_layer(s)
+            exp = port.interpret_values(occ.view(np.uint8).ravel(), tu, 255, 100, tri).reshape(16, 16)
+            assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("size", [1000])
+def test_warehouse_midsize_vs_checker(cuda, port, size):
+    """Warehouse world with ray-cast scans (the C3 recipe at 1000^2, R=20): full stack parity against the checker."""
+    static, obs, robot, fp = synth.warehouse_c3(size=size, n_obs=4)
+    outs = []
+    for api in (cuda, port):
+        cm = api.costmap(size, size, 0.05)
+        s = cm.add_grid_layer(0)
+        o = cm.add_obstacle_layer(1, True, 2.0)
+        cm.add_inflation_layer(1.0, 10.0)
+        cm.set_footprint(fp)
+        cm.set_grid_layer(s, static)
+        cm.set_observations(o, obs)
+        w = cm.update_map(*robot)
+        outs.append((w, cm.get(), cm.get_layer(o)))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][2], outs[1][2])
+    diff = outs[0][1] != outs[1][1]
+    assert diff.mean() <= 1e-5, f"{int(diff.sum())} cells differ"
+    assert (outs[0][1][diff] > outs[1][1][diff]).all()
+
+
+def test_c3_full_size_properties(cuda):
+    """Config C3 at full size (4000x4000, R=20): size-independent properties instead of the 10 s CPU run --
+    idempotence, inflation lower-bounds (every cell >= table cost of its nearest lethal cell along rows/columns),
+    lethal cells preserved, no cell above 254, unchanged far from obstacles."""
+    static, obs, robot, fp = synth.warehouse_c3()
+    cm = cuda.costmap(4000, 4000, 0.05)
+    s = cm.add_grid_layer(0)
+    o = cm.add_obstacle_layer(1, True, 2.0)
+    il = cm.add_inflation_layer(1.0, 10.0)
+    cm.set_footprint(fp)
+    cm.set_grid_layer(s, static)
+    cm.set_observations(o, obs)
+    assert cm.update_map(*robot) == (0, 4000, 0, 4000)
+    g1 = cm.get()
+    cm.touch_grid_layer(s, 0, 0, 4000, 4000)
+    assert cm.update_map(*robot) == (0, 4000, 0, 4000)
+    g2 = cm.get()
+    assert np.array_equal(g1, g2)
+    assert (g1[static == 254] == 254).all() and g1.max() == 254
+    R, costs, _ = cm.inflation_tables(il)
+    leth = g1 == 254
+    for d in range(1, R + 1):   # axis-aligned lower bounds at every distance
+        c = costs[d, 0]
+        assert (g1[:, d:][leth[:, :-d]] >= c).all() and (g1[:, :-d][leth[:, d:]] >= c).all()
+        assert (g1[d:, :][leth[:-d, :]] >= c).all() and (g1[:-d, :][leth[d:, :]] >= c).all()
+    # cells farther than R (Chebyshev) from any lethal cell are untouched
+    import scipy.ndimage as ndi
+    far = ~ndi.binary_dilation(leth, structure=np.ones((3, 3), bool), iterations=R)
+    assert (g1[far] == 0).all()
