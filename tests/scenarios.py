@@ -23,6 +23,8 @@ def random_layer(rng, sy, sx, kind):
         g[rng.random((sy, sx)) < 0.01] = 254
     elif kind == "values":
         g = rng.choice(np.array([0, 0, 0, 1, 50, 100, 128, 200, 252, 253, 254, 255], np.uint8), size=(sy, sx))
+    elif kind == "values_nolethal":  # no isolated LETHAL cells: keeps a scenario in the tie-free class
+        g = rng.choice(np.array([0, 0, 0, 1, 50, 100, 128, 200, 252, 253, 255, 255], np.uint8), size=(sy, sx))
     return g
 
 
@@ -123,7 +125,7 @@ def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False):
         if "static" in ids and (cyc == 0 or rng.random() < 0.3):
             cm.set_grid_layer(ids["static"], random_layer(rng, sy, sx, kind))
         if "extra" in ids and (cyc == 0 or rng.random() < 0.5):
-            cm.set_grid_layer(ids["extra"], random_layer(rng, sy, sx, "values"))
+            cm.set_grid_layer(ids["extra"], random_layer(rng, sy, sx, "values_nolethal" if tie_free else "values"))
         obs = random_observations(rng, sx, sy, res, ox, oy, int(rng.integers(0, 4)), 40)
         if tie_free:
             for o in obs:
