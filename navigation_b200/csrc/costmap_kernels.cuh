@@ -531,6 +531,228 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast variant of the same sweep for R <= 31 cells (every configuration the reference's defaults produce).
+//
+//   tile 256 x 64 cells per CTA (halo 32 columns, R rows), 256 threads, about 75 KB of shared memory at R = 20
+//   phase 1  16 cells per uint4 load; merge policies evaluated on 4 packed bytes per 32-bit op; the LETHAL
+//            predicate becomes one seed bit per cell (10 x 32-bit words per region row)
+//   phase 2  per (row, 64-column segment) that has any seed bit: nearest seed along the row by clz/ffs on funnel-
+//            shifted windows, stored squared as packed u16x2; rows without seeds are never touched again
+//   phase 3  each thread owns 2 columns x 8 rows of accumulators and walks only the non-empty rows of its
+//            (8 + 2R)-row window: acc_k = min(acc_k, hx^2 + dy_k^2) is ONE VIADDMNMX.U16x2 per row and cell pair
+//   epilogue table lookup by d^2, InflationLayer's max/NO_INFORMATION rule, uint4 write-back of the whole tile
+constexpr int kFTX = 256, kFTY = 64, kFThreads = 256, kFHalo = 32;
+constexpr int kFGroups = (kFTX + 2 * kFHalo) / 16;  // 20 groups of 16 cells per region row
+constexpr int kFWords = (kFTX + 2 * kFHalo) / 32;   // 10 seed words per region row
+constexpr int kFMaxRows = kFTY + 2 * 32;
+constexpr uint32_t kH2Inf = 0x3000;  // "no seed within R on this row" (as a squared distance, per 16-bit half)
+
+__device__ __forceinline__ uint32_t merge4(uint32_t m, uint32_t v, int policy) {
+  switch (policy) {
+    case NAVGPU_TRUE_OVERWRITE: return v;
+    case NAVGPU_OVERWRITE: {
+      const uint32_t vn = __vcmpeq4(v, 0xffffffffu);
+      return (m & vn) | (v & ~vn);
+    }
+    case NAVGPU_MAX: {
+      const uint32_t vn = __vcmpeq4(v, 0xffffffffu), mn = __vcmpeq4(m, 0xffffffffu), lt = __vcmpltu4(m, v);
+      const uint32_t take = ~vn & (mn | lt);
+      return (v & take) | (m & ~take);
+    }
+    case NAVGPU_ADDITION: {
+      const uint32_t vn = __vcmpeq4(v, 0xffffffffu), mn = __vcmpeq4(m, 0xffffffffu);
+      uint32_t s = __vaddus4(m, v);
+      const uint32_t ge = __vcmpgeu4(s, 0xfdfdfdfdu);
+      s = (ge & 0xfcfcfcfcu) | (s & ~ge);
+      const uint32_t r = (mn & v) | (~mn & s);
+      return (vn & m) | (~vn & r);
+    }
+    default: return m;
+  }
+}
+
+__device__ __forceinline__ uint32_t lethal_bits4(uint32_t v) {  // one bit per byte that equals LETHAL_OBSTACLE
+  const uint32_t e = __vcmpeq4(v, 0xfefefefeu) & 0x01010101u;
+  return (e * 0x01020408u) >> 24;
+}
+
+__global__ void __launch_bounds__(kFThreads) k_update_costs_fast(UpdateArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const DevWindow w = *a.win;
+  if (!w.valid) return;
+  const int R = a.R;
+  const int tx0 = blockIdx.x * kFTX, ty0 = blockIdx.y * kFTY;
+  if (tx0 >= w.xn + 2 * R || tx0 + kFTX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kFTY <= w.y0 - 2 * R) return;
+
+  const int rows = kFTY + 2 * R;
+  uint8_t* tile = smem;                                               // kFTY x kFTX
+  uint32_t* bits = reinterpret_cast<uint32_t*>(tile + kFTX * kFTY);  // rows x kFWords
+  uint32_t* h2 = bits + kFMaxRows * kFWords;                          // rows x (kFTX / 2) packed u16x2
+  uint32_t* rowmask = h2 + rows * (kFTX / 2);                         // 4 segments x 4 words
+  uint32_t* sq = rowmask + 16;                                        // 128 packed squares, index dy + 64
+  uint8_t* table = reinterpret_cast<uint8_t*>(sq + 128);              // R*R + 1
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i <= R * R; i += kFThreads) table[i] = a.cost_d2[i];
+  if (tid < 128) {
+    const int d = tid - 64;
+    sq[tid] = (uint32_t)(d * d) * 0x10001u;
+  }
+  if (tid < 16) rowmask[tid] = 0;
+
+  const int sx0 = max(0, w.x0 - R), sxn = min((int)a.sx, w.xn + R);  // seed region (inflation_layer.cpp:203-211)
+  const int sy0 = max(0, w.y0 - R), syn = min((int)a.sy, w.yn + R);
+  const int rx0 = tx0 - kFHalo, ry0 = ty0 - R;
+
+  // ---- phase 1
+  for (int item = tid; item < rows * kFGroups; item += kFThreads) {
+    const int row = item / kFGroups, grp = item - row * kFGroups;
+    const int y = ry0 + row, x = rx0 + grp * 16;
+    uint32_t seed16 = 0;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < (int)a.sy && x >= 0 && x < (int)a.sx) {
+      const size_t off = (size_t)y * a.pitch + x;
+      const bool row_in = y >= w.y0 && y < w.yn;
+      const bool any_in = row_in && x + 16 > w.x0 && x < w.xn;
+      const bool all_in = row_in && x >= w.x0 && x + 16 <= w.xn;
+      if (!(all_in && a.do_reset)) v = *reinterpret_cast<const uint4*>(a.master + off);
+      if (all_in) {
+        if (a.do_reset) {
+          const uint32_t d4 = a.def * 0x01010101u;
+          v = make_uint4(d4, d4, d4, d4);
+        }
+        for (int l = 0; l < a.ml.n; ++l) {
+          const uint4 lv = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
+          const int pol = a.ml.policy[l];
+          v.x = merge4(v.x, lv.x, pol);
+          v.y = merge4(v.y, lv.y, pol);
+          v.z = merge4(v.z, lv.z, pol);
+          v.w = merge4(v.w, lv.w, pol);
+        }
+      } else if (any_in) {  // group straddles the window edge: per-cell path
+        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        for (int l = -1; l < a.ml.n; ++l) {
+          uint4 lv4 = make_uint4(0, 0, 0, 0);
+          if (l >= 0) lv4 = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
+          const uint32_t lw[4] = {lv4.x, lv4.y, lv4.z, lv4.w};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int cx = x + i;
+            if (cx < w.x0 || cx >= w.xn) continue;
+            const int sh = 8 * (i & 3);
+            uint8_t m = (uint8_t)(vv[i >> 2] >> sh);
+            if (l < 0) { if (a.do_reset) m = a.def; }
+            else m = apply_policy(m, (uint8_t)(lw[i >> 2] >> sh), a.ml.policy[l]);
+            vv[i >> 2] = (vv[i >> 2] & ~(0xffu << sh)) | ((uint32_t)m << sh);
+          }
+        }
+        v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+      }
+      if (y >= sy0 && y < syn) {
+        const uint32_t lb = lethal_bits4(v.x) | (lethal_bits4(v.y) << 4) | (lethal_bits4(v.z) << 8) | (lethal_bits4(v.w) << 12);
+        const int lo = min(16, max(0, sx0 - x)), hi = min(16, max(0, sxn - x));
+        seed16 = lb & ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      }
+      // cells past the last column are padding: keep them zero in the tile
+      if (x + 16 > (int)a.sx) {
+        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        for (int i = 0; i < 16; ++i)
+          if (x + i >= (int)a.sx) vv[i >> 2] &= ~(0xffu << (8 * (i & 3)));
+        v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+      }
+    }
+    reinterpret_cast<uint16_t*>(bits)[row * (kFWords * 2) + grp] = (uint16_t)seed16;
+    if (row >= R && row < R + kFTY && grp >= 2 && grp < 2 + kFTX / 16)
+      *reinterpret_cast<uint4*>(tile + (row - R) * kFTX + (grp - 2) * 16) = v;
+  }
+  __syncthreads();
+
+  // ---- phase 2: squared horizontal distances for the rows that have seeds
+  {
+    const int seg = warp & 3, sub = warp >> 2;
+    uint32_t local[4] = {0, 0, 0, 0};
+    for (int r = sub; r < rows; r += 2) {
+      const uint32_t* wr = bits + r * kFWords + 2 * seg;
+      const uint32_t W0 = wr[0], W1 = wr[1], W2 = wr[2], W3 = wr[3];
+      if ((W0 | W1 | W2 | W3) == 0) continue;
+      local[r >> 5] |= 1u << (r & 31);
+      const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
+      uint32_t packed = 0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int sh = (2 * lane + c) & 31;
+        const uint32_t right = __funnelshift_r(B, C, sh);        // bit k   <-> dx = +k
+        const uint32_t left = __funnelshift_rc(A, B, sh + 1);    // bit 31-k <-> dx = -k
+        int d = 64;
+        if (right) d = __ffs(right) - 1;
+        if (left) d = min(d, __clz(left));
+        const uint32_t hh = d <= R ? (uint32_t)(d * d) : kH2Inf;
+        packed |= hh << (16 * c);
+      }
+      h2[r * (kFTX / 2) + seg * 32 + lane] = packed;
+    }
+    if (lane == 0)
+      for (int k = 0; k < 4; ++k)
+        if (local[k]) atomicOr(&rowmask[seg * 4 + k], local[k]);
+  }
+  __syncthreads();
+
+  // ---- phase 3 + epilogue
+  {
+    const int seg = warp & 3, half = warp >> 2;
+    const uint32_t R2 = (uint32_t)(R * R);
+    for (int g = 0; g < 4; ++g) {
+      const int yr0 = half * 32 + g * 8;  // first tile row of this group; its region rows are yr0 .. yr0 + 7 + 2R
+      uint32_t acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0xffffffffu;
+      const int lo = yr0, hi = yr0 + 8 + 2 * R;  // region-row range [lo, hi)
+      for (int wd = lo >> 5; wd <= (hi - 1) >> 5; ++wd) {
+        uint32_t m = rowmask[seg * 4 + wd];
+        const int base = wd * 32;
+        if (lo > base) m &= 0xffffffffu << (lo - base);
+        if (hi < base + 32) m &= (1u << (hi - base)) - 1u;
+        while (m) {
+          const int r = base + __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t hh = h2[r * (kFTX / 2) + seg * 32 + lane];
+          const uint32_t* sqp = sq + 64 + (r - R - yr0);  // dy of row k is (r - R) - (yr0 + k)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = __viaddmin_u16x2(hh, sqp[-k], acc[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t da = acc[k] & 0xffffu, db = acc[k] >> 16;
+        if (da <= R2 || db <= R2) {
+          uint16_t* cp = reinterpret_cast<uint16_t*>(tile + (yr0 + k) * kFTX + seg * 64 + 2 * lane);
+          const uint16_t cur = *cp;
+          uint8_t va = (uint8_t)(cur & 0xff), vb = (uint8_t)(cur >> 8);
+          if (da <= R2) va = inflate_combine(va, table[da]);
+          if (db <= R2) vb = inflate_combine(vb, table[db]);
+          *cp = (uint16_t)(va | (vb << 8));
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  for (int item = tid; item < kFTX * kFTY / 16; item += kFThreads) {
+    const int r = item / (kFTX / 16), c = (item - r * (kFTX / 16)) * 16;
+    const int y = ty0 + r, x = tx0 + c;
+    if (y < (int)a.sy && x < (int)a.pitch)
+      *reinterpret_cast<uint4*>(a.master + (size_t)y * a.pitch + x) = *reinterpret_cast<const uint4*>(tile + r * kFTX + c);
+  }
+}
+
+inline size_t update_costs_fast_smem(int R) {
+  const int rows = kFTY + 2 * R;
+  return (size_t)kFTX * kFTY + (size_t)kFMaxRows * kFWords * 4 + (size_t)rows * (kFTX / 2) * 4 + 16 * 4 + 128 * 4 +
+         (size_t)R * R + 1 + 16;
+}
+
 inline size_t update_costs_smem(int R) {
   const int HX = (R + 7) & ~7;
   const int groups = (kTX + 2 * HX) / 8;

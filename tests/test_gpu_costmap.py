@@ -114,6 +114,21 @@ def test_inflation_radius_sweep_bit_exact(cuda, port):
         assert np.array_equal(outs[0], outs[1]), f"radius {radius}"
 
 
+def test_generic_and_fast_sweep_kernels_agree(cuda, port):
+    """Both sweep kernels (generic any-R, and the R <= 31 fast path) against the checker on the same map."""
+    g = synth.blocks_c1()
+    expect = None
+    for generic in (False, True):
+        cm, s, o = c1_stack(cuda, g, radius=1.0)
+        cm.force_generic_sweep(generic)
+        cm.update_map(10, 10, 0)
+        if expect is None:
+            b, _, _ = c1_stack(port, g, radius=1.0)
+            b.update_map(10, 10, 0)
+            expect = b.get()
+        assert np.array_equal(cm.get(), expect), f"generic={generic}"
+
+
 def test_plugin_seam_inflate_and_merge_host(cuda, port):
     """navgpu_inflate_host / navgpu_merge_host: the bodies of Layer::updateCosts overrides on a HOST master grid."""
     rng = np.random.default_rng(11)
