@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // Fast variant of the same sweep for R <= 31 cells (every configuration the reference's defaults produce).
 //
-//   tile 256 x 64 cells per CTA (halo 32 columns, R rows), 256 threads, about 75 KB of shared memory at R = 20
+//   tile 256 x 64 cells per CTA (halo 32 columns, R rows), 512 threads, about 75 KB of shared memory at R = 20
 //   phase 1  16 cells per uint4 load; merge policies evaluated on 4 packed bytes per 32-bit op; the LETHAL
 //            predicate becomes one seed bit per cell (10 x 32-bit words per region row)
 //   phase 2  per (row, 64-column segment) that has any seed bit: nearest seed along the row by clz/ffs on funnel-
@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 //   phase 3  each thread owns 2 columns x 8 rows of accumulators and walks only the non-empty rows of its
 //            (8 + 2R)-row window: acc_k = min(acc_k, hx^2 + dy_k^2) is ONE VIADDMNMX.U16x2 per row and cell pair
 //   epilogue table lookup by d^2, InflationLayer's max/NO_INFORMATION rule, uint4 write-back of the whole tile
-constexpr int kFTX = 256, kFTY = 64, kFThreads = 256, kFHalo = 32;
+constexpr int kFTX = 256, kFTY = 64, kFThreads = 512, kFHalo = 32;
+constexpr int kFRowWarps = kFThreads / 32 / 4;  // warps per 64-column segment
 constexpr int kFGroups = (kFTX + 2 * kFHalo) / 16;  // 20 groups of 16 cells per region row
 constexpr int kFWords = (kFTX + 2 * kFHalo) / 32;   // 10 seed words per region row
 constexpr int kFMaxRows = kFTY + 2 * 32;
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(kFThreads) k_update_costs_fast(UpdateArgs a) {
   {
     const int seg = warp & 3, sub = warp >> 2;
     uint32_t local[4] = {0, 0, 0, 0};
-    for (int r = sub; r < rows; r += 2) {
+    for (int r = sub; r < rows; r += kFRowWarps) {
       const uint32_t* wr = bits + r * kFWords + 2 * seg;
       const uint32_t W0 = wr[0], W1 = wr[1], W2 = wr[2], W3 = wr[3];
       if ((W0 | W1 | W2 | W3) == 0) continue;
@@ -701,10 +702,11 @@ __global__ void __launch_bounds__(kFThreads) k_update_costs_fast(UpdateArgs a) {
 
   // ---- phase 3 + epilogue
   {
-    const int seg = warp & 3, half = warp >> 2;
+    const int seg = warp & 3, part = warp >> 2;
     const uint32_t R2 = (uint32_t)(R * R);
-    for (int g = 0; g < 4; ++g) {
-      const int yr0 = half * 32 + g * 8;  // first tile row of this group; its region rows are yr0 .. yr0 + 7 + 2R
+    constexpr int kRowsPerWarp = kFTY / kFRowWarps;
+    for (int g = 0; g < kRowsPerWarp / 8; ++g) {
+      const int yr0 = part * kRowsPerWarp + g * 8;  // first tile row of this group; region rows yr0 .. yr0 + 7 + 2R
       uint32_t acc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = 0xffffffffu;
