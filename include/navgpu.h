@@ -188,9 +188,8 @@ int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel
                            int64_t* n_samples_total);
 /* finish a sharded sweep on every rank: given the all-gathered per-rank (cost,index) minima pick the winner exactly
  * as simple_scored_sampling_planner.cpp:111-116 would, regenerate its trajectory and update the oscillation flags */
-int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double vel[3], const double* costs,
-                              const int64_t* indices, int n_ranks, navgpu_dwa_result* result, double* best_points,
-                              int points_capacity);
+int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double* costs, const int64_t* indices,
+                              int n_ranks, navgpu_dwa_result* result, double* best_points, int points_capacity);
 /* the four MapGrid distance fields after prepare(): which = 0 path, 1 goal, 2 goal_front, 3 alignment (fp64, host) */
 int navgpu_dwa_get_grid(navgpu_dwa* h, int which, double* host_out);
 /* enqueue one full scoring cycle without host synchronisation (timing) */

@@ -105,8 +105,8 @@ SIGNATURES = {
                                             C.c_int, _f64p, C.c_int]),
     "navgpu_dwa_score_range": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.c_int64, C.c_int64, _f64p, _i64p,
                                          _i64p]),
-    "navgpu_dwa_finish_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, _i64p, C.c_int, C.POINTER(DwaResult),
-                                            _f64p, C.c_int]),
+    "navgpu_dwa_finish_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _i64p, C.c_int, C.POINTER(DwaResult), _f64p,
+                                            C.c_int]),
     "navgpu_dwa_get_grid": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
     "navgpu_dwa_find_best_path_async": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int]),
     "navgpu_dwa_synchronize": (C.c_int, [C.c_void_p]),
@@ -333,15 +333,14 @@ class Dwa:
                                                        begin, end, C.byref(cost), C.byref(idx), C.byref(total)))
         return cost.value, idx.value, total.value
 
-    def finish_sharded(self, pose, vel, costs, indices, max_points=4096):
+    def finish_sharded(self, pose, costs, indices, max_points=4096):
         p = np.ascontiguousarray(pose, dtype=np.float64)
-        v = np.ascontiguousarray(vel, dtype=np.float64)
         c = np.ascontiguousarray(costs, dtype=np.float64)
         i = np.ascontiguousarray(indices, dtype=np.int64)
         res = DwaResult()
         pts = np.zeros((max_points, 3))
-        self.api.check(self.lib.navgpu_dwa_finish_sharded(self.h, _p(p, _f64p), _p(v, _f64p), _p(c, _f64p), _p(i, _i64p),
-                                                          c.size, C.byref(res), _p(pts, _f64p), max_points))
+        self.api.check(self.lib.navgpu_dwa_finish_sharded(self.h, _p(p, _f64p), _p(c, _f64p), _p(i, _i64p), c.size,
+                                                          C.byref(res), _p(pts, _f64p), max_points))
         return dict(ok=res.cost >= 0, cost=res.cost, xv=res.xv, yv=res.yv, thetav=res.thetav,
                     best_index=res.best_index, n_samples=res.n_samples, points=pts[:res.n_points].copy())
 

@@ -1,23 +1,608 @@
-// dwa.cu -- Path B (placeholder while the kernels are being written): every entry point reports UNSUPPORTED.
-#include "common.cuh"
+// dwa.cu -- Path B host side: the DWA rollout scorer behind the navgpu_dwa_* C ABI.
+//
+// Mirrors dwa_local_planner::DWAPlanner's wiring of base_local_planner's generator, critics and search
+// (dwa_local_planner/src/dwa_planner.cpp:52-182, 240-371).  Grid work (4x MapGrid wavefront), rollouts, critics and
+// the argmin run in dwa_kernels.cuh; the host keeps the planner's scalar state: configuration, plan geometry,
+// the per-axis velocity samples (VelocityIterator is a 20-entry fp64 accumulation) and the oscillation flags.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "dwa_kernels.cuh"
+
 using namespace navgpu;
-struct navgpu_dwa { int unused; };
-extern "C" {
-void navgpu_dwa_default_config(navgpu_dwa_config* c) { memset(c, 0, sizeof(*c)); }
-#define NB return fail(NAVGPU_ERR_UNSUPPORTED, "Path B not built yet")
-int navgpu_dwa_create(navgpu_dwa**, const navgpu_dwa_config*, uint32_t, uint32_t, double, int) { NB; }
-int navgpu_dwa_destroy(navgpu_dwa*) { return NAVGPU_OK; }
-int navgpu_dwa_reconfigure(navgpu_dwa*, const navgpu_dwa_config*) { NB; }
-int navgpu_dwa_set_costmap(navgpu_dwa*, const uint8_t*, double, double) { NB; }
-int navgpu_dwa_set_costmap_device(navgpu_dwa*, const uint8_t*, uint32_t, double, double) { NB; }
-int navgpu_dwa_set_plan(navgpu_dwa*, const double*, const double*, int) { NB; }
-int navgpu_dwa_reset_oscillation(navgpu_dwa*) { NB; }
-int navgpu_dwa_get_oscillation_mask(navgpu_dwa*, int*) { NB; }
-int navgpu_dwa_find_best_path(navgpu_dwa*, const double*, const double*, const double*, int, navgpu_dwa_result*, double*, int, double*, int) { NB; }
-int navgpu_dwa_score_range(navgpu_dwa*, const double*, const double*, const double*, int, int64_t, int64_t, double*, int64_t*, int64_t*) { NB; }
-int navgpu_dwa_finish_sharded(navgpu_dwa*, const double*, const double*, const double*, const int64_t*, int, navgpu_dwa_result*, double*, int) { NB; }
-int navgpu_dwa_get_grid(navgpu_dwa*, int, double*) { NB; }
-int navgpu_dwa_find_best_path_async(navgpu_dwa*, const double*, const double*, const double*, int) { NB; }
-int navgpu_dwa_synchronize(navgpu_dwa*) { NB; }
-void* navgpu_dwa_stream(navgpu_dwa*) { return nullptr; }
+
+namespace {
+
+struct P2 {
+  double x, y;
+};
+
+// VelocityIterator, base_local_planner/include/base_local_planner/velocity_iterator.h:49-74
+std::vector<double> velocity_samples(double mn, double mx, int n) {
+  std::vector<double> s;
+  if (mn == mx) {
+    s.push_back(mn);
+    return s;
+  }
+  n = std::max(2, n);
+  const double step = (mx - mn) / double(std::max(1, n - 1));
+  double cur, next = mn;
+  for (int j = 0; j < n - 1; ++j) {
+    cur = next;
+    next += step;
+    s.push_back(cur);
+    if (cur < 0 && next > 0) s.push_back(0.0);
+  }
+  s.push_back(mx);
+  return s;
 }
+
+// MapGrid::adjustPlanResolution, base_local_planner/src/map_grid.cpp:135-171 (plan geometry only)
+void adjust_plan_resolution(const std::vector<P2>& in, std::vector<P2>& out, double resolution) {
+  out.clear();
+  if (in.empty()) return;
+  double last_x = in[0].x, last_y = in[0].y;
+  out.push_back(in[0]);
+  const double min_sq_resolution = resolution * resolution * 4;
+  for (size_t i = 1; i < in.size(); ++i) {
+    const double loop_x = in[i].x, loop_y = in[i].y;
+    const double sqdist = (loop_x - last_x) * (loop_x - last_x) + (loop_y - last_y) * (loop_y - last_y);
+    if (sqdist > min_sq_resolution) {
+      const int steps = ((sqrt(sqdist) - sqrt(min_sq_resolution)) / resolution) - 1;
+      const double deltax = (loop_x - last_x) / steps, deltay = (loop_y - last_y) / steps;
+      for (int j = 1; j < steps; ++j) out.push_back(P2{last_x + j * deltax, last_y + j * deltay});
+    }
+    out.push_back(in[i]);
+    last_x = loop_x;
+    last_y = loop_y;
+  }
+}
+
+// OscillationCostFunction's latched state (oscillation_cost_function.h:78-83, .cpp:56-164)
+struct Oscillation {
+  bool strafe_pos_only = false, strafe_neg_only = false, strafing_pos = false, strafing_neg = false;
+  bool rot_pos_only = false, rot_neg_only = false, rotating_pos = false, rotating_neg = false;
+  bool forward_pos_only = false, forward_neg_only = false, forward_pos = false, forward_neg = false;
+  float prev[3] = {0.f, 0.f, 0.f};
+  void reset() {
+    strafe_pos_only = strafe_neg_only = strafing_pos = strafing_neg = false;
+    rot_pos_only = rot_neg_only = rotating_pos = rotating_neg = false;
+    forward_pos_only = forward_neg_only = forward_pos = forward_neg = false;
+  }
+  int mask() const {
+    return int(forward_pos_only) | int(forward_neg_only) << 1 | int(strafe_pos_only) << 2 | int(strafe_neg_only) << 3 |
+           int(rot_pos_only) << 4 | int(rot_neg_only) << 5;
+  }
+  bool set_flags(double xv, double yv, double thv, double min_vel_trans) {
+    bool flag_set = false;
+    if (xv < 0.0) { if (forward_pos) { forward_neg_only = true; flag_set = true; } forward_pos = false; forward_neg = true; }
+    if (xv > 0.0) { if (forward_neg) { forward_pos_only = true; flag_set = true; } forward_neg = false; forward_pos = true; }
+    if (fabs(xv) <= min_vel_trans) {
+      if (yv < 0) { if (strafing_pos) { strafe_neg_only = true; flag_set = true; } strafing_pos = false; strafing_neg = true; }
+      if (yv > 0) { if (strafing_neg) { strafe_pos_only = true; flag_set = true; } strafing_neg = false; strafing_pos = true; }
+      if (thv < 0) { if (rotating_pos) { rot_neg_only = true; flag_set = true; } rotating_pos = false; rotating_neg = true; }
+      if (thv > 0) { if (rotating_neg) { rot_pos_only = true; flag_set = true; } rotating_neg = false; rotating_pos = true; }
+    }
+    return flag_set;
+  }
+  void update(const float pos[3], double cost, double xv, double yv, double thv, double min_vel_trans, double reset_dist,
+              double reset_angle) {
+    if (cost < 0) return;
+    if (set_flags(xv, yv, thv, min_vel_trans)) { prev[0] = pos[0]; prev[1] = pos[1]; prev[2] = pos[2]; }
+    if (forward_pos_only || forward_neg_only || strafe_pos_only || strafe_neg_only || rot_pos_only || rot_neg_only) {
+      const double x_diff = pos[0] - prev[0], y_diff = pos[1] - prev[1];
+      const double sq_dist = x_diff * x_diff + y_diff * y_diff;
+      const double th_diff = pos[2] - prev[2];
+      if (sq_dist > reset_dist * reset_dist || fabs(th_diff) > reset_angle) reset();
+    }
+  }
+};
+
+constexpr int kPointsCapacity = 4096;
+
+struct Cycle {
+  DwaScoreArgs args;
+  long long n_samples = 0;
+};
+
+}  // namespace
+
+struct navgpu_dwa {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  navgpu_dwa_config cfg;
+  unsigned sx = 0, sy = 0;
+  double res = 0;
+  // local costmap: own copy (set_costmap) or a borrowed device grid (set_costmap_device)
+  uint8_t* d_cost_own = nullptr;
+  const uint8_t* d_cost = nullptr;
+  unsigned pitch = 0;
+  double ox = 0, oy = 0;
+  // plans, already resolution-adjusted: 0 global plan, 1 front plan, 2 what the alignment critic last received
+  std::vector<P2> plan;
+  std::vector<P2> adjusted[3];
+  double* d_plan[3] = {nullptr, nullptr, nullptr};
+  size_t plan_capacity[3] = {0, 0, 0};
+  bool plan_dirty[3] = {false, false, false};
+  double alignment_scale = 0, path_scale = 0, goal_scale = 0, obstacle_scale = 0;
+  uint32_t* d_dist[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* d_samples = nullptr;
+  size_t samples_capacity = 0;
+  double* d_block_cost = nullptr;
+  long long* d_block_index = nullptr;
+  size_t block_capacity = 0;
+  unsigned int* d_counters = nullptr;
+  double* d_best_cost = nullptr;
+  long long* d_best_index = nullptr;
+  DwaDeviceResult* d_result = nullptr;
+  double* d_points = nullptr;
+  DwaDeviceResult* h_result = nullptr;  // pinned
+  double* h_points = nullptr;           // pinned
+  double* h_best = nullptr;             // pinned: cost, index (as long long bits)
+  double* d_terms = nullptr;
+  double* d_reported = nullptr;
+  size_t terms_capacity = 0;
+  Oscillation osc;
+  // result_traj_ persists across cycles (dwa_planner.cpp:316, simple_scored_sampling_planner.cpp:123-134)
+  double res_xv = 0, res_yv = 0, res_thv = 0;
+  std::vector<double> res_points;
+  long long n_samples_last = 0;
+  bool have_last = false;
+  Cycle last;  // arguments of the last score_range launch (for finish_sharded)
+};
+
+namespace {
+
+int use_device(navgpu_dwa* h) {
+  NAVGPU_CUDA(cudaSetDevice(h->device));
+  return NAVGPU_OK;
+}
+
+void apply_config(navgpu_dwa* h) {  // DWAPlanner::reconfigure, dwa_planner.cpp:52-112
+  const navgpu_dwa_config& c = h->cfg;
+  h->path_scale = h->res * c.path_distance_bias * 0.5;
+  h->alignment_scale = h->res * c.path_distance_bias * 0.5;
+  h->goal_scale = h->res * c.goal_distance_bias * 0.5;
+  h->obstacle_scale = h->res * c.occdist_scale;
+}
+
+int upload_plan(navgpu_dwa* h, int k) {
+  if (!h->plan_dirty[k]) return NAVGPU_OK;
+  const std::vector<P2>& v = h->adjusted[k];
+  if (v.size() > h->plan_capacity[k]) {
+    if (h->d_plan[k]) cudaFree(h->d_plan[k]);
+    h->d_plan[k] = nullptr;
+    const size_t cap = std::max<size_t>(256, v.size() * 2);
+    NAVGPU_CUDA(cudaMalloc(&h->d_plan[k], cap * sizeof(P2)));
+    h->plan_capacity[k] = cap;
+  }
+  if (!v.empty()) {
+    NAVGPU_CUDA(cudaMemcpyAsync(h->d_plan[k], v.data(), v.size() * sizeof(P2), cudaMemcpyHostToDevice, h->stream));
+    NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // pageable source owned by the handle
+  }
+  h->plan_dirty[k] = false;
+  return NAVGPU_OK;
+}
+
+// SimpleTrajectoryGenerator::initialise, simple_trajectory_generator.cpp:60-135: the per-axis samples
+struct Samples {
+  std::vector<float> v;  // xs | ys | ths
+  int nx = 0, ny = 0, nth = 0;
+};
+Samples enumerate_samples(const navgpu_dwa_config& cfg, const float pos[3], const float vel[3], const float goal[2]) {
+  Samples s;
+  const double max_vel_th = cfg.max_rot_vel, min_vel_th = -1.0 * max_vel_th;
+  const float acc[3] = {float(cfg.acc_lim_x), float(cfg.acc_lim_y), float(cfg.acc_lim_theta)};
+  double min_vel_x = cfg.min_vel_x, max_vel_x = cfg.max_vel_x, min_vel_y = cfg.min_vel_y, max_vel_y = cfg.max_vel_y;
+  const int nx = cfg.vx_samples <= 0 ? 1 : cfg.vx_samples, ny = cfg.vy_samples <= 0 ? 1 : cfg.vy_samples,
+            nth = cfg.vth_samples <= 0 ? 1 : cfg.vth_samples;  // dwa_planner.cpp:86-109
+  float mx[3], mn[3];
+  if (!cfg.use_dwa) {
+    const double dist = hypot(goal[0] - pos[0], goal[1] - pos[1]);
+    max_vel_x = std::max(std::min(max_vel_x, dist / cfg.sim_time), min_vel_x);
+    max_vel_y = std::max(std::min(max_vel_y, dist / cfg.sim_time), min_vel_y);
+    mx[0] = std::min(max_vel_x, vel[0] + acc[0] * cfg.sim_time);
+    mx[1] = std::min(max_vel_y, vel[1] + acc[1] * cfg.sim_time);
+    mx[2] = std::min(max_vel_th, vel[2] + acc[2] * cfg.sim_time);
+    mn[0] = std::max(min_vel_x, vel[0] - acc[0] * cfg.sim_time);
+    mn[1] = std::max(min_vel_y, vel[1] - acc[1] * cfg.sim_time);
+    mn[2] = std::max(min_vel_th, vel[2] - acc[2] * cfg.sim_time);
+  } else {
+    mx[0] = std::min(max_vel_x, vel[0] + acc[0] * cfg.sim_period);
+    mx[1] = std::min(max_vel_y, vel[1] + acc[1] * cfg.sim_period);
+    mx[2] = std::min(max_vel_th, vel[2] + acc[2] * cfg.sim_period);
+    mn[0] = std::max(min_vel_x, vel[0] - acc[0] * cfg.sim_period);
+    mn[1] = std::max(min_vel_y, vel[1] - acc[1] * cfg.sim_period);
+    mn[2] = std::max(min_vel_th, vel[2] - acc[2] * cfg.sim_period);
+  }
+  const std::vector<double> xs = velocity_samples(mn[0], mx[0], nx), ys = velocity_samples(mn[1], mx[1], ny),
+                            ths = velocity_samples(mn[2], mx[2], nth);
+  s.nx = (int)xs.size(); s.ny = (int)ys.size(); s.nth = (int)ths.size();
+  for (double a : xs) s.v.push_back((float)a);
+  for (double a : ys) s.v.push_back((float)a);
+  for (double a : ths) s.v.push_back((float)a);
+  return s;
+}
+
+// uploads the per-cycle inputs and launches the 4 MapGrid wavefronts; fills the scoring arguments
+int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const double* footprint_xy, int n_footprint,
+                Cycle& cy) {
+  NAVGPU_TRY(use_device(h));
+  if (!h->d_cost) return fail(NAVGPU_ERR_INVALID, "no costmap set");
+  if (h->plan.empty()) return fail(NAVGPU_ERR_INVALID, "no plan set");
+  if (n_footprint < 0 || n_footprint > kMaxFootprint) return fail(NAVGPU_ERR_UNSUPPORTED, "footprint with more than %d vertices", kMaxFootprint);
+  const navgpu_dwa_config& c = h->cfg;
+  const float pos[3] = {(float)pose[0], (float)pose[1], (float)pose[2]};  // Eigen::Vector3f, dwa_planner.cpp:303-306
+  const float vel[3] = {(float)velv[0], (float)velv[1], (float)velv[2]};
+  const float goal[2] = {(float)h->plan.back().x, (float)h->plan.back().y};
+  Samples s = enumerate_samples(c, pos, vel, goal);
+  if (s.v.size() > h->samples_capacity) {
+    if (h->d_samples) cudaFree(h->d_samples);
+    h->d_samples = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&h->d_samples, s.v.size() * 2 * sizeof(float)));
+    h->samples_capacity = s.v.size() * 2;
+  }
+  NAVGPU_CUDA(cudaMemcpyAsync(h->d_samples, s.v.data(), s.v.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // pageable source
+  for (int k = 0; k < 3; ++k) NAVGPU_TRY(upload_plan(h, k));
+
+  DwaGeom g{h->d_cost, h->sx, h->sy, h->pitch, h->res, h->ox, h->oy};
+  // prepare() of the critics (simple_scored_sampling_planner.cpp:87-93): four wavefronts, one CTA each
+  MapGridArgs ma;
+  ma.g = g;
+  ma.allow_unknown = c.allow_unknown;
+  ma.job[0] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 0, h->d_dist[0]};  // path: setTargetCells
+  ma.job[1] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 1, h->d_dist[1]};  // goal: setLocalGoal
+  ma.job[2] = MapGridJob{h->d_plan[1], (int)h->adjusted[1].size(), 1, h->d_dist[2]};  // goal_front
+  ma.job[3] = MapGridJob{h->d_plan[2], (int)h->adjusted[2].size(), 0, h->d_dist[3]};  // alignment
+  const int W = (h->sx + 31) / 32;
+  const size_t mg_smem = size_t(4) * W * h->sy * sizeof(uint32_t);
+  if (mg_smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap %ux%u too large for the MapGrid kernel", h->sx, h->sy);
+  if (mg_smem > 48 * 1024)
+    NAVGPU_CUDA(cudaFuncSetAttribute(k_mapgrid_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg_smem));
+  k_mapgrid_prepare<<<4, kMapGridThreads, mg_smem, h->stream>>>(ma, 4);
+  NAVGPU_LAUNCHED(1);
+
+  DwaScoreArgs& a = cy.args;
+  a.g = g;
+  for (int k = 0; k < 4; ++k) a.dist[k] = h->d_dist[k];
+  a.vxs = h->d_samples;
+  a.vys = h->d_samples + s.nx;
+  a.vths = h->d_samples + s.nx + s.ny;
+  a.nx = s.nx; a.ny = s.ny; a.nth = s.nth;
+  cy.n_samples = (long long)s.nx * s.ny * s.nth;
+  a.begin = 0;
+  a.end = cy.n_samples;
+  for (int k = 0; k < 3; ++k) { a.pos[k] = pos[k]; a.vel[k] = vel[k]; }
+  a.acc[0] = (float)c.acc_lim_x; a.acc[1] = (float)c.acc_lim_y; a.acc[2] = (float)c.acc_lim_theta;
+  a.min_trans_vel = c.min_trans_vel; a.max_trans_vel = c.max_trans_vel; a.min_rot_vel = c.min_rot_vel;
+  a.sim_time = c.sim_time; a.sim_granularity = c.sim_granularity; a.angular_sim_granularity = c.angular_sim_granularity;
+  a.use_dwa = c.use_dwa; a.sum_scores = c.sum_scores; a.allow_unknown = c.allow_unknown;
+  a.osc_mask = h->osc.mask();
+  a.scale_obstacle = h->obstacle_scale;
+  a.scale_goal_front = h->goal_scale;
+  a.scale_alignment = h->alignment_scale;
+  a.scale_path = h->path_scale;
+  a.scale_goal = h->goal_scale;
+  a.xshift = c.forward_point_distance;
+  a.nfp = n_footprint;
+  for (int k = 0; k < n_footprint; ++k) { a.fpx[k] = footprint_xy[2 * k]; a.fpy[k] = footprint_xy[2 * k + 1]; }
+  a.all_terms = nullptr;
+  a.counters = h->d_counters;
+  a.best_cost = h->d_best_cost;
+  a.best_index = h->d_best_index;
+  h->n_samples_last = cy.n_samples;
+  return NAVGPU_OK;
+}
+
+int launch_score(navgpu_dwa* h, Cycle& cy) {
+  DwaScoreArgs& a = cy.args;
+  const long long n = a.end - a.begin;
+  if (n <= 0) return fail(NAVGPU_ERR_INVALID, "empty sample range");
+  const long long blocks = (n + kDwaWarpsPerBlock - 1) / kDwaWarpsPerBlock;
+  if (blocks > 0x7fffffffLL) return fail(NAVGPU_ERR_UNSUPPORTED, "too many samples in one launch");
+  if ((size_t)blocks > h->block_capacity) {
+    if (h->d_block_cost) cudaFree(h->d_block_cost);
+    if (h->d_block_index) cudaFree(h->d_block_index);
+    h->d_block_cost = nullptr;
+    h->d_block_index = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&h->d_block_cost, blocks * sizeof(double)));
+    NAVGPU_CUDA(cudaMalloc(&h->d_block_index, blocks * sizeof(long long)));
+    h->block_capacity = blocks;
+  }
+  a.block_cost = h->d_block_cost;
+  a.block_index = h->d_block_index;
+  NAVGPU_CUDA(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned int), h->stream));
+  k_dwa_score<<<(unsigned)blocks, kDwaWarpsPerBlock * 32, 0, h->stream>>>(a);
+  NAVGPU_LAUNCHED(1);
+  return NAVGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void navgpu_dwa_default_config(navgpu_dwa_config* c) {
+  // base_local_planner/src/local_planner_limits/__init__.py:15-45, dwa_local_planner/cfg/DWAPlanner.cfg:15-43
+  c->max_trans_vel = 0.55; c->min_trans_vel = 0.1; c->max_vel_x = 0.55; c->min_vel_x = 0.0;
+  c->max_vel_y = 0.1; c->min_vel_y = -0.1; c->max_rot_vel = 1.0; c->min_rot_vel = 0.4;
+  c->acc_lim_x = 2.5; c->acc_lim_y = 2.5; c->acc_lim_theta = 3.2;
+  c->sim_time = 1.7; c->sim_granularity = 0.025; c->angular_sim_granularity = 0.1; c->sim_period = 0.05;
+  c->path_distance_bias = 32.0; c->goal_distance_bias = 24.0; c->occdist_scale = 0.01;
+  c->forward_point_distance = 0.325; c->cheat_factor = 1.0;
+  c->oscillation_reset_dist = 0.05; c->oscillation_reset_angle = 0.2;
+  c->scaling_speed = 0.25; c->max_scaling_factor = 0.2;
+  c->vx_samples = 3; c->vy_samples = 10; c->vth_samples = 20;
+  c->use_dwa = 1; c->sum_scores = 0; c->allow_unknown = 0;
+}
+
+int navgpu_dwa_create(navgpu_dwa** out, const navgpu_dwa_config* cfg, uint32_t size_x, uint32_t size_y,
+                      double resolution, int device) {
+  if (!out || !cfg || size_x == 0 || size_y == 0 || !(resolution > 0)) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (navgpu_device_count() <= device) return fail(NAVGPU_ERR_CUDA, "no CUDA device %d (libnavgpu has no CPU fallback)", device);
+  if ((unsigned long long)size_x * size_y + 1 >= 0xffffffffull) return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap too large");
+  std::unique_ptr<navgpu_dwa> h(new navgpu_dwa);
+  h->device = device;
+  h->cfg = *cfg;
+  h->sx = size_x; h->sy = size_y; h->res = resolution;
+  NAVGPU_CUDA(cudaSetDevice(device));
+  NAVGPU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; ++k) NAVGPU_CUDA(cudaMalloc(&h->d_dist[k], size_t(size_x) * size_y * sizeof(uint32_t)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_counters, 2 * sizeof(unsigned int)));
+  NAVGPU_CUDA(cudaMemset(h->d_counters, 0, 2 * sizeof(unsigned int)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_best_cost, sizeof(double)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_best_index, sizeof(long long)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_result, sizeof(DwaDeviceResult)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_points, size_t(kPointsCapacity) * 3 * sizeof(double)));
+  NAVGPU_CUDA(cudaMallocHost(&h->h_result, sizeof(DwaDeviceResult)));
+  NAVGPU_CUDA(cudaMallocHost(&h->h_points, size_t(kPointsCapacity) * 3 * sizeof(double)));
+  NAVGPU_CUDA(cudaMallocHost(&h->h_best, 2 * sizeof(double)));
+  apply_config(h.get());
+  *out = h.release();
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_destroy(navgpu_dwa* h) {
+  if (!h) return NAVGPU_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_cost_own);
+  for (int k = 0; k < 3; ++k) cudaFree(h->d_plan[k]);
+  for (int k = 0; k < 4; ++k) cudaFree(h->d_dist[k]);
+  cudaFree(h->d_samples); cudaFree(h->d_block_cost); cudaFree(h->d_block_index); cudaFree(h->d_counters);
+  cudaFree(h->d_best_cost); cudaFree(h->d_best_index); cudaFree(h->d_result); cudaFree(h->d_points);
+  cudaFree(h->d_terms); cudaFree(h->d_reported);
+  cudaFreeHost(h->h_result); cudaFreeHost(h->h_points); cudaFreeHost(h->h_best);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_reconfigure(navgpu_dwa* h, const navgpu_dwa_config* cfg) {
+  if (!h || !cfg) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  h->cfg = *cfg;
+  apply_config(h);
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_set_costmap(navgpu_dwa* h, const uint8_t* host_grid, double origin_x, double origin_y) {
+  if (!h || !host_grid) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_TRY(use_device(h));
+  const unsigned pitch = grid_pitch(h->sx);
+  if (!h->d_cost_own) NAVGPU_CUDA(cudaMalloc(&h->d_cost_own, size_t(pitch) * h->sy));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(h->d_cost_own, pitch, host_grid, h->sx, h->sx, h->sy, cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  h->d_cost = h->d_cost_own;
+  h->pitch = pitch;
+  h->ox = origin_x;
+  h->oy = origin_y;
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_set_costmap_device(navgpu_dwa* h, const uint8_t* dev_grid, uint32_t pitch, double origin_x, double origin_y) {
+  if (!h || !dev_grid || pitch < h->sx) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  h->d_cost = dev_grid;
+  h->pitch = pitch;
+  h->ox = origin_x;
+  h->oy = origin_y;
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_set_plan(navgpu_dwa* h, const double pose[3], const double* plan_xy, int n) {  // dwa_planner.cpp:240-286
+  if (!h || !pose || !plan_xy || n <= 0) return fail(NAVGPU_ERR_INVALID, "bad plan");
+  h->plan.resize(n);
+  for (int i = 0; i < n; ++i) h->plan[i] = P2{plan_xy[2 * i], plan_xy[2 * i + 1]};
+  adjust_plan_resolution(h->plan, h->adjusted[0], h->res);
+  h->plan_dirty[0] = true;
+  const P2 goal = h->plan.back();
+  const float pos[3] = {(float)pose[0], (float)pose[1], (float)pose[2]};
+  const double sq_dist = (pos[0] - goal.x) * (pos[0] - goal.x) + (pos[1] - goal.y) * (pos[1] - goal.y);
+  std::vector<P2> front = h->plan;
+  const double angle_to_goal = atan2(goal.y - pos[1], goal.x - pos[0]);
+  front.back().x = front.back().x + h->cfg.forward_point_distance * cos(angle_to_goal);
+  front.back().y = front.back().y + h->cfg.forward_point_distance * sin(angle_to_goal);
+  adjust_plan_resolution(front, h->adjusted[1], h->res);
+  h->plan_dirty[1] = true;
+  if (sq_dist > h->cfg.forward_point_distance * h->cfg.forward_point_distance * h->cfg.cheat_factor) {
+    h->alignment_scale = h->res * h->cfg.path_distance_bias * 0.5;
+    h->adjusted[2] = h->adjusted[0];
+    h->plan_dirty[2] = true;
+  } else {
+    h->alignment_scale = 0.0;  // the alignment critic keeps the target poses it had (:282-285)
+  }
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_reset_oscillation(navgpu_dwa* h) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  h->osc.reset();
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_get_oscillation_mask(navgpu_dwa* h, int* mask_out) {
+  if (!h || !mask_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  *mask_out = h->osc.mask();
+  return NAVGPU_OK;
+}
+
+static int finish_and_collect(navgpu_dwa* h, Cycle& cy, long long forced_index, const double pose[3],
+                              navgpu_dwa_result* result, double* best_points, int points_capacity) {
+  k_dwa_finish<<<1, 32, 0, h->stream>>>(cy.args, forced_index, h->d_result, h->d_points, kPointsCapacity);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaGetLastError());
+  NAVGPU_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(DwaDeviceResult), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(h->h_points, h->d_points, size_t(kPointsCapacity) * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  const DwaDeviceResult& r = *h->h_result;
+  if (r.cost >= 0) {
+    h->res_xv = r.xv; h->res_yv = r.yv; h->res_thv = r.thetav;
+    h->res_points.assign(h->h_points, h->h_points + size_t(3) * r.n_points);
+  }
+  const float pos[3] = {(float)pose[0], (float)pose[1], (float)pose[2]};
+  // oscillation_costs_.updateOscillationFlags(pos, &result_traj_, min_trans_vel), dwa_planner.cpp:357
+  h->osc.update(pos, r.cost, h->res_xv, h->res_yv, h->res_thv, h->cfg.min_trans_vel, h->cfg.oscillation_reset_dist,
+                h->cfg.oscillation_reset_angle);
+  if (result) {
+    result->cost = r.cost;
+    result->xv = h->res_xv; result->yv = h->res_yv; result->thetav = h->res_thv;
+    result->best_index = (int32_t)r.best_index;
+    result->n_samples = (int32_t)cy.n_samples;
+    result->n_scored = r.n_scored;
+    result->n_points = (int32_t)(h->res_points.size() / 3);
+  }
+  if (best_points) {
+    const size_t n = std::min<size_t>(h->res_points.size() / 3, (size_t)std::max(0, points_capacity));
+    memcpy(best_points, h->res_points.data(), n * 3 * sizeof(double));
+  }
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_find_best_path(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                              int n_footprint, navgpu_dwa_result* result, double* all_costs, int all_capacity,
+                              double* best_points, int points_capacity) {
+  if (!h || !pose || !vel || (n_footprint > 0 && !footprint_xy)) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  Cycle cy;
+  NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy));
+  if (all_costs) {
+    const size_t need = size_t(cy.n_samples);
+    if (need > h->terms_capacity) {
+      if (h->d_terms) cudaFree(h->d_terms);
+      if (h->d_reported) cudaFree(h->d_reported);
+      h->d_terms = h->d_reported = nullptr;
+      NAVGPU_CUDA(cudaMalloc(&h->d_terms, need * 6 * sizeof(double)));
+      NAVGPU_CUDA(cudaMalloc(&h->d_reported, need * sizeof(double)));
+      h->terms_capacity = need;
+    }
+    cy.args.all_terms = h->d_terms;
+  }
+  NAVGPU_TRY(launch_score(h, cy));
+  if (all_costs) {
+    k_dwa_report<<<1, 1024, 0, h->stream>>>(h->d_terms, h->d_reported, cy.n_samples);
+    NAVGPU_LAUNCHED(1);
+  }
+  NAVGPU_TRY(finish_and_collect(h, cy, -1, pose, result, best_points, points_capacity));
+  if (all_costs) {
+    const size_t n = std::min<size_t>((size_t)cy.n_samples, (size_t)std::max(0, all_capacity));
+    NAVGPU_CUDA(cudaMemcpy(all_costs, h->d_reported, n * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_find_best_path_async(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                                    int n_footprint) {
+  if (!h || !pose || !vel) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  Cycle cy;
+  NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy));
+  NAVGPU_TRY(launch_score(h, cy));
+  k_dwa_finish<<<1, 32, 0, h->stream>>>(cy.args, -1, h->d_result, h->d_points, kPointsCapacity);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaGetLastError());
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                           int n_footprint, int64_t begin, int64_t end, double* best_cost, int64_t* best_index,
+                           int64_t* n_samples_total) {
+  if (!h || !pose || !vel || !best_cost || !best_index) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  Cycle cy;
+  NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy));
+  if (n_samples_total) *n_samples_total = cy.n_samples;
+  begin = std::max<int64_t>(0, begin);
+  end = std::min<int64_t>(cy.n_samples, end);
+  if (end <= begin) {
+    h->last = cy;
+    h->have_last = true;
+    *best_cost = std::numeric_limits<double>::infinity();
+    *best_index = -1;
+    NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+    return NAVGPU_OK;
+  }
+  cy.args.begin = begin;
+  cy.args.end = end;
+  NAVGPU_TRY(launch_score(h, cy));
+  NAVGPU_CUDA(cudaGetLastError());
+  h->last = cy;
+  h->have_last = true;
+  NAVGPU_CUDA(cudaMemcpyAsync(&h->h_best[0], h->d_best_cost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(&h->h_best[1], h->d_best_index, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  *best_cost = h->h_best[0];
+  long long idx;
+  memcpy(&idx, &h->h_best[1], sizeof(idx));
+  *best_index = idx;
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double* costs, const int64_t* indices,
+                              int n_ranks, navgpu_dwa_result* result, double* best_points, int points_capacity) {
+  if (!h || !pose || !costs || !indices || n_ranks <= 0) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (!h->have_last) return fail(NAVGPU_ERR_INVALID, "navgpu_dwa_score_range must run first");
+  NAVGPU_TRY(use_device(h));
+  // every rank applies the same rule: smallest cost, lowest sample index on ties == "first strictly smaller"
+  // (simple_scored_sampling_planner.cpp:111-116)
+  double bc = std::numeric_limits<double>::infinity();
+  long long bi = -1;
+  for (int r = 0; r < n_ranks; ++r)
+    if (indices[r] >= 0 && (bi < 0 || costs[r] < bc || (costs[r] == bc && indices[r] < bi))) {
+      bc = costs[r];
+      bi = indices[r];
+    }
+  Cycle cy = h->last;
+  if (bi < 0) {  // nothing valid anywhere: result_traj_.cost_ = -7, flags untouched
+    if (result) {
+      result->cost = -7.0;
+      result->xv = h->res_xv; result->yv = h->res_yv; result->thetav = h->res_thv;
+      result->best_index = -1;
+      result->n_samples = (int32_t)cy.n_samples;
+      result->n_scored = 0;
+      result->n_points = (int32_t)(h->res_points.size() / 3);
+    }
+    return NAVGPU_OK;
+  }
+  return finish_and_collect(h, cy, bi, pose, result, best_points, points_capacity);
+}
+
+int navgpu_dwa_get_grid(navgpu_dwa* h, int which, double* host_out) {
+  if (!h || which < 0 || which > 3 || !host_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_TRY(use_device(h));
+  const size_t n = size_t(h->sx) * h->sy;
+  std::vector<uint32_t> tmp(n);
+  NAVGPU_CUDA(cudaMemcpyAsync(tmp.data(), h->d_dist[which], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < n; ++i) host_out[i] = (double)tmp[i];
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_synchronize(navgpu_dwa* h) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+void* navgpu_dwa_stream(navgpu_dwa* h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"

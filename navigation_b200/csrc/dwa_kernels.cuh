@@ -1,0 +1,633 @@
+// dwa_kernels.cuh -- Path B device code: DWA rollout scoring on the GPU (sm_100a).
+//
+// Reference semantics (file:line under /root/reference) are cited next to each piece; the host side that
+// sequences the kernels per DWAPlanner::findBestPath is in dwa.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace navgpu {
+
+constexpr int kMaxFootprint = 16;
+constexpr int kDwaWarpsPerBlock = 8;
+
+struct DwaGeom {
+  const uint8_t* cost;  // local costmap, row pitch `pitch`
+  unsigned sx, sy, pitch;
+  double res, ox, oy;
+};
+
+__device__ __forceinline__ bool dwa_world_to_map(const DwaGeom& g, double wx, double wy, int& mx, int& my) {
+  // Costmap2D::worldToMap, costmap_2d/src/costmap_2d.cpp:208-220
+  if (wx < g.ox || wy < g.oy) return false;
+  const unsigned ux = (unsigned)(int)((wx - g.ox) / g.res), uy = (unsigned)(int)((wy - g.oy) / g.res);
+  mx = (int)ux;
+  my = (int)uy;
+  return ux < g.sx && uy < g.sy;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MapGridCostFunction::prepare for the four grids of DWAPlanner (path, goal, goal_front, alignment):
+// MapGrid::resetPathDist + setTargetCells | setLocalGoal + computeTargetDistance
+// (base_local_planner/src/map_grid_cost_function.cpp:59-68, src/map_grid.cpp:127-133, 174-310).
+//
+// One CTA per grid.  The FIFO wavefront with unit edge costs is order independent, so it is evaluated level by level
+// on bit planes held in shared memory: frontier F, visited V, passable P, one 32-cell word per thread step:
+//     touched = (F<<1 | F>>1 | F(up) | F(down)) & ~V       cells first touched at this level (updatePathCell)
+//     dist[touched & ~P] = size_x*size_y (obstacleCosts, not expanded),  dist[touched & P] = level + 1
+// A seed is expanded even when it lies on an obstacle, exactly like the reference's queue.  Untouched cells keep
+// size_x*size_y + 1 (unreachableCellCosts).
+struct MapGridJob {
+  const double* plan_xy;  // already passed through MapGrid::adjustPlanResolution on the host (pure plan geometry)
+  int n_points;
+  int local_goal;  // setLocalGoal (last seed only) vs setTargetCells
+  uint32_t* dist;  // sx*sy, row-major, no pitch
+};
+struct MapGridArgs {
+  DwaGeom g;
+  int allow_unknown;
+  MapGridJob job[4];
+};
+
+constexpr int kMapGridThreads = 512;
+
+__global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare(MapGridArgs a, int jobs_per_robot) {
+  extern __shared__ uint32_t mg_smem[];
+  const MapGridJob job = a.job[blockIdx.x % jobs_per_robot];
+  const DwaGeom g = a.g;
+  const int W = (g.sx + 31) / 32, NW = W * (int)g.sy;
+  uint32_t* P = mg_smem;
+  uint32_t* V = P + NW;
+  uint32_t* F0 = V + NW;
+  uint32_t* F1 = F0 + NW;
+  __shared__ int s_first, s_end;
+  const int tid = threadIdx.x;
+  const uint32_t n_cells = g.sx * g.sy;
+
+  for (uint32_t i = tid; i < n_cells; i += kMapGridThreads) job.dist[i] = n_cells + 1;  // resetPathDist
+  for (int wi = tid; wi < NW; wi += kMapGridThreads) {
+    const int r = wi / W, w = wi - r * W;
+    uint32_t p = 0;
+    const uint8_t* row = g.cost + (size_t)r * g.pitch + w * 32;
+    const int nbits = min(32, (int)g.sx - w * 32);
+    for (int b = 0; b < nbits; ++b) {
+      const uint8_t c = row[b];
+      const bool obstacle = c == kLethal || c == kInscribed || (c == kNoInfo && !a.allow_unknown);  // map_grid.cpp:109-116
+      p |= (uint32_t)(!obstacle) << b;
+    }
+    P[wi] = p;
+    V[wi] = 0;
+    F0[wi] = 0;
+    F1[wi] = 0;
+  }
+  if (tid == 0) {
+    s_first = 0x7fffffff;
+    s_end = job.n_points;
+  }
+  __syncthreads();
+
+  // seeds: plan points from the first one that is on the map and not NO_INFORMATION until the plan first leaves the
+  // map again (map_grid.cpp:189-202 / :225-239)
+  auto point_ok = [&](int i, int& mx, int& my) -> bool {
+    const double wx = job.plan_xy[2 * i], wy = job.plan_xy[2 * i + 1];
+    if (!dwa_world_to_map(g, wx, wy, mx, my)) return false;
+    return g.cost[(size_t)my * g.pitch + mx] != kNoInfo;
+  };
+  for (int i = tid; i < job.n_points; i += kMapGridThreads) {
+    int mx, my;
+    if (point_ok(i, mx, my)) atomicMin(&s_first, i);
+  }
+  __syncthreads();
+  const int first = s_first;
+  if (first == 0x7fffffff) return;  // nothing on the map: every cell stays unreachable
+  for (int i = first + 1 + tid; i < job.n_points; i += kMapGridThreads) {
+    int mx, my;
+    if (!point_ok(i, mx, my)) atomicMin(&s_end, i);
+  }
+  __syncthreads();
+  const int end = s_end;
+  for (int i = (job.local_goal ? end - 1 : first) + tid; i < end; i += kMapGridThreads) {
+    int mx, my;
+    point_ok(i, mx, my);
+    const int wi = my * W + (mx >> 5);
+    atomicOr(&F0[wi], 1u << (mx & 31));
+    atomicOr(&V[wi], 1u << (mx & 31));
+    job.dist[(size_t)my * g.sx + mx] = 0;
+  }
+  __syncthreads();
+
+  uint32_t* F = F0;
+  uint32_t* Fn = F1;
+  for (uint32_t level = 0;; ++level) {
+    int any = 0;
+    for (int wi = tid; wi < NW; wi += kMapGridThreads) {
+      const int r = wi / W, w = wi - r * W;
+      const uint32_t f = F[wi];
+      uint32_t nb = (f << 1) | (f >> 1);
+      if (w > 0) nb |= F[wi - 1] >> 31;
+      if (w + 1 < W) nb |= F[wi + 1] << 31;
+      if (r > 0) nb |= F[wi - W];
+      if (r + 1 < (int)g.sy) nb |= F[wi + W];
+      const int nbits = (int)g.sx - w * 32;
+      if (nbits < 32) nb &= (1u << nbits) - 1u;
+      const uint32_t v = V[wi];
+      const uint32_t touched = nb & ~v;
+      uint32_t next = 0;
+      if (touched) {
+        V[wi] = v | touched;
+        const uint32_t p = P[wi];
+        next = touched & p;
+        uint32_t t = touched;
+        uint32_t* drow = job.dist + (size_t)r * g.sx + w * 32;
+        while (t) {
+          const int b = __ffs(t) - 1;
+          t &= t - 1;
+          drow[b] = ((p >> b) & 1u) ? level + 1 : n_cells;
+        }
+      }
+      Fn[wi] = next;
+      any |= next != 0;
+    }
+    if (!__syncthreads_or(any)) break;
+    uint32_t* tmp = F;
+    F = Fn;
+    Fn = tmp;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rollout + the six critics + argmin: SimpleTrajectoryGenerator::generateTrajectory
+// (base_local_planner/src/simple_trajectory_generator.cpp:180-276), OscillationCostFunction::scoreTrajectory
+// (src/oscillation_cost_function.cpp:166-176), ObstacleCostFunction::scoreTrajectory + CostmapModel::footprintCost
+// (src/obstacle_cost_function.cpp:74-142, src/costmap_model.cpp:50-142, include/base_local_planner/world_model.h:65-86,
+// line_iterator.h:38-139), MapGridCostFunction::scoreTrajectory (src/map_grid_cost_function.cpp:75-129) and
+// SimpleScoredSamplingPlanner::scoreTrajectory/findBestTrajectory (src/simple_scored_sampling_planner.cpp:50-142).
+//
+// One warp per velocity sample, one lane per trajectory point.  The float32 Euler state is a sequential recurrence
+// (every step rounds to float), but its trig terms depend only on the heading sequence, which is a cheap scalar
+// recurrence: all lanes replay theta, each lane evaluates cos/sin for its own step in fp64, and the x/y prefix is
+// accumulated with shuffles in the reference's order and rounding.  No FMA contraction (-fmad=false).
+struct DwaScoreArgs {
+  DwaGeom g;
+  const uint32_t* dist[4];  // 0 path, 1 goal, 2 goal_front, 3 alignment
+  const float* vxs;
+  const float* vys;
+  const float* vths;
+  int nx, ny, nth;
+  long long begin, end;  // sample index range scored by this launch
+  float pos[3], vel[3], acc[3];
+  double min_trans_vel, max_trans_vel, min_rot_vel;
+  double sim_time, sim_granularity, angular_sim_granularity;
+  int use_dwa, sum_scores, allow_unknown, osc_mask;
+  double scale_obstacle, scale_goal_front, scale_alignment, scale_path, scale_goal;
+  double xshift;
+  int nfp;
+  double fpx[kMaxFootprint], fpy[kMaxFootprint];
+  double* all_terms;   // nullable: 6 doubles per sample of [begin, end): per-critic scaled cost or negative code
+  double* block_cost;  // per-CTA minimum
+  long long* block_index;
+  unsigned int* counters;  // [0] CTAs done, [1] samples the generator accepted
+  double* best_cost;       // final (cost, index) of the range; +inf / -1 when none valid
+  long long* best_index;
+};
+
+struct TrajResult {
+  double cost;  // total per SimpleScoredSamplingPlanner::scoreTrajectory with best_traj_cost = -1 (no early exit)
+  bool generated;
+  int num_steps;
+};
+
+__device__ __forceinline__ double nan_quiet() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// CostmapModel::footprintCost for one pose, given cos/sin of its heading; < 0 means illegal
+__device__ double footprint_cost(const DwaScoreArgs& a, double x, double y, double cos_th, double sin_th) {
+  const DwaGeom& g = a.g;
+  int cx, cy;
+  if (!dwa_world_to_map(g, x, y, cx, cy)) return -1.0;
+  if (a.nfp < 3) {
+    const uint8_t c = g.cost[(size_t)cy * g.pitch + cx];
+    if (c == kLethal || c == kInscribed || (c == kNoInfo && !a.allow_unknown)) return -1.0;
+    return c;
+  }
+  int fx0, fy0, px, py;
+  {
+    const double wx = x + (a.fpx[0] * cos_th - a.fpy[0] * sin_th), wy = y + (a.fpx[0] * sin_th + a.fpy[0] * cos_th);
+    if (!dwa_world_to_map(g, wx, wy, fx0, fy0)) return -1.0;
+  }
+  px = fx0;
+  py = fy0;
+  int best = 0;
+  for (int e = 0; e < a.nfp; ++e) {
+    int qx, qy;
+    if (e + 1 < a.nfp) {
+      const double wx = x + (a.fpx[e + 1] * cos_th - a.fpy[e + 1] * sin_th);
+      const double wy = y + (a.fpx[e + 1] * sin_th + a.fpy[e + 1] * cos_th);
+      if (!dwa_world_to_map(g, wx, wy, qx, qy)) return -1.0;
+    } else {
+      qx = fx0;
+      qy = fy0;
+    }
+    // LineIterator from (px,py) to (qx,qy), both end points included
+    const int dx = abs(qx - px), dy = abs(qy - py);
+    const int xinc = qx >= px ? 1 : -1, yinc = qy >= py ? 1 : -1;
+    int cxx = px, cyy = py;
+    int den, num, numadd, n;
+    const bool xmajor = dx >= dy;
+    if (xmajor) { den = dx; num = dx / 2; numadd = dy; n = dx; }
+    else { den = dy; num = dy / 2; numadd = dx; n = dy; }
+    for (int k = 0; k <= n; ++k) {
+      const uint8_t c = g.cost[(size_t)cyy * g.pitch + cxx];
+      if (c == kLethal || (c == kNoInfo && !a.allow_unknown)) return -1.0;  // CostmapModel::pointCost :133-142
+      best = max(best, (int)c);
+      num += numadd;
+      if (num >= den) {
+        num -= den;
+        if (xmajor) cyy += yinc; else cxx += xinc;
+      }
+      if (xmajor) cxx += xinc; else cyy += yinc;
+    }
+    px = qx;
+    py = qy;
+  }
+  return (double)best;
+}
+
+// scores one velocity sample with a whole warp; points_out (nullable) receives 3 doubles per trajectory point
+__device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int lane, double* terms_out,
+                                   double* points_out, int points_capacity) {
+  TrajResult res;
+  res.cost = nan_quiet();
+  res.generated = false;
+  res.num_steps = 0;
+  const int ith = (int)(sample % a.nth);
+  const long long t1 = sample / a.nth;
+  const int iy = (int)(t1 % a.ny), ix = (int)(t1 / a.ny);
+  const float svx = a.vxs[ix], svy = a.vys[iy], svth = a.vths[ith];
+
+  // generateTrajectory :186-216
+  const double vmag = hypot((double)svx, (double)svy);
+  const double eps = 1e-4;
+  if ((a.min_trans_vel >= 0 && vmag + eps < a.min_trans_vel) && (a.min_rot_vel >= 0 && fabs((double)svth) + eps < a.min_rot_vel))
+    return res;
+  if (a.max_trans_vel >= 0 && vmag - eps > a.max_trans_vel) return res;
+  const double sim_time_distance = vmag * a.sim_time;
+  const double sim_time_angle = fabs((double)svth) * a.sim_time;
+  const int num_steps = (int)ceil(fmax(sim_time_distance / a.sim_granularity, sim_time_angle / a.angular_sim_granularity));
+  if (num_steps <= 0) return res;
+  const double dt = a.sim_time / num_steps;
+  res.generated = true;
+  res.num_steps = num_steps;
+
+  const bool continued = !a.use_dwa;
+  float lvx = svx, lvy = svy, lvth = svth;  // loop_vel
+  auto new_vel = [&](float v, float target, float acc) -> float {  // computeNewVelocities :265-276
+    if (v < target) return (float)fmin((double)target, v + acc * dt);
+    return (float)fmax((double)target, v - acc * dt);
+  };
+  if (continued) {
+    lvx = new_vel(a.vel[0], svx, a.acc[0]);
+    lvy = new_vel(a.vel[1], svy, a.acc[1]);
+    lvth = new_vel(a.vel[2], svth, a.acc[2]);
+  }
+  const float txv = lvx, tyv = lvy, tthv = lvth;  // traj.xv_, yv_, thetav_
+
+  // OscillationCostFunction (scale 1): sign of the sampled velocity against the latched flags
+  const double xv = txv, yv = tyv, thv = tthv;
+  const int m = a.osc_mask;
+  const bool osc_bad = ((m & 1) && xv < 0.0) || ((m & 2) && xv > 0.0) || ((m & 4) && yv < 0.0) ||
+                       ((m & 8) && yv > 0.0) || ((m & 16) && thv < 0.0) || ((m & 32) && thv > 0.0);
+
+  float sx = a.pos[0], sy = a.pos[1], sth = a.pos[2];  // state at the first point of the current round
+  bool obst_fail = false;
+  double obst_sum = 0.0, obst_last = 0.0;
+  // per map-grid critic: code of the first failing point (0 = none yet) and the value at the last point
+  double grid_code[4] = {0, 0, 0, 0}, grid_last[4] = {0, 0, 0, 0};
+
+  for (int base = 0; base < num_steps; base += 32) {
+    const int cnt = min(32, num_steps - base);
+    // heading (and velocity) recurrence, replayed by every lane; lane l keeps the values of step base + l
+    float th = sth, my_th = sth, my_vx = lvx, my_vy = lvy;
+    for (int l = 0; l < cnt; ++l) {
+      if (lane == l) my_th = th;
+      if (continued) {
+        lvx = new_vel(lvx, svx, a.acc[0]);
+        lvy = new_vel(lvy, svy, a.acc[1]);
+        lvth = new_vel(lvth, svth, a.acc[2]);
+      }
+      if (lane == l) { my_vx = lvx; my_vy = lvy; }
+      th = (float)((double)th + lvth * dt);  // computeNewPositions :258
+    }
+    // trig of my own step, fp64 on the float heading (:256-257)
+    const double thd = (double)my_th;
+    double c, s;
+    sincos(thd, &s, &c);
+    double ddx = my_vx * c, ddy = my_vx * s;
+    if (my_vy != 0.0f) {
+      ddx = ddx + my_vy * cos(M_PI_2 + thd);
+      ddy = ddy + my_vy * sin(M_PI_2 + thd);
+    } else {
+      ddx = ddx + 0.0;
+      ddy = ddy + 0.0;
+    }
+    ddx = ddx * dt;
+    ddy = ddy * dt;
+    // x / y prefix in the reference's order: pos = float(pos + delta) per step
+    float x = sx, y = sy, my_x = sx, my_y = sy;
+    for (int l = 0; l < cnt; ++l) {
+      if (lane == l) { my_x = x; my_y = y; }
+      const double dxl = __shfl_sync(0xffffffffu, ddx, l), dyl = __shfl_sync(0xffffffffu, ddy, l);
+      x = (float)((double)x + dxl);
+      y = (float)((double)y + dyl);
+    }
+    sx = x;
+    sy = y;
+    sth = th;
+
+    const bool active = lane < cnt;
+    const double px = my_x, py = my_y;
+    if (points_out && active && base + lane < points_capacity) {
+      points_out[3 * (base + lane)] = px;
+      points_out[3 * (base + lane) + 1] = py;
+      points_out[3 * (base + lane) + 2] = thd;
+    }
+    // ---- obstacle critic on my point
+    double occ = 0.0;
+    bool fail = false;
+    if (active) {
+      const double f = a.nfp == 0 ? -9.0 : footprint_cost(a, px, py, c, s);
+      if (f < 0) fail = true;
+      else {
+        int cx, cy;
+        dwa_world_to_map(a.g, px, py, cx, cy);  // cannot fail here: footprintCost checked the centre first
+        occ = fmax(fmax(0.0, f), (double)a.g.cost[(size_t)cy * a.g.pitch + cx]);
+      }
+    }
+    obst_fail |= __any_sync(0xffffffffu, fail);
+    double ssum = occ;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);  // small integers: exact
+    obst_sum += ssum;
+    obst_last = __shfl_sync(0xffffffffu, occ, cnt - 1);
+    // ---- the four map-grid critics on my point
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool shifted = k >= 2;        // goal_front, alignment use xshift (dwa_planner.cpp:80-81)
+      const bool stop_on_failure = k < 2;  // path, goal (:126-127 turn it off for the other two)
+      double code = 0.0, d = 0.0;
+      if (active) {
+        double qx = px, qy = py;
+        if (shifted && a.xshift != 0.0) {
+          qx = qx + a.xshift * c;
+          qy = qy + a.xshift * s;
+        }
+        int cx, cy;
+        if (!dwa_world_to_map(a.g, qx, qy, cx, cy)) code = -4.0;
+        else {
+          const uint32_t dd = a.dist[k][(size_t)cy * a.g.sx + cx];
+          const uint32_t n_cells = a.g.sx * a.g.sy;
+          d = (double)dd;
+          if (stop_on_failure) {
+            if (dd == n_cells) code = -3.0;
+            else if (dd == n_cells + 1) code = -2.0;
+          }
+        }
+      }
+      const unsigned failing = __ballot_sync(0xffffffffu, code != 0.0);
+      if (failing && grid_code[k] == 0.0) grid_code[k] = __shfl_sync(0xffffffffu, code, __ffs(failing) - 1);
+      grid_last[k] = __shfl_sync(0xffffffffu, d, cnt - 1);
+    }
+  }
+
+  // SimpleScoredSamplingPlanner::scoreTrajectory with critics in DWAPlanner's order (dwa_planner.cpp:167-173)
+  const double raw[6] = {osc_bad ? -5.0 : 0.0,
+                         a.nfp == 0 ? -9.0 : (obst_fail ? -6.0 : (a.sum_scores ? obst_sum : obst_last)),
+                         grid_code[2] != 0.0 ? grid_code[2] : grid_last[2],
+                         grid_code[3] != 0.0 ? grid_code[3] : grid_last[3],
+                         grid_code[0] != 0.0 ? grid_code[0] : grid_last[0],
+                         grid_code[1] != 0.0 ? grid_code[1] : grid_last[1]};
+  const double scale[6] = {1.0, a.scale_obstacle, a.scale_goal_front, a.scale_alignment, a.scale_path, a.scale_goal};
+  double total = 0.0;
+  bool done = false;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double term = 0.0;  // what this critic adds; negative = rejecting code; skipped critics add nothing
+    if (scale[k] != 0.0) {
+      double cst = raw[k];
+      if (cst < 0) term = cst;
+      else {
+        if (cst != 0) cst *= scale[k];
+        term = cst;
+      }
+    }
+    if (terms_out && lane == 0) terms_out[k] = scale[k] == 0.0 ? 0.0 : term;
+    if (!done) {
+      if (term < 0) {
+        total = term;
+        done = true;
+      } else {
+        total += term;
+      }
+    }
+  }
+  res.cost = total;
+  return res;
+}
+
+// lexicographic (cost, index) minimum: the reference keeps the FIRST sample with the strictly smallest cost
+__device__ __forceinline__ bool better(double c1, long long i1, double c2, long long i2) {
+  return c1 < c2 || (c1 == c2 && i1 < i2);
+}
+
+__global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreArgs a) {
+  __shared__ double s_cost[kDwaWarpsPerBlock];
+  __shared__ long long s_index[kDwaWarpsPerBlock];
+  __shared__ int s_generated[kDwaWarpsPerBlock];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long sample = a.begin + (long long)blockIdx.x * kDwaWarpsPerBlock + warp;
+  double cost = INFINITY;
+  long long index = -1;
+  int generated = 0;
+  if (sample < a.end) {
+    double* terms = a.all_terms ? a.all_terms + 6 * (sample - a.begin) : nullptr;
+    const TrajResult r = score_sample(a, sample, lane, terms, nullptr, 0);
+    generated = r.generated;
+    if (terms && !r.generated && lane == 0)
+      for (int k = 0; k < 6; ++k) terms[k] = nan_quiet();
+    if (r.generated && r.cost >= 0) {
+      cost = r.cost;
+      index = sample;
+    }
+  }
+  if (lane == 0) {
+    s_cost[warp] = cost;
+    s_index[warp] = index;
+    s_generated[warp] = generated;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bc = INFINITY;
+    long long bi = -1;
+    int gen = 0;
+    for (int wdx = 0; wdx < kDwaWarpsPerBlock; ++wdx) {
+      gen += s_generated[wdx];
+      if (s_index[wdx] >= 0 && (bi < 0 || better(s_cost[wdx], s_index[wdx], bc, bi))) {
+        bc = s_cost[wdx];
+        bi = s_index[wdx];
+      }
+    }
+    a.block_cost[blockIdx.x] = bc;
+    a.block_index[blockIdx.x] = bi;
+    if (gen) atomicAdd(&a.counters[1], (unsigned)gen);
+    __threadfence();
+    s_last = atomicAdd(&a.counters[0], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // the last CTA to finish reduces the per-CTA minima
+  __threadfence();
+  double bc = INFINITY;
+  long long bi = -1;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    const double c = a.block_cost[i];
+    const long long ix = a.block_index[i];
+    if (ix >= 0 && (bi < 0 || better(c, ix, bc, bi))) {
+      bc = c;
+      bi = ix;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (bi < 0 || better(oc, oi, bc, bi))) {
+      bc = oc;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    s_cost[warp] = bc;
+    s_index[warp] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bc = INFINITY;
+    bi = -1;
+    for (int wdx = 0; wdx < kDwaWarpsPerBlock; ++wdx)
+      if (s_index[wdx] >= 0 && (bi < 0 || better(s_cost[wdx], s_index[wdx], bc, bi))) {
+        bc = s_cost[wdx];
+        bi = s_index[wdx];
+      }
+    *a.best_cost = bc;
+    *a.best_index = bi;
+    a.counters[0] = 0;  // re-armed for the next launch (counters[1] is read and cleared by k_dwa_finish)
+  }
+}
+
+// Result record copied back to the host after k_dwa_finish
+struct DwaDeviceResult {
+  double cost, xv, yv, thetav;
+  long long best_index;
+  int n_points, n_scored;
+};
+
+// Regenerates the winning trajectory (its points are what findBestTrajectory copies out, :123-134).
+// When forced_index >= 0 that sample is used instead of *best_index (sharded sweeps).
+__global__ void k_dwa_finish(DwaScoreArgs a, long long forced_index, DwaDeviceResult* out, double* points,
+                             int points_capacity) {
+  const int lane = threadIdx.x & 31;
+  const long long idx = forced_index >= 0 ? forced_index : *a.best_index;
+  TrajResult r;
+  r.cost = -7.0;
+  r.generated = false;
+  r.num_steps = 0;
+  if (idx >= 0) r = score_sample(a, idx, lane, nullptr, points, points_capacity);
+  if (lane == 0) {
+    out->best_index = idx;
+    out->n_scored = (int)a.counters[1];
+    a.counters[1] = 0;
+    if (idx >= 0 && r.generated && r.cost >= 0) {
+      const int ith = (int)(idx % a.nth);
+      const long long t1 = idx / a.nth;
+      const int iy = (int)(t1 % a.ny), ix = (int)(t1 / a.ny);
+      float vx = a.vxs[ix], vy = a.vys[iy], vth = a.vths[ith];
+      if (!a.use_dwa) {  // traj.xv_ is the first accelerated velocity (:221-227)
+        const double dt = a.sim_time / r.num_steps;
+        auto nv = [&](float v, float target, float acc) -> float {
+          if (v < target) return (float)fmin((double)target, v + acc * dt);
+          return (float)fmax((double)target, v - acc * dt);
+        };
+        vx = nv(a.vel[0], vx, a.acc[0]);
+        vy = nv(a.vel[1], vy, a.acc[1]);
+        vth = nv(a.vel[2], vth, a.acc[2]);
+      }
+      out->cost = r.cost;
+      out->xv = vx;
+      out->yv = vy;
+      out->thetav = vth;
+      out->n_points = min(r.num_steps, points_capacity);
+    } else {
+      out->cost = -7.0;  // dwa_planner.cpp:316
+      out->best_index = -1;
+      out->n_points = -1;  // host keeps its stale velocities / points, like result_traj_ does
+    }
+  }
+}
+
+// all_explored costs exactly as the sequential search reports them (simple_scored_sampling_planner.cpp:50-79,
+// 99-110): a sample's critic sum stops at the first critic after which it exceeds the best cost found BEFORE it.
+// One CTA walks the samples in order carrying that running best.
+__global__ void k_dwa_report(const double* __restrict__ terms, double* __restrict__ reported, long long n) {
+  __shared__ double s_full[1024];
+  __shared__ double s_prefix[1024];
+  __shared__ double s_carry;
+  if (threadIdx.x == 0) s_carry = -1.0;  // best_traj_cost = -1
+  __syncthreads();
+  for (long long base = 0; base < n; base += blockDim.x) {
+    const long long i = base + threadIdx.x;
+    double t[6];
+    double full = nan_quiet();
+    bool gen = false;
+    if (i < n) {
+      for (int k = 0; k < 6; ++k) t[k] = terms[6 * i + k];
+      gen = !isnan(t[0]);
+      if (gen) {
+        full = 0.0;
+        for (int k = 0; k < 6; ++k) {
+          if (t[k] < 0) { full = t[k]; break; }
+          full += t[k];
+        }
+      }
+    }
+    s_full[threadIdx.x] = (gen && full >= 0) ? full : INFINITY;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive running minimum over this chunk, seeded with the carry
+      double best = s_carry;
+      for (int j = 0; j < (int)blockDim.x; ++j) {
+        s_prefix[j] = best;
+        const double f = s_full[j];
+        if (f != INFINITY && (best < 0 || f < best)) best = f;
+      }
+      s_carry = best;
+    }
+    __syncthreads();
+    if (i < n) {
+      double rep = nan_quiet();
+      if (gen) {
+        const double best = s_prefix[threadIdx.x];
+        rep = 0.0;
+        for (int k = 0; k < 6; ++k) {
+          // a critic with scale 0 is skipped before the early-exit test: its stored term is exactly 0 and the
+          // running sum cannot newly exceed best, so testing after it is equivalent
+          if (t[k] < 0) { rep = t[k]; break; }
+          rep += t[k];
+          if (best > 0 && rep > best) break;
+        }
+      }
+      reported[i] = rep;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace navgpu

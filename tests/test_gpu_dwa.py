@@ -1,0 +1,132 @@
+"""Path B parity: the CUDA DWA scorer (through the C ABI) against the CPU checker and the reference's goldens.
+
+Tolerance (BASELINE.json north_star): trajectory costs within 1e-5 relative, identical best trajectory.  In practice
+everything below is asserted bit-exact first (fp64 sums without FMA contraction, integer grids) and only falls back
+to the 1e-5 comparison where CUDA's cos/sin (<= 2 ulp) could differ from glibc's in the last bit.
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import scenarios as sc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def assert_cycles_match(a, b):
+    exact = 0
+    for c, (x, y) in enumerate(zip(a, b)):
+        assert sc.dwa_results_equal(x, y, rtol=RTOL), (
+            f"cycle {c}: best {x['best_index']} vs {y['best_index']}, cost {x['cost']} vs {y['cost']}, "
+            f"n {x['n_samples']}/{x['n_scored']} vs {y['n_samples']}/{y['n_scored']}, mask {x['mask']} vs {y['mask']}")
+        exact += sc.dwa_results_equal(x, y, rtol=0.0)
+    return exact
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_dwa_scenarios_match_checker(cuda, port, seed):
+    """Multi-cycle findBestPath: 4 MapGrid wavefronts, sample enumeration, rollout, six critics, argmin, oscillation
+    flags; random sample counts, holonomic / non-holonomic, use_dwa on/off, sum_scores on/off."""
+    assert_cycles_match(sc.run_dwa_scenario(cuda, port, seed), sc.run_dwa_scenario(port, port, seed))
+
+
+@pytest.mark.parametrize("seed,path", gu.dwa_cases())
+def test_dwa_golden_fixtures(cuda, port, seed, path):
+    gu.check_dwa_case(cuda, port, seed, path, rtol=RTOL)
+
+
+def c2_setup(api, grid_api, **over):
+    """Config C2: 6 m x 6 m rolling local costmap @0.05 (120x120), 20 x 1 x 20 samples, sim_time 1.7 s, pentagon
+    footprint, corridor world inflated by the checker."""
+    rng = np.random.default_rng(42)
+    grid = sc.local_costmap(grid_api, rng, style="corridor")
+    cfg = dict(vx_samples=20, vy_samples=1, vth_samples=20, max_vel_y=0.0, min_vel_y=0.0)
+    cfg.update(over)
+    d = api.dwa(120, 120, 0.05, **cfg)
+    d.set_costmap(grid, 0.0, 0.0)
+    pose, vel = (1.5, 3.0, 0.0), (0.3, 0.0, 0.0)
+    plan = np.stack([np.arange(1.0, 7.0, 0.05), np.full(120, 3.0)], 1)
+    d.set_plan(pose, plan)
+    return d, pose, vel
+
+
+def test_c2_bit_exact_selection_and_costs(cuda, port):
+    a, pose, vel = c2_setup(cuda, port)
+    b, _, _ = c2_setup(port, port)
+    ra = a.find_best_path(pose, vel, sc.PENTAGON)
+    rb = b.find_best_path(pose, vel, sc.PENTAGON)
+    assert ra["n_samples"] == rb["n_samples"] and ra["n_samples"] in (400, 420)
+    assert ra["best_index"] == rb["best_index"] and ra["ok"]
+    assert np.allclose(ra["costs"], rb["costs"], rtol=RTOL, atol=0, equal_nan=True)
+    assert ra["cost"] == pytest.approx(rb["cost"], rel=RTOL)
+    assert (ra["xv"], ra["yv"], ra["thetav"]) == (rb["xv"], rb["yv"], rb["thetav"])
+    assert np.allclose(ra["points"], rb["points"], rtol=RTOL, atol=1e-12)
+    for k in range(4):
+        assert np.array_equal(a.grid(k), b.grid(k))
+
+
+def test_sharded_sweep_equals_single_search(cuda, port):
+    """Sample-range sharding (config C4's multi-GPU scheme) on one GPU: per-shard (cost, index) minima combined with
+    the lowest-index tie rule reproduce the unsharded search, whatever the shard boundaries."""
+    over = dict(vx_samples=30, vy_samples=3, vth_samples=25, acc_lim_x=20.0, acc_lim_theta=20.0)
+    a, pose, vel = c2_setup(cuda, port, **over)
+    single = a.find_best_path(pose, vel, sc.PENTAGON, want_costs=False)
+    b, _, _ = c2_setup(cuda, port, **over)
+    n = single["n_samples"]
+    for shards in (2, 3, 8):
+        b.reset_oscillation()
+        cuts = np.linspace(0, n, shards + 1).astype(np.int64)
+        costs, idx = [], []
+        for r in range(shards):
+            c, i, total = b.score_range(pose, vel, sc.PENTAGON, int(cuts[r]), int(cuts[r + 1]))
+            assert total == n
+            costs.append(c)
+            idx.append(i)
+        res = b.finish_sharded(pose, costs, idx)
+        assert res["best_index"] == single["best_index"] and res["cost"] == single["cost"]
+        assert np.array_equal(res["points"], single["points"])
+    ref, _, _ = c2_setup(port, port, **over)
+    rr = ref.find_best_path(pose, vel, sc.PENTAGON)
+    assert rr["best_index"] == single["best_index"] and rr["cost"] == pytest.approx(single["cost"], rel=RTOL)
+
+
+def test_dense_sweep_reduced_c4(cuda, port):
+    """Config C4 at reduced density (60 x 12 x 60 ~ 45 k samples incl. inserted zeros) against the checker."""
+    over = dict(vx_samples=60, vy_samples=12, vth_samples=60, acc_lim_x=20.0, acc_lim_y=20.0, acc_lim_theta=20.0,
+                max_vel_y=0.1, min_vel_y=-0.1)
+    a, pose, vel = c2_setup(cuda, port, **over)
+    b, _, _ = c2_setup(port, port, **over)
+    ra = a.find_best_path(pose, vel, sc.PENTAGON)
+    rb = b.find_best_path(pose, vel, sc.PENTAGON)
+    assert ra["n_samples"] == rb["n_samples"] > 40000 and ra["n_scored"] == rb["n_scored"]
+    assert ra["best_index"] == rb["best_index"]
+    assert np.allclose(ra["costs"], rb["costs"], rtol=RTOL, atol=0, equal_nan=True)
+    # how many per-sample costs are bit-identical (informational; cos/sin last-bit differences are the only source)
+    same = np.sum((ra["costs"] == rb["costs"]) | (np.isnan(ra["costs"]) & np.isnan(rb["costs"])))
+    assert same >= 0.999 * ra["n_samples"]
+
+
+def test_no_valid_trajectory_keeps_stale_result(cuda, port):
+    """Boxed in by lethal cells: cost -7, velocities/points keep the previous cycle's values (result_traj_ semantics)."""
+    grid = np.zeros((120, 120), np.uint8)
+    outs = []
+    for api in (cuda, port):
+        d = api.dwa(120, 120, 0.05, vx_samples=5, vy_samples=1, vth_samples=5, max_vel_y=0.0, min_vel_y=0.0)
+        d.set_costmap(grid, 0.0, 0.0)
+        pose, vel = (3.0, 3.0, 0.0), (0.2, 0.0, 0.0)
+        plan = np.stack([np.arange(3.0, 5.5, 0.05), np.full(50, 3.0)], 1)
+        d.set_plan(pose, plan)
+        r1 = d.find_best_path(pose, vel, sc.PENTAGON)
+        g2 = grid.copy()
+        g2[50:70, 50:70] = 254
+        d.set_costmap(g2, 0.0, 0.0)
+        r2 = d.find_best_path(pose, vel, sc.PENTAGON)
+        outs.append((r1, r2))
+    (a1, a2), (b1, b2) = outs
+    assert a1["ok"] and b1["ok"] and not a2["ok"] and not b2["ok"]
+    assert a2["cost"] == b2["cost"] == -7.0
+    assert (a2["xv"], a2["thetav"]) == (b2["xv"], b2["thetav"]) == (a1["xv"], a1["thetav"])
+    assert np.allclose(a2["points"], b2["points"], rtol=RTOL, atol=1e-12) and len(a2["points"]) == len(a1["points"])
+    assert np.array_equal(a2["costs"], b2["costs"], equal_nan=True)
