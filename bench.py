@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 
 C3 = dict(size=4000, resolution=0.05, n_obs=8, n_beams=360, scan_range=10.0, inflation_radius=1.0, scaling=10.0)
 ALGO_BYTES_PER_CELL = 3  # read static + read obstacle + write master
+METRIC = "ms per updateMap+inflation @4k^2 grid; DWA trajectories scored/sec"
+WORKLOAD = ("C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, 10 m raytrace+mark) + "
+            "inflation 1.0 m (R=20); DWA half: C2 findBestPath 20x1x20 and C4 sweep 200x20x200 on a 120x120 local map")
 
 
 def env_int(name, default):
@@ -104,15 +107,80 @@ def obs_bytes(obs):
     return sum(o["points"].nbytes + 64 for o in obs)
 
 
+
+C2 = dict(n=120, resolution=0.05, vx_samples=20, vy_samples=1, vth_samples=20)
+C4 = dict(n=120, resolution=0.05, vx_samples=200, vy_samples=20, vth_samples=200)
+PENTAGON = [(-0.325, -0.325), (-0.325, 0.325), (0.325, 0.325), (0.46, 0.0), (0.325, -0.325)]
+
+
+def local_map_c2():
+    """6 m x 6 m local costmap @0.05: corridor walls + one box, inflated (radius 0.55, scaling 10) by the product's own
+    costmap path when a GPU is present, else by the checker (reference arm)."""
+    g = np.zeros((120, 120), np.uint8)
+    g[26:29, :] = 254
+    g[91:94, :] = 254
+    g[52:58, 84:90] = 254
+    return g
+
+
+def inflate_local(api, g, **kw):
+    cm = api.costmap(120, 120, 0.05, **kw)
+    s = cm.add_grid_layer(0)
+    cm.add_inflation_layer(0.55, 10.0)
+    cm.set_footprint(PENTAGON)
+    cm.set_grid_layer(s, g)
+    cm.update_map(0, 0, 0)
+    return cm.get()
+
+
+def dwa_setup(api, grid, cfg, **kw):
+    over = dict(vx_samples=cfg["vx_samples"], vy_samples=cfg["vy_samples"], vth_samples=cfg["vth_samples"])
+    if cfg is C2:
+        over.update(max_vel_y=0.0, min_vel_y=0.0)
+    else:  # C4: wide dynamic window (SURVEY.md section 8d)
+        over.update(acc_lim_x=20.0, acc_lim_y=20.0, acc_lim_theta=20.0, max_vel_y=0.1, min_vel_y=-0.1)
+    d = api.dwa(120, 120, 0.05, **over, **kw)
+    d.set_costmap(grid, 0.0, 0.0)
+    pose, vel = (1.5, 3.0, 0.0), (0.3, 0.0, 0.0)
+    plan = np.stack([np.arange(1.0, 7.0, 0.05), np.full(120, 3.0)], 1)
+    d.set_plan(pose, plan)
+    return d, pose, vel
+
+
+def dwa_cpu_numbers(budget_s=25.0):
+    """Reference CPU code on C2 (latency) and on C4 (throughput, full sweep once: about 20 s on one core)."""
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.available("reference") else "port"
+    api = pyoracle.load(kind)
+    grid = inflate_local(api, local_map_c2())
+    d, pose, vel = dwa_setup(api, grid, C2)
+    d.find_best_path(pose, vel, PENTAGON)
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 20 and time.perf_counter() - t0 < 3.0:
+        r = d.find_best_path(pose, vel, PENTAGON)
+        reps += 1
+    c2_ms = 1e3 * (time.perf_counter() - t0) / reps
+    d4, pose, vel = dwa_setup(api, grid, C4)
+    t0 = time.perf_counter()
+    r4 = d4.find_best_path(pose, vel, PENTAGON)
+    c4_s = time.perf_counter() - t0
+    return {"kind": kind, "cores": 1, "c2_findBestPath_ms": c2_ms, "c2_samples": int(r["n_samples"]),
+            "c4_traj_per_s": r4["n_samples"] / c4_s, "c4_samples": int(r4["n_samples"]), "c4_s": c4_s,
+            "c4_best_index": int(r4["best_index"]), "c2_best_index": int(r["best_index"]),
+            "sample": "C2: mean of up to 20 findBestPath calls; C4: one full 200x20x200 sweep, single thread"}
+
 def run_reference(args, rank):
     """The reference's CPU implementation of the path on the host cores (single-threaded per costmap, as the reference
-    is).  Each step is a bounded sample: the C3 recipe on a 1000x1000 crop, scaled by the cell ratio (x16)."""
+    is).  Each step is one C3 update at full size when K+W of them fit in about four minutes, else the C3 recipe on a
+    1000x1000 crop scaled by the cell ratio."""
     if rank != 0:
         return
     from oracle import pyoracle
     kind = "reference" if pyoracle.available("reference") else "port"
     api = pyoracle.load(kind)
-    sample = 1000
+    full = (args.steps + args.warmup) * 4.0 < 240.0
+    sample = C3["size"] if full else 1000
     cm, (s, o, il), sets = build_c3(api.costmap, size=sample)
     scale = (C3["size"] / sample) ** 2
     times = []
@@ -126,17 +194,19 @@ def run_reference(args, rank):
         if step >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times)) * scale
+    what = ("one full C3 update per step" if full else
+            f"C3 recipe on a {sample}x{sample} crop per step, time scaled by the cell ratio x{scale:g}")
     line = {
-        "impl": "reference", "metric": "ms per updateMap+inflation @4k^2 grid", "value": ms, "unit": "ms",
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, "
-                               "10 m raytrace+mark) + inflation 1.0 m (R=20)"},
-        "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": kind,
-                         "sample": f"C3 recipe on a {sample}x{sample} crop per step, time scaled by the cell ratio x{scale:g}"},
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": kind, "sample": what},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_dwa:
+        line["dwa"] = dwa_cpu_numbers()
     print(json.dumps(line), flush=True)
 
 
@@ -153,6 +223,69 @@ def cpu_baseline_c3():
     ms = 1e3 * (time.perf_counter() - t0)
     return {"value": ms, "unit": "ms", "cores": 1, "kind": kind,
             "sample": "one full C3 update (4000x4000, R=20, 8x360 beams), single thread as the reference runs it"}
+
+
+
+def run_native_dwa(api, torch, dist, rank, world, local_rank, steps):
+    """C2 latency (synchronous findBestPath through the C ABI, host pose in / result out) and C4 throughput.
+    With world > 1 the C4 sample range is sharded over the ranks: each scores its slice, the per-rank (cost, index)
+    minima are all-gathered over NCCL and every rank finishes with the same winner."""
+    dev = f"cuda:{local_rank}"
+    grid = inflate_local(api, local_map_c2(), device=local_rank)
+    out = {}
+    d2, pose, vel = dwa_setup(api, grid, C2, device=local_rank)
+    for _ in range(5):
+        r2 = d2.find_best_path(pose, vel, PENTAGON, want_costs=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = max(20, steps)
+    for _ in range(reps):
+        r2 = d2.find_best_path(pose, vel, PENTAGON, want_costs=False)
+    out["c2_findBestPath_us"] = 1e6 * (time.perf_counter() - t0) / reps
+    out["c2_samples"] = int(r2["n_samples"])
+    out["c2_best_index"] = int(r2["best_index"])
+    out["c2_traj_per_s"] = r2["n_samples"] / (out["c2_findBestPath_us"] * 1e-6)
+
+    d4, pose, vel = dwa_setup(api, grid, C4, device=local_rank)
+    stream = torch.cuda.ExternalStream(d4.stream(), device=local_rank)
+    c, i, total = d4.score_range(pose, vel, PENTAGON, 0, 1)
+    lo, hi = (total * rank) // world, (total * (rank + 1)) // world
+    buf = torch.zeros(2, dtype=torch.float64, device=dev)
+    gathered = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+
+    def one_sweep():
+        c, i, _ = d4.score_range(pose, vel, PENTAGON, lo, hi)
+        if dist is None:
+            return d4.finish_sharded(pose, [c], [i])
+        buf[0], buf[1] = c, float(i)  # indices < 2^53 are exact in fp64
+        dist.all_gather_into_tensor(gathered, buf)
+        g = gathered.cpu().numpy().reshape(world, 2)
+        return d4.finish_sharded(pose, g[:, 0], g[:, 1].astype(np.int64))
+
+    for _ in range(3):
+        r4 = one_sweep()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_sweeps = max(5, steps)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(n_sweeps):
+        r4 = one_sweep()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / n_sweeps
+    sweep_s = max(wall, 1e-3 * e0.elapsed_time(e1) / n_sweeps)
+    if dist is not None:
+        t = torch.tensor([sweep_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sweep_s = float(t.item())
+    out.update({"c4_samples": int(total), "c4_sweep_ms": 1e3 * sweep_s, "c4_traj_per_s": total / sweep_s,
+                "c4_best_index": int(r4["best_index"]), "c4_best_cost": float(r4["cost"]),
+                "c4_sharding": f"sample range split over {world} rank(s), all_gather of (cost, index)" if world > 1
+                else "single GPU"})
+    return out
 
 
 def run_native(args, rank, world, local_rank):
@@ -246,6 +379,9 @@ def run_native(args, rank, world, local_rank):
     e2e_ms = max(e0.elapsed_time(e1) / args.steps, e2e_wall_ms)
     clocks = sampler.summary()
 
+    dwa = None if args.no_dwa else run_native_dwa(api, torch, dist, rank, world, local_rank, args.steps)
+    launches = api.launch_count() - launches0 if not args.no_dwa else launches
+
     if dist is not None:
         t = torch.tensor([ms_per_step, e2e_ms, hot_ms, float(np.mean(sweep_ms))], device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -260,11 +396,10 @@ def run_native(args, rank, world, local_rank):
         peak, peak_src = measured_peak_gbs()
         achieved = ALGO_BYTES_PER_CELL * n_cells / (sweep * 1e-3) / 1e9
         line = {
-            "metric": "ms per updateMap+inflation @4k^2 grid", "value": ms_per_step, "unit": "ms",
+            "metric": METRIC, "value": ms_per_step, "unit": "ms",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, "
-                                   "10 m raytrace+mark) + inflation 1.0 m (R=20)",
+            "config": {"workload": WORKLOAD,
                        "l2": "flushed (256 MiB memset) before every timed cycle",
                        "multi_gpu": "replicas only for the costmap path" if world > 1 else "single GPU",
                        "hot_l2_ms_per_step": hot_ms},
@@ -276,8 +411,12 @@ def run_native(args, rank, world, local_rank):
                          "traffic": None, "kernel": "k_update_costs", "kernel_ms": sweep,
                          "algorithmic_bytes": ALGO_BYTES_PER_CELL * n_cells, "peak_source": peak_src},
         }
+        if dwa is not None:
+            line["dwa"] = dwa
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_c3()
+            if dwa is not None:
+                line["dwa"]["cpu_baseline"] = dwa_cpu_numbers()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -290,6 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dwa", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
