@@ -249,7 +249,7 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // pageable source
   for (int k = 0; k < 3; ++k) NAVGPU_TRY(upload_plan(h, k));
 
-  DwaGeom g{h->d_cost, h->sx, h->sy, h->pitch, h->res, h->ox, h->oy};
+  DwaGeom g{h->d_cost, h->sx, h->sy, h->pitch, h->res, h->ox, h->oy, 1.0 / h->res};
   // prepare() of the critics (simple_scored_sampling_planner.cpp:87-93): four wavefronts, one CTA each
   MapGridArgs ma;
   ma.g = g;

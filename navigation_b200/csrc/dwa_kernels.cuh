@@ -15,12 +15,23 @@ struct DwaGeom {
   const uint8_t* cost;  // local costmap, row pitch `pitch`
   unsigned sx, sy, pitch;
   double res, ox, oy;
+  double inv_res;  // 1 / res, only ever used through exact_cell
 };
+
+// (int)(d / res) exactly as IEEE division + truncation would give it, without paying for the division on the common
+// path: d * (1/res) is within a few ulp of d / res, so the truncated integers can only differ when the quotient is
+// within 1e-9 (relative) of an integer -- only then is the real division evaluated.
+__device__ __forceinline__ int exact_cell(double d, double res, double inv_res) {
+  const double q = d * inv_res;
+  const double r = rint(q);
+  if (fabs(q - r) <= 1e-9 * fmax(1.0, fabs(q))) return (int)(d / res);
+  return (int)q;
+}
 
 __device__ __forceinline__ bool dwa_world_to_map(const DwaGeom& g, double wx, double wy, int& mx, int& my) {
   // Costmap2D::worldToMap, costmap_2d/src/costmap_2d.cpp:208-220
   if (wx < g.ox || wy < g.oy) return false;
-  const unsigned ux = (unsigned)(int)((wx - g.ox) / g.res), uy = (unsigned)(int)((wy - g.oy) / g.res);
+  const unsigned ux = (unsigned)exact_cell(wx - g.ox, g.res, g.inv_res), uy = (unsigned)exact_cell(wy - g.oy, g.res, g.inv_res);
   mx = (int)ux;
   my = (int)uy;
   return ux < g.sx && uy < g.sy;
@@ -199,62 +210,49 @@ struct TrajResult {
 
 __device__ __forceinline__ double nan_quiet() { return __longlong_as_double(0x7ff8000000000000ll); }
 
-// CostmapModel::footprintCost for one pose, given cos/sin of its heading; < 0 means illegal
-__device__ double footprint_cost(const DwaScoreArgs& a, double x, double y, double cos_th, double sin_th) {
+// One footprint edge of one pose: CostmapModel::lineCost over the LineIterator cells between the map cells of two
+// consecutive oriented footprint vertices (costmap_model.cpp:75-131, line_iterator.h:38-139).  Returns the maximum
+// cell cost along the edge, or -1 when a vertex is off the map or a cell is LETHAL / (NO_INFORMATION && !allow_unknown).
+__device__ int footprint_edge_cost(const DwaScoreArgs& a, double x, double y, double cos_th, double sin_th, int e) {
   const DwaGeom& g = a.g;
-  int cx, cy;
-  if (!dwa_world_to_map(g, x, y, cx, cy)) return -1.0;
-  if (a.nfp < 3) {
-    const uint8_t c = g.cost[(size_t)cy * g.pitch + cx];
-    if (c == kLethal || c == kInscribed || (c == kNoInfo && !a.allow_unknown)) return -1.0;
-    return c;
-  }
-  int fx0, fy0, px, py;
+  const int e1 = e + 1 < a.nfp ? e + 1 : 0;
+  int px, py, qx, qy;
   {
-    const double wx = x + (a.fpx[0] * cos_th - a.fpy[0] * sin_th), wy = y + (a.fpx[0] * sin_th + a.fpy[0] * cos_th);
-    if (!dwa_world_to_map(g, wx, wy, fx0, fy0)) return -1.0;
+    const double wx = x + (a.fpx[e] * cos_th - a.fpy[e] * sin_th), wy = y + (a.fpx[e] * sin_th + a.fpy[e] * cos_th);
+    if (!dwa_world_to_map(g, wx, wy, px, py)) return -1;
   }
-  px = fx0;
-  py = fy0;
+  {
+    const double wx = x + (a.fpx[e1] * cos_th - a.fpy[e1] * sin_th), wy = y + (a.fpx[e1] * sin_th + a.fpy[e1] * cos_th);
+    if (!dwa_world_to_map(g, wx, wy, qx, qy)) return -1;
+  }
+  const int dx = abs(qx - px), dy = abs(qy - py);
+  const int xinc = qx >= px ? 1 : -1, yinc = (qy >= py ? 1 : -1) * (int)g.pitch;
+  const bool xmajor = dx >= dy;
+  const int den = xmajor ? dx : dy, numadd = xmajor ? dy : dx;
+  const int major = xmajor ? xinc : yinc, minor = xmajor ? yinc : xinc;
+  int num = den / 2;
+  int off = py * (int)g.pitch + px;
   int best = 0;
-  for (int e = 0; e < a.nfp; ++e) {
-    int qx, qy;
-    if (e + 1 < a.nfp) {
-      const double wx = x + (a.fpx[e + 1] * cos_th - a.fpy[e + 1] * sin_th);
-      const double wy = y + (a.fpx[e + 1] * sin_th + a.fpy[e + 1] * cos_th);
-      if (!dwa_world_to_map(g, wx, wy, qx, qy)) return -1.0;
-    } else {
-      qx = fx0;
-      qy = fy0;
+  bool bad = false;
+  const uint8_t unknown_bad = a.allow_unknown ? 0 : kNoInfo;  // 0 never equals a cost we reject
+  for (int k = 0; k <= den; ++k) {
+    const int c = g.cost[off];
+    bad |= (c == kLethal) | (c == unknown_bad && unknown_bad != 0);  // CostmapModel::pointCost :133-142
+    best = max(best, c);
+    num += numadd;
+    if (num >= den) {
+      num -= den;
+      off += minor;
     }
-    // LineIterator from (px,py) to (qx,qy), both end points included
-    const int dx = abs(qx - px), dy = abs(qy - py);
-    const int xinc = qx >= px ? 1 : -1, yinc = qy >= py ? 1 : -1;
-    int cxx = px, cyy = py;
-    int den, num, numadd, n;
-    const bool xmajor = dx >= dy;
-    if (xmajor) { den = dx; num = dx / 2; numadd = dy; n = dx; }
-    else { den = dy; num = dy / 2; numadd = dx; n = dy; }
-    for (int k = 0; k <= n; ++k) {
-      const uint8_t c = g.cost[(size_t)cyy * g.pitch + cxx];
-      if (c == kLethal || (c == kNoInfo && !a.allow_unknown)) return -1.0;  // CostmapModel::pointCost :133-142
-      best = max(best, (int)c);
-      num += numadd;
-      if (num >= den) {
-        num -= den;
-        if (xmajor) cyy += yinc; else cxx += xinc;
-      }
-      if (xmajor) cxx += xinc; else cyy += yinc;
-    }
-    px = qx;
-    py = qy;
+    off += major;
   }
-  return (double)best;
+  return bad ? -1 : best;
 }
 
 // scores one velocity sample with a whole warp; points_out (nullable) receives 3 doubles per trajectory point
+constexpr int kWarpScratchDoubles = 128 + 16;  // 4 x 32 pose doubles + 32 ints
 __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int lane, double* terms_out,
-                                   double* points_out, int points_capacity) {
+                                   double* points_out, int points_capacity, double* warp_scratch) {
   TrajResult res;
   res.cost = nan_quiet();
   res.generated = false;
@@ -350,16 +348,39 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
       points_out[3 * (base + lane) + 1] = py;
       points_out[3 * (base + lane) + 2] = thd;
     }
-    // ---- obstacle critic on my point
+    // ---- obstacle critic: (point, edge) work items spread over all 32 lanes, so a short tail round costs one edge
+    // per lane instead of a whole footprint per active lane
+    double* pose_s = warp_scratch;              // x, y, cos, sin of the round's points
+    // per point: max edge cost; bit 31 set (the unsigned maximum) once any edge of the point is illegal
+    unsigned* edge_max = reinterpret_cast<unsigned*>(warp_scratch + 128);
+    pose_s[lane] = px;
+    pose_s[32 + lane] = py;
+    pose_s[64 + lane] = c;
+    pose_s[96 + lane] = s;
+    edge_max[lane] = 0;
+    __syncwarp();
     double occ = 0.0;
     bool fail = false;
+    if (a.nfp >= 3) {
+      const int items = cnt * a.nfp;
+      for (int it = lane; it < items; it += 32) {
+        const int p = it / a.nfp, e = it - p * a.nfp;
+        const int ec = footprint_edge_cost(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], e);
+        atomicMax(&edge_max[p], ec < 0 ? 0x80000000u : (unsigned)ec);
+      }
+      __syncwarp();
+    }
     if (active) {
-      const double f = a.nfp == 0 ? -9.0 : footprint_cost(a, px, py, c, s);
-      if (f < 0) fail = true;
+      int cx, cy;
+      if (a.nfp == 0 || !dwa_world_to_map(a.g, px, py, cx, cy)) fail = true;  // off-map centre: costmap_model.cpp:57-58
       else {
-        int cx, cy;
-        dwa_world_to_map(a.g, px, py, cx, cy);  // cannot fail here: footprintCost checked the centre first
-        occ = fmax(fmax(0.0, f), (double)a.g.cost[(size_t)cy * a.g.pitch + cx]);
+        const int centre = a.g.cost[cy * (int)a.g.pitch + cx];
+        int f = (int)edge_max[lane];
+        if (a.nfp < 3) {  // point robot: the centre cell alone (:61-67)
+          f = (centre == kLethal || centre == kInscribed || (centre == kNoInfo && !a.allow_unknown)) ? -1 : centre;
+        }
+        if (f < 0) fail = true;
+        else occ = fmax(fmax(0.0, (double)f), (double)centre);
       }
     }
     obst_fail |= __any_sync(0xffffffffu, fail);
@@ -368,6 +389,7 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
     for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);  // small integers: exact
     obst_sum += ssum;
     obst_last = __shfl_sync(0xffffffffu, occ, cnt - 1);
+    __syncwarp();
     // ---- the four map-grid critics on my point
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -383,7 +405,7 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
         int cx, cy;
         if (!dwa_world_to_map(a.g, qx, qy, cx, cy)) code = -4.0;
         else {
-          const uint32_t dd = a.dist[k][(size_t)cy * a.g.sx + cx];
+          const uint32_t dd = a.dist[k][cy * (int)a.g.sx + cx];
           const uint32_t n_cells = a.g.sx * a.g.sy;
           d = (double)dd;
           if (stop_on_failure) {
@@ -443,6 +465,7 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreAr
   __shared__ long long s_index[kDwaWarpsPerBlock];
   __shared__ int s_generated[kDwaWarpsPerBlock];
   __shared__ bool s_last;
+  __shared__ double s_scratch[kDwaWarpsPerBlock][kWarpScratchDoubles];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long sample = a.begin + (long long)blockIdx.x * kDwaWarpsPerBlock + warp;
   double cost = INFINITY;
@@ -450,7 +473,7 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreAr
   int generated = 0;
   if (sample < a.end) {
     double* terms = a.all_terms ? a.all_terms + 6 * (sample - a.begin) : nullptr;
-    const TrajResult r = score_sample(a, sample, lane, terms, nullptr, 0);
+    const TrajResult r = score_sample(a, sample, lane, terms, nullptr, 0, s_scratch[warp]);
     generated = r.generated;
     if (terms && !r.generated && lane == 0)
       for (int k = 0; k < 6; ++k) terms[k] = nan_quiet();
@@ -535,13 +558,14 @@ struct DwaDeviceResult {
 // When forced_index >= 0 that sample is used instead of *best_index (sharded sweeps).
 __global__ void k_dwa_finish(DwaScoreArgs a, long long forced_index, DwaDeviceResult* out, double* points,
                              int points_capacity) {
+  __shared__ double s_scratch[kWarpScratchDoubles];
   const int lane = threadIdx.x & 31;
   const long long idx = forced_index >= 0 ? forced_index : *a.best_index;
   TrajResult r;
   r.cost = -7.0;
   r.generated = false;
   r.num_steps = 0;
-  if (idx >= 0) r = score_sample(a, idx, lane, nullptr, points, points_capacity);
+  if (idx >= 0) r = score_sample(a, idx, lane, nullptr, points, points_capacity, s_scratch);
   if (lane == 0) {
     out->best_index = idx;
     out->n_scored = (int)a.counters[1];
