@@ -152,6 +152,8 @@ struct navgpu_costmap {
   InflationBoundsState* d_infl = nullptr;
   DevWindow* d_win = nullptr;
   DevWindow* h_win = nullptr;  // pinned
+  uint16_t* d_seeds = nullptr;  // seed bitmask of the fast sweep (k_merge_seed -> k_inflate)
+  size_t seeds_capacity = 0;
   int win[4] = {0, 0, 0, 0};
   bool poly_attr_set = false;
   bool profile = false;
@@ -214,14 +216,39 @@ int upload_tables(navgpu_costmap* h, Layer& L) {
   return NAVGPU_OK;
 }
 
-// picks the fast (R <= 32) or the generic sweep kernel
-int launch_sweep(const UpdateArgs& a, cudaStream_t stream, bool force_generic) {
+// One sweep over the master grid: the two-kernel fast path (k_merge_seed [+ k_inflate], R <= 31) or the generic
+// fused kernel (any R <= 254).  `seeds` is the handle's seed bitmask (sy x seed_pitch16(pitch) uint16, pads zero).
+int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic) {
   const int R = a.R;
-  if (R > 0 && R <= 31 && !force_generic) {
-    size_t smem = update_costs_fast_smem(R);
-    NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((a.sx + kFTX - 1) / kFTX, (a.sy + kFTY - 1) / kFTY);
-    k_update_costs_fast<<<grid, kFThreads, smem, stream>>>(a);
+  if (R <= 31 && !force_generic) {
+    MergeSeedArgs m;
+    m.master = a.master;
+    m.sx = a.sx; m.sy = a.sy; m.pitch = a.pitch;
+    m.def = a.def;
+    m.do_reset = a.do_reset;
+    m.win = a.win;
+    m.ml = a.ml;
+    m.R = R;
+    m.seeds = seeds;
+    if (R > 0 && !seeds) return fail(NAVGPU_ERR_INVALID, "seed bitmask missing");
+    dim3 block(kMSGroupsX, kMSRowsY);
+    dim3 grid((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16), (a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
+    if (a.ml.n > 0 || a.do_reset || R > 0) {
+      k_merge_seed<<<grid, block, 0, stream>>>(m);
+      NAVGPU_LAUNCHED(1);
+    }
+    if (R > 0) {
+      InflateArgs ia;
+      ia.master = a.master;
+      ia.sx = a.sx; ia.sy = a.sy; ia.pitch = a.pitch;
+      ia.win = a.win;
+      ia.R = R;
+      ia.cost_d2 = a.cost_d2;
+      ia.seeds = reinterpret_cast<const uint32_t*>(seeds);
+      dim3 igrid((a.sx + kITX - 1) / kITX, (a.sy + kITY - 1) / kITY);
+      k_inflate<<<igrid, kIThreads, 0, stream>>>(ia);
+      NAVGPU_LAUNCHED(1);
+    }
     return NAVGPU_OK;
   }
   size_t smem = update_costs_smem(R);
@@ -230,6 +257,18 @@ int launch_sweep(const UpdateArgs& a, cudaStream_t stream, bool force_generic) {
     NAVGPU_CUDA(cudaFuncSetAttribute(k_update_costs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((a.sx + kTX - 1) / kTX, (a.sy + kTY - 1) / kTY);
   k_update_costs<<<grid, kUpdateThreads, smem, stream>>>(a);
+  NAVGPU_LAUNCHED(1);
+  return NAVGPU_OK;
+}
+
+int ensure_seeds(uint16_t** seeds, size_t* cap, unsigned pitch, unsigned sy, cudaStream_t stream) {
+  const size_t need = size_t(seed_pitch16(pitch)) * sy * sizeof(uint16_t);
+  if (*seeds && need <= *cap) return NAVGPU_OK;
+  if (*seeds) cudaFree(*seeds);
+  *seeds = nullptr;
+  NAVGPU_CUDA(cudaMalloc(seeds, need));
+  NAVGPU_CUDA(cudaMemsetAsync(*seeds, 0, need, stream));  // the pad groups stay zero for good
+  *cap = need;
   return NAVGPU_OK;
 }
 
@@ -243,10 +282,10 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   a.ml = ml;
   a.R = R;
   a.cost_d2 = cost_d2;
+  if (R > 0 && R <= 31) NAVGPU_TRY(ensure_seeds(&h->d_seeds, &h->seeds_capacity, h->pitch, h->sy, h->stream));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[0], h->stream);
-  NAVGPU_TRY(launch_sweep(a, h->stream, h->force_generic));
+  NAVGPU_TRY(launch_sweep(a, h->d_seeds, h->stream, h->force_generic));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[1], h->stream);
-  NAVGPU_LAUNCHED(1);
   return NAVGPU_OK;
 }
 
@@ -457,7 +496,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
     cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
-  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win);
+  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds);
   cudaFreeHost(h->h_win);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -827,7 +866,9 @@ struct SeamContext {
   uint8_t* d_layer = nullptr;
   uint8_t* d_table = nullptr;
   DevWindow* d_win = nullptr;
-  size_t cap_master = 0, cap_layer = 0, cap_table = 0;
+  uint16_t* d_seeds = nullptr;
+  size_t cap_master = 0, cap_layer = 0, cap_table = 0, cap_seeds = 0;
+  unsigned seeds_pitch = 0;
 };
 
 int seam_context(int device, SeamContext** out) {
@@ -889,8 +930,15 @@ int seam_run(uint8_t* master, const uint8_t* layer, uint32_t size_x, uint32_t si
   a.ml = ml;
   a.R = R;
   a.cost_d2 = c->d_table;
-  NAVGPU_TRY(launch_sweep(a, c->stream, false));
-  NAVGPU_LAUNCHED(2);
+  if (R > 0 && R <= 31) {
+    NAVGPU_TRY(ensure_seeds(&c->d_seeds, &c->cap_seeds, pitch, rows, c->stream));
+    if (c->seeds_pitch != pitch) {  // another row layout: the pad groups of the new layout must read as zero
+      NAVGPU_CUDA(cudaMemsetAsync(c->d_seeds, 0, c->cap_seeds, c->stream));
+      c->seeds_pitch = pitch;
+    }
+  }
+  NAVGPU_TRY(launch_sweep(a, c->d_seeds, c->stream, false));
+  NAVGPU_LAUNCHED(1);
   NAVGPU_CUDA(cudaGetLastError());
   NAVGPU_CUDA(cudaMemcpy2DAsync(master + size_t(y_lo) * size_x, size_x, c->d_master, pitch, size_x, rows,
                                 cudaMemcpyDeviceToHost, c->stream));

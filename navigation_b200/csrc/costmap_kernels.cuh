@@ -533,22 +533,40 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fast variant of the same sweep for R <= 31 cells (every configuration the reference's defaults produce).
+// Fast path of the same sweep for R <= 31 cells (every configuration the reference's defaults produce), split in two
+// kernels so that the layer merge is a pure streaming pass and only ONE BIT per cell crosses tile borders:
 //
-//   tile 256 x 64 cells per CTA (halo 32 columns, R rows), 512 threads, about 75 KB of shared memory at R = 20
-//   phase 1  16 cells per uint4 load; merge policies evaluated on 4 packed bytes per 32-bit op; the LETHAL
-//            predicate becomes one seed bit per cell (10 x 32-bit words per region row)
-//   phase 2  per (row, 64-column segment) that has any seed bit: nearest seed along the row by clz/ffs on funnel-
-//            shifted windows, stored squared as packed u16x2; rows without seeds are never touched again
-//   phase 3  each thread owns 2 columns x 8 rows of accumulators and walks only the non-empty rows of its
-//            (8 + 2R)-row window: acc_k = min(acc_k, hx^2 + dy_k^2) is ONE VIADDMNMX.U16x2 per row and cell pair
-//   epilogue table lookup by d^2, InflationLayer's max/NO_INFORMATION rule, uint4 write-back of the whole tile
-constexpr int kFTX = 256, kFTY = 64, kFThreads = 512, kFHalo = 32;
-constexpr int kFRowWarps = kFThreads / 32 / 4;  // warps per 64-column segment
-constexpr int kFGroups = (kFTX + 2 * kFHalo) / 16;  // 20 groups of 16 cells per region row
-constexpr int kFWords = (kFTX + 2 * kFHalo) / 32;   // 10 seed words per region row
-constexpr int kFMaxRows = kFTY + 2 * 32;
+//   k_merge_seed   16 cells per thread: uint4 loads of every layer, merge policies on 4 packed bytes per 32-bit op,
+//                  uint4 store of the pre-inflation master value, and the "== LETHAL and inside the seed region"
+//                  predicate as a uint16 into a device-wide seed bitmask (1 bit per cell, 2 MB at 4000^2).
+//   k_inflate      tile 64 x 128 cells per CTA: seed words of the tile + halo (R rows, 32 columns) come from the
+//                  bitmask; phase 2 turns every row that has seeds into squared horizontal distances (clz/ffs on
+//                  funnel-shifted windows, packed u16x2); phase 3 gives each thread 2 columns x 8 rows of
+//                  accumulators and walks only the non-empty rows of its (8 + 2R)-row window with ONE
+//                  VIADDMNMX.U16x2 per row and cell pair; the epilogue looks the cost up by d^2 and applies
+//                  InflationLayer's max / NO_INFORMATION rule directly on the master grid, touching only rows that
+//                  inflation reaches.  A tile whose seed words are all zero exits after the load.
+constexpr int kMSGroupsX = 32, kMSRowsY = 8, kMSRowIters = 2;  // k_merge_seed: CTA = 512 columns x 16 rows
+constexpr int kITX = 64, kITY = 128, kIThreads = 256, kIMaxRows = kITY + 2 * 31;
 constexpr uint32_t kH2Inf = 0x3000;  // "no seed within R on this row" (as a squared distance, per 16-bit half)
+
+// layout of the seed bitmask: one row per grid row, 2 zero pad groups (32 cells) on either side of the row
+__host__ __device__ inline unsigned seed_pitch16(unsigned pitch) { return pitch / 16 + 4; }
+
+struct MergeSeedArgs {
+  uint8_t* master;
+  unsigned sx, sy, pitch;
+  uint8_t def;
+  int do_reset;
+  const DevWindow* win;
+  MergeLayers ml;
+  int R;            // 0: merge only (seeds may be null)
+  uint16_t* seeds;  // sy x seed_pitch16(pitch)
+};
+
+__device__ __forceinline__ uint32_t inc4(uint32_t x) {  // per-byte x + 1 (mod 256), no carry between bytes
+  return ((x & 0x7f7f7f7fu) + 0x01010101u) ^ (x & 0x80808080u);
+}
 
 __device__ __forceinline__ uint32_t merge4(uint32_t m, uint32_t v, int policy) {
   switch (policy) {
@@ -558,8 +576,9 @@ __device__ __forceinline__ uint32_t merge4(uint32_t m, uint32_t v, int policy) {
       return (m & vn) | (v & ~vn);
     }
     case NAVGPU_MAX: {
-      const uint32_t vn = __vcmpeq4(v, 0xffffffffu), mn = __vcmpeq4(m, 0xffffffffu), lt = __vcmpltu4(m, v);
-      const uint32_t take = ~vn & (mn | lt);
+      // "skip layer == 255; write if master == 255 or master < layer" is an unsigned maximum once NO_INFORMATION is
+      // rotated to the bottom of the order: x -> x + 1 (mod 256) per byte sends 255 to 0 and keeps every other order
+      const uint32_t take = __vcmpltu4(inc4(m), inc4(v));
       return (v & take) | (m & ~take);
     }
     case NAVGPU_ADDITION: {
@@ -574,185 +593,244 @@ __device__ __forceinline__ uint32_t merge4(uint32_t m, uint32_t v, int policy) {
   }
 }
 
+__device__ __forceinline__ uint4 merge16(uint4 m, uint4 v, int policy) {
+  // the switch sits outside the four word-merges so it is resolved once per 16 cells
+  switch (policy) {
+    case NAVGPU_TRUE_OVERWRITE: return v;
+    case NAVGPU_OVERWRITE:
+      return make_uint4(merge4(m.x, v.x, NAVGPU_OVERWRITE), merge4(m.y, v.y, NAVGPU_OVERWRITE),
+                        merge4(m.z, v.z, NAVGPU_OVERWRITE), merge4(m.w, v.w, NAVGPU_OVERWRITE));
+    case NAVGPU_MAX:
+      if ((v.x | v.y | v.z | v.w) == 0) {  // an all-FREE_SPACE group of the layer only turns NO_INFORMATION into 0
+        return make_uint4(m.x & ~__vcmpeq4(m.x, 0xffffffffu), m.y & ~__vcmpeq4(m.y, 0xffffffffu),
+                          m.z & ~__vcmpeq4(m.z, 0xffffffffu), m.w & ~__vcmpeq4(m.w, 0xffffffffu));
+      }
+      if ((v.x & v.y & v.z & v.w) == 0xffffffffu) return m;  // an all-NO_INFORMATION group changes nothing
+      return make_uint4(merge4(m.x, v.x, NAVGPU_MAX), merge4(m.y, v.y, NAVGPU_MAX), merge4(m.z, v.z, NAVGPU_MAX),
+                        merge4(m.w, v.w, NAVGPU_MAX));
+    case NAVGPU_ADDITION:
+      return make_uint4(merge4(m.x, v.x, NAVGPU_ADDITION), merge4(m.y, v.y, NAVGPU_ADDITION),
+                        merge4(m.z, v.z, NAVGPU_ADDITION), merge4(m.w, v.w, NAVGPU_ADDITION));
+    default: return m;
+  }
+}
+
 __device__ __forceinline__ uint32_t lethal_bits4(uint32_t v) {  // one bit per byte that equals LETHAL_OBSTACLE
   const uint32_t e = __vcmpeq4(v, 0xfefefefeu) & 0x01010101u;
   return (e * 0x01020408u) >> 24;
 }
 
-__global__ void __launch_bounds__(kFThreads) k_update_costs_fast(UpdateArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(kMSGroupsX * kMSRowsY) k_merge_seed(MergeSeedArgs a) {
   const DevWindow w = *a.win;
   if (!w.valid) return;
   const int R = a.R;
-  const int tx0 = blockIdx.x * kFTX, ty0 = blockIdx.y * kFTY;
-  if (tx0 >= w.xn + 2 * R || tx0 + kFTX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kFTY <= w.y0 - 2 * R) return;
-
-  const int rows = kFTY + 2 * R;
-  uint8_t* tile = smem;                                               // kFTY x kFTX
-  uint32_t* bits = reinterpret_cast<uint32_t*>(tile + kFTX * kFTY);  // rows x kFWords
-  uint32_t* h2 = bits + kFMaxRows * kFWords;                          // rows x (kFTX / 2) packed u16x2
-  uint32_t* rowmask = h2 + rows * (kFTX / 2);                         // 4 segments x 4 words
-  uint32_t* sq = rowmask + 16;                                        // 128 packed squares, index dy + 64
-  uint8_t* table = reinterpret_cast<uint8_t*>(sq + 128);              // R*R + 1
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int i = tid; i <= R * R; i += kFThreads) table[i] = a.cost_d2[i];
-  if (tid < 128) {
-    const int d = tid - 64;
-    sq[tid] = (uint32_t)(d * d) * 0x10001u;
-  }
-  if (tid < 16) rowmask[tid] = 0;
-
+  // everything k_inflate can read: its tiles intersect window +- 2R, extend up to a tile further, and look R rows /
+  // 32 columns beyond their own extent
+  const int my = R > 0 ? 3 * R + kITY : 0, mx = R > 0 ? 2 * R + kITX + 32 : 0;
+  const int bx0 = blockIdx.x * (kMSGroupsX * 16), by0 = blockIdx.y * (kMSRowsY * kMSRowIters);
+  if (bx0 >= w.xn + mx || bx0 + kMSGroupsX * 16 <= w.x0 - mx || by0 >= w.yn + my ||
+      by0 + kMSRowsY * kMSRowIters <= w.y0 - my)
+    return;
   const int sx0 = max(0, w.x0 - R), sxn = min((int)a.sx, w.xn + R);  // seed region (inflation_layer.cpp:203-211)
   const int sy0 = max(0, w.y0 - R), syn = min((int)a.sy, w.yn + R);
-  const int rx0 = tx0 - kFHalo, ry0 = ty0 - R;
+  const int x = bx0 + threadIdx.x * 16;
+  if (x >= (int)a.pitch) return;
+  const unsigned sp16 = seed_pitch16(a.pitch);
+  const bool col_any = x + 16 > w.x0 && x < w.xn, col_all = x >= w.x0 && x + 16 <= w.xn;
+  const bool col_seed = R > 0 && x + 16 > sx0 && x < sxn;
 
-  // ---- phase 1
-  for (int item = tid; item < rows * kFGroups; item += kFThreads) {
-    const int row = item / kFGroups, grp = item - row * kFGroups;
-    const int y = ry0 + row, x = rx0 + grp * 16;
-    uint32_t seed16 = 0;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < (int)a.sy && x >= 0 && x < (int)a.sx) {
-      const size_t off = (size_t)y * a.pitch + x;
-      const bool row_in = y >= w.y0 && y < w.yn;
-      const bool any_in = row_in && x + 16 > w.x0 && x < w.xn;
-      const bool all_in = row_in && x >= w.x0 && x + 16 <= w.xn;
-      if (!(all_in && a.do_reset)) v = *reinterpret_cast<const uint4*>(a.master + off);
-      if (all_in) {
-        if (a.do_reset) {
-          const uint32_t d4 = a.def * 0x01010101u;
-          v = make_uint4(d4, d4, d4, d4);
-        }
-        for (int l = 0; l < a.ml.n; ++l) {
-          const uint4 lv = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
-          const int pol = a.ml.policy[l];
-          v.x = merge4(v.x, lv.x, pol);
-          v.y = merge4(v.y, lv.y, pol);
-          v.z = merge4(v.z, lv.z, pol);
-          v.w = merge4(v.w, lv.w, pol);
-        }
-      } else if (any_in) {  // group straddles the window edge: per-cell path
-        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-        for (int l = -1; l < a.ml.n; ++l) {
-          uint4 lv4 = make_uint4(0, 0, 0, 0);
-          if (l >= 0) lv4 = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
-          const uint32_t lw[4] = {lv4.x, lv4.y, lv4.z, lv4.w};
+  // loads of all row iterations first (memory-level parallelism), then the merges
+  uint4 mv[kMSRowIters];
+  uint4 lv[kMSRowIters][2];
+  const int nfast = min(a.ml.n, 2);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int cx = x + i;
-            if (cx < w.x0 || cx >= w.xn) continue;
-            const int sh = 8 * (i & 3);
-            uint8_t m = (uint8_t)(vv[i >> 2] >> sh);
-            if (l < 0) { if (a.do_reset) m = a.def; }
-            else m = apply_policy(m, (uint8_t)(lw[i >> 2] >> sh), a.ml.policy[l]);
-            vv[i >> 2] = (vv[i >> 2] & ~(0xffu << sh)) | ((uint32_t)m << sh);
-          }
-        }
-        v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+  for (int it = 0; it < kMSRowIters; ++it) {
+    const int y = by0 + threadIdx.y + it * kMSRowsY;
+    mv[it] = make_uint4(0, 0, 0, 0);
+    lv[it][0] = lv[it][1] = make_uint4(0, 0, 0, 0);
+    if (y >= (int)a.sy) continue;
+    const size_t off = (size_t)y * a.pitch + x;
+    const bool row_in = y >= w.y0 && y < w.yn;
+    const bool any_in = row_in && col_any, all_in = row_in && col_all;
+    const bool need_master = any_in ? !(all_in && a.do_reset) : (col_seed && y >= sy0 && y < syn);
+    if (need_master) mv[it] = *reinterpret_cast<const uint4*>(a.master + off);
+    if (any_in) {
+      if (nfast > 0) lv[it][0] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off);
+      if (nfast > 1) lv[it][1] = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kMSRowIters; ++it) {
+    const int y = by0 + threadIdx.y + it * kMSRowsY;
+    if (y >= (int)a.sy) continue;
+    const size_t off = (size_t)y * a.pitch + x;
+    const bool row_in = y >= w.y0 && y < w.yn;
+    const bool any_in = row_in && col_any, all_in = row_in && col_all;
+    uint4 v = mv[it];
+    if (all_in) {
+      if (a.do_reset) {
+        const uint32_t d4 = a.def * 0x01010101u;
+        v = make_uint4(d4, d4, d4, d4);
       }
-      if (y >= sy0 && y < syn) {
+      if (a.ml.n > 0) v = merge16(v, lv[it][0], a.ml.policy[0]);
+      if (a.ml.n > 1) v = merge16(v, lv[it][1], a.ml.policy[1]);
+      for (int l = 2; l < a.ml.n; ++l)
+        v = merge16(v, *reinterpret_cast<const uint4*>(a.ml.grid[l] + off), a.ml.policy[l]);
+    } else if (any_in) {  // group straddles the window edge: per-cell path
+      uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+      for (int l = -1; l < a.ml.n; ++l) {
+        uint4 lv4 = make_uint4(0, 0, 0, 0);
+        if (l == 0) lv4 = lv[it][0];
+        else if (l == 1) lv4 = lv[it][1];
+        else if (l >= 2) lv4 = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
+        const uint32_t lw[4] = {lv4.x, lv4.y, lv4.z, lv4.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int cx = x + i;
+          if (cx < w.x0 || cx >= w.xn) continue;
+          const int sh = 8 * (i & 3);
+          uint8_t m = (uint8_t)(vv[i >> 2] >> sh);
+          if (l < 0) { if (a.do_reset) m = a.def; }
+          else m = apply_policy(m, (uint8_t)(lw[i >> 2] >> sh), a.ml.policy[l]);
+          vv[i >> 2] = (vv[i >> 2] & ~(0xffu << sh)) | ((uint32_t)m << sh);
+        }
+      }
+      v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    if (any_in) *reinterpret_cast<uint4*>(a.master + off) = v;
+    if (R > 0) {
+      uint32_t seed16 = 0;
+      if (col_seed && y >= sy0 && y < syn && (v.x | v.y | v.z | v.w) != 0) {
         const uint32_t lb = lethal_bits4(v.x) | (lethal_bits4(v.y) << 4) | (lethal_bits4(v.z) << 8) | (lethal_bits4(v.w) << 12);
         const int lo = min(16, max(0, sx0 - x)), hi = min(16, max(0, sxn - x));
         seed16 = lb & ((1u << hi) - 1u) & ~((1u << lo) - 1u);
       }
-      // cells past the last column are padding: keep them zero in the tile
-      if (x + 16 > (int)a.sx) {
-        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-        for (int i = 0; i < 16; ++i)
-          if (x + i >= (int)a.sx) vv[i >> 2] &= ~(0xffu << (8 * (i & 3)));
-        v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-      }
+      a.seeds[(size_t)y * sp16 + 2 + (x >> 4)] = (uint16_t)seed16;
     }
-    reinterpret_cast<uint16_t*>(bits)[row * (kFWords * 2) + grp] = (uint16_t)seed16;
-    if (row >= R && row < R + kFTY && grp >= 2 && grp < 2 + kFTX / 16)
-      *reinterpret_cast<uint4*>(tile + (row - R) * kFTX + (grp - 2) * 16) = v;
-  }
-  __syncthreads();
-
-  // ---- phase 2: squared horizontal distances for the rows that have seeds
-  {
-    const int seg = warp & 3, sub = warp >> 2;
-    uint32_t local[4] = {0, 0, 0, 0};
-    for (int r = sub; r < rows; r += kFRowWarps) {
-      const uint32_t* wr = bits + r * kFWords + 2 * seg;
-      const uint32_t W0 = wr[0], W1 = wr[1], W2 = wr[2], W3 = wr[3];
-      if ((W0 | W1 | W2 | W3) == 0) continue;
-      local[r >> 5] |= 1u << (r & 31);
-      const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
-      uint32_t packed = 0;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int sh = (2 * lane + c) & 31;
-        const uint32_t right = __funnelshift_r(B, C, sh);        // bit k   <-> dx = +k
-        const uint32_t left = __funnelshift_rc(A, B, sh + 1);    // bit 31-k <-> dx = -k
-        int d = 64;
-        if (right) d = __ffs(right) - 1;
-        if (left) d = min(d, __clz(left));
-        const uint32_t hh = d <= R ? (uint32_t)(d * d) : kH2Inf;
-        packed |= hh << (16 * c);
-      }
-      h2[r * (kFTX / 2) + seg * 32 + lane] = packed;
-    }
-    if (lane == 0)
-      for (int k = 0; k < 4; ++k)
-        if (local[k]) atomicOr(&rowmask[seg * 4 + k], local[k]);
-  }
-  __syncthreads();
-
-  // ---- phase 3 + epilogue
-  {
-    const int seg = warp & 3, part = warp >> 2;
-    const uint32_t R2 = (uint32_t)(R * R);
-    constexpr int kRowsPerWarp = kFTY / kFRowWarps;
-    for (int g = 0; g < kRowsPerWarp / 8; ++g) {
-      const int yr0 = part * kRowsPerWarp + g * 8;  // first tile row of this group; region rows yr0 .. yr0 + 7 + 2R
-      uint32_t acc[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = 0xffffffffu;
-      const int lo = yr0, hi = yr0 + 8 + 2 * R;  // region-row range [lo, hi)
-      for (int wd = lo >> 5; wd <= (hi - 1) >> 5; ++wd) {
-        uint32_t m = rowmask[seg * 4 + wd];
-        const int base = wd * 32;
-        if (lo > base) m &= 0xffffffffu << (lo - base);
-        if (hi < base + 32) m &= (1u << (hi - base)) - 1u;
-        while (m) {
-          const int r = base + __ffs(m) - 1;
-          m &= m - 1;
-          const uint32_t hh = h2[r * (kFTX / 2) + seg * 32 + lane];
-          const uint32_t* sqp = sq + 64 + (r - R - yr0);  // dy of row k is (r - R) - (yr0 + k)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = __viaddmin_u16x2(hh, sqp[-k], acc[k]);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t da = acc[k] & 0xffffu, db = acc[k] >> 16;
-        if (da <= R2 || db <= R2) {
-          uint16_t* cp = reinterpret_cast<uint16_t*>(tile + (yr0 + k) * kFTX + seg * 64 + 2 * lane);
-          const uint16_t cur = *cp;
-          uint8_t va = (uint8_t)(cur & 0xff), vb = (uint8_t)(cur >> 8);
-          if (da <= R2) va = inflate_combine(va, table[da]);
-          if (db <= R2) vb = inflate_combine(vb, table[db]);
-          *cp = (uint16_t)(va | (vb << 8));
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  for (int item = tid; item < kFTX * kFTY / 16; item += kFThreads) {
-    const int r = item / (kFTX / 16), c = (item - r * (kFTX / 16)) * 16;
-    const int y = ty0 + r, x = tx0 + c;
-    if (y < (int)a.sy && x < (int)a.pitch)
-      *reinterpret_cast<uint4*>(a.master + (size_t)y * a.pitch + x) = *reinterpret_cast<const uint4*>(tile + r * kFTX + c);
   }
 }
 
-inline size_t update_costs_fast_smem(int R) {
-  const int rows = kFTY + 2 * R;
-  return (size_t)kFTX * kFTY + (size_t)kFMaxRows * kFWords * 4 + (size_t)rows * (kFTX / 2) * 4 + 16 * 4 + 128 * 4 +
-         (size_t)R * R + 1 + 16;
+struct InflateArgs {
+  uint8_t* master;
+  unsigned sx, sy, pitch;
+  const DevWindow* win;
+  int R;
+  const uint8_t* cost_d2;  // R*R+1 entries: cost by squared cell distance
+  const uint32_t* seeds;   // the bitmask written by k_merge_seed, viewed as 32-bit words
+};
+
+__global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
+  __shared__ uint32_t sbits[kIMaxRows * 4];       // seed words W0..W3 of each region row: columns tx0-32 .. tx0+95
+  __shared__ uint32_t h2[kIMaxRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
+  __shared__ uint32_t rowmask[(kIMaxRows + 31) / 32];
+  __shared__ uint32_t sq[128];     // packed squares, index dy + 64
+  __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
+  const DevWindow w = *a.win;
+  if (!w.valid) return;
+  const int R = a.R;
+  const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
+  if (tx0 >= w.xn + 2 * R || tx0 + kITX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kITY <= w.y0 - 2 * R) return;
+  const int rows = kITY + 2 * R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned sp32 = seed_pitch16(a.pitch) / 2;
+
+  // ---- seed words of the region; leave when there is nothing to inflate from
+  int any = 0;
+  for (int i = tid; i < rows * 4; i += kIThreads) {
+    const int gy = ty0 - R + (i >> 2);
+    uint32_t v = 0;
+    if (gy >= 0 && gy < (int)a.sy) v = a.seeds[(size_t)gy * sp32 + (tx0 >> 5) + (i & 3)];
+    sbits[i] = v;
+    any |= v != 0;
+  }
+  for (int i = tid; i <= R * R; i += kIThreads) table[i] = a.cost_d2[i];
+  if (tid == 0) table[R * R + 1] = 0;
+  if (tid < 128) {
+    const int d = tid - 64;
+    sq[tid] = (uint32_t)(d * d) * 0x10001u;
+  }
+  if (tid < (kIMaxRows + 31) / 32) rowmask[tid] = 0;
+  if (!__syncthreads_or(any)) return;
+
+  // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row)
+  for (int r = warp; r < rows; r += kIThreads / 32) {
+    // only seeds within R columns of the tile can matter: the top R bits of W0, the low R bits of W3
+    const uint32_t W0 = sbits[4 * r] & ~(0xffffffffu >> R), W1 = sbits[4 * r + 1], W2 = sbits[4 * r + 2],
+                   W3 = sbits[4 * r + 3] & ((1u << R) - 1u);
+    if ((W0 | W1 | W2 | W3) == 0) continue;
+    if (lane == 0) atomicOr(&rowmask[r >> 5], 1u << (r & 31));
+    const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int sh = (2 * lane + c) & 31;
+      const uint32_t right = __funnelshift_r(B, C, sh);      // bit k    <-> dx = +k
+      const uint32_t left = __funnelshift_rc(A, B, sh + 1);  // bit 31-k <-> dx = -k
+      int d = 64;
+      if (right) d = __ffs(right) - 1;
+      if (left) d = min(d, __clz(left));
+      const uint32_t hh = d <= R ? (uint32_t)(d * d) : kH2Inf;
+      packed |= hh << (16 * c);
+    }
+    h2[r * (kITX / 2) + lane] = packed;
+  }
+  __syncthreads();
+
+  // ---- phase 3 + epilogue: each warp owns 64 columns x 8 rows at a time
+  const uint32_t R2x2 = (uint32_t)(R * R) * 0x10001u;
+  const int x = tx0 + 2 * lane;
+  const bool xok = x < (int)a.sx;
+  const uint32_t keep_hi = x + 1 >= (int)a.sx ? 0xff00u : 0u;
+  for (int g = warp; g < kITY / 8; g += kIThreads / 32) {
+    const int yr0 = g * 8;  // first tile row of this group; region rows yr0 .. yr0 + 7 + 2R
+    uint32_t acc[8], hit[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0x7fff7fffu;
+    const int lo = yr0, hi = yr0 + 8 + 2 * R;  // region-row range [lo, hi)
+    for (int wd = lo >> 5; wd <= (hi - 1) >> 5; ++wd) {
+      uint32_t m = rowmask[wd];
+      const int base = wd * 32;
+      if (lo > base) m &= 0xffffffffu << (lo - base);
+      if (hi < base + 32) m &= (1u << (hi - base)) - 1u;
+      while (m) {
+        const int r = base + __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t hh = h2[r * (kITX / 2) + lane];
+        const uint32_t* sqp = sq + 64 + (r - R - yr0);  // dy of row k is (r - R) - (yr0 + k)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = __viaddmin_u16x2(hh, sqp[-k], acc[k]);
+      }
+    }
+    // rows that inflation reaches somewhere in these 64 columns: read, combine (inflation_layer.cpp:249-254), write.
+    // Both cells of the pair are handled in one 32-bit word: byte k of `cost2` / `cur` belongs to cell k.
+    const int kmax = xok ? min(8, (int)a.sy - (ty0 + yr0)) : 0;
+    uint8_t* prow = a.master + (size_t)(ty0 + yr0) * a.pitch + x;
+    uint32_t cur[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // bit 15 of every half whose squared distance is within reach (no borrow crosses the halves)
+      hit[k] = k < kmax ? ((R2x2 | 0x80008000u) - (acc[k] & 0x7fff7fffu)) & 0x80008000u : 0u;
+      cur[k] = 0;
+      if (hit[k]) cur[k] = *reinterpret_cast<const uint16_t*>(prow + (size_t)k * a.pitch);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (!hit[k]) continue;
+      const uint32_t d2 = __vminu2(acc[k], R2x2 + 0x10001u);  // out of reach -> table[R*R+1] = 0
+      const uint32_t c16 = (uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 16);
+      const uint32_t old2 = cur[k];
+      const uint32_t o16 = __byte_perm(old2, 0, 0x4140);  // the two cells' bytes, one per 16-bit lane
+      uint32_t r16 = __vmaxu2(o16, c16);
+      // NO_INFORMATION is replaced only by costs >= INSCRIBED
+      const uint32_t keep = __vminu2(__vmaxu2(c16, 0x00fc00fcu), 0x00fd00fdu) - 0x00fc00fcu;  // 1 where cost >= 253
+      const uint32_t noinfo = ((o16 + 0x00010001u) >> 8) & 0x00010001u;                       // 1 where old == 255
+      const uint32_t repl = (noinfo & keep) * 0xffffu;                                        // 0xffff per such half
+      r16 = (c16 & repl) | (r16 & ~repl);
+      uint32_t out = __byte_perm(r16, 0, 0x4420);
+      out = (out & ~keep_hi) | (old2 & keep_hi);  // padding column: left as it is
+      *reinterpret_cast<uint16_t*>(prow + (size_t)k * a.pitch) = (uint16_t)out;
+    }
+  }
 }
 
 inline size_t update_costs_smem(int R) {

@@ -252,3 +252,53 @@ def test_c3_full_size_properties(cuda):
     import scipy.ndimage as ndi
     far = ~ndi.binary_dilation(leth, structure=np.ones((3, 3), bool), iterations=R)
     assert (g1[far] == 0).all()
+
+
+@pytest.mark.parametrize("policy", [0, 1, 2, 3])  # TrueOverwrite, Overwrite, Max, Addition
+@pytest.mark.parametrize("track_unknown", [False, True])
+@pytest.mark.parametrize("inflate", [False, True])
+def test_merge_policies_on_run_structured_layers(cuda, port, policy, track_unknown, inflate):
+    """CostmapLayer::updateWith* (costmap_layer.cpp:62-157) on layers made of 16-cell-aligned runs of FREE_SPACE,
+    NO_INFORMATION and arbitrary bytes, which exercise the streaming kernel's all-zero / all-255 group shortcuts, on
+    an odd-sized grid (partial groups at the right edge) and a sub-window (partial groups at the window edge).
+    Arbitrary bytes exclude LETHAL (isolated lethal cells make inflation tie-order dependent); thick lethal blocks are
+    added instead so the inflated variant stays in the tie-free class and plain equality holds."""
+    rng = np.random.default_rng(7 + policy)
+    sx, sy = 333, 97
+    grids = []
+    for _ in range(2):
+        g = rng.integers(0, 256, size=(sy, sx)).astype(np.uint8)
+        for y in range(sy):
+            for x0 in range(0, sx, 16):
+                r = rng.random()
+                if r < 0.3:
+                    g[y, x0:x0 + 16] = 0
+                elif r < 0.5:
+                    g[y, x0:x0 + 16] = 255
+                elif r < 0.6:
+                    g[y, x0:x0 + 16] = rng.choice(np.array([0, 255, 253, 252], np.uint8), size=len(g[y, x0:x0 + 16]))
+        g[g == 254] = 253
+        if policy == 3:  # sums that clip to 252 would otherwise never be lethal; keep addition operands small
+            g[(g > 100) & (g < 255)] = 100
+        for _ in range(3):
+            x, y = rng.integers(0, sx - 12), rng.integers(0, sy - 12)
+            g[y:y + 8, x:x + 9] = 254
+        grids.append(g)
+    out = []
+    for api in (cuda, port):
+        cm = api.costmap(sx, sy, 0.05, track_unknown=track_unknown)
+        a = cm.add_grid_layer(0)
+        b = cm.add_grid_layer(policy)
+        if inflate:
+            cm.add_inflation_layer(0.3, 10.0)
+        cm.set_footprint(sc.square_footprint(0.1))
+        cm.set_grid_layer(a, grids[0])
+        cm.set_grid_layer(b, grids[1])
+        w1 = cm.update_map(0, 0, 0)
+        m1 = cm.get()
+        cm.touch_grid_layer(b, 21, 13, 150, 40)  # a window that starts and ends inside 16-cell groups
+        w2 = cm.update_map(0, 0, 0)
+        out.append((w1, m1, w2, cm.get()))
+    assert out[0][0] == out[1][0] and out[0][2] == out[1][2]
+    assert np.array_equal(out[0][1], out[1][1]), f"{(out[0][1] != out[1][1]).sum()} cells differ after the full update"
+    assert np.array_equal(out[0][3], out[1][3]), f"{(out[0][3] != out[1][3]).sum()} cells differ after the window update"
