@@ -99,11 +99,14 @@ int navgpu_costmap_update_map(navgpu_costmap* h, double robot_x, double robot_y,
 int navgpu_costmap_update_map_async(navgpu_costmap* h, double robot_x, double robot_y, double robot_yaw);
 int navgpu_costmap_synchronize(navgpu_costmap* h);
 /* measurement hooks: when enabled, navgpu_costmap_update_map_async brackets the whole cycle and the fused
- * reset+merge+inflation sweep with CUDA events on the handle's stream; last_timing returns both (ms) */
+ * reset+merge+inflation sweep with CUDA events on the handle's stream; last_timing returns both (ms).  The events
+ * themselves cost a few microseconds per cycle, so throughput is measured with profiling off. */
 int navgpu_costmap_set_profiling(navgpu_costmap* h, int enabled);
-/* test hook: use the generic (any-R) sweep kernel even where the R <= 32 fast kernel applies */
+/* test hook: use the generic (any-R) fused sweep kernel even where the R <= 31 two-kernel fast path applies */
 int navgpu_costmap_force_generic_sweep(navgpu_costmap* h, int enabled);
 int navgpu_costmap_last_timing(navgpu_costmap* h, float* cycle_ms, float* sweep_ms);
+/* the sweep's two kernels separately: streaming merge + seed bitmask (k_merge_seed), inflation (k_inflate) */
+int navgpu_costmap_last_timing_split(navgpu_costmap* h, float* merge_ms, float* inflate_ms);
 /* the CUDA stream of this handle (cudaStream_t) so callers can record events on it */
 void* navgpu_costmap_stream(navgpu_costmap* h);
 /* master grid read-back to HOST: whole grid, or a window [x0,xn) x [y0,yn) packed row-major into out */

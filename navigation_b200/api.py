@@ -80,6 +80,7 @@ SIGNATURES = {
     "navgpu_costmap_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "navgpu_costmap_force_generic_sweep": (C.c_int, [C.c_void_p, C.c_int]),
     "navgpu_costmap_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "navgpu_costmap_last_timing_split": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "navgpu_costmap_get": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
     "navgpu_costmap_set": (C.c_int, [C.c_void_p, _u8p]),
@@ -221,6 +222,12 @@ class Costmap:
         c, s = C.c_float(), C.c_float()
         self.api.check(self.lib.navgpu_costmap_last_timing(self.h, C.byref(c), C.byref(s)))
         return float(c.value), float(s.value)
+
+    def last_timing_split(self):
+        """(k_merge_seed ms, k_inflate ms) of the last profiled update_map_async."""
+        m, i = C.c_float(), C.c_float()
+        self.api.check(self.lib.navgpu_costmap_last_timing_split(self.h, C.byref(m), C.byref(i)))
+        return float(m.value), float(i.value)
 
     def get(self):
         out = np.empty((self.size_y, self.size_x), dtype=np.uint8)

@@ -48,6 +48,7 @@ struct CostTables {
   std::vector<uint8_t> costs;  // (R+2)^2, [dx][dy]
   std::vector<double> dists;
   std::vector<uint8_t> by_d2;  // R*R+1: cost by squared distance
+  int reach2 = 0;              // largest squared distance with a non-zero cost
   bool ambiguous = false;      // two (dx,dy) with equal dx^2+dy^2 but different cached cost (never seen in practice)
 };
 static uint8_t compute_cost(double distance, double resolution, double inscribed, double weight) {
@@ -60,6 +61,12 @@ static uint8_t compute_cost(double distance, double resolution, double inscribed
     cost = (unsigned char)((kInscribed - 1) * factor);
   }
   return cost;
+}
+static int reach_of(const std::vector<uint8_t>& by_d2) {
+  int reach2 = 0;
+  for (size_t d2 = 0; d2 < by_d2.size(); ++d2)
+    if (by_d2[d2] != 0) reach2 = (int)d2;
+  return reach2;
 }
 void build_tables(CostTables& t, unsigned R, double resolution, double inscribed, double weight) {
   t.R = R;
@@ -86,6 +93,7 @@ void build_tables(CostTables& t, unsigned R, double resolution, double inscribed
         t.ambiguous = true;
       }
     }
+  t.reach2 = reach_of(t.by_d2);
 }
 
 static unsigned cell_distance(double world_dist, double resolution) {  // Costmap2D::cellDistance, costmap_2d.cpp:181-185
@@ -119,7 +127,8 @@ struct Layer {
   DevObs* d_clear = nullptr;
   DevObs* d_mark = nullptr;
   float* d_xyz = nullptr;
-  size_t xyz_capacity = 0, obs_capacity = 0;
+  long long* d_mark_cells = nullptr;  // scratch of k_obstacle_update: one prepared cell offset per marking point
+  size_t xyz_capacity = 0, obs_capacity = 0, mark_cells_capacity = 0;
   int n_clear = 0, n_mark = 0, total_rays = 0, total_marks = 0;
   std::vector<Pt> transformed_footprint;
   // inflation layer
@@ -152,6 +161,7 @@ struct navgpu_costmap {
   InflationBoundsState* d_infl = nullptr;
   DevWindow* d_win = nullptr;
   DevWindow* h_win = nullptr;  // pinned
+  unsigned* d_ticket = nullptr;  // k_obstacle_update's "last CTA" counter
   uint16_t* d_seeds = nullptr;  // seed bitmask of the fast sweep (k_merge_seed -> k_inflate)
   size_t seeds_capacity = 0;
   int win[4] = {0, 0, 0, 0};
@@ -159,6 +169,7 @@ struct navgpu_costmap {
   bool profile = false;
   bool force_generic = false;  // tests: exercise the generic sweep kernel also for R <= 32
   cudaEvent_t ev_sweep[2] = {nullptr, nullptr};
+  cudaEvent_t ev_mid = nullptr;  // between k_merge_seed and k_inflate
   cudaEvent_t ev_cycle[2] = {nullptr, nullptr};
 
   size_t bytes() const { return size_t(pitch) * sy; }
@@ -218,7 +229,7 @@ int upload_tables(navgpu_costmap* h, Layer& L) {
 
 // One sweep over the master grid: the two-kernel fast path (k_merge_seed [+ k_inflate], R <= 31) or the generic
 // fused kernel (any R <= 254).  `seeds` is the handle's seed bitmask (sy x seed_pitch16(pitch) uint16, pads zero).
-int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic) {
+int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic, cudaEvent_t ev_mid = nullptr) {
   const int R = a.R;
   if (R <= 31 && !force_generic) {
     MergeSeedArgs m;
@@ -237,12 +248,14 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
       k_merge_seed<<<grid, block, 0, stream>>>(m);
       NAVGPU_LAUNCHED(1);
     }
+    if (ev_mid) cudaEventRecord(ev_mid, stream);
     if (R > 0) {
       InflateArgs ia;
       ia.master = a.master;
       ia.sx = a.sx; ia.sy = a.sy; ia.pitch = a.pitch;
       ia.win = a.win;
       ia.R = R;
+      ia.reach2 = a.reach2;
       ia.cost_d2 = a.cost_d2;
       ia.seeds = reinterpret_cast<const uint32_t*>(seeds);
       dim3 igrid((a.sx + kITX - 1) / kITX, (a.sy + kITY - 1) / kITY);
@@ -272,7 +285,7 @@ int ensure_seeds(uint16_t** seeds, size_t* cap, unsigned pitch, unsigned sy, cud
   return NAVGPU_OK;
 }
 
-int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2) {
+int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2, int reach2 = 0) {
   UpdateArgs a;
   a.master = h->master[h->cur];
   a.sx = h->sx; a.sy = h->sy; a.pitch = h->pitch;
@@ -282,10 +295,40 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   a.ml = ml;
   a.R = R;
   a.cost_d2 = cost_d2;
+  a.reach2 = reach2;
   if (R > 0 && R <= 31) NAVGPU_TRY(ensure_seeds(&h->d_seeds, &h->seeds_capacity, h->pitch, h->sy, h->stream));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[0], h->stream);
-  NAVGPU_TRY(launch_sweep(a, h->d_seeds, h->stream, h->force_generic));
+  NAVGPU_TRY(launch_sweep(a, h->d_seeds, h->stream, h->force_generic, h->profile && R > 0 ? h->ev_mid : nullptr));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[1], h->stream);
+  return NAVGPU_OK;
+}
+
+// Host part of ObstacleLayer::updateCosts' footprint clearing (obstacle_layer.cpp:432-435 -> setConvexPolygonCost,
+// costmap_2d.cpp:315-342): vertices to cells; *mode = 0 nothing to clear, 1 fits k_obstacle_update, 2 stand-alone kernel
+int footprint_polygon(navgpu_costmap* h, const Layer& L, PolyArgs& pa, int* mode) {
+  *mode = 0;
+  pa.n = 0;
+  if (L.transformed_footprint.size() > 32) return fail(NAVGPU_ERR_UNSUPPORTED, "footprint with more than 32 vertices");
+  for (const Pt& p : L.transformed_footprint) {  // worldToMap, costmap_2d.cpp:208-220; any vertex off the map: no clearing
+    if (p.x < L.ox || p.y < L.oy) return NAVGPU_OK;
+    unsigned mx = (int)((p.x - L.ox) / h->res), my = (int)((p.y - L.oy) / h->res);
+    if (!(mx < h->sx && my < h->sy)) return NAVGPU_OK;
+    pa.vx[pa.n] = (int)mx;
+    pa.vy[pa.n] = (int)my;
+    ++pa.n;
+  }
+  if (pa.n < 3) return NAVGPU_OK;
+  long long outline = 0, minx = pa.vx[0], maxx = pa.vx[0], miny = pa.vy[0], maxy = pa.vy[0];
+  for (int k = 0; k < pa.n; ++k) {
+    int k1 = (k + 1) % pa.n;
+    outline += std::max(std::abs(pa.vx[k1] - pa.vx[k]), std::abs(pa.vy[k1] - pa.vy[k])) + 1;
+    minx = std::min<long long>(minx, pa.vx[k]); maxx = std::max<long long>(maxx, pa.vx[k]);
+    miny = std::min<long long>(miny, pa.vy[k]); maxy = std::max<long long>(maxy, pa.vy[k]);
+  }
+  const long long cells = outline + (maxx - minx + 1) * (maxy - miny + 1);
+  if (cells > kPolyMaxCells || h->sx > 65535 || h->sy > 65535)
+    return fail(NAVGPU_ERR_UNSUPPORTED, "footprint polygon covers too many cells for the device rasteriser");
+  *mode = cells <= kPolySmallCells ? 1 : 2;
   return NAVGPU_OK;
 }
 
@@ -297,10 +340,11 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     NAVGPU_TRY(roll_grid(h, h->master, h->cur, h->ox, h->oy, h->def, rx - h->size_m_x() / 2, ry - h->size_m_y() / 2));
   if (h->layers.empty()) return NAVGPU_OK;
 
-  // ---- updateBounds of every plugin, in order (:96-115)
+  // ---- updateBounds of every plugin, in order (:96-115): host-side scalars first
   BoundsArgs ba;
   ba.n_layers = (int)h->layers.size();
   ba.master = h->geom(h->ox, h->oy);
+  int last_obstacle = -1;
   for (size_t li = 0; li < h->layers.size(); ++li) {
     Layer& L = h->layers[li];
     BoundsLayer& B = ba.layer[li];
@@ -318,8 +362,9 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     } else if (L.kind == 1) {  // ObstacleLayer::updateBounds (obstacle_layer.cpp:340-413)
       if (h->rolling)
         NAVGPU_TRY(roll_grid(h, L.grid, L.cur, L.ox, L.oy, L.def, rx - h->size_m_x() / 2, ry - h->size_m_y() / 2));
+      L.transformed_footprint.clear();
       if (!L.enabled) continue;
-      Geom g = h->geom(L.ox, L.oy);
+      last_obstacle = (int)li;
       double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
       // raytraceFreespace touches the sensor origin once per clearing observation whose origin is on the map
       // (:504-521); origins and geometry are host-side scalars, the per-ray end points are touched on the device
@@ -331,21 +376,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
         bx0 = std::min(o.ox, bx0); by0 = std::min(o.oy, by0);
         bx1 = std::max(o.ox, bx1); by1 = std::max(o.oy, by1);
       }
-      if (L.total_rays > 0) {  // all clearing before any marking (:362-365 then :368)
-        int warps_per_block = 8;
-        int blocks = (L.total_rays + warps_per_block - 1) / warps_per_block;
-        k_raytrace_clear<<<blocks, warps_per_block * 32, 0, h->stream>>>(L.grid[L.cur], g, L.d_clear, L.n_clear, L.d_xyz,
-                                                                        L.total_rays, h->d_boxes + li);
-        NAVGPU_LAUNCHED(1);
-      }
-      if (L.total_marks > 0) {
-        int blocks = (L.total_marks + 255) / 256;
-        k_mark_points<<<blocks, 256, 0, h->stream>>>(L.grid[L.cur], g, L.d_mark, L.n_mark, L.d_xyz, L.total_marks,
-                                                     L.max_obstacle_height, h->d_boxes + li);
-        NAVGPU_LAUNCHED(1);
-      }
       if (L.footprint_clearing) {  // updateFootprint (:415-425) with transformFootprint (footprint.cpp:106-120)
-        L.transformed_footprint.clear();
         double cos_th = cos(ryaw), sin_th = sin(ryaw);
         for (const Pt& p : h->footprint)
           L.transformed_footprint.push_back(Pt{rx + (p.x * cos_th - p.y * sin_th), ry + (p.x * sin_th + p.y * cos_th)});
@@ -364,8 +395,46 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
       L.need_reinflation = false;
     }
   }
-  k_finalize_bounds<<<1, 32, 0, h->stream>>>(ba, h->d_boxes, h->d_infl, h->d_win);
-  NAVGPU_LAUNCHED(1);
+
+  // ---- device part: one k_obstacle_update per enabled obstacle layer (ray-trace clearing, then marking, then the
+  // footprint polygon of updateCosts); the last one also finalises the bounds into the cycle's window
+  for (size_t li = 0; li < h->layers.size(); ++li) {
+    Layer& L = h->layers[li];
+    if (L.kind != 1 || !L.enabled) continue;
+    ObstacleArgs oa;
+    oa.grid = L.grid[L.cur];
+    oa.g = h->geom(L.ox, L.oy);
+    oa.clear = L.d_clear; oa.mark = L.d_mark; oa.xyz = L.d_xyz;
+    oa.n_clear = L.n_clear; oa.total_rays = L.total_rays; oa.n_mark = L.n_mark; oa.total_marks = L.total_marks;
+    oa.max_obstacle_height = L.max_obstacle_height;
+    oa.box = h->d_boxes + li;
+    oa.mark_cells = L.d_mark_cells;
+    oa.ticket = h->d_ticket;
+    int mode = 0;
+    if (L.footprint_clearing) NAVGPU_TRY(footprint_polygon(h, L, oa.poly, &mode));
+    oa.do_poly = mode == 1;
+    oa.do_finalize = (int)li == last_obstacle;
+    if (oa.do_finalize) oa.ba = ba;
+    oa.boxes = h->d_boxes; oa.infl = h->d_infl; oa.win = h->d_win;
+    static const int debug_skip = getenv("NAVGPU_DEBUG_SKIP") ? atoi(getenv("NAVGPU_DEBUG_SKIP")) : 0;
+    oa.debug_skip = debug_skip;
+    const int blocks = std::max(1, (L.total_rays * 32 + kObstacleThreads - 1) / kObstacleThreads);
+    k_obstacle_update<<<blocks, kObstacleThreads, 0, h->stream>>>(oa);
+    NAVGPU_LAUNCHED(1);
+    if (mode == 2) {  // large footprint: stand-alone rasteriser with dynamic shared memory
+      size_t smem = 2 * kPolyMaxCells * sizeof(uint32_t);
+      if (!h->poly_attr_set) {
+        NAVGPU_CUDA(cudaFuncSetAttribute(k_polygon_clear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->poly_attr_set = true;
+      }
+      k_polygon_clear<<<1, 256, smem, h->stream>>>(L.grid[L.cur], h->pitch, oa.poly, kFree);
+      NAVGPU_LAUNCHED(1);
+    }
+  }
+  if (last_obstacle < 0) {
+    k_finalize_bounds<<<1, 32, 0, h->stream>>>(ba, h->d_boxes, h->d_infl, h->d_win);
+    NAVGPU_LAUNCHED(1);
+  }
 
   // ---- resetMap + updateCosts of every plugin, in order (:137-142), fused into as few sweeps as possible:
   // consecutive cost layers merge in one pass, an inflation layer closes the pass.
@@ -375,40 +444,6 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   bool pending = true;  // the reset itself must happen even with no enabled layer
   for (size_t li = 0; li < h->layers.size(); ++li) {
     Layer& L = h->layers[li];
-    if (L.kind == 1 && L.enabled && L.footprint_clearing) {
-      // setConvexPolygonCost(transformed_footprint_, FREE_SPACE) on the layer's own grid (obstacle_layer.cpp:432-435)
-      PolyArgs pa;
-      pa.n = 0;
-      bool ok = L.transformed_footprint.size() <= 32;
-      if (L.transformed_footprint.size() > 32) return fail(NAVGPU_ERR_UNSUPPORTED, "footprint with more than 32 vertices");
-      long long outline = 0;
-      for (const Pt& p : L.transformed_footprint) {  // worldToMap, costmap_2d.cpp:208-220
-        if (p.x < L.ox || p.y < L.oy) { ok = false; break; }
-        unsigned mx = (int)((p.x - L.ox) / h->res), my = (int)((p.y - L.oy) / h->res);
-        if (!(mx < h->sx && my < h->sy)) { ok = false; break; }
-        pa.vx[pa.n] = (int)mx;
-        pa.vy[pa.n] = (int)my;
-        ++pa.n;
-      }
-      if (ok && pa.n >= 3) {
-        long long minx = pa.vx[0], maxx = pa.vx[0], miny = pa.vy[0], maxy = pa.vy[0];
-        for (int k = 0; k < pa.n; ++k) {
-          int k1 = (k + 1) % pa.n;
-          outline += std::max(std::abs(pa.vx[k1] - pa.vx[k]), std::abs(pa.vy[k1] - pa.vy[k])) + 1;
-          minx = std::min<long long>(minx, pa.vx[k]); maxx = std::max<long long>(maxx, pa.vx[k]);
-          miny = std::min<long long>(miny, pa.vy[k]); maxy = std::max<long long>(maxy, pa.vy[k]);
-        }
-        if (outline + (maxx - minx + 1) * (maxy - miny + 1) > kPolyMaxCells || h->sx > 65535 || h->sy > 65535)
-          return fail(NAVGPU_ERR_UNSUPPORTED, "footprint polygon covers too many cells for the device rasteriser");
-        size_t smem = 2 * kPolyMaxCells * sizeof(uint32_t);
-        if (!h->poly_attr_set) {
-          NAVGPU_CUDA(cudaFuncSetAttribute(k_polygon_clear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          h->poly_attr_set = true;
-        }
-        k_polygon_clear<<<1, 256, smem, h->stream>>>(L.grid[L.cur], h->pitch, pa, kFree);
-        NAVGPU_LAUNCHED(1);
-      }
-    }
     if (L.kind == 0 || L.kind == 1) {
       if (!L.enabled) continue;
       int policy = L.kind == 0 ? L.policy
@@ -427,7 +462,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
         NAVGPU_TRY(launch_update(h, ml, 0, 0, nullptr));
         ml.n = 0;
       }
-      NAVGPU_TRY(launch_update(h, ml, do_reset, (int)L.tables.R, L.d_cost_d2));
+      NAVGPU_TRY(launch_update(h, ml, do_reset, (int)L.tables.R, L.d_cost_d2, L.tables.reach2));
       ml.n = 0;
       do_reset = 0;
       pending = false;
@@ -471,6 +506,8 @@ int navgpu_costmap_create(navgpu_costmap** out, uint32_t size_x, uint32_t size_y
   NAVGPU_CUDA(cudaMalloc(&h->d_boxes, sizeof(DevBox) * kMaxLayers));
   NAVGPU_CUDA(cudaMalloc(&h->d_infl, sizeof(InflationBoundsState) * kMaxLayers));
   NAVGPU_CUDA(cudaMalloc(&h->d_win, sizeof(DevWindow)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_ticket, sizeof(unsigned)));
+  NAVGPU_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
   NAVGPU_CUDA(cudaMallocHost(&h->h_win, sizeof(DevWindow)));
   DevBox boxes[kMaxLayers];
   InflationBoundsState infl[kMaxLayers];
@@ -493,10 +530,10 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   cudaStreamSynchronize(h->stream);
   for (Layer& L : h->layers) {
     cudaFree(L.grid[0]); cudaFree(L.grid[1]);
-    cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2);
+    cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_mark_cells);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
-  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds);
+  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket);
   cudaFreeHost(h->h_win);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -677,6 +714,12 @@ int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_
     NAVGPU_CUDA(cudaMalloc(&L->d_xyz, xyz.size() * sizeof(float)));
     L->xyz_capacity = xyz.size();
   }
+  if ((size_t)marks > L->mark_cells_capacity) {
+    if (L->d_mark_cells) cudaFree(L->d_mark_cells);
+    L->d_mark_cells = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&L->d_mark_cells, size_t(marks) * 2 * sizeof(long long)));
+    L->mark_cells_capacity = size_t(marks) * 2;
+  }
   size_t need = std::max(clear.size(), mark.size());
   if (need > L->obs_capacity) {
     if (L->d_clear) cudaFree(L->d_clear);
@@ -725,11 +768,13 @@ int navgpu_costmap_force_generic_sweep(navgpu_costmap* h, int enabled) {
 int navgpu_costmap_set_profiling(navgpu_costmap* h, int enabled) {
   if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
   NAVGPU_TRY(use_device(h));
-  if (enabled && !h->ev_sweep[0])
+  if (enabled && !h->ev_sweep[0]) {
     for (int i = 0; i < 2; ++i) {
       NAVGPU_CUDA(cudaEventCreate(&h->ev_sweep[i]));
       NAVGPU_CUDA(cudaEventCreate(&h->ev_cycle[i]));
     }
+    NAVGPU_CUDA(cudaEventCreate(&h->ev_mid));
+  }
   h->profile = enabled != 0;
   return NAVGPU_OK;
 }
@@ -771,6 +816,15 @@ int navgpu_costmap_update_map(navgpu_costmap* h, double rx, double ry, double ry
   }
   if (window_out)
     for (int i = 0; i < 4; ++i) window_out[i] = h->win[i];
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_last_timing_split(navgpu_costmap* h, float* merge_ms, float* inflate_ms) {
+  if (!h || !h->profile) return fail(NAVGPU_ERR_INVALID, "profiling is not enabled on this handle");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaEventSynchronize(h->ev_sweep[1]));
+  if (merge_ms) NAVGPU_CUDA(cudaEventElapsedTime(merge_ms, h->ev_sweep[0], h->ev_mid));
+  if (inflate_ms) NAVGPU_CUDA(cudaEventElapsedTime(inflate_ms, h->ev_mid, h->ev_sweep[1]));
   return NAVGPU_OK;
 }
 
@@ -930,6 +984,9 @@ int seam_run(uint8_t* master, const uint8_t* layer, uint32_t size_x, uint32_t si
   a.ml = ml;
   a.R = R;
   a.cost_d2 = c->d_table;
+  a.reach2 = 0;
+  for (int d2 = 0; R > 0 && d2 <= R * R; ++d2)
+    if (by_d2[d2] != 0) a.reach2 = d2;
   if (R > 0 && R <= 31) {
     NAVGPU_TRY(ensure_seeds(&c->d_seeds, &c->cap_seeds, pitch, rows, c->stream));
     if (c->seeds_pitch != pitch) {  // another row layout: the pad groups of the new layout must read as zero

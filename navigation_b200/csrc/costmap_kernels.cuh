@@ -21,24 +21,31 @@ __device__ __forceinline__ bool world_to_map(const Geom& g, double wx, double wy
   return mx < g.sx && my < g.sy;
 }
 
-__device__ __forceinline__ void box_touch_warp(DevBox* box, double x, double y, bool active) {
-  // warp-aggregated CostmapLayer::touch (src/costmap_layer.cpp:8-14): one atomic per warp and coordinate
-  unsigned long long ex_min = active ? enc_double(x) : ~0ull, ex_max = active ? enc_double(x) : 0ull;
-  unsigned long long ey_min = active ? enc_double(y) : ~0ull, ey_max = active ? enc_double(y) : 0ull;
+// CostmapLayer::touch (src/costmap_layer.cpp:8-14) accumulated per thread in registers, then reduced per warp with
+// shuffles and folded into the layer's device box with one atomic per warp and coordinate
+struct BoxAcc {
+  unsigned long long minx = ~0ull, miny = ~0ull, maxx = 0ull, maxy = 0ull;
+  __device__ __forceinline__ void touch(double x, double y) {
+    const unsigned long long ex = enc_double(x), ey = enc_double(y);
+    minx = min(minx, ex); maxx = max(maxx, ex);
+    miny = min(miny, ey); maxy = max(maxy, ey);
+  }
+  __device__ __forceinline__ void flush_warp(DevBox* box) {  // all 32 lanes must call
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ex_min = min(ex_min, __shfl_xor_sync(0xffffffffu, ex_min, o));
-    ex_max = max(ex_max, __shfl_xor_sync(0xffffffffu, ex_max, o));
-    ey_min = min(ey_min, __shfl_xor_sync(0xffffffffu, ey_min, o));
-    ey_max = max(ey_max, __shfl_xor_sync(0xffffffffu, ey_max, o));
+    for (int o = 16; o > 0; o >>= 1) {
+      minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+      maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+      miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+      maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    }
+    if ((threadIdx.x & 31) == 0 && maxx != 0ull) {
+      atomicMin(&box->minx, minx);
+      atomicMax(&box->maxx, maxx);
+      atomicMin(&box->miny, miny);
+      atomicMax(&box->maxy, maxy);
+    }
   }
-  if ((threadIdx.x & 31) == 0 && ex_max != 0ull) {
-    atomicMin(&box->minx, ex_min);
-    atomicMax(&box->maxx, ex_max);
-    atomicMin(&box->miny, ey_min);
-    atomicMax(&box->maxy, ey_max);
-  }
-}
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Rolling-window origin shift, Costmap2D::updateOrigin (src/costmap_2d.cpp:264-313): out of place,
@@ -89,10 +96,9 @@ struct DevObs {
 // contraction); the Bresenham walk is evaluated in closed form so the lanes write cells i, i+32, ... in parallel:
 // after i major steps the reference's error accumulator has taken floor((abs_da/2 + i*abs_db)/abs_da) minor steps.
 // All writers store FREE_SPACE, so write order between rays does not matter.
-__global__ void k_raytrace_clear(uint8_t* __restrict__ grid, Geom g, const DevObs* __restrict__ obs, int n_obs,
-                                 const float* __restrict__ xyz, int total_rays, DevBox* box) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void raytrace_ray(uint8_t* __restrict__ grid, const Geom& g, const DevObs* __restrict__ obs,
+                                             int n_obs, const float* __restrict__ xyz, int total_rays, DevBox* box,
+                                             int warp, int lane) {
   bool touch1 = false;
   double t1x = 0, t1y = 0;
   if (warp < total_rays) {
@@ -144,9 +150,16 @@ __global__ void k_raytrace_clear(uint8_t* __restrict__ grid, Geom g, const DevOb
         const unsigned end = min((unsigned)(scale * da), da);
         const long long start = (long long)y0 * g.pitch + x0;
         const unsigned half = da / 2;
-        for (unsigned i = lane; i <= end; i += 32) {  // cells 0..end-1 of the loop plus the final at(offset)
-          const unsigned m = da ? (unsigned)((half + (unsigned long long)i * db) / da) : 0u;
-          grid[start + (long long)i * off_a + (long long)m * off_b] = kFree;
+        if (da < 32768u) {  // i * db < 2^30: the closed form fits 32-bit arithmetic
+          for (unsigned i = lane; i <= end; i += 32) {  // cells 0..end-1 of the loop plus the final at(offset)
+            const unsigned m = da ? (half + i * db) / da : 0u;
+            grid[start + (long long)((int)i * off_a + (int)m * off_b)] = kFree;
+          }
+        } else {
+          for (unsigned i = lane; i <= end; i += 32) {
+            const unsigned m = (unsigned)((half + (unsigned long long)i * db) / da);
+            grid[start + (long long)i * off_a + (long long)m * off_b] = kFree;
+          }
         }
         // updateRaytraceBounds
         const double ddx = wx - ox, ddy = wy - oy;
@@ -158,37 +171,48 @@ __global__ void k_raytrace_clear(uint8_t* __restrict__ grid, Geom g, const DevOb
       }
     }
   }
-  // every lane of a warp holds the same values; reduce across the block's warps through lane 0 only
-  box_touch_warp(box, t1x, t1y, touch1 && lane == 0);
+  // every lane of the warp holds the same end point: lane 0 publishes it
+  if (touch1 && lane == 0) {
+    const unsigned long long ex = enc_double(t1x), ey = enc_double(t1y);
+    atomicMin(&box->minx, ex);
+    atomicMax(&box->maxx, ex);
+    atomicMin(&box->miny, ey);
+    atomicMax(&box->maxy, ey);
+  }
 }
 
-// ObstacleLayer::updateBounds marking loop (plugins/obstacle_layer.cpp:368-410): one thread per point
-__global__ void k_mark_points(uint8_t* __restrict__ grid, Geom g, const DevObs* __restrict__ obs, int n_obs,
-                              const float* __restrict__ xyz, int total_points, double max_obstacle_height,
-                              DevBox* box) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool touched = false;
-  double px = 0, py = 0;
-  if (t < total_points) {
-    int k = 0;
-    while (k + 1 < n_obs && obs[k + 1].first_ray <= t) ++k;
-    const DevObs o = obs[k];
-    const int pi = o.first_point + (t - o.first_ray);
-    px = xyz[3 * (size_t)pi];
-    py = xyz[3 * (size_t)pi + 1];
-    const double pz = xyz[3 * (size_t)pi + 2];
-    if (!(pz > max_obstacle_height)) {
-      const double sq_dist = (px - o.ox) * (px - o.ox) + (py - o.oy) * (py - o.oy) + (pz - o.oz) * (pz - o.oz);
-      if (!(sq_dist >= o.obstacle_range * o.obstacle_range)) {
-        unsigned mx, my;
-        if (world_to_map(g, px, py, mx, my)) {
-          grid[(size_t)my * g.pitch + mx] = kLethal;
-          touched = true;
-        }
+// ObstacleLayer::updateBounds marking loop (plugins/obstacle_layer.cpp:368-410), split in two so that the fp64 tests
+// run on every CTA while the stores wait for all ray-trace clearing to finish:
+//   mark_prepare  one thread per point: height / range tests, worldToMap, touch; leaves the cell offset (or -1) in
+//                 `cells`
+//   mark_commit   the threads of ONE CTA store LETHAL_OBSTACLE to the prepared offsets
+__device__ __forceinline__ void mark_prepare(const Geom& g, const DevObs* __restrict__ obs, int n_obs,
+                                             const float* __restrict__ xyz, double max_obstacle_height, BoxAcc& acc,
+                                             long long* __restrict__ cells, int t) {
+  int k = 0;
+  while (k + 1 < n_obs && obs[k + 1].first_ray <= t) ++k;
+  const DevObs o = obs[k];
+  const size_t pi = (size_t)(o.first_point + (t - o.first_ray));
+  const double px = xyz[3 * pi], py = xyz[3 * pi + 1], pz = xyz[3 * pi + 2];
+  long long cell = -1;
+  if (!(pz > max_obstacle_height)) {
+    const double sq_dist = (px - o.ox) * (px - o.ox) + (py - o.oy) * (py - o.oy) + (pz - o.oz) * (pz - o.oz);
+    if (!(sq_dist >= o.obstacle_range * o.obstacle_range)) {
+      unsigned mx, my;
+      if (world_to_map(g, px, py, mx, my)) {
+        cell = (long long)my * g.pitch + mx;
+        acc.touch(px, py);
       }
     }
   }
-  box_touch_warp(box, px, py, touched);
+  cells[t] = cell;
+}
+
+__device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, const long long* cells, int total_points) {
+  for (int t = threadIdx.x; t < total_points; t += blockDim.x) {
+    const long long cell = __ldcg(cells + t);  // written by other CTAs of this launch
+    if (cell >= 0) grid[cell] = kLethal;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -196,15 +220,16 @@ __global__ void k_mark_points(uint8_t* __restrict__ grid, Geom g, const DevObs* 
 // One CTA.  Outline cells come from the closed-form Bresenham (parallel), the reference's back-stepping bubble sort
 // is a stable sort by x (parallel rank), and the column walk -- which in the reference iterates over the very
 // vector it appends to -- is replayed verbatim by one thread so that degenerate footprints fill identically.
-constexpr int kPolyMaxCells = 12288;
+constexpr int kPolyMaxCells = 12288;   // stand-alone kernel (dynamic shared memory)
+constexpr int kPolySmallCells = 2048;  // inside k_obstacle_update (static shared memory)
 struct PolyArgs {
   int n;
   int vx[32], vy[32];
 };
-__global__ void k_polygon_clear(uint8_t* __restrict__ grid, unsigned pitch, PolyArgs poly, uint8_t value) {
-  extern __shared__ uint32_t poly_smem[];
-  uint32_t* cells = poly_smem;                  // packed x | y << 16, in outline order
-  uint32_t* sorted = poly_smem + kPolyMaxCells;  // the vector convexFillCells works on
+// cells / sorted: `capacity` packed (x | y << 16) entries each: the outline in order, and the vector convexFillCells
+// works on.  Called by every thread of one CTA.
+__device__ __forceinline__ void polygon_clear_cta(uint8_t* __restrict__ grid, unsigned pitch, const PolyArgs& poly,
+                                                  uint8_t value, uint32_t* cells, uint32_t* sorted, int capacity) {
   __shared__ int edge_first[33];
   __shared__ int n_total;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -240,6 +265,46 @@ __global__ void k_polygon_clear(uint8_t* __restrict__ grid, unsigned pitch, Poly
     cells[j] = (uint32_t)x | ((uint32_t)y << 16);
   }
   __syncthreads();
+  // Regular outlines -- every column between the extreme vertices holds at least two outline cells, which is what a
+  // closed outline gives -- make the reference's column walk (costmap_2d.cpp:391-427) a per-column [min_y, max_y)
+  // fill: the first two sorted entries of a column seed min/max, the rest extend them.  That case runs in parallel;
+  // anything else (degenerate footprints) replays the walk verbatim below.
+  {
+    __shared__ int s_irregular;
+    int min_x = poly.vx[0], max_x = poly.vx[0], min_y = poly.vy[0], max_y = poly.vy[0];
+    for (int k = 1; k < poly.n; ++k) {
+      min_x = min(min_x, poly.vx[k]); max_x = max(max_x, poly.vx[k]);
+      min_y = min(min_y, poly.vy[k]); max_y = max(max_y, poly.vy[k]);
+    }
+    const int W = max_x - min_x + 1, H = max_y - min_y + 1;
+    if (W >= 2 && 3 * W <= capacity) {  // block-uniform
+      int* colmin = reinterpret_cast<int*>(sorted);
+      int* colmax = colmin + W;
+      int* colcnt = colmax + W;
+      for (int c = tid; c < W; c += nt) { colmin[c] = 0x7fffffff; colmax[c] = -1; colcnt[c] = 0; }
+      if (tid == 0) s_irregular = 0;
+      __syncthreads();
+      for (int j = tid; j < n_outline; j += nt) {
+        const int c = (int)(cells[j] & 0xffffu) - min_x, y = (int)(cells[j] >> 16);
+        atomicMin(&colmin[c], y);
+        atomicMax(&colmax[c], y);
+        atomicAdd(&colcnt[c], 1);
+      }
+      __syncthreads();
+      for (int c = tid; c < W; c += nt)
+        if (colcnt[c] < 2) s_irregular = 1;
+      __syncthreads();
+      if (!s_irregular) {
+        for (int j = tid; j < n_outline; j += nt) grid[(size_t)(cells[j] >> 16) * pitch + (cells[j] & 0xffffu)] = value;
+        for (int j = tid; j < W * H; j += nt) {
+          const int c = j % W, y = min_y + j / W;
+          if (y >= colmin[c] && y < colmax[c]) grid[(size_t)y * pitch + (min_x + c)] = value;
+        }
+        return;
+      }
+      __syncthreads();  // the scratch is reused by the walk
+    }
+  }
   for (int j = tid; j < n_outline; j += nt) {  // stable rank by x
     const uint32_t xj = cells[j] & 0xffffu;
     int rank = 0;
@@ -267,7 +332,7 @@ __global__ void k_polygon_clear(uint8_t* __restrict__ grid, unsigned pitch, Poly
         else if (Y(i) > max_y) max_y = Y(i);
         ++i;
       }
-      for (int y = min_y; y < max_y && size < kPolyMaxCells; ++y) sorted[size++] = (uint32_t)x | ((uint32_t)y << 16);
+      for (int y = min_y; y < max_y && size < capacity; ++y) sorted[size++] = (uint32_t)x | ((uint32_t)y << 16);
     }
     n_total = size;
   }
@@ -297,8 +362,8 @@ struct BoundsArgs {
 struct InflationBoundsState {
   double last_min_x, last_min_y, last_max_x, last_max_y;
 };
-__global__ void k_finalize_bounds(BoundsArgs a, DevBox* boxes, InflationBoundsState* infl, DevWindow* win) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void finalize_bounds(const BoundsArgs& a, DevBox* boxes, InflationBoundsState* infl,
+                                                DevWindow* win) {  // one thread
   double minx = 1e30, miny = 1e30, maxx = -1e30, maxy = -1e30;
   for (int l = 0; l < a.n_layers; ++l) {
     const BoundsLayer& L = a.layer[l];
@@ -307,7 +372,10 @@ __global__ void k_finalize_bounds(BoundsArgs a, DevBox* boxes, InflationBoundsSt
         minx = fmin(minx, L.hx0); miny = fmin(miny, L.hy0);
         maxx = fmax(maxx, L.hx1); maxy = fmax(maxy, L.hy1);
       }
-      DevBox b = boxes[l];
+      // accumulated with atomics by other CTAs: read past L1
+      DevBox b;
+      b.minx = __ldcg(&boxes[l].minx); b.miny = __ldcg(&boxes[l].miny);
+      b.maxx = __ldcg(&boxes[l].maxx); b.maxy = __ldcg(&boxes[l].maxy);
       if (b.maxx != 0ull) {  // something was touched on the device this cycle
         minx = fmin(minx, dec_double(b.minx)); miny = fmin(miny, dec_double(b.miny));
         maxx = fmax(maxx, dec_double(b.maxx)); maxy = fmax(maxy, dec_double(b.maxy));
@@ -345,6 +413,80 @@ __global__ void k_finalize_bounds(BoundsArgs a, DevBox* boxes, InflationBoundsSt
   win->valid = !(xn < x0 || yn < y0);
 }
 
+__global__ void k_finalize_bounds(BoundsArgs a, DevBox* boxes, InflationBoundsState* infl, DevWindow* win) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) finalize_bounds(a, boxes, infl, win);
+}
+
+// stand-alone polygon rasteriser for footprints too large for k_obstacle_update's static scratch
+__global__ void k_polygon_clear(uint8_t* __restrict__ grid, unsigned pitch, PolyArgs poly, uint8_t value) {
+  extern __shared__ uint32_t poly_smem[];
+  polygon_clear_cta(grid, pitch, poly, value, poly_smem, poly_smem + kPolyMaxCells, kPolyMaxCells);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One launch per obstacle layer and cycle: ObstacleLayer::updateBounds + the footprint part of updateCosts
+// (plugins/obstacle_layer.cpp:340-448).  Every CTA ray-traces 8 rays (one warp each).  The reference clears ALL rays
+// before it marks ANY point (:362-365 then :368), so the CTA that finishes last (ticket + __threadfence, no
+// spinning) marks the points, clears the footprint polygon (what updateCosts does first, on the same grid) and, for
+// the last observation-driven layer of the stack, runs the bounds pass that needs every layer's accumulated box.
+struct ObstacleArgs {
+  uint8_t* grid;
+  Geom g;
+  const DevObs* clear;
+  const DevObs* mark;
+  const float* xyz;
+  int n_clear, total_rays, n_mark, total_marks;
+  double max_obstacle_height;
+  DevBox* box;  // this layer's box
+  long long* mark_cells;  // total_marks entries of scratch
+  unsigned* ticket;
+  int do_poly;
+  PolyArgs poly;
+  int do_finalize;
+  BoundsArgs ba;
+  DevBox* boxes;
+  InflationBoundsState* infl;
+  DevWindow* win;
+  int debug_skip;  // measurement only (NAVGPU_DEBUG_SKIP): 1 marks, 2 polygon, 4 bounds, 8 ray tracing -- wrong results
+};
+constexpr int kObstacleThreads = 256;
+
+__global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleArgs a) {
+  __shared__ uint32_t poly_cells[kPolySmallCells], poly_sorted[kPolySmallCells];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kObstacleThreads + threadIdx.x) >> 5;
+  if (!(a.debug_skip & 8)) raytrace_ray(a.grid, a.g, a.clear, a.n_clear, a.xyz, a.total_rays, a.box, warp, lane);
+  {  // this CTA's share of the marking tests
+    const int per_cta = (a.total_marks + gridDim.x - 1) / gridDim.x;
+    BoxAcc acc;
+    for (int i = threadIdx.x; i < per_cta; i += kObstacleThreads) {
+      const int t = blockIdx.x * per_cta + i;
+      if (t < a.total_marks && !(a.debug_skip & 1))
+        mark_prepare(a.g, a.mark, a.n_mark, a.xyz, a.max_obstacle_height, acc, a.mark_cells, t);
+    }
+    acc.flush_warp(a.box);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (!(a.debug_skip & 1)) mark_commit_cta(a.grid, a.mark_cells, a.total_marks);
+  __syncthreads();
+  if (a.do_poly && !(a.debug_skip & 2)) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
+  if (threadIdx.x == 0) {
+    *a.ticket = 0;  // re-armed for the next cycle
+    if (a.do_finalize && !(a.debug_skip & 4)) {
+      __threadfence();
+      finalize_bounds(a.ba, a.boxes, a.infl, a.win);
+    }
+  }
+}
+
 __global__ void k_set_window(DevWindow* win, int x0, int xn, int y0, int yn) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     win->x0 = x0; win->xn = xn; win->y0 = y0; win->yn = yn;
@@ -378,6 +520,7 @@ struct UpdateArgs {
   MergeLayers ml;
   int R;                   // 0: no inflation in this pass
   const uint8_t* cost_d2;  // R*R+1 entries: cost by squared cell distance
+  int reach2;              // largest squared distance whose cost is not 0 (a cost of 0 never changes a cell)
 };
 
 __device__ __forceinline__ uint8_t apply_policy(uint8_t m, uint8_t v, int policy) {
@@ -546,7 +689,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 //                  VIADDMNMX.U16x2 per row and cell pair; the epilogue looks the cost up by d^2 and applies
 //                  InflationLayer's max / NO_INFORMATION rule directly on the master grid, touching only rows that
 //                  inflation reaches.  A tile whose seed words are all zero exits after the load.
-constexpr int kMSGroupsX = 32, kMSRowsY = 8, kMSRowIters = 2;  // k_merge_seed: CTA = 512 columns x 16 rows
+constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2;  // k_merge_seed: CTA = 256 columns x 32 rows
 constexpr int kITX = 64, kITY = 128, kIThreads = 256, kIMaxRows = kITY + 2 * 31;
 constexpr uint32_t kH2Inf = 0x3000;  // "no seed within R on this row" (as a squared distance, per 16-bit half)
 
@@ -620,51 +763,41 @@ __device__ __forceinline__ uint32_t lethal_bits4(uint32_t v) {  // one bit per b
   return (e * 0x01020408u) >> 24;
 }
 
-__global__ void __launch_bounds__(kMSGroupsX * kMSRowsY) k_merge_seed(MergeSeedArgs a) {
-  const DevWindow w = *a.win;
-  if (!w.valid) return;
+// body of k_merge_seed for one thread: kMSRowIters groups of 16 cells in one column of groups.  kInterior: the whole
+// CTA tile lies inside the window, the seed region and the map, so every per-group edge test folds away.
+template <bool kInterior>
+__device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const DevWindow& w, int x, int by0, int sx0,
+                                                 int sxn, int sy0, int syn) {
   const int R = a.R;
-  // everything k_inflate can read: its tiles intersect window +- 2R, extend up to a tile further, and look R rows /
-  // 32 columns beyond their own extent
-  const int my = R > 0 ? 3 * R + kITY : 0, mx = R > 0 ? 2 * R + kITX + 32 : 0;
-  const int bx0 = blockIdx.x * (kMSGroupsX * 16), by0 = blockIdx.y * (kMSRowsY * kMSRowIters);
-  if (bx0 >= w.xn + mx || bx0 + kMSGroupsX * 16 <= w.x0 - mx || by0 >= w.yn + my ||
-      by0 + kMSRowsY * kMSRowIters <= w.y0 - my)
-    return;
-  const int sx0 = max(0, w.x0 - R), sxn = min((int)a.sx, w.xn + R);  // seed region (inflation_layer.cpp:203-211)
-  const int sy0 = max(0, w.y0 - R), syn = min((int)a.sy, w.yn + R);
-  const int x = bx0 + threadIdx.x * 16;
-  if (x >= (int)a.pitch) return;
   const unsigned sp16 = seed_pitch16(a.pitch);
-  const bool col_any = x + 16 > w.x0 && x < w.xn, col_all = x >= w.x0 && x + 16 <= w.xn;
-  const bool col_seed = R > 0 && x + 16 > sx0 && x < sxn;
+  const bool col_any = kInterior || (x + 16 > w.x0 && x < w.xn), col_all = kInterior || (x >= w.x0 && x + 16 <= w.xn);
+  const bool col_seed = kInterior ? R > 0 : (R > 0 && x + 16 > sx0 && x < sxn);
 
   // loads of all row iterations first (memory-level parallelism), then the merges
   uint4 mv[kMSRowIters];
   uint4 lv[kMSRowIters][2];
-  const int nfast = min(a.ml.n, 2);
 #pragma unroll
   for (int it = 0; it < kMSRowIters; ++it) {
     const int y = by0 + threadIdx.y + it * kMSRowsY;
     mv[it] = make_uint4(0, 0, 0, 0);
     lv[it][0] = lv[it][1] = make_uint4(0, 0, 0, 0);
-    if (y >= (int)a.sy) continue;
+    if (!kInterior && y >= (int)a.sy) continue;
     const size_t off = (size_t)y * a.pitch + x;
-    const bool row_in = y >= w.y0 && y < w.yn;
+    const bool row_in = kInterior || (y >= w.y0 && y < w.yn);
     const bool any_in = row_in && col_any, all_in = row_in && col_all;
     const bool need_master = any_in ? !(all_in && a.do_reset) : (col_seed && y >= sy0 && y < syn);
     if (need_master) mv[it] = *reinterpret_cast<const uint4*>(a.master + off);
     if (any_in) {
-      if (nfast > 0) lv[it][0] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off);
-      if (nfast > 1) lv[it][1] = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off);
+      if (a.ml.n > 0) lv[it][0] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off);
+      if (a.ml.n > 1) lv[it][1] = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off);
     }
   }
 #pragma unroll
   for (int it = 0; it < kMSRowIters; ++it) {
     const int y = by0 + threadIdx.y + it * kMSRowsY;
-    if (y >= (int)a.sy) continue;
+    if (!kInterior && y >= (int)a.sy) continue;
     const size_t off = (size_t)y * a.pitch + x;
-    const bool row_in = y >= w.y0 && y < w.yn;
+    const bool row_in = kInterior || (y >= w.y0 && y < w.yn);
     const bool any_in = row_in && col_any, all_in = row_in && col_all;
     uint4 v = mv[it];
     if (all_in) {
@@ -684,7 +817,6 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY) k_merge_seed(MergeSeedA
         else if (l == 1) lv4 = lv[it][1];
         else if (l >= 2) lv4 = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
         const uint32_t lw[4] = {lv4.x, lv4.y, lv4.z, lv4.w};
-#pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int cx = x + i;
           if (cx < w.x0 || cx >= w.xn) continue;
@@ -700,13 +832,38 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY) k_merge_seed(MergeSeedA
     if (any_in) *reinterpret_cast<uint4*>(a.master + off) = v;
     if (R > 0) {
       uint32_t seed16 = 0;
-      if (col_seed && y >= sy0 && y < syn && (v.x | v.y | v.z | v.w) != 0) {
-        const uint32_t lb = lethal_bits4(v.x) | (lethal_bits4(v.y) << 4) | (lethal_bits4(v.z) << 8) | (lethal_bits4(v.w) << 12);
-        const int lo = min(16, max(0, sx0 - x)), hi = min(16, max(0, sxn - x));
-        seed16 = lb & ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      if ((kInterior || (col_seed && y >= sy0 && y < syn)) && (v.x | v.y | v.z | v.w) != 0) {
+        seed16 = lethal_bits4(v.x) | (lethal_bits4(v.y) << 4) | (lethal_bits4(v.z) << 8) | (lethal_bits4(v.w) << 12);
+        if (!kInterior) {
+          const int lo = min(16, max(0, sx0 - x)), hi = min(16, max(0, sxn - x));
+          seed16 &= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+        }
       }
       a.seeds[(size_t)y * sp16 + 2 + (x >> 4)] = (uint16_t)seed16;
     }
+  }
+}
+
+__global__ void __launch_bounds__(kMSGroupsX * kMSRowsY) k_merge_seed(MergeSeedArgs a) {
+  const DevWindow w = *a.win;
+  if (!w.valid) return;
+  const int R = a.R;
+  // everything k_inflate can read: its tiles intersect window +- 2R, extend up to a tile further, and look R rows /
+  // 32 columns beyond their own extent
+  const int my = R > 0 ? 3 * R + kITY : 0, mx = R > 0 ? 2 * R + kITX + 32 : 0;
+  constexpr int kW = kMSGroupsX * 16, kH = kMSRowsY * kMSRowIters;
+  const int bx0 = blockIdx.x * kW, by0 = blockIdx.y * kH;
+  if (bx0 >= w.xn + mx || bx0 + kW <= w.x0 - mx || by0 >= w.yn + my || by0 + kH <= w.y0 - my) return;
+  const int sx0 = max(0, w.x0 - R), sxn = min((int)a.sx, w.xn + R);  // seed region (inflation_layer.cpp:203-211)
+  const int sy0 = max(0, w.y0 - R), syn = min((int)a.sy, w.yn + R);
+  const int x = bx0 + threadIdx.x * 16;
+  // the window lies inside the map, the seed region contains the window: a tile inside the window is interior
+  const bool interior = bx0 >= w.x0 && bx0 + kW <= w.xn && by0 >= w.y0 && by0 + kH <= w.yn;
+  if (interior) {
+    merge_seed_items<true>(a, w, x, by0, sx0, sxn, sy0, syn);
+  } else {
+    if (x >= (int)a.pitch) return;
+    merge_seed_items<false>(a, w, x, by0, sx0, sxn, sy0, syn);
   }
 }
 
@@ -715,6 +872,7 @@ struct InflateArgs {
   unsigned sx, sy, pitch;
   const DevWindow* win;
   int R;
+  int reach2;              // largest squared distance whose cost is not 0: nothing beyond it can change a cell
   const uint8_t* cost_d2;  // R*R+1 entries: cost by squared cell distance
   const uint32_t* seeds;   // the bitmask written by k_merge_seed, viewed as 32-bit words
 };
@@ -727,9 +885,14 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
   const DevWindow w = *a.win;
   if (!w.valid) return;
-  const int R = a.R;
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
-  if (tx0 >= w.xn + 2 * R || tx0 + kITX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kITY <= w.y0 - 2 * R) return;
+  {
+    const int R = a.R;
+    if (tx0 >= w.xn + 2 * R || tx0 + kITX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kITY <= w.y0 - 2 * R) return;
+  }
+  // from here on R is the effective reach: seeds further than sqrt(reach2) cells away only ever contribute cost 0,
+  // and max(old, 0) / the NO_INFORMATION rule leave the cell as it is
+  const int R = (int)sqrtf((float)a.reach2 + 0.5f);
   const int rows = kITY + 2 * R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned sp32 = seed_pitch16(a.pitch) / 2;
@@ -743,8 +906,8 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     sbits[i] = v;
     any |= v != 0;
   }
-  for (int i = tid; i <= R * R; i += kIThreads) table[i] = a.cost_d2[i];
-  if (tid == 0) table[R * R + 1] = 0;
+  for (int i = tid; i <= a.reach2; i += kIThreads) table[i] = a.cost_d2[i];
+  if (tid == 0) table[a.reach2 + 1] = 0;
   if (tid < 128) {
     const int d = tid - 64;
     sq[tid] = (uint32_t)(d * d) * 0x10001u;
@@ -777,13 +940,13 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   __syncthreads();
 
   // ---- phase 3 + epilogue: each warp owns 64 columns x 8 rows at a time
-  const uint32_t R2x2 = (uint32_t)(R * R) * 0x10001u;
+  const uint32_t R2x2 = (uint32_t)a.reach2 * 0x10001u;
   const int x = tx0 + 2 * lane;
   const bool xok = x < (int)a.sx;
   const uint32_t keep_hi = x + 1 >= (int)a.sx ? 0xff00u : 0u;
   for (int g = warp; g < kITY / 8; g += kIThreads / 32) {
     const int yr0 = g * 8;  // first tile row of this group; region rows yr0 .. yr0 + 7 + 2R
-    uint32_t acc[8], hit[8];
+    uint32_t acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0x7fff7fffu;
     const int lo = yr0, hi = yr0 + 8 + 2 * R;  // region-row range [lo, hi)
@@ -805,30 +968,35 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     // Both cells of the pair are handled in one 32-bit word: byte k of `cost2` / `cur` belongs to cell k.
     const int kmax = xok ? min(8, (int)a.sy - (ty0 + yr0)) : 0;
     uint8_t* prow = a.master + (size_t)(ty0 + yr0) * a.pitch + x;
-    uint32_t cur[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      // bit 15 of every half whose squared distance is within reach (no borrow crosses the halves)
-      hit[k] = k < kmax ? ((R2x2 | 0x80008000u) - (acc[k] & 0x7fff7fffu)) & 0x80008000u : 0u;
-      cur[k] = 0;
-      if (hit[k]) cur[k] = *reinterpret_cast<const uint16_t*>(prow + (size_t)k * a.pitch);
-    }
+    for (int half = 0; half < 2; ++half) {  // four rows at a time keeps the loads in flight within 32 registers
+      uint32_t cur[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (!hit[k]) continue;
-      const uint32_t d2 = __vminu2(acc[k], R2x2 + 0x10001u);  // out of reach -> table[R*R+1] = 0
-      const uint32_t c16 = (uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 16);
-      const uint32_t old2 = cur[k];
-      const uint32_t o16 = __byte_perm(old2, 0, 0x4140);  // the two cells' bytes, one per 16-bit lane
-      uint32_t r16 = __vmaxu2(o16, c16);
-      // NO_INFORMATION is replaced only by costs >= INSCRIBED
-      const uint32_t keep = __vminu2(__vmaxu2(c16, 0x00fc00fcu), 0x00fd00fdu) - 0x00fc00fcu;  // 1 where cost >= 253
-      const uint32_t noinfo = ((o16 + 0x00010001u) >> 8) & 0x00010001u;                       // 1 where old == 255
-      const uint32_t repl = (noinfo & keep) * 0xffffu;                                        // 0xffff per such half
-      r16 = (c16 & repl) | (r16 & ~repl);
-      uint32_t out = __byte_perm(r16, 0, 0x4420);
-      out = (out & ~keep_hi) | (old2 & keep_hi);  // padding column: left as it is
-      *reinterpret_cast<uint16_t*>(prow + (size_t)k * a.pitch) = (uint16_t)out;
+      for (int q = 0; q < 4; ++q) {
+        const int k = 4 * half + q;
+        // bit 15 of every half whose squared distance is within reach (no borrow crosses the halves)
+        const uint32_t hit = k < kmax ? ((R2x2 | 0x80008000u) - acc[k]) & 0x80008000u : 0u;
+        cur[q] = 0xffffffffu;  // "row not reached" (a uint16 load never produces it)
+        if (hit) cur[q] = *reinterpret_cast<const uint16_t*>(prow + (size_t)k * a.pitch);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = 4 * half + q;
+        if (cur[q] == 0xffffffffu) continue;
+        const uint32_t d2 = __vminu2(acc[k], R2x2 + 0x10001u);  // out of reach -> table[reach2 + 1] = 0
+        const uint32_t c16 = (uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 16);
+        const uint32_t old2 = cur[q];
+        const uint32_t o16 = __byte_perm(old2, 0, 0x4140);  // the two cells' bytes, one per 16-bit lane
+        uint32_t r16 = __vmaxu2(o16, c16);
+        // NO_INFORMATION is replaced only by costs >= INSCRIBED
+        const uint32_t keep = __vminu2(__vmaxu2(c16, 0x00fc00fcu), 0x00fd00fdu) - 0x00fc00fcu;  // 1 where cost >= 253
+        const uint32_t noinfo = ((o16 + 0x00010001u) >> 8) & 0x00010001u;                       // 1 where old == 255
+        const uint32_t repl = (noinfo & keep) * 0xffffu;                                        // 0xffff per such half
+        r16 = (c16 & repl) | (r16 & ~repl);
+        uint32_t out = __byte_perm(r16, 0, 0x4420);
+        out = (out & ~keep_hi) | (old2 & keep_hi);  // padding column: left as it is
+        if (out != old2) *reinterpret_cast<uint16_t*>(prow + (size_t)k * a.pitch) = (uint16_t)out;
+      }
     }
   }
 }
