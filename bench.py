@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 
 C3 = dict(size=4000, resolution=0.05, n_obs=8, n_beams=360, scan_range=10.0, inflation_radius=1.0, scaling=10.0)
 ALGO_BYTES_PER_CELL = 3  # read static + read obstacle + write master
+# dram__bytes_read.sum + dram__bytes_write.sum of the two sweep kernels per launch pair, from the ncu --set full
+# capture summarised in profiles/ (the master grid stays in the 126 MB L2, so DRAM sees the two input layers only)
+TRAFFIC_BYTES = None
 METRIC = "ms per updateMap+inflation @4k^2 grid; DWA trajectories scored/sec"
 WORKLOAD = ("C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, 10 m raytrace+mark) + "
             "inflation 1.0 m (R=20); DWA half: C2 findBestPath 20x1x20 and C4 sweep 200x20x200 on a 120x120 local map")
@@ -304,7 +307,6 @@ def run_native(args, rank, world, local_rank):
 
     size = C3["size"]
     cm, (s, o, il), sets = build_c3(lambda *a: api.costmap(*a, device=local_rank))
-    cm.set_profiling(True)
     stream = torch.cuda.ExternalStream(cm.stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
     n_cells = size * size
@@ -315,7 +317,8 @@ def run_native(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input loop (value): scans already on the device, L2 flushed before every cycle
+    # ---- resident-input loop (value): scans already on the device, L2 flushed before every cycle, the handle's own
+    # profiling events OFF (they cost a few microseconds per cycle)
     obs, robot = sets[0]
     cm.set_observations(o, obs)
     for _ in range(max(3, args.warmup)):
@@ -323,7 +326,6 @@ def run_native(args, rank, world, local_rank):
         cm.update_map(*robot)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sweep_ms = []
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -335,11 +337,24 @@ def run_native(args, rank, world, local_rank):
         cm.touch_grid_layer(s, 0, 0, size, size)  # has_updated_data_: forces the full window
         cm.update_map_async(*robot)
         stops[k].record(stream)
-        sweep_ms.append(cm.last_timing()[1])
     barrier()
     launches = api.launch_count() - launches0
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
     ms_per_step = float(np.mean(step_ms))
+
+    # ---- the same cycles again with the handle's events ON: durations of the sweep kernels for the roofline
+    cm.set_profiling(True)
+    sweep_ms, merge_ms, inflate_ms = [], [], []
+    for k in range(max(5, args.steps)):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        cm.update_map_async(*robot)
+        sweep_ms.append(cm.last_timing()[1])
+        m, i = cm.last_timing_split()
+        merge_ms.append(m)
+        inflate_ms.append(i)
+    cm.set_profiling(False)
 
     # ---- hot-L2 loop (informational): back-to-back cycles without the flush
     barrier()
@@ -383,14 +398,15 @@ def run_native(args, rank, world, local_rank):
     launches = api.launch_count() - launches0 if not args.no_dwa else launches
 
     if dist is not None:
-        t = torch.tensor([ms_per_step, e2e_ms, hot_ms, float(np.mean(sweep_ms))], device=f"cuda:{local_rank}")
+        t = torch.tensor([ms_per_step, e2e_ms, hot_ms, float(np.mean(sweep_ms)), float(np.mean(merge_ms)),
+                          float(np.mean(inflate_ms))], device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step, e2e_ms, hot_ms, sweep = [float(v) for v in t.tolist()]
+        ms_per_step, e2e_ms, hot_ms, sweep, merge, inflate = [float(v) for v in t.tolist()]
         lt = torch.tensor([launches], device=f"cuda:{local_rank}")
         dist.all_reduce(lt)
         launches = int(lt.item())
     else:
-        sweep = float(np.mean(sweep_ms))
+        sweep, merge, inflate = float(np.mean(sweep_ms)), float(np.mean(merge_ms)), float(np.mean(inflate_ms))
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -408,7 +424,8 @@ def run_native(args, rank, world, local_rank):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_update_costs", "kernel_ms": sweep,
+                         "traffic": TRAFFIC_BYTES, "kernel": "k_merge_seed + k_inflate (the reset+merge+inflation sweep)",
+                         "kernel_ms": sweep, "k_merge_seed_ms": merge, "k_inflate_ms": inflate,
                          "algorithmic_bytes": ALGO_BYTES_PER_CELL * n_cells, "peak_source": peak_src},
         }
         if dwa is not None:

@@ -137,10 +137,8 @@ struct navgpu_dwa {
   unsigned int* d_counters = nullptr;
   double* d_best_cost = nullptr;
   long long* d_best_index = nullptr;
-  DwaDeviceResult* d_result = nullptr;
-  double* d_points = nullptr;
-  DwaDeviceResult* h_result = nullptr;  // pinned
-  double* h_points = nullptr;           // pinned
+  DwaDeviceResult* h_result = nullptr;  // pinned + mapped: written by the finishing step on the device
+  double* h_points = nullptr;           // pinned + mapped
   double* h_best = nullptr;             // pinned: cost, index (as long long bits)
   double* d_terms = nullptr;
   double* d_reported = nullptr;
@@ -227,6 +225,38 @@ Samples enumerate_samples(const navgpu_dwa_config& cfg, const float pos[3], cons
   return s;
 }
 
+// MapGridCostFunction::prepare for `n_ctas` grids (jobs_per_robot per robot): the register-resident bit-sliced kernel
+// when the map's bit words fit 4 per thread, else the general shared-memory kernel
+int launch_mapgrid(navgpu_dwa* h, const MapGridArgs& ma, int n_ctas, int jobs_per_robot) {
+  const int W = (h->sx + 31) / 32, NW = W * (int)h->sy;
+  int planes = 1;
+  while ((1ull << planes) <= (unsigned long long)h->sx * h->sy + 1) ++planes;  // levels go up to n_cells
+  const size_t sliced_smem = (size_t(3 + planes) * NW + 2) * sizeof(uint32_t);
+  const int wpt = (NW + kMapGridThreads - 1) / kMapGridThreads;
+  if (wpt <= 4 && planes <= kMapGridMaxPlanes && sliced_smem <= 200 * 1024) {
+    auto launch = [&](auto kernel) -> int {
+      if (sliced_smem > 48 * 1024)
+        NAVGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sliced_smem));
+      kernel<<<n_ctas, kMapGridThreads, sliced_smem, h->stream>>>(ma, jobs_per_robot, planes);
+      return NAVGPU_OK;
+    };
+    switch (wpt) {
+      case 1: NAVGPU_TRY(launch(k_mapgrid_prepare_sliced<1>)); break;
+      case 2: NAVGPU_TRY(launch(k_mapgrid_prepare_sliced<2>)); break;
+      case 3: NAVGPU_TRY(launch(k_mapgrid_prepare_sliced<3>)); break;
+      default: NAVGPU_TRY(launch(k_mapgrid_prepare_sliced<4>)); break;
+    }
+  } else {
+    const size_t mg_smem = size_t(4) * NW * sizeof(uint32_t);
+    if (mg_smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap %ux%u too large for the MapGrid kernel", h->sx, h->sy);
+    if (mg_smem > 48 * 1024)
+      NAVGPU_CUDA(cudaFuncSetAttribute(k_mapgrid_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg_smem));
+    k_mapgrid_prepare<<<n_ctas, kMapGridThreads, mg_smem, h->stream>>>(ma, jobs_per_robot);
+  }
+  NAVGPU_LAUNCHED(1);
+  return NAVGPU_OK;
+}
+
 // uploads the per-cycle inputs and launches the 4 MapGrid wavefronts; fills the scoring arguments
 int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const double* footprint_xy, int n_footprint,
                 Cycle& cy) {
@@ -239,14 +269,17 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   const float vel[3] = {(float)velv[0], (float)velv[1], (float)velv[2]};
   const float goal[2] = {(float)h->plan.back().x, (float)h->plan.back().y};
   Samples s = enumerate_samples(c, pos, vel, goal);
-  if (s.v.size() > h->samples_capacity) {
-    if (h->d_samples) cudaFree(h->d_samples);
-    h->d_samples = nullptr;
-    NAVGPU_CUDA(cudaMalloc(&h->d_samples, s.v.size() * 2 * sizeof(float)));
-    h->samples_capacity = s.v.size() * 2;
+  const bool inline_samples = s.v.size() <= (size_t)kInlineSamples;  // they then travel in the kernel parameters
+  if (!inline_samples) {
+    if (s.v.size() > h->samples_capacity) {
+      if (h->d_samples) cudaFree(h->d_samples);
+      h->d_samples = nullptr;
+      NAVGPU_CUDA(cudaMalloc(&h->d_samples, s.v.size() * 2 * sizeof(float)));
+      h->samples_capacity = s.v.size() * 2;
+    }
+    NAVGPU_CUDA(cudaMemcpyAsync(h->d_samples, s.v.data(), s.v.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // pageable source
   }
-  NAVGPU_CUDA(cudaMemcpyAsync(h->d_samples, s.v.data(), s.v.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // pageable source
   for (int k = 0; k < 3; ++k) NAVGPU_TRY(upload_plan(h, k));
 
   DwaGeom g{h->d_cost, h->sx, h->sy, h->pitch, h->res, h->ox, h->oy, 1.0 / h->res};
@@ -258,13 +291,7 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   ma.job[1] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 1, h->d_dist[1]};  // goal: setLocalGoal
   ma.job[2] = MapGridJob{h->d_plan[1], (int)h->adjusted[1].size(), 1, h->d_dist[2]};  // goal_front
   ma.job[3] = MapGridJob{h->d_plan[2], (int)h->adjusted[2].size(), 0, h->d_dist[3]};  // alignment
-  const int W = (h->sx + 31) / 32;
-  const size_t mg_smem = size_t(4) * W * h->sy * sizeof(uint32_t);
-  if (mg_smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap %ux%u too large for the MapGrid kernel", h->sx, h->sy);
-  if (mg_smem > 48 * 1024)
-    NAVGPU_CUDA(cudaFuncSetAttribute(k_mapgrid_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg_smem));
-  k_mapgrid_prepare<<<4, kMapGridThreads, mg_smem, h->stream>>>(ma, 4);
-  NAVGPU_LAUNCHED(1);
+  NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
 
   DwaScoreArgs& a = cy.args;
   a.g = g;
@@ -273,6 +300,8 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   a.vys = h->d_samples + s.nx;
   a.vths = h->d_samples + s.nx + s.ny;
   a.nx = s.nx; a.ny = s.ny; a.nth = s.nth;
+  a.inline_samples = inline_samples ? 1 : 0;
+  if (inline_samples) memcpy(a.samples_inline, s.v.data(), s.v.size() * sizeof(float));
   cy.n_samples = (long long)s.nx * s.ny * s.nth;
   a.begin = 0;
   a.end = cy.n_samples;
@@ -294,11 +323,14 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   a.counters = h->d_counters;
   a.best_cost = h->d_best_cost;
   a.best_index = h->d_best_index;
+  a.finish_out = nullptr;
+  a.finish_points = nullptr;
+  a.finish_capacity = 0;
   h->n_samples_last = cy.n_samples;
   return NAVGPU_OK;
 }
 
-int launch_score(navgpu_dwa* h, Cycle& cy) {
+int launch_score(navgpu_dwa* h, Cycle& cy, bool finish) {
   DwaScoreArgs& a = cy.args;
   const long long n = a.end - a.begin;
   if (n <= 0) return fail(NAVGPU_ERR_INVALID, "empty sample range");
@@ -315,7 +347,13 @@ int launch_score(navgpu_dwa* h, Cycle& cy) {
   }
   a.block_cost = h->d_block_cost;
   a.block_index = h->d_block_index;
-  NAVGPU_CUDA(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned int), h->stream));
+  if (finish) {  // the last CTA regenerates the winner into mapped host memory and re-arms both counters
+    a.finish_out = h->h_result;
+    a.finish_points = h->h_points;
+    a.finish_capacity = kPointsCapacity;
+  } else {
+    NAVGPU_CUDA(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned int), h->stream));
+  }
   k_dwa_score<<<(unsigned)blocks, kDwaWarpsPerBlock * 32, 0, h->stream>>>(a);
   NAVGPU_LAUNCHED(1);
   return NAVGPU_OK;
@@ -343,7 +381,8 @@ int navgpu_dwa_create(navgpu_dwa** out, const navgpu_dwa_config* cfg, uint32_t s
                       double resolution, int device) {
   if (!out || !cfg || size_x == 0 || size_y == 0 || !(resolution > 0)) return fail(NAVGPU_ERR_INVALID, "bad arguments");
   if (navgpu_device_count() <= device) return fail(NAVGPU_ERR_CUDA, "no CUDA device %d (libnavgpu has no CPU fallback)", device);
-  if ((unsigned long long)size_x * size_y + 1 >= 0xffffffffull) return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap too large");
+  if ((unsigned long long)size_x * size_y + 1 >= 0xffffffffull || size_x > 32767 || size_y > 32767)
+    return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap too large");
   std::unique_ptr<navgpu_dwa> h(new navgpu_dwa);
   h->device = device;
   h->cfg = *cfg;
@@ -355,10 +394,10 @@ int navgpu_dwa_create(navgpu_dwa** out, const navgpu_dwa_config* cfg, uint32_t s
   NAVGPU_CUDA(cudaMemset(h->d_counters, 0, 2 * sizeof(unsigned int)));
   NAVGPU_CUDA(cudaMalloc(&h->d_best_cost, sizeof(double)));
   NAVGPU_CUDA(cudaMalloc(&h->d_best_index, sizeof(long long)));
-  NAVGPU_CUDA(cudaMalloc(&h->d_result, sizeof(DwaDeviceResult)));
-  NAVGPU_CUDA(cudaMalloc(&h->d_points, size_t(kPointsCapacity) * 3 * sizeof(double)));
-  NAVGPU_CUDA(cudaMallocHost(&h->h_result, sizeof(DwaDeviceResult)));
-  NAVGPU_CUDA(cudaMallocHost(&h->h_points, size_t(kPointsCapacity) * 3 * sizeof(double)));
+  // result record and winner points are written by the kernels straight into mapped pinned host memory (unified
+  // addressing: the same pointer is valid on the device)
+  NAVGPU_CUDA(cudaHostAlloc(&h->h_result, sizeof(DwaDeviceResult), cudaHostAllocMapped));
+  NAVGPU_CUDA(cudaHostAlloc(&h->h_points, size_t(kPointsCapacity) * 3 * sizeof(double), cudaHostAllocMapped));
   NAVGPU_CUDA(cudaMallocHost(&h->h_best, 2 * sizeof(double)));
   apply_config(h.get());
   *out = h.release();
@@ -373,7 +412,7 @@ int navgpu_dwa_destroy(navgpu_dwa* h) {
   for (int k = 0; k < 3; ++k) cudaFree(h->d_plan[k]);
   for (int k = 0; k < 4; ++k) cudaFree(h->d_dist[k]);
   cudaFree(h->d_samples); cudaFree(h->d_block_cost); cudaFree(h->d_block_index); cudaFree(h->d_counters);
-  cudaFree(h->d_best_cost); cudaFree(h->d_best_index); cudaFree(h->d_result); cudaFree(h->d_points);
+  cudaFree(h->d_best_cost); cudaFree(h->d_best_index);
   cudaFree(h->d_terms); cudaFree(h->d_reported);
   cudaFreeHost(h->h_result); cudaFreeHost(h->h_points); cudaFreeHost(h->h_best);
   cudaStreamDestroy(h->stream);
@@ -448,13 +487,11 @@ int navgpu_dwa_get_oscillation_mask(navgpu_dwa* h, int* mask_out) {
   return NAVGPU_OK;
 }
 
-static int finish_and_collect(navgpu_dwa* h, Cycle& cy, long long forced_index, const double pose[3],
-                              navgpu_dwa_result* result, double* best_points, int points_capacity) {
-  k_dwa_finish<<<1, 32, 0, h->stream>>>(cy.args, forced_index, h->d_result, h->d_points, kPointsCapacity);
-  NAVGPU_LAUNCHED(1);
+// waits for the finishing step, then applies what findBestPath does with the winner on the host: result_traj_
+// bookkeeping and the oscillation flags (dwa_planner.cpp:316-357)
+static int collect(navgpu_dwa* h, Cycle& cy, const double pose[3], navgpu_dwa_result* result, double* best_points,
+                   int points_capacity) {
   NAVGPU_CUDA(cudaGetLastError());
-  NAVGPU_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(DwaDeviceResult), cudaMemcpyDeviceToHost, h->stream));
-  NAVGPU_CUDA(cudaMemcpyAsync(h->h_points, h->d_points, size_t(kPointsCapacity) * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   const DwaDeviceResult& r = *h->h_result;
   if (r.cost >= 0) {
@@ -498,12 +535,12 @@ int navgpu_dwa_find_best_path(navgpu_dwa* h, const double pose[3], const double 
     }
     cy.args.all_terms = h->d_terms;
   }
-  NAVGPU_TRY(launch_score(h, cy));
+  NAVGPU_TRY(launch_score(h, cy, true));
   if (all_costs) {
     k_dwa_report<<<1, 1024, 0, h->stream>>>(h->d_terms, h->d_reported, cy.n_samples);
     NAVGPU_LAUNCHED(1);
   }
-  NAVGPU_TRY(finish_and_collect(h, cy, -1, pose, result, best_points, points_capacity));
+  NAVGPU_TRY(collect(h, cy, pose, result, best_points, points_capacity));
   if (all_costs) {
     const size_t n = std::min<size_t>((size_t)cy.n_samples, (size_t)std::max(0, all_capacity));
     NAVGPU_CUDA(cudaMemcpy(all_costs, h->d_reported, n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -516,9 +553,7 @@ int navgpu_dwa_find_best_path_async(navgpu_dwa* h, const double pose[3], const d
   if (!h || !pose || !vel) return fail(NAVGPU_ERR_INVALID, "bad arguments");
   Cycle cy;
   NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy));
-  NAVGPU_TRY(launch_score(h, cy));
-  k_dwa_finish<<<1, 32, 0, h->stream>>>(cy.args, -1, h->d_result, h->d_points, kPointsCapacity);
-  NAVGPU_LAUNCHED(1);
+  NAVGPU_TRY(launch_score(h, cy, true));
   NAVGPU_CUDA(cudaGetLastError());
   return NAVGPU_OK;
 }
@@ -542,7 +577,7 @@ int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel
   }
   cy.args.begin = begin;
   cy.args.end = end;
-  NAVGPU_TRY(launch_score(h, cy));
+  NAVGPU_TRY(launch_score(h, cy, false));
   NAVGPU_CUDA(cudaGetLastError());
   h->last = cy;
   h->have_last = true;
@@ -582,7 +617,9 @@ int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double*
     }
     return NAVGPU_OK;
   }
-  return finish_and_collect(h, cy, bi, pose, result, best_points, points_capacity);
+  k_dwa_finish<<<1, 32, 0, h->stream>>>(cy.args, bi, bc, h->h_result, h->h_points, kPointsCapacity);
+  NAVGPU_LAUNCHED(1);
+  return collect(h, cy, pose, result, best_points, points_capacity);
 }
 
 int navgpu_dwa_get_grid(navgpu_dwa* h, int which, double* host_out) {

@@ -9,6 +9,7 @@
 namespace navgpu {
 
 constexpr int kMaxFootprint = 16;
+constexpr int kInlineSamples = 640;  // per-axis velocity samples carried in the kernel parameters
 constexpr int kDwaWarpsPerBlock = 8;
 
 struct DwaGeom {
@@ -61,7 +62,209 @@ struct MapGridArgs {
 };
 
 constexpr int kMapGridThreads = 512;
+constexpr int kMapGridMaxPlanes = 18;
 
+// seeds: plan points from the first one that is on the map and not NO_INFORMATION until the plan first leaves the
+// map again (map_grid.cpp:189-202 / :225-239); sets the seed bits in F0 (shared memory, zeroed by the caller).
+// Returns false when no plan point is on the map (every cell stays unreachable).
+__device__ __forceinline__ bool mapgrid_seed(const MapGridJob& job, const DwaGeom& g, uint32_t* F0, int W) {
+  __shared__ int s_first, s_end;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_first = 0x7fffffff;
+    s_end = job.n_points;
+  }
+  __syncthreads();
+  // cell of plan point i (my << 16 | mx), or -1 when it is off the map or on NO_INFORMATION.  worldToMap costs two
+  // fp64 divisions whenever a point sits on a cell border (plans are often laid out on the grid), so every thread
+  // evaluates its points once and keeps the first kCached of them in registers for the later passes.
+  constexpr int kCached = 8;
+  auto point_cell = [&](int i) -> int {
+    int mx, my;
+    const double wx = job.plan_xy[2 * i], wy = job.plan_xy[2 * i + 1];
+    if (!dwa_world_to_map(g, wx, wy, mx, my)) return -1;
+    if (g.cost[(size_t)my * g.pitch + mx] == kNoInfo) return -1;
+    return (my << 16) | mx;
+  };
+  int cached[kCached];
+#pragma unroll
+  for (int q = 0; q < kCached; ++q) {
+    const int i = tid + q * kMapGridThreads;
+    cached[q] = i < job.n_points ? point_cell(i) : -1;
+    if (cached[q] >= 0) atomicMin(&s_first, i);
+  }
+  for (int i = tid + kCached * kMapGridThreads; i < job.n_points; i += kMapGridThreads)
+    if (point_cell(i) >= 0) atomicMin(&s_first, i);
+  __syncthreads();
+  const int first = s_first;
+  if (first == 0x7fffffff) return false;
+#pragma unroll
+  for (int q = 0; q < kCached; ++q) {
+    const int i = tid + q * kMapGridThreads;
+    if (i > first && i < job.n_points && cached[q] < 0) atomicMin(&s_end, i);
+  }
+  for (int i = tid + kCached * kMapGridThreads; i < job.n_points; i += kMapGridThreads)
+    if (i > first && point_cell(i) < 0) atomicMin(&s_end, i);
+  __syncthreads();
+  const int end = s_end, lo = job.local_goal ? end - 1 : first;
+#pragma unroll
+  for (int q = 0; q < kCached; ++q) {
+    const int i = tid + q * kMapGridThreads;
+    if (i >= lo && i < end) atomicOr(&F0[(cached[q] >> 16) * W + ((cached[q] & 0xffff) >> 5)], 1u << (cached[q] & 31));
+  }
+  for (int i = tid + kCached * kMapGridThreads; i < end; i += kMapGridThreads) {
+    if (i < lo) continue;
+    const int c = point_cell(i);
+    atomicOr(&F0[(c >> 16) * W + ((c & 0xffff) >> 5)], 1u << (c & 31));
+  }
+  __syncthreads();
+  return true;
+}
+
+// passable bits of one 32-cell word of the costmap (map_grid.cpp:109-116)
+__device__ __forceinline__ uint32_t mapgrid_passable(const DwaGeom& g, int allow_unknown, int r, int w) {
+  uint32_t p = 0;
+  const uint8_t* row = g.cost + (size_t)r * g.pitch + w * 32;
+  const int nbits = min(32, (int)g.sx - w * 32);
+  if (nbits == 32 && ((size_t)row & 3) == 0) {
+    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t v = row4[q];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t c = (v >> (8 * b)) & 0xffu;
+        const bool obstacle = c == kLethal || c == kInscribed || (c == kNoInfo && !allow_unknown);
+        p |= (uint32_t)(!obstacle) << (4 * q + b);
+      }
+    }
+    return p;
+  }
+  for (int b = 0; b < nbits; ++b) {
+    const uint8_t c = row[b];
+    const bool obstacle = c == kLethal || c == kInscribed || (c == kNoInfo && !allow_unknown);
+    p |= (uint32_t)(!obstacle) << b;
+  }
+  return p;
+}
+
+// Fast variant: every thread keeps its kWPT words' visited / passable / seed bits and the bit-sliced level counters
+// (plane k holds bit k of the level at which each cell was first touched) in REGISTERS; only the frontier goes
+// through shared memory, so one level costs five shared loads, a handful of logic ops and one barrier.  After the
+// wavefront dies out the planes are parked in shared memory and un-sliced by whole warps (one word per warp step,
+// lane = cell) into coalesced uint32 stores.
+template <int kWPT>
+__global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapGridArgs a, int jobs_per_robot, int planes) {
+  extern __shared__ uint32_t mg_smem[];
+  const MapGridJob job = a.job[blockIdx.x % jobs_per_robot];
+  const DwaGeom g = a.g;
+  const int W = (g.sx + 31) / 32, NW = W * (int)g.sy;
+  uint32_t* F0 = mg_smem;  // NW words + one that stays zero
+  uint32_t* F1 = F0 + NW + 1;
+  const int tid = threadIdx.x;
+  const uint32_t n_cells = g.sx * g.sy;
+  if (tid == 0) F0[NW] = F1[NW] = 0;
+
+  uint32_t P[kWPT], V[kWPT], S[kWPT], D[kMapGridMaxPlanes][kWPT];
+#pragma unroll
+  for (int q = 0; q < kWPT; ++q) {
+    const int wi = tid + q * kMapGridThreads;
+    P[q] = 0;
+    if (wi < NW) {
+      P[q] = mapgrid_passable(g, a.allow_unknown, wi / W, wi % W);
+      F0[wi] = 0;
+      F1[wi] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kMapGridMaxPlanes; ++k) D[k][q] = 0;
+  }
+  __syncthreads();
+  const bool seeded = mapgrid_seed(job, g, F0, W);
+#pragma unroll
+  for (int q = 0; q < kWPT; ++q) {
+    const int wi = tid + q * kMapGridThreads;
+    S[q] = (seeded && wi < NW) ? F0[wi] : 0u;
+    V[q] = S[q];
+  }
+
+  // neighbour word indices and the valid-column mask of every owned word, hoisted out of the level loop; a missing
+  // neighbour (map border) reads the always-zero word at index NW
+  int iL[kWPT], iR[kWPT], iU[kWPT], iD[kWPT];
+  uint32_t colmask[kWPT];
+#pragma unroll
+  for (int q = 0; q < kWPT; ++q) {
+    const int wi = tid + q * kMapGridThreads;
+    const int r = wi / W, w = wi - r * W;
+    iL[q] = (wi < NW && w > 0) ? wi - 1 : NW;
+    iR[q] = (wi < NW && w + 1 < W) ? wi + 1 : NW;
+    iU[q] = (wi < NW && r > 0) ? wi - W : NW;
+    iD[q] = (wi < NW && r + 1 < (int)g.sy) ? wi + W : NW;
+    const int nbits = (int)g.sx - w * 32;
+    colmask[q] = wi < NW ? (nbits < 32 ? (1u << nbits) - 1u : 0xffffffffu) : 0u;
+  }
+  uint32_t* F = F0;
+  uint32_t* Fn = F1;
+  uint32_t last_level = 0;
+  if (seeded) {
+    for (uint32_t level = 0;; ++level) {
+      int any = 0;
+      last_level = level + 1;
+#pragma unroll
+      for (int q = 0; q < kWPT; ++q) {
+        const int wi = tid + q * kMapGridThreads;
+        if (kWPT > 1 && wi >= NW) continue;
+        const uint32_t f = F[min(wi, NW)];
+        const uint32_t nb = ((f << 1) | (f >> 1) | (F[iL[q]] >> 31) | (F[iR[q]] << 31) | F[iU[q]] | F[iD[q]]) & colmask[q];
+        const uint32_t touched = nb & ~V[q];
+        uint32_t next = 0;
+        if (touched) {  // rare: a word is touched during only a few levels
+          V[q] |= touched;
+          next = touched & P[q];  // obstacles are touched but not expanded (updatePathCell)
+          const uint32_t lv = level + 1;
+#pragma unroll
+          for (int k = 0; k < kMapGridMaxPlanes; ++k)
+            if ((lv >> k) & 1u) D[k][q] |= next;
+        }
+        if (wi < NW) Fn[wi] = next;
+        any |= next != 0;
+      }
+      if (!__syncthreads_or(any)) break;
+      uint32_t* tmp = F;
+      F = Fn;
+      Fn = tmp;
+    }
+  }
+  __syncthreads();
+  planes = min(planes, 32 - __clz(last_level));  // only the planes the deepest level reached can hold a set bit
+  // park V, P, S and the planes: layout [3 + planes][NW]
+  uint32_t* park = mg_smem;
+#pragma unroll
+  for (int q = 0; q < kWPT; ++q) {
+    const int wi = tid + q * kMapGridThreads;
+    if (wi >= NW) continue;
+    park[wi] = V[q];
+    park[NW + wi] = P[q];
+    park[2 * NW + wi] = S[q];
+#pragma unroll
+    for (int k = 0; k < kMapGridMaxPlanes; ++k)
+      if (k < planes) park[(3 + k) * NW + wi] = D[k][q];
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int wi = warp; wi < NW; wi += kMapGridThreads / 32) {
+    const int r = wi / W, w = wi - r * W;
+    const int c = w * 32 + lane;
+    if (c >= (int)g.sx) continue;
+    const uint32_t v = (park[wi] >> lane) & 1u, p = (park[NW + wi] >> lane) & 1u, sd = (park[2 * NW + wi] >> lane) & 1u;
+    uint32_t d = 0;
+    for (int k = 0; k < planes; ++k) d |= ((park[(3 + k) * NW + wi] >> lane) & 1u) << k;
+    // seeds 0 (even on an obstacle), untouched cells unreachableCellCosts, touched obstacles obstacleCosts
+    job.dist[(size_t)r * g.sx + c] = sd ? 0u : (!v ? n_cells + 1 : (!p ? n_cells : d));
+  }
+}
+
+// General variant for local costmaps too large for the register-resident kernel: all bit planes in shared memory,
+// distances written as cells are touched.
 __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare(MapGridArgs a, int jobs_per_robot) {
   extern __shared__ uint32_t mg_smem[];
   const MapGridJob job = a.job[blockIdx.x % jobs_per_robot];
@@ -178,13 +381,22 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare(MapGridArgs
 // (every step rounds to float), but its trig terms depend only on the heading sequence, which is a cheap scalar
 // recurrence: all lanes replay theta, each lane evaluates cos/sin for its own step in fp64, and the x/y prefix is
 // accumulated with shuffles in the reference's order and rounding.  No FMA contraction (-fmad=false).
+// Result record of one search, written by the finishing step
+struct DwaDeviceResult {
+  double cost, xv, yv, thetav;
+  long long best_index;
+  int n_points, n_scored;
+};
+
 struct DwaScoreArgs {
   DwaGeom g;
   const uint32_t* dist[4];  // 0 path, 1 goal, 2 goal_front, 3 alignment
-  const float* vxs;
+  const float* vxs;  // per-axis samples in device memory (only when they do not fit samples_inline)
   const float* vys;
   const float* vths;
   int nx, ny, nth;
+  int inline_samples;  // 1: the samples travel in samples_inline (xs | ys | ths), no upload
+  float samples_inline[kInlineSamples];
   long long begin, end;  // sample index range scored by this launch
   float pos[3], vel[3], acc[3];
   double min_trans_vel, max_trans_vel, min_rot_vel;
@@ -200,6 +412,11 @@ struct DwaScoreArgs {
   unsigned int* counters;  // [0] CTAs done, [1] samples the generator accepted
   double* best_cost;       // final (cost, index) of the range; +inf / -1 when none valid
   long long* best_index;
+  // when finish_out is set the last CTA also regenerates the winner (findBestTrajectory :123-134) and writes the
+  // result record and its points straight into (mapped, pinned) host memory
+  DwaDeviceResult* finish_out;
+  double* finish_points;
+  int finish_capacity;
 };
 
 struct TrajResult {
@@ -249,8 +466,16 @@ __device__ int footprint_edge_cost(const DwaScoreArgs& a, double x, double y, do
   return bad ? -1 : best;
 }
 
-// scores one velocity sample with a whole warp; points_out (nullable) receives 3 doubles per trajectory point
+__device__ __forceinline__ float sample_vx(const DwaScoreArgs& a, int i) { return a.inline_samples ? a.samples_inline[i] : a.vxs[i]; }
+__device__ __forceinline__ float sample_vy(const DwaScoreArgs& a, int i) { return a.inline_samples ? a.samples_inline[a.nx + i] : a.vys[i]; }
+__device__ __forceinline__ float sample_vth(const DwaScoreArgs& a, int i) {
+  return a.inline_samples ? a.samples_inline[a.nx + a.ny + i] : a.vths[i];
+}
+
+// scores one velocity sample with a whole warp; points_out (nullable) receives 3 doubles per trajectory point.
+// kScore = false only generates the trajectory (points, step count): the critics are skipped and cost stays NaN.
 constexpr int kWarpScratchDoubles = 128 + 16;  // 4 x 32 pose doubles + 32 ints
+template <bool kScore>
 __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int lane, double* terms_out,
                                    double* points_out, int points_capacity, double* warp_scratch) {
   TrajResult res;
@@ -260,7 +485,7 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
   const int ith = (int)(sample % a.nth);
   const long long t1 = sample / a.nth;
   const int iy = (int)(t1 % a.ny), ix = (int)(t1 / a.ny);
-  const float svx = a.vxs[ix], svy = a.vys[iy], svth = a.vths[ith];
+  const float svx = sample_vx(a, ix), svy = sample_vy(a, iy), svth = sample_vth(a, ith);
 
   // generateTrajectory :186-216
   const double vmag = hypot((double)svx, (double)svy);
@@ -348,6 +573,7 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
       points_out[3 * (base + lane) + 1] = py;
       points_out[3 * (base + lane) + 2] = thd;
     }
+    if (!kScore) continue;
     // ---- obstacle critic: (point, edge) work items spread over all 32 lanes, so a short tail round costs one edge
     // per lane instead of a whole footprint per active lane
     double* pose_s = warp_scratch;              // x, y, cos, sin of the round's points
@@ -420,6 +646,7 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
     }
   }
 
+  if (!kScore) return res;
   // SimpleScoredSamplingPlanner::scoreTrajectory with critics in DWAPlanner's order (dwa_planner.cpp:167-173)
   const double raw[6] = {osc_bad ? -5.0 : 0.0,
                          a.nfp == 0 ? -9.0 : (obst_fail ? -6.0 : (a.sum_scores ? obst_sum : obst_last)),
@@ -455,6 +682,48 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
   return res;
 }
 
+// Regenerates the winning trajectory (its points are what findBestTrajectory copies out, :123-134) with one warp;
+// `cost` is the total the scoring pass found for it.  idx < 0: nothing valid (result_traj_.cost_ = -7,
+// dwa_planner.cpp:316).
+__device__ void finish_winner(const DwaScoreArgs& a, long long idx, double cost, DwaDeviceResult* out, double* points,
+                              int points_capacity, double* warp_scratch) {
+  const int lane = threadIdx.x & 31;
+  TrajResult r;
+  r.generated = false;
+  r.num_steps = 0;
+  if (idx >= 0) r = score_sample<false>(a, idx, lane, nullptr, points, points_capacity, warp_scratch);
+  if (lane == 0) {
+    out->n_scored = (int)a.counters[1];
+    a.counters[1] = 0;
+    if (idx >= 0 && r.generated && cost >= 0) {
+      const int ith = (int)(idx % a.nth);
+      const long long t1 = idx / a.nth;
+      const int iy = (int)(t1 % a.ny), ix = (int)(t1 / a.ny);
+      float vx = sample_vx(a, ix), vy = sample_vy(a, iy), vth = sample_vth(a, ith);
+      if (!a.use_dwa) {  // traj.xv_ is the first accelerated velocity (:221-227)
+        const double dt = a.sim_time / r.num_steps;
+        auto nv = [&](float v, float target, float acc) -> float {
+          if (v < target) return (float)fmin((double)target, v + acc * dt);
+          return (float)fmax((double)target, v - acc * dt);
+        };
+        vx = nv(a.vel[0], vx, a.acc[0]);
+        vy = nv(a.vel[1], vy, a.acc[1]);
+        vth = nv(a.vel[2], vth, a.acc[2]);
+      }
+      out->cost = cost;
+      out->xv = vx;
+      out->yv = vy;
+      out->thetav = vth;
+      out->best_index = idx;
+      out->n_points = min(r.num_steps, points_capacity);
+    } else {
+      out->cost = -7.0;  // dwa_planner.cpp:316
+      out->best_index = -1;
+      out->n_points = -1;  // host keeps its stale velocities / points, like result_traj_ does
+    }
+  }
+}
+
 // lexicographic (cost, index) minimum: the reference keeps the FIRST sample with the strictly smallest cost
 __device__ __forceinline__ bool better(double c1, long long i1, double c2, long long i2) {
   return c1 < c2 || (c1 == c2 && i1 < i2);
@@ -473,7 +742,7 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreAr
   int generated = 0;
   if (sample < a.end) {
     double* terms = a.all_terms ? a.all_terms + 6 * (sample - a.begin) : nullptr;
-    const TrajResult r = score_sample(a, sample, lane, terms, nullptr, 0, s_scratch[warp]);
+    const TrajResult r = score_sample<true>(a, sample, lane, terms, nullptr, 0, s_scratch[warp]);
     generated = r.generated;
     if (terms && !r.generated && lane == 0)
       for (int k = 0; k < 6; ++k) terms[k] = nan_quiet();
@@ -543,59 +812,20 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreAr
       }
     *a.best_cost = bc;
     *a.best_index = bi;
-    a.counters[0] = 0;  // re-armed for the next launch (counters[1] is read and cleared by k_dwa_finish)
+    a.counters[0] = 0;  // re-armed for the next launch (counters[1] is read and cleared by the finishing step)
+    s_cost[0] = bc;
+    s_index[0] = bi;
   }
+  if (a.finish_out == nullptr) return;
+  __syncthreads();
+  if (warp == 0) finish_winner(a, s_index[0], s_cost[0], a.finish_out, a.finish_points, a.finish_capacity, s_scratch[0]);
 }
 
-// Result record copied back to the host after k_dwa_finish
-struct DwaDeviceResult {
-  double cost, xv, yv, thetav;
-  long long best_index;
-  int n_points, n_scored;
-};
-
-// Regenerates the winning trajectory (its points are what findBestTrajectory copies out, :123-134).
-// When forced_index >= 0 that sample is used instead of *best_index (sharded sweeps).
-__global__ void k_dwa_finish(DwaScoreArgs a, long long forced_index, DwaDeviceResult* out, double* points,
-                             int points_capacity) {
+// stand-alone finish for sharded sweeps: the winner was chosen from the all-gathered per-rank minima
+__global__ void k_dwa_finish(DwaScoreArgs a, long long forced_index, double forced_cost, DwaDeviceResult* out,
+                             double* points, int points_capacity) {
   __shared__ double s_scratch[kWarpScratchDoubles];
-  const int lane = threadIdx.x & 31;
-  const long long idx = forced_index >= 0 ? forced_index : *a.best_index;
-  TrajResult r;
-  r.cost = -7.0;
-  r.generated = false;
-  r.num_steps = 0;
-  if (idx >= 0) r = score_sample(a, idx, lane, nullptr, points, points_capacity, s_scratch);
-  if (lane == 0) {
-    out->best_index = idx;
-    out->n_scored = (int)a.counters[1];
-    a.counters[1] = 0;
-    if (idx >= 0 && r.generated && r.cost >= 0) {
-      const int ith = (int)(idx % a.nth);
-      const long long t1 = idx / a.nth;
-      const int iy = (int)(t1 % a.ny), ix = (int)(t1 / a.ny);
-      float vx = a.vxs[ix], vy = a.vys[iy], vth = a.vths[ith];
-      if (!a.use_dwa) {  // traj.xv_ is the first accelerated velocity (:221-227)
-        const double dt = a.sim_time / r.num_steps;
-        auto nv = [&](float v, float target, float acc) -> float {
-          if (v < target) return (float)fmin((double)target, v + acc * dt);
-          return (float)fmax((double)target, v - acc * dt);
-        };
-        vx = nv(a.vel[0], vx, a.acc[0]);
-        vy = nv(a.vel[1], vy, a.acc[1]);
-        vth = nv(a.vel[2], vth, a.acc[2]);
-      }
-      out->cost = r.cost;
-      out->xv = vx;
-      out->yv = vy;
-      out->thetav = vth;
-      out->n_points = min(r.num_steps, points_capacity);
-    } else {
-      out->cost = -7.0;  // dwa_planner.cpp:316
-      out->best_index = -1;
-      out->n_points = -1;  // host keeps its stale velocities / points, like result_traj_ does
-    }
-  }
+  finish_winner(a, forced_index, forced_cost, out, points, points_capacity, s_scratch);
 }
 
 // all_explored costs exactly as the sequential search reports them (simple_scored_sampling_planner.cpp:50-79,

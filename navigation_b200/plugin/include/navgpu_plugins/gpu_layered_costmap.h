@@ -1,0 +1,144 @@
+// GpuLayeredCostmap -- the device-resident counterpart of costmap_2d::LayeredCostmap for stacks that are made of the
+// layers libnavgpu implements (static-style grid layers, obstacle layers, inflation): one updateMap() runs the whole
+// cycle of costmap_2d/src/layered_costmap.cpp:79-150 on the GPU (bounds of every layer, resetMap, merges in plugin
+// order, ray-trace clearing + marking + footprint clearing, inflation) without the master grid leaving HBM, and
+// getCostmap() brings the updated window back into an ordinary costmap_2d::Costmap2D for host-side consumers.
+// Header-only RAII over the navgpu_costmap_* C ABI (include/navgpu.h); method names follow LayeredCostmap /
+// Costmap2DROS.  Errors: methods return false and keep navgpu_last_error(); there is no CPU fallback.
+#ifndef NAVGPU_PLUGINS_GPU_LAYERED_COSTMAP_H_
+#define NAVGPU_PLUGINS_GPU_LAYERED_COSTMAP_H_
+
+#include <costmap_2d/costmap_2d.h>
+#include <costmap_2d/observation.h>
+#include <geometry_msgs/Point.h>
+
+#include <cstring>
+#include <vector>
+
+#include "navgpu.h"
+
+namespace navgpu_plugins {
+
+class GpuLayeredCostmap {
+ public:
+  // LayeredCostmap(global_frame, rolling_window, track_unknown) + resizeMap (layered_costmap.cpp:50-77)
+  GpuLayeredCostmap(unsigned int size_x, unsigned int size_y, double resolution, double origin_x, double origin_y,
+                    bool rolling_window, bool track_unknown, int device = 0)
+      : handle_(NULL), host_(size_x, size_y, resolution, origin_x, origin_y, track_unknown ? 255 : 0) {
+    status_ = navgpu_costmap_create(&handle_, size_x, size_y, resolution, origin_x, origin_y, rolling_window,
+                                    track_unknown, device);
+    bounds_[0] = bounds_[1] = bounds_[2] = bounds_[3] = 0;
+  }
+  ~GpuLayeredCostmap() {
+    if (handle_) navgpu_costmap_destroy(handle_);
+  }
+  GpuLayeredCostmap(const GpuLayeredCostmap&) = delete;
+  GpuLayeredCostmap& operator=(const GpuLayeredCostmap&) = delete;
+
+  bool ok() const { return handle_ != NULL && status_ == NAVGPU_OK; }
+  int lastStatus() const { return status_; }
+
+  // plugins are appended in costmap `plugins:` order (costmap_2d_ros.cpp:115-128); the returned id names the layer
+  int addStaticLayer(bool use_maximum = false) {  // StaticLayer::updateCosts policy (static_layer.cpp:287-299)
+    int id = -1;
+    status_ = navgpu_costmap_add_grid_layer(handle_, use_maximum ? NAVGPU_MAX : NAVGPU_TRUE_OVERWRITE, &id);
+    return id;
+  }
+  int addObstacleLayer(int combination_method = 1, bool footprint_clearing_enabled = true,
+                       double max_obstacle_height = 2.0) {  // cfg/ObstaclePlugin.cfg:7-10
+    int id = -1;
+    status_ = navgpu_costmap_add_obstacle_layer(handle_, combination_method, footprint_clearing_enabled,
+                                                max_obstacle_height, &id);
+    return id;
+  }
+  int addInflationLayer(double inflation_radius = 0.55, double cost_scaling_factor = 10.0) {  // cfg/InflationPlugin.cfg
+    int id = -1;
+    status_ = navgpu_costmap_add_inflation_layer(handle_, inflation_radius, cost_scaling_factor, &id);
+    return id;
+  }
+
+  // LayeredCostmap::setFootprint (layered_costmap.cpp:163-173)
+  bool setFootprint(const std::vector<geometry_msgs::Point>& footprint_spec) {
+    std::vector<double> xy(2 * footprint_spec.size());
+    for (size_t i = 0; i < footprint_spec.size(); ++i) {
+      xy[2 * i] = footprint_spec[i].x;
+      xy[2 * i + 1] = footprint_spec[i].y;
+    }
+    return check(navgpu_costmap_set_footprint(handle_, xy.data(), (int)footprint_spec.size()));
+  }
+  // StaticLayer::incomingMap (static_layer.cpp:165-223): nav_msgs/OccupancyGrid data, interpreted on the device
+  bool setStaticMap(int layer, const signed char* occupancy, bool track_unknown_space = true,
+                    unsigned char unknown_cost_value = 255, unsigned char lethal_threshold = 100, bool trinary = true) {
+    return check(navgpu_grid_layer_set_occupancy(handle_, layer, occupancy, track_unknown_space, unknown_cost_value,
+                                                 lethal_threshold, trinary));
+  }
+  bool setLayerCosts(int layer, const unsigned char* costs) { return check(navgpu_grid_layer_set(handle_, layer, costs)); }
+  // ObstacleLayer's marking / clearing observations for the coming cycles (obstacle_layer.cpp:340-365, 450-464);
+  // cloud points are float32 x, y, z exactly as pcl::PointXYZ stores them
+  bool setObservations(int layer, const std::vector<costmap_2d::Observation>& marking_and_clearing) {
+    std::vector<navgpu_observation> obs(marking_and_clearing.size());
+    std::vector<std::vector<float> > xyz(marking_and_clearing.size());
+    for (size_t i = 0; i < marking_and_clearing.size(); ++i) {
+      const costmap_2d::Observation& o = marking_and_clearing[i];
+      xyz[i].resize(3 * o.cloud_->points.size());
+      for (size_t p = 0; p < o.cloud_->points.size(); ++p) {
+        xyz[i][3 * p] = o.cloud_->points[p].x;
+        xyz[i][3 * p + 1] = o.cloud_->points[p].y;
+        xyz[i][3 * p + 2] = o.cloud_->points[p].z;
+      }
+      obs[i].origin_x = o.origin_.x; obs[i].origin_y = o.origin_.y; obs[i].origin_z = o.origin_.z;
+      obs[i].obstacle_range = o.obstacle_range_;
+      obs[i].raytrace_range = o.raytrace_range_;
+      obs[i].xyz = xyz[i].data();
+      obs[i].n_points = (int)o.cloud_->points.size();
+      obs[i].marking = 1;
+      obs[i].clearing = 1;
+      obs[i].pad_ = 0;
+    }
+    return check(navgpu_obstacle_set_observations(handle_, layer, obs.data(), (int)obs.size()));
+  }
+  bool setInflationParameters(int layer, double inflation_radius, double cost_scaling_factor) {
+    return check(navgpu_inflation_set_params(handle_, layer, inflation_radius, cost_scaling_factor));
+  }
+  bool setEnabled(int layer, bool enabled) { return check(navgpu_layer_set_enabled(handle_, layer, enabled)); }
+
+  // LayeredCostmap::updateMap (layered_costmap.cpp:79-150)
+  bool updateMap(double robot_x, double robot_y, double robot_yaw) {
+    return check(navgpu_costmap_update_map(handle_, robot_x, robot_y, robot_yaw, bounds_));
+  }
+  // LayeredCostmap::getBounds (layered_costmap.h:129-135)
+  void getBounds(unsigned int* x0, unsigned int* xn, unsigned int* y0, unsigned int* yn) const {
+    *x0 = bounds_[0]; *xn = bounds_[1]; *y0 = bounds_[2]; *yn = bounds_[3];
+  }
+  // LayeredCostmap::getCostmap: refreshes the host copy inside the last update window and returns it
+  costmap_2d::Costmap2D* getCostmap() {
+    const int w = bounds_[1] - bounds_[0], h = bounds_[3] - bounds_[2];
+    if (w > 0 && h > 0) {
+      window_.resize(size_t(w) * h);
+      if (!check(navgpu_costmap_get_window(handle_, bounds_[0], bounds_[2], bounds_[1], bounds_[3], window_.data())))
+        return NULL;
+      double origin[2];
+      navgpu_costmap_get_origin(handle_, origin);
+      host_.updateOrigin(origin[0], origin[1]);
+      unsigned char* dst = host_.getCharMap();
+      const unsigned int sx = host_.getSizeInCellsX();
+      for (int r = 0; r < h; ++r) memcpy(dst + size_t(bounds_[2] + r) * sx + bounds_[0], window_.data() + size_t(r) * w, w);
+    }
+    return &host_;
+  }
+  navgpu_costmap* handle() { return handle_; }
+
+ private:
+  bool check(int rc) {
+    status_ = rc;
+    return rc == NAVGPU_OK;
+  }
+  navgpu_costmap* handle_;
+  costmap_2d::Costmap2D host_;
+  std::vector<unsigned char> window_;
+  int bounds_[4];
+  int status_;
+};
+
+}  // namespace navgpu_plugins
+#endif

@@ -1,0 +1,267 @@
+// Drop-in check of the C++ adapters in navigation_b200/plugin against the REFERENCE'S OWN classes.
+//
+// Built only where /root/reference exists (oracle/Makefile target `dropin`): this file and the adapters are compiled
+// against the reference's headers (plus the stub headers in oracle/shim for ROS/Boost/PCL) and linked with
+// oracle/_ref/libnavref.so (the reference's unmodified hot-path sources) and navigation_b200/libnavgpu.so.
+//
+//   A1  costmap_2d::LayeredCostmap (reference) + test grid layer + reference costmap_2d::InflationLayer
+//       versus the same LayeredCostmap + the same grid layer + navgpu_plugins::GpuInflationLayer as the plugin:
+//       master grids must be identical over several cycles (full window, sub-window, parameter change).
+//   A2  navgpu_plugins::GpuLayeredCostmap (whole stack on the device) versus the reference stack.
+//   B   navgpu_plugins::GpuScoredSamplingPlanner as a base_local_planner::TrajectorySearch versus the reference's
+//       generator + critics + SimpleScoredSamplingPlanner wired like DWAPlanner (through libnavref's C API).
+// Prints one line per check and exits non-zero on any mismatch.  Test infrastructure, not product code.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include <costmap_2d/cost_values.h>
+#include <costmap_2d/costmap_layer.h>
+#include <costmap_2d/inflation_layer.h>
+#include <costmap_2d/layered_costmap.h>
+
+#include <navgpu_plugins/gpu_inflation_layer.h>
+#include <navgpu_plugins/gpu_layered_costmap.h>
+#include <navgpu_plugins/gpu_scored_sampling_planner.h>
+
+#include "oracle_api.h"
+
+namespace {
+
+using costmap_2d::Costmap2D;
+using costmap_2d::LayeredCostmap;
+
+// A CostmapLayer fed by the test: StaticLayer's non-rolling behaviour (static_layer.cpp:263-299) with TrueOverwrite
+class TestGridLayer : public costmap_2d::CostmapLayer {
+ public:
+  TestGridLayer() : x_(0), y_(0), w_(0), h_(0), updated_(false) {}
+  void onInitialize() override {
+    current_ = true;
+    enabled_ = true;
+    default_value_ = costmap_2d::FREE_SPACE;
+    matchSize();
+  }
+  void setData(const std::vector<unsigned char>& d) {
+    memcpy(costmap_, d.data(), d.size());
+    touchRegion(0, 0, size_x_, size_y_);
+  }
+  void setCells(unsigned x, unsigned y, unsigned w, unsigned h, unsigned char v) {
+    for (unsigned j = y; j < y + h; ++j) memset(costmap_ + j * size_x_ + x, v, w);
+    touchRegion(x, y, w, h);
+  }
+  void touchRegion(unsigned x, unsigned y, unsigned w, unsigned h) { x_ = x; y_ = y; w_ = w; h_ = h; updated_ = true; }
+  void updateBounds(double, double, double, double* min_x, double* min_y, double* max_x, double* max_y) override {
+    if (!updated_) return;
+    double wx, wy;
+    mapToWorld(x_, y_, wx, wy);
+    *min_x = std::min(wx, *min_x);
+    *min_y = std::min(wy, *min_y);
+    mapToWorld(x_ + w_, y_ + h_, wx, wy);
+    *max_x = std::max(wx, *max_x);
+    *max_y = std::max(wy, *max_y);
+    updated_ = false;
+  }
+  void updateCosts(Costmap2D& master, int min_i, int min_j, int max_i, int max_j) override {
+    updateWithTrueOverwrite(master, min_i, min_j, max_i, max_j);
+  }
+  unsigned x_, y_, w_, h_;
+  bool updated_;
+};
+
+std::vector<geometry_msgs::Point> squareFootprint(double half) {
+  std::vector<geometry_msgs::Point> fp(4);
+  fp[0].x = half; fp[0].y = half;
+  fp[1].x = half; fp[1].y = -half;
+  fp[2].x = -half; fp[2].y = -half;
+  fp[3].x = -half; fp[3].y = half;
+  return fp;
+}
+
+// thick axis-aligned blocks: the tie-free map class on which the reference's result does not depend on heap order
+std::vector<unsigned char> blockMap(unsigned sx, unsigned sy, unsigned seed) {
+  std::mt19937 rng(seed);
+  std::vector<unsigned char> g(size_t(sx) * sy, 0);
+  for (int k = 0; k < 40; ++k) {
+    unsigned w = 3 + rng() % 40, h = 3 + rng() % 40, x = rng() % (sx - w), y = rng() % (sy - h);
+    for (unsigned j = y; j < y + h; ++j) memset(&g[size_t(j) * sx + x], 254, w);
+  }
+  return g;
+}
+
+long countDiff(const unsigned char* a, const unsigned char* b, size_t n) {
+  long d = 0;
+  for (size_t i = 0; i < n; ++i) d += a[i] != b[i];
+  return d;
+}
+
+int failures = 0;
+void report(const char* name, long diff, long total) {
+  printf("%-64s %s (%ld of %ld cells differ)\n", name, diff == 0 ? "OK" : "MISMATCH", diff, total);
+  if (diff != 0) ++failures;
+}
+
+struct Stack {
+  LayeredCostmap lc;
+  TestGridLayer* grid;
+  costmap_2d::Layer* inflation;
+  Stack(unsigned sx, unsigned sy, double res, costmap_2d::Layer* infl) : lc("map", false, false), grid(new TestGridLayer), inflation(infl) {
+    lc.resizeMap(sx, sy, res, 0.0, 0.0);
+    boost::shared_ptr<costmap_2d::Layer> g(grid), i(infl);
+    lc.addPlugin(g);
+    grid->initialize(&lc, "static", NULL);
+    lc.addPlugin(i);
+    infl->initialize(&lc, "inflation", NULL);
+    lc.setFootprint(squareFootprint(0.325));
+  }
+};
+
+void testInflationPlugin() {
+  const unsigned sx = 400, sy = 300;
+  const double res = 0.05;
+  costmap_2d::InflationLayer* ref_layer = new costmap_2d::InflationLayer;
+  navgpu_plugins::GpuInflationLayer* gpu_layer = new navgpu_plugins::GpuInflationLayer;
+  Stack ref(sx, sy, res, ref_layer), gpu(sx, sy, res, gpu_layer);
+  const std::vector<unsigned char> map = blockMap(sx, sy, 7);
+  ref.grid->setData(map);
+  gpu.grid->setData(map);
+  const size_t n = size_t(sx) * sy;
+  ref.lc.updateMap(5.0, 5.0, 0.0);
+  gpu.lc.updateMap(5.0, 5.0, 0.0);
+  report("A1 cycle 1: full window, radius 0.55", countDiff(ref.lc.getCostmap()->getCharMap(), gpu.lc.getCostmap()->getCharMap(), n), n);
+  // cycle 2: a new block appears in a sub-window
+  ref.grid->setCells(120, 80, 30, 12, 254);
+  gpu.grid->setCells(120, 80, 30, 12, 254);
+  ref.lc.updateMap(5.0, 5.0, 0.0);
+  gpu.lc.updateMap(5.0, 5.0, 0.0);
+  unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+  ref.lc.getBounds(&a0, &a1, &a2, &a3);
+  gpu.lc.getBounds(&b0, &b1, &b2, &b3);
+  report("A1 cycle 2: sub-window bounds", (a0 != b0) + (a1 != b1) + (a2 != b2) + (a3 != b3), 4);
+  report("A1 cycle 2: sub-window update", countDiff(ref.lc.getCostmap()->getCharMap(), gpu.lc.getCostmap()->getCharMap(), n), n);
+  // cycle 3: the block disappears again (cleared cells must lose their inflation inside the window)
+  ref.grid->setCells(120, 80, 30, 12, 0);
+  gpu.grid->setCells(120, 80, 30, 12, 0);
+  ref.lc.updateMap(5.0, 5.0, 0.0);
+  gpu.lc.updateMap(5.0, 5.0, 0.0);
+  report("A1 cycle 3: block removed", countDiff(ref.lc.getCostmap()->getCharMap(), gpu.lc.getCostmap()->getCharMap(), n), n);
+  // cycle 4: reconfigure to the C3 inflation (1.0 m => R = 20 cells), which forces a whole-map re-inflation
+  ref_layer->setInflationParameters(1.0, 10.0);
+  gpu_layer->setInflationParameters(1.0, 10.0);
+  ref.lc.updateMap(5.0, 5.0, 0.0);
+  gpu.lc.updateMap(5.0, 5.0, 0.0);
+  report("A1 cycle 4: setInflationParameters(1.0, 10)", countDiff(ref.lc.getCostmap()->getCharMap(), gpu.lc.getCostmap()->getCharMap(), n), n);
+  report("A1 computeCost agrees on 0..25 cells", [&] {
+    long d = 0;
+    for (int i = 0; i <= 25; ++i) d += ref_layer->computeCost(i) != gpu_layer->computeCost(i);
+    return d;
+  }(), 26);
+}
+
+void testFusedStack() {
+  const unsigned sx = 400, sy = 300;
+  const double res = 0.05;
+  Stack ref(sx, sy, res, new costmap_2d::InflationLayer);
+  navgpu_plugins::GpuLayeredCostmap gpu(sx, sy, res, 0.0, 0.0, false, false);
+  const int s = gpu.addStaticLayer(false);
+  gpu.addInflationLayer(0.55, 10.0);
+  gpu.setFootprint(squareFootprint(0.325));
+  const std::vector<unsigned char> map = blockMap(sx, sy, 11);
+  ref.grid->setData(map);
+  gpu.setLayerCosts(s, map.data());
+  ref.lc.updateMap(5.0, 5.0, 0.0);
+  const bool ok = gpu.ok() && gpu.updateMap(5.0, 5.0, 0.0);
+  Costmap2D* out = ok ? gpu.getCostmap() : NULL;
+  const size_t n = size_t(sx) * sy;
+  if (!out) {
+    printf("A2 GpuLayeredCostmap failed: %s\n", navgpu_last_error());
+    ++failures;
+    return;
+  }
+  report("A2 GpuLayeredCostmap vs reference LayeredCostmap", countDiff(ref.lc.getCostmap()->getCharMap(), out->getCharMap(), n), n);
+}
+
+void testScoredSamplingPlanner() {
+  // local costmap: corridor + box, inflated by the reference stack
+  const unsigned n = 120;
+  const double res = 0.05;
+  Stack ref(n, n, res, new costmap_2d::InflationLayer);
+  std::vector<unsigned char> g(size_t(n) * n, 0);
+  for (unsigned y = 26; y < 29; ++y) memset(&g[y * n], 254, n);
+  for (unsigned y = 91; y < 94; ++y) memset(&g[y * n], 254, n);
+  for (unsigned y = 52; y < 58; ++y) memset(&g[y * n + 84], 254, 6);
+  ref.grid->setData(g);
+  ref.lc.updateMap(3.0, 3.0, 0.0);
+  Costmap2D* local = ref.lc.getCostmap();
+
+  navo_dwa_config rc;
+  navo_dwa_default_config(&rc);
+  rc.vx_samples = 20; rc.vy_samples = 1; rc.vth_samples = 20; rc.max_vel_y = 0.0; rc.min_vel_y = 0.0;
+  navgpu_dwa_config gc = navgpu_plugins::GpuScoredSamplingPlanner::defaultConfig();
+  gc.vx_samples = 20; gc.vy_samples = 1; gc.vth_samples = 20; gc.max_vel_y = 0.0; gc.min_vel_y = 0.0;
+
+  void* refp = navo_dwa_create(&rc, n, n, res);
+  navo_dwa_set_costmap(refp, local->getCharMap(), 0.0, 0.0);
+  navgpu_plugins::GpuScoredSamplingPlanner gpu(gc, local);
+  base_local_planner::TrajectorySearch* search = &gpu;  // used through the reference's interface
+
+  std::vector<double> plan_xy;
+  std::vector<geometry_msgs::PoseStamped> plan;
+  for (int i = 0; i < 120; ++i) {
+    geometry_msgs::PoseStamped p;
+    p.pose.position.x = 1.0 + 0.05 * i;
+    p.pose.position.y = 3.0;
+    plan.push_back(p);
+    plan_xy.push_back(p.pose.position.x);
+    plan_xy.push_back(p.pose.position.y);
+  }
+  const std::vector<geometry_msgs::Point> fp = squareFootprint(0.3);
+  std::vector<double> fp_xy;
+  for (size_t i = 0; i < fp.size(); ++i) { fp_xy.push_back(fp[i].x); fp_xy.push_back(fp[i].y); }
+
+  double pose[3] = {1.5, 3.0, 0.0}, vel[3] = {0.3, 0.0, 0.0};
+  long bad = 0, cycles = 0;
+  for (int c = 0; c < 6; ++c, ++cycles) {
+    navo_dwa_set_plan(refp, pose, plan_xy.data(), 120);
+    gpu.setPlan(pose[0], pose[1], pose[2], plan);
+    navo_dwa_result rr;
+    std::vector<double> rcosts(1 << 12), rpts(3 * 4096);
+    navo_dwa_find_best_path(refp, pose, vel, fp_xy.data(), 4, &rr, rcosts.data(), (int)rcosts.size(), rpts.data(), 4096);
+    gpu.setState(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], fp);
+    base_local_planner::Trajectory traj;
+    std::vector<base_local_planner::Trajectory> explored;
+    const bool found = search->findBestTrajectory(traj, &explored);
+    const bool same = found == (rr.cost >= 0) && gpu.bestIndex() == rr.best_index &&
+                      std::fabs(traj.cost_ - rr.cost) <= 1e-5 * std::fabs(rr.cost) && traj.xv_ == rr.xv &&
+                      traj.thetav_ == rr.thetav && (int)traj.getPointsSize() == rr.n_points &&
+                      (int)explored.size() == rr.n_scored && gpu.oscillationMask() == navo_dwa_get_oscillation_mask(refp);
+    if (!same) {
+      ++bad;
+      printf("  cycle %d: reference best %d cost %.9g (%d pts, %d scored) / gpu best %d cost %.9g (%u pts, %zu explored)\n", c,
+             rr.best_index, rr.cost, rr.n_points, rr.n_scored, gpu.bestIndex(), traj.cost_, traj.getPointsSize(), explored.size());
+    }
+    if (rr.cost >= 0) {  // follow the chosen command for one control period
+      double x, y, th;
+      traj.getPoint(std::min(2u, traj.getPointsSize() - 1), x, y, th);
+      pose[0] = x; pose[1] = y; pose[2] = th;
+      vel[0] = rr.xv; vel[1] = rr.yv; vel[2] = rr.thetav;
+    }
+  }
+  navo_dwa_destroy(refp);
+  report("B  GpuScoredSamplingPlanner vs reference DWA search, 6 cycles", bad, cycles);
+}
+
+}  // namespace
+
+int main() {
+  if (navgpu_device_count() == 0) {
+    printf("no CUDA device: the adapters have no CPU fallback\n");
+    return 2;
+  }
+  testInflationPlugin();
+  testFusedStack();
+  testScoredSamplingPlanner();
+  printf("%s\n", failures ? "DROP-IN FAILED" : "DROP-IN OK");
+  return failures ? 1 : 0;
+}

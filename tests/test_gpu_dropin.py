@@ -1,0 +1,44 @@
+"""Drop-in check of the C++ adapters (navigation_b200/plugin) next to the reference's own classes.
+
+oracle/_ref/dropin_harness is built here, where /root/reference exists (`make -C oracle dropin`): the adapters and
+tests/cpp/dropin_harness.cpp are compiled against the reference's headers and linked with the reference's unmodified
+hot-path sources (oracle/_ref/libnavref.so) and libnavgpu.so.  The binary travels to the GPU box with the snapshot."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "dropin_harness")
+
+
+def build_harness():
+    from navigation_b200 import build
+    build.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "dropin"])
+
+
+def test_dropin_harness_builds_against_reference_headers():
+    """GpuInflationLayer : costmap_2d::Layer, GpuLayeredCostmap and GpuScoredSamplingPlanner : TrajectorySearch compile
+    against the reference's own headers and link with its compiled sources (no GPU needed for that)."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    build_harness()
+    assert os.access(HARNESS, os.X_OK)
+
+
+@pytest.mark.gpu
+def test_adapters_match_reference_classes(cuda):
+    """A1: reference LayeredCostmap with GpuInflationLayer as its plugin == with costmap_2d::InflationLayer (4 cycles);
+    A2: GpuLayeredCostmap == reference stack; B: GpuScoredSamplingPlanner through base_local_planner::TrajectorySearch
+    == the reference's generator + critics + SimpleScoredSamplingPlanner (best index, cost <= 1e-5 rel, velocities,
+    point count, explored count, oscillation flags) over 6 control cycles."""
+    if not os.path.exists(HARNESS):
+        if os.path.isdir("/root/reference"):
+            build_harness()
+        else:
+            pytest.skip("oracle/_ref/dropin_harness was not built (needs /root/reference)")
+    r = subprocess.run([HARNESS], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "DROP-IN OK" in r.stdout

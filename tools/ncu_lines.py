@@ -1,5 +1,6 @@
 """Reads an .ncu-rep (source page, SASS) and attributes executed instructions and stall samples to CUDA source lines
-using nvdisasm's line info for the same kernel in libnavgpu.so.  Usage: ncu_lines.py REP KERNEL_SUBSTR [launch_idx]"""
+using nvdisasm's line info for the same kernel in libnavgpu.so (rebuild nothing between the capture and this).
+Usage: ncu_lines.py REP KERNEL_SUBSTR [launch_idx] [MANGLED_SUBSTR]"""
 import csv
 import io
 import re
@@ -9,6 +10,7 @@ import collections
 
 rep, kern = sys.argv[1], sys.argv[2]
 which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+mangled = sys.argv[4] if len(sys.argv) > 4 else kern
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 # split per kernel block
 blocks, cur = [], None
@@ -33,7 +35,7 @@ lines = None
 for cub in glob.glob("/tmp/*.cubin"):
     dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
     # find the function section
-    m = re.search(r"\.text\.[^\n]*" + re.escape(kern) + r"[^\n]*\n", dis)
+    m = re.search(r"\.text\.[^\n]*" + re.escape(mangled) + r"[^\n]*\n", dis)
     if not m:
         continue
     body = dis[m.end():]
