@@ -201,6 +201,27 @@ int navgpu_dwa_find_best_path_async(navgpu_dwa* h, const double pose[3], const d
 int navgpu_dwa_synchronize(navgpu_dwa* h);
 void* navgpu_dwa_stream(navgpu_dwa* h);
 
+/* ---- Fleet mode: N independent robots per control cycle (config C5) ------------------------------------------
+ * Every robot has its own local costmap (raw obstacles in, inflated on the device exactly like a layered costmap
+ * with a static-style layer + InflationLayer), plan, pose, velocity and oscillation state; one navgpu_fleet_step is
+ * LayeredCostmap::updateMap + DWAPlanner::findBestPath for all of them in a handful of launches.  Robots are
+ * independent, so a multi-GPU job gives each rank its own fleet with its share of the robots (no collective). */
+typedef struct navgpu_fleet navgpu_fleet;
+int navgpu_fleet_create(navgpu_fleet** out, int n_robots, const navgpu_dwa_config* cfg, uint32_t size_x,
+                        uint32_t size_y, double resolution, double inflation_radius, double cost_scaling_factor,
+                        const double* footprint_xy, int n_footprint, int device);
+int navgpu_fleet_destroy(navgpu_fleet* f);
+/* raw (un-inflated) local maps [n][size_y][size_x] and their world origins [n][2], HOST memory */
+int navgpu_fleet_set_maps(navgpu_fleet* f, const uint8_t* raw_maps, const double* origins_xy);
+/* DWAPlanner::updatePlanAndLocalCosts for every robot: poses [n][3], concatenated plan points, offsets [n + 1] */
+int navgpu_fleet_set_plans(navgpu_fleet* f, const double* poses, const double* plan_xy, const int32_t* plan_offsets);
+int navgpu_fleet_reset_oscillation(navgpu_fleet* f);
+/* one control cycle; poses, vels [n][3]; results: n entries (n_points = 0, winners' points are not materialised) */
+int navgpu_fleet_step(navgpu_fleet* f, const double* poses, const double* vels, navgpu_dwa_result* results);
+/* inflated local costmap of one robot, HOST size_y x size_x */
+int navgpu_fleet_get_costmap(navgpu_fleet* f, int robot, uint8_t* host_out);
+int navgpu_fleet_get_oscillation_mask(navgpu_fleet* f, int robot, int* mask_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,15 @@ SIGNATURES = {
     "navgpu_dwa_find_best_path_async": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int]),
     "navgpu_dwa_synchronize": (C.c_int, [C.c_void_p]),
     "navgpu_dwa_stream": (C.c_void_p, [C.c_void_p]),
+    "navgpu_fleet_create": (C.c_int, [_vpp, C.c_int, C.POINTER(DwaConfig), C.c_uint32, C.c_uint32, C.c_double, C.c_double,
+                                      C.c_double, _f64p, C.c_int, C.c_int]),
+    "navgpu_fleet_destroy": (C.c_int, [C.c_void_p]),
+    "navgpu_fleet_set_maps": (C.c_int, [C.c_void_p, _u8p, _f64p]),
+    "navgpu_fleet_set_plans": (C.c_int, [C.c_void_p, _f64p, _f64p, _i32p]),
+    "navgpu_fleet_reset_oscillation": (C.c_int, [C.c_void_p]),
+    "navgpu_fleet_step": (C.c_int, [C.c_void_p, _f64p, _f64p, C.POINTER(DwaResult)]),
+    "navgpu_fleet_get_costmap": (C.c_int, [C.c_void_p, C.c_int, _u8p]),
+    "navgpu_fleet_get_oscillation_mask": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
 }
 
 
@@ -363,6 +372,71 @@ class Dwa:
         return out
 
 
+class Fleet:
+    """N independent robots per control cycle (navgpu_fleet_*): local-costmap inflation + DWA scoring, batched."""
+
+    def __init__(self, api, n_robots, size_x, size_y, resolution, footprint_xy, inflation_radius=0.55,
+                 cost_scaling_factor=10.0, device=0, **overrides):
+        self.api, self.lib, self.n = api, api.lib, n_robots
+        self.size_x, self.size_y = size_x, size_y
+        self.cfg = DwaConfig()
+        self.lib.navgpu_dwa_default_config(C.byref(self.cfg))
+        for k, v in overrides.items():
+            setattr(self.cfg, k, v)
+        fp = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        h = C.c_void_p()
+        api.check(self.lib.navgpu_fleet_create(C.byref(h), n_robots, C.byref(self.cfg), size_x, size_y, resolution,
+                                               inflation_radius, cost_scaling_factor, _p(fp, _f64p), fp.shape[0], device))
+        self.h = h
+        self._results = (DwaResult * n_robots)()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.navgpu_fleet_destroy(self.h)
+            self.h = None
+
+    def set_maps(self, raw_maps, origins_xy):
+        m = np.ascontiguousarray(raw_maps, dtype=np.uint8)
+        o = np.ascontiguousarray(origins_xy, dtype=np.float64)
+        assert m.shape == (self.n, self.size_y, self.size_x) and o.shape == (self.n, 2)
+        self.api.check(self.lib.navgpu_fleet_set_maps(self.h, _p(m, _u8p), _p(o, _f64p)))
+
+    def set_plans(self, poses, plans):
+        """plans: list of (k_i, 2) arrays, one per robot."""
+        p = np.ascontiguousarray(poses, dtype=np.float64)
+        off = np.zeros(self.n + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(q) for q in plans])
+        xy = np.ascontiguousarray(np.concatenate([np.asarray(q, dtype=np.float64).reshape(-1, 2) for q in plans]))
+        self.api.check(self.lib.navgpu_fleet_set_plans(self.h, _p(p, _f64p), _p(xy, _f64p), _p(off, _i32p)))
+
+    def reset_oscillation(self):
+        self.api.check(self.lib.navgpu_fleet_reset_oscillation(self.h))
+
+    def step(self, poses, vels):
+        p = np.ascontiguousarray(poses, dtype=np.float64)
+        v = np.ascontiguousarray(vels, dtype=np.float64)
+        assert p.shape == (self.n, 3) and v.shape == (self.n, 3)
+        self.api.check(self.lib.navgpu_fleet_step(self.h, _p(p, _f64p), _p(v, _f64p), self._results))
+        r = self._results
+        return [dict(cost=r[i].cost, xv=r[i].xv, yv=r[i].yv, thetav=r[i].thetav, best_index=r[i].best_index,
+                     n_samples=r[i].n_samples, n_scored=r[i].n_scored) for i in range(self.n)]
+
+    def step_raw(self, poses, vels):
+        """step() without building Python dicts (benchmarks); returns the ctypes result array."""
+        self.api.check(self.lib.navgpu_fleet_step(self.h, _p(poses, _f64p), _p(vels, _f64p), self._results))
+        return self._results
+
+    def costmap(self, robot):
+        out = np.empty((self.size_y, self.size_x), dtype=np.uint8)
+        self.api.check(self.lib.navgpu_fleet_get_costmap(self.h, robot, _p(out, _u8p)))
+        return out
+
+    def oscillation_mask(self, robot):
+        m = C.c_int32()
+        self.api.check(self.lib.navgpu_fleet_get_oscillation_mask(self.h, robot, C.byref(m)))
+        return int(m.value)
+
+
 class Api:
     name = "cuda"
 
@@ -390,6 +464,9 @@ class Api:
 
     def dwa(self, *a, **k):
         return Dwa(self, *a, **k)
+
+    def fleet(self, *a, **k):
+        return Fleet(self, *a, **k)
 
     def build_cost_table(self, resolution, inscribed_radius, inflation_radius, cost_scaling_factor):
         cap = 256 * 256

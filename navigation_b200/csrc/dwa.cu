@@ -291,6 +291,7 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   ma.job[1] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 1, h->d_dist[1]};  // goal: setLocalGoal
   ma.job[2] = MapGridJob{h->d_plan[1], (int)h->adjusted[1].size(), 1, h->d_dist[2]};  // goal_front
   ma.job[3] = MapGridJob{h->d_plan[2], (int)h->adjusted[2].size(), 0, h->d_dist[3]};  // alignment
+  ma.fleet = nullptr;
   NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
 
   DwaScoreArgs& a = cy.args;
@@ -641,5 +642,321 @@ int navgpu_dwa_synchronize(navgpu_dwa* h) {
 }
 
 void* navgpu_dwa_stream(navgpu_dwa* h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"
+
+// ==================================================================================================================
+// Fleet mode (config C5): N independent robots per control cycle -- inflation of every robot's local costmap, four
+// MapGrid wavefronts per robot, rollout scoring of every robot's velocity samples -- as a handful of launches.
+// The N local maps are stacked along y in ONE device-resident layered costmap (static-style layer + inflation
+// layer) with kFleetPadRows rows of free space between robots so inflation cannot leak from one robot into the next;
+// the planner side reuses the single-planner kernels with per-robot arguments (FleetRobot).
+// ==================================================================================================================
+namespace {
+constexpr unsigned kFleetPadRows = 64;  // >= 2 * the largest cell inflation radius the fast sweep supports (31)
+}
+
+struct navgpu_fleet {
+  int device = 0;
+  int n = 0;
+  unsigned sx = 0, sy = 0, stride = 0;  // rows per robot in the stacked grid
+  double res = 0;
+  navgpu_dwa_config cfg;
+  navgpu_costmap* costmap = nullptr;
+  int static_layer = -1;
+  cudaStream_t stream = nullptr;  // the costmap's stream
+  uint8_t* d_stage = nullptr;     // n x stride x pitch staging of the raw maps (pad rows stay zero)
+  unsigned pitch = 0;
+  const uint8_t* d_master = nullptr;
+  std::vector<double> origins;  // n x 2
+  std::vector<std::vector<P2>> plan, adj_path, adj_front, adj_align;
+  std::vector<double> align_scale;
+  std::vector<Oscillation> osc;
+  std::vector<double> res_v;  // n x 3 persistent result velocities
+  std::vector<double> footprint;
+  double path_scale = 0, goal_scale = 0, obstacle_scale = 0;
+  // device side
+  FleetRobot* d_robots = nullptr;
+  double* d_plans = nullptr;
+  size_t plans_capacity = 0;
+  float* d_samples = nullptr;
+  size_t samples_capacity = 0;
+  uint32_t* d_dist = nullptr;  // n x 4 x sx*sy
+  double* d_block_cost = nullptr;
+  long long* d_block_index = nullptr;
+  size_t blocks_capacity = 0;
+  unsigned* d_generated = nullptr;
+  DwaDeviceResult* d_results = nullptr;
+  DwaDeviceResult* h_results = nullptr;  // pinned
+  bool plans_dirty = true;
+  std::vector<FleetRobot> h_robots;
+  std::vector<size_t> plan_off;  // per robot x 3 plans: offset (in points) into d_plans
+};
+
+extern "C" {
+
+int navgpu_fleet_create(navgpu_fleet** out, int n_robots, const navgpu_dwa_config* cfg, uint32_t size_x, uint32_t size_y,
+                        double resolution, double inflation_radius, double cost_scaling_factor,
+                        const double* footprint_xy, int n_footprint, int device) {
+  if (!out || !cfg || n_robots <= 0 || size_x == 0 || size_y == 0 || !(resolution > 0) || n_footprint < 0 ||
+      n_footprint > kMaxFootprint || (n_footprint > 0 && !footprint_xy))
+    return fail(NAVGPU_ERR_INVALID, "bad fleet arguments");
+  if (navgpu_device_count() <= device) return fail(NAVGPU_ERR_CUDA, "no CUDA device %d (libnavgpu has no CPU fallback)", device);
+  if (size_x > 32767 || size_y > 32767) return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap too large");
+  std::unique_ptr<navgpu_fleet> f(new navgpu_fleet);
+  f->device = device;
+  f->n = n_robots;
+  f->sx = size_x; f->sy = size_y; f->stride = size_y + kFleetPadRows;
+  f->res = resolution;
+  f->cfg = *cfg;
+  f->footprint.assign(footprint_xy, footprint_xy + 2 * n_footprint);
+  f->path_scale = resolution * cfg->path_distance_bias * 0.5;
+  f->goal_scale = resolution * cfg->goal_distance_bias * 0.5;
+  f->obstacle_scale = resolution * cfg->occdist_scale;
+  if ((unsigned long long)f->stride * n_robots > 0x7fffffffull) return fail(NAVGPU_ERR_UNSUPPORTED, "fleet too large");
+  // the stacked costmap: every robot's window is "the whole map" each cycle, like a rolling local costmap
+  NAVGPU_TRY(navgpu_costmap_create(&f->costmap, size_x, f->stride * n_robots, resolution, 0.0, 0.0, 0, 0, device));
+  NAVGPU_TRY(navgpu_costmap_add_grid_layer(f->costmap, NAVGPU_TRUE_OVERWRITE, &f->static_layer));
+  int il;
+  NAVGPU_TRY(navgpu_costmap_add_inflation_layer(f->costmap, inflation_radius, cost_scaling_factor, &il));
+  NAVGPU_TRY(navgpu_costmap_set_footprint(f->costmap, footprint_xy, n_footprint));
+  f->stream = (cudaStream_t)navgpu_costmap_stream(f->costmap);
+  uint32_t pitch;
+  NAVGPU_TRY(navgpu_costmap_device_grid(f->costmap, &f->d_master, &pitch));
+  f->pitch = pitch;
+  NAVGPU_CUDA(cudaSetDevice(device));
+  const size_t stage_bytes = size_t(pitch) * f->stride * n_robots;
+  NAVGPU_CUDA(cudaMalloc(&f->d_stage, stage_bytes));
+  NAVGPU_CUDA(cudaMemset(f->d_stage, 0, stage_bytes));
+  NAVGPU_CUDA(cudaMalloc(&f->d_robots, sizeof(FleetRobot) * n_robots));
+  NAVGPU_CUDA(cudaMalloc(&f->d_dist, size_t(n_robots) * 4 * size_x * size_y * sizeof(uint32_t)));
+  NAVGPU_CUDA(cudaMalloc(&f->d_generated, sizeof(unsigned) * n_robots));
+  NAVGPU_CUDA(cudaMemset(f->d_generated, 0, sizeof(unsigned) * n_robots));
+  NAVGPU_CUDA(cudaMalloc(&f->d_results, sizeof(DwaDeviceResult) * n_robots));
+  NAVGPU_CUDA(cudaMallocHost(&f->h_results, sizeof(DwaDeviceResult) * n_robots));
+  f->origins.assign(size_t(2) * n_robots, 0.0);
+  f->plan.resize(n_robots); f->adj_path.resize(n_robots); f->adj_front.resize(n_robots); f->adj_align.resize(n_robots);
+  f->align_scale.assign(n_robots, 0.0);
+  f->osc.resize(n_robots);
+  f->res_v.assign(size_t(3) * n_robots, 0.0);
+  f->h_robots.resize(n_robots);
+  *out = f.release();
+  return NAVGPU_OK;
+}
+
+int navgpu_fleet_destroy(navgpu_fleet* f) {
+  if (!f) return NAVGPU_OK;
+  cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  cudaFree(f->d_stage); cudaFree(f->d_robots); cudaFree(f->d_plans); cudaFree(f->d_samples); cudaFree(f->d_dist);
+  cudaFree(f->d_block_cost); cudaFree(f->d_block_index); cudaFree(f->d_generated); cudaFree(f->d_results);
+  cudaFreeHost(f->h_results);
+  navgpu_costmap_destroy(f->costmap);
+  delete f;
+  return NAVGPU_OK;
+}
+
+// raw (un-inflated) local maps of all robots, [n][size_y][size_x] in HOST memory, and their world origins [n][2]
+int navgpu_fleet_set_maps(navgpu_fleet* f, const uint8_t* raw_maps, const double* origins_xy) {
+  if (!f || !raw_maps || !origins_xy) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_CUDA(cudaSetDevice(f->device));
+  f->origins.assign(origins_xy, origins_xy + size_t(2) * f->n);
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(raw_maps), f->sx, f->sx, f->sy);
+  p.dstPtr = make_cudaPitchedPtr(f->d_stage, f->pitch, f->sx, f->stride);
+  p.extent = make_cudaExtent(f->sx, f->sy, f->n);
+  p.kind = cudaMemcpyHostToDevice;
+  NAVGPU_CUDA(cudaMemcpy3DAsync(&p, f->stream));
+  NAVGPU_TRY(navgpu_grid_layer_set_device(f->costmap, f->static_layer, f->d_stage, f->pitch));
+  NAVGPU_CUDA(cudaStreamSynchronize(f->stream));  // raw_maps may be pageable
+  return NAVGPU_OK;
+}
+
+// DWAPlanner::updatePlanAndLocalCosts for every robot: plan_xy = concatenated (x, y) points, plan_offsets[n + 1] in
+// points, poses [n][3]
+int navgpu_fleet_set_plans(navgpu_fleet* f, const double* poses, const double* plan_xy, const int32_t* plan_offsets) {
+  if (!f || !poses || !plan_xy || !plan_offsets) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  const navgpu_dwa_config& c = f->cfg;
+  for (int r = 0; r < f->n; ++r) {
+    const int b = plan_offsets[r], e = plan_offsets[r + 1];
+    if (e <= b) return fail(NAVGPU_ERR_INVALID, "robot %d has an empty plan", r);
+    std::vector<P2>& plan = f->plan[r];
+    plan.resize(e - b);
+    for (int i = b; i < e; ++i) plan[i - b] = P2{plan_xy[2 * i], plan_xy[2 * i + 1]};
+    adjust_plan_resolution(plan, f->adj_path[r], f->res);
+    const P2 goal = plan.back();
+    const float pos[3] = {(float)poses[3 * r], (float)poses[3 * r + 1], (float)poses[3 * r + 2]};
+    const double sq_dist = (pos[0] - goal.x) * (pos[0] - goal.x) + (pos[1] - goal.y) * (pos[1] - goal.y);
+    std::vector<P2> front = plan;
+    const double angle_to_goal = atan2(goal.y - pos[1], goal.x - pos[0]);
+    front.back().x = front.back().x + c.forward_point_distance * cos(angle_to_goal);
+    front.back().y = front.back().y + c.forward_point_distance * sin(angle_to_goal);
+    adjust_plan_resolution(front, f->adj_front[r], f->res);
+    if (sq_dist > c.forward_point_distance * c.forward_point_distance * c.cheat_factor) {
+      f->align_scale[r] = f->res * c.path_distance_bias * 0.5;
+      f->adj_align[r] = f->adj_path[r];
+    } else {
+      f->align_scale[r] = 0.0;
+    }
+    if (f->adj_align[r].empty()) f->adj_align[r] = f->adj_path[r];  // never set before: scale 0 or the path itself
+  }
+  f->plans_dirty = true;
+  return NAVGPU_OK;
+}
+
+int navgpu_fleet_reset_oscillation(navgpu_fleet* f) {
+  if (!f) return fail(NAVGPU_ERR_INVALID, "null handle");
+  for (Oscillation& o : f->osc) o.reset();
+  return NAVGPU_OK;
+}
+
+// One control cycle of the whole fleet: inflate every local map, then DWAPlanner::findBestPath for every robot.
+// poses, vels: [n][3]; results: n entries (n_points is always 0: the winners' points are not materialised).
+int navgpu_fleet_step(navgpu_fleet* f, const double* poses, const double* vels, navgpu_dwa_result* results) {
+  if (!f || !poses || !vels || !results) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_CUDA(cudaSetDevice(f->device));
+  const navgpu_dwa_config& c = f->cfg;
+  const int n = f->n;
+  // ---- Path A for all robots: one full-window update of the stacked costmap
+  NAVGPU_TRY(navgpu_grid_layer_touch(f->costmap, f->static_layer, 0, 0, f->sx, f->stride * n));
+  NAVGPU_TRY(navgpu_costmap_update_map_async(f->costmap, 0.0, 0.0, 0.0));
+
+  // ---- plans (only when they changed)
+  if (f->plans_dirty) {
+    size_t total = 0;
+    f->plan_off.assign(size_t(3) * n, 0);
+    for (int r = 0; r < n; ++r) {
+      f->plan_off[3 * r] = total; total += f->adj_path[r].size();
+      f->plan_off[3 * r + 1] = total; total += f->adj_front[r].size();
+      f->plan_off[3 * r + 2] = total; total += f->adj_align[r].size();
+    }
+    std::vector<P2> flat(total);
+    for (int r = 0; r < n; ++r) {
+      std::copy(f->adj_path[r].begin(), f->adj_path[r].end(), flat.begin() + f->plan_off[3 * r]);
+      std::copy(f->adj_front[r].begin(), f->adj_front[r].end(), flat.begin() + f->plan_off[3 * r + 1]);
+      std::copy(f->adj_align[r].begin(), f->adj_align[r].end(), flat.begin() + f->plan_off[3 * r + 2]);
+    }
+    if (total > f->plans_capacity) {
+      if (f->d_plans) cudaFree(f->d_plans);
+      f->d_plans = nullptr;
+      NAVGPU_CUDA(cudaMalloc(&f->d_plans, total * 2 * sizeof(P2)));
+      f->plans_capacity = total * 2;
+    }
+    NAVGPU_CUDA(cudaMemcpyAsync(f->d_plans, flat.data(), total * sizeof(P2), cudaMemcpyHostToDevice, f->stream));
+    NAVGPU_CUDA(cudaStreamSynchronize(f->stream));
+    f->plans_dirty = false;
+  }
+
+  // ---- per-robot scalars: samples (SimpleTrajectoryGenerator::initialise), pose, velocity, oscillation mask
+  std::vector<float> samples;
+  int max_samples = 0;
+  const size_t cells = size_t(f->sx) * f->sy;
+  for (int r = 0; r < n; ++r) {
+    const float pos[3] = {(float)poses[3 * r], (float)poses[3 * r + 1], (float)poses[3 * r + 2]};
+    const float vel[3] = {(float)vels[3 * r], (float)vels[3 * r + 1], (float)vels[3 * r + 2]};
+    const float goal[2] = {(float)f->plan[r].back().x, (float)f->plan[r].back().y};
+    const Samples s = enumerate_samples(c, pos, vel, goal);
+    if (s.v.size() > (size_t)kInlineSamples) return fail(NAVGPU_ERR_UNSUPPORTED, "more than %d per-axis samples per robot", kInlineSamples);
+    FleetRobot& R = f->h_robots[r];
+    R.grids.g = DwaGeom{f->d_master + size_t(r) * f->stride * f->pitch, f->sx, f->sy, f->pitch, f->res,
+                        f->origins[2 * r], f->origins[2 * r + 1], 1.0 / f->res};
+    uint32_t* dist = f->d_dist + size_t(r) * 4 * cells;
+    const P2* plans = reinterpret_cast<const P2*>(f->d_plans);
+    R.grids.job[0] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r]), (int)f->adj_path[r].size(), 0, dist};
+    R.grids.job[1] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r]), (int)f->adj_path[r].size(), 1, dist + cells};
+    R.grids.job[2] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 1]), (int)f->adj_front[r].size(), 1, dist + 2 * cells};
+    R.grids.job[3] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 2]), (int)f->adj_align[r].size(), 0, dist + 3 * cells};
+    for (int k = 0; k < 3; ++k) { R.pos[k] = pos[k]; R.vel[k] = vel[k]; }
+    R.osc_mask = f->osc[r].mask();
+    R.scale_alignment = f->align_scale[r];
+    R.nx = s.nx; R.ny = s.ny; R.nth = s.nth;
+    R.samples_offset = (int)samples.size();
+    samples.insert(samples.end(), s.v.begin(), s.v.end());
+    max_samples = std::max(max_samples, s.nx * s.ny * s.nth);
+  }
+  if (samples.size() > f->samples_capacity) {
+    if (f->d_samples) cudaFree(f->d_samples);
+    f->d_samples = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&f->d_samples, samples.size() * 2 * sizeof(float)));
+    f->samples_capacity = samples.size() * 2;
+  }
+  NAVGPU_CUDA(cudaMemcpyAsync(f->d_samples, samples.data(), samples.size() * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(f->d_robots, f->h_robots.data(), sizeof(FleetRobot) * n, cudaMemcpyHostToDevice, f->stream));
+  const int bpr = (max_samples + kDwaWarpsPerBlock - 1) / kDwaWarpsPerBlock;
+  const size_t blocks = size_t(bpr) * n;
+  if (blocks > f->blocks_capacity) {
+    if (f->d_block_cost) cudaFree(f->d_block_cost);
+    if (f->d_block_index) cudaFree(f->d_block_index);
+    f->d_block_cost = nullptr; f->d_block_index = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&f->d_block_cost, blocks * sizeof(double)));
+    NAVGPU_CUDA(cudaMalloc(&f->d_block_index, blocks * sizeof(long long)));
+    f->blocks_capacity = blocks;
+  }
+  if (blocks > 0x7fffffffull) return fail(NAVGPU_ERR_UNSUPPORTED, "too many samples in one fleet launch");
+
+  // ---- 4 MapGrid wavefronts per robot, one launch
+  navgpu_dwa tmp;  // geometry carrier for launch_mapgrid
+  tmp.sx = f->sx; tmp.sy = f->sy; tmp.stream = f->stream;
+  MapGridArgs ma;
+  memset(&ma, 0, sizeof(ma));
+  ma.g = DwaGeom{nullptr, f->sx, f->sy, f->pitch, f->res, 0.0, 0.0, 1.0 / f->res};
+  ma.allow_unknown = c.allow_unknown;
+  ma.fleet = f->d_robots;
+  NAVGPU_TRY(launch_mapgrid(&tmp, ma, 4 * n, 4));
+
+  // ---- rollouts + critics + per-robot argmin
+  DwaScoreArgs base;
+  memset(&base, 0, sizeof(base));
+  base.g = ma.g;
+  base.acc[0] = (float)c.acc_lim_x; base.acc[1] = (float)c.acc_lim_y; base.acc[2] = (float)c.acc_lim_theta;
+  base.min_trans_vel = c.min_trans_vel; base.max_trans_vel = c.max_trans_vel; base.min_rot_vel = c.min_rot_vel;
+  base.sim_time = c.sim_time; base.sim_granularity = c.sim_granularity; base.angular_sim_granularity = c.angular_sim_granularity;
+  base.use_dwa = c.use_dwa; base.sum_scores = c.sum_scores; base.allow_unknown = c.allow_unknown;
+  base.scale_obstacle = f->obstacle_scale;
+  base.scale_goal_front = f->goal_scale;
+  base.scale_path = f->path_scale;
+  base.scale_goal = f->goal_scale;
+  base.xshift = c.forward_point_distance;
+  base.nfp = (int)(f->footprint.size() / 2);
+  for (int k = 0; k < base.nfp; ++k) { base.fpx[k] = f->footprint[2 * k]; base.fpy[k] = f->footprint[2 * k + 1]; }
+  k_fleet_score<<<(unsigned)blocks, kDwaWarpsPerBlock * 32, 0, f->stream>>>(base, f->d_robots, f->d_samples, bpr, f->d_block_cost,
+                                                                          f->d_block_index, f->d_generated);
+  k_fleet_finish<<<n, 32, 0, f->stream>>>(base, f->d_robots, f->d_samples, bpr, f->d_block_cost, f->d_block_index,
+                                          f->d_generated, f->d_results);
+  NAVGPU_LAUNCHED(2);
+  NAVGPU_CUDA(cudaGetLastError());
+  NAVGPU_CUDA(cudaMemcpyAsync(f->h_results, f->d_results, sizeof(DwaDeviceResult) * n, cudaMemcpyDeviceToHost, f->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(f->stream));
+
+  // ---- host epilogue per robot: result_traj_ bookkeeping + oscillation flags (dwa_planner.cpp:316-357)
+  for (int r = 0; r < n; ++r) {
+    const DwaDeviceResult& d = f->h_results[r];
+    if (d.cost >= 0) { f->res_v[3 * r] = d.xv; f->res_v[3 * r + 1] = d.yv; f->res_v[3 * r + 2] = d.thetav; }
+    const float pos[3] = {(float)poses[3 * r], (float)poses[3 * r + 1], (float)poses[3 * r + 2]};
+    f->osc[r].update(pos, d.cost, f->res_v[3 * r], f->res_v[3 * r + 1], f->res_v[3 * r + 2], c.min_trans_vel,
+                     c.oscillation_reset_dist, c.oscillation_reset_angle);
+    navgpu_dwa_result& o = results[r];
+    o.cost = d.cost;
+    o.xv = f->res_v[3 * r]; o.yv = f->res_v[3 * r + 1]; o.thetav = f->res_v[3 * r + 2];
+    o.best_index = (int32_t)d.best_index;
+    o.n_samples = f->h_robots[r].nx * f->h_robots[r].ny * f->h_robots[r].nth;
+    o.n_scored = d.n_scored;
+    o.n_points = 0;
+  }
+  return NAVGPU_OK;
+}
+
+// inflated local costmap of one robot (HOST, size_y x size_x), for parity checks
+int navgpu_fleet_get_costmap(navgpu_fleet* f, int robot, uint8_t* host_out) {
+  if (!f || robot < 0 || robot >= f->n || !host_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  return navgpu_costmap_get_window(f->costmap, 0, (int)(robot * f->stride), (int)f->sx, (int)(robot * f->stride + f->sy), host_out);
+}
+
+int navgpu_fleet_get_oscillation_mask(navgpu_fleet* f, int robot, int* mask_out) {
+  if (!f || robot < 0 || robot >= f->n || !mask_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  *mask_out = f->osc[robot].mask();
+  return NAVGPU_OK;
+}
 
 }  // extern "C"

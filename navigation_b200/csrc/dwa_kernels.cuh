@@ -4,6 +4,8 @@
 // sequences the kernels per DWAPlanner::findBestPath is in dwa.cu.
 #pragma once
 
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace navgpu {
@@ -55,10 +57,24 @@ struct MapGridJob {
   int local_goal;  // setLocalGoal (last seed only) vs setTargetCells
   uint32_t* dist;  // sx*sy, row-major, no pitch
 };
-struct MapGridArgs {
+struct MapGridRobot {  // fleet mode: one per robot, in device memory
   DwaGeom g;
+  MapGridJob job[4];
+};
+struct FleetRobot {
+  MapGridRobot grids;  // geometry + the four MapGrid jobs (dist pointers are the robot's distance grids)
+  float pos[3], vel[3];
+  int osc_mask;
+  double scale_alignment;  // 0 once the robot is within forward_point_distance of its goal (dwa_planner.cpp:277-285)
+  int nx, ny, nth;
+  int samples_offset;  // into the fleet's float sample array: xs | ys | ths of this robot
+};
+
+struct MapGridArgs {
+  DwaGeom g;  // fleet mode: only sx, sy, res of it are used (shared by all robots)
   int allow_unknown;
   MapGridJob job[4];
+  const FleetRobot* fleet;  // null: single planner (g, job above); else CTA b serves robot b / jobs_per_robot
 };
 
 constexpr int kMapGridThreads = 512;
@@ -156,8 +172,9 @@ __device__ __forceinline__ uint32_t mapgrid_passable(const DwaGeom& g, int allow
 template <int kWPT>
 __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapGridArgs a, int jobs_per_robot, int planes) {
   extern __shared__ uint32_t mg_smem[];
-  const MapGridJob job = a.job[blockIdx.x % jobs_per_robot];
-  const DwaGeom g = a.g;
+  const MapGridJob job = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.job[blockIdx.x % jobs_per_robot]
+                                 : a.job[blockIdx.x % jobs_per_robot];
+  const DwaGeom g = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.g : a.g;
   const int W = (g.sx + 31) / 32, NW = W * (int)g.sy;
   uint32_t* F0 = mg_smem;  // NW words + one that stays zero
   uint32_t* F1 = F0 + NW + 1;
@@ -267,8 +284,9 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapG
 // distances written as cells are touched.
 __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare(MapGridArgs a, int jobs_per_robot) {
   extern __shared__ uint32_t mg_smem[];
-  const MapGridJob job = a.job[blockIdx.x % jobs_per_robot];
-  const DwaGeom g = a.g;
+  const MapGridJob job = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.job[blockIdx.x % jobs_per_robot]
+                                 : a.job[blockIdx.x % jobs_per_robot];
+  const DwaGeom g = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.g : a.g;
   const int W = (g.sx + 31) / 32, NW = W * (int)g.sy;
   uint32_t* P = mg_smem;
   uint32_t* V = P + NW;
@@ -686,15 +704,15 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
 // `cost` is the total the scoring pass found for it.  idx < 0: nothing valid (result_traj_.cost_ = -7,
 // dwa_planner.cpp:316).
 __device__ void finish_winner(const DwaScoreArgs& a, long long idx, double cost, DwaDeviceResult* out, double* points,
-                              int points_capacity, double* warp_scratch) {
+                              int points_capacity, double* warp_scratch, unsigned* n_generated) {
   const int lane = threadIdx.x & 31;
   TrajResult r;
   r.generated = false;
   r.num_steps = 0;
   if (idx >= 0) r = score_sample<false>(a, idx, lane, nullptr, points, points_capacity, warp_scratch);
   if (lane == 0) {
-    out->n_scored = (int)a.counters[1];
-    a.counters[1] = 0;
+    out->n_scored = (int)*n_generated;  // samples the generator accepted; re-armed for the next search
+    *n_generated = 0;
     if (idx >= 0 && r.generated && cost >= 0) {
       const int ith = (int)(idx % a.nth);
       const long long t1 = idx / a.nth;
@@ -818,14 +836,15 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreAr
   }
   if (a.finish_out == nullptr) return;
   __syncthreads();
-  if (warp == 0) finish_winner(a, s_index[0], s_cost[0], a.finish_out, a.finish_points, a.finish_capacity, s_scratch[0]);
+  if (warp == 0)
+    finish_winner(a, s_index[0], s_cost[0], a.finish_out, a.finish_points, a.finish_capacity, s_scratch[0], &a.counters[1]);
 }
 
 // stand-alone finish for sharded sweeps: the winner was chosen from the all-gathered per-rank minima
 __global__ void k_dwa_finish(DwaScoreArgs a, long long forced_index, double forced_cost, DwaDeviceResult* out,
                              double* points, int points_capacity) {
   __shared__ double s_scratch[kWarpScratchDoubles];
-  finish_winner(a, forced_index, forced_cost, out, points, points_capacity, s_scratch);
+  finish_winner(a, forced_index, forced_cost, out, points, points_capacity, s_scratch, &a.counters[1]);
 }
 
 // all_explored costs exactly as the sequential search reports them (simple_scored_sampling_planner.cpp:50-79,
@@ -882,6 +901,127 @@ __global__ void k_dwa_report(const double* __restrict__ terms, double* __restric
     }
     __syncthreads();
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fleet mode (config C5): many independent robots, each with its own local costmap, plan, pose, velocity and
+// oscillation mask, scored in ONE launch.  A CTA serves one robot: it copies the shared DwaScoreArgs into shared
+// memory, patches the robot's fields in, and runs the very same score_sample as the single-planner kernel.
+__device__ __forceinline__ void fleet_patch_args(DwaScoreArgs& s_a, const DwaScoreArgs& base, const FleetRobot& r,
+                                                 const float* samples) {
+  // cooperative word copy of the shared arguments, then the robot's own fields
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&base);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&s_a);
+  constexpr int kHeadWords = (int)(offsetof(DwaScoreArgs, samples_inline) / 4);
+  constexpr int kTailStart = (int)((offsetof(DwaScoreArgs, samples_inline) + sizeof(float) * kInlineSamples) / 4);
+  constexpr int kWords = (int)(sizeof(DwaScoreArgs) / 4);
+  for (int i = threadIdx.x; i < kHeadWords; i += blockDim.x) dst[i] = src[i];
+  for (int i = kTailStart + threadIdx.x; i < kWords; i += blockDim.x) dst[i] = src[i];
+  const int n_s = r.nx + r.ny + r.nth;
+  for (int i = threadIdx.x; i < n_s; i += blockDim.x) s_a.samples_inline[i] = samples[r.samples_offset + i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_a.g = r.grids.g;
+    for (int k = 0; k < 4; ++k) s_a.dist[k] = r.grids.job[k].dist;
+    s_a.nx = r.nx; s_a.ny = r.ny; s_a.nth = r.nth;
+    s_a.inline_samples = 1;
+    for (int k = 0; k < 3; ++k) { s_a.pos[k] = r.pos[k]; s_a.vel[k] = r.vel[k]; }
+    s_a.osc_mask = r.osc_mask;
+    s_a.scale_alignment = r.scale_alignment;
+    s_a.begin = 0;
+    s_a.end = (long long)r.nx * r.ny * r.nth;
+    s_a.all_terms = nullptr;
+    s_a.finish_out = nullptr;
+  }
+  __syncthreads();
+}
+
+// grid = n_robots * blocks_per_robot CTAs; per CTA the (cost, index) minimum of its 8 samples
+__global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_fleet_score(DwaScoreArgs base, const FleetRobot* robots,
+                                                                        const float* samples, int blocks_per_robot,
+                                                                        double* block_cost, long long* block_index,
+                                                                        unsigned* generated) {
+  __shared__ DwaScoreArgs s_a;
+  __shared__ double s_cost[kDwaWarpsPerBlock];
+  __shared__ long long s_index[kDwaWarpsPerBlock];
+  __shared__ int s_generated[kDwaWarpsPerBlock];
+  __shared__ double s_scratch[kDwaWarpsPerBlock][kWarpScratchDoubles];
+  const int robot = blockIdx.x / blocks_per_robot, local = blockIdx.x % blocks_per_robot;
+  const FleetRobot& r = robots[robot];
+  if ((long long)local * kDwaWarpsPerBlock >= (long long)r.nx * r.ny * r.nth) {  // no samples for this CTA
+    if (threadIdx.x == 0) {
+      block_cost[blockIdx.x] = INFINITY;
+      block_index[blockIdx.x] = -1;
+    }
+    return;
+  }
+  fleet_patch_args(s_a, base, r, samples);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long sample = (long long)local * kDwaWarpsPerBlock + warp;
+  double cost = INFINITY;
+  long long index = -1;
+  int gen = 0;
+  if (sample < s_a.end) {
+    const TrajResult t = score_sample<true>(s_a, sample, lane, nullptr, nullptr, 0, s_scratch[warp]);
+    gen = t.generated;
+    if (t.generated && t.cost >= 0) {
+      cost = t.cost;
+      index = sample;
+    }
+  }
+  if (lane == 0) {
+    s_cost[warp] = cost;
+    s_index[warp] = index;
+    s_generated[warp] = gen;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bc = INFINITY;
+    long long bi = -1;
+    int g = 0;
+    for (int wdx = 0; wdx < kDwaWarpsPerBlock; ++wdx) {
+      g += s_generated[wdx];
+      if (s_index[wdx] >= 0 && (bi < 0 || better(s_cost[wdx], s_index[wdx], bc, bi))) {
+        bc = s_cost[wdx];
+        bi = s_index[wdx];
+      }
+    }
+    block_cost[blockIdx.x] = bc;
+    block_index[blockIdx.x] = bi;
+    if (g) atomicAdd(&generated[robot], (unsigned)g);
+  }
+}
+
+// one warp (= one CTA) per robot: reduce its CTAs' minima with the first-strictly-smaller rule and fill the result
+__global__ void __launch_bounds__(32) k_fleet_finish(DwaScoreArgs base, const FleetRobot* robots, const float* samples,
+                                                     int blocks_per_robot, const double* block_cost,
+                                                     const long long* block_index, unsigned* generated,
+                                                     DwaDeviceResult* results) {
+  __shared__ DwaScoreArgs s_a;
+  __shared__ double s_scratch[kWarpScratchDoubles];
+  const int robot = blockIdx.x, lane = threadIdx.x;
+  fleet_patch_args(s_a, base, robots[robot], samples);
+  double bc = INFINITY;
+  long long bi = -1;
+  for (int i = lane; i < blocks_per_robot; i += 32) {
+    const double c = block_cost[(size_t)robot * blocks_per_robot + i];
+    const long long ix = block_index[(size_t)robot * blocks_per_robot + i];
+    if (ix >= 0 && (bi < 0 || better(c, ix, bc, bi))) {
+      bc = c;
+      bi = ix;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (bi < 0 || better(oc, oi, bc, bi))) {
+      bc = oc;
+      bi = oi;
+    }
+  }
+  finish_winner(s_a, bi, bc, results + robot, nullptr, 0, s_scratch, generated + robot);
 }
 
 }  // namespace navgpu

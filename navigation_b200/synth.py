@@ -91,3 +91,26 @@ def blocks_c1(size=400, seed=1, adversarial=False):
     if adversarial:
         g[rng.random((size, size)) < 0.01] = LETHAL
     return g
+
+
+def fleet_robot(robot_id, n=120, res=0.05):
+    """Config C5: the independent inputs of one robot of the fleet, seeded by its id -- a raw (un-inflated) n x n local
+    map made of thick axis-aligned structure (corridor walls and boxes; the class on which the reference's inflation
+    is tie-order independent), its world origin, pose, velocity and a plan through it."""
+    rng = np.random.default_rng(1_000_003 * 7 + robot_id)
+    raw = np.zeros((n, n), np.uint8)
+    lo, hi = int(n * rng.uniform(0.15, 0.3)), int(n * rng.uniform(0.7, 0.85))
+    raw[lo - 4:lo - 1, :] = 254
+    raw[hi + 1:hi + 4, :] = 254
+    for _ in range(int(rng.integers(1, 4))):
+        bx, by = int(rng.integers(n // 2, n - 12)), int(rng.integers(lo + 6, hi - 12))
+        w, h = int(rng.integers(3, 9)), int(rng.integers(3, 9))
+        raw[by:by + h, bx:bx + w] = 254
+    ox, oy = float(rng.uniform(-50, 50)), float(rng.uniform(-50, 50))
+    size = n * res
+    mid = oy + (lo + hi) / 2 * res
+    pose = (ox + size * rng.uniform(0.15, 0.35), mid + rng.uniform(-0.3, 0.3), float(rng.uniform(-0.4, 0.4)))
+    vel = (float(rng.uniform(0.0, 0.5)), 0.0, float(rng.uniform(-0.4, 0.4)))
+    t = np.linspace(-0.05, 1.2, int(rng.integers(40, 160)))
+    plan = np.stack([pose[0] + t * size * 0.75, mid + 0.25 * np.sin(t * rng.uniform(1, 3)) * rng.uniform(0, 1)], 1)
+    return dict(raw=raw, origin=(ox, oy), pose=pose, vel=vel, plan=plan)
