@@ -35,7 +35,8 @@ ALGO_BYTES_PER_CELL = 3  # read static + read obstacle + write master (SURVEY.md
 TRAFFIC_BYTES = None
 METRIC = "ms per updateMap+inflation @4k^2 grid; DWA trajectories scored/sec"
 WORKLOAD = ("C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, 10 m raytrace+mark) + "
-            "inflation 1.0 m (R=20); DWA half: C2 findBestPath 20x1x20 and C4 sweep 200x20x200 on a 120x120 local map")
+            "inflation 1.0 m (R=20); DWA half: C2 findBestPath 20x1x20, C4 sweep 200x20x200 on a 120x120 local map, "
+            "C5 fleet of 4096 robots (local-map inflation + 20x1x20 scoring each)")
 
 
 def env_int(name, default):
@@ -210,6 +211,7 @@ def run_reference(args, rank):
     }
     if not args.no_dwa:
         line["dwa"] = dwa_cpu_numbers()
+        line["dwa"]["c5"] = fleet_cpu_numbers()
     print(json.dumps(line), flush=True)
 
 
@@ -251,19 +253,16 @@ def run_native_dwa(api, torch, dist, rank, world, local_rank, steps):
 
     d4, pose, vel = dwa_setup(api, grid, C4, device=local_rank)
     stream = torch.cuda.ExternalStream(d4.stream(), device=local_rank)
+    from navigation_b200 import sharding
     c, i, total = d4.score_range(pose, vel, PENTAGON, 0, 1)
-    lo, hi = (total * rank) // world, (total * (rank + 1)) // world
-    buf = torch.zeros(2, dtype=torch.float64, device=dev)
-    gathered = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+    lo, hi = sharding.split_range(total, rank, world)
 
     def one_sweep():
         c, i, _ = d4.score_range(pose, vel, PENTAGON, lo, hi)
         if dist is None:
             return d4.finish_sharded(pose, [c], [i])
-        buf[0], buf[1] = c, float(i)  # indices < 2^53 are exact in fp64
-        dist.all_gather_into_tensor(gathered, buf)
-        g = gathered.cpu().numpy().reshape(world, 2)
-        return d4.finish_sharded(pose, g[:, 0], g[:, 1].astype(np.int64))
+        costs, indices = sharding.allgather_minima(dist, torch, c, i, dev)  # NCCL, 16 bytes per rank
+        return d4.finish_sharded(pose, costs, indices)
 
     for _ in range(3):
         r4 = one_sweep()
@@ -289,6 +288,93 @@ def run_native_dwa(api, torch, dist, rank, world, local_rank, steps):
                 "c4_sharding": f"sample range split over {world} rank(s), all_gather of (cost, index)" if world > 1
                 else "single GPU"})
     return out
+
+
+C5 = dict(n_robots=4096, n=120, resolution=0.05, vx_samples=20, vy_samples=1, vth_samples=20)
+
+
+def fleet_inputs(ids):
+    from navigation_b200 import synth
+    robots = [synth.fleet_robot(i) for i in ids]
+    return (np.stack([r["raw"] for r in robots]), np.array([r["origin"] for r in robots]),
+            np.array([r["pose"] for r in robots]), np.array([r["vel"] for r in robots]), [r["plan"] for r in robots])
+
+
+def run_native_fleet(api, torch, dist, rank, world, local_rank, steps):
+    """C5: 4096 independent robots per control cycle, partitioned over the ranks (no collective): every robot's raw
+    local map is inflated and its 20 x 1 x 20 velocity samples are scored.  Timed through the C ABI with host buffers:
+    `step` = poses/velocities in, results out (maps already resident); `e2e` additionally uploads all raw maps."""
+    from navigation_b200 import sharding
+    n_total = C5["n_robots"]
+    lo, hi = sharding.split_range(n_total, rank, world)
+    raw, origins, poses, vels, plans = fleet_inputs(range(lo, hi))
+    fleet = api.fleet(hi - lo, 120, 120, 0.05, PENTAGON, 0.55, 10.0, device=local_rank, vx_samples=C5["vx_samples"],
+                      vy_samples=C5["vy_samples"], vth_samples=C5["vth_samples"], max_vel_y=0.0, min_vel_y=0.0)
+    fleet.set_maps(raw, origins)
+    fleet.set_plans(poses, plans)
+    poses = np.ascontiguousarray(poses)
+    vels = np.ascontiguousarray(vels)
+    for _ in range(3):
+        fleet.step_raw(poses, vels)
+    reps = max(5, min(steps, 10))
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        if dist is not None:
+            t = torch.tensor([dt], device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    step_s = timed(lambda: fleet.step_raw(poses, vels))
+
+    def full():
+        fleet.set_maps(raw, origins)
+        fleet.step_raw(poses, vels)
+    e2e_s = timed(full)
+    res = fleet.step(poses, vels)
+    n_traj = sum(r["n_samples"] for r in res)
+    n_valid = sum(r["cost"] >= 0 for r in res)
+    if dist is not None:
+        t = torch.tensor([float(n_traj), float(n_valid)], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t)
+        n_traj, n_valid = int(t[0].item()), int(t[1].item())
+    return {"c5_robots": n_total, "c5_cycle_ms": 1e3 * step_s, "c5_robot_cycles_per_s": n_total / step_s,
+            "c5_traj_per_s": n_traj / step_s, "c5_e2e_cycle_ms": 1e3 * e2e_s,
+            "c5_e2e_robot_cycles_per_s": n_total / e2e_s, "c5_h2d_bytes_per_e2e_cycle": int(raw.nbytes) * world,
+            "c5_partitioning": f"robots split over {world} rank(s), no collective" if world > 1 else "single GPU",
+            "c5_valid_robots": int(n_valid)}
+
+
+def fleet_cpu_numbers(n_robots=8):
+    """The reference's CPU code on a few fleet robots: LayeredCostmap inflation + findBestPath per robot, one core."""
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.available("reference") else "port"
+    api = pyoracle.load(kind)
+    raw, origins, poses, vels, plans = fleet_inputs(range(n_robots))
+    t0 = time.perf_counter()
+    for i in range(n_robots):
+        cm = api.costmap(120, 120, 0.05, *origins[i])
+        s = cm.add_grid_layer(0)
+        cm.add_inflation_layer(0.55, 10.0)
+        cm.set_footprint(PENTAGON)
+        cm.set_grid_layer(s, raw[i])
+        cm.update_map(0, 0, 0)
+        d = api.dwa(120, 120, 0.05, vx_samples=C5["vx_samples"], vy_samples=C5["vy_samples"],
+                    vth_samples=C5["vth_samples"], max_vel_y=0.0, min_vel_y=0.0)
+        d.set_costmap(cm.get(), *origins[i])
+        d.set_plan(poses[i], plans[i])
+        d.find_best_path(poses[i], vels[i], PENTAGON)
+    dt = time.perf_counter() - t0
+    return {"kind": kind, "cores": 1, "c5_robot_cycles_per_s": n_robots / dt,
+            "sample": f"{n_robots} fleet robots (inflation + findBestPath each), single thread"}
 
 
 def run_native(args, rank, world, local_rank):
@@ -392,10 +478,11 @@ def run_native(args, rank, world, local_rank):
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
     e2e_ms = max(e0.elapsed_time(e1) / args.steps, e2e_wall_ms)
-    clocks = sampler.summary()
-
     dwa = None if args.no_dwa else run_native_dwa(api, torch, dist, rank, world, local_rank, args.steps)
+    if dwa is not None:
+        dwa.update(run_native_fleet(api, torch, dist, rank, world, local_rank, args.steps))
     launches = api.launch_count() - launches0 if not args.no_dwa else launches
+    clocks = sampler.summary()
 
     if dist is not None:
         t = torch.tensor([ms_per_step, e2e_ms, hot_ms, float(np.mean(sweep_ms)), float(np.mean(merge_ms)),
@@ -434,6 +521,7 @@ def run_native(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu_baseline_c3()
             if dwa is not None:
                 line["dwa"]["cpu_baseline"] = dwa_cpu_numbers()
+                line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers()})
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

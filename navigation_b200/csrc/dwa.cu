@@ -665,6 +665,7 @@ struct navgpu_fleet {
   navgpu_costmap* costmap = nullptr;
   int static_layer = -1;
   cudaStream_t stream = nullptr;  // the costmap's stream
+  uint8_t* d_raw = nullptr;       // n x sy x sx: the raw maps as they arrive from the host
   uint8_t* d_stage = nullptr;     // n x stride x pitch staging of the raw maps (pad rows stay zero)
   unsigned pitch = 0;
   const uint8_t* d_master = nullptr;
@@ -728,6 +729,7 @@ int navgpu_fleet_create(navgpu_fleet** out, int n_robots, const navgpu_dwa_confi
   const size_t stage_bytes = size_t(pitch) * f->stride * n_robots;
   NAVGPU_CUDA(cudaMalloc(&f->d_stage, stage_bytes));
   NAVGPU_CUDA(cudaMemset(f->d_stage, 0, stage_bytes));
+  NAVGPU_CUDA(cudaMalloc(&f->d_raw, size_t(n_robots) * size_y * size_x));
   NAVGPU_CUDA(cudaMalloc(&f->d_robots, sizeof(FleetRobot) * n_robots));
   NAVGPU_CUDA(cudaMalloc(&f->d_dist, size_t(n_robots) * 4 * size_x * size_y * sizeof(uint32_t)));
   NAVGPU_CUDA(cudaMalloc(&f->d_generated, sizeof(unsigned) * n_robots));
@@ -748,7 +750,7 @@ int navgpu_fleet_destroy(navgpu_fleet* f) {
   if (!f) return NAVGPU_OK;
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
-  cudaFree(f->d_stage); cudaFree(f->d_robots); cudaFree(f->d_plans); cudaFree(f->d_samples); cudaFree(f->d_dist);
+  cudaFree(f->d_stage); cudaFree(f->d_raw); cudaFree(f->d_robots); cudaFree(f->d_plans); cudaFree(f->d_samples); cudaFree(f->d_dist);
   cudaFree(f->d_block_cost); cudaFree(f->d_block_index); cudaFree(f->d_generated); cudaFree(f->d_results);
   cudaFreeHost(f->h_results);
   navgpu_costmap_destroy(f->costmap);
@@ -761,13 +763,16 @@ int navgpu_fleet_set_maps(navgpu_fleet* f, const uint8_t* raw_maps, const double
   if (!f || !raw_maps || !origins_xy) return fail(NAVGPU_ERR_INVALID, "bad arguments");
   NAVGPU_CUDA(cudaSetDevice(f->device));
   f->origins.assign(origins_xy, origins_xy + size_t(2) * f->n);
-  cudaMemcpy3DParms p;
-  memset(&p, 0, sizeof(p));
-  p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(raw_maps), f->sx, f->sx, f->sy);
-  p.dstPtr = make_cudaPitchedPtr(f->d_stage, f->pitch, f->sx, f->stride);
-  p.extent = make_cudaExtent(f->sx, f->sy, f->n);
-  p.kind = cudaMemcpyHostToDevice;
-  NAVGPU_CUDA(cudaMemcpy3DAsync(&p, f->stream));
+  // one contiguous H2D copy, then a device-side scatter into the padded stack
+  const size_t raw_bytes = size_t(f->n) * f->sy * f->sx;
+  NAVGPU_CUDA(cudaMemcpyAsync(f->d_raw, raw_maps, raw_bytes, cudaMemcpyHostToDevice, f->stream));
+  {
+    dim3 block(32, 8);
+    const size_t rows = size_t(f->n) * f->sy;
+    k_fleet_scatter_maps<<<(unsigned)((rows + 7) / 8), block, 0, f->stream>>>(f->d_raw, f->d_stage, f->sx, f->sy, f->stride,
+                                                                             f->pitch, (unsigned)f->n);
+    NAVGPU_LAUNCHED(1);
+  }
   NAVGPU_TRY(navgpu_grid_layer_set_device(f->costmap, f->static_layer, f->d_stage, f->pitch));
   NAVGPU_CUDA(cudaStreamSynchronize(f->stream));  // raw_maps may be pageable
   return NAVGPU_OK;

@@ -993,6 +993,23 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_fleet_score(DwaScore
   }
 }
 
+// raw local maps [n][sy][sx] (contiguous) -> the stacked, padded layer grid: robot r's row y lands on row
+// r * stride + y with row pitch `pitch`; pad rows and pad columns are never written (they stay zero)
+__global__ void k_fleet_scatter_maps(const uint8_t* __restrict__ raw, uint8_t* __restrict__ stacked, unsigned sx,
+                                     unsigned sy, unsigned stride, unsigned pitch, unsigned n) {
+  const size_t row = (size_t)blockIdx.x * blockDim.y + threadIdx.y;  // row over all robots
+  if (row >= (size_t)n * sy) return;
+  const unsigned r = (unsigned)(row / sy), y = (unsigned)(row - (size_t)r * sy);
+  const uint8_t* src = raw + row * sx;
+  uint8_t* dst = stacked + ((size_t)r * stride + y) * pitch;
+  if ((sx & 3u) == 0 && (((size_t)src) & 3u) == 0) {
+    for (unsigned x = threadIdx.x * 4; x < sx; x += blockDim.x * 4)
+      *reinterpret_cast<uint32_t*>(dst + x) = *reinterpret_cast<const uint32_t*>(src + x);
+  } else {
+    for (unsigned x = threadIdx.x; x < sx; x += blockDim.x) dst[x] = src[x];
+  }
+}
+
 // one warp (= one CTA) per robot: reduce its CTAs' minima with the first-strictly-smaller rule and fill the result
 __global__ void __launch_bounds__(32) k_fleet_finish(DwaScoreArgs base, const FleetRobot* robots, const float* samples,
                                                      int blocks_per_robot, const double* block_cost,

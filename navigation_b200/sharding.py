@@ -1,0 +1,48 @@
+"""Host-side partitioning of the two workloads that shard; torch.distributed is plumbing only.
+
+* Dense rollout sweep (config C4): the enumerated velocity samples (x outer, y, theta inner -- the reference's order and
+  therefore its tie-break order, simple_trajectory_generator.cpp:121-133) are split into contiguous index ranges, one
+  per rank; every rank scores its range on its GPU and contributes one 16-byte (cost, global index) minimum; after one
+  all-gather every rank applies the same rule the sequential search applies (first strictly smaller cost ==
+  smallest cost, lowest index on ties, simple_scored_sampling_planner.cpp:111-116).
+* Fleet (config C5): robots are independent; rank r owns robots [n*r/G, n*(r+1)/G).  No collective on the data path.
+"""
+import numpy as np
+
+
+def split_range(total, rank, world):
+    """Contiguous share [lo, hi) of `total` items for `rank` of `world`."""
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
+def local_minimum(costs, begin=0):
+    """(cost, global index) of the first strictly smallest valid cost of a slice; (inf, -1) when none is valid.
+    `costs` follows the C ABI's all_costs convention: NaN = not generated, negative = rejected."""
+    c = np.asarray(costs, dtype=np.float64)
+    valid = ~np.isnan(c) & (c >= 0)
+    if not valid.any():
+        return float("inf"), -1
+    masked = np.where(valid, c, np.inf)
+    i = int(np.argmin(masked))  # argmin returns the first of equal minima
+    return float(masked[i]), begin + i
+
+
+def pick_winner(costs, indices):
+    """Winner among per-rank minima: smallest cost, lowest sample index on ties; (inf, -1) when every rank has none.
+    Identical to navgpu_dwa_finish_sharded's host rule."""
+    best_c, best_i = float("inf"), -1
+    for c, i in zip(costs, indices):
+        i = int(i)
+        if i >= 0 and (best_i < 0 or c < best_c or (c == best_c and i < best_i)):
+            best_c, best_i = float(c), i
+    return best_c, best_i
+
+
+def allgather_minima(dist, torch, cost, index, device):
+    """All-gather of one (cost, index) pair per rank.  The index travels as fp64 (exact below 2^53)."""
+    world = dist.get_world_size()
+    buf = torch.tensor([cost, float(index)], dtype=torch.float64, device=device)
+    out = torch.zeros(2 * world, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, buf)
+    g = out.cpu().numpy().reshape(world, 2)
+    return g[:, 0].copy(), g[:, 1].astype(np.int64)
