@@ -21,13 +21,26 @@ struct DwaGeom {
   double inv_res;  // 1 / res, only ever used through exact_cell
 };
 
-// (int)(d / res) exactly as IEEE division + truncation would give it, without paying for the division on the common
-// path: d * (1/res) is within a few ulp of d / res, so the truncated integers can only differ when the quotient is
-// within 1e-9 (relative) of an integer -- only then is the real division evaluated.
+// (int)(d / res) exactly as IEEE division + truncation gives it, without the fp64 division.
+// Fast path: q = d * (1/res) is within a few ulp of d / res, so truncation agrees unless the quotient is within 1e-9
+// (relative) of an integer r.  Near an integer the decision is made exactly: e = fma(-r, res, d) is the exact value
+// of d - r * res (it has at most ~38 significant bits there), so the real quotient is r + e / res.  e >= 0 gives r.
+// For e < 0 the correctly rounded quotient still reaches r when r - d/res is at most half the spacing of the doubles
+// just below r (a tie rounds to r, whose mantissa is even), i.e. -e <= 2^(k-53) * res with k = floor(log2 r), one less
+// when r is a power of two; otherwise the result is r - 1.  (Poses laid out on the grid -- x = 1.5 at 0.05 m cells --
+// sit exactly on such borders, so this path is common, not exotic.)
 __device__ __forceinline__ int exact_cell(double d, double res, double inv_res) {
   const double q = d * inv_res;
   const double r = rint(q);
-  if (fabs(q - r) <= 1e-9 * fmax(1.0, fabs(q))) return (int)(d / res);
+  if (fabs(q - r) <= 1e-9 * fmax(1.0, fabs(q))) {
+    const int ri = (int)r;
+    if (ri <= 0) return (int)(d / res);  // d within 1e-9 cells of the origin: keep the division
+    const double e = fma(-r, res, d);
+    if (e >= 0.0) return ri;
+    const int k = 31 - __clz(ri) - (((ri & (ri - 1)) == 0) ? 1 : 0);
+    const double half_spacing = __longlong_as_double((long long)(1023 + k - 53) << 52);  // 2^(k - 53)
+    return (-e <= half_spacing * res) ? ri : ri - 1;
+  }
   return (int)q;
 }
 

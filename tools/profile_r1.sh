@@ -1,11 +1,12 @@
 #!/bin/bash
-# ncu captures for profiles/ (run under gpurun, one GPU). Every ncu command is preceded by the same command run plain.
-set -x
+# All ncu captures behind profiles/ (run under gpurun on one GPU).  Each ncu command follows a plain run of the same
+# command line that exited 0 (tools/profile_kernel.sh / tools/profile_launches.sh do that).
 export PROBE_REPS=3
-python tools/probe_sweep.py > gpurun_out/plain_sweep.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_update_costs_fast -s 6 -c 2 -f -o gpurun_out/prof_sweep_r1 python tools/probe_sweep.py > gpurun_out/ncu_sweep.log 2>&1
-python tools/probe_dwa.py > gpurun_out/plain_dwa.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_dwa_score|k_mapgrid_prepare' -s 8 -c 4 -f -o gpurun_out/prof_dwa_r1 python tools/probe_dwa.py > gpurun_out/ncu_dwa.log 2>&1
+bash tools/profile_kernel.sh 'k_merge_seed|k_inflate' prof_sweep_r1 tools/probe_sweep.py 12 2
+bash tools/profile_kernel.sh k_obstacle_update prof_obstacle_r1 tools/probe_cycle.py 6 1
+bash tools/profile_kernel.sh k_dwa_score prof_c4_r1 tools/probe_c4.py 1 1
+bash tools/profile_kernel.sh k_mapgrid_prepare_sliced prof_mapgrid_r1 tools/probe_dwa.py 3 1
+bash tools/profile_launches.sh tools/probe_fleet.py fleet
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-tail -2 gpurun_out/plain_*.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+tail -c 600 gpurun_out/plain_bench.log
