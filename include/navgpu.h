@@ -112,6 +112,9 @@ void* navgpu_costmap_stream(navgpu_costmap* h);
 /* master grid read-back to HOST: whole grid, or a window [x0,xn) x [y0,yn) packed row-major into out */
 int navgpu_costmap_get(navgpu_costmap* h, uint8_t* host_out);
 int navgpu_costmap_get_window(navgpu_costmap* h, int x0, int y0, int xn, int yn, uint8_t* host_out);
+/* the same window as nav_msgs/OccupancyGrid data: Costmap2DPublisher's cost translation table
+ * (costmap_2d/src/costmap_2d_publisher.cpp:56-71, 139-152) applied on the device while the window is packed */
+int navgpu_costmap_get_window_occupancy(navgpu_costmap* h, int x0, int y0, int xn, int yn, int8_t* host_out);
 int navgpu_costmap_set(navgpu_costmap* h, const uint8_t* host_in);
 int navgpu_layer_get(navgpu_costmap* h, int layer, uint8_t* host_out);
 int navgpu_costmap_get_origin(navgpu_costmap* h, double out[2]);

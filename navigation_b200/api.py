@@ -83,6 +83,7 @@ SIGNATURES = {
     "navgpu_costmap_last_timing_split": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "navgpu_costmap_get": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
+    "navgpu_costmap_get_window_occupancy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _i8p]),
     "navgpu_costmap_set": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_layer_get": (C.c_int, [C.c_void_p, C.c_int, _u8p]),
     "navgpu_costmap_get_origin": (C.c_int, [C.c_void_p, _f64p]),
@@ -247,6 +248,11 @@ class Costmap:
         if out is None:
             out = np.empty((yn - y0, xn - x0), dtype=np.uint8)
         self.api.check(self.lib.navgpu_costmap_get_window(self.h, x0, y0, xn, yn, _p(out, _u8p)))
+        return out
+
+    def get_window_occupancy(self, x0, y0, xn, yn):
+        out = np.empty((yn - y0, xn - x0), dtype=np.int8)
+        self.api.check(self.lib.navgpu_costmap_get_window_occupancy(self.h, x0, y0, xn, yn, _p(out, _i8p)))
         return out
 
     def set(self, grid):

@@ -124,6 +124,7 @@ struct Layer {
   bool footprint_clearing = true;
   double max_obstacle_height = 2.0;
   std::vector<HostObs> obs;
+  std::vector<DevObs> h_clear, h_mark;  // host copies of the device tables (they also travel as kernel parameters)
   DevObs* d_clear = nullptr;
   DevObs* d_mark = nullptr;
   float* d_xyz = nullptr;
@@ -162,6 +163,8 @@ struct navgpu_costmap {
   DevWindow* d_win = nullptr;
   DevWindow* h_win = nullptr;  // pinned
   unsigned* d_ticket = nullptr;  // k_obstacle_update's "last CTA" counter
+  int8_t* d_occupancy = nullptr;  // packed window for navgpu_costmap_get_window_occupancy
+  size_t occupancy_capacity = 0;
   uint16_t* d_seeds = nullptr;  // seed bitmask of the fast sweep (k_merge_seed -> k_inflate)
   size_t seeds_capacity = 0;
   int win[4] = {0, 0, 0, 0};
@@ -405,6 +408,8 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     oa.grid = L.grid[L.cur];
     oa.g = h->geom(L.ox, L.oy);
     oa.clear = L.d_clear; oa.mark = L.d_mark; oa.xyz = L.d_xyz;
+    if (L.n_clear <= kInlineObs) std::copy(L.h_clear.begin(), L.h_clear.end(), oa.clear_inline);
+    if (L.n_mark <= kInlineObs) std::copy(L.h_mark.begin(), L.h_mark.end(), oa.mark_inline);
     oa.n_clear = L.n_clear; oa.total_rays = L.total_rays; oa.n_mark = L.n_mark; oa.total_marks = L.total_marks;
     oa.max_obstacle_height = L.max_obstacle_height;
     oa.box = h->d_boxes + li;
@@ -533,7 +538,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
     cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_mark_cells);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
-  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket);
+  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
   cudaFreeHost(h->h_win);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -734,6 +739,8 @@ int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   L->n_clear = (int)clear.size();
   L->n_mark = (int)mark.size();
+  L->h_clear = clear;
+  L->h_mark = mark;
   L->total_rays = rays;
   L->total_marks = marks;
   return NAVGPU_OK;
@@ -837,6 +844,26 @@ int navgpu_costmap_get_window(navgpu_costmap* h, int x0, int y0, int xn, int yn,
   NAVGPU_TRY(use_device(h));
   NAVGPU_CUDA(cudaMemcpy2DAsync(host_out, xn - x0, h->master[h->cur] + size_t(y0) * h->pitch + x0, h->pitch, xn - x0,
                                 yn - y0, cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_get_window_occupancy(navgpu_costmap* h, int x0, int y0, int xn, int yn, int8_t* host_out) {
+  if (!h || !host_out || x0 < 0 || y0 < 0 || xn > (int)h->sx || yn > (int)h->sy || xn < x0 || yn < y0)
+    return fail(NAVGPU_ERR_INVALID, "bad window");
+  if (xn == x0 || yn == y0) return NAVGPU_OK;
+  NAVGPU_TRY(use_device(h));
+  const size_t n = size_t(xn - x0) * (yn - y0);
+  if (n > h->occupancy_capacity) {
+    if (h->d_occupancy) cudaFree(h->d_occupancy);
+    h->d_occupancy = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&h->d_occupancy, n));
+    h->occupancy_capacity = n;
+  }
+  dim3 block(256), grid((xn - x0 + 255) / 256, yn - y0);
+  k_translate_window<<<grid, block, 0, h->stream>>>(h->master[h->cur], h->pitch, x0, y0, xn - x0, yn - y0, h->d_occupancy);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaMemcpyAsync(host_out, h->d_occupancy, n, cudaMemcpyDeviceToHost, h->stream));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   return NAVGPU_OK;
 }

@@ -30,6 +30,38 @@ struct BoxAcc {
     minx = min(minx, ex); maxx = max(maxx, ex);
     miny = min(miny, ey); maxy = max(maxy, ey);
   }
+  __device__ __forceinline__ void merge(const BoxAcc& o) {
+    minx = min(minx, o.minx); maxx = max(maxx, o.maxx);
+    miny = min(miny, o.miny); maxy = max(maxy, o.maxy);
+  }
+  // every thread of the CTA must call; one atomic per coordinate and CTA (the box words are shared by every CTA of
+  // the launch, so per-warp atomics serialise on four L2 addresses)
+  __device__ __forceinline__ void flush_cta(DevBox* box, unsigned long long (*s_box)[4]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+      maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+      miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+      maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    }
+    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+      s_box[warp][0] = minx; s_box[warp][1] = miny; s_box[warp][2] = maxx; s_box[warp][3] = maxy;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      const bool is_min = threadIdx.x < 2;
+      unsigned long long v = s_box[0][threadIdx.x];
+      for (int w = 1; w < n_warps; ++w) v = is_min ? min(v, s_box[w][threadIdx.x]) : max(v, s_box[w][threadIdx.x]);
+      unsigned long long any = s_box[0][2];
+      for (int w = 1; w < n_warps; ++w) any = max(any, s_box[w][2]);
+      if (any != 0ull) {
+        unsigned long long* dst = threadIdx.x == 0 ? &box->minx : threadIdx.x == 1 ? &box->miny : threadIdx.x == 2 ? &box->maxx : &box->maxy;
+        if (is_min) atomicMin(dst, v);
+        else atomicMax(dst, v);
+      }
+    }
+  }
   __device__ __forceinline__ void flush_warp(DevBox* box) {  // all 32 lanes must call
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -97,7 +129,7 @@ struct DevObs {
 // after i major steps the reference's error accumulator has taken floor((abs_da/2 + i*abs_db)/abs_da) minor steps.
 // All writers store FREE_SPACE, so write order between rays does not matter.
 __device__ __forceinline__ void raytrace_ray(uint8_t* __restrict__ grid, const Geom& g, const DevObs* __restrict__ obs,
-                                             int n_obs, const float* __restrict__ xyz, int total_rays, DevBox* box,
+                                             int n_obs, const float* __restrict__ xyz, int total_rays, BoxAcc& acc,
                                              int warp, int lane) {
   bool touch1 = false;
   double t1x = 0, t1y = 0;
@@ -171,14 +203,8 @@ __device__ __forceinline__ void raytrace_ray(uint8_t* __restrict__ grid, const G
       }
     }
   }
-  // every lane of the warp holds the same end point: lane 0 publishes it
-  if (touch1 && lane == 0) {
-    const unsigned long long ex = enc_double(t1x), ey = enc_double(t1y);
-    atomicMin(&box->minx, ex);
-    atomicMax(&box->maxx, ex);
-    atomicMin(&box->miny, ey);
-    atomicMax(&box->maxy, ey);
-  }
+  // every lane of the warp holds the same end point
+  if (touch1 && lane == 0) acc.touch(t1x, t1y);
 }
 
 // ObstacleLayer::updateBounds marking loop (plugins/obstacle_layer.cpp:368-410), split in two so that the fp64 tests
@@ -209,9 +235,17 @@ __device__ __forceinline__ void mark_prepare(const Geom& g, const DevObs* __rest
 }
 
 __device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, const long long* cells, int total_points) {
-  for (int t = threadIdx.x; t < total_points; t += blockDim.x) {
-    const long long cell = __ldcg(cells + t);  // written by other CTAs of this launch
-    if (cell >= 0) grid[cell] = kLethal;
+  const int nt = blockDim.x;
+  for (int base = threadIdx.x; base < total_points; base += 4 * nt) {  // four loads in flight per thread
+    long long cell[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = base + u * nt;
+      cell[u] = t < total_points ? __ldcg(cells + t) : -1;  // written by other CTAs of this launch: read past L1
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (cell[u] >= 0) grid[cell[u]] = kLethal;
   }
 }
 
@@ -429,11 +463,13 @@ __global__ void k_polygon_clear(uint8_t* __restrict__ grid, unsigned pitch, Poly
 // before it marks ANY point (:362-365 then :368), so the CTA that finishes last (ticket + __threadfence, no
 // spinning) marks the points, clears the footprint polygon (what updateCosts does first, on the same grid) and, for
 // the last observation-driven layer of the stack, runs the bounds pass that needs every layer's accumulated box.
+constexpr int kInlineObs = 16;
 struct ObstacleArgs {
   uint8_t* grid;
   Geom g;
   const DevObs* clear;
   const DevObs* mark;
+  DevObs clear_inline[kInlineObs], mark_inline[kInlineObs];  // used when n_clear / n_mark <= kInlineObs
   const float* xyz;
   int n_clear, total_rays, n_mark, total_marks;
   double max_obstacle_height;
@@ -453,20 +489,25 @@ constexpr int kObstacleThreads = 256;
 
 __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleArgs a) {
   __shared__ uint32_t poly_cells[kPolySmallCells], poly_sorted[kPolySmallCells];
+  __shared__ unsigned long long s_box[kObstacleThreads / 32][4];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * kObstacleThreads + threadIdx.x) >> 5;
-  if (!(a.debug_skip & 8)) raytrace_ray(a.grid, a.g, a.clear, a.n_clear, a.xyz, a.total_rays, a.box, warp, lane);
+  // the observation tables travel in the kernel parameters when they fit (no dependent global loads to find a ray's
+  // observation), else they are read from device memory
+  const DevObs* clear_tab = a.n_clear <= kInlineObs ? a.clear_inline : a.clear;
+  const DevObs* mark_tab = a.n_mark <= kInlineObs ? a.mark_inline : a.mark;
+  BoxAcc acc;
+  if (!(a.debug_skip & 8)) raytrace_ray(a.grid, a.g, clear_tab, a.n_clear, a.xyz, a.total_rays, acc, warp, lane);
   {  // this CTA's share of the marking tests
     const int per_cta = (a.total_marks + gridDim.x - 1) / gridDim.x;
-    BoxAcc acc;
     for (int i = threadIdx.x; i < per_cta; i += kObstacleThreads) {
       const int t = blockIdx.x * per_cta + i;
       if (t < a.total_marks && !(a.debug_skip & 1))
-        mark_prepare(a.g, a.mark, a.n_mark, a.xyz, a.max_obstacle_height, acc, a.mark_cells, t);
+        mark_prepare(a.g, mark_tab, a.n_mark, a.xyz, a.max_obstacle_height, acc, a.mark_cells, t);
     }
-    acc.flush_warp(a.box);
   }
+  acc.flush_cta(a.box, s_box);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -485,6 +526,23 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
       finalize_bounds(a.ba, a.boxes, a.infl, a.win);
     }
   }
+}
+
+// Costmap2DPublisher's cost -> occupancy translation (src/costmap_2d_publisher.cpp:56-71, applied per cell in
+// prepareGrid :95-113 and publishCostmap :139-152), fused with the packing of a window for the download:
+// 0 -> 0, 253 -> 99, 254 -> 100, 255 -> -1, 1..252 -> 1 + 97 * (v - 1) / 251.
+__global__ void k_translate_window(const uint8_t* __restrict__ master, unsigned pitch, int x0, int y0, int w, int h,
+                                   int8_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const int v = master[(size_t)(y0 + y) * pitch + x0 + x];
+  int o;
+  if (v == 0) o = 0;
+  else if (v == kInscribed) o = 99;
+  else if (v == kLethal) o = 100;
+  else if (v == kNoInfo) o = -1;
+  else o = 1 + (97 * (v - 1)) / 251;
+  out[(size_t)y * w + x] = (int8_t)o;
 }
 
 __global__ void k_set_window(DevWindow* win, int x0, int xn, int y0, int yn) {

@@ -302,3 +302,18 @@ def test_merge_policies_on_run_structured_layers(cuda, port, policy, track_unkno
     assert out[0][0] == out[1][0] and out[0][2] == out[1][2]
     assert np.array_equal(out[0][1], out[1][1]), f"{(out[0][1] != out[1][1]).sum()} cells differ after the full update"
     assert np.array_equal(out[0][3], out[1][3]), f"{(out[0][3] != out[1][3]).sum()} cells differ after the window update"
+
+
+def test_publisher_translation_fused_into_the_download(cuda):
+    """Costmap2DPublisher's cost -> occupancy table (costmap_2d_publisher.cpp:56-71) applied on the device while a
+    window is packed for the download: every one of the 256 cost values, odd window."""
+    table = np.zeros(256, np.int8)
+    table[253], table[254], table[255] = 99, 100, -1
+    for i in range(1, 253):
+        table[i] = 1 + (97 * (i - 1)) // 251
+    sx, sy = 301, 77
+    grid = (np.arange(sx * sy, dtype=np.uint32).reshape(sy, sx) * 7 % 256).astype(np.uint8)
+    cm = cuda.costmap(sx, sy, 0.05)
+    cm.set(grid)
+    assert np.array_equal(cm.get_window_occupancy(0, 0, sx, sy), table[grid])
+    assert np.array_equal(cm.get_window_occupancy(13, 5, 290, 71), table[grid[5:71, 13:290]])
