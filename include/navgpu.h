@@ -187,6 +187,11 @@ int navgpu_dwa_get_oscillation_mask(navgpu_dwa* h, int* mask_out);
 int navgpu_dwa_find_best_path(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
                               int n_footprint, navgpu_dwa_result* result, double* all_costs, int all_capacity,
                               double* best_points, int points_capacity);
+/* DWAPlanner::checkTrajectory (dwa_planner.cpp:213-237): resets the oscillation flags, generates the ONE trajectory
+ * of vel_samples and scores it with the critics' state of the last findBestPath (no prepare()); *cost_out >= 0
+ * means the trajectory is legal.  A sample the generator rejects scores 0, exactly like the reference. */
+int navgpu_dwa_check_trajectory(navgpu_dwa* h, const double pose[3], const double vel[3], const double vel_samples[3],
+                                const double* footprint_xy, int n_footprint, double* cost_out);
 /* sample-range sharded variant for multi-GPU sweeps: scores enumerated samples [begin, end) only and returns this
  * shard's (cost, global index) minimum without touching the oscillation state; cost = +inf when none valid. */
 int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,

@@ -105,6 +105,7 @@ SIGNATURES = {
     "navgpu_dwa_get_oscillation_mask": (C.c_int, [C.c_void_p, _i32p]),
     "navgpu_dwa_find_best_path": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.POINTER(DwaResult), _f64p,
                                             C.c_int, _f64p, C.c_int]),
+    "navgpu_dwa_check_trajectory": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, _f64p, C.c_int, _f64p]),
     "navgpu_dwa_score_range": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.c_int64, C.c_int64, _f64p, _i64p,
                                          _i64p]),
     "navgpu_dwa_finish_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _i64p, C.c_int, C.POINTER(DwaResult), _f64p,
@@ -338,6 +339,17 @@ class Dwa:
         return dict(ok=res.cost >= 0, cost=res.cost, xv=res.xv, yv=res.yv, thetav=res.thetav,
                     best_index=res.best_index, n_samples=res.n_samples, n_scored=res.n_scored,
                     costs=costs[:res.n_samples].copy() if want_costs else None, points=pts[:res.n_points].copy())
+
+    def check_trajectory(self, pose, vel, vel_samples, footprint_xy):
+        """DWAPlanner::checkTrajectory: cost of the single trajectory for vel_samples (>= 0 means legal)."""
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        s = np.ascontiguousarray(vel_samples, dtype=np.float64)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        cost = np.zeros(1)
+        self.api.check(self.lib.navgpu_dwa_check_trajectory(self.h, _p(p, _f64p), _p(v, _f64p), _p(s, _f64p),
+                                                            _p(f, _f64p), f.shape[0], _p(cost, _f64p)))
+        return float(cost[0])
 
     def find_best_path_async(self, pose, vel, footprint_xy):
         p = np.ascontiguousarray(pose, dtype=np.float64)

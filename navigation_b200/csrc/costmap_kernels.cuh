@@ -749,6 +749,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 //                  inflation reaches.  A tile whose seed words are all zero exits after the load.
 constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2;  // k_merge_seed: CTA = 256 columns x 32 rows
 constexpr int kITX = 64, kITY = 128, kIThreads = 256, kIMaxRows = kITY + 2 * 31;
+constexpr int kIMaskWords = (kIMaxRows + 32 + 70 + 31) / 32 + 1;
 constexpr uint32_t kH2Inf = 0x3000;  // "no seed within R on this row" (as a squared distance, per 16-bit half)
 
 // layout of the seed bitmask: one row per grid row, 2 zero pad groups (32 cells) on either side of the row
@@ -938,8 +939,7 @@ struct InflateArgs {
 __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   __shared__ uint32_t sbits[kIMaxRows * 4];       // seed words W0..W3 of each region row: columns tx0-32 .. tx0+95
   __shared__ uint32_t h2[kIMaxRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
-  __shared__ uint32_t rowmask[(kIMaxRows + 31) / 32];
-  __shared__ uint32_t sq[128];     // packed squares, index dy + 64
+  __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
   const DevWindow w = *a.win;
   if (!w.valid) return;
@@ -966,11 +966,7 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   }
   for (int i = tid; i <= a.reach2; i += kIThreads) table[i] = a.cost_d2[i];
   if (tid == 0) table[a.reach2 + 1] = 0;
-  if (tid < 128) {
-    const int d = tid - 64;
-    sq[tid] = (uint32_t)(d * d) * 0x10001u;
-  }
-  if (tid < (kIMaxRows + 31) / 32) rowmask[tid] = 0;
+  if (tid < kIMaskWords) rowmask[tid] = 0;
   if (!__syncthreads_or(any)) return;
 
   // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row)
@@ -979,7 +975,7 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     const uint32_t W0 = sbits[4 * r] & ~(0xffffffffu >> R), W1 = sbits[4 * r + 1], W2 = sbits[4 * r + 2],
                    W3 = sbits[4 * r + 3] & ((1u << R) - 1u);
     if ((W0 | W1 | W2 | W3) == 0) continue;
-    if (lane == 0) atomicOr(&rowmask[r >> 5], 1u << (r & 31));
+    if (lane == 0) atomicOr(&rowmask[(r >> 5) + 1], 1u << (r & 31));
     const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
     uint32_t packed = 0;
 #pragma unroll
@@ -1007,19 +1003,35 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     uint32_t acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0x7fff7fffu;
-    const int lo = yr0, hi = yr0 + 8 + 2 * R;  // region-row range [lo, hi)
-    for (int wd = lo >> 5; wd <= (hi - 1) >> 5; ++wd) {
-      uint32_t m = rowmask[wd];
-      const int base = wd * 32;
-      if (lo > base) m &= 0xffffffffu << (lo - base);
-      if (hi < base + 32) m &= (1u << (hi - base)) - 1u;
-      while (m) {
-        const int r = base + __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t hh = h2[r * (kITX / 2) + lane];
-        const uint32_t* sqp = sq + 64 + (r - R - yr0);  // dy of row k is (r - R) - (yr0 + k)
+    // Region rows that can matter for tile rows yr0 .. yr0 + 7 are r = yr0 + R + j with j in [-R, 7 + R].  The walk is
+    // unrolled over j in [-31, 38] so that dy = j - k is a compile-time constant: dy^2 becomes an immediate operand
+    // of VIADDMNMX and the row's address an immediate offset; rows without seeds cost one bit test, eight rows
+    // without seeds one byte test.  Rows beyond +-R only ever add candidates above the reach, which changes nothing.
+    {
+      const uint32_t* hb = h2 + (yr0 + R) * (kITX / 2) + lane;
+      const int p0 = yr0 + R + 1;  // position of j = -31 in rowmask (which is stored with a 32-row offset)
+      const int wi = p0 >> 5, sh = p0 & 31;
+      const uint32_t m0 = __funnelshift_r(rowmask[wi], rowmask[wi + 1], sh),
+                     m1 = __funnelshift_r(rowmask[wi + 1], rowmask[wi + 2], sh),
+                     m2 = __funnelshift_r(rowmask[wi + 2], rowmask[wi + 3], sh);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = __viaddmin_u16x2(hh, sqp[-k], acc[k]);
+      for (int c = 0; c < 9; ++c) {
+        const uint32_t word = c < 4 ? m0 : (c < 8 ? m1 : m2);
+        const uint32_t bits8 = (word >> ((c & 3) * 8)) & 0xffu;
+        if (bits8 == 0) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int j = 8 * c + b - 31;
+          if (j > 38) continue;
+          if (bits8 & (1u << b)) {
+            const uint32_t hh = hb[j * (kITX / 2)];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int dy = j - k;
+              if (dy >= -31 && dy <= 31) acc[k] = __viaddmin_u16x2(hh, (uint32_t)(dy * dy) * 0x10001u, acc[k]);
+            }
+          }
+        }
       }
     }
     // rows that inflation reaches somewhere in these 64 columns: read, combine (inflation_layer.cpp:249-254), write.

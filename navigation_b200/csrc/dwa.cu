@@ -259,7 +259,7 @@ int launch_mapgrid(navgpu_dwa* h, const MapGridArgs& ma, int n_ctas, int jobs_pe
 
 // uploads the per-cycle inputs and launches the 4 MapGrid wavefronts; fills the scoring arguments
 int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const double* footprint_xy, int n_footprint,
-                Cycle& cy) {
+                Cycle& cy, bool prepare = true) {
   NAVGPU_TRY(use_device(h));
   if (!h->d_cost) return fail(NAVGPU_ERR_INVALID, "no costmap set");
   if (h->plan.empty()) return fail(NAVGPU_ERR_INVALID, "no plan set");
@@ -292,7 +292,7 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   ma.job[2] = MapGridJob{h->d_plan[1], (int)h->adjusted[1].size(), 1, h->d_dist[2]};  // goal_front
   ma.job[3] = MapGridJob{h->d_plan[2], (int)h->adjusted[2].size(), 0, h->d_dist[3]};  // alignment
   ma.fleet = nullptr;
-  NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
+  if (prepare) NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
 
   DwaScoreArgs& a = cy.args;
   a.g = g;
@@ -556,6 +556,29 @@ int navgpu_dwa_find_best_path_async(navgpu_dwa* h, const double pose[3], const d
   NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy));
   NAVGPU_TRY(launch_score(h, cy, true));
   NAVGPU_CUDA(cudaGetLastError());
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_check_trajectory(navgpu_dwa* h, const double pose[3], const double vel[3], const double vel_samples[3],
+                                const double* footprint_xy, int n_footprint, double* cost_out) {
+  if (!h || !pose || !vel || !vel_samples || !cost_out || (n_footprint > 0 && !footprint_xy))
+    return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  h->osc.reset();  // dwa_planner.cpp:217
+  Cycle cy;
+  NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy, false));  // critics keep their last prepare()
+  DwaScoreArgs& a = cy.args;
+  a.nx = a.ny = a.nth = 1;
+  a.inline_samples = 1;
+  for (int k = 0; k < 3; ++k) a.samples_inline[k] = (float)vel_samples[k];  // Eigen::Vector3f vel_samples
+  a.begin = 0;
+  a.end = 1;
+  a.osc_mask = 0;
+  double* out = reinterpret_cast<double*>(h->h_points);  // mapped pinned scratch
+  k_dwa_check<<<1, 32, 0, h->stream>>>(a, out);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaGetLastError());
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  *cost_out = *out;
   return NAVGPU_OK;
 }
 

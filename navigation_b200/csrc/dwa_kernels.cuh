@@ -232,13 +232,12 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapG
     const int nbits = (int)g.sx - w * 32;
     colmask[q] = wi < NW ? (nbits < 32 ? (1u << nbits) - 1u : 0xffffffffu) : 0u;
   }
-  uint32_t* F = F0;
-  uint32_t* Fn = F1;
   uint32_t last_level = 0;
   if (seeded) {
-    for (uint32_t level = 0;; ++level) {
+    // one BFS level: read frontier `F`, write the next one into `Fn`.  Two levels per loop trip with the buffers'
+    // roles fixed at compile time, so neighbour loads are [index + constant] and nothing is swapped.
+    auto one_level = [&](const uint32_t* F, uint32_t* Fn, uint32_t lv) -> int {
       int any = 0;
-      last_level = level + 1;
 #pragma unroll
       for (int q = 0; q < kWPT; ++q) {
         const int wi = tid + q * kMapGridThreads;
@@ -250,18 +249,27 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapG
         if (touched) {  // rare: a word is touched during only a few levels
           V[q] |= touched;
           next = touched & P[q];  // obstacles are touched but not expanded (updatePathCell)
-          const uint32_t lv = level + 1;
+          if (next) {
 #pragma unroll
-          for (int k = 0; k < kMapGridMaxPlanes; ++k)
-            if ((lv >> k) & 1u) D[k][q] |= next;
+            for (int k = 0; k < 8; ++k)
+              if ((lv >> k) & 1u) D[k][q] |= next;
+            if (lv >> 8) {
+#pragma unroll
+              for (int k = 8; k < kMapGridMaxPlanes; ++k)
+                if ((lv >> k) & 1u) D[k][q] |= next;
+            }
+          }
         }
         if (wi < NW) Fn[wi] = next;
         any |= next != 0;
       }
-      if (!__syncthreads_or(any)) break;
-      uint32_t* tmp = F;
-      F = Fn;
-      Fn = tmp;
+      return any;
+    };
+    for (uint32_t level = 0;; level += 2) {
+      last_level = level + 1;
+      if (!__syncthreads_or(one_level(F0, F1, level + 1))) break;
+      last_level = level + 2;
+      if (!__syncthreads_or(one_level(F1, F0, level + 2))) break;
     }
   }
   __syncthreads();
@@ -851,6 +859,14 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreAr
   __syncthreads();
   if (warp == 0)
     finish_winner(a, s_index[0], s_cost[0], a.finish_out, a.finish_points, a.finish_capacity, s_scratch[0], &a.counters[1]);
+}
+
+// DWAPlanner::checkTrajectory: one warp scores sample 0 of a one-sample argument block; a rejected sample leaves an
+// empty trajectory, which every critic scores as 0 (an empty footprint still answers -9)
+__global__ void k_dwa_check(DwaScoreArgs a, double* cost_out) {
+  __shared__ double s_scratch[kWarpScratchDoubles];
+  const TrajResult r = score_sample<true>(a, 0, threadIdx.x & 31, nullptr, nullptr, 0, s_scratch);
+  if (threadIdx.x == 0) *cost_out = r.generated ? r.cost : ((a.nfp == 0 && a.scale_obstacle != 0.0) ? -9.0 : 0.0);
 }
 
 // stand-alone finish for sharded sweeps: the winner was chosen from the all-gathered per-rank minima

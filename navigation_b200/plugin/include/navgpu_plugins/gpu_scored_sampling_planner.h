@@ -52,6 +52,10 @@ class GpuScoredSamplingPlanner : public base_local_planner::TrajectorySearch {
   bool findBestTrajectory(base_local_planner::Trajectory& traj,
                           std::vector<base_local_planner::Trajectory>* all_explored = 0) override;
 
+  // DWAPlanner::checkTrajectory (:213-237): true when the single trajectory for vel_samples is legal
+  bool checkTrajectory(double pose_x, double pose_y, double pose_yaw, double vel_x, double vel_y, double vel_yaw,
+                       double sample_x, double sample_y, double sample_yaw, double* cost_out = 0);
+
   int lastStatus() const { return last_status_; }
   int bestIndex() const { return result_.best_index; }
   int samplesScored() const { return result_.n_scored; }

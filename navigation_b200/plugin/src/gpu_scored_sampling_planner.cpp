@@ -98,6 +98,22 @@ void GpuScoredSamplingPlanner::setState(double x, double y, double yaw, double v
   }
 }
 
+bool GpuScoredSamplingPlanner::checkTrajectory(double x, double y, double yaw, double vx, double vy, double vyaw,
+                                               double sx, double sy, double syaw, double* cost_out) {
+  if (!ensureHandle()) return false;
+  const double pose[3] = {x, y, yaw}, vel[3] = {vx, vy, vyaw}, samp[3] = {sx, sy, syaw};
+  double cost = -1.0;
+  last_status_ = navgpu_dwa_check_trajectory(handle_, pose, vel, samp, footprint_xy_.empty() ? NULL : footprint_xy_.data(),
+                                             (int)(footprint_xy_.size() / 2), &cost);
+  if (last_status_ != NAVGPU_OK) {
+    ROS_ERROR("GpuScoredSamplingPlanner: navgpu_dwa_check_trajectory failed (%d): %s", last_status_, navgpu_last_error());
+    return false;
+  }
+  if (cost_out) *cost_out = cost;
+  if (cost < 0) ROS_WARN("Invalid Trajectory %f, %f, %f, cost: %f", sx, sy, syaw, cost);
+  return cost >= 0;
+}
+
 bool GpuScoredSamplingPlanner::findBestTrajectory(base_local_planner::Trajectory& traj,
                                                   std::vector<base_local_planner::Trajectory>* all_explored) {
   traj.cost_ = -7.0;  // dwa_planner.cpp:316

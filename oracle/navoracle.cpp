@@ -1086,6 +1086,18 @@ int navo_dwa_find_best_path(void* h, const double pose[3], const double velv[3],
     }
   return best_cost >= 0 ? 1 : 0;
 }
+double navo_dwa_check_trajectory(void* h, const double pose[3], const double velv[3], const double vel_samples[3],
+                                 const double* footprint_xy, int n_footprint) {  // dwa_planner.cpp:213-237
+  Dwa* d = static_cast<Dwa*>(h);
+  d->footprint = to_pts(footprint_xy, n_footprint);
+  V3f pos{{float(pose[0]), float(pose[1]), float(pose[2])}};
+  V3f vel{{float(velv[0]), float(velv[1]), float(velv[2])}};
+  V3f samp{{float(vel_samples[0]), float(vel_samples[1]), float(vel_samples[2])}};
+  d->reset_osc();
+  Traj t;
+  d->generate(pos, vel, samp, t);  // a rejected sample leaves an empty trajectory, which every critic scores as 0
+  return d->score(t, -1);
+}
 void navo_dwa_get_grid(void* h, int which, double* out) {
   Dwa* d = static_cast<Dwa*>(h);
   MapGridCritic* g[4] = {&d->path, &d->goal, &d->goal_front, &d->alignment};

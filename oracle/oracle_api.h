@@ -113,6 +113,10 @@ int navo_dwa_get_oscillation_mask(void* h); /* bit0 fwd_pos_only,1 fwd_neg_only,
 int navo_dwa_find_best_path(void* h, const double pose[3], const double vel[3], const double* footprint_xy,
                             int n_footprint, navo_dwa_result* result, double* all_costs, int all_capacity,
                             double* best_points, int points_capacity);
+/* DWAPlanner::checkTrajectory (dwa_planner.cpp:213-237): resets the oscillation flags, generates ONE trajectory for
+ * vel_samples and scores it with the critics' current state (no prepare()); returns the cost (>= 0: legal) */
+double navo_dwa_check_trajectory(void* h, const double pose[3], const double vel[3], const double vel_samples[3],
+                                 const double* footprint_xy, int n_footprint);
 /* the four MapGrid distance fields after prepare(): which = 0 path, 1 goal, 2 goal_front, 3 alignment */
 void navo_dwa_get_grid(void* h, int which, double* out);
 /* only the 4 prepare() calls (MapGrid BFS), for timing them separately */

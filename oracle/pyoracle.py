@@ -82,6 +82,7 @@ def _declare(lib, prefix):
         "dwa_reset_oscillation": (None, [vp]),
         "dwa_get_oscillation_mask": (i, [vp]),
         "dwa_find_best_path": (i, [vp, _f64p, _f64p, _f64p, i, C.POINTER(DwaResult), _f64p, i, _f64p, i]),
+        "dwa_check_trajectory": (d, [vp, _f64p, _f64p, _f64p, _f64p, i]),
         "dwa_get_grid": (None, [vp, i, _f64p]),
         "dwa_prepare_only": (None, [vp]),
         "velocity_samples": (i, [d, d, i, _f64p, i]),
@@ -235,6 +236,15 @@ class Dwa:
 
     def oscillation_mask(self):
         return self.lib.navo_dwa_get_oscillation_mask(self.h)
+
+    def check_trajectory(self, pose, vel, vel_samples, footprint_xy):
+        """DWAPlanner::checkTrajectory: cost of the single trajectory for vel_samples (>= 0 means legal)."""
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        s = np.ascontiguousarray(vel_samples, dtype=np.float64)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        return float(self.lib.navo_dwa_check_trajectory(self.h, _p(p, _f64p), _p(v, _f64p), _p(s, _f64p), _p(f, _f64p),
+                                                        f.shape[0]))
 
     def find_best_path(self, pose, vel, footprint_xy, max_samples=1 << 21, max_points=4096):
         p = np.ascontiguousarray(pose, dtype=np.float64)

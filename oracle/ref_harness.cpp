@@ -642,6 +642,23 @@ int navo_dwa_find_best_path(void* hv, const double pose[3], const double velv[3]
   return h->result_traj_.cost_ >= 0 ? 1 : 0;
 }
 
+double navo_dwa_check_trajectory(void* hv, const double pose[3], const double velv[3], const double vel_samples[3],
+                                 const double* footprint_xy, int n_footprint) {  // dwa_planner.cpp:213-237
+  DwaHandle* h = static_cast<DwaHandle*>(hv);
+  h->obstacle_costs_.setFootprint(toPoints(footprint_xy, n_footprint));  // what the last findBestPath left behind
+  Eigen::Vector3f pos(pose[0], pose[1], pose[2]);
+  Eigen::Vector3f vel(velv[0], velv[1], velv[2]);
+  Eigen::Vector3f samp(vel_samples[0], vel_samples[1], vel_samples[2]);
+  h->oscillation_costs_.resetOscillationFlags();
+  Trajectory traj;
+  geometry_msgs::PoseStamped goal_pose = h->global_plan_.back();
+  Eigen::Vector3f goal(goal_pose.pose.position.x, goal_pose.pose.position.y, 0.0f);
+  LocalPlannerLimits limits = h->limits;
+  h->generator_.initialise(pos, vel, goal, &limits, h->vsamples_);
+  h->generator_.generateTrajectory(pos, vel, samp, traj);
+  return h->scored_sampling_planner_.scoreTrajectory(traj, -1);
+}
+
 void navo_dwa_get_grid(void* hv, int which, double* out) {
   DwaHandle* h = static_cast<DwaHandle*>(hv);
   MapGridCostFunction* g[4] = {&h->path_costs_, &h->goal_costs_, &h->goal_front_costs_, &h->alignment_costs_};

@@ -130,3 +130,23 @@ def test_no_valid_trajectory_keeps_stale_result(cuda, port):
     assert (a2["xv"], a2["thetav"]) == (b2["xv"], b2["thetav"]) == (a1["xv"], a1["thetav"])
     assert np.allclose(a2["points"], b2["points"], rtol=RTOL, atol=1e-12) and len(a2["points"]) == len(a1["points"])
     assert np.array_equal(a2["costs"], b2["costs"], equal_nan=True)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_check_trajectory_matches_checker(cuda, port, seed):
+    """DWAPlanner::checkTrajectory (dwa_planner.cpp:213-237) through navgpu_dwa_check_trajectory: the cost of one
+    given velocity sample against the critics' state of the last findBestPath, oscillation flags reset."""
+    outs = []
+    for api in (cuda, port):
+        rng = np.random.default_rng(seed)
+        s = sc.dwa_scenario(rng)
+        grid = sc.local_costmap(port, np.random.default_rng(seed + 1000), ox=s["origin"][0], oy=s["origin"][1], style=s["style"])
+        d = api.dwa(120, 120, 0.05, vx_samples=5, vy_samples=1, vth_samples=7)
+        d.set_costmap(grid, *s["origin"])
+        d.set_plan(s["pose"], s["plan"])
+        d.find_best_path(s["pose"], s["vel"], sc.PENTAGON)
+        costs = [d.check_trajectory(s["pose"], s["vel"], v, sc.PENTAGON)
+                 for v in [(0.3, 0.0, 0.2), (0.55, 0.0, -1.0), (0.0, 0.0, 0.0), (0.05, 0.0, 0.1), (0.5, 0.1, 0.9), (2.0, 0.0, 0.0)]]
+        outs.append((costs, d.oscillation_mask()))
+    assert outs[0][1] == outs[1][1] == 0
+    assert np.allclose(outs[0][0], outs[1][0], rtol=RTOL, atol=0), f"{outs}"
