@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 
 #include "../../include/navgpu.h"
 
@@ -42,6 +43,23 @@ inline int fail(int code, const char* fmt, ...) {
     int rc_ = (expr);              \
     if (rc_ != NAVGPU_OK) return rc_; \
   } while (0)
+
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining;
+// it must call cudaGridDependencySynchronize() before touching anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline std::atomic<uint64_t>& launch_counter() {
   static std::atomic<uint64_t> c{0};

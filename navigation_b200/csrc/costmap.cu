@@ -248,7 +248,7 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
     dim3 block(kMSGroupsX, kMSRowsY);
     dim3 grid((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16), (a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
     if (a.ml.n > 0 || a.do_reset || R > 0) {
-      k_merge_seed<<<grid, block, 0, stream>>>(m);
+      NAVGPU_CUDA(launch_pdl(k_merge_seed, grid, block, 0, stream, m));
       NAVGPU_LAUNCHED(1);
     }
     if (ev_mid) cudaEventRecord(ev_mid, stream);
@@ -262,7 +262,7 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
       ia.cost_d2 = a.cost_d2;
       ia.seeds = reinterpret_cast<const uint32_t*>(seeds);
       dim3 igrid((a.sx + kITX - 1) / kITX, (a.sy + kITY - 1) / kITY);
-      k_inflate<<<igrid, kIThreads, 0, stream>>>(ia);
+      NAVGPU_CUDA(launch_pdl(k_inflate, igrid, dim3(kIThreads), 0, stream, ia));
       NAVGPU_LAUNCHED(1);
     }
     return NAVGPU_OK;

@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * kObstacleThreads + threadIdx.x) >> 5;
+  cudaTriggerProgrammaticLaunchCompletion();  // k_merge_seed may be scheduled behind us; it waits for our completion
   // the observation tables travel in the kernel parameters when they fit (no dependent global loads to find a ray's
   // observation), else they are read from device memory
   const DevObs* clear_tab = a.n_clear <= kInlineObs ? a.clear_inline : a.clear;
@@ -904,6 +905,10 @@ __device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const D
 }
 
 __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY) k_merge_seed(MergeSeedArgs a) {
+  // launched with programmatic stream serialization: let k_inflate be scheduled as soon as every CTA of this grid
+  // is resident, and wait for the kernel before us (window, obstacle grid) before reading anything
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   const DevWindow w = *a.win;
   if (!w.valid) return;
   const int R = a.R;
@@ -941,6 +946,10 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   __shared__ uint32_t h2[kIMaxRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
   __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
+  // the cost table was uploaded long before this cycle: stage it while k_merge_seed is still draining, then wait
+  for (int i = threadIdx.x; i <= a.reach2; i += kIThreads) table[i] = a.cost_d2[i];
+  if (threadIdx.x == 0) table[a.reach2 + 1] = 0;
+  cudaGridDependencySynchronize();
   const DevWindow w = *a.win;
   if (!w.valid) return;
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
@@ -964,8 +973,6 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     sbits[i] = v;
     any |= v != 0;
   }
-  for (int i = tid; i <= a.reach2; i += kIThreads) table[i] = a.cost_d2[i];
-  if (tid == 0) table[a.reach2 + 1] = 0;
   if (tid < kIMaskWords) rowmask[tid] = 0;
   if (!__syncthreads_or(any)) return;
 
