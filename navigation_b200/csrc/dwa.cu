@@ -355,7 +355,7 @@ int launch_score(navgpu_dwa* h, Cycle& cy, bool finish) {
   } else {
     NAVGPU_CUDA(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned int), h->stream));
   }
-  k_dwa_score<<<(unsigned)blocks, kDwaWarpsPerBlock * 32, 0, h->stream>>>(a);
+  NAVGPU_CUDA(launch_pdl(k_dwa_score, dim3((unsigned)blocks), dim3(kDwaWarpsPerBlock * 32), 0, h->stream, a));
   NAVGPU_LAUNCHED(1);
   return NAVGPU_OK;
 }

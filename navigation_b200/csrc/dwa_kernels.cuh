@@ -185,6 +185,7 @@ __device__ __forceinline__ uint32_t mapgrid_passable(const DwaGeom& g, int allow
 template <int kWPT>
 __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapGridArgs a, int jobs_per_robot, int planes) {
   extern __shared__ uint32_t mg_smem[];
+  cudaTriggerProgrammaticLaunchCompletion();  // the scoring kernel may be scheduled behind us; it waits for our end
   const MapGridJob job = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.job[blockIdx.x % jobs_per_robot]
                                  : a.job[blockIdx.x % jobs_per_robot];
   const DwaGeom g = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.g : a.g;
@@ -289,15 +290,16 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapG
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
-  for (int wi = warp; wi < NW; wi += kMapGridThreads / 32) {
-    const int r = wi / W, w = wi - r * W;
-    const int c = w * 32 + lane;
-    if (c >= (int)g.sx) continue;
-    const uint32_t v = (park[wi] >> lane) & 1u, p = (park[NW + wi] >> lane) & 1u, sd = (park[2 * NW + wi] >> lane) & 1u;
-    uint32_t d = 0;
-    for (int k = 0; k < planes; ++k) d |= ((park[(3 + k) * NW + wi] >> lane) & 1u) << k;
-    // seeds 0 (even on an obstacle), untouched cells unreachableCellCosts, touched obstacles obstacleCosts
-    job.dist[(size_t)r * g.sx + c] = sd ? 0u : (!v ? n_cells + 1 : (!p ? n_cells : d));
+  for (int r = warp; r < (int)g.sy; r += kMapGridThreads / 32) {  // a warp per row, a lane per cell of each word
+    for (int w = 0; w < W; ++w) {
+      const int wi = r * W + w, c = w * 32 + lane;
+      if (c >= (int)g.sx) continue;
+      const uint32_t v = (park[wi] >> lane) & 1u, p = (park[NW + wi] >> lane) & 1u, sd = (park[2 * NW + wi] >> lane) & 1u;
+      uint32_t d = 0;
+      for (int k = 0; k < planes; ++k) d |= ((park[(3 + k) * NW + wi] >> lane) & 1u) << k;
+      // seeds 0 (even on an obstacle), untouched cells unreachableCellCosts, touched obstacles obstacleCosts
+      job.dist[(size_t)r * g.sx + c] = sd ? 0u : (!v ? n_cells + 1 : (!p ? n_cells : d));
+    }
   }
 }
 
@@ -776,6 +778,7 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreAr
   __shared__ double s_scratch[kDwaWarpsPerBlock][kWarpScratchDoubles];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long sample = a.begin + (long long)blockIdx.x * kDwaWarpsPerBlock + warp;
+  cudaGridDependencySynchronize();  // launched with programmatic stream serialization behind the MapGrid kernel
   double cost = INFINITY;
   long long index = -1;
   int generated = 0;

@@ -317,3 +317,31 @@ def test_publisher_translation_fused_into_the_download(cuda):
     cm.set(grid)
     assert np.array_equal(cm.get_window_occupancy(0, 0, sx, sy), table[grid])
     assert np.array_equal(cm.get_window_occupancy(13, 5, 290, 71), table[grid[5:71, 13:290]])
+
+
+def test_c3_full_size_bit_exact_vs_checker(cuda, port):
+    """Config C3 at BASELINE.json's full size -- 4000 x 4000 @0.05, static + obstacle (8 observations x 360 ray-cast
+    beams, 10 m) + inflation 1.0 m (R = 20), full window -- against the CPU checker (a few seconds on one core):
+    identical window, obstacle layer and master grid over two cycles with different scans."""
+    outs = []
+    for api in (cuda, port):
+        cm = api.costmap(4000, 4000, 0.05)
+        s = cm.add_grid_layer(0)
+        o = cm.add_obstacle_layer(1, True, 2.0)
+        cm.add_inflation_layer(1.0, 10.0)
+        trace = []
+        for cyc in range(2):
+            static, obs, robot, fp = synth.warehouse_c3(cycle=cyc)
+            if cyc == 0:
+                cm.set_footprint(fp)
+                cm.set_grid_layer(s, static)
+            else:
+                cm.touch_grid_layer(s, 0, 0, 4000, 4000)
+            cm.set_observations(o, obs)
+            w = cm.update_map(*robot)
+            trace.append((w, cm.get(), cm.get_layer(o)))
+        outs.append(trace)
+    for cyc, (a, b) in enumerate(zip(*outs)):
+        assert a[0] == b[0] == (0, 4000, 0, 4000)
+        assert np.array_equal(a[2], b[2]), f"cycle {cyc}: obstacle layer differs in {(a[2] != b[2]).sum()} cells"
+        assert np.array_equal(a[1], b[1]), f"cycle {cyc}: master grid differs in {(a[1] != b[1]).sum()} cells"

@@ -150,3 +150,22 @@ def test_check_trajectory_matches_checker(cuda, port, seed):
         outs.append((costs, d.oscillation_mask()))
     assert outs[0][1] == outs[1][1] == 0
     assert np.allclose(outs[0][0], outs[1][0], rtol=RTOL, atol=0), f"{outs}"
+
+
+def test_c4_full_sweep_vs_checker(cuda, port):
+    """Config C4 at BASELINE.json's full size: 200 x 20 x 200 samples (844 200 with the inserted zeros) scored against
+    one local costmap; the checker needs ~10 s on one core.  Same winner, same sample counts, every reported cost
+    within 1e-5 relative (and bit-identical for all but a handful)."""
+    over = dict(vx_samples=200, vy_samples=20, vth_samples=200, acc_lim_x=20.0, acc_lim_y=20.0, acc_lim_theta=20.0,
+                max_vel_y=0.1, min_vel_y=-0.1)
+    a, pose, vel = c2_setup(cuda, port, **over)
+    b, _, _ = c2_setup(port, port, **over)
+    ra = a.find_best_path(pose, vel, sc.PENTAGON)
+    rb = b.find_best_path(pose, vel, sc.PENTAGON)
+    assert ra["n_samples"] == rb["n_samples"] == 844200 and ra["n_scored"] == rb["n_scored"]
+    assert ra["best_index"] == rb["best_index"] and ra["cost"] == rb["cost"]
+    assert (ra["xv"], ra["yv"], ra["thetav"]) == (rb["xv"], rb["yv"], rb["thetav"])
+    assert np.allclose(ra["costs"], rb["costs"], rtol=RTOL, atol=0, equal_nan=True)
+    same = np.sum((ra["costs"] == rb["costs"]) | (np.isnan(ra["costs"]) & np.isnan(rb["costs"])))
+    assert same >= 0.9999 * ra["n_samples"], f"{ra['n_samples'] - same} costs differ in the last bits"
+    assert np.array_equal(ra["points"], rb["points"])
