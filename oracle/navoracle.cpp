@@ -367,6 +367,167 @@ struct ObstacleLayer : CostLayerBase {  // obstacle_layer.cpp:340-448, 498-610
   }
 };
 
+
+// ------------------------------------------------------------------ VoxelLayer + voxel_grid::VoxelGrid
+// costmap_2d/plugins/voxel_layer.cpp:84-177, 262-438 and voxel_grid/include/voxel_grid/voxel_grid.h:95-118, 226-385.
+// A column is one uint32: bit z = "unknown or marked", bit z + 16 = "marked" (known marked 11, unknown 01, free 00).
+struct VoxelLayer : ObstacleLayer {
+  double origin_z, z_resolution;
+  unsigned size_z, unknown_threshold, mark_threshold;
+  std::vector<uint32_t> vox;
+  VoxelLayer(int cmeth, bool fc, double mh, double oz, double zres, int zv, int unknown_thr, int mark_thr)
+      : ObstacleLayer(cmeth, fc, mh), origin_z(oz), z_resolution(zres), size_z(std::min(zv, 16)),
+        unknown_threshold(unknown_thr + (16 - zv)),  // voxel_layer.cpp:92 (VOXEL_BITS = 16)
+        mark_threshold(mark_thr) {}
+  void match_size(Costmap& cm) override {  // :97-102: the voxel grid starts all-unknown
+    ObstacleLayer::match_size(cm);
+    vox.assign(size_t(g.sx) * g.sy, 0x0000ffffu);
+  }
+  static bool bits_below_threshold(unsigned n, unsigned thr) {  // voxel_grid.h:160-174
+    unsigned count = 0;
+    for (; n;) {
+      ++count;
+      if (count > thr) return false;
+      n &= n - 1;
+    }
+    return true;
+  }
+  bool w2m3f(double wx, double wy, double wz, double& mx, double& my, double& mz) const {  // voxel_layer.h:103-115
+    if (wx < g.ox || wy < g.oy || wz < origin_z) return false;
+    mx = (wx - g.ox) / g.res;
+    my = (wy - g.oy) / g.res;
+    mz = (wz - origin_z) / z_resolution;
+    return mx < g.sx && my < g.sy && mz < size_z;
+  }
+  bool w2m3(double wx, double wy, double wz, unsigned& mx, unsigned& my, unsigned& mz) const {  // :117-130
+    if (wx < g.ox || wy < g.oy || wz < origin_z) return false;
+    mx = (int)((wx - g.ox) / g.res);
+    my = (int)((wy - g.oy) / g.res);
+    mz = (int)((wz - origin_z) / z_resolution);
+    return mx < g.sx && my < g.sy && mz < size_z;
+  }
+  // VoxelGrid::clearVoxelLineInMap = raytraceLine + bresenham3D + ClearVoxelInMap (voxel_grid.h:226-297, 335-372)
+  void clear_line(double x0, double y0, double z0, double x1, double y1, double z1, unsigned max_length) {
+    if (x0 >= g.sx || y0 >= g.sy || z0 >= size_z || x1 >= g.sx || y1 >= g.sy || z1 >= size_z) return;  // voxel_grid.cpp:147-152
+    int dx = int(x1) - int(x0), dy = int(y1) - int(y0), dz = int(z1) - int(z0);
+    unsigned adx = abs(dx), ady = abs(dy), adz = abs(dz);
+    int off_dx = dx > 0 ? 1 : -1, off_dy = (dy > 0 ? 1 : -1) * int(g.sx), off_dz = dz > 0 ? 1 : -1;
+    unsigned z_mask = ((1u << 16) | 1u) << (unsigned)z0;
+    unsigned offset = (unsigned)y0 * g.sx + (unsigned)x0;
+    double dist = sqrt((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1) + (z0 - z1) * (z0 - z1));
+    double scale = std::min(1.0, max_length / dist);
+    auto at = [&]() {
+      uint32_t& col = vox[offset];
+      col &= ~z_mask;
+      unsigned unknown_bits = uint16_t(col >> 16) ^ uint16_t(col);
+      unsigned marked_bits = col >> 16;
+      if (bits_below_threshold(marked_bits, mark_threshold)) {
+        g.c[offset] = bits_below_threshold(unknown_bits, unknown_threshold) ? kFree : kNoInfo;
+      }
+    };
+    // axis kinds: 0 = grid offset (x or y), 1 = z mask
+    auto step = [&](int kind, int off) {
+      if (kind == 0) offset += off;
+      else if (off > 0) z_mask <<= 1;
+      else z_mask >>= 1;
+    };
+    auto bres = [&](int ka, int kb, int kc, unsigned da, unsigned db, unsigned dc, int err_b, int err_c, int oa, int ob,
+                    int oc, unsigned max_len) {
+      unsigned end = std::min(max_len, da);
+      for (unsigned i = 0; i < end; ++i) {
+        at();
+        step(ka, oa);
+        err_b += db;
+        err_c += dc;
+        if ((unsigned)err_b >= da) { step(kb, ob); err_b -= da; }
+        if ((unsigned)err_c >= da) { step(kc, oc); err_c -= da; }
+      }
+      at();
+    };
+    if (adx >= std::max(ady, adz)) bres(0, 0, 1, adx, ady, adz, adx / 2, adx / 2, off_dx, off_dy, off_dz, (unsigned)(scale * adx));
+    else if (ady >= adz) bres(0, 0, 1, ady, adx, adz, ady / 2, ady / 2, off_dy, off_dx, off_dz, (unsigned)(scale * ady));
+    else bres(1, 0, 0, adz, adx, ady, adz / 2, adz / 2, off_dz, off_dx, off_dy, (unsigned)(scale * adz));
+  }
+  void raytrace_freespace_voxel(const Obs& o, Bounds& b) {  // voxel_layer.cpp:262-350
+    if (o.xyz.empty()) return;
+    double sensor_x, sensor_y, sensor_z;
+    const double ox = o.ox, oy = o.oy, oz = o.oz;
+    if (!w2m3f(ox, oy, oz, sensor_x, sensor_y, sensor_z)) return;
+    const double map_end_x = g.ox + g.size_m_x(), map_end_y = g.oy + g.size_m_y();
+    for (size_t i = 0; i < o.xyz.size() / 3; ++i) {
+      double wpx = o.xyz[3 * i], wpy = o.xyz[3 * i + 1], wpz = o.xyz[3 * i + 2];
+      double distance = sqrt((wpx - ox) * (wpx - ox) + (wpy - oy) * (wpy - oy) + (wpz - oz) * (wpz - oz));
+      double scaling_fact = 1.0;
+      scaling_fact = std::max(std::min(scaling_fact, (distance - 2 * g.res) / distance), 0.0);
+      wpx = scaling_fact * (wpx - ox) + ox;
+      wpy = scaling_fact * (wpy - oy) + oy;
+      wpz = scaling_fact * (wpz - oz) + oz;
+      double a = wpx - ox, bb = wpy - oy, c = wpz - oz, t = 1.0;
+      if (wpz > max_obstacle_height) t = std::max(0.0, std::min(t, (max_obstacle_height - 0.01 - oz) / c));
+      else if (wpz < origin_z) t = std::min(t, (origin_z - oz) / c);
+      if (wpx < g.ox) t = std::min(t, (g.ox - ox) / a);
+      if (wpy < g.oy) t = std::min(t, (g.oy - oy) / bb);
+      if (wpx > map_end_x) t = std::min(t, (map_end_x - ox) / a);
+      if (wpy > map_end_y) t = std::min(t, (map_end_y - oy) / bb);
+      wpx = ox + a * t;
+      wpy = oy + bb * t;
+      wpz = oz + c * t;
+      double px, py, pz;
+      if (w2m3f(wpx, wpy, wpz, px, py, pz)) {
+        clear_line(sensor_x, sensor_y, sensor_z, px, py, pz, g.cell_distance(o.raytrace_range));
+        double dx = wpx - ox, dy = wpy - oy;  // updateRaytraceBounds, obstacle_layer.cpp:602-610
+        double full = hypot(dx, dy);
+        double scale = std::min(1.0, o.raytrace_range / full);
+        touch(ox + dx * scale, oy + dy * scale, b);
+      }
+    }
+  }
+  void update_origin_voxel(double nox, double noy) {  // voxel_layer.cpp:371-438
+    int cell_ox = int((nox - g.ox) / g.res), cell_oy = int((noy - g.oy) / g.res);
+    int isx = g.sx, isy = g.sy;
+    int llx = std::min(std::max(cell_ox, 0), isx), lly = std::min(std::max(cell_oy, 0), isy);
+    int urx = std::min(std::max(cell_ox + isx, 0), isx), ury = std::min(std::max(cell_oy + isy, 0), isy);
+    unsigned w = urx - llx, h = ury - lly;
+    std::vector<uint32_t> keep(size_t(w) * h);
+    for (unsigned r = 0; r < h; ++r) memcpy(keep.data() + size_t(r) * w, vox.data() + size_t(lly + r) * g.sx + llx, w * 4);
+    g.update_origin(nox, noy);  // the 2-D part (copy, reset to default, copy back, origin)
+    std::fill(vox.begin(), vox.end(), 0x0000ffffu);
+    int start_x = llx - cell_ox, start_y = lly - cell_oy;
+    for (unsigned r = 0; r < h; ++r) memcpy(vox.data() + size_t(start_y + r) * g.sx + start_x, keep.data() + size_t(r) * w, w * 4);
+  }
+  void update_bounds(Costmap& cm, double rx, double ry, double ryaw, Bounds& b) override {  // voxel_layer.cpp:116-177
+    if (cm.rolling) update_origin_voxel(rx - g.size_m_x() / 2, ry - g.size_m_y() / 2);
+    if (!enabled) return;
+    for (const Obs& o : obs)
+      if (o.clearing) raytrace_freespace_voxel(o, b);
+    for (const Obs& o : obs) {
+      if (!o.marking) continue;
+      double sq_range = o.obstacle_range * o.obstacle_range;
+      for (size_t i = 0; i < o.xyz.size() / 3; ++i) {
+        const float fx = o.xyz[3 * i], fy = o.xyz[3 * i + 1], fz = o.xyz[3 * i + 2];
+        if (fz > max_obstacle_height) continue;
+        double sq = (fx - o.ox) * (fx - o.ox) + (fy - o.oy) * (fy - o.oy) + (fz - o.oz) * (fz - o.oz);
+        if (sq >= sq_range) continue;
+        unsigned mx, my, mz;
+        if (fz < origin_z) {
+          if (!w2m3(fx, fy, origin_z, mx, my, mz)) continue;
+        } else if (!w2m3(fx, fy, fz, mx, my, mz)) {
+          continue;
+        }
+        uint32_t& col = vox[size_t(my) * g.sx + mx];  // markVoxelInMap, voxel_grid.h:98-118
+        col |= ((uint32_t)1 << mz << 16) | (1u << mz);
+        if (!bits_below_threshold(col >> 16, mark_threshold)) {
+          g.c[size_t(my) * g.sx + mx] = kLethal;
+          touch((double)fx, (double)fy, b);
+        }
+      }
+    }
+    if (!footprint_clearing) return;
+    transform_footprint(rx, ry, ryaw, cm.footprint, transformed_footprint);
+    for (const Pt& p : transformed_footprint) touch(p.x, p.y, b);
+  }
+};
+
 struct QCell {  // CellData, inflation_layer.h:55-85
   double distance;
   unsigned index, x, y, sx, sy;
@@ -877,6 +1038,56 @@ static int add_layer(Costmap* cm, LayerBase* l) {
 int navo_costmap_add_grid_layer(void* h, int policy) { return add_layer(static_cast<Costmap*>(h), new GridLayer(policy)); }
 int navo_costmap_add_obstacle_layer(void* h, int combination_method, int footprint_clearing, double max_obstacle_height) {
   return add_layer(static_cast<Costmap*>(h), new ObstacleLayer(combination_method, footprint_clearing != 0, max_obstacle_height));
+}
+int navo_costmap_add_voxel_layer(void* h, int combination_method, int footprint_clearing, double max_obstacle_height,
+                                 double origin_z, double z_resolution, int z_voxels, int unknown_threshold,
+                                 int mark_threshold) {
+  return add_layer(static_cast<Costmap*>(h), new VoxelLayer(combination_method, footprint_clearing != 0, max_obstacle_height,
+                                                            origin_z, z_resolution, z_voxels, unknown_threshold, mark_threshold));
+}
+void navo_layer_get_voxels(void* h, int layer, uint32_t* out) {
+  VoxelLayer* v = dynamic_cast<VoxelLayer*>(static_cast<Costmap*>(h)->layers[layer].get());
+  if (v) memcpy(out, v->vox.data(), v->vox.size() * sizeof(uint32_t));
+}
+int navo_voxel_line_cells(uint32_t size_x, double x0, double y0, double z0, double x1, double y1, double z1,
+                          uint32_t max_length, uint32_t* offsets_out, int32_t* z_out, int capacity) {
+  // same walk as VoxelLayer::clear_line, collecting instead of clearing
+  int dx = int(x1) - int(x0), dy = int(y1) - int(y0), dz = int(z1) - int(z0);
+  unsigned adx = abs(dx), ady = abs(dy), adz = abs(dz);
+  int off_dx = dx > 0 ? 1 : -1, off_dy = (dy > 0 ? 1 : -1) * int(size_x), off_dz = dz > 0 ? 1 : -1;
+  unsigned z_mask = ((1u << 16) | 1u) << (unsigned)z0, offset = (unsigned)y0 * size_x + (unsigned)x0;
+  double dist = sqrt((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1) + (z0 - z1) * (z0 - z1));
+  double scale = std::min(1.0, max_length / dist);
+  int n = 0;
+  auto at = [&]() {
+    if (n < capacity) {
+      offsets_out[n] = offset;
+      z_out[n] = __builtin_ctz(z_mask & 0xffffu ? z_mask & 0xffffu : 0x10000u);
+    }
+    ++n;
+  };
+  auto step = [&](int kind, int off) {
+    if (kind == 0) offset += off;
+    else if (off > 0) z_mask <<= 1;
+    else z_mask >>= 1;
+  };
+  auto bres = [&](int ka, int kb, int kc, unsigned da, unsigned db, unsigned dc, int oa, int ob, int oc, unsigned max_len) {
+    int err_b = da / 2, err_c = da / 2;
+    unsigned end = std::min(max_len, da);
+    for (unsigned i = 0; i < end; ++i) {
+      at();
+      step(ka, oa);
+      err_b += db;
+      err_c += dc;
+      if ((unsigned)err_b >= da) { step(kb, ob); err_b -= da; }
+      if ((unsigned)err_c >= da) { step(kc, oc); err_c -= da; }
+    }
+    at();
+  };
+  if (adx >= std::max(ady, adz)) bres(0, 0, 1, adx, ady, adz, off_dx, off_dy, off_dz, (unsigned)(scale * adx));
+  else if (ady >= adz) bres(0, 0, 1, ady, adx, adz, off_dy, off_dx, off_dz, (unsigned)(scale * ady));
+  else bres(1, 0, 0, adz, adx, ady, off_dz, off_dx, off_dy, (unsigned)(scale * adz));
+  return n;
 }
 int navo_costmap_add_inflation_layer(void* h, double inflation_radius, double cost_scaling_factor) {
   Costmap* cm = static_cast<Costmap*>(h);

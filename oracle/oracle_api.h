@@ -46,6 +46,15 @@ void navo_costmap_destroy(void* h);
 int navo_costmap_add_grid_layer(void* h, int policy);
 int navo_costmap_add_obstacle_layer(void* h, int combination_method, int footprint_clearing,
                                     double max_obstacle_height);
+/* VoxelLayer (costmap_2d/plugins/voxel_layer.cpp, cfg/VoxelPlugin.cfg): a 3-D obstacle layer; observations, enable and
+ * grid read-back work through the obstacle-layer calls.  navo_layer_get_voxels: size_x*size_y uint32 columns. */
+int navo_costmap_add_voxel_layer(void* h, int combination_method, int footprint_clearing, double max_obstacle_height,
+                                 double origin_z, double z_resolution, int z_voxels, int unknown_threshold,
+                                 int mark_threshold);
+void navo_layer_get_voxels(void* h, int layer, uint32_t* out);
+/* voxel_grid::VoxelGrid::raytraceLine (voxel_grid.h:226-297): the visited voxels as (grid offset, z) pairs; returns count */
+int navo_voxel_line_cells(uint32_t size_x, double x0, double y0, double z0, double x1, double y1, double z1,
+                          uint32_t max_length, uint32_t* offsets_out, int32_t* z_out, int capacity);
 int navo_costmap_add_inflation_layer(void* h, double inflation_radius, double cost_scaling_factor);
 /* LayeredCostmap::setFootprint (layered_costmap.cpp:163-173); xy = n (x,y) pairs in the robot frame */
 void navo_costmap_set_footprint(void* h, const double* xy, int n);

@@ -59,6 +59,9 @@ def _declare(lib, prefix):
         "costmap_add_grid_layer": (i, [vp, i]),
         "costmap_add_obstacle_layer": (i, [vp, i, i, d]),
         "costmap_add_inflation_layer": (i, [vp, d, d]),
+        "costmap_add_voxel_layer": (i, [vp, i, i, d, d, d, i, i, i]),
+        "layer_get_voxels": (None, [vp, i, _u32p]),
+        "voxel_line_cells": (i, [u, d, d, d, d, d, d, u, _u32p, _i32p, i]),
         "costmap_set_footprint": (None, [vp, _f64p, i]),
         "grid_layer_set": (None, [vp, i, _u8p]),
         "grid_layer_touch": (None, [vp, i, u, u, u, u]),
@@ -135,6 +138,18 @@ class Costmap:
 
     def add_inflation_layer(self, inflation_radius=0.55, cost_scaling_factor=10.0):
         return self.lib.navo_costmap_add_inflation_layer(self.h, inflation_radius, cost_scaling_factor)
+
+    def add_voxel_layer(self, combination_method=1, footprint_clearing=True, max_obstacle_height=2.0, origin_z=0.0,
+                        z_resolution=0.2, z_voxels=10, unknown_threshold=15, mark_threshold=0):
+        """VoxelLayer with cfg/VoxelPlugin.cfg's defaults."""
+        return self.lib.navo_costmap_add_voxel_layer(self.h, combination_method, int(footprint_clearing),
+                                                     max_obstacle_height, origin_z, z_resolution, z_voxels,
+                                                     unknown_threshold, mark_threshold)
+
+    def get_voxels(self, layer):
+        out = np.zeros((self.size_y, self.size_x), dtype=np.uint32)
+        self.lib.navo_layer_get_voxels(self.h, layer, _p(out, _u32p))
+        return out
 
     def set_footprint(self, xy):
         a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
@@ -294,6 +309,15 @@ class Api:
         out = np.zeros(cap, dtype=np.uint32)
         n = self.lib.navo_raytrace_cells(size_x, x0, y0, x1, y1, max_length, _p(out, _u32p), cap)
         return out[:n].copy()
+
+    def voxel_line_cells(self, size_x, p0, p1, max_length=0xFFFFFFFF):
+        """Voxels visited by VoxelGrid::raytraceLine from p0 to p1 (float voxel coordinates): (offset, z) rows."""
+        cap = 1 << 14
+        off = np.zeros(cap, dtype=np.uint32)
+        z = np.zeros(cap, dtype=np.int32)
+        n = self.lib.navo_voxel_line_cells(size_x, *[float(v) for v in p0], *[float(v) for v in p1], max_length,
+                                           _p(off, _u32p), _p(z, _i32p), cap)
+        return np.stack([off[:n].astype(np.int64), z[:n].astype(np.int64)], 1)
 
     def footprint_radii(self, xy):
         a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

@@ -7,10 +7,12 @@
 //   reference, unmodified: Costmap2D, Layer, LayeredCostmap, CostmapLayer (all four updateWith*),
 //       InflationLayer, raytraceLine/bresenham2D/MarkCell, setConvexPolygonCost, MapGrid, MapGridCostFunction,
 //       ObstacleCostFunction, CostmapModel, LineIterator, OscillationCostFunction, SimpleTrajectoryGenerator,
-//       VelocityIterator, SimpleScoredSamplingPlanner, Trajectory, calculateMinAndMaxDistances (via LayeredCostmap).
+//       VelocityIterator, SimpleScoredSamplingPlanner, Trajectory, calculateMinAndMaxDistances (via LayeredCostmap),
+//       voxel_grid::VoxelGrid (markVoxelInMap, clearVoxelLineInMap = raytraceLine/bresenham3D/ClearVoxelInMap).
 //   restated in this file: ObstacleLayer::updateBounds/raytraceFreespace/updateRaytraceBounds/updateFootprint/
 //       updateCosts bodies (costmap_2d/plugins/obstacle_layer.cpp:340-448,498-610) on top of the reference's
-//       protected CostmapLayer primitives; StaticLayer::updateBounds/updateCosts non-rolling branch and
+//       protected CostmapLayer primitives; VoxelLayer::updateBounds/raytraceFreespace/updateOrigin/matchSize/resetMaps
+//       (costmap_2d/plugins/voxel_layer.cpp:84-101,116-177,262-350,371-438) on top of the reference's VoxelGrid; StaticLayer::updateBounds/updateCosts non-rolling branch and
 //       interpretValue (static_layer.cpp:149-163,263-299); transformFootprint and calculateMinAndMaxDistances
 //       (footprint.cpp:41-67,106-120, that TU needs boost tokenizer + XmlRpc); DWAPlanner's wiring
 //       (dwa_planner.cpp:52-112,116-182,240-286,292-319,357).
@@ -21,6 +23,7 @@
 #include <costmap_2d/cost_values.h>
 #include <costmap_2d/costmap_math.h>
 #include <costmap_2d/observation.h>
+#include <voxel_grid/voxel_grid.h>
 #include <base_local_planner/map_grid.h>
 #include <base_local_planner/map_grid_cost_function.h>
 #include <base_local_planner/obstacle_cost_function.h>
@@ -193,7 +196,7 @@ class RefObstacleLayer : public CostmapLayer {
     }
   }
 
- private:
+ protected:
   void raytraceFreespace(const OwnedObservation& obs, double* min_x, double* min_y, double* max_x,
                          double* max_y) {  // obstacle_layer.cpp:498-576
     double ox = obs.ox, oy = obs.oy;
@@ -246,6 +249,153 @@ class RefObstacleLayer : public CostmapLayer {
   double max_obstacle_height_;
   bool rolling_window_;
   std::vector<geometry_msgs::Point> transformed_footprint_;
+};
+
+
+// VoxelLayer's algorithmic part (costmap_2d/plugins/voxel_layer.cpp) on top of the reference's own VoxelGrid and the
+// ObstacleLayer restatement above (VoxelLayer derives from ObstacleLayer and inherits updateCosts).
+class RefVoxelLayer : public RefObstacleLayer {
+ public:
+  RefVoxelLayer(int combination_method, bool footprint_clearing, double max_obstacle_height, double origin_z,
+                double z_resolution, int z_voxels, int unknown_threshold, int mark_threshold)
+      : RefObstacleLayer(combination_method, footprint_clearing, max_obstacle_height),
+        voxel_grid_(0, 0, 0),
+        z_resolution_(z_resolution),
+        origin_z_(origin_z),
+        unknown_threshold_(unknown_threshold + (VOXEL_BITS - z_voxels)),  // voxel_layer.cpp:92
+        mark_threshold_(mark_threshold),
+        size_z_(z_voxels) {}
+  void matchSize() override {  // voxel_layer.cpp:97-102
+    RefObstacleLayer::matchSize();
+    voxel_grid_.resize(size_x_, size_y_, size_z_);
+  }
+  void resetMaps() override {  // :112-116
+    Costmap2D::resetMaps();
+    voxel_grid_.reset();
+  }
+  const uint32_t* voxels() { return voxel_grid_.getData(); }
+
+  void updateBounds(double robot_x, double robot_y, double robot_yaw, double* min_x, double* min_y, double* max_x,
+                    double* max_y) override {  // voxel_layer.cpp:116-177 (+ ObstacleLayer::updateFootprint :201)
+    if (rolling_window_) updateOriginVoxel(robot_x - getSizeInMetersX() / 2, robot_y - getSizeInMetersY() / 2);
+    if (!enabled_) return;
+    useExtraBounds(min_x, min_y, max_x, max_y);
+    for (size_t i = 0; i < observations_.size(); ++i)
+      if (observations_[i].clearing) raytraceFreespaceVoxel(observations_[i], min_x, min_y, max_x, max_y);
+    for (size_t k = 0; k < observations_.size(); ++k) {
+      const OwnedObservation& obs = observations_[k];
+      if (!obs.marking) continue;
+      double sq_obstacle_range = obs.obstacle_range * obs.obstacle_range;
+      for (size_t i = 0; i < obs.xyz.size() / 3; ++i) {
+        const float fx = obs.xyz[3 * i], fy = obs.xyz[3 * i + 1], fz = obs.xyz[3 * i + 2];
+        if (fz > max_obstacle_height_) continue;
+        double sq_dist = (fx - obs.ox) * (fx - obs.ox) + (fy - obs.oy) * (fy - obs.oy) + (fz - obs.oz) * (fz - obs.oz);
+        if (sq_dist >= sq_obstacle_range) continue;
+        unsigned int mx, my, mz;
+        if (fz < origin_z_) {
+          if (!worldToMap3D(fx, fy, origin_z_, mx, my, mz)) continue;
+        } else if (!worldToMap3D(fx, fy, fz, mx, my, mz)) {
+          continue;
+        }
+        if (voxel_grid_.markVoxelInMap(mx, my, mz, mark_threshold_)) {
+          costmap_[getIndex(mx, my)] = costmap_2d::LETHAL_OBSTACLE;
+          touch((double)fx, (double)fy, min_x, min_y, max_x, max_y);
+        }
+      }
+    }
+    if (!footprint_clearing_enabled_) return;
+    costmap_2d::transformFootprint(robot_x, robot_y, robot_yaw, getFootprint(), transformed_footprint_);
+    for (unsigned int i = 0; i < transformed_footprint_.size(); i++)
+      touch(transformed_footprint_[i].x, transformed_footprint_[i].y, min_x, min_y, max_x, max_y);
+  }
+
+ private:
+  static const unsigned int VOXEL_BITS = 16;  // voxel_layer.cpp:44
+  bool worldToMap3DFloat(double wx, double wy, double wz, double& mx, double& my, double& mz) {  // voxel_layer.h:103-115
+    if (wx < origin_x_ || wy < origin_y_ || wz < origin_z_) return false;
+    mx = ((wx - origin_x_) / resolution_);
+    my = ((wy - origin_y_) / resolution_);
+    mz = ((wz - origin_z_) / z_resolution_);
+    return mx < size_x_ && my < size_y_ && mz < size_z_;
+  }
+  bool worldToMap3D(double wx, double wy, double wz, unsigned int& mx, unsigned int& my, unsigned int& mz) {  // :117-130
+    if (wx < origin_x_ || wy < origin_y_ || wz < origin_z_) return false;
+    mx = (int)((wx - origin_x_) / resolution_);
+    my = (int)((wy - origin_y_) / resolution_);
+    mz = (int)((wz - origin_z_) / z_resolution_);
+    return mx < size_x_ && my < size_y_ && mz < size_z_;
+  }
+  static double dist3(double x0, double y0, double z0, double x1, double y1, double z1) {  // :140-143
+    return sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0) + (z1 - z0) * (z1 - z0));
+  }
+  void raytraceFreespaceVoxel(const OwnedObservation& obs, double* min_x, double* min_y, double* max_x,
+                              double* max_y) {  // voxel_layer.cpp:262-350
+    if (obs.xyz.empty()) return;
+    double sensor_x, sensor_y, sensor_z;
+    double ox = obs.ox, oy = obs.oy, oz = obs.oz;
+    if (!worldToMap3DFloat(ox, oy, oz, sensor_x, sensor_y, sensor_z)) return;
+    double map_end_x = origin_x_ + getSizeInMetersX();
+    double map_end_y = origin_y_ + getSizeInMetersY();
+    for (size_t i = 0; i < obs.xyz.size() / 3; ++i) {
+      double wpx = obs.xyz[3 * i], wpy = obs.xyz[3 * i + 1], wpz = obs.xyz[3 * i + 2];
+      double distance = dist3(ox, oy, oz, wpx, wpy, wpz);
+      double scaling_fact = 1.0;
+      scaling_fact = std::max(std::min(scaling_fact, (distance - 2 * resolution_) / distance), 0.0);
+      wpx = scaling_fact * (wpx - ox) + ox;
+      wpy = scaling_fact * (wpy - oy) + oy;
+      wpz = scaling_fact * (wpz - oz) + oz;
+      double a = wpx - ox, b = wpy - oy, c = wpz - oz, t = 1.0;
+      if (wpz > max_obstacle_height_) {
+        t = std::max(0.0, std::min(t, (max_obstacle_height_ - 0.01 - oz) / c));
+      } else if (wpz < origin_z_) {
+        t = std::min(t, (origin_z_ - oz) / c);
+      }
+      if (wpx < origin_x_) t = std::min(t, (origin_x_ - ox) / a);
+      if (wpy < origin_y_) t = std::min(t, (origin_y_ - oy) / b);
+      if (wpx > map_end_x) t = std::min(t, (map_end_x - ox) / a);
+      if (wpy > map_end_y) t = std::min(t, (map_end_y - oy) / b);
+      wpx = ox + a * t;
+      wpy = oy + b * t;
+      wpz = oz + c * t;
+      double point_x, point_y, point_z;
+      if (worldToMap3DFloat(wpx, wpy, wpz, point_x, point_y, point_z)) {
+        unsigned int cell_raytrace_range = cellDistance(obs.raytrace_range);
+        voxel_grid_.clearVoxelLineInMap(sensor_x, sensor_y, sensor_z, point_x, point_y, point_z, costmap_,
+                                        unknown_threshold_, mark_threshold_, costmap_2d::FREE_SPACE,
+                                        costmap_2d::NO_INFORMATION, cell_raytrace_range);
+        // updateRaytraceBounds, obstacle_layer.cpp:602-610
+        double dx = wpx - ox, dy = wpy - oy;
+        double full_distance = hypot(dx, dy);
+        double scale = std::min(1.0, obs.raytrace_range / full_distance);
+        touch(ox + dx * scale, oy + dy * scale, min_x, min_y, max_x, max_y);
+      }
+    }
+  }
+  void updateOriginVoxel(double new_origin_x, double new_origin_y) {  // voxel_layer.cpp:371-438
+    int cell_ox = int((new_origin_x - origin_x_) / resolution_), cell_oy = int((new_origin_y - origin_y_) / resolution_);
+    double new_grid_ox = origin_x_ + cell_ox * resolution_, new_grid_oy = origin_y_ + cell_oy * resolution_;
+    int size_x = size_x_, size_y = size_y_;
+    int lower_left_x = std::min(std::max(cell_ox, 0), size_x), lower_left_y = std::min(std::max(cell_oy, 0), size_y);
+    int upper_right_x = std::min(std::max(cell_ox + size_x, 0), size_x);
+    int upper_right_y = std::min(std::max(cell_oy + size_y, 0), size_y);
+    unsigned int cell_size_x = upper_right_x - lower_left_x, cell_size_y = upper_right_y - lower_left_y;
+    unsigned char* local_map = new unsigned char[cell_size_x * cell_size_y];
+    unsigned int* local_voxel_map = new unsigned int[cell_size_x * cell_size_y];
+    unsigned int* voxel_map = voxel_grid_.getData();
+    copyMapRegion(costmap_, lower_left_x, lower_left_y, size_x_, local_map, 0, 0, cell_size_x, cell_size_x, cell_size_y);
+    copyMapRegion(voxel_map, lower_left_x, lower_left_y, size_x_, local_voxel_map, 0, 0, cell_size_x, cell_size_x, cell_size_y);
+    resetMaps();
+    origin_x_ = new_grid_ox;
+    origin_y_ = new_grid_oy;
+    int start_x = lower_left_x - cell_ox, start_y = lower_left_y - cell_oy;
+    copyMapRegion(local_map, 0, 0, cell_size_x, costmap_, start_x, start_y, size_x_, cell_size_x, cell_size_y);
+    copyMapRegion(local_voxel_map, 0, 0, cell_size_x, voxel_map, start_x, start_y, size_x_, cell_size_x, cell_size_y);
+    delete[] local_map;
+    delete[] local_voxel_map;
+  }
+  voxel_grid::VoxelGrid voxel_grid_;
+  double z_resolution_, origin_z_;
+  unsigned int unknown_threshold_, mark_threshold_, size_z_;
 };
 
 // exposes Costmap2D's protected raytraceLine
@@ -310,6 +460,41 @@ int navo_costmap_add_obstacle_layer(void* hv, int combination_method, int footpr
   return addLayer(static_cast<CostmapHandle*>(hv),
                   new RefObstacleLayer(combination_method, footprint_clearing != 0, max_obstacle_height), 1,
                   "obstacles");
+}
+int navo_costmap_add_voxel_layer(void* hv, int combination_method, int footprint_clearing, double max_obstacle_height,
+                                 double origin_z, double z_resolution, int z_voxels, int unknown_threshold,
+                                 int mark_threshold) {
+  // kind 1: everything the C API does with an obstacle layer applies (observations, enable, grid read-back)
+  return addLayer(static_cast<CostmapHandle*>(hv),
+                  new RefVoxelLayer(combination_method, footprint_clearing != 0, max_obstacle_height, origin_z,
+                                    z_resolution, z_voxels, unknown_threshold, mark_threshold), 1, "voxels");
+}
+void navo_layer_get_voxels(void* hv, int layer, uint32_t* out) {
+  CostmapHandle* h = static_cast<CostmapHandle*>(hv);
+  RefVoxelLayer* v = dynamic_cast<RefVoxelLayer*>(h->layers[layer]);
+  if (!v) return;
+  Costmap2D* c = h->lc->getCostmap();
+  memcpy(out, v->voxels(), size_t(c->getSizeInCellsX()) * c->getSizeInCellsY() * sizeof(uint32_t));
+}
+namespace {
+struct VoxelCollect {  // an ActionType for the reference's VoxelGrid::raytraceLine template
+  std::vector<std::pair<unsigned, unsigned> >* v;
+  void operator()(unsigned int offset, unsigned int z_mask) { v->push_back(std::make_pair(offset, z_mask)); }
+};
+}  // namespace
+int navo_voxel_line_cells(uint32_t size_x, double x0, double y0, double z0, double x1, double y1, double z1,
+                          uint32_t max_length, uint32_t* offsets_out, int32_t* z_out, int capacity) {
+  unsigned size_y = unsigned(std::max(y0, y1)) + 2;
+  voxel_grid::VoxelGrid vg(size_x, size_y, 16);
+  std::vector<std::pair<unsigned, unsigned> > cells;
+  VoxelCollect c{&cells};
+  vg.raytraceLine(c, x0, y0, z0, x1, y1, z1, max_length);
+  int n = 0;
+  for (size_t i = 0; i < cells.size() && n < capacity; ++i, ++n) {
+    offsets_out[n] = cells[i].first;
+    z_out[n] = __builtin_ctz(cells[i].second & 0xffffu ? cells[i].second & 0xffffu : 0x10000u);
+  }
+  return int(cells.size());
 }
 int navo_costmap_add_inflation_layer(void* hv, double inflation_radius, double cost_scaling_factor) {
   CostmapHandle* h = static_cast<CostmapHandle*>(hv);

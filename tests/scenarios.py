@@ -185,3 +185,45 @@ def dwa_results_equal(a, b, rtol=0.0):
         np.allclose(a["costs"], b["costs"], rtol=rtol, atol=0, equal_nan=True) and \
         np.allclose(a["points"], b["points"], rtol=rtol, atol=1e-12)
     return bool(ok)
+
+
+def run_voxel_scenario(api, seed, cycles=4, max_size=70):
+    """Multi-cycle LayeredCostmap scenario with a VoxelLayer (3-D ray-trace clearing + marking) [+ inflation];
+    returns per cycle (window, master, voxel layer's 2-D grid, voxel columns, origin).  mark_threshold stays 0 (the
+    reference's default): with a positive threshold the reference's bounds depend on the order of the cloud points."""
+    rng = np.random.default_rng(seed)
+    sx, sy = int(rng.integers(20, max_size)), int(rng.integers(20, max_size))
+    res = float(rng.choice([0.05, 0.1, 0.25]))
+    ox, oy = float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3))
+    rolling = bool(rng.random() < 0.4)
+    tu = bool(rng.random() < 0.5)
+    z_voxels = int(rng.choice([4, 10, 16]))
+    z_res = float(rng.choice([0.1, 0.2]))
+    origin_z = float(rng.choice([0.0, -0.1]))
+    unknown_threshold = int(rng.choice([0, 8, 15]))
+    max_h = float(rng.choice([1.0, 2.0]))
+    cm = api.costmap(sx, sy, res, ox, oy, rolling=rolling, track_unknown=tu)
+    ids = {}
+    if not rolling:
+        ids["static"] = cm.add_grid_layer(po.TRUE_OVERWRITE)
+    ids["voxel"] = cm.add_voxel_layer(int(rng.integers(0, 2)), bool(rng.random() < 0.7), max_h, origin_z, z_res, z_voxels,
+                                      unknown_threshold, 0)
+    with_inflation = bool(rng.random() < 0.5)
+    if with_inflation:
+        ids["inflation"] = cm.add_inflation_layer(0.3, 10.0)
+    cm.set_footprint(square_footprint())
+    trace = []
+    rx, ry = ox + sx * res / 2, oy + sy * res / 2
+    for cyc in range(cycles):
+        if "static" in ids and cyc == 0:
+            cm.set_grid_layer(ids["static"], random_layer(rng, sy, sx, "blocks"))
+        obs = random_observations(rng, sx, sy, res, ox, oy, int(rng.integers(1, 4)), 60)
+        for o in obs:  # sensor heights and point heights inside and outside the voxel column
+            o["origin"] = (o["origin"][0], o["origin"][1], float(rng.uniform(-0.3, z_voxels * z_res + 0.3)))
+            o["points"][:, 2] = rng.uniform(-0.4, z_voxels * z_res + 0.5, len(o["points"])).astype(np.float32)
+        cm.set_observations(ids["voxel"], obs)
+        rx += rng.uniform(-0.5, 0.5)
+        ry += rng.uniform(-0.5, 0.5)
+        w = cm.update_map(rx, ry, float(rng.uniform(-3, 3)))
+        trace.append((w, cm.get().copy(), cm.get_layer(ids["voxel"]).copy(), cm.get_voxels(ids["voxel"]).copy(), cm.origin()))
+    return trace, with_inflation

@@ -265,3 +265,28 @@ def test_interpret_value(api):  # static_layer.cpp:149-163 with the defaults of 
 def test_footprint_radii(api):  # costmap_2d/test/footprint_tests.cpp expectations re-derived: square of half-width a
     i, c = api.footprint_radii([(1, 1), (1, -1), (-1, -1), (-1, 1)])
     assert i == 1.0 and abs(c - np.sqrt(2)) < 1e-15
+
+
+def test_voxel_grid_basic_marking_and_clearing(api):  # voxel_grid/test/voxel_grid_tests.cpp:40-128
+    """The tabletop of basicMarkingAndClearing: 11 marked lines of 4 voxels at z = 12 (44 voxels), one cleared row of
+    11, a vertical column of 16 -- expressed through VoxelGrid::raytraceLine's visited voxels on a 50-wide grid."""
+    size_x, table_z = 50, 12
+    table = set()
+    for x in range(5, 16):  # markVoxelLine(x, 0, 12, x, 3, 12)
+        cells = api.voxel_line_cells(size_x, (x, 0, table_z), (x, 3, table_z))
+        assert [tuple(c) for c in cells] == [(y * size_x + x, table_z) for y in range(4)]
+        table |= {tuple(c) for c in cells}
+    assert len(table) == 44
+    row = api.voxel_line_cells(size_x, (5, 0, table_z), (15, 0, table_z))  # clearVoxelLine along the table's first row
+    assert [tuple(c) for c in row] == [(x, table_z) for x in range(5, 16)]
+    assert len(table - {tuple(c) for c in row}) == 33
+    col = api.voxel_line_cells(size_x, (0, 0, 0), (0, 0, 15))  # clearVoxelLine(0, 0, 0, 0, 0, sizeZ - 1)
+    assert [tuple(c) for c in col] == [(0, z) for z in range(16)]
+
+
+def test_voxel_line_length_limit_and_diagonal(api):  # voxel_grid.h:226-297 (raytraceLine + bresenham3D)
+    cells = api.voxel_line_cells(50, (2.7, 1.2, 0.5), (12.9, 6.1, 9.8))
+    assert tuple(cells[0]) == (1 * 50 + 2, 0) and tuple(cells[-1]) == (6 * 50 + 12, 9) and len(cells) == 11
+    short = api.voxel_line_cells(50, (2.7, 1.2, 0.5), (12.9, 6.1, 9.8), max_length=4)
+    assert len(short) == int(min(1.0, 4 / np.sqrt(10.2 ** 2 + 4.9 ** 2 + 9.3 ** 2)) * 10) + 1
+    assert np.array_equal(short, cells[:len(short)])
