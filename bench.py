@@ -107,6 +107,33 @@ def build_c3(api_costmap_factory, size=None, n_obs=None):
     return cm, (s, o, il), sets
 
 
+def voxel_numbers(api_factory, reps, sync=None, size=None):
+    """The C3 recipe with a VoxelLayer (cfg/VoxelPlugin.cfg defaults: 10 voxels of 0.2 m) in place of the obstacle
+    layer: wall time of one full-window update_map through the binding (device work + launch overhead)."""
+    from navigation_b200 import synth
+    size = size or C3["size"]
+    static, obs, robot, fp = synth.warehouse_c3(size=size, resolution=C3["resolution"], n_obs=C3["n_obs"],
+                                                n_beams=C3["n_beams"], scan_range=C3["scan_range"])
+    for o in obs:  # give the ray-cast end points heights inside the 2 m column
+        o["origin"] = (o["origin"][0], o["origin"][1], 0.5)
+        o["points"][:, 2] = (0.1 + 1.7 * (np.arange(len(o["points"])) % 7) / 7.0).astype(np.float32)
+    cm = api_factory(size, size, C3["resolution"])
+    s = cm.add_grid_layer(0)
+    v = cm.add_voxel_layer(1, True, 2.0, 0.0, 0.2, 10, 15, 0)
+    cm.add_inflation_layer(C3["inflation_radius"], C3["scaling"])
+    cm.set_footprint(fp)
+    cm.set_grid_layer(s, static)
+    cm.set_observations(v, obs)
+    cm.update_map(*robot)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        cm.update_map(*robot)
+    if sync:
+        sync()
+    return 1e3 * (time.perf_counter() - t0) / reps
+
+
 def obs_bytes(obs):
     return sum(o["points"].nbytes + 64 for o in obs)
 
@@ -495,6 +522,7 @@ def run_native(args, rank, world, local_rank):
     else:
         sweep, merge, inflate = float(np.mean(sweep_ms)), float(np.mean(merge_ms)), float(np.mean(inflate_ms))
 
+    voxel_ms = voxel_numbers(lambda *a: api.costmap(*a, device=local_rank), max(5, args.steps), torch.cuda.synchronize)
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = ALGO_BYTES_PER_CELL * n_cells / (sweep * 1e-3) / 1e9
@@ -515,10 +543,17 @@ def run_native(args, rank, world, local_rank):
                          "kernel_ms": sweep, "k_merge_seed_ms": merge, "k_inflate_ms": inflate,
                          "algorithmic_bytes": ALGO_BYTES_PER_CELL * n_cells, "peak_source": peak_src},
         }
+        line["voxel_layer"] = {"c3_with_voxel_layer_update_map_ms": voxel_ms,
+                               "what": "C3 with costmap_2d::VoxelLayer (10 x 0.2 m voxels) instead of ObstacleLayer, "
+                                       "synchronous navgpu_costmap_update_map, hot L2"}
         if dwa is not None:
             line["dwa"] = dwa
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_c3()
+            from oracle import pyoracle
+            kind = "reference" if pyoracle.available("reference") else "port"
+            line["voxel_layer"]["cpu_ms"] = voxel_numbers(pyoracle.load(kind).costmap, 1)
+            line["voxel_layer"]["cpu_kind"] = kind
             if dwa is not None:
                 line["dwa"]["cpu_baseline"] = dwa_cpu_numbers()
                 line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers()})

@@ -71,6 +71,14 @@ int navgpu_costmap_destroy(navgpu_costmap* h);
 int navgpu_costmap_add_grid_layer(navgpu_costmap* h, int policy, int* layer_out);
 int navgpu_costmap_add_obstacle_layer(navgpu_costmap* h, int combination_method, int footprint_clearing,
                                       double max_obstacle_height, int* layer_out);
+/* VoxelLayer (costmap_2d/plugins/voxel_layer.cpp, cfg/VoxelPlugin.cfg): the 3-D obstacle layer -- columns of up to 16
+ * voxels (voxel_grid/include/voxel_grid/voxel_grid.h), 3-D Bresenham clearing, marking, rolling origin.  It takes
+ * observations, enable and grid read-back through the obstacle-layer calls.  mark_threshold must be 0 (the default). */
+int navgpu_costmap_add_voxel_layer(navgpu_costmap* h, int combination_method, int footprint_clearing,
+                                   double max_obstacle_height, double origin_z, double z_resolution, int z_voxels,
+                                   int unknown_threshold, int mark_threshold, int* layer_out);
+/* the voxel columns (size_y x size_x uint32: bit z = unknown-or-marked, bit z + 16 = marked) to HOST */
+int navgpu_layer_get_voxels(navgpu_costmap* h, int layer, uint32_t* host_out);
 int navgpu_costmap_add_inflation_layer(navgpu_costmap* h, double inflation_radius, double cost_scaling_factor,
                                        int* layer_out);
 /* LayeredCostmap::setFootprint (layered_costmap.cpp:163-173): n (x,y) pairs, robot frame */

@@ -64,6 +64,9 @@ SIGNATURES = {
     "navgpu_costmap_add_grid_layer": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
     "navgpu_costmap_add_obstacle_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, _i32p]),
     "navgpu_costmap_add_inflation_layer": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _i32p]),
+    "navgpu_costmap_add_voxel_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                                 C.c_int, C.c_int, _i32p]),
+    "navgpu_layer_get_voxels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]),
     "navgpu_costmap_set_footprint": (C.c_int, [C.c_void_p, _f64p, C.c_int]),
     "navgpu_grid_layer_set": (C.c_int, [C.c_void_p, C.c_int, _u8p]),
     "navgpu_grid_layer_set_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]),
@@ -161,6 +164,18 @@ class Costmap:
         out = C.c_int32()
         return self._layer(self.lib.navgpu_costmap_add_inflation_layer(self.h, inflation_radius, cost_scaling_factor,
                                                                        C.byref(out)), out)
+
+    def add_voxel_layer(self, combination_method=1, footprint_clearing=True, max_obstacle_height=2.0, origin_z=0.0,
+                        z_resolution=0.2, z_voxels=10, unknown_threshold=15, mark_threshold=0):
+        out = C.c_int32()
+        return self._layer(self.lib.navgpu_costmap_add_voxel_layer(
+            self.h, combination_method, int(footprint_clearing), max_obstacle_height, origin_z, z_resolution, z_voxels,
+            unknown_threshold, mark_threshold, C.byref(out)), out)
+
+    def get_voxels(self, layer):
+        out = np.zeros((self.size_y, self.size_x), dtype=np.uint32)
+        self.api.check(self.lib.navgpu_layer_get_voxels(self.h, layer, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
 
     def set_footprint(self, xy):
         a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

@@ -132,6 +132,10 @@ struct Layer {
   size_t xyz_capacity = 0, obs_capacity = 0, mark_cells_capacity = 0;
   int n_clear = 0, n_mark = 0, total_rays = 0, total_marks = 0;
   std::vector<Pt> transformed_footprint;
+  // voxel layer (an obstacle layer with columns of 16 voxels, plugins/voxel_layer.cpp)
+  bool voxel = false;
+  VoxelGeom vg{0.0, 0.2, 10u, 21u, 0u};
+  uint32_t* vox[2] = {nullptr, nullptr};
   // inflation layer
   double radius = 0, weight = 0, inscribed = 0;
   bool need_reinflation = false;
@@ -363,8 +367,17 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
       B.hy1 = L.oy + (L.uy + L.uh + 0.5) * h->res;
       L.updated = false;
     } else if (L.kind == 1) {  // ObstacleLayer::updateBounds (obstacle_layer.cpp:340-413)
-      if (h->rolling)
+      if (h->rolling) {
+        if (L.voxel) {  // VoxelLayer::updateOrigin moves the columns with the 2-D cells (voxel_layer.cpp:371-438)
+          const double new_ox = rx - h->size_m_x() / 2, new_oy = ry - h->size_m_y() / 2;
+          const int cell_ox = int((new_ox - L.ox) / h->res), cell_oy = int((new_oy - L.oy) / h->res);
+          if (!L.vox[L.cur ^ 1]) NAVGPU_CUDA(cudaMalloc(&L.vox[L.cur ^ 1], h->bytes() * sizeof(uint32_t)));
+          dim3 block(256), g((h->pitch + 255) / 256, h->sy);
+          k_shift_voxels<<<g, block, 0, h->stream>>>(L.vox[L.cur], L.vox[L.cur ^ 1], h->sx, h->sy, h->pitch, cell_ox, cell_oy);
+          NAVGPU_LAUNCHED(1);
+        }
         NAVGPU_TRY(roll_grid(h, L.grid, L.cur, L.ox, L.oy, L.def, rx - h->size_m_x() / 2, ry - h->size_m_y() / 2));
+      }
       L.transformed_footprint.clear();
       if (!L.enabled) continue;
       last_obstacle = (int)li;
@@ -372,7 +385,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
       // raytraceFreespace touches the sensor origin once per clearing observation whose origin is on the map
       // (:504-521); origins and geometry are host-side scalars, the per-ray end points are touched on the device
       for (const HostObs& o : L.obs) {
-        if (!o.clearing) continue;
+        if (!o.clearing || L.voxel) continue;  // VoxelLayer::raytraceFreespace does not touch the sensor origin
         if (o.ox < L.ox || o.oy < L.oy) continue;
         unsigned mx = (int)((o.ox - L.ox) / h->res), my = (int)((o.oy - L.oy) / h->res);
         if (!(mx < h->sx && my < h->sy)) continue;
@@ -404,6 +417,39 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   for (size_t li = 0; li < h->layers.size(); ++li) {
     Layer& L = h->layers[li];
     if (L.kind != 1 || !L.enabled) continue;
+    if (L.voxel) {
+      VoxelArgs va;
+      va.grid = L.grid[L.cur];
+      va.vox = L.vox[L.cur];
+      va.g = h->geom(L.ox, L.oy);
+      va.v = L.vg;
+      va.clear = L.d_clear; va.mark = L.d_mark; va.xyz = L.d_xyz;
+      va.n_clear = L.n_clear; va.total_rays = L.total_rays; va.n_mark = L.n_mark; va.total_marks = L.total_marks;
+      va.max_obstacle_height = L.max_obstacle_height;
+      va.box = h->d_boxes + li;
+      va.mark_cells = L.d_mark_cells;
+      va.ticket = h->d_ticket;
+      int vmode = 0;
+      if (L.footprint_clearing) NAVGPU_TRY(footprint_polygon(h, L, va.poly, &vmode));
+      va.do_poly = vmode == 1;
+      va.do_finalize = (int)li == last_obstacle;
+      if (va.do_finalize) va.ba = ba;
+      va.boxes = h->d_boxes; va.infl = h->d_infl; va.win = h->d_win;
+      const int vblocks = std::max(1, (L.total_rays * 32 + kObstacleThreads - 1) / kObstacleThreads);
+      k_voxel_clear<<<vblocks, kObstacleThreads, 0, h->stream>>>(va);
+      k_voxel_commit<<<vblocks, kObstacleThreads, 0, h->stream>>>(va);
+      NAVGPU_LAUNCHED(2);
+      if (vmode == 2) {
+        size_t smem = 2 * kPolyMaxCells * sizeof(uint32_t);
+        if (!h->poly_attr_set) {
+          NAVGPU_CUDA(cudaFuncSetAttribute(k_polygon_clear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          h->poly_attr_set = true;
+        }
+        k_polygon_clear<<<1, 256, smem, h->stream>>>(L.grid[L.cur], h->pitch, va.poly, kFree);
+        NAVGPU_LAUNCHED(1);
+      }
+      continue;
+    }
     ObstacleArgs oa;
     oa.grid = L.grid[L.cur];
     oa.g = h->geom(L.ox, L.oy);
@@ -536,6 +582,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   for (Layer& L : h->layers) {
     cudaFree(L.grid[0]); cudaFree(L.grid[1]);
     cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_mark_cells);
+    cudaFree(L.vox[0]); cudaFree(L.vox[1]);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
   cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
@@ -580,6 +627,45 @@ int navgpu_costmap_add_obstacle_layer(navgpu_costmap* h, int combination_method,
   NAVGPU_TRY(add_cost_layer(h, L));
   h->layers.push_back(L);
   if (layer_out) *layer_out = (int)h->layers.size() - 1;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_add_voxel_layer(navgpu_costmap* h, int combination_method, int footprint_clearing,
+                                   double max_obstacle_height, double origin_z, double z_resolution, int z_voxels,
+                                   int unknown_threshold, int mark_threshold, int* layer_out) {
+  if (!h || z_voxels < 0 || z_voxels > 16 || !(z_resolution > 0) || unknown_threshold < 0 || mark_threshold < 0)
+    return fail(NAVGPU_ERR_INVALID, "bad voxel layer arguments");
+  if (mark_threshold != 0)  // with a positive threshold the reference's bounds depend on the order of the cloud points
+    return fail(NAVGPU_ERR_UNSUPPORTED, "mark_threshold %d: only the reference's default 0 is implemented", mark_threshold);
+  if (h->layers.size() >= (size_t)kMaxLayers) return fail(NAVGPU_ERR_UNSUPPORTED, "more than %d layers", kMaxLayers);
+  NAVGPU_TRY(use_device(h));
+  Layer L;
+  L.kind = 1;
+  L.voxel = true;
+  L.combination_method = combination_method;
+  L.footprint_clearing = footprint_clearing != 0;
+  L.max_obstacle_height = max_obstacle_height;
+  // VoxelLayer::reconfigureCB (voxel_layer.cpp:84-95): unknown_threshold_ = config.unknown_threshold + (16 - z_voxels)
+  L.vg = VoxelGeom{origin_z, z_resolution, (unsigned)z_voxels, (unsigned)(unknown_threshold + (16 - z_voxels)), (unsigned)mark_threshold};
+  NAVGPU_TRY(add_cost_layer(h, L));
+  // VoxelGrid starts (and resets to) all-unknown columns (voxel_grid.cpp:41-59)
+  NAVGPU_CUDA(cudaMalloc(&L.vox[0], h->bytes() * sizeof(uint32_t)));
+  {
+    std::vector<uint32_t> unknown(h->bytes(), 0x0000ffffu);
+    NAVGPU_CUDA(cudaMemcpy(L.vox[0], unknown.data(), unknown.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  h->layers.push_back(L);
+  if (layer_out) *layer_out = (int)h->layers.size() - 1;
+  return NAVGPU_OK;
+}
+
+int navgpu_layer_get_voxels(navgpu_costmap* h, int layer, uint32_t* host_out) {
+  Layer* L = (h && layer >= 0 && layer < (int)h->layers.size()) ? &h->layers[layer] : nullptr;
+  if (!L || !L->voxel || !host_out) return fail(NAVGPU_ERR_INVALID, "not a voxel layer");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(host_out, h->sx * sizeof(uint32_t), L->vox[L->cur], h->pitch * sizeof(uint32_t),
+                                h->sx * sizeof(uint32_t), h->sy, cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   return NAVGPU_OK;
 }
 

@@ -546,6 +546,254 @@ __global__ void k_translate_window(const uint8_t* __restrict__ master, unsigned 
   out[(size_t)y * w + x] = (int8_t)o;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// VoxelLayer (plugins/voxel_layer.cpp) on voxel_grid::VoxelGrid columns (voxel_grid/include/voxel_grid/voxel_grid.h):
+// one uint32 per cell, bit z = "unknown or marked", bit z + 16 = "marked".  The column array shares the 2-D layer
+// grid's indexing (offset = y * pitch + x).
+//
+// The reference clears ray by ray and re-derives the 2-D cell after every cleared voxel (ClearVoxelInMap,
+// voxel_grid.h:335-372).  Clearing only ever removes bits and both threshold tests are monotone in the bits, so the
+// value a cell ends with is the rule applied to the column AFTER ALL clears (untouched when the marked count is still
+// above its threshold).  Hence two launches: k_voxel_clear does every ray's atomicAnd (and the marking tests, into a
+// scratch list); k_voxel_commit walks the rays again and writes the 2-D cells from the final columns, then its last
+// CTA commits the marks (markVoxelInMap :98-118: all marking comes after all clearing, voxel_layer.cpp:136-177),
+// clears the footprint polygon and finalises the bounds exactly like k_obstacle_update.
+struct VoxelGeom {
+  double origin_z, z_resolution;
+  unsigned size_z, unknown_threshold, mark_threshold;
+};
+
+__device__ __forceinline__ bool bits_below_threshold(unsigned n, unsigned thr) { return (unsigned)__popc(n) <= thr; }
+
+// VoxelLayer::worldToMap3DFloat (voxel_layer.h:103-115)
+__device__ __forceinline__ bool world_to_map_3d_float(const Geom& g, const VoxelGeom& v, double wx, double wy, double wz,
+                                                      double& mx, double& my, double& mz) {
+  if (wx < g.ox || wy < g.oy || wz < v.origin_z) return false;
+  mx = (wx - g.ox) / g.res;
+  my = (wy - g.oy) / g.res;
+  mz = (wz - v.origin_z) / v.z_resolution;
+  return mx < g.sx && my < g.sy && mz < v.size_z;
+}
+
+// One ray of VoxelLayer::raytraceFreespace (voxel_layer.cpp:262-350) reduced to what VoxelGrid::raytraceLine /
+// bresenham3D (voxel_grid.h:226-297) walks: start cell, dominant-axis length and the closed-form minor-axis steps.
+struct VoxelRay {
+  bool valid;
+  long long start;  // y0 * pitch + x0
+  int z0;
+  unsigned da, db, dc, end;  // dominant / minor extents, number of bresenham iterations (cells 0 .. end are visited)
+  int off_a, off_b, off_c;   // grid offsets per step; 0 for the axis that moves the z mask
+  int dz_a, dz_b, dz_c;      // z steps per step of that axis (+-1 on the z axis, else 0)
+  double ex, ey;             // updateRaytraceBounds end point
+};
+
+__device__ VoxelRay voxel_ray_setup(const Geom& g, const VoxelGeom& v, const DevObs& o, const float* __restrict__ xyz,
+                                    int point, double max_obstacle_height) {
+  VoxelRay r;
+  r.valid = false;
+  double sensor_x, sensor_y, sensor_z;
+  const double ox = o.ox, oy = o.oy, oz = o.oz;
+  if (!world_to_map_3d_float(g, v, ox, oy, oz, sensor_x, sensor_y, sensor_z)) return r;  // whole observation skipped
+  const double map_end_x = g.ox + (g.sx - 1 + 0.5) * g.res, map_end_y = g.oy + (g.sy - 1 + 0.5) * g.res;  // getSizeInMeters
+  double wpx = xyz[3 * (size_t)point], wpy = xyz[3 * (size_t)point + 1], wpz = xyz[3 * (size_t)point + 2];
+  const double distance = sqrt((wpx - ox) * (wpx - ox) + (wpy - oy) * (wpy - oy) + (wpz - oz) * (wpz - oz));
+  double scaling_fact = 1.0;
+  scaling_fact = fmax(fmin(scaling_fact, (distance - 2 * g.res) / distance), 0.0);
+  wpx = scaling_fact * (wpx - ox) + ox;
+  wpy = scaling_fact * (wpy - oy) + oy;
+  wpz = scaling_fact * (wpz - oz) + oz;
+  const double a = wpx - ox, b = wpy - oy, c = wpz - oz;
+  double t = 1.0;
+  if (wpz > max_obstacle_height) t = fmax(0.0, fmin(t, (max_obstacle_height - 0.01 - oz) / c));
+  else if (wpz < v.origin_z) t = fmin(t, (v.origin_z - oz) / c);
+  if (wpx < g.ox) t = fmin(t, (g.ox - ox) / a);
+  if (wpy < g.oy) t = fmin(t, (g.oy - oy) / b);
+  if (wpx > map_end_x) t = fmin(t, (map_end_x - ox) / a);
+  if (wpy > map_end_y) t = fmin(t, (map_end_y - oy) / b);
+  wpx = ox + a * t;
+  wpy = oy + b * t;
+  wpz = oz + c * t;
+  double px, py, pz;
+  if (!world_to_map_3d_float(g, v, wpx, wpy, wpz, px, py, pz)) return r;
+  // clearVoxelLineInMap's own end-point test (voxel_grid.cpp:133-137) holds by construction of both points
+  const unsigned cell_range = (unsigned)fmax(0.0, ceil(o.raytrace_range / g.res));  // cellDistance
+  const int dx = (int)px - (int)sensor_x, dy = (int)py - (int)sensor_y, dz = (int)pz - (int)sensor_z;
+  const unsigned adx = abs(dx), ady = abs(dy), adz = abs(dz);
+  const int off_dx = dx > 0 ? 1 : -1, off_dy = (dy > 0 ? 1 : -1) * (int)g.pitch, sgn_dz = dz > 0 ? 1 : -1;
+  const double dist = sqrt((sensor_x - px) * (sensor_x - px) + (sensor_y - py) * (sensor_y - py) +
+                           (sensor_z - pz) * (sensor_z - pz));
+  const double scale = fmin(1.0, cell_range / dist);
+  r.start = (long long)(unsigned)sensor_y * g.pitch + (unsigned)sensor_x;
+  r.z0 = (int)(unsigned)sensor_z;
+  r.dz_a = r.dz_b = r.dz_c = 0;
+  if (adx >= max(ady, adz)) {
+    r.da = adx; r.db = ady; r.dc = adz;
+    r.off_a = off_dx; r.off_b = off_dy; r.off_c = 0; r.dz_c = sgn_dz;
+  } else if (ady >= adz) {
+    r.da = ady; r.db = adx; r.dc = adz;
+    r.off_a = off_dy; r.off_b = off_dx; r.off_c = 0; r.dz_c = sgn_dz;
+  } else {
+    r.da = adz; r.db = adx; r.dc = ady;
+    r.off_a = 0; r.dz_a = sgn_dz; r.off_b = off_dx; r.off_c = off_dy;
+  }
+  r.end = min((unsigned)(scale * r.da), r.da);
+  const double ddx = wpx - ox, ddy = wpy - oy;  // updateRaytraceBounds (obstacle_layer.cpp:602-610)
+  const double s2 = fmin(1.0, o.raytrace_range / hypot(ddx, ddy));
+  r.ex = ox + ddx * s2;
+  r.ey = oy + ddy * s2;
+  r.valid = true;
+  return r;
+}
+
+// voxel i of the ray (0 <= i <= end): after i iterations the error accumulators of bresenham3D have produced
+// floor((da/2 + i*db) / da) steps on axis b and likewise on c
+__device__ __forceinline__ void voxel_ray_cell(const VoxelRay& r, unsigned i, long long& offset, int& z) {
+  const unsigned half = r.da / 2;
+  const unsigned nb = r.da ? (unsigned)((half + (unsigned long long)i * r.db) / r.da) : 0u;
+  const unsigned nc = r.da ? (unsigned)((half + (unsigned long long)i * r.dc) / r.da) : 0u;
+  offset = r.start + (long long)i * r.off_a + (long long)nb * r.off_b + (long long)nc * r.off_c;
+  z = r.z0 + (int)i * r.dz_a + (int)nb * r.dz_b + (int)nc * r.dz_c;
+}
+
+struct VoxelArgs {
+  uint8_t* grid;   // the layer's 2-D grid
+  uint32_t* vox;   // the columns, same indexing
+  Geom g;
+  VoxelGeom v;
+  const DevObs* clear;
+  const DevObs* mark;
+  const float* xyz;
+  int n_clear, total_rays, n_mark, total_marks;
+  double max_obstacle_height;
+  DevBox* box;
+  long long* mark_cells;  // total_marks entries: (offset << 5) | z, or -1
+  unsigned* ticket;
+  int do_poly;
+  PolyArgs poly;
+  int do_finalize;
+  BoundsArgs ba;
+  DevBox* boxes;
+  InflationBoundsState* infl;
+  DevWindow* win;
+};
+
+__device__ __forceinline__ const DevObs& obs_of(const DevObs* tab, int n, int index, int& local) {
+  int k = 0;
+  while (k + 1 < n && tab[k + 1].first_ray <= index) ++k;
+  local = tab[k].first_point + (index - tab[k].first_ray);
+  return tab[k];
+}
+
+__global__ void __launch_bounds__(kObstacleThreads) k_voxel_clear(VoxelArgs a) {
+  __shared__ unsigned long long s_box[kObstacleThreads / 32][4];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kObstacleThreads + threadIdx.x) >> 5;
+  BoxAcc acc;
+  if (warp < a.total_rays) {
+    int point;
+    const DevObs& o = obs_of(a.clear, a.n_clear, warp, point);
+    const VoxelRay r = voxel_ray_setup(a.g, a.v, o, a.xyz, point, a.max_obstacle_height);
+    if (r.valid) {
+      for (unsigned i = lane; i <= r.end; i += 32) {
+        long long off;
+        int z;
+        voxel_ray_cell(r, i, off, z);
+        atomicAnd(&a.vox[off], ~(0x00010001u << z));  // clear unknown and clear cell
+      }
+      if (lane == 0) acc.touch(r.ex, r.ey);
+    }
+  }
+  {  // this CTA's share of the marking tests (voxel_layer.cpp:136-177)
+    const int per_cta = (a.total_marks + gridDim.x - 1) / gridDim.x;
+    for (int i = threadIdx.x; i < per_cta; i += kObstacleThreads) {
+      const int t = blockIdx.x * per_cta + i;
+      if (t >= a.total_marks) continue;
+      int point;
+      const DevObs& o = obs_of(a.mark, a.n_mark, t, point);
+      const float fx = a.xyz[3 * (size_t)point], fy = a.xyz[3 * (size_t)point + 1], fz = a.xyz[3 * (size_t)point + 2];
+      long long cell = -1;
+      if (!(fz > a.max_obstacle_height)) {
+        const double sq_dist = (fx - o.ox) * (fx - o.ox) + (fy - o.oy) * (fy - o.oy) + (fz - o.oz) * (fz - o.oz);
+        if (!(sq_dist >= o.obstacle_range * o.obstacle_range)) {
+          const double wz = fz < a.v.origin_z ? a.v.origin_z : (double)fz;
+          const double wx = fx, wy = fy;
+          if (!(wx < a.g.ox || wy < a.g.oy || wz < a.v.origin_z)) {  // worldToMap3D, voxel_layer.h:117-130
+            const unsigned mx = (unsigned)(int)((wx - a.g.ox) / a.g.res), my = (unsigned)(int)((wy - a.g.oy) / a.g.res),
+                           mz = (unsigned)(int)((wz - a.v.origin_z) / a.v.z_resolution);
+            if (mx < a.g.sx && my < a.g.sy && mz < a.v.size_z) {
+              cell = (((long long)my * a.g.pitch + mx) << 5) | mz;
+              acc.touch((double)fx, (double)fy);  // mark_threshold is 0: every marked voxel lights its cell
+            }
+          }
+        }
+      }
+      a.mark_cells[t] = cell;
+    }
+  }
+  acc.flush_cta(a.box, s_box);
+}
+
+__global__ void __launch_bounds__(kObstacleThreads) k_voxel_commit(VoxelArgs a) {
+  __shared__ uint32_t poly_cells[kPolySmallCells], poly_sorted[kPolySmallCells];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kObstacleThreads + threadIdx.x) >> 5;
+  cudaTriggerProgrammaticLaunchCompletion();
+  if (warp < a.total_rays) {
+    int point;
+    const DevObs& o = obs_of(a.clear, a.n_clear, warp, point);
+    const VoxelRay r = voxel_ray_setup(a.g, a.v, o, a.xyz, point, a.max_obstacle_height);
+    if (r.valid) {
+      for (unsigned i = lane; i <= r.end; i += 32) {
+        long long off;
+        int z;
+        voxel_ray_cell(r, i, off, z);
+        const uint32_t col = a.vox[off];  // final: every clear of this cycle happened in k_voxel_clear
+        const unsigned unknown_bits = (uint16_t)(col >> 16) ^ (uint16_t)col, marked_bits = col >> 16;
+        if (bits_below_threshold(marked_bits, a.v.mark_threshold))
+          a.grid[off] = bits_below_threshold(unknown_bits, a.v.unknown_threshold) ? kFree : kNoInfo;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int t = threadIdx.x; t < a.total_marks; t += kObstacleThreads) {  // markVoxelInMap + LETHAL_OBSTACLE
+    const long long cell = a.mark_cells[t];
+    if (cell < 0) continue;
+    const long long off = cell >> 5;
+    const unsigned z = (unsigned)(cell & 31);
+    const uint32_t col = atomicOr(&a.vox[off], 0x00010001u << z) | (0x00010001u << z);
+    if (!bits_below_threshold(col >> 16, a.v.mark_threshold)) a.grid[off] = kLethal;
+  }
+  __syncthreads();
+  if (a.do_poly) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
+  if (threadIdx.x == 0) {
+    *a.ticket = 0;
+    if (a.do_finalize) {
+      __threadfence();
+      finalize_bounds(a.ba, a.boxes, a.infl, a.win);
+    }
+  }
+}
+
+// VoxelLayer::updateOrigin's column part (voxel_layer.cpp:371-438): same shift as k_shift_grid, unknown columns elsewhere
+__global__ void k_shift_voxels(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, unsigned sx, unsigned sy,
+                               unsigned pitch, int cell_ox, int cell_oy) {
+  unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned y = blockIdx.y;
+  if (x >= pitch || y >= sy) return;
+  uint32_t v = 0x0000ffffu;
+  long long ox = (long long)x + cell_ox, oy = (long long)y + cell_oy;
+  if (x < sx && ox >= 0 && ox < (long long)sx && oy >= 0 && oy < (long long)sy) v = src[(size_t)oy * pitch + ox];
+  dst[(size_t)y * pitch + x] = v;
+}
+
 __global__ void k_set_window(DevWindow* win, int x0, int xn, int y0, int yn) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     win->x0 = x0; win->xn = xn; win->y0 = y0; win->yn = yn;

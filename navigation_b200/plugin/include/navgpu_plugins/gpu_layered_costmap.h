@@ -51,6 +51,16 @@ class GpuLayeredCostmap {
                                                 max_obstacle_height, &id);
     return id;
   }
+  // VoxelLayer with cfg/VoxelPlugin.cfg's parameters (what Costmap2DROS creates for `map_type: voxel`,
+  // costmap_2d_ros.cpp:215-228); observations go through setObservations like for an obstacle layer
+  int addVoxelLayer(int combination_method = 1, bool footprint_clearing_enabled = true, double max_obstacle_height = 2.0,
+                    double origin_z = 0.0, double z_resolution = 0.2, int z_voxels = 10, int unknown_threshold = 15,
+                    int mark_threshold = 0) {
+    int id = -1;
+    status_ = navgpu_costmap_add_voxel_layer(handle_, combination_method, footprint_clearing_enabled, max_obstacle_height,
+                                             origin_z, z_resolution, z_voxels, unknown_threshold, mark_threshold, &id);
+    return id;
+  }
   int addInflationLayer(double inflation_radius = 0.55, double cost_scaling_factor = 10.0) {  // cfg/InflationPlugin.cfg
     int id = -1;
     status_ = navgpu_costmap_add_inflation_layer(handle_, inflation_radius, cost_scaling_factor, &id);

@@ -345,3 +345,21 @@ def test_c3_full_size_bit_exact_vs_checker(cuda, port):
         assert a[0] == b[0] == (0, 4000, 0, 4000)
         assert np.array_equal(a[2], b[2]), f"cycle {cyc}: obstacle layer differs in {(a[2] != b[2]).sum()} cells"
         assert np.array_equal(a[1], b[1]), f"cycle {cyc}: master grid differs in {(a[1] != b[1]).sum()} cells"
+
+
+@pytest.mark.parametrize("seed", range(200, 240))
+def test_voxel_layer_matches_checker(cuda, port, seed):
+    """VoxelLayer on the GPU (k_voxel_clear / k_voxel_commit: 3-D Bresenham clearing through uint32 voxel columns,
+    marking, rolling origin) against the checker: windows, voxel columns and the layer's 2-D grid bit-exact; the
+    master grid bit-exact unless the scenario inflates point-like marks (tie-order dependent cells, rare, one-sided)."""
+    a, inflated = sc.run_voxel_scenario(cuda, seed)
+    b, _ = sc.run_voxel_scenario(port, seed)
+    for cyc, (x, y) in enumerate(zip(a, b)):
+        assert x[0] == y[0] and x[4] == y[4], f"cycle {cyc}: window/origin {x[0]} {x[4]} vs {y[0]} {y[4]}"
+        assert np.array_equal(x[3], y[3]), f"cycle {cyc}: voxel columns differ in {(x[3] != y[3]).sum()} cells"
+        assert np.array_equal(x[2], y[2]), f"cycle {cyc}: voxel layer grid differs in {(x[2] != y[2]).sum()} cells"
+        diff = x[1] != y[1]
+        if inflated:
+            assert diff.sum() <= max(3, 2e-3 * diff.size) and (x[1][diff] > y[1][diff]).all()
+        else:
+            assert not diff.any(), f"cycle {cyc}: master differs in {diff.sum()} cells"
