@@ -467,8 +467,6 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     oa.do_finalize = (int)li == last_obstacle;
     if (oa.do_finalize) oa.ba = ba;
     oa.boxes = h->d_boxes; oa.infl = h->d_infl; oa.win = h->d_win;
-    static const int debug_skip = getenv("NAVGPU_DEBUG_SKIP") ? atoi(getenv("NAVGPU_DEBUG_SKIP")) : 0;
-    oa.debug_skip = debug_skip;
     const int blocks = std::max(1, (L.total_rays * 32 + kObstacleThreads - 1) / kObstacleThreads);
     k_obstacle_update<<<blocks, kObstacleThreads, 0, h->stream>>>(oa);
     NAVGPU_LAUNCHED(1);

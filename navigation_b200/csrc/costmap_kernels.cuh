@@ -483,7 +483,6 @@ struct ObstacleArgs {
   DevBox* boxes;
   InflationBoundsState* infl;
   DevWindow* win;
-  int debug_skip;  // measurement only (NAVGPU_DEBUG_SKIP): 1 marks, 2 polygon, 4 bounds, 8 ray tracing -- wrong results
 };
 constexpr int kObstacleThreads = 256;
 
@@ -499,12 +498,12 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   const DevObs* clear_tab = a.n_clear <= kInlineObs ? a.clear_inline : a.clear;
   const DevObs* mark_tab = a.n_mark <= kInlineObs ? a.mark_inline : a.mark;
   BoxAcc acc;
-  if (!(a.debug_skip & 8)) raytrace_ray(a.grid, a.g, clear_tab, a.n_clear, a.xyz, a.total_rays, acc, warp, lane);
+  raytrace_ray(a.grid, a.g, clear_tab, a.n_clear, a.xyz, a.total_rays, acc, warp, lane);
   {  // this CTA's share of the marking tests
     const int per_cta = (a.total_marks + gridDim.x - 1) / gridDim.x;
     for (int i = threadIdx.x; i < per_cta; i += kObstacleThreads) {
       const int t = blockIdx.x * per_cta + i;
-      if (t < a.total_marks && !(a.debug_skip & 1))
+      if (t < a.total_marks)
         mark_prepare(a.g, mark_tab, a.n_mark, a.xyz, a.max_obstacle_height, acc, a.mark_cells, t);
     }
   }
@@ -517,12 +516,12 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (!(a.debug_skip & 1)) mark_commit_cta(a.grid, a.mark_cells, a.total_marks);
+  mark_commit_cta(a.grid, a.mark_cells, a.total_marks);
   __syncthreads();
-  if (a.do_poly && !(a.debug_skip & 2)) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
+  if (a.do_poly) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
   if (threadIdx.x == 0) {
     *a.ticket = 0;  // re-armed for the next cycle
-    if (a.do_finalize && !(a.debug_skip & 4)) {
+    if (a.do_finalize) {
       __threadfence();
       finalize_bounds(a.ba, a.boxes, a.infl, a.win);
     }
