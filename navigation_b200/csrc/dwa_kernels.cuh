@@ -468,21 +468,23 @@ struct TrajResult {
 
 __device__ __forceinline__ double nan_quiet() { return __longlong_as_double(0x7ff8000000000000ll); }
 
+// Map cell (y << 16 | x) of one oriented footprint vertex of one pose, or -1 when it is off the map
+// (WorldModel::footprintCost world_model.h:65-86: rotate + translate; CostmapModel::footprintCost worldToMap).
+__device__ __forceinline__ int footprint_vertex_cell(const DwaScoreArgs& a, double x, double y, double cos_th, double sin_th,
+                                                     int v) {
+  const double wx = x + (a.fpx[v] * cos_th - a.fpy[v] * sin_th), wy = y + (a.fpx[v] * sin_th + a.fpy[v] * cos_th);
+  int cx, cy;
+  if (!dwa_world_to_map(a.g, wx, wy, cx, cy)) return -1;
+  return (cy << 16) | cx;
+}
+
 // One footprint edge of one pose: CostmapModel::lineCost over the LineIterator cells between the map cells of two
 // consecutive oriented footprint vertices (costmap_model.cpp:75-131, line_iterator.h:38-139).  Returns the maximum
 // cell cost along the edge, or -1 when a vertex is off the map or a cell is LETHAL / (NO_INFORMATION && !allow_unknown).
-__device__ int footprint_edge_cost(const DwaScoreArgs& a, double x, double y, double cos_th, double sin_th, int e) {
+__device__ int footprint_edge_cost(const DwaScoreArgs& a, int cell_p, int cell_q) {
   const DwaGeom& g = a.g;
-  const int e1 = e + 1 < a.nfp ? e + 1 : 0;
-  int px, py, qx, qy;
-  {
-    const double wx = x + (a.fpx[e] * cos_th - a.fpy[e] * sin_th), wy = y + (a.fpx[e] * sin_th + a.fpy[e] * cos_th);
-    if (!dwa_world_to_map(g, wx, wy, px, py)) return -1;
-  }
-  {
-    const double wx = x + (a.fpx[e1] * cos_th - a.fpy[e1] * sin_th), wy = y + (a.fpx[e1] * sin_th + a.fpy[e1] * cos_th);
-    if (!dwa_world_to_map(g, wx, wy, qx, qy)) return -1;
-  }
+  if ((cell_p | cell_q) < 0) return -1;  // a vertex off the map (costmap_model.cpp:79-90)
+  const int px = cell_p & 0xffff, py = cell_p >> 16, qx = cell_q & 0xffff, qy = cell_q >> 16;
   const int dx = abs(qx - px), dy = abs(qy - py);
   const int xinc = qx >= px ? 1 : -1, yinc = (qy >= py ? 1 : -1) * (int)g.pitch;
   const bool xmajor = dx >= dy;
@@ -515,7 +517,7 @@ __device__ __forceinline__ float sample_vth(const DwaScoreArgs& a, int i) {
 
 // scores one velocity sample with a whole warp; points_out (nullable) receives 3 doubles per trajectory point.
 // kScore = false only generates the trajectory (points, step count): the critics are skipped and cost stays NaN.
-constexpr int kWarpScratchDoubles = 128 + 16;  // 4 x 32 pose doubles + 32 ints
+constexpr int kWarpScratchDoubles = 128 + 16 + 16 * kMaxFootprint;  // 4 x 32 pose doubles, 32 ints, 32 x kMaxFootprint vertex cells
 template <bool kScore>
 __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int lane, double* terms_out,
                                    double* points_out, int points_capacity, double* warp_scratch) {
@@ -629,10 +631,18 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
     double occ = 0.0;
     bool fail = false;
     if (a.nfp >= 3) {
+      // every (point, vertex) cell once, then every (point, edge) walk between two of them
+      int* vcell = reinterpret_cast<int*>(warp_scratch + 128 + 16);  // [point][kMaxFootprint]
       const int items = cnt * a.nfp;
       for (int it = lane; it < items; it += 32) {
+        const int p = it / a.nfp, v = it - p * a.nfp;
+        vcell[p * kMaxFootprint + v] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
+      }
+      __syncwarp();
+      for (int it = lane; it < items; it += 32) {
         const int p = it / a.nfp, e = it - p * a.nfp;
-        const int ec = footprint_edge_cost(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], e);
+        const int e1 = e + 1 < a.nfp ? e + 1 : 0;
+        const int ec = footprint_edge_cost(a, vcell[p * kMaxFootprint + e], vcell[p * kMaxFootprint + e1]);
         atomicMax(&edge_max[p], ec < 0 ? 0x80000000u : (unsigned)ec);
       }
       __syncwarp();
