@@ -1268,6 +1268,7 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
       const uint32_t m0 = __funnelshift_r(rowmask[wi], rowmask[wi + 1], sh),
                      m1 = __funnelshift_r(rowmask[wi + 1], rowmask[wi + 2], sh),
                      m2 = __funnelshift_r(rowmask[wi + 2], rowmask[wi + 3], sh);
+      if ((m0 | m1 | (m2 & 0x3fu)) == 0) continue;  // no seeded row anywhere near these eight rows: nothing to inflate
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
         const uint32_t word = c < 4 ? m0 : (c < 8 ? m1 : m2);
