@@ -1190,6 +1190,7 @@ struct InflateArgs {
 
 __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   __shared__ uint32_t sbits[kIMaxRows * 4];       // seed words W0..W3 of each region row: columns tx0-32 .. tx0+95
+  __shared__ uint32_t pbits[kIMaxRows * 4];       // the same without interior seeds (see below)
   __shared__ uint32_t h2[kIMaxRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
   __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
@@ -1223,11 +1224,29 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   if (tid < kIMaskWords) rowmask[tid] = 0;
   if (!__syncthreads_or(any)) return;
 
+  // ---- interior seeds cannot be the nearest seed of any other cell: a seed whose four neighbours are seeds too has,
+  // for every non-seed cell p, a neighbouring seed strictly closer to p (step along the larger coordinate difference),
+  // so the minimum over all seeds is attained on the boundary seeds; the interior cell itself already holds LETHAL,
+  // which max() keeps.  Dropping them empties most rows of thick structures for phases 2 and 3.  Seeds on the rim
+  // of the loaded region (unknown neighbours) are kept.
+  for (int i = tid; i < rows * 4; i += kIThreads) {
+    const int r = i >> 2, wq = i & 3;
+    const uint32_t c = sbits[i];
+    uint32_t keep = c;
+    if (c != 0 && r > 0 && r + 1 < rows) {
+      const uint32_t left = (c << 1) | (wq > 0 ? sbits[i - 1] >> 31 : 0u);
+      const uint32_t right = (c >> 1) | (wq < 3 ? sbits[i + 1] << 31 : 0u);
+      keep = c & ~(left & right & sbits[i - 4] & sbits[i + 4]);
+    }
+    pbits[i] = keep;
+  }
+  __syncthreads();
+
   // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row)
   for (int r = warp; r < rows; r += kIThreads / 32) {
     // only seeds within R columns of the tile can matter: the top R bits of W0, the low R bits of W3
-    const uint32_t W0 = sbits[4 * r] & ~(0xffffffffu >> R), W1 = sbits[4 * r + 1], W2 = sbits[4 * r + 2],
-                   W3 = sbits[4 * r + 3] & ((1u << R) - 1u);
+    const uint32_t W0 = pbits[4 * r] & ~(0xffffffffu >> R), W1 = pbits[4 * r + 1], W2 = pbits[4 * r + 2],
+                   W3 = pbits[4 * r + 3] & ((1u << R) - 1u);
     if ((W0 | W1 | W2 | W3) == 0) continue;
     if (lane == 0) atomicOr(&rowmask[(r >> 5) + 1], 1u << (r & 31));
     const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
