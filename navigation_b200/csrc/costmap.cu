@@ -266,7 +266,11 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
       ia.cost_d2 = a.cost_d2;
       ia.seeds = reinterpret_cast<const uint32_t*>(seeds);
       dim3 igrid((a.sx + kITX - 1) / kITX, (a.sy + kITY - 1) / kITY);
-      NAVGPU_CUDA(launch_pdl(k_inflate, igrid, dim3(kIThreads), 0, stream, ia));
+      // the instantiation whose unrolled row walk just covers the effective reach (what k_inflate calls R)
+      const int reach = (int)sqrtf((float)a.reach2 + 0.5f);
+      if (reach <= 12) NAVGPU_CUDA(launch_pdl(k_inflate<12>, igrid, dim3(kIThreads), 0, stream, ia));
+      else if (reach <= 20) NAVGPU_CUDA(launch_pdl(k_inflate<20>, igrid, dim3(kIThreads), 0, stream, ia));
+      else NAVGPU_CUDA(launch_pdl(k_inflate<31>, igrid, dim3(kIThreads), 0, stream, ia));
       NAVGPU_LAUNCHED(1);
     }
     return NAVGPU_OK;

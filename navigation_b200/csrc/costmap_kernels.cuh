@@ -1188,6 +1188,9 @@ struct InflateArgs {
   const uint32_t* seeds;   // the bitmask written by k_merge_seed, viewed as 32-bit words
 };
 
+// RMAX bounds the effective reach (in cells) this instantiation can handle: the phase-3 walk is unrolled over
+// 8 + 2 * RMAX region rows, so a small RMAX keeps the kernel's code (and its instruction-cache footprint) small.
+template <int RMAX>
 __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   __shared__ uint32_t sbits[kIMaxRows * 4];       // seed words W0..W3 of each region row: columns tx0-32 .. tx0+95
   __shared__ uint32_t pbits[kIMaxRows * 4];       // the same without interior seeds (see below)
@@ -1229,6 +1232,8 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   // so the minimum over all seeds is attained on the boundary seeds; the interior cell itself already holds LETHAL,
   // which max() keeps.  Dropping them empties most rows of thick structures for phases 2 and 3.  Seeds on the rim
   // of the loaded region (unknown neighbours) are kept.
+  // Only seeds within R columns of the tile can matter (the top R bits of W0, the low R bits of W3): pbits holds the
+  // words already masked that way, and rowmask gets a bit for every row that still has one.
   for (int i = tid; i < rows * 4; i += kIThreads) {
     const int r = i >> 2, wq = i & 3;
     const uint32_t c = sbits[i];
@@ -1238,31 +1243,36 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
       const uint32_t right = (c >> 1) | (wq < 3 ? sbits[i + 1] << 31 : 0u);
       keep = c & ~(left & right & sbits[i - 4] & sbits[i + 4]);
     }
+    if (wq == 0) keep &= ~(0xffffffffu >> R);
+    if (wq == 3) keep &= (1u << R) - 1u;
     pbits[i] = keep;
+    if (keep) atomicOr(&rowmask[(r >> 5) + 1], 1u << (r & 31));
   }
   __syncthreads();
 
-  // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row)
-  for (int r = warp; r < rows; r += kIThreads / 32) {
-    // only seeds within R columns of the tile can matter: the top R bits of W0, the low R bits of W3
-    const uint32_t W0 = pbits[4 * r] & ~(0xffffffffu >> R), W1 = pbits[4 * r + 1], W2 = pbits[4 * r + 2],
-                   W3 = pbits[4 * r + 3] & ((1u << R) - 1u);
-    if ((W0 | W1 | W2 | W3) == 0) continue;
-    if (lane == 0) atomicOr(&rowmask[(r >> 5) + 1], 1u << (r & 31));
-    const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
-    uint32_t packed = 0;
+  // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row; warp w takes the
+  // seeded rows r = w mod 8, straight from the row mask)
+  for (int wi = 0; wi * 32 < rows; ++wi) {
+    uint32_t m = rowmask[wi + 1] & (0x01010101u << warp);
+    while (m) {
+      const int r = wi * 32 + __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t W0 = pbits[4 * r], W1 = pbits[4 * r + 1], W2 = pbits[4 * r + 2], W3 = pbits[4 * r + 3];
+      const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
+      uint32_t packed = 0;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int sh = (2 * lane + c) & 31;
-      const uint32_t right = __funnelshift_r(B, C, sh);      // bit k    <-> dx = +k
-      const uint32_t left = __funnelshift_rc(A, B, sh + 1);  // bit 31-k <-> dx = -k
-      int d = 64;
-      if (right) d = __ffs(right) - 1;
-      if (left) d = min(d, __clz(left));
-      const uint32_t hh = d <= R ? (uint32_t)(d * d) : kH2Inf;
-      packed |= hh << (16 * c);
+      for (int c = 0; c < 2; ++c) {
+        const int sh = (2 * lane + c) & 31;
+        const uint32_t right = __funnelshift_r(B, C, sh);      // bit k    <-> dx = +k
+        const uint32_t left = __funnelshift_rc(A, B, sh + 1);  // bit 31-k <-> dx = -k
+        int d = 64;
+        if (right) d = __ffs(right) - 1;
+        if (left) d = min(d, __clz(left));
+        const uint32_t hh = d <= R ? (uint32_t)(d * d) : kH2Inf;
+        packed |= hh << (16 * c);
+      }
+      h2[r * (kITX / 2) + lane] = packed;
     }
-    h2[r * (kITX / 2) + lane] = packed;
   }
   __syncthreads();
 
@@ -1277,32 +1287,37 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0x7fff7fffu;
     // Region rows that can matter for tile rows yr0 .. yr0 + 7 are r = yr0 + R + j with j in [-R, 7 + R].  The walk is
-    // unrolled over j in [-31, 38] so that dy = j - k is a compile-time constant: dy^2 becomes an immediate operand
-    // of VIADDMNMX and the row's address an immediate offset; rows without seeds cost one bit test, eight rows
+    // unrolled over j in [-RMAX, 7 + RMAX] so that dy = j - k is a compile-time constant: dy^2 becomes an immediate
+    // operand of VIADDMNMX and the row's address an immediate offset; rows without seeds cost one bit test, eight rows
     // without seeds one byte test.  Rows beyond +-R only ever add candidates above the reach, which changes nothing.
     {
+      constexpr int NJ = 8 + 2 * RMAX, NW = (NJ + 31) / 32, NB = (NJ + 7) / 8;
       const uint32_t* hb = h2 + (yr0 + R) * (kITX / 2) + lane;
-      const int p0 = yr0 + R + 1;  // position of j = -31 in rowmask (which is stored with a 32-row offset)
+      const int p0 = yr0 + R - RMAX + 32;  // position of j = -RMAX in rowmask (which is stored with a 32-row offset)
       const int wi = p0 >> 5, sh = p0 & 31;
-      const uint32_t m0 = __funnelshift_r(rowmask[wi], rowmask[wi + 1], sh),
-                     m1 = __funnelshift_r(rowmask[wi + 1], rowmask[wi + 2], sh),
-                     m2 = __funnelshift_r(rowmask[wi + 2], rowmask[wi + 3], sh);
-      if ((m0 | m1 | (m2 & 0x3fu)) == 0) continue;  // no seeded row anywhere near these eight rows: nothing to inflate
+      uint32_t mw[NW];
+      uint32_t anyrow = 0;
 #pragma unroll
-      for (int c = 0; c < 9; ++c) {
-        const uint32_t word = c < 4 ? m0 : (c < 8 ? m1 : m2);
-        const uint32_t bits8 = (word >> ((c & 3) * 8)) & 0xffu;
+      for (int q = 0; q < NW; ++q) {
+        mw[q] = __funnelshift_r(rowmask[wi + q], rowmask[wi + q + 1], sh);
+        if (q == NW - 1 && (NJ & 31) != 0) mw[q] &= (1u << (NJ & 31)) - 1u;
+        anyrow |= mw[q];
+      }
+      if (anyrow == 0) continue;  // no seeded row anywhere near these eight rows: nothing to inflate
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        const uint32_t bits8 = (mw[c >> 2] >> ((c & 3) * 8)) & 0xffu;
         if (bits8 == 0) continue;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          const int j = 8 * c + b - 31;
-          if (j > 38) continue;
+          const int j = 8 * c + b - RMAX;
+          if (j > 7 + RMAX) continue;
           if (bits8 & (1u << b)) {
             const uint32_t hh = hb[j * (kITX / 2)];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const int dy = j - k;
-              if (dy >= -31 && dy <= 31) acc[k] = __viaddmin_u16x2(hh, (uint32_t)(dy * dy) * 0x10001u, acc[k]);
+              if (dy >= -RMAX && dy <= RMAX) acc[k] = __viaddmin_u16x2(hh, (uint32_t)(dy * dy) * 0x10001u, acc[k]);
             }
           }
         }
@@ -1328,8 +1343,15 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
         const int k = 4 * half + q;
         if (cur[q] == 0xffffffffu) continue;
         const uint32_t d2 = __vminu2(acc[k], R2x2 + 0x10001u);  // out of reach -> table[reach2 + 1] = 0
-        const uint32_t c16 = (uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 16);
         const uint32_t old2 = cur[q];
+        if (__vcmpeq4(old2, 0xffffffffu) == 0) {  // (a uint16 load: the upper bytes are 0)
+          // neither cell is NO_INFORMATION (the usual case): a plain byte maximum (inflation_layer.cpp:253-254)
+          const uint32_t c8 = ((uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 8)) & ~keep_hi;
+          const uint32_t out = __vmaxu4(old2, c8);
+          if (out != old2) *reinterpret_cast<uint16_t*>(prow + (size_t)k * a.pitch) = (uint16_t)out;
+          continue;
+        }
+        const uint32_t c16 = (uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 16);
         const uint32_t o16 = __byte_perm(old2, 0, 0x4140);  // the two cells' bytes, one per 16-bit lane
         uint32_t r16 = __vmaxu2(o16, c16);
         // NO_INFORMATION is replaced only by costs >= INSCRIBED
