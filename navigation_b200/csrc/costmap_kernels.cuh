@@ -998,6 +998,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2;  // k_merge_seed: CTA = 256 columns x 32 rows
 constexpr int kITX = 64, kITY = 128, kIThreads = 256, kIMaxRows = kITY + 2 * 31;
 constexpr int kIMaskWords = (kIMaxRows + 32 + 70 + 31) / 32 + 1;
+constexpr int kISparseRows = 12;  // k_inflate phase 3: up to this many seeded rows per window take the set-bit walk
 constexpr uint32_t kH2Inf = 0x3000;  // "no seed within R on this row" (as a squared distance, per 16-bit half)
 
 // layout of the seed bitmask: one row per grid row, 2 zero pad groups (32 cells) on either side of the row
@@ -1286,10 +1287,13 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     uint32_t acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0x7fff7fffu;
-    // Region rows that can matter for tile rows yr0 .. yr0 + 7 are r = yr0 + R + j with j in [-R, 7 + R].  The walk is
-    // unrolled over j in [-RMAX, 7 + RMAX] so that dy = j - k is a compile-time constant: dy^2 becomes an immediate
-    // operand of VIADDMNMX and the row's address an immediate offset; rows without seeds cost one bit test, eight rows
-    // without seeds one byte test.  Rows beyond +-R only ever add candidates above the reach, which changes nothing.
+    // Region rows that can matter for tile rows yr0 .. yr0 + 7 are r = yr0 + R + j with j in [-R, 7 + R]; rows beyond
+    // +-R only ever add candidates above the reach, which changes nothing.  Two walks over the row mask of
+    // j in [-RMAX, 7 + RMAX] (warp-uniform either way):
+    //  * few seeded rows (the usual case: walls, shelves): visit the set bits only; dy^2 = (j - k)^2 for k = 0..7
+    //    comes from one three-input add per k, (j-k)^2 = (j-k+1)^2 - (2j+1) + 2k, on both 16-bit halves at once;
+    //  * many seeded rows: the walk unrolled over j, so that dy^2 is an immediate operand of VIADDMNMX and the row's
+    //    address an immediate offset; rows without seeds cost one bit test, eight such rows one byte test.
     {
       constexpr int NJ = 8 + 2 * RMAX, NW = (NJ + 31) / 32, NB = (NJ + 7) / 8;
       const uint32_t* hb = h2 + (yr0 + R) * (kITX / 2) + lane;
@@ -1297,27 +1301,49 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
       const int wi = p0 >> 5, sh = p0 & 31;
       uint32_t mw[NW];
       uint32_t anyrow = 0;
+      int nrows = 0;
 #pragma unroll
       for (int q = 0; q < NW; ++q) {
         mw[q] = __funnelshift_r(rowmask[wi + q], rowmask[wi + q + 1], sh);
         if (q == NW - 1 && (NJ & 31) != 0) mw[q] &= (1u << (NJ & 31)) - 1u;
         anyrow |= mw[q];
+        nrows += __popc(mw[q]);
       }
       if (anyrow == 0) continue;  // no seeded row anywhere near these eight rows: nothing to inflate
+      if (nrows <= kISparseRows) {
 #pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        const uint32_t bits8 = (mw[c >> 2] >> ((c & 3) * 8)) & 0xffu;
-        if (bits8 == 0) continue;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int j = 8 * c + b - RMAX;
-          if (j > 7 + RMAX) continue;
-          if (bits8 & (1u << b)) {
+        for (int q = 0; q < NW; ++q) {
+          uint32_t m = mw[q];
+          while (m) {
+            const int j = __ffs(m) - 1 + 32 * q - RMAX;
+            m &= m - 1;
             const uint32_t hh = hb[j * (kITX / 2)];
+            uint32_t q2 = (uint32_t)(j * j) * 0x10001u;                // dy^2 for k = 0, in both halves
+            const uint32_t nstep = (uint32_t)(-(2 * j + 1)) * 0x10001u;  // -(2j + 1), likewise (mod 2^32: exact)
+            acc[0] = __viaddmin_u16x2(hh, q2, acc[0]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int dy = j - k;
-              if (dy >= -RMAX && dy <= RMAX) acc[k] = __viaddmin_u16x2(hh, (uint32_t)(dy * dy) * 0x10001u, acc[k]);
+            for (int k = 1; k < 8; ++k) {
+              q2 = q2 + nstep + (uint32_t)(2 * k) * 0x10001u;
+              acc[k] = __viaddmin_u16x2(hh, q2, acc[k]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          const uint32_t bits8 = (mw[c >> 2] >> ((c & 3) * 8)) & 0xffu;
+          if (bits8 == 0) continue;
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            const int j = 8 * c + b - RMAX;
+            if (j > 7 + RMAX) continue;
+            if (bits8 & (1u << b)) {
+              const uint32_t hh = hb[j * (kITX / 2)];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int dy = j - k;
+                if (dy >= -RMAX && dy <= RMAX) acc[k] = __viaddmin_u16x2(hh, (uint32_t)(dy * dy) * 0x10001u, acc[k]);
+              }
             }
           }
         }
