@@ -238,6 +238,60 @@ int navgpu_fleet_step(navgpu_fleet* f, const double* poses, const double* vels, 
 int navgpu_fleet_get_costmap(navgpu_fleet* f, int robot, uint8_t* host_out);
 int navgpu_fleet_get_oscillation_mask(navgpu_fleet* f, int robot, int* mask_out);
 
+
+/* ---- legacy base_local_planner::TrajectoryPlanner ---------------------------------------------
+ * The rollout planner behind TrajectoryPlannerROS (base_local_planner/src/trajectory_planner.cpp): the two MapGrid
+ * wavefronts (path_map_, goal_map_) and generateTrajectory for every velocity sample of createTrajectories run on
+ * the device; the sequential selection among the scored samples (in-place rotation / strafing / escape rules and
+ * their oscillation flags, :560-905) is scalar bookkeeping and stays on the host.  Replaces
+ * base_local_planner::TrajectoryPlanner::{updatePlan, findBestPath, scoreTrajectory, checkTrajectory}
+ * (include/base_local_planner/trajectory_planner.h:116-212). */
+typedef struct {
+  double acc_lim_x, acc_lim_y, acc_lim_theta;
+  double sim_time, sim_granularity, angular_sim_granularity, sim_period;
+  double pdist_scale, gdist_scale, occdist_scale;
+  double heading_lookahead, oscillation_reset_dist, escape_reset_dist, escape_reset_theta;
+  double max_vel_x, min_vel_x, max_vel_th, min_vel_th, min_in_place_vel_th, backup_vel;
+  double heading_scoring_timestep, stop_time_buffer;
+  double y_vels[8];
+  int32_t n_y_vels, vx_samples, vtheta_samples;
+  int32_t holonomic_robot, dwa, heading_scoring, simple_attractor;
+  int32_t allow_unknown;
+} navgpu_tp_config;
+
+typedef struct {
+  double cost, xv, yv, thetav; /* the returned Trajectory's cost_, xv_, yv_, thetav_ */
+  int32_t n_points;
+  /* bit0 stuck_left, 1 stuck_right, 2 stuck_left_strafe, 3 stuck_right_strafe, 4 rotating_left, 5 rotating_right,
+   * 6 strafe_left, 7 strafe_right, 8 escaping_ (trajectory_planner.h:283-288) */
+  int32_t flags;
+} navgpu_tp_result;
+
+typedef struct navgpu_tp navgpu_tp;
+
+/* TrajectoryPlannerROS::initialize's defaults (trajectory_planner_ros.cpp:116-213) */
+void navgpu_tp_default_config(navgpu_tp_config* cfg);
+/* TrajectoryPlanner ctor (trajectory_planner.cpp:135-187); heading_scoring is NAVGPU_ERR_UNSUPPORTED */
+int navgpu_tp_create(navgpu_tp** out, const navgpu_tp_config* cfg, uint32_t size_x, uint32_t size_y, double resolution,
+                     const double* footprint_xy, int n_footprint, int device);
+int navgpu_tp_destroy(navgpu_tp* h);
+int navgpu_tp_set_costmap(navgpu_tp* h, const uint8_t* host_grid, double origin_x, double origin_y);
+int navgpu_tp_set_costmap_device(navgpu_tp* h, const uint8_t* dev_grid, uint32_t pitch, double origin_x,
+                                 double origin_y);
+/* TrajectoryPlanner::updatePlan(new_plan, compute_dists = false), trajectory_planner.cpp:477-502 */
+int navgpu_tp_update_plan(navgpu_tp* h, const double* plan_xy, int n);
+/* TrajectoryPlanner::findBestPath (:908-980): footprint cells -> within_robot, both wavefronts, every sample of
+ * createTrajectories scored, the reference's selection; points (nullable): 3 * points_capacity doubles */
+int navgpu_tp_find_best_path(navgpu_tp* h, const double pose[3], const double vel[3], navgpu_tp_result* result,
+                             double* points, int points_capacity);
+/* TrajectoryPlanner::scoreTrajectory (:520-535; checkTrajectory is `cost >= 0`) on the maps of the last findBestPath */
+int navgpu_tp_score_trajectory(navgpu_tp* h, const double pose[3], const double vel[3], const double vel_samples[3],
+                               double* cost_out);
+/* path_map_ (which = 0) / goal_map_ (1) target_dist after the last findBestPath, fp64, host */
+int navgpu_tp_get_grid(navgpu_tp* h, int which, double* host_out);
+/* number of velocity samples the last findBestPath scored on the device */
+int navgpu_tp_last_sample_count(navgpu_tp* h, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,23 @@ class DwaResult(C.Structure):
                 ("n_points", C.c_int32)]
 
 
+class TpConfig(C.Structure):
+    """navgpu_tp_config: the legacy base_local_planner::TrajectoryPlanner's parameters."""
+    _fields_ = [(n, C.c_double) for n in (
+        "acc_lim_x", "acc_lim_y", "acc_lim_theta", "sim_time", "sim_granularity", "angular_sim_granularity",
+        "sim_period", "pdist_scale", "gdist_scale", "occdist_scale", "heading_lookahead", "oscillation_reset_dist",
+        "escape_reset_dist", "escape_reset_theta", "max_vel_x", "min_vel_x", "max_vel_th", "min_vel_th",
+        "min_in_place_vel_th", "backup_vel", "heading_scoring_timestep", "stop_time_buffer")] + [
+            ("y_vels", C.c_double * 8)] + [(n, C.c_int32) for n in (
+                "n_y_vels", "vx_samples", "vtheta_samples", "holonomic_robot", "dwa", "heading_scoring",
+                "simple_attractor", "allow_unknown")]
+
+
+class TpResult(C.Structure):
+    _fields_ = [("cost", C.c_double), ("xv", C.c_double), ("yv", C.c_double), ("thetav", C.c_double),
+                ("n_points", C.c_int32), ("flags", C.c_int32)]
+
+
 _u8p = C.POINTER(C.c_uint8)
 _i8p = C.POINTER(C.c_int8)
 _f64p = C.POINTER(C.c_double)
@@ -126,6 +143,16 @@ SIGNATURES = {
     "navgpu_fleet_step": (C.c_int, [C.c_void_p, _f64p, _f64p, C.POINTER(DwaResult)]),
     "navgpu_fleet_get_costmap": (C.c_int, [C.c_void_p, C.c_int, _u8p]),
     "navgpu_fleet_get_oscillation_mask": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
+    "navgpu_tp_default_config": (None, [C.POINTER(TpConfig)]),
+    "navgpu_tp_create": (C.c_int, [_vpp, C.POINTER(TpConfig), C.c_uint32, C.c_uint32, C.c_double, _f64p, C.c_int, C.c_int]),
+    "navgpu_tp_destroy": (C.c_int, [C.c_void_p]),
+    "navgpu_tp_set_costmap": (C.c_int, [C.c_void_p, _u8p, C.c_double, C.c_double]),
+    "navgpu_tp_set_costmap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_double]),
+    "navgpu_tp_update_plan": (C.c_int, [C.c_void_p, _f64p, C.c_int]),
+    "navgpu_tp_find_best_path": (C.c_int, [C.c_void_p, _f64p, _f64p, C.POINTER(TpResult), _f64p, C.c_int]),
+    "navgpu_tp_score_trajectory": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, _f64p]),
+    "navgpu_tp_get_grid": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
+    "navgpu_tp_last_sample_count": (C.c_int, [C.c_void_p, _i32p]),
 }
 
 
@@ -405,6 +432,73 @@ class Dwa:
         return out
 
 
+class TrajectoryPlanner:
+    """The legacy base_local_planner::TrajectoryPlanner (navgpu_tp_*)."""
+
+    def __init__(self, api, size_x, size_y, resolution, footprint_xy, device=0, **overrides):
+        self.api, self.lib = api, api.lib
+        self.size_x, self.size_y = size_x, size_y
+        self.cfg = TpConfig()
+        self.lib.navgpu_tp_default_config(C.byref(self.cfg))
+        for k, v in overrides.items():
+            if k == "y_vels":
+                for j, y in enumerate(v):
+                    self.cfg.y_vels[j] = y
+                self.cfg.n_y_vels = len(v)
+            else:
+                setattr(self.cfg, k, v)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        h = C.c_void_p()
+        api.check(self.lib.navgpu_tp_create(C.byref(h), C.byref(self.cfg), size_x, size_y, resolution, _p(f, _f64p),
+                                            f.shape[0], device))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.navgpu_tp_destroy(self.h)
+            self.h = None
+
+    def set_costmap(self, grid, origin_x=0.0, origin_y=0.0):
+        a = np.ascontiguousarray(grid, dtype=np.uint8)
+        assert a.size == self.size_x * self.size_y
+        self.api.check(self.lib.navgpu_tp_set_costmap(self.h, _p(a, _u8p), origin_x, origin_y))
+
+    def set_costmap_device(self, dev_ptr, pitch, origin_x, origin_y):
+        self.api.check(self.lib.navgpu_tp_set_costmap_device(self.h, C.c_void_p(dev_ptr), pitch, origin_x, origin_y))
+
+    def update_plan(self, plan_xy):
+        a = np.ascontiguousarray(plan_xy, dtype=np.float64).reshape(-1, 2)
+        self.api.check(self.lib.navgpu_tp_update_plan(self.h, _p(a, _f64p), a.shape[0]))
+
+    def find_best_path(self, pose, vel, max_points=4096):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        res = TpResult()
+        pts = np.zeros((max_points, 3))
+        self.api.check(self.lib.navgpu_tp_find_best_path(self.h, _p(p, _f64p), _p(v, _f64p), C.byref(res), _p(pts, _f64p),
+                                                         max_points))
+        return dict(cost=res.cost, xv=res.xv, yv=res.yv, thetav=res.thetav, flags=res.flags,
+                    points=pts[:res.n_points].copy())
+
+    def score_trajectory(self, pose, vel, vel_samples):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        s = np.ascontiguousarray(vel_samples, dtype=np.float64)
+        c = C.c_double()
+        self.api.check(self.lib.navgpu_tp_score_trajectory(self.h, _p(p, _f64p), _p(v, _f64p), _p(s, _f64p), C.byref(c)))
+        return float(c.value)
+
+    def grid(self, which):
+        out = np.empty((self.size_y, self.size_x), dtype=np.float64)
+        self.api.check(self.lib.navgpu_tp_get_grid(self.h, which, _p(out, _f64p)))
+        return out
+
+    def last_sample_count(self):
+        n = C.c_int32()
+        self.api.check(self.lib.navgpu_tp_last_sample_count(self.h, C.byref(n)))
+        return int(n.value)
+
+
 class Fleet:
     """N independent robots per control cycle (navgpu_fleet_*): local-costmap inflation + DWA scoring, batched."""
 
@@ -500,6 +594,9 @@ class Api:
 
     def fleet(self, *a, **k):
         return Fleet(self, *a, **k)
+
+    def trajectory_planner(self, *a, **k):
+        return TrajectoryPlanner(self, *a, **k)
 
     def build_cost_table(self, resolution, inscribed_radius, inflation_radius, cost_scaling_factor):
         cap = 256 * 256

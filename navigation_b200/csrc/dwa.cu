@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "dwa_kernels.cuh"
+#include "tp_kernels.cuh"
 
 using namespace navgpu;
 
@@ -227,7 +228,11 @@ Samples enumerate_samples(const navgpu_dwa_config& cfg, const float pos[3], cons
 
 // MapGridCostFunction::prepare for `n_ctas` grids (jobs_per_robot per robot): the register-resident bit-sliced kernel
 // when the map's bit words fit 4 per thread, else the general shared-memory kernel
-int launch_mapgrid(navgpu_dwa* h, const MapGridArgs& ma, int n_ctas, int jobs_per_robot) {
+struct MapGridTarget {  // what launch_mapgrid needs of a planner handle
+  unsigned sx, sy;
+  cudaStream_t stream;
+};
+int launch_mapgrid(const MapGridTarget* h, const MapGridArgs& ma, int n_ctas, int jobs_per_robot) {
   const int W = (h->sx + 31) / 32, NW = W * (int)h->sy;
   int planes = 1;
   while ((1ull << planes) <= (unsigned long long)h->sx * h->sy + 1) ++planes;  // levels go up to n_cells
@@ -255,6 +260,11 @@ int launch_mapgrid(navgpu_dwa* h, const MapGridArgs& ma, int n_ctas, int jobs_pe
   }
   NAVGPU_LAUNCHED(1);
   return NAVGPU_OK;
+}
+
+int launch_mapgrid(navgpu_dwa* h, const MapGridArgs& ma, int n_ctas, int jobs_per_robot) {
+  const MapGridTarget t{h->sx, h->sy, h->stream};
+  return launch_mapgrid(&t, ma, n_ctas, jobs_per_robot);
 }
 
 // uploads the per-cycle inputs and launches the 4 MapGrid wavefronts; fills the scoring arguments
@@ -988,3 +998,6 @@ int navgpu_fleet_get_oscillation_mask(navgpu_fleet* f, int robot, int* mask_out)
 }
 
 }  // extern "C"
+
+// the legacy TrajectoryPlanner shares this translation unit's kernels (MapGrid wavefront, footprint walks)
+#include "trajectory_planner.inc"

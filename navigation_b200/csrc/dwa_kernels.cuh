@@ -69,6 +69,9 @@ struct MapGridJob {
   int n_points;
   int local_goal;  // setLocalGoal (last seed only) vs setTargetCells
   uint32_t* dist;  // sx*sy, row-major, no pitch
+  // MapCell::within_robot as a bit per cell ((sx+31)/32 words per row), or null: obstacle cells under it stay
+  // passable (map_grid.cpp:109-112; only the legacy TrajectoryPlanner marks cells, trajectory_planner.cpp:918-930)
+  const uint32_t* within_robot = nullptr;
 };
 struct MapGridRobot {  // fleet mode: one per robot, in device memory
   DwaGeom g;
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapG
     const int wi = tid + q * kMapGridThreads;
     P[q] = 0;
     if (wi < NW) {
-      P[q] = mapgrid_passable(g, a.allow_unknown, wi / W, wi % W);
+      P[q] = mapgrid_passable(g, a.allow_unknown, wi / W, wi % W) | (job.within_robot ? job.within_robot[wi] : 0u);
       F0[wi] = 0;
       F1[wi] = 0;
     }
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare(MapGridArgs
       const bool obstacle = c == kLethal || c == kInscribed || (c == kNoInfo && !a.allow_unknown);  // map_grid.cpp:109-116
       p |= (uint32_t)(!obstacle) << b;
     }
-    P[wi] = p;
+    P[wi] = p | (job.within_robot ? job.within_robot[wi] : 0u);
     V[wi] = 0;
     F0[wi] = 0;
     F1[wi] = 0;
@@ -470,7 +473,8 @@ __device__ __forceinline__ double nan_quiet() { return __longlong_as_double(0x7f
 
 // Map cell (y << 16 | x) of one oriented footprint vertex of one pose, or -1 when it is off the map
 // (WorldModel::footprintCost world_model.h:65-86: rotate + translate; CostmapModel::footprintCost worldToMap).
-__device__ __forceinline__ int footprint_vertex_cell(const DwaScoreArgs& a, double x, double y, double cos_th, double sin_th,
+template <class Args>
+__device__ __forceinline__ int footprint_vertex_cell(const Args& a, double x, double y, double cos_th, double sin_th,
                                                      int v) {
   const double wx = x + (a.fpx[v] * cos_th - a.fpy[v] * sin_th), wy = y + (a.fpx[v] * sin_th + a.fpy[v] * cos_th);
   int cx, cy;
@@ -481,7 +485,8 @@ __device__ __forceinline__ int footprint_vertex_cell(const DwaScoreArgs& a, doub
 // One footprint edge of one pose: CostmapModel::lineCost over the LineIterator cells between the map cells of two
 // consecutive oriented footprint vertices (costmap_model.cpp:75-131, line_iterator.h:38-139).  Returns the maximum
 // cell cost along the edge, or -1 when a vertex is off the map or a cell is LETHAL / (NO_INFORMATION && !allow_unknown).
-__device__ int footprint_edge_cost(const DwaScoreArgs& a, int cell_p, int cell_q) {
+template <class Args>
+__device__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
   const DwaGeom& g = a.g;
   if ((cell_p | cell_q) < 0) return -1;  // a vertex off the map (costmap_model.cpp:79-90)
   const int px = cell_p & 0xffff, py = cell_p >> 16, qx = cell_q & 0xffff, qy = cell_q >> 16;

@@ -140,6 +140,43 @@ int navo_line_cells(int x0, int y0, int x1, int y1, int32_t* xy_out, int capacit
 void navo_mapgrid_bfs(const uint8_t* costs, uint32_t size_x, uint32_t size_y, const int32_t* seeds_xy, int n_seeds,
                       int allow_unknown, double* dist_out);
 
+/* ---- legacy base_local_planner::TrajectoryPlanner (base_local_planner/src/trajectory_planner.cpp), SURVEY 8f-4:
+ * the second consumer of the rollout scorer.  Implemented by libnavref.so only (the compiled reference); the CUDA
+ * path is checked against it directly and against golden fixtures generated from it (tests/golden/tp_*.npz). */
+typedef struct {
+  double acc_lim_x, acc_lim_y, acc_lim_theta;
+  double sim_time, sim_granularity, angular_sim_granularity, sim_period;
+  double pdist_scale, gdist_scale, occdist_scale;
+  double heading_lookahead, oscillation_reset_dist, escape_reset_dist, escape_reset_theta;
+  double max_vel_x, min_vel_x, max_vel_th, min_vel_th, min_in_place_vel_th, backup_vel;
+  double heading_scoring_timestep, stop_time_buffer;
+  double y_vels[8];
+  int32_t n_y_vels, vx_samples, vtheta_samples;
+  int32_t holonomic_robot, dwa, heading_scoring, simple_attractor;
+  int32_t allow_unknown; /* indeterminate in the reference (uninitialised Costmap2D copy); honoured by the CUDA path */
+} navo_tp_config;
+typedef struct {
+  double cost, xv, yv, thetav;
+  int32_t n_points;
+  /* bit0 stuck_left, 1 stuck_right, 2 stuck_left_strafe, 3 stuck_right_strafe, 4 rotating_left, 5 rotating_right,
+   * 6 strafe_left, 7 strafe_right, 8 escaping_ */
+  int32_t flags;
+} navo_tp_result;
+void navo_tp_default_config(navo_tp_config* cfg); /* trajectory_planner_ros.cpp:116-213 defaults */
+void* navo_tp_create(const navo_tp_config* cfg, uint32_t size_x, uint32_t size_y, double resolution,
+                     const double* footprint_xy, int n_footprint);
+void navo_tp_destroy(void* h);
+void navo_tp_set_costmap(void* h, const uint8_t* grid, double origin_x, double origin_y);
+/* TrajectoryPlanner::updatePlan(plan, compute_dists = false), trajectory_planner.cpp:477-502 */
+void navo_tp_update_plan(void* h, const double* plan_xy, int n);
+/* TrajectoryPlanner::findBestPath :908-980; points = 3 doubles per point of the returned trajectory; returns 0 */
+int navo_tp_find_best_path(void* h, const double pose[3], const double vel[3], navo_tp_result* result, double* points,
+                           int points_capacity);
+/* TrajectoryPlanner::scoreTrajectory :520-535 on the distance maps of the last findBestPath */
+double navo_tp_score_trajectory(void* h, const double pose[3], const double vel[3], const double vel_samples[3]);
+/* path_map_ (0) / goal_map_ (1) target_dist after the last findBestPath */
+void navo_tp_get_grid(void* h, int which, double* out);
+
 const char* navo_impl_name(void);
 
 #ifdef __cplusplus

@@ -39,6 +39,23 @@ class DwaResult(C.Structure):
                 ("n_points", C.c_int32)]
 
 
+class TpConfig(C.Structure):
+    """navo_tp_config / navgpu_tp_config: the legacy base_local_planner::TrajectoryPlanner's parameters."""
+    _fields_ = [(n, C.c_double) for n in (
+        "acc_lim_x", "acc_lim_y", "acc_lim_theta", "sim_time", "sim_granularity", "angular_sim_granularity",
+        "sim_period", "pdist_scale", "gdist_scale", "occdist_scale", "heading_lookahead", "oscillation_reset_dist",
+        "escape_reset_dist", "escape_reset_theta", "max_vel_x", "min_vel_x", "max_vel_th", "min_vel_th",
+        "min_in_place_vel_th", "backup_vel", "heading_scoring_timestep", "stop_time_buffer")] + [
+            ("y_vels", C.c_double * 8)] + [(n, C.c_int32) for n in (
+                "n_y_vels", "vx_samples", "vtheta_samples", "holonomic_robot", "dwa", "heading_scoring",
+                "simple_attractor", "allow_unknown")]
+
+
+class TpResult(C.Structure):
+    _fields_ = [("cost", C.c_double), ("xv", C.c_double), ("yv", C.c_double), ("thetav", C.c_double),
+                ("n_points", C.c_int32), ("flags", C.c_int32)]
+
+
 _u8p = C.POINTER(C.c_uint8)
 _f64p = C.POINTER(C.c_double)
 _i32p = C.POINTER(C.c_int32)
@@ -93,10 +110,26 @@ def _declare(lib, prefix):
         "mapgrid_bfs": (None, [_u8p, u, u, _i32p, i, i, _f64p]),
         "impl_name": (C.c_char_p, []),
     }
+    # the legacy TrajectoryPlanner is exported by the compiled reference only
+    optional = {
+        "tp_default_config": (None, [C.POINTER(TpConfig)]),
+        "tp_create": (vp, [C.POINTER(TpConfig), u, u, d, _f64p, i]),
+        "tp_destroy": (None, [vp]),
+        "tp_set_costmap": (None, [vp, _u8p, d, d]),
+        "tp_update_plan": (None, [vp, _f64p, i]),
+        "tp_find_best_path": (i, [vp, _f64p, _f64p, C.POINTER(TpResult), _f64p, i]),
+        "tp_score_trajectory": (d, [vp, _f64p, _f64p, _f64p]),
+        "tp_get_grid": (None, [vp, i, _f64p]),
+    }
     for name, (res, args) in sig.items():
         f = g(name)
         f.restype = res
         f.argtypes = args
+    for name, (res, args) in optional.items():
+        if hasattr(lib, prefix + name):
+            f = g(name)
+            f.restype = res
+            f.argtypes = args
     return sig
 
 
@@ -283,6 +316,60 @@ class Dwa:
         self.lib.navo_dwa_prepare_only(self.h)
 
 
+class TrajectoryPlanner:
+    """The legacy base_local_planner::TrajectoryPlanner (compiled reference only)."""
+
+    def __init__(self, api, size_x, size_y, resolution, footprint_xy, **overrides):
+        self.lib = api.lib
+        self.size_x, self.size_y = size_x, size_y
+        self.cfg = TpConfig()
+        self.lib.navo_tp_default_config(C.byref(self.cfg))
+        for k, v in overrides.items():
+            if k == "y_vels":
+                for j, y in enumerate(v):
+                    self.cfg.y_vels[j] = y
+                self.cfg.n_y_vels = len(v)
+            else:
+                setattr(self.cfg, k, v)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        self.h = C.c_void_p(self.lib.navo_tp_create(C.byref(self.cfg), size_x, size_y, resolution, _p(f, _f64p),
+                                                    f.shape[0]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.navo_tp_destroy(self.h)
+            self.h = None
+
+    def set_costmap(self, grid, origin_x=0.0, origin_y=0.0):
+        a = np.ascontiguousarray(grid, dtype=np.uint8)
+        assert a.size == self.size_x * self.size_y
+        self.lib.navo_tp_set_costmap(self.h, _p(a, _u8p), origin_x, origin_y)
+
+    def update_plan(self, plan_xy):
+        a = np.ascontiguousarray(plan_xy, dtype=np.float64).reshape(-1, 2)
+        self.lib.navo_tp_update_plan(self.h, _p(a, _f64p), a.shape[0])
+
+    def find_best_path(self, pose, vel, max_points=4096):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        res = TpResult()
+        pts = np.zeros((max_points, 3))
+        self.lib.navo_tp_find_best_path(self.h, _p(p, _f64p), _p(v, _f64p), C.byref(res), _p(pts, _f64p), max_points)
+        return dict(cost=res.cost, xv=res.xv, yv=res.yv, thetav=res.thetav, flags=res.flags,
+                    points=pts[:res.n_points].copy())
+
+    def score_trajectory(self, pose, vel, vel_samples):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        s = np.ascontiguousarray(vel_samples, dtype=np.float64)
+        return float(self.lib.navo_tp_score_trajectory(self.h, _p(p, _f64p), _p(v, _f64p), _p(s, _f64p)))
+
+    def grid(self, which):
+        out = np.empty((self.size_y, self.size_x), dtype=np.float64)
+        self.lib.navo_tp_get_grid(self.h, which, _p(out, _f64p))
+        return out
+
+
 class Api:
     def __init__(self, kind):
         self.kind = kind
@@ -295,6 +382,9 @@ class Api:
 
     def dwa(self, *a, **k):
         return Dwa(self, *a, **k)
+
+    def trajectory_planner(self, *a, **k):
+        return TrajectoryPlanner(self, *a, **k)
 
     def interpret_values(self, values, track_unknown=True, unknown_cost_value=255, lethal_threshold=100,
                          trinary=True):

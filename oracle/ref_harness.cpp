@@ -33,6 +33,12 @@
 #include <base_local_planner/velocity_iterator.h>
 #include <base_local_planner/line_iterator.h>
 #include <base_local_planner/local_planner_limits.h>
+#include <base_local_planner/costmap_model.h>
+// the harness reads TrajectoryPlanner's private distance maps and oscillation flags (the reference translation unit
+// itself is compiled untouched; access specifiers do not change the layout)
+#define private public
+#include <base_local_planner/trajectory_planner.h>
+#undef private
 
 #include <cmath>
 #include <limits>
@@ -899,6 +905,89 @@ void navo_mapgrid_bfs(const uint8_t* costs, uint32_t size_x, uint32_t size_y, co
   mg.computeTargetDistance(q, cm);
   for (uint32_t y = 0; y < size_y; ++y)
     for (uint32_t x = 0; x < size_x; ++x) dist_out[size_t(y) * size_x + x] = mg(x, y).target_dist;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// legacy TrajectoryPlanner: the reference's own class, constructed as TrajectoryPlannerROS::initialize does
+// (trajectory_planner_ros.cpp:116-250) and driven through its public findBestPath / scoreTrajectory.
+namespace {
+struct TpHandle {
+  Costmap2D costmap;
+  CostmapModel world_model;
+  std::unique_ptr<TrajectoryPlanner> tp;
+  TpHandle(const navo_tp_config& c, unsigned sx, unsigned sy, double res, const double* fp, int nfp)
+      : costmap(sx, sy, res, 0.0, 0.0, 0), world_model(costmap) {
+    std::vector<double> yv(c.y_vels, c.y_vels + c.n_y_vels);
+    tp.reset(new TrajectoryPlanner(world_model, costmap, toPoints(fp, nfp), c.acc_lim_x, c.acc_lim_y, c.acc_lim_theta,
+                                   c.sim_time, c.sim_granularity, c.vx_samples, c.vtheta_samples, c.pdist_scale,
+                                   c.gdist_scale, c.occdist_scale, c.heading_lookahead, c.oscillation_reset_dist,
+                                   c.escape_reset_dist, c.escape_reset_theta, c.holonomic_robot != 0, c.max_vel_x,
+                                   c.min_vel_x, c.max_vel_th, c.min_vel_th, c.min_in_place_vel_th, c.backup_vel,
+                                   c.dwa != 0, c.heading_scoring != 0, c.heading_scoring_timestep, false,
+                                   c.simple_attractor != 0, yv, c.stop_time_buffer, c.sim_period,
+                                   c.angular_sim_granularity));
+  }
+};
+}  // namespace
+
+extern "C" {
+
+void navo_tp_default_config(navo_tp_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->acc_lim_x = 2.5; c->acc_lim_y = 2.5; c->acc_lim_theta = 3.2;
+  c->sim_time = 1.0; c->sim_granularity = 0.025; c->angular_sim_granularity = 0.025; c->sim_period = 0.05;
+  c->pdist_scale = 0.6; c->gdist_scale = 0.8; c->occdist_scale = 0.01;
+  c->heading_lookahead = 0.325; c->oscillation_reset_dist = 0.05; c->escape_reset_dist = 0.10;
+  c->escape_reset_theta = M_PI_4;
+  c->max_vel_x = 0.5; c->min_vel_x = 0.1; c->max_vel_th = 1.0; c->min_vel_th = -1.0; c->min_in_place_vel_th = 0.4;
+  c->backup_vel = -0.1; c->heading_scoring_timestep = 0.8; c->stop_time_buffer = 0.2;
+  c->y_vels[0] = -0.3; c->y_vels[1] = -0.1; c->y_vels[2] = 0.1; c->y_vels[3] = 0.3; c->n_y_vels = 4;
+  c->vx_samples = 3; c->vtheta_samples = 20;
+  c->holonomic_robot = 1; c->dwa = 1; c->heading_scoring = 0; c->simple_attractor = 0; c->allow_unknown = 0;
+}
+
+void* navo_tp_create(const navo_tp_config* cfg, uint32_t size_x, uint32_t size_y, double resolution,
+                     const double* footprint_xy, int n_footprint) {
+  return new TpHandle(*cfg, size_x, size_y, resolution, footprint_xy, n_footprint);
+}
+void navo_tp_destroy(void* hv) { delete static_cast<TpHandle*>(hv); }
+void navo_tp_set_costmap(void* hv, const uint8_t* grid, double ox, double oy) {
+  setCostmap(static_cast<TpHandle*>(hv)->costmap, grid, ox, oy);
+}
+void navo_tp_update_plan(void* hv, const double* plan_xy, int n) {
+  static_cast<TpHandle*>(hv)->tp->updatePlan(toPoses(plan_xy, n), false);
+}
+
+int navo_tp_find_best_path(void* hv, const double pose[3], const double vel[3], navo_tp_result* result, double* points,
+                           int points_capacity) {
+  TpHandle* h = static_cast<TpHandle*>(hv);
+  tf::Stamped<tf::Pose> gp, gv, drive;
+  gp.origin = tf::Vector3(pose[0], pose[1], 0.0); gp.yaw = pose[2];
+  gv.origin = tf::Vector3(vel[0], vel[1], 0.0); gv.yaw = vel[2];
+  Trajectory best = h->tp->findBestPath(gp, gv, drive);
+  result->cost = best.cost_; result->xv = best.xv_; result->yv = best.yv_; result->thetav = best.thetav_;
+  result->n_points = (int)best.getPointsSize();
+  const TrajectoryPlanner& t = *h->tp;
+  result->flags = (t.stuck_left ? 1 : 0) | (t.stuck_right ? 2 : 0) | (t.stuck_left_strafe ? 4 : 0) |
+                  (t.stuck_right_strafe ? 8 : 0) | (t.rotating_left ? 16 : 0) | (t.rotating_right ? 32 : 0) |
+                  (t.strafe_left ? 64 : 0) | (t.strafe_right ? 128 : 0) | (t.escaping_ ? 256 : 0);
+  for (int i = 0; i < result->n_points && i < points_capacity; ++i)
+    best.getPoint(i, points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+  return 0;
+}
+
+double navo_tp_score_trajectory(void* hv, const double pose[3], const double vel[3], const double vs[3]) {
+  return static_cast<TpHandle*>(hv)->tp->scoreTrajectory(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], vs[0],
+                                                         vs[1], vs[2]);
+}
+
+void navo_tp_get_grid(void* hv, int which, double* out) {
+  TpHandle* h = static_cast<TpHandle*>(hv);
+  MapGrid& g = which == 0 ? h->tp->path_map_ : h->tp->goal_map_;
+  for (unsigned y = 0; y < g.size_y_; ++y)
+    for (unsigned x = 0; x < g.size_x_; ++x) out[size_t(y) * g.size_x_ + x] = g(x, y).target_dist;
 }
 
 }  // extern "C"

@@ -16,7 +16,11 @@
 #include <algorithm>
 namespace boost {
 using std::recursive_mutex;
-using std::mutex;
+struct mutex : std::mutex {
+  struct scoped_lock : std::unique_lock<std::mutex> {
+    explicit scoped_lock(::boost::mutex& m) : std::unique_lock<std::mutex>(m) {}
+  };
+};
 using std::unique_lock;
 using std::shared_ptr;
 using std::bind;

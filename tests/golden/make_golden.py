@@ -18,6 +18,7 @@ import scenarios as sc  # noqa: E402
 COSTMAP_SEEDS = [0, 1, 2, 3, 5, 8, 13, 21]
 COSTMAP_TIEFREE_SEEDS = [100, 101, 102, 103, 104, 105]
 DWA_SEEDS = [0, 1, 3, 4, 9, 20, 32]
+TP_SEEDS = [0, 2, 5, 7, 11, 16, 23, 31]
 
 
 def main():
@@ -44,6 +45,17 @@ def main():
             for k in range(4):
                 d[f"grid{c}_{k}"] = r["grids"][k].astype(np.int32)
         np.savez_compressed(os.path.join(HERE, f"dwa_{seed}.npz"), **d)
+    port = po.load("port")  # the local costmaps come from the restatement, as in the tests
+    for seed in TP_SEEDS:
+        out = sc.run_tp_scenario(ref, port, seed)
+        d = {}
+        for c, r in enumerate(out):
+            d[f"scalars{c}"] = np.array([r["cost"], r["xv"], r["yv"], r["thetav"], r["flags"]], np.float64)
+            d[f"points{c}"] = r["points"]
+            d[f"scores{c}"] = r["scores"]
+            for k in range(2):
+                d[f"grid{c}_{k}"] = r["grids"][k].astype(np.int32)
+        np.savez_compressed(os.path.join(HERE, f"tp_{seed}.npz"), **d)
     print("golden fixtures written to", HERE)
 
 

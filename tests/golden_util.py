@@ -23,6 +23,24 @@ def dwa_cases():
             for p in sorted(glob.glob(os.path.join(GOLDEN, "dwa_*.npz")))]
 
 
+def tp_cases():
+    return [(int(re.match(r"tp_(\d+)\.npz", os.path.basename(p)).group(1)), p)
+            for p in sorted(glob.glob(os.path.join(GOLDEN, "tp_*.npz")))]
+
+
+def load_tp_case(path):
+    """The reference TrajectoryPlanner's outputs for sc.run_tp_scenario(seed): a list of per-cycle result dicts."""
+    g = np.load(path)
+    out = []
+    c = 0
+    while f"scalars{c}" in g:
+        s = g[f"scalars{c}"]
+        out.append(dict(cost=s[0], xv=s[1], yv=s[2], thetav=s[3], flags=int(s[4]), points=g[f"points{c}"],
+                        scores=g[f"scores{c}"], grids=[g[f"grid{c}_{k}"].astype(np.float64) for k in range(2)]))
+        c += 1
+    return out
+
+
 def check_costmap_case(api, tie_free, seed, path, exact=True):
     """Returns the number of mismatching master cells over all cycles (0 = bit-exact); asserts windows/layers."""
     g = np.load(path)

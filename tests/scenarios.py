@@ -227,3 +227,68 @@ def run_voxel_scenario(api, seed, cycles=4, max_size=70):
         w = cm.update_map(rx, ry, float(rng.uniform(-3, 3)))
         trace.append((w, cm.get().copy(), cm.get_layer(ids["voxel"]).copy(), cm.get_voxels(ids["voxel"]).copy(), cm.origin()))
     return trace, with_inflation
+
+
+def run_tp_scenario(api, grid_api, seed, cycles=6):
+    """Multi-cycle scenario of the legacy base_local_planner::TrajectoryPlanner (findBestPath + scoreTrajectory).
+    `api` needs .trajectory_planner (the CUDA binding and the compiled reference have it); the local costmap comes from
+    `grid_api`.  A third of the seeds start the robot against a wall or turned away from the plan, so that the
+    in-place-rotation, strafing and back-up branches of createTrajectories and their latched flags are exercised."""
+    rng = np.random.default_rng(seed + 5000)
+    s = dwa_scenario(rng)
+    grid = local_costmap(grid_api, np.random.default_rng(seed + 6000), ox=s["origin"][0], oy=s["origin"][1],
+                         style=s["style"])
+    over = dict(vx_samples=int(rng.integers(1, 9)), vtheta_samples=int(rng.integers(1, 21)),
+                holonomic_robot=int(rng.random() < 0.6), dwa=int(rng.random() < 0.7),
+                sim_time=float(rng.choice([1.0, 1.7, 0.5])))
+    if rng.random() < 0.15:
+        over.update(simple_attractor=1)
+    if rng.random() < 0.3:
+        over.update(angular_sim_granularity=0.1)
+    if rng.random() < 0.3:
+        over.update(y_vels=[-0.2, 0.2])
+    if rng.random() < 0.2:
+        over.update(min_vel_x=-0.1)
+    tp = api.trajectory_planner(120, 120, 0.05, PENTAGON, **over)
+    tp.set_costmap(grid, *s["origin"])
+    tp.update_plan(s["plan"])
+    pose = np.array(s["pose"])
+    vel = np.array(s["vel"])
+    mode = int(rng.integers(0, 3))
+    if mode == 1:  # nose against the lower corridor wall / a random heading
+        pose[2] = float(rng.uniform(-3.1, 3.1))
+        if s["style"] == "corridor":
+            pose[1] = s["origin"][1] + (0.25 * 120 + rng.uniform(6, 12)) * 0.05
+    elif mode == 2:  # inside an inflated / lethal area: nothing but backing up is legal
+        ys, xs = np.nonzero(grid >= 253)
+        if len(xs):
+            k = int(rng.integers(0, len(xs)))
+            pose[0] = s["origin"][0] + (xs[k] + 0.5) * 0.05
+            pose[1] = s["origin"][1] + (ys[k] + 0.5) * 0.05
+    out = []
+    for cyc in range(cycles):
+        if cyc == 3 and rng.random() < 0.5:
+            tp.update_plan(s["plan"][: max(2, len(s["plan"]) // 2)])
+        r = tp.find_best_path(pose, vel)
+        r["grids"] = [tp.grid(0), tp.grid(1)]
+        probes = [(0.3, 0.0, 0.2), (float(rng.uniform(-0.2, 0.5)), float(rng.choice([0.0, 0.1])), float(rng.uniform(-1, 1)))]
+        r["scores"] = np.array([tp.score_trajectory(pose, vel, p) for p in probes])
+        out.append(r)
+        vel = np.array([r["xv"], r["yv"], r["thetav"]]) if r["cost"] >= 0 else vel * 0
+        step = float(rng.choice([0.02, 0.2]))  # below / above oscillation_reset_dist and escape_reset_dist
+        pose = pose + np.array([step * vel[0] * np.cos(pose[2]), step * vel[0] * np.sin(pose[2]), step * vel[2]])
+    return out
+
+
+def tp_results_equal(a, b, rtol=0.0):
+    if a["flags"] != b["flags"] or len(a["points"]) != len(b["points"]):
+        return False
+    if not all(np.array_equal(x, y) for x, y in zip(a["grids"], b["grids"])):
+        return False
+    if (a["xv"], a["yv"], a["thetav"]) != (b["xv"], b["yv"], b["thetav"]):
+        return False
+    if rtol == 0.0:
+        return a["cost"] == b["cost"] and np.array_equal(a["points"], b["points"]) and np.array_equal(a["scores"], b["scores"])
+    return bool(np.isclose(a["cost"], b["cost"], rtol=rtol, atol=0) and
+                np.allclose(a["points"], b["points"], rtol=rtol, atol=1e-12) and
+                np.allclose(a["scores"], b["scores"], rtol=rtol, atol=0))

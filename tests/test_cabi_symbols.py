@@ -47,6 +47,8 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(navigation_b200.api.NavGpuError, match="no CUDA device"):
         a.fleet(2, 10, 10, 0.05, [(0.1, 0.1), (0.1, -0.1), (-0.1, -0.1), (-0.1, 0.1)])
     with pytest.raises(navigation_b200.api.NavGpuError, match="no CUDA device"):
+        a.trajectory_planner(10, 10, 0.05, [(0.1, 0.1), (0.1, -0.1), (-0.1, -0.1), (-0.1, 0.1)])
+    with pytest.raises(navigation_b200.api.NavGpuError, match="no CUDA device"):
         a.inflate_host(np.zeros((8, 8), np.uint8), 0, 0, 8, 8, np.zeros((4, 4), np.uint8), 2)
     # the host-side table builder is pure arithmetic (the reference's computeCost) and works everywhere
     R, costs, dists = a.build_cost_table(0.05, 0.325, 0.55, 10.0)
@@ -57,7 +59,7 @@ def test_product_package_never_touches_the_oracle():
     bad = []
     for dirpath, _, files in os.walk(os.path.join(ROOT, "navigation_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inc")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 code = "\n".join(l for l in text.split("\n") if "never imports or loads anything from oracle/" not in l)
                 if re.search(r"import oracle|from oracle|pyoracle|libnavoracle|libnavref|navo_|oracle_api", code):
