@@ -178,6 +178,23 @@ def dwa_setup(api, grid, cfg, **kw):
     return d, pose, vel
 
 
+def tp_numbers(api, grid, reps=20, **kw):
+    """Legacy base_local_planner::TrajectoryPlanner (SURVEY.md 8f-4) on the C2 local map: 20 x 20 forward samples + 2
+    holonomic + 20 in-place + 4 strafing + 1 back-up = 427 rollouts per findBestPath, through the synchronous call."""
+    tp = api.trajectory_planner(120, 120, 0.05, PENTAGON, vx_samples=20, vtheta_samples=20, sim_time=1.7, **kw)
+    tp.set_costmap(grid, 0.0, 0.0)
+    tp.update_plan(np.stack([np.arange(1.0, 7.0, 0.05), np.full(120, 3.0)], 1))
+    pose, vel = (1.5, 3.0, 0.0), (0.3, 0.0, 0.0)
+    for _ in range(3):
+        r = tp.find_best_path(pose, vel)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = tp.find_best_path(pose, vel)
+    us = 1e6 * (time.perf_counter() - t0) / reps
+    return {"findBestPath_us": us, "samples": 427, "traj_per_s": 427 / (us * 1e-6), "best": [r["xv"], r["yv"], r["thetav"]],
+            "best_cost": r["cost"]}
+
+
 def dwa_cpu_numbers(budget_s=25.0):
     """Reference CPU code on C2 (latency) and on C4 (throughput, full sweep once: about 20 s on one core)."""
     from oracle import pyoracle
@@ -548,6 +565,8 @@ def run_native(args, rank, world, local_rank):
                                        "synchronous navgpu_costmap_update_map, hot L2"}
         if dwa is not None:
             line["dwa"] = dwa
+            line["trajectory_planner"] = tp_numbers(api, inflate_local(api, local_map_c2(), device=local_rank),
+                                                    device=local_rank)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_c3()
             from oracle import pyoracle
@@ -557,6 +576,10 @@ def run_native(args, rank, world, local_rank):
             if dwa is not None:
                 line["dwa"]["cpu_baseline"] = dwa_cpu_numbers()
                 line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers()})
+                if kind == "reference":  # the legacy planner exists in the compiled reference only
+                    ref_api = pyoracle.load(kind)
+                    line["trajectory_planner"]["cpu_baseline"] = dict(
+                        tp_numbers(ref_api, inflate_local(ref_api, local_map_c2()), reps=5), kind=kind, cores=1)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -275,6 +275,10 @@ void navgpu_tp_default_config(navgpu_tp_config* cfg);
 int navgpu_tp_create(navgpu_tp** out, const navgpu_tp_config* cfg, uint32_t size_x, uint32_t size_y, double resolution,
                      const double* footprint_xy, int n_footprint, int device);
 int navgpu_tp_destroy(navgpu_tp* h);
+/* TrajectoryPlanner::reconfigure (trajectory_planner.cpp:59-133); the oscillation / escape state is kept */
+int navgpu_tp_reconfigure(navgpu_tp* h, const navgpu_tp_config* cfg);
+/* TrajectoryPlanner::setFootprint (trajectory_planner.h:195) */
+int navgpu_tp_set_footprint(navgpu_tp* h, const double* footprint_xy, int n_footprint);
 int navgpu_tp_set_costmap(navgpu_tp* h, const uint8_t* host_grid, double origin_x, double origin_y);
 int navgpu_tp_set_costmap_device(navgpu_tp* h, const uint8_t* dev_grid, uint32_t pitch, double origin_x,
                                  double origin_y);

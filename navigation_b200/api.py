@@ -146,6 +146,8 @@ SIGNATURES = {
     "navgpu_tp_default_config": (None, [C.POINTER(TpConfig)]),
     "navgpu_tp_create": (C.c_int, [_vpp, C.POINTER(TpConfig), C.c_uint32, C.c_uint32, C.c_double, _f64p, C.c_int, C.c_int]),
     "navgpu_tp_destroy": (C.c_int, [C.c_void_p]),
+    "navgpu_tp_reconfigure": (C.c_int, [C.c_void_p, C.POINTER(TpConfig)]),
+    "navgpu_tp_set_footprint": (C.c_int, [C.c_void_p, _f64p, C.c_int]),
     "navgpu_tp_set_costmap": (C.c_int, [C.c_void_p, _u8p, C.c_double, C.c_double]),
     "navgpu_tp_set_costmap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_double]),
     "navgpu_tp_update_plan": (C.c_int, [C.c_void_p, _f64p, C.c_int]),

@@ -10,6 +10,10 @@
 //   A2  navgpu_plugins::GpuLayeredCostmap (whole stack on the device) versus the reference stack.
 //   B   navgpu_plugins::GpuScoredSamplingPlanner as a base_local_planner::TrajectorySearch versus the reference's
 //       generator + critics + SimpleScoredSamplingPlanner wired like DWAPlanner (through libnavref's C API).
+//   C   navgpu_plugins::GpuTrajectoryPlanner versus the reference's base_local_planner::TrajectoryPlanner, both
+//       constructed with the same arguments on the same Costmap2D and driven through the same public calls
+//       (updatePlan, findBestPath with tf::Stamped<tf::Pose>, scoreTrajectory, checkTrajectory) for 8 cycles,
+//       including cycles where the robot is boxed in and the planner rotates in place / backs up.
 // Prints one line per check and exits non-zero on any mismatch.  Test infrastructure, not product code.
 #include <cmath>
 #include <cstdio>
@@ -25,6 +29,10 @@
 #include <navgpu_plugins/gpu_inflation_layer.h>
 #include <navgpu_plugins/gpu_layered_costmap.h>
 #include <navgpu_plugins/gpu_scored_sampling_planner.h>
+#include <navgpu_plugins/gpu_trajectory_planner.h>
+
+#include <base_local_planner/costmap_model.h>
+#include <base_local_planner/trajectory_planner.h>
 
 #include "oracle_api.h"
 
@@ -252,6 +260,74 @@ void testScoredSamplingPlanner() {
   report("B  GpuScoredSamplingPlanner vs reference DWA search, 6 cycles", bad, cycles);
 }
 
+void testTrajectoryPlanner() {
+  const unsigned n = 120;
+  const double res = 0.05;
+  Stack ref(n, n, res, new costmap_2d::InflationLayer);
+  std::vector<unsigned char> g(size_t(n) * n, 0);
+  for (unsigned y = 26; y < 29; ++y) memset(&g[y * n], 254, n);
+  for (unsigned y = 91; y < 94; ++y) memset(&g[y * n], 254, n);
+  for (unsigned y = 44; y < 76; ++y) memset(&g[y * n + 70], 254, 4);  // a barrier across most of the corridor
+  ref.grid->setData(g);
+  ref.lc.updateMap(3.0, 3.0, 0.0);
+  Costmap2D* local = ref.lc.getCostmap();
+  const std::vector<geometry_msgs::Point> fp = squareFootprint(0.3);
+  const std::vector<double> y_vels = {-0.3, -0.1, 0.1, 0.3};
+  base_local_planner::CostmapModel world_model(*local);
+  // TrajectoryPlannerROS's defaults (trajectory_planner_ros.cpp:116-213)
+  base_local_planner::TrajectoryPlanner rtp(world_model, *local, fp, 2.5, 2.5, 3.2, 1.0, 0.025, 6, 20, 0.6, 0.8, 0.01, 0.325,
+                                            0.05, 0.10, M_PI_4, true, 0.5, 0.1, 1.0, -1.0, 0.4, -0.1, true, false, 0.8,
+                                            false, false, y_vels, 0.2, 0.05, 0.025);
+  navgpu_plugins::GpuTrajectoryPlanner gtp(world_model, *local, fp, 2.5, 2.5, 3.2, 1.0, 0.025, 6, 20, 0.6, 0.8, 0.01, 0.325,
+                                           0.05, 0.10, M_PI_4, true, 0.5, 0.1, 1.0, -1.0, 0.4, -0.1, true, false, 0.8,
+                                           false, false, y_vels, 0.2, 0.05, 0.025);
+  std::vector<geometry_msgs::PoseStamped> plan;
+  for (int i = 0; i < 98; ++i) {
+    geometry_msgs::PoseStamped p;
+    p.pose.position.x = 1.0 + 0.05 * i;
+    p.pose.position.y = 3.0;
+    plan.push_back(p);
+  }
+  rtp.updatePlan(plan, false);
+  gtp.updatePlan(plan, false);
+  double pose[3] = {1.5, 3.0, 0.0}, vel[3] = {0.3, 0.0, 0.0};
+  long bad = 0, cycles = 0;
+  for (int c = 0; c < 8; ++c, ++cycles) {
+    if (c == 4) { pose[0] = 3.15; pose[1] = 3.0; pose[2] = 0.1; vel[0] = 0.0; }  // nose against the barrier
+    tf::Stamped<tf::Pose> gp, gv, rd, gd;
+    gp.setOrigin(tf::Vector3(pose[0], pose[1], 0.0));
+    gv.setOrigin(tf::Vector3(vel[0], vel[1], 0.0));
+    tf::Matrix3x3 m;
+    m.setRotation(tf::createQuaternionFromYaw(pose[2]));
+    gp.setBasis(m);
+    m.setRotation(tf::createQuaternionFromYaw(vel[2]));
+    gv.setBasis(m);
+    base_local_planner::Trajectory rt = rtp.findBestPath(gp, gv, rd);
+    base_local_planner::Trajectory gt = gtp.findBestPath(gp, gv, gd);
+    const double rs = rtp.scoreTrajectory(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], 0.3, 0.0, 0.2);
+    const double gs = gtp.scoreTrajectory(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], 0.3, 0.0, 0.2);
+    const bool rc = rtp.checkTrajectory(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], 0.5, 0.0, -1.0);
+    const bool gc = gtp.checkTrajectory(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], 0.5, 0.0, -1.0);
+    const bool same = std::fabs(rt.cost_ - gt.cost_) <= 1e-5 * std::fabs(rt.cost_) && rt.xv_ == gt.xv_ && rt.yv_ == gt.yv_ &&
+                      rt.thetav_ == gt.thetav_ && rt.getPointsSize() == gt.getPointsSize() &&
+                      std::fabs(rs - gs) <= 1e-5 * std::fabs(rs) && rc == gc &&
+                      rd.getOrigin().getX() == gd.getOrigin().getX() && tf::getYaw(rd.getRotation()) == tf::getYaw(gd.getRotation());
+    if (!same) {
+      ++bad;
+      printf("  cycle %d: reference cost %.9g v (%.6g %.6g %.6g) %u pts score %.9g / gpu cost %.9g v (%.6g %.6g %.6g) %u pts score %.9g\n",
+             c, rt.cost_, rt.xv_, rt.yv_, rt.thetav_, rt.getPointsSize(), rs, gt.cost_, gt.xv_, gt.yv_, gt.thetav_,
+             gt.getPointsSize(), gs);
+    }
+    if (rt.cost_ >= 0 && rt.getPointsSize() > 0) {  // follow the chosen command for a few steps
+      double x, y, th;
+      rt.getPoint(std::min(4u, rt.getPointsSize() - 1), x, y, th);
+      pose[0] = x; pose[1] = y; pose[2] = th;
+      vel[0] = rt.xv_; vel[1] = rt.yv_; vel[2] = rt.thetav_;
+    }
+  }
+  report("C  GpuTrajectoryPlanner vs reference TrajectoryPlanner, 8 cycles", bad, cycles);
+}
+
 }  // namespace
 
 int main() {
@@ -262,6 +338,7 @@ int main() {
   testInflationPlugin();
   testFusedStack();
   testScoredSamplingPlanner();
+  testTrajectoryPlanner();
   printf("%s\n", failures ? "DROP-IN FAILED" : "DROP-IN OK");
   return failures ? 1 : 0;
 }
