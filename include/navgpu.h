@@ -94,6 +94,27 @@ int navgpu_grid_layer_touch(navgpu_costmap* h, int layer, uint32_t x, uint32_t y
 int navgpu_layer_set_enabled(navgpu_costmap* h, int layer, int enabled);
 /* observations persist until replaced (ObstacleLayer::addStaticObservation :450-464); copied H2D here */
 int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_observation* obs, int n_obs);
+/* Observation ingest on the device: one sensor_msgs/LaserScan per observation instead of a
+ * world-frame cloud.  Replaces, per scan, laser_geometry's projection in ObstacleLayer::laserScanCallback /
+ * laserScanValidInfCallback (plugins/obstacle_layer.cpp:252-311) and ObservationBuffer::bufferCloud
+ * (src/observation_buffer.cpp:129-195: sensor origin, pcl_ros::transformPointCloud into the global frame, height
+ * filter).  sensor_to_global_* is the tf transform bufferCloud looks up (global_frame <- sensor frame). */
+typedef struct {
+  const float* ranges; /* LaserScan.ranges, n_ranges float32 (NaN / inf allowed, as on the wire) */
+  int32_t n_ranges;
+  int32_t inf_is_valid; /* inf_is_valid source parameter: +inf counts as range_max - 0.0001 (:277-292) */
+  float angle_min, angle_increment, range_min, range_max;
+  double sensor_to_global_translation[3];
+  double sensor_to_global_rotation_xyzw[4]; /* unit quaternion, tf order */
+  double min_obstacle_height, max_obstacle_height; /* of the ObservationBuffer */
+  double obstacle_range, raytrace_range;
+  int32_t marking, clearing;
+} navgpu_laser_scan;
+/* replaces the layer's observations by the n_scans scans (like navgpu_obstacle_set_observations, they persist) */
+int navgpu_obstacle_set_scans(navgpu_costmap* h, int layer, const navgpu_laser_scan* scans, int n_scans);
+/* the cloud of observation `index` as the layer holds it on the device, dropped rays removed (tests, debugging);
+ * returns the point count in *n_out, copies min(count, capacity) points of 3 floats */
+int navgpu_obstacle_get_cloud(navgpu_costmap* h, int layer, int index, float* xyz_out, int capacity, int* n_out);
 /* InflationLayer::setInflationParameters (:356-370) */
 int navgpu_inflation_set_params(navgpu_costmap* h, int layer, double inflation_radius, double cost_scaling_factor);
 /* inflation algorithm: 0 = exact windowed nearest-lethal distance (default; equals the reference wherever its

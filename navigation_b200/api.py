@@ -41,6 +41,16 @@ class DwaResult(C.Structure):
                 ("n_points", C.c_int32)]
 
 
+class LaserScan(C.Structure):
+    """navgpu_laser_scan"""
+    _fields_ = [("ranges", C.POINTER(C.c_float)), ("n_ranges", C.c_int32), ("inf_is_valid", C.c_int32),
+                ("angle_min", C.c_float), ("angle_increment", C.c_float), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("translation", C.c_double * 3), ("rotation_xyzw", C.c_double * 4),
+                ("min_obstacle_height", C.c_double), ("max_obstacle_height", C.c_double),
+                ("obstacle_range", C.c_double), ("raytrace_range", C.c_double), ("marking", C.c_int32),
+                ("clearing", C.c_int32)]
+
+
 class TpConfig(C.Structure):
     """navgpu_tp_config: the legacy base_local_planner::TrajectoryPlanner's parameters."""
     _fields_ = [(n, C.c_double) for n in (
@@ -91,6 +101,8 @@ SIGNATURES = {
     "navgpu_grid_layer_touch": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "navgpu_layer_set_enabled": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "navgpu_obstacle_set_observations": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Observation), C.c_int]),
+    "navgpu_obstacle_set_scans": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(LaserScan), C.c_int]),
+    "navgpu_obstacle_get_cloud": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, _i32p]),
     "navgpu_inflation_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "navgpu_inflation_set_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "navgpu_costmap_update_map": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, _i32p]),
@@ -245,6 +257,37 @@ class Costmap:
             arr[k].marking = int(o.get("marking", True))
             arr[k].clearing = int(o.get("clearing", True))
         self.api.check(self.lib.navgpu_obstacle_set_observations(self.h, layer, arr, len(observations)))
+
+    def set_scans(self, layer, scans):
+        """On-device observation ingest: scans = list of dicts (ranges, angle_min, angle_increment, range_min,
+        range_max, translation, rotation_xyzw, min/max_obstacle_height, obstacle_range, raytrace_range, marking,
+        clearing, inf_is_valid)."""
+        arr = (LaserScan * max(1, len(scans)))()
+        keep = []
+        for k, sc in enumerate(scans):
+            r = np.ascontiguousarray(sc["ranges"], dtype=np.float32)
+            keep.append(r)
+            s = arr[k]
+            s.ranges = r.ctypes.data_as(C.POINTER(C.c_float))
+            s.n_ranges = len(r)
+            s.inf_is_valid = int(sc.get("inf_is_valid", 0))
+            s.angle_min, s.angle_increment = sc["angle_min"], sc["angle_increment"]
+            s.range_min, s.range_max = sc["range_min"], sc["range_max"]
+            for j in range(3):
+                s.translation[j] = sc["translation"][j]
+            for j in range(4):
+                s.rotation_xyzw[j] = sc["rotation_xyzw"][j]
+            s.min_obstacle_height, s.max_obstacle_height = sc["min_obstacle_height"], sc["max_obstacle_height"]
+            s.obstacle_range, s.raytrace_range = sc["obstacle_range"], sc["raytrace_range"]
+            s.marking, s.clearing = int(sc.get("marking", True)), int(sc.get("clearing", True))
+        self.api.check(self.lib.navgpu_obstacle_set_scans(self.h, layer, arr, len(scans)))
+
+    def get_cloud(self, layer, index, capacity=1 << 16):
+        out = np.zeros((capacity, 3), dtype=np.float32)
+        n = C.c_int32()
+        self.api.check(self.lib.navgpu_obstacle_get_cloud(self.h, layer, index, out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                          capacity, C.byref(n)))
+        return out[:n.value].copy()
 
     def set_inflation_params(self, layer, inflation_radius, cost_scaling_factor):
         self.api.check(self.lib.navgpu_inflation_set_params(self.h, layer, inflation_radius, cost_scaling_factor))

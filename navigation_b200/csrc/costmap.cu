@@ -130,6 +130,8 @@ struct Layer {
   float* d_xyz = nullptr;
   long long* d_mark_cells = nullptr;  // scratch of k_obstacle_update: one prepared cell offset per marking point
   size_t xyz_capacity = 0, obs_capacity = 0, mark_cells_capacity = 0;
+  char* d_scan = nullptr;  // staging of navgpu_obstacle_set_scans: ScanRec records + ranges
+  size_t scan_capacity = 0;
   int n_clear = 0, n_mark = 0, total_rays = 0, total_marks = 0;
   std::vector<Pt> transformed_footprint;
   // voxel layer (an obstacle layer with columns of 16 voxels, plugins/voxel_layer.cpp)
@@ -583,7 +585,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   cudaStreamSynchronize(h->stream);
   for (Layer& L : h->layers) {
     cudaFree(L.grid[0]); cudaFree(L.grid[1]);
-    cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_mark_cells);
+    cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_mark_cells); cudaFree(L.d_scan);
     cudaFree(L.vox[0]); cudaFree(L.vox[1]);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
@@ -771,6 +773,43 @@ int navgpu_layer_set_enabled(navgpu_costmap* h, int layer, int enabled) {
   return NAVGPU_OK;
 }
 
+// common tail of navgpu_obstacle_set_observations / navgpu_obstacle_set_scans: device buffers for n_floats of xyz,
+// the clearing / marking observation tables and the marking scratch; `xyz_host` (nullable) is uploaded
+static int install_observations(navgpu_costmap* h, Layer* L, const std::vector<DevObs>& clear, const std::vector<DevObs>& mark,
+                                int rays, int marks, const float* xyz_host, size_t n_floats) {
+  if (n_floats > L->xyz_capacity) {
+    if (L->d_xyz) cudaFree(L->d_xyz);
+    L->d_xyz = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&L->d_xyz, n_floats * sizeof(float)));
+    L->xyz_capacity = n_floats;
+  }
+  if ((size_t)marks > L->mark_cells_capacity) {
+    if (L->d_mark_cells) cudaFree(L->d_mark_cells);
+    L->d_mark_cells = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&L->d_mark_cells, size_t(marks) * 2 * sizeof(long long)));
+    L->mark_cells_capacity = size_t(marks) * 2;
+  }
+  size_t need = std::max(clear.size(), mark.size());
+  if (need > L->obs_capacity) {
+    if (L->d_clear) cudaFree(L->d_clear);
+    if (L->d_mark) cudaFree(L->d_mark);
+    NAVGPU_CUDA(cudaMalloc(&L->d_clear, need * sizeof(DevObs)));
+    NAVGPU_CUDA(cudaMalloc(&L->d_mark, need * sizeof(DevObs)));
+    L->obs_capacity = need;
+  }
+  if (xyz_host && n_floats) NAVGPU_CUDA(cudaMemcpyAsync(L->d_xyz, xyz_host, n_floats * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (!clear.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_clear, clear.data(), clear.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
+  if (!mark.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_mark, mark.data(), mark.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  L->n_clear = (int)clear.size();
+  L->n_mark = (int)mark.size();
+  L->h_clear = clear;
+  L->h_mark = mark;
+  L->total_rays = rays;
+  L->total_marks = marks;
+  return NAVGPU_OK;
+}
+
 int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_observation* obs, int n_obs) {
   Layer* L = get_layer(h, layer, 1);
   if (!L || n_obs < 0 || (n_obs > 0 && !obs)) return fail(NAVGPU_ERR_INVALID, "bad obstacle layer / observations");
@@ -802,35 +841,97 @@ int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_
       mark.push_back(d);
     }
   }
-  if (xyz.size() > L->xyz_capacity) {
-    if (L->d_xyz) cudaFree(L->d_xyz);
-    NAVGPU_CUDA(cudaMalloc(&L->d_xyz, xyz.size() * sizeof(float)));
-    L->xyz_capacity = xyz.size();
+  return install_observations(h, L, clear, mark, rays, marks, xyz.data(), xyz.size());
+}
+
+// Observation ingest on the device: see k_project_scans (costmap_kernels.cuh) for what is computed and which
+// reference / third-party code it stands for.
+int navgpu_obstacle_set_scans(navgpu_costmap* h, int layer, const navgpu_laser_scan* scans, int n_scans) {
+  Layer* L = get_layer(h, layer, 1);
+  if (!L || n_scans < 0 || (n_scans > 0 && !scans)) return fail(NAVGPU_ERR_INVALID, "bad obstacle layer / scans");
+  NAVGPU_TRY(use_device(h));
+  std::vector<float> ranges;
+  std::vector<ScanRec> recs;
+  std::vector<DevObs> clear, mark;
+  L->obs.clear();
+  int rays = 0, marks = 0, points = 0;
+  for (int i = 0; i < n_scans; ++i) {
+    const navgpu_laser_scan& sc = scans[i];
+    if (sc.n_ranges < 0 || (sc.n_ranges > 0 && !sc.ranges)) return fail(NAVGPU_ERR_INVALID, "bad scan %d", i);
+    ScanRec r;
+    r.angle_min = sc.angle_min;
+    r.angle_increment = sc.angle_increment;
+    r.range_min = sc.range_min;
+    r.range_max = sc.range_max;
+    // pcl_ros::transformPointCloud: Eigen::Quaternionf(w, x, y, z) -> float rotation matrix (Eigen's
+    // QuaternionBase::toRotationMatrix), Eigen::Vector3f origin; all arithmetic in float
+    const float qx = (float)sc.sensor_to_global_rotation_xyzw[0], qy = (float)sc.sensor_to_global_rotation_xyzw[1],
+                qz = (float)sc.sensor_to_global_rotation_xyzw[2], qw = (float)sc.sensor_to_global_rotation_xyzw[3];
+    const float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+    const float twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy,
+                tyz = tz * qy, tzz = tz * qz;
+    r.m[0] = 1.0f - (tyy + tzz); r.m[1] = txy - twz; r.m[2] = txz + twy;
+    r.m[3] = txy + twz; r.m[4] = 1.0f - (txx + tzz); r.m[5] = tyz - twx;
+    r.m[6] = txz - twy; r.m[7] = tyz + twx; r.m[8] = 1.0f - (txx + tyy);
+    for (int k = 0; k < 3; ++k) r.t[k] = (float)sc.sensor_to_global_translation[k];
+    r.min_obstacle_height = sc.min_obstacle_height;
+    r.max_obstacle_height = sc.max_obstacle_height;
+    r.inf_is_valid = sc.inf_is_valid;
+    r.first_point = points;
+    r.n_points = sc.n_ranges;
+    r.first_range = (int)ranges.size();
+    ranges.insert(ranges.end(), sc.ranges, sc.ranges + sc.n_ranges);
+    recs.push_back(r);
+    DevObs d;  // the sensor origin is the transform of (0, 0, 0): its translation (observation_buffer.cpp:143-151)
+    d.ox = sc.sensor_to_global_translation[0]; d.oy = sc.sensor_to_global_translation[1]; d.oz = sc.sensor_to_global_translation[2];
+    d.obstacle_range = sc.obstacle_range;
+    d.raytrace_range = sc.raytrace_range;
+    d.first_point = points;
+    d.n_points = sc.n_ranges;
+    d.flags = (sc.marking ? 1 : 0) | (sc.clearing ? 2 : 0);
+    L->obs.push_back(HostObs{d.ox, d.oy, d.oz, d.obstacle_range, d.raytrace_range, d.first_point, d.n_points, sc.marking != 0,
+                             sc.clearing != 0});
+    if (sc.clearing && d.n_points > 0) { d.first_ray = rays; rays += d.n_points; clear.push_back(d); }
+    if (sc.marking && d.n_points > 0) { d.first_ray = marks; marks += d.n_points; mark.push_back(d); }
+    points += sc.n_ranges;
   }
-  if ((size_t)marks > L->mark_cells_capacity) {
-    if (L->d_mark_cells) cudaFree(L->d_mark_cells);
-    L->d_mark_cells = nullptr;
-    NAVGPU_CUDA(cudaMalloc(&L->d_mark_cells, size_t(marks) * 2 * sizeof(long long)));
-    L->mark_cells_capacity = size_t(marks) * 2;
+  NAVGPU_TRY(install_observations(h, L, clear, mark, rays, marks, nullptr, size_t(points) * 3));
+  if (points == 0) return NAVGPU_OK;
+  const size_t need = ranges.size() * sizeof(float) + recs.size() * sizeof(ScanRec);
+  if (need > L->scan_capacity) {
+    if (L->d_scan) cudaFree(L->d_scan);
+    L->d_scan = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&L->d_scan, 2 * need));
+    L->scan_capacity = 2 * need;
   }
-  size_t need = std::max(clear.size(), mark.size());
-  if (need > L->obs_capacity) {
-    if (L->d_clear) cudaFree(L->d_clear);
-    if (L->d_mark) cudaFree(L->d_mark);
-    NAVGPU_CUDA(cudaMalloc(&L->d_clear, need * sizeof(DevObs)));
-    NAVGPU_CUDA(cudaMalloc(&L->d_mark, need * sizeof(DevObs)));
-    L->obs_capacity = need;
+  ScanRec* d_recs = reinterpret_cast<ScanRec*>(L->d_scan);  // records first (8-byte aligned), ranges behind them
+  float* d_ranges = reinterpret_cast<float*>(L->d_scan + recs.size() * sizeof(ScanRec));
+  NAVGPU_CUDA(cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(ScanRec), cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(d_ranges, ranges.data(), ranges.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  k_project_scans<<<(points + 255) / 256, 256, 0, h->stream>>>(d_recs, (int)recs.size(), d_ranges, L->d_xyz, points);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // the staging vectors above are pageable
+  return NAVGPU_OK;
+}
+
+int navgpu_obstacle_get_cloud(navgpu_costmap* h, int layer, int index, float* xyz_out, int capacity, int* n_out) {
+  Layer* L = get_layer(h, layer, 1);
+  if (!L || !n_out || index < 0 || index >= (int)L->obs.size() || capacity < 0 || (capacity > 0 && !xyz_out))
+    return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_TRY(use_device(h));
+  const HostObs& o = L->obs[index];
+  std::vector<float> tmp(size_t(o.n_points) * 3);
+  if (o.n_points > 0) {
+    NAVGPU_CUDA(cudaMemcpyAsync(tmp.data(), L->d_xyz + size_t(o.first_point) * 3, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   }
-  if (!xyz.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_xyz, xyz.data(), xyz.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  if (!clear.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_clear, clear.data(), clear.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
-  if (!mark.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_mark, mark.data(), mark.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
-  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
-  L->n_clear = (int)clear.size();
-  L->n_mark = (int)mark.size();
-  L->h_clear = clear;
-  L->h_mark = mark;
-  L->total_rays = rays;
-  L->total_marks = marks;
+  int n = 0;
+  for (int i = 0; i < o.n_points; ++i) {
+    if (tmp[3 * i] != tmp[3 * i]) continue;  // a dropped ray
+    if (n < capacity) memcpy(xyz_out + 3 * n, &tmp[3 * i], 3 * sizeof(float));
+    ++n;
+  }
+  *n_out = n;
   return NAVGPU_OK;
 }
 

@@ -122,6 +122,58 @@ struct DevObs {
   int flags;      // bit0 marking, bit1 clearing
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Observation ingest: sensor_msgs/LaserScan ranges -> world-frame cloud of an Observation, i.e. what
+// ObstacleLayer::laserScanCallback (plugins/obstacle_layer.cpp:252-275; laserScanValidInfCallback :277-311) and
+// ObservationBuffer::bufferCloud (src/observation_buffer.cpp:129-195) produce on the host:
+//   1. laser_geometry::LaserProjection::projectLaser (laser_geometry 1.6.x, not part of the reference tree): a ray is
+//      kept when range < range_max && range >= range_min; x = float(double(range) * cos(angle_min + double(i) *
+//      angle_increment)), y likewise with sin, z = 0.  (transformLaserScanToPointCloud is called with the scan's own
+//      frame as the target, obstacle_layer.cpp:262, so its per-ray transform is the identity.)
+//   2. pcl_ros::transformPointCloud into the global frame (pcl_ros 1.4.x transforms.hpp + PCL 1.7): the tf rotation
+//      becomes an Eigen::Quaternionf, its float rotation matrix and the float translation form an Affine3f, every
+//      point is ((m0 * x + m1 * y) + m2 * z) + t per row in float.
+//   3. points with z outside [min_obstacle_height, max_obstacle_height] are dropped (observation_buffer.cpp:170-177).
+// Every ray keeps its slot in the observation's cloud; a dropped ray is stored as NaN, which raytrace_ray and
+// mark_prepare skip -- clearing and marking are order independent, so this equals the compacted cloud.
+struct ScanRec {
+  double angle_min, angle_increment;  // float fields of the message, widened exactly
+  float range_min, range_max;
+  float m[9], t[3];  // Affine3f: rotation (row-major) and translation
+  double min_obstacle_height, max_obstacle_height;
+  int inf_is_valid;  // laserScanValidInfCallback: +inf becomes range_max - 0.0001f
+  int first_point, n_points;
+  int first_range;  // offset into the uploaded ranges
+};
+
+__global__ void k_project_scans(const ScanRec* __restrict__ recs, int n_scans, const float* __restrict__ ranges,
+                                float* __restrict__ xyz, int total) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int k = 0;
+  while (k + 1 < n_scans && recs[k + 1].first_point - recs[0].first_point <= t) ++k;
+  const ScanRec& r = recs[k];
+  const int i = t - (r.first_point - recs[0].first_point);
+  float range = ranges[r.first_range + i];
+  if (r.inf_is_valid && !isfinite(range) && range > 0) range = r.range_max - 0.0001f;
+  const float nanf_ = __int_as_float(0x7fc00000);
+  float ox = nanf_, oy = nanf_, oz = nanf_;
+  if (range < r.range_max && range >= r.range_min) {
+    const double ang = r.angle_min + (double)i * r.angle_increment;
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    const float x = (float)((double)range * cs), y = (float)((double)range * sn), z = 0.0f;
+    const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.m[0], x), __fmul_rn(r.m[1], y)), __fmul_rn(r.m[2], z)), r.t[0]);
+    const float gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.m[3], x), __fmul_rn(r.m[4], y)), __fmul_rn(r.m[5], z)), r.t[1]);
+    const float gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.m[6], x), __fmul_rn(r.m[7], y)), __fmul_rn(r.m[8], z)), r.t[2]);
+    if ((double)gz <= r.max_obstacle_height && (double)gz >= r.min_obstacle_height) {
+      ox = gx; oy = gy; oz = gz;
+    }
+  }
+  float* out = xyz + 3 * (size_t)(r.first_point + i);
+  out[0] = ox; out[1] = oy; out[2] = oz;
+}
+
 // ObstacleLayer::raytraceFreespace (plugins/obstacle_layer.cpp:498-576) + Costmap2D::raytraceLine / bresenham2D
 // (include/costmap_2d/costmap_2d.h:359-412) + updateRaytraceBounds (:602-610).
 // One warp per ray.  All lanes evaluate the fp64 clip (identical operation order to the reference, no FMA
@@ -140,7 +192,9 @@ __device__ __forceinline__ void raytrace_ray(uint8_t* __restrict__ grid, const G
     const int pi = o.first_point + (warp - o.first_ray);
     const double ox = o.ox, oy = o.oy;
     unsigned x0, y0;
-    if (world_to_map(g, ox, oy, x0, y0)) {  // otherwise the whole observation is skipped (:507-513)
+    // a NaN point is a ray the on-device scan ingest dropped (k_project_scans): it is not part of the cloud
+    const float px_raw = xyz[3 * (size_t)pi];
+    if (px_raw == px_raw && world_to_map(g, ox, oy, x0, y0)) {  // origin off the map: the whole observation is skipped (:507-513)
       const double origin_x = g.ox, origin_y = g.oy;
       const double map_end_x = origin_x + g.sx * g.res;
       const double map_end_y = origin_y + g.sy * g.res;
@@ -221,7 +275,7 @@ __device__ __forceinline__ void mark_prepare(const Geom& g, const DevObs* __rest
   const size_t pi = (size_t)(o.first_point + (t - o.first_ray));
   const double px = xyz[3 * pi], py = xyz[3 * pi + 1], pz = xyz[3 * pi + 2];
   long long cell = -1;
-  if (!(pz > max_obstacle_height)) {
+  if (px == px && !(pz > max_obstacle_height)) {  // NaN: a ray dropped by the on-device scan ingest
     const double sq_dist = (px - o.ox) * (px - o.ox) + (py - o.oy) * (py - o.oy) + (pz - o.oz) * (pz - o.oz);
     if (!(sq_dist >= o.obstacle_range * o.obstacle_range)) {
       unsigned mx, my;
@@ -595,6 +649,7 @@ __device__ VoxelRay voxel_ray_setup(const Geom& g, const VoxelGeom& v, const Dev
   if (!world_to_map_3d_float(g, v, ox, oy, oz, sensor_x, sensor_y, sensor_z)) return r;  // whole observation skipped
   const double map_end_x = g.ox + (g.sx - 1 + 0.5) * g.res, map_end_y = g.oy + (g.sy - 1 + 0.5) * g.res;  // getSizeInMeters
   double wpx = xyz[3 * (size_t)point], wpy = xyz[3 * (size_t)point + 1], wpz = xyz[3 * (size_t)point + 2];
+  if (wpx != wpx) return r;  // NaN: a ray dropped by the on-device scan ingest (k_project_scans)
   const double distance = sqrt((wpx - ox) * (wpx - ox) + (wpy - oy) * (wpy - oy) + (wpz - oz) * (wpz - oz));
   double scaling_fact = 1.0;
   scaling_fact = fmax(fmin(scaling_fact, (distance - 2 * g.res) / distance), 0.0);
@@ -711,7 +766,7 @@ __global__ void __launch_bounds__(kObstacleThreads) k_voxel_clear(VoxelArgs a) {
       const DevObs& o = obs_of(a.mark, a.n_mark, t, point);
       const float fx = a.xyz[3 * (size_t)point], fy = a.xyz[3 * (size_t)point + 1], fz = a.xyz[3 * (size_t)point + 2];
       long long cell = -1;
-      if (!(fz > a.max_obstacle_height)) {
+      if (fx == fx && !(fz > a.max_obstacle_height)) {  // NaN: dropped by the scan ingest
         const double sq_dist = (fx - o.ox) * (fx - o.ox) + (fy - o.oy) * (fy - o.oy) + (fz - o.oz) * (fz - o.oz);
         if (!(sq_dist >= o.obstacle_range * o.obstacle_range)) {
           const double wz = fz < a.v.origin_z ? a.v.origin_z : (double)fz;

@@ -107,6 +107,14 @@ class GpuLayeredCostmap {
     }
     return check(navgpu_obstacle_set_observations(handle_, layer, obs.data(), (int)obs.size()));
   }
+  // On-device observation ingest: hand over the LaserScans themselves instead of projected clouds.  One entry per
+  // buffered scan; the caller fills navgpu_laser_scan from sensor_msgs::LaserScan (ranges.data(), angle_min, ...),
+  // the tf transform global_frame <- scan frame it would have given bufferCloud, and the ObservationBuffer's
+  // min / max_obstacle_height, obstacle_range, raytrace_range.  Replaces ObstacleLayer::laserScanCallback /
+  // laserScanValidInfCallback (obstacle_layer.cpp:252-311) + ObservationBuffer::bufferCloud (observation_buffer.cpp:129-195).
+  bool setLaserScans(int layer, const std::vector<navgpu_laser_scan>& scans) {
+    return check(navgpu_obstacle_set_scans(handle_, layer, scans.data(), (int)scans.size()));
+  }
   bool setInflationParameters(int layer, double inflation_radius, double cost_scaling_factor) {
     return check(navgpu_inflation_set_params(handle_, layer, inflation_radius, cost_scaling_factor));
   }

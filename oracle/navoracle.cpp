@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "oracle_api.h"
+#include "scan_ingest_restated.h"
 
 namespace {
 

@@ -85,6 +85,19 @@ int navo_raytrace_cells(uint32_t size_x, uint32_t x0, uint32_t y0, uint32_t x1, 
 /* calculateMinAndMaxDistances (footprint.cpp:41-67) */
 void navo_footprint_radii(const double* xy, int n, double* inscribed, double* circumscribed);
 
+/* observation ingest, restated in oracle/scan_ingest_restated.h (see its header: the third-party
+ * part of this path is PARITY UNPINNED).  Returns the number of points of the resulting world-frame cloud. */
+typedef struct {
+  const float* ranges;
+  int32_t n_ranges;
+  int32_t inf_is_valid;
+  float angle_min, angle_increment, range_min, range_max;
+  double translation[3];   /* tf: global frame <- sensor frame */
+  double rotation_xyzw[4];
+  double min_obstacle_height, max_obstacle_height;
+} navo_laser_scan;
+int navo_project_scan(const navo_laser_scan* scan, float* xyz_out, int capacity, double origin_out[3]);
+
 /* ---- Path B ---- */
 typedef struct {
   /* base_local_planner::LocalPlannerLimits (local_planner_limits.h:43-124) */

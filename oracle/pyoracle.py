@@ -39,6 +39,13 @@ class DwaResult(C.Structure):
                 ("n_points", C.c_int32)]
 
 
+class LaserScan(C.Structure):
+    _fields_ = [("ranges", C.POINTER(C.c_float)), ("n_ranges", C.c_int32), ("inf_is_valid", C.c_int32),
+                ("angle_min", C.c_float), ("angle_increment", C.c_float), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("translation", C.c_double * 3), ("rotation_xyzw", C.c_double * 4),
+                ("min_obstacle_height", C.c_double), ("max_obstacle_height", C.c_double)]
+
+
 class TpConfig(C.Structure):
     """navo_tp_config / navgpu_tp_config: the legacy base_local_planner::TrajectoryPlanner's parameters."""
     _fields_ = [(n, C.c_double) for n in (
@@ -109,6 +116,7 @@ def _declare(lib, prefix):
         "line_cells": (i, [i, i, i, i, _i32p, i]),
         "mapgrid_bfs": (None, [_u8p, u, u, _i32p, i, i, _f64p]),
         "impl_name": (C.c_char_p, []),
+        "project_scan": (i, [C.POINTER(LaserScan), C.POINTER(C.c_float), i, _f64p]),
     }
     # the legacy TrajectoryPlanner is exported by the compiled reference only
     optional = {
@@ -408,6 +416,27 @@ class Api:
         n = self.lib.navo_voxel_line_cells(size_x, *[float(v) for v in p0], *[float(v) for v in p1], max_length,
                                            _p(off, _u32p), _p(z, _i32p), cap)
         return np.stack([off[:n].astype(np.int64), z[:n].astype(np.int64)], 1)
+
+    def project_scan(self, scan):
+        """Observation ingest restated (oracle/scan_ingest_restated.h): scan = dict(ranges, angle_min, angle_increment,
+        range_min, range_max, translation, rotation_xyzw, min_obstacle_height, max_obstacle_height, inf_is_valid);
+        returns (origin, float32 (n, 3) world-frame cloud)."""
+        r = np.ascontiguousarray(scan["ranges"], dtype=np.float32)
+        s = LaserScan()
+        s.ranges = r.ctypes.data_as(C.POINTER(C.c_float))
+        s.n_ranges = len(r)
+        s.inf_is_valid = int(scan.get("inf_is_valid", 0))
+        s.angle_min, s.angle_increment = scan["angle_min"], scan["angle_increment"]
+        s.range_min, s.range_max = scan["range_min"], scan["range_max"]
+        for k in range(3):
+            s.translation[k] = scan["translation"][k]
+        for k in range(4):
+            s.rotation_xyzw[k] = scan["rotation_xyzw"][k]
+        s.min_obstacle_height, s.max_obstacle_height = scan["min_obstacle_height"], scan["max_obstacle_height"]
+        out = np.zeros((max(1, len(r)), 3), dtype=np.float32)
+        origin = np.zeros(3)
+        n = self.lib.navo_project_scan(C.byref(s), out.ctypes.data_as(C.POINTER(C.c_float)), len(r), _p(origin, _f64p))
+        return tuple(origin), out[:n].copy()
 
     def footprint_radii(self, xy):
         a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

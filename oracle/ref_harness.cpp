@@ -47,6 +47,7 @@
 #include <vector>
 
 #include "oracle_api.h"
+#include "scan_ingest_restated.h"
 
 // ---- footprint.cpp needs boost::tokenizer/XmlRpc; its two pure functions are restated (footprint.cpp:41-67,106-120)
 namespace costmap_2d {

@@ -290,3 +290,24 @@ def test_voxel_line_length_limit_and_diagonal(api):  # voxel_grid.h:226-297 (ray
     short = api.voxel_line_cells(50, (2.7, 1.2, 0.5), (12.9, 6.1, 9.8), max_length=4)
     assert len(short) == int(min(1.0, 4 / np.sqrt(10.2 ** 2 + 4.9 ** 2 + 9.3 ** 2)) * 10) + 1
     assert np.array_equal(short, cells[:len(short)])
+
+
+def test_scan_ingest_restatement_known_values(port):
+    """oracle/scan_ingest_restated.h (the checker of navgpu_obstacle_set_scans): rays at 0 / 90 / 180 degrees land on
+    (r, 0), (~0, r), (-r, ~0); NaN, negative and >= range_max ranges are dropped; +inf survives only with inf_is_valid,
+    as range_max - 0.0001f (obstacle_layer.cpp:277-292); the sensor origin is the transform's translation and the height
+    filter of ObservationBuffer::bufferCloud (observation_buffer.cpp:170-177) keeps min <= z <= max."""
+    base = dict(angle_min=np.float32(0.0), angle_increment=np.float32(np.pi / 2), range_min=np.float32(0.1),
+                range_max=np.float32(4.0), translation=(1.0, -2.0, 0.2), rotation_xyzw=(0, 0, 0, 1),
+                min_obstacle_height=0.0, max_obstacle_height=2.0)
+    org, a = port.project_scan(dict(base, ranges=[1.0, 2.0, 3.0, np.nan, -1.0, 4.0, np.inf], inf_is_valid=0))
+    assert org == (1.0, -2.0, 0.2) and a.shape == (3, 3)
+    assert a[0, 0] == 2.0 and a[0, 1] == -2.0 and a[1, 1] == 0.0 and a[2, 0] == -2.0 and np.all(a[:, 2] == np.float32(0.2))
+    _, b = port.project_scan(dict(base, ranges=[np.inf, 0.05], inf_is_valid=1))
+    assert b.shape == (1, 3) and b[0, 0] == np.float32(1.0) + (np.float32(4.0) - np.float32(0.0001))
+    _, c = port.project_scan(dict(base, ranges=[1.0], translation=(0, 0, 2.5)))
+    assert len(c) == 0  # above max_obstacle_height
+    # a quarter turn about z: the ray along the sensor's x axis points along the global y axis
+    q = (0.0, 0.0, np.sin(np.pi / 4), np.cos(np.pi / 4))
+    _, d = port.project_scan(dict(base, ranges=[1.0], rotation_xyzw=q, translation=(0, 0, 0.2)))
+    assert abs(d[0, 0]) < 1e-6 and abs(d[0, 1] - 1.0) < 1e-6
