@@ -1207,7 +1207,7 @@ __device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const D
   }
 }
 
-__global__ void __launch_bounds__(kMSGroupsX * kMSRowsY) k_merge_seed(MergeSeedArgs a) {
+__global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSeedArgs a) {
   // launched with programmatic stream serialization: let k_inflate be scheduled as soon as every CTA of this grid
   // is resident, and wait for the kernel before us (window, obstacle grid) before reading anything
   cudaTriggerProgrammaticLaunchCompletion();

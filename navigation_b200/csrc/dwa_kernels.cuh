@@ -22,8 +22,8 @@ struct DwaGeom {
 };
 
 // (int)(d / res) exactly as IEEE division + truncation gives it, without the fp64 division.
-// Fast path: q = d * (1/res) is within a few ulp of d / res, so truncation agrees unless the quotient is within 1e-9
-// (relative) of an integer r.  Near an integer the decision is made exactly: e = fma(-r, res, d) is the exact value
+// Fast path: q = d * (1/res) is within a few ulp of d / res, so truncation agrees unless the quotient is within 1e-6
+// of an integer r.  Near an integer the decision is made exactly: e = fma(-r, res, d) is the exact value
 // of d - r * res (it has at most ~38 significant bits there), so the real quotient is r + e / res.  e >= 0 gives r.
 // For e < 0 the correctly rounded quotient still reaches r when r - d/res is at most half the spacing of the doubles
 // just below r (a tie rounds to r, whose mantissa is even), i.e. -e <= 2^(k-53) * res with k = floor(log2 r), one less
@@ -32,7 +32,9 @@ struct DwaGeom {
 __device__ __forceinline__ int exact_cell(double d, double res, double inv_res) {
   const double q = d * inv_res;
   const double r = rint(q);
-  if (fabs(q - r) <= 1e-9 * fmax(1.0, fabs(q))) {
+  // q is within a few ulp of d / res (|error| < 2e-11 for the map sizes create() accepts, q < 32768), so a fixed
+  // 1e-6 band around the integers catches every case in which truncating q could disagree with truncating d / res
+  if (fabs(q - r) <= 1e-6) {
     const int ri = (int)r;
     if (ri <= 0) return (int)(d / res);  // d within 1e-9 cells of the origin: keep the division
     const double e = fma(-r, res, d);
@@ -497,20 +499,34 @@ __device__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
   const int major = xmajor ? xinc : yinc, minor = xmajor ? yinc : xinc;
   int num = den / 2;
   int off = py * (int)g.pitch + px;
-  int best = 0;
-  bool bad = false;
-  const uint8_t unknown_bad = a.allow_unknown ? 0 : kNoInfo;  // 0 never equals a cost we reject
-  for (int k = 0; k <= den; ++k) {
-    const int c = g.cost[off];
-    bad |= (c == kLethal) | (c == unknown_bad && unknown_bad != 0);  // CostmapModel::pointCost :133-142
-    best = max(best, c);
-    num += numadd;
-    if (num >= den) {
-      num -= den;
-      off += minor;
+  // CostmapModel::pointCost (:133-142) rejects LETHAL, and NO_INFORMATION unless unknown cells are allowed; the line
+  // cost is the largest cell cost.  Both come out of one running maximum (and, when 255 is allowed, one running
+  // minimum of c ^ 0xfe, which is 0 exactly for LETHAL), so the walk costs a load and one or two min/max per cell.
+  int best = 0, lethal_probe = 0xff;
+  if (a.allow_unknown) {
+    for (int k = 0; k <= den; ++k) {
+      const int c = g.cost[off];
+      best = max(best, c);
+      lethal_probe = min(lethal_probe, c ^ 0xfe);
+      num += numadd;
+      if (num >= den) {
+        num -= den;
+        off += minor;
+      }
+      off += major;
     }
-    off += major;
+  } else {
+    for (int k = 0; k <= den; ++k) {
+      best = max(best, (int)g.cost[off]);
+      num += numadd;
+      if (num >= den) {
+        num -= den;
+        off += minor;
+      }
+      off += major;
+    }
   }
+  const bool bad = a.allow_unknown ? lethal_probe == 0 : best >= kLethal;
   return bad ? -1 : best;
 }
 
@@ -639,13 +655,15 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
       // every (point, vertex) cell once, then every (point, edge) walk between two of them
       int* vcell = reinterpret_cast<int*>(warp_scratch + 128 + 16);  // [point][kMaxFootprint]
       const int items = cnt * a.nfp;
+      // it / nfp for it < 512, nfp <= 16 as a multiply by ceil(2^16 / nfp) (error < 512 / 2^16 < 1 / nfp: exact)
+      const unsigned inv_nfp = (65536u + (unsigned)a.nfp - 1u) / (unsigned)a.nfp;
       for (int it = lane; it < items; it += 32) {
-        const int p = it / a.nfp, v = it - p * a.nfp;
+        const int p = (int)(((unsigned)it * inv_nfp) >> 16), v = it - p * a.nfp;
         vcell[p * kMaxFootprint + v] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
       }
       __syncwarp();
       for (int it = lane; it < items; it += 32) {
-        const int p = it / a.nfp, e = it - p * a.nfp;
+        const int p = (int)(((unsigned)it * inv_nfp) >> 16), e = it - p * a.nfp;
         const int e1 = e + 1 < a.nfp ? e + 1 : 0;
         const int ec = footprint_edge_cost(a, vcell[p * kMaxFootprint + e], vcell[p * kMaxFootprint + e1]);
         atomicMax(&edge_max[p], ec < 0 ? 0x80000000u : (unsigned)ec);
