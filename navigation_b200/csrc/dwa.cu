@@ -62,6 +62,11 @@ void adjust_plan_resolution(const std::vector<P2>& in, std::vector<P2>& out, dou
   }
 }
 
+// two resolution-adjusted plans with the same points seed the same MapGrid
+bool same_plan(const std::vector<P2>& a, const std::vector<P2>& b) {
+  return a.size() == b.size() && (a.empty() || memcmp(a.data(), b.data(), a.size() * sizeof(P2)) == 0);
+}
+
 // OscillationCostFunction's latched state (oscillation_cost_function.h:78-83, .cpp:56-164)
 struct Oscillation {
   bool strafe_pos_only = false, strafe_neg_only = false, strafing_pos = false, strafing_neg = false;
@@ -128,6 +133,8 @@ struct navgpu_dwa {
   double* d_plan[3] = {nullptr, nullptr, nullptr};
   size_t plan_capacity[3] = {0, 0, 0};
   bool plan_dirty[3] = {false, false, false};
+  bool align_is_path = false;  // adjusted[2] == adjusted[0]: the alignment grid is the path grid, computed once
+  bool align_aliased = false;  // ... and that is how the grids of the last prepare() were laid out
   double alignment_scale = 0, path_scale = 0, goal_scale = 0, obstacle_scale = 0;
   uint32_t* d_dist[4] = {nullptr, nullptr, nullptr, nullptr};
   float* d_samples = nullptr;
@@ -301,12 +308,20 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   ma.job[1] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 1, h->d_dist[1]};  // goal: setLocalGoal
   ma.job[2] = MapGridJob{h->d_plan[1], (int)h->adjusted[1].size(), 1, h->d_dist[2]};  // goal_front
   ma.job[3] = MapGridJob{h->d_plan[2], (int)h->adjusted[2].size(), 0, h->d_dist[3]};  // alignment
+  if (h->align_is_path) {  // same poses, same mode as the path grid: one wavefront serves both critics
+    ma.job[3].dist = h->d_dist[0];
+    ma.job[3].skip = 1;
+  }
   ma.fleet = nullptr;
-  if (prepare) NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
+  if (prepare) {
+    NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
+    h->align_aliased = h->align_is_path;
+  }
 
   DwaScoreArgs& a = cy.args;
   a.g = g;
   for (int k = 0; k < 4; ++k) a.dist[k] = h->d_dist[k];
+  if (h->align_aliased) a.dist[3] = h->d_dist[0];
   a.vxs = h->d_samples;
   a.vys = h->d_samples + s.nx;
   a.vths = h->d_samples + s.nx + s.ny;
@@ -483,6 +498,7 @@ int navgpu_dwa_set_plan(navgpu_dwa* h, const double pose[3], const double* plan_
   } else {
     h->alignment_scale = 0.0;  // the alignment critic keeps the target poses it had (:282-285)
   }
+  h->align_is_path = same_plan(h->adjusted[2], h->adjusted[0]);
   return NAVGPU_OK;
 }
 
@@ -661,7 +677,8 @@ int navgpu_dwa_get_grid(navgpu_dwa* h, int which, double* host_out) {
   NAVGPU_TRY(use_device(h));
   const size_t n = size_t(h->sx) * h->sy;
   std::vector<uint32_t> tmp(n);
-  NAVGPU_CUDA(cudaMemcpyAsync(tmp.data(), h->d_dist[which], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  const uint32_t* src = (which == 3 && h->align_aliased) ? h->d_dist[0] : h->d_dist[which];
+  NAVGPU_CUDA(cudaMemcpyAsync(tmp.data(), src, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   for (size_t i = 0; i < n; ++i) host_out[i] = (double)tmp[i];
   return NAVGPU_OK;
@@ -704,6 +721,7 @@ struct navgpu_fleet {
   const uint8_t* d_master = nullptr;
   std::vector<double> origins;  // n x 2
   std::vector<std::vector<P2>> plan, adj_path, adj_front, adj_align;
+  std::vector<char> align_is_path;  // per robot: adj_align == adj_path
   std::vector<double> align_scale;
   std::vector<Oscillation> osc;
   std::vector<double> res_v;  // n x 3 persistent result velocities
@@ -771,6 +789,7 @@ int navgpu_fleet_create(navgpu_fleet** out, int n_robots, const navgpu_dwa_confi
   NAVGPU_CUDA(cudaMallocHost(&f->h_results, sizeof(DwaDeviceResult) * n_robots));
   f->origins.assign(size_t(2) * n_robots, 0.0);
   f->plan.resize(n_robots); f->adj_path.resize(n_robots); f->adj_front.resize(n_robots); f->adj_align.resize(n_robots);
+  f->align_is_path.assign(n_robots, 0);
   f->align_scale.assign(n_robots, 0.0);
   f->osc.resize(n_robots);
   f->res_v.assign(size_t(3) * n_robots, 0.0);
@@ -838,6 +857,7 @@ int navgpu_fleet_set_plans(navgpu_fleet* f, const double* poses, const double* p
       f->align_scale[r] = 0.0;
     }
     if (f->adj_align[r].empty()) f->adj_align[r] = f->adj_path[r];  // never set before: scale 0 or the path itself
+    f->align_is_path[r] = same_plan(f->adj_align[r], f->adj_path[r]);
   }
   f->plans_dirty = true;
   return NAVGPU_OK;
@@ -905,6 +925,10 @@ int navgpu_fleet_step(navgpu_fleet* f, const double* poses, const double* vels, 
     R.grids.job[1] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r]), (int)f->adj_path[r].size(), 1, dist + cells};
     R.grids.job[2] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 1]), (int)f->adj_front[r].size(), 1, dist + 2 * cells};
     R.grids.job[3] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 2]), (int)f->adj_align[r].size(), 0, dist + 3 * cells};
+    if (f->align_is_path[r]) {  // the alignment critic holds the path critic's poses: one wavefront serves both
+      R.grids.job[3].dist = dist;
+      R.grids.job[3].skip = 1;
+    }
     for (int k = 0; k < 3; ++k) { R.pos[k] = pos[k]; R.vel[k] = vel[k]; }
     R.osc_mask = f->osc[r].mask();
     R.scale_alignment = f->align_scale[r];

@@ -74,6 +74,9 @@ struct MapGridJob {
   // MapCell::within_robot as a bit per cell ((sx+31)/32 words per row), or null: obstacle cells under it stay
   // passable (map_grid.cpp:109-112; only the legacy TrajectoryPlanner marks cells, trajectory_planner.cpp:918-930)
   const uint32_t* within_robot = nullptr;
+  // 1: this grid is identical to another job's (same plan, same mode) whose buffer `dist` already points to -- nothing
+  // to compute (DWAPlanner's alignment critic gets the very poses of the path critic, dwa_planner.cpp:277-281)
+  int skip = 0;
 };
 struct MapGridRobot {  // fleet mode: one per robot, in device memory
   DwaGeom g;
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare_sliced(MapG
   cudaTriggerProgrammaticLaunchCompletion();  // the scoring kernel may be scheduled behind us; it waits for our end
   const MapGridJob job = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.job[blockIdx.x % jobs_per_robot]
                                  : a.job[blockIdx.x % jobs_per_robot];
+  if (job.skip) return;
   const DwaGeom g = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.g : a.g;
   const int W = (g.sx + 31) / 32, NW = W * (int)g.sy;
   uint32_t* F0 = mg_smem;  // NW words + one that stays zero
@@ -314,6 +318,7 @@ __global__ void __launch_bounds__(kMapGridThreads) k_mapgrid_prepare(MapGridArgs
   extern __shared__ uint32_t mg_smem[];
   const MapGridJob job = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.job[blockIdx.x % jobs_per_robot]
                                  : a.job[blockIdx.x % jobs_per_robot];
+  if (job.skip) return;
   const DwaGeom g = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.g : a.g;
   const int W = (g.sx + 31) / 32, NW = W * (int)g.sy;
   uint32_t* P = mg_smem;
