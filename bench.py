@@ -32,7 +32,7 @@ C3 = dict(size=4000, resolution=0.05, n_obs=8, n_beams=360, scan_range=10.0, inf
 ALGO_BYTES_PER_CELL = 3  # read static + read obstacle + write master
 # dram__bytes_read.sum + dram__bytes_write.sum of the two sweep kernels per launch pair, from the ncu --set full
 # capture summarised in profiles/ (the master grid stays in the 126 MB L2, so DRAM sees the two input layers only)
-TRAFFIC_BYTES = 43_843_000  # k_merge_seed 32.84 MB read + 0.01 MB written, k_inflate 10.99 MB read (profiles/r1_sweep_ncu_summary.txt)
+TRAFFIC_BYTES = 43_884_500  # k_merge_seed 32.84 MB read + 0.02 MB written, k_inflate 11.02 MB read (profiles/r1_sweep_ncu_summary.txt)
 METRIC = "ms per updateMap+inflation @4k^2 grid; DWA trajectories scored/sec"
 WORKLOAD = ("C3 full-window updateMap 4000x4000 @0.05 m: static + obstacle (8 obs x 360 beams, 10 m raytrace+mark) + "
             "inflation 1.0 m (R=20); DWA half: C2 findBestPath 20x1x20, C4 sweep 200x20x200 on a 120x120 local map, "
