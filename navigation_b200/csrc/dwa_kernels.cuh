@@ -808,7 +808,7 @@ __device__ __forceinline__ bool better(double c1, long long i1, double c2, long 
   return c1 < c2 || (c1 == c2 && i1 < i2);
 }
 
-__global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score(DwaScoreArgs a) {
+__global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_dwa_score(DwaScoreArgs a) {
   __shared__ double s_cost[kDwaWarpsPerBlock];
   __shared__ long long s_index[kDwaWarpsPerBlock];
   __shared__ int s_generated[kDwaWarpsPerBlock];
@@ -1008,7 +1008,7 @@ __device__ __forceinline__ void fleet_patch_args(DwaScoreArgs& s_a, const DwaSco
 }
 
 // grid = n_robots * blocks_per_robot CTAs; per CTA the (cost, index) minimum of its 8 samples
-__global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_fleet_score(DwaScoreArgs base, const FleetRobot* robots,
+__global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_fleet_score(DwaScoreArgs base, const FleetRobot* robots,
                                                                         const float* samples, int blocks_per_robot,
                                                                         double* block_cost, long long* block_index,
                                                                         unsigned* generated) {
