@@ -28,6 +28,13 @@ def tp_cases():
             for p in sorted(glob.glob(os.path.join(GOLDEN, "tp_*.npz")))]
 
 
+TP_BOXED = 9000  # the "seed" of sc.run_tp_boxed_scenario among the tp_*.npz fixtures
+
+
+def run_tp_case(api, grid_api, seed):
+    return sc.run_tp_boxed_scenario(api) if seed == TP_BOXED else sc.run_tp_scenario(api, grid_api, seed)
+
+
 def load_tp_case(path):
     """The reference TrajectoryPlanner's outputs for sc.run_tp_scenario(seed): a list of per-cycle result dicts."""
     g = np.load(path)

@@ -292,3 +292,36 @@ def tp_results_equal(a, b, rtol=0.0):
     return bool(np.isclose(a["cost"], b["cost"], rtol=rtol, atol=0) and
                 np.allclose(a["points"], b["points"], rtol=rtol, atol=1e-12) and
                 np.allclose(a["scores"], b["scores"], rtol=rtol, atol=0))
+
+
+def run_tp_boxed_scenario(api, cycles=9):
+    """The legacy TrajectoryPlanner in a slot just wider than the robot, open along y: driving forward and rotating in
+    place collide, so createTrajectories falls through to strafing (trajectory_planner.cpp:752-797); the plan is then
+    reversed (the other strafing direction wins and the first one is latched as stuck), and finally the slot is closed
+    on both sides, which leaves backing up and escape mode (:851-903)."""
+    n, res = 120, 0.05
+    grid = np.zeros((n, n), np.uint8)
+    grid[:, 50:52] = 254   # wall behind the robot: x in [2.50, 2.60)
+    grid[:, 70:72] = 254   # wall ahead: x in [3.50, 3.60)
+    tp = api.trajectory_planner(n, n, res, PENTAGON, holonomic_robot=1, vx_samples=4, vtheta_samples=10)
+    tp.set_costmap(grid, 0.0, 0.0)
+    plan = np.stack([np.full(60, 3.0), np.linspace(3.0, 5.9, 60)], 1)  # the plan runs along the slot
+    tp.update_plan(plan)
+    pose = np.array([3.0, 3.0, 0.0])
+    vel = np.zeros(3)
+    out = []
+    for cyc in range(cycles):
+        if cyc == 3:
+            tp.update_plan(np.stack([np.full(60, 3.0), np.linspace(3.0, 0.1, 60)], 1))
+        if cyc == 6:
+            closed = grid.copy()
+            closed[49:51, :] = 254
+            closed[70:72, :] = 254
+            tp.set_costmap(closed, 0.0, 0.0)
+        r = tp.find_best_path(pose, vel)
+        r["grids"] = [tp.grid(0), tp.grid(1)]
+        r["scores"] = np.array([tp.score_trajectory(pose, vel, (0.0, 0.1, 0.0)), tp.score_trajectory(pose, vel, (0.1, 0.0, 0.0))])
+        out.append(r)
+        vel = np.array([r["xv"], r["yv"], r["thetav"]]) if r["cost"] >= 0 else vel * 0
+        pose = pose + np.array([0.0, 0.01 * vel[1], 0.0])  # creep: below oscillation_reset_dist, the flags stay latched
+    return out

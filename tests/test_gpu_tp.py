@@ -31,7 +31,15 @@ def test_tp_scenarios_match_reference(cuda, port, ref, seed):
 
 @pytest.mark.parametrize("seed,path", gu.tp_cases())
 def test_tp_golden_fixtures(cuda, port, seed, path):
-    assert_cycles_match(sc.run_tp_scenario(cuda, port, seed), gu.load_tp_case(path), f"golden seed {seed}")
+    assert_cycles_match(gu.run_tp_case(cuda, port, seed), gu.load_tp_case(path), f"golden seed {seed}")
+
+
+def test_tp_boxed_in_matches_reference(cuda, ref):
+    """Strafing in both directions with its stuck flag latching, then backing up with nothing legal left."""
+    got, want = sc.run_tp_boxed_scenario(cuda), sc.run_tp_boxed_scenario(ref)
+    assert_cycles_match(got, want, "boxed")
+    assert any(r["yv"] > 0 for r in got) and any(r["yv"] < 0 for r in got) and any(r["xv"] < 0 for r in got)
+    assert got[-1]["flags"] & 4  # stuck_left_strafe
 
 
 def test_tp_scores_every_sample_on_the_device(cuda, port):
