@@ -256,6 +256,7 @@ def run_reference(args, rank):
     if not args.no_dwa:
         line["dwa"] = dwa_cpu_numbers()
         line["dwa"]["c5"] = fleet_cpu_numbers()
+        line["dwa"]["c5_all_cores"] = fleet_cpu_parallel_numbers()
     print(json.dumps(line), flush=True)
 
 
@@ -421,6 +422,50 @@ def fleet_cpu_numbers(n_robots=8):
             "sample": f"{n_robots} fleet robots (inflation + findBestPath each), single thread"}
 
 
+def _fleet_worker(ids):
+    return fleet_cpu_numbers_ids(ids)
+
+
+def fleet_cpu_numbers_ids(ids):
+    """Seconds the reference's CPU code needs for the fleet robots `ids` (one process, one core)."""
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.available("reference") else "port"
+    api = pyoracle.load(kind)
+    raw, origins, poses, vels, plans = fleet_inputs(ids)
+    t0 = time.perf_counter()
+    for i in range(len(ids)):
+        cm = api.costmap(120, 120, 0.05, *origins[i])
+        s = cm.add_grid_layer(0)
+        cm.add_inflation_layer(0.55, 10.0)
+        cm.set_footprint(PENTAGON)
+        cm.set_grid_layer(s, raw[i])
+        cm.update_map(0, 0, 0)
+        d = api.dwa(120, 120, 0.05, vx_samples=C5["vx_samples"], vy_samples=C5["vy_samples"],
+                    vth_samples=C5["vth_samples"], max_vel_y=0.0, min_vel_y=0.0)
+        d.set_costmap(cm.get(), *origins[i])
+        d.set_plan(poses[i], plans[i])
+        d.find_best_path(poses[i], vels[i], PENTAGON)
+    return time.perf_counter() - t0
+
+
+def fleet_cpu_parallel_numbers(per_core=6):
+    """The same on every host core at once (robots are independent, so the fleet is embarrassingly parallel on a CPU
+    too): one process per core, `per_core` robots each; aggregate robot-cycles/s."""
+    import multiprocessing as mp
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.available("reference") else "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    chunks = [list(range(c * per_core, (c + 1) * per_core)) for c in range(cores)]
+    ctx = mp.get_context("spawn")  # the parent may hold a CUDA context and torch threads: no fork
+    with ctx.Pool(cores) as pool:
+        pool.map(_fleet_worker, [c[:1] for c in chunks])  # processes up, libraries loaded
+        dt = max(pool.map(_fleet_worker, chunks, chunksize=1))
+    return {"kind": kind, "cores": cores, "c5_robot_cycles_per_s": cores * per_core / dt,
+            "c5_traj_per_s": cores * per_core * 420 / dt,
+            "sample": f"{per_core} fleet robots per process, one process per host core running concurrently; "
+                      "slowest process's compute time"}
+
+
 def run_native(args, rank, world, local_rank):
     import torch
     import navigation_b200
@@ -575,7 +620,7 @@ def run_native(args, rank, world, local_rank):
             line["voxel_layer"]["cpu_kind"] = kind
             if dwa is not None:
                 line["dwa"]["cpu_baseline"] = dwa_cpu_numbers()
-                line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers()})
+                line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers(), "c5_all_cores": fleet_cpu_parallel_numbers()})
                 if kind == "reference":  # the legacy planner exists in the compiled reference only
                     ref_api = pyoracle.load(kind)
                     line["trajectory_planner"]["cpu_baseline"] = dict(
