@@ -109,7 +109,12 @@ typedef struct {
   double min_obstacle_height, max_obstacle_height; /* of the ObservationBuffer */
   double obstacle_range, raytrace_range;
   int32_t marking, clearing;
+  int32_t is_cloud; /* 0: LaserScan ranges; 1: `ranges` holds n_ranges sensor-frame points (3 floats each) */
+  int32_t pad_;
 } navgpu_laser_scan;
+/* A PointCloud / PointCloud2 source is the same path without the projection (pointCloudCallback /
+ * pointCloud2Callback, obstacle_layer.cpp:313-339): set `ranges` to the cloud's n_ranges x (x, y, z) float32 in the
+ * SENSOR frame and is_cloud = 1 below; angle_* / range_* / inf_is_valid are then ignored. */
 /* replaces the layer's observations by the n_scans scans (like navgpu_obstacle_set_observations, they persist) */
 int navgpu_obstacle_set_scans(navgpu_costmap* h, int layer, const navgpu_laser_scan* scans, int n_scans);
 /* the cloud of observation `index` as the layer holds it on the device, dropped rays removed (tests, debugging);

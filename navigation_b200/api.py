@@ -48,7 +48,7 @@ class LaserScan(C.Structure):
                 ("range_max", C.c_float), ("translation", C.c_double * 3), ("rotation_xyzw", C.c_double * 4),
                 ("min_obstacle_height", C.c_double), ("max_obstacle_height", C.c_double),
                 ("obstacle_range", C.c_double), ("raytrace_range", C.c_double), ("marking", C.c_int32),
-                ("clearing", C.c_int32)]
+                ("clearing", C.c_int32), ("is_cloud", C.c_int32), ("pad_", C.c_int32)]
 
 
 class TpConfig(C.Structure):
@@ -265,14 +265,19 @@ class Costmap:
         arr = (LaserScan * max(1, len(scans)))()
         keep = []
         for k, sc in enumerate(scans):
-            r = np.ascontiguousarray(sc["ranges"], dtype=np.float32)
-            keep.append(r)
             s = arr[k]
+            if "points" in sc:  # a PointCloud(2) source: (n, 3) float32 in the sensor frame
+                r = np.ascontiguousarray(sc["points"], dtype=np.float32).reshape(-1, 3)
+                s.is_cloud = 1
+            else:
+                r = np.ascontiguousarray(sc["ranges"], dtype=np.float32)
+                s.is_cloud = 0
+                s.angle_min, s.angle_increment = sc["angle_min"], sc["angle_increment"]
+                s.range_min, s.range_max = sc["range_min"], sc["range_max"]
+            keep.append(r)
             s.ranges = r.ctypes.data_as(C.POINTER(C.c_float))
             s.n_ranges = len(r)
             s.inf_is_valid = int(sc.get("inf_is_valid", 0))
-            s.angle_min, s.angle_increment = sc["angle_min"], sc["angle_increment"]
-            s.range_min, s.range_max = sc["range_min"], sc["range_max"]
             for j in range(3):
                 s.translation[j] = sc["translation"][j]
             for j in range(4):

@@ -880,7 +880,8 @@ int navgpu_obstacle_set_scans(navgpu_costmap* h, int layer, const navgpu_laser_s
     r.first_point = points;
     r.n_points = sc.n_ranges;
     r.first_range = (int)ranges.size();
-    ranges.insert(ranges.end(), sc.ranges, sc.ranges + sc.n_ranges);
+    r.is_cloud = sc.is_cloud != 0;
+    ranges.insert(ranges.end(), sc.ranges, sc.ranges + size_t(sc.n_ranges) * (sc.is_cloud ? 3 : 1));
     recs.push_back(r);
     DevObs d;  // the sensor origin is the transform of (0, 0, 0): its translation (observation_buffer.cpp:143-151)
     d.ox = sc.sensor_to_global_translation[0]; d.oy = sc.sensor_to_global_translation[1]; d.oz = sc.sensor_to_global_translation[2];

@@ -143,7 +143,8 @@ struct ScanRec {
   double min_obstacle_height, max_obstacle_height;
   int inf_is_valid;  // laserScanValidInfCallback: +inf becomes range_max - 0.0001f
   int first_point, n_points;
-  int first_range;  // offset into the uploaded ranges
+  int first_range;  // offset (in floats) into the uploaded ranges / sensor-frame points
+  int is_cloud;     // 0: LaserScan ranges; 1: a PointCloud / PointCloud2 source, n_points x (x, y, z) in the sensor frame
 };
 
 __global__ void k_project_scans(const ScanRec* __restrict__ recs, int n_scans, const float* __restrict__ ranges,
@@ -154,15 +155,28 @@ __global__ void k_project_scans(const ScanRec* __restrict__ recs, int n_scans, c
   while (k + 1 < n_scans && recs[k + 1].first_point - recs[0].first_point <= t) ++k;
   const ScanRec& r = recs[k];
   const int i = t - (r.first_point - recs[0].first_point);
-  float range = ranges[r.first_range + i];
-  if (r.inf_is_valid && !isfinite(range) && range > 0) range = r.range_max - 0.0001f;
   const float nanf_ = __int_as_float(0x7fc00000);
   float ox = nanf_, oy = nanf_, oz = nanf_;
-  if (range < r.range_max && range >= r.range_min) {
-    const double ang = r.angle_min + (double)i * r.angle_increment;
-    double sn, cs;
-    sincos(ang, &sn, &cs);
-    const float x = (float)((double)range * cs), y = (float)((double)range * sn), z = 0.0f;
+  float x = 0.0f, y = 0.0f, z = 0.0f;
+  bool keep;
+  if (r.is_cloud) {  // pointCloudCallback / pointCloud2Callback (obstacle_layer.cpp:313-339): the points as they are
+    x = ranges[r.first_range + 3 * i];
+    y = ranges[r.first_range + 3 * i + 1];
+    z = ranges[r.first_range + 3 * i + 2];
+    keep = true;
+  } else {
+    float range = ranges[r.first_range + i];
+    if (r.inf_is_valid && !isfinite(range) && range > 0) range = r.range_max - 0.0001f;
+    keep = range < r.range_max && range >= r.range_min;
+    if (keep) {
+      const double ang = r.angle_min + (double)i * r.angle_increment;
+      double sn, cs;
+      sincos(ang, &sn, &cs);
+      x = (float)((double)range * cs);
+      y = (float)((double)range * sn);
+    }
+  }
+  if (keep) {
     const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.m[0], x), __fmul_rn(r.m[1], y)), __fmul_rn(r.m[2], z)), r.t[0]);
     const float gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.m[3], x), __fmul_rn(r.m[4], y)), __fmul_rn(r.m[5], z)), r.t[1]);
     const float gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.m[6], x), __fmul_rn(r.m[7], y)), __fmul_rn(r.m[8], z)), r.t[2]);

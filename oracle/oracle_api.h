@@ -95,6 +95,8 @@ typedef struct {
   double translation[3];   /* tf: global frame <- sensor frame */
   double rotation_xyzw[4];
   double min_obstacle_height, max_obstacle_height;
+  int32_t is_cloud; /* 1: `ranges` holds n_ranges sensor-frame points (x, y, z): a PointCloud(2) source, no projection */
+  int32_t pad_;
 } navo_laser_scan;
 int navo_project_scan(const navo_laser_scan* scan, float* xyz_out, int capacity, double origin_out[3]);
 

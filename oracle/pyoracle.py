@@ -43,7 +43,8 @@ class LaserScan(C.Structure):
     _fields_ = [("ranges", C.POINTER(C.c_float)), ("n_ranges", C.c_int32), ("inf_is_valid", C.c_int32),
                 ("angle_min", C.c_float), ("angle_increment", C.c_float), ("range_min", C.c_float),
                 ("range_max", C.c_float), ("translation", C.c_double * 3), ("rotation_xyzw", C.c_double * 4),
-                ("min_obstacle_height", C.c_double), ("max_obstacle_height", C.c_double)]
+                ("min_obstacle_height", C.c_double), ("max_obstacle_height", C.c_double), ("is_cloud", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 class TpConfig(C.Structure):
@@ -421,13 +422,18 @@ class Api:
         """Observation ingest restated (oracle/scan_ingest_restated.h): scan = dict(ranges, angle_min, angle_increment,
         range_min, range_max, translation, rotation_xyzw, min_obstacle_height, max_obstacle_height, inf_is_valid);
         returns (origin, float32 (n, 3) world-frame cloud)."""
-        r = np.ascontiguousarray(scan["ranges"], dtype=np.float32)
         s = LaserScan()
+        if "points" in scan:  # a PointCloud(2) source: (n, 3) float32 in the sensor frame
+            r = np.ascontiguousarray(scan["points"], dtype=np.float32).reshape(-1, 3)
+            s.is_cloud = 1
+        else:
+            r = np.ascontiguousarray(scan["ranges"], dtype=np.float32)
+            s.is_cloud = 0
+            s.angle_min, s.angle_increment = scan["angle_min"], scan["angle_increment"]
+            s.range_min, s.range_max = scan["range_min"], scan["range_max"]
         s.ranges = r.ctypes.data_as(C.POINTER(C.c_float))
         s.n_ranges = len(r)
         s.inf_is_valid = int(scan.get("inf_is_valid", 0))
-        s.angle_min, s.angle_increment = scan["angle_min"], scan["angle_increment"]
-        s.range_min, s.range_max = scan["range_min"], scan["range_max"]
         for k in range(3):
             s.translation[k] = scan["translation"][k]
         for k in range(4):

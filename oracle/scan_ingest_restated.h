@@ -13,6 +13,7 @@
  * and, from the reference itself (this part IS the reference's algorithm):
  *   ObstacleLayer::laserScanValidInfCallback  plugins/obstacle_layer.cpp:277-292  (+inf -> range_max - 0.0001f)
  *   ObstacleLayer::laserScanCallback          :252-275  (target frame = the scan's own frame: identity transform)
+ *   ObstacleLayer::pointCloud(2)Callback      :313-339  (is_cloud: the sensor-frame points go straight to bufferCloud)
  *   ObservationBuffer::bufferCloud            src/observation_buffer.cpp:129-195  (origin = transform of (0,0,0);
  *                                             points with z outside [min, max]_obstacle_height dropped, order kept)
  * Included by both checker libraries so that they export the same symbol.
@@ -37,11 +38,16 @@ extern "C" int navo_project_scan(const navo_laser_scan* s, float* xyz_out, int c
   for (int k = 0; k < 3; ++k) origin_out[k] = s->translation[k];
   int count = 0;
   for (int i = 0; i < s->n_ranges; ++i) {
-    float range = s->ranges[i];
-    if (s->inf_is_valid && !std::isfinite(range) && range > 0) range = s->range_max - 0.0001f;
-    if (!(range < s->range_max && range >= s->range_min)) continue;
-    const double ang = (double)s->angle_min + (double)i * (double)s->angle_increment;
-    const float x = (float)((double)range * cos(ang)), y = (float)((double)range * sin(ang)), z = 0.0f;
+    float x, y, z;
+    if (s->is_cloud) {  /* pointCloudCallback / pointCloud2Callback (obstacle_layer.cpp:313-339): no projection */
+      x = s->ranges[3 * i]; y = s->ranges[3 * i + 1]; z = s->ranges[3 * i + 2];
+    } else {
+      float range = s->ranges[i];
+      if (s->inf_is_valid && !std::isfinite(range) && range > 0) range = s->range_max - 0.0001f;
+      if (!(range < s->range_max && range >= s->range_min)) continue;
+      const double ang = (double)s->angle_min + (double)i * (double)s->angle_increment;
+      x = (float)((double)range * cos(ang)); y = (float)((double)range * sin(ang)); z = 0.0f;
+    }
     volatile float p0, p1, p2, acc;  /* volatile: one float rounding per operation, no contraction */
     float g[3];
     for (int r = 0; r < 3; ++r) {

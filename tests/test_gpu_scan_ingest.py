@@ -38,6 +38,17 @@ def random_scan(rng, sx, sy, res, ox, oy):
                 clearing=bool(rng.random() < 0.8), inf_is_valid=int(rng.random() < 0.5))
 
 
+def random_cloud(rng, sx, sy, res, ox, oy):
+    """A PointCloud(2) source (e.g. a depth camera): sensor-frame points, tilted sensor, heights in and out of the band."""
+    s = random_scan(rng, sx, sy, res, ox, oy)
+    n = int(rng.integers(1, 2000))
+    pts = np.stack([rng.uniform(0.2, 5.0, n), rng.uniform(-2.5, 2.5, n), rng.uniform(-0.8, 2.5, n)], 1).astype(np.float32)
+    for k in ("ranges", "angle_min", "angle_increment", "range_min", "range_max"):
+        del s[k]
+    s["points"] = pts
+    return s
+
+
 @pytest.mark.parametrize("seed", range(20))
 def test_scan_ingest_matches_restatement(cuda, port, seed):
     rng = np.random.default_rng(seed + 900)
@@ -55,7 +66,8 @@ def test_scan_ingest_matches_restatement(cuda, port, seed):
         stacks.append((cm, o))
     one_ulp = 0
     for cyc in range(3):
-        scans = [random_scan(rng, sx, sy, res, ox, oy) for _ in range(int(rng.integers(1, 4)))]
+        scans = [random_cloud(rng, sx, sy, res, ox, oy) if rng.random() < 0.35 else random_scan(rng, sx, sy, res, ox, oy)
+                 for _ in range(int(rng.integers(1, 4)))]
         clouds = [port.project_scan(s_) for s_ in scans]
         (g, go), (c, co) = stacks
         g.set_scans(go, scans)
