@@ -1262,9 +1262,12 @@ struct InflateArgs {
 // 8 + 2 * RMAX region rows, so a small RMAX keeps the kernel's code (and its instruction-cache footprint) small.
 template <int RMAX>
 __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
-  __shared__ uint32_t sbits[kIMaxRows * 4];       // seed words W0..W3 of each region row: columns tx0-32 .. tx0+95
-  __shared__ uint32_t pbits[kIMaxRows * 4];       // the same without interior seeds (see below)
-  __shared__ uint32_t h2[kIMaxRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
+  constexpr int kRows = kITY + 2 * RMAX;       // region rows this instantiation can hold
+  __shared__ uint32_t pbits[kRows * 4];        // seed words W0..W3 of each region row (columns tx0-32 .. tx0+95), pruned
+  __shared__ uint32_t h2[kRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
+  // the unpruned seed words only live until the pruning pass has read them: they borrow the start of h2, which phase 2
+  // fills afterwards (and only for seeded rows; phase 3 never reads another row)
+  uint32_t* const sbits = h2;
   __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
   // the cost table was uploaded long before this cycle: stage it while k_merge_seed is still draining, then wait
