@@ -325,3 +325,27 @@ def run_tp_boxed_scenario(api, cycles=9):
         vel = np.array([r["xv"], r["yv"], r["thetav"]]) if r["cost"] >= 0 else vel * 0
         pose = pose + np.array([0.0, 0.01 * vel[1], 0.0])  # creep: below oscillation_reset_dist, the flags stay latched
     return out
+
+
+def tp_utest_footprint_obstacles(api):
+    """base_local_planner/test/utest.cpp:86-110 (TrajectoryPlannerTest::footprintObstacles) through scoreTrajectory:
+    10 x 10 map at 1 m, square footprint of +-2 m, the robot at (4.5, 4.5) heading +y, an obstacle at cell (4, 6).
+    Driving into it with (vx 4, acc 4) and rotating with (vtheta pi/2, acc pi/4) must both come back as -1."""
+    fp = [(2, 2), (2, -2), (-2, -2), (-2, 2)]
+    grid = np.zeros((10, 10), np.uint8)
+    grid[6, 4] = 254
+    out = []
+    for acc, samp in (((4.0, 0.0, 0.0), (4.0, 0.0, 0.0)), ((0.0, 0.0, np.pi / 4), (0.0, 0.0, np.pi / 2))):
+        tp = api.trajectory_planner(10, 10, 1.0, fp, acc_lim_x=acc[0], acc_lim_y=acc[1], acc_lim_theta=acc[2], sim_time=1.0,
+                                    sim_granularity=1.0, vx_samples=2)
+        tp.set_costmap(grid, 0.0, 0.0)
+        out.append(tp.score_trajectory((4.5, 4.5, np.pi / 2), (0.0, 0.0, 0.0), samp))
+    # and with the obstacle out of the footprint's way the same commands are legal
+    grid2 = np.zeros((10, 10), np.uint8)
+    grid2[9, 9] = 254
+    tp = api.trajectory_planner(10, 10, 1.0, fp, acc_lim_x=4.0, acc_lim_y=0.0, acc_lim_theta=0.0, sim_time=1.0,
+                                sim_granularity=1.0, vx_samples=2, simple_attractor=1)
+    tp.set_costmap(grid2, 0.0, 0.0)
+    tp.update_plan([(4.5, 4.5), (4.5, 6.5)])
+    out.append(tp.score_trajectory((4.5, 4.5, np.pi / 2), (0.0, 0.0, 0.0), (1.0, 0.0, 0.0)))
+    return out

@@ -42,6 +42,13 @@ def test_tp_boxed_in_matches_reference(cuda, ref):
     assert got[-1]["flags"] & 4  # stuck_left_strafe
 
 
+def test_tp_utest_footprint_obstacles(cuda):
+    """base_local_planner/test/utest.cpp:86-110: trajectories that run or rotate the footprint into an obstacle are
+    invalid (-1); the same command on a clear map is legal."""
+    a, b, c = sc.tp_utest_footprint_obstacles(cuda)
+    assert a == -1.0 and b == -1.0 and c >= 0.0
+
+
 def test_tp_scores_every_sample_on_the_device(cuda, port):
     """3 x 20 forward samples + 2 holonomic + 20 in-place + 4 strafing + 1 back-up, all scored by one k_tp_score."""
     rng = np.random.default_rng(7)

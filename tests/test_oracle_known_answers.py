@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as po
+import scenarios as sc
 
 MAX_Z = 1.0  # costmap_2d/include/costmap_2d/testing_helper.h:10
 
@@ -311,3 +312,9 @@ def test_scan_ingest_restatement_known_values(port):
     q = (0.0, 0.0, np.sin(np.pi / 4), np.cos(np.pi / 4))
     _, d = port.project_scan(dict(base, ranges=[1.0], rotation_xyzw=q, translation=(0, 0, 0.2)))
     assert abs(d[0, 0]) < 1e-6 and abs(d[0, 1] - 1.0) < 1e-6
+
+
+def test_tp_utest_footprint_obstacles(ref):
+    """The reference's own TrajectoryPlanner known answer (utest.cpp:86-110) through the compiled reference."""
+    a, b, c = sc.tp_utest_footprint_obstacles(ref)
+    assert a == -1.0 and b == -1.0 and c >= 0.0
