@@ -297,7 +297,7 @@ typedef struct navgpu_tp navgpu_tp;
 
 /* TrajectoryPlannerROS::initialize's defaults (trajectory_planner_ros.cpp:116-213) */
 void navgpu_tp_default_config(navgpu_tp_config* cfg);
-/* TrajectoryPlanner ctor (trajectory_planner.cpp:135-187); heading_scoring is NAVGPU_ERR_UNSUPPORTED */
+/* TrajectoryPlanner ctor (trajectory_planner.cpp:135-187) */
 int navgpu_tp_create(navgpu_tp** out, const navgpu_tp_config* cfg, uint32_t size_x, uint32_t size_y, double resolution,
                      const double* footprint_xy, int n_footprint, int device);
 int navgpu_tp_destroy(navgpu_tp* h);

@@ -32,6 +32,10 @@ struct TpScoreArgs {
   double sim_time, sim_granularity, angular_sim_granularity;
   int simple_attractor;
   double goal_x, goal_y;  // last pose of the global plan (simple_attractor_)
+  int heading_scoring;    // heading_scoring_: path / goal distance and the heading difference of ONE step only
+  double heading_scoring_timestep;
+  const double* plan_xy;  // the global plan as received (not resolution-adjusted), n_plan (x, y) pairs
+  int n_plan;
   double pdist_scale, gdist_scale, occdist_scale;
   double heading_lookahead;
   int allow_unknown;
@@ -48,17 +52,64 @@ __device__ __forceinline__ double tp_new_velocity(double vg, double vi, double a
   return fmax(vg, vi - a_max * dt);
 }
 
+// TrajectoryPlanner::lineCost + pointCost (trajectory_planner.cpp:389-475): Bresenham from (x0, y0) to (x1, y1), both
+// ends included; false as soon as a cell is LETHAL, INSCRIBED or (NO_INFORMATION and unknown is not allowed)
+__device__ bool tp_line_is_clear(const TpScoreArgs& a, int x0, int x1, int y0, int y1) {
+  const int dx = abs(x1 - x0), dy = abs(y1 - y0);
+  const int xinc = x1 >= x0 ? 1 : -1, yinc = y1 >= y0 ? 1 : -1;
+  const bool xmajor = dx >= dy;
+  const int den = xmajor ? dx : dy, numadd = xmajor ? dy : dx;
+  int num = den / 2, x = x0, y = y0;
+  for (int k = 0; k <= den; ++k) {
+    const int c = a.g.cost[y * (int)a.g.pitch + x];
+    if (c == kLethal || c == kInscribed || (c == kNoInfo && !a.allow_unknown)) return false;
+    num += numadd;
+    if (num >= den) {
+      num -= den;
+      if (xmajor) y += yinc; else x += xinc;
+    }
+    if (xmajor) x += xinc; else y += yinc;
+  }
+  return true;
+}
+
+// TrajectoryPlanner::headingDiff (:372-387) with the whole warp: the farthest pose of the global plan that is on the
+// map and in clear line of sight of the robot's cell; lanes test 32 candidates at a time, from the end of the plan.
+// All lanes pass the same arguments and get the same result.
+__device__ double tp_heading_diff(const TpScoreArgs& a, int cell_x, int cell_y, double x, double y, double heading, int lane) {
+  for (int top = a.n_plan - 1; top >= 0; top -= 32) {
+    const int i = top - lane;
+    bool clear = false;
+    int gx_c = 0, gy_c = 0;
+    if (i >= 0 && dwa_world_to_map(a.g, a.plan_xy[2 * i], a.plan_xy[2 * i + 1], gx_c, gy_c))
+      clear = tp_line_is_clear(a, cell_x, gx_c, cell_y, gy_c);
+    const unsigned found = __ballot_sync(0xffffffffu, clear);
+    if (found) {
+      const int src = __ffs(found) - 1;  // the lowest lane holds the highest plan index
+      gx_c = __shfl_sync(0xffffffffu, gx_c, src);
+      gy_c = __shfl_sync(0xffffffffu, gy_c, src);
+      const double gx = a.g.ox + (gx_c + 0.5) * a.g.res, gy = a.g.oy + (gy_c + 0.5) * a.g.res;  // Costmap2D::mapToWorld
+      // angles::shortest_angular_distance(heading, atan2(...)) = normalize_angle(to - from)
+      double d = fmod(fmod(atan2(gy - y, gx - x) - heading, 2.0 * M_PI) + 2.0 * M_PI, 2.0 * M_PI);
+      if (d > M_PI) d -= 2.0 * M_PI;
+      return fabs(d);
+    }
+  }
+  return 1.7976931348623157e308;  // DBL_MAX
+}
+
 __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, double* warp_scratch) {
   const double vx_samp = a.samples[3 * sample], vy_samp = a.samples[3 * sample + 1], vth_samp = a.samples[3 * sample + 2];
   const double vmag = hypot(vx_samp, vy_samp);
-  int num_steps = (int)(fmax((vmag * a.sim_time) / a.sim_granularity, fabs(vth_samp) / a.angular_sim_granularity) + 0.5);
+  int num_steps = a.heading_scoring ? (int)(a.sim_time / a.sim_granularity + 0.5)
+                                    : (int)(fmax((vmag * a.sim_time) / a.sim_granularity, fabs(vth_samp) / a.angular_sim_granularity) + 0.5);
   if (num_steps == 0) num_steps = 1;
   const double dt = a.sim_time / num_steps;
   const uint32_t n_cells = a.g.sx * a.g.sy;  // path_map_.obstacleCosts(): the "impossible" cost (:535, :591)
 
   double sx = a.x, sy = a.y, sth = a.theta;  // state at the first step of the current round
   double vxi = a.vx, vyi = a.vy, vthi = a.vtheta;
-  double occ_cost = 0.0, path_dist = 0.0, goal_dist = 0.0, ahead = -1.0;
+  double occ_cost = 0.0, path_dist = 0.0, goal_dist = 0.0, ahead = -1.0, heading_diff = 0.0, time = 0.0;
   double fail_code = 0.0;
   int n_points = num_steps;
   double* out_pts = a.points ? a.points + (size_t)sample * a.points_stride * 3 : nullptr;
@@ -67,9 +118,10 @@ __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, doub
     const int cnt = min(32, num_steps - base);
     // velocity / heading recurrence (:352-361): the point of step l uses theta_l; the move to step l + 1 uses the
     // velocities already advanced to l + 1 and, for x / y, still theta_l
-    double th = sth, my_th = sth, my_vx = 0.0, my_vy = 0.0;
+    double th = sth, my_th = sth, my_vx = 0.0, my_vy = 0.0, my_time = 0.0;
     for (int l = 0; l < cnt; ++l) {
-      if (lane == l) my_th = th;
+      if (lane == l) { my_th = th; my_time = time; }
+      time += dt;  // `time += dt` once per step, as the reference accumulates it (:369)
       vxi = tp_new_velocity(vx_samp, vxi, a.acc_x, dt);
       vyi = tp_new_velocity(vy_samp, vyi, a.acc_y, dt);
       vthi = tp_new_velocity(vth_samp, vthi, a.acc_theta, dt);
@@ -126,6 +178,8 @@ __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, doub
     }
     // ---- my step
     double code = 0.0, occ = 0.0, pd = 0.0, gd = 0.0;
+    bool heading_step = false;
+    int my_cx = 0, my_cy = 0;
     if (active) {
       int cx, cy;
       if (!dwa_world_to_map(a.g, px, py, cx, cy)) code = -1.0;  // off the known map (:274-277)
@@ -140,10 +194,16 @@ __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, doub
           if (a.simple_attractor) {
             gd = (px - a.goal_x) * (px - a.goal_x) + (py - a.goal_y) * (py - a.goal_y);
           } else {
-            const uint32_t pdi = a.path_dist[cy * (int)a.g.sx + cx], gdi = a.goal_dist[cy * (int)a.g.sx + cx];
-            pd = (double)pdi;
-            gd = (double)gdi;
-            if (n_cells <= gdi || n_cells <= pdi) code = -2.0;  // no clear path to the goal (:337-342)
+            // with heading scoring only the step inside [timestep, timestep + dt) looks at the distance maps (:318-331)
+            heading_step = a.heading_scoring && my_time >= a.heading_scoring_timestep && my_time < a.heading_scoring_timestep + dt;
+            if (!a.heading_scoring || heading_step) {
+              const uint32_t pdi = a.path_dist[cy * (int)a.g.sx + cx], gdi = a.goal_dist[cy * (int)a.g.sx + cx];
+              pd = (double)pdi;
+              gd = (double)gdi;
+              if (n_cells <= gdi || n_cells <= pdi) code = -2.0;  // no clear path to the goal (:337-342)
+            }
+            my_cx = cx;
+            my_cy = cy;
           }
         }
       }
@@ -165,8 +225,20 @@ __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, doub
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     occ_cost = fmax(occ_cost, m);
-    path_dist = __shfl_sync(0xffffffffu, pd, cnt - 1);
-    goal_dist = __shfl_sync(0xffffffffu, gd, cnt - 1);
+    if (!a.heading_scoring || a.simple_attractor) {
+      path_dist = __shfl_sync(0xffffffffu, pd, cnt - 1);
+      goal_dist = __shfl_sync(0xffffffffu, gd, cnt - 1);
+    } else {
+      const unsigned hs = __ballot_sync(0xffffffffu, heading_step);
+      if (hs) {  // at most one step of a trajectory qualifies
+        const int src = __ffs(hs) - 1;
+        path_dist = __shfl_sync(0xffffffffu, pd, src);
+        goal_dist = __shfl_sync(0xffffffffu, gd, src);
+        heading_diff = tp_heading_diff(a, __shfl_sync(0xffffffffu, my_cx, src), __shfl_sync(0xffffffffu, my_cy, src),
+                                       __shfl_sync(0xffffffffu, px, src), __shfl_sync(0xffffffffu, py, src),
+                                       __shfl_sync(0xffffffffu, my_th, src), lane);
+      }
+    }
     if (base + cnt >= num_steps) {  // the end point, pushed heading_lookahead ahead (:672-681 / :760-769)
       double ag = -1.0;
       if (lane == cnt - 1) {
@@ -179,8 +251,10 @@ __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, doub
   }
   if (lane == 0) {
     TpSampleResult r;
-    r.cost = fail_code != 0.0 ? fail_code
-                              : a.pdist_scale * path_dist + goal_dist * a.gdist_scale + a.occdist_scale * occ_cost;  // :364-365
+    const double legal = a.heading_scoring
+                             ? a.occdist_scale * occ_cost + a.pdist_scale * path_dist + 0.3 * heading_diff + goal_dist * a.gdist_scale
+                             : a.pdist_scale * path_dist + goal_dist * a.gdist_scale + a.occdist_scale * occ_cost;  // :362-367
+    r.cost = fail_code != 0.0 ? fail_code : legal;
     r.ahead_gdist = fail_code != 0.0 ? -1.0 : ahead;
     r.n_points = n_points;
     r.pad_ = 0;

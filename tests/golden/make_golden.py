@@ -18,7 +18,7 @@ import scenarios as sc  # noqa: E402
 COSTMAP_SEEDS = [0, 1, 2, 3, 5, 8, 13, 21]
 COSTMAP_TIEFREE_SEEDS = [100, 101, 102, 103, 104, 105]
 DWA_SEEDS = [0, 1, 3, 4, 9, 20, 32]
-TP_SEEDS = [0, 2, 5, 7, 11, 16, 23, 31, 9000]  # 9000 = sc.run_tp_boxed_scenario (golden_util.TP_BOXED)
+TP_SEEDS = [0, 2, 4, 5, 7, 9, 11, 16, 23, 31, 9000]  # 9000 = sc.run_tp_boxed_scenario (golden_util.TP_BOXED)
 
 
 def main():

@@ -249,6 +249,9 @@ def run_tp_scenario(api, grid_api, seed, cycles=6):
         over.update(y_vels=[-0.2, 0.2])
     if rng.random() < 0.2:
         over.update(min_vel_x=-0.1)
+    if seed % 5 == 4:  # heading scoring: distances and the heading difference of the one step at heading_scoring_timestep
+        over.update(heading_scoring=1, heading_scoring_timestep=float([0.1, 0.8, 0.45][(seed // 5) % 3]))
+        over.pop("simple_attractor", None)
     tp = api.trajectory_planner(120, 120, 0.05, PENTAGON, **over)
     tp.set_costmap(grid, *s["origin"])
     tp.update_plan(s["plan"])
