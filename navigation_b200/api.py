@@ -243,7 +243,9 @@ class Costmap:
     def set_enabled(self, layer, enabled):
         self.api.check(self.lib.navgpu_layer_set_enabled(self.h, layer, int(enabled)))
 
-    def set_observations(self, layer, observations):
+    @staticmethod
+    def pack_observations(observations):
+        """The navgpu_observation array for a list of observation dicts (what a C++ caller holds anyway); reusable."""
         arr = (Observation * max(1, len(observations)))()
         keep = []
         for k, o in enumerate(observations):
@@ -256,7 +258,14 @@ class Costmap:
             arr[k].n_points = pts.shape[0]
             arr[k].marking = int(o.get("marking", True))
             arr[k].clearing = int(o.get("clearing", True))
-        self.api.check(self.lib.navgpu_obstacle_set_observations(self.h, layer, arr, len(observations)))
+        return arr, len(observations), keep
+
+    def set_observations(self, layer, observations):
+        arr, n, _keep = self.pack_observations(observations)
+        self.api.check(self.lib.navgpu_obstacle_set_observations(self.h, layer, arr, n))
+
+    def set_packed_observations(self, layer, packed):
+        self.api.check(self.lib.navgpu_obstacle_set_observations(self.h, layer, packed[0], packed[1]))
 
     def set_scans(self, layer, scans):
         """On-device observation ingest: scans = list of dicts (ranges, angle_min, angle_increment, range_min,

@@ -131,6 +131,9 @@ struct Layer {
   long long* d_mark_cells = nullptr;  // scratch of k_obstacle_update: one prepared cell offset per marking point
   size_t xyz_capacity = 0, obs_capacity = 0, mark_cells_capacity = 0;
   char* d_scan = nullptr;  // staging of navgpu_obstacle_set_scans: ScanRec records + ranges
+  char* h_stage = nullptr;  // pinned staging of navgpu_obstacle_set_observations' uploads
+  size_t stage_capacity = 0;
+  cudaEvent_t ev_stage = nullptr;
   size_t scan_capacity = 0;
   int n_clear = 0, n_mark = 0, total_rays = 0, total_marks = 0;
   std::vector<Pt> transformed_footprint;
@@ -586,6 +589,8 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   for (Layer& L : h->layers) {
     cudaFree(L.grid[0]); cudaFree(L.grid[1]);
     cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_mark_cells); cudaFree(L.d_scan);
+    if (L.h_stage) cudaFreeHost(L.h_stage);
+    if (L.ev_stage) cudaEventDestroy(L.ev_stage);
     cudaFree(L.vox[0]); cudaFree(L.vox[1]);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
@@ -797,10 +802,38 @@ static int install_observations(navgpu_costmap* h, Layer* L, const std::vector<D
     NAVGPU_CUDA(cudaMalloc(&L->d_mark, need * sizeof(DevObs)));
     L->obs_capacity = need;
   }
-  if (xyz_host && n_floats) NAVGPU_CUDA(cudaMemcpyAsync(L->d_xyz, xyz_host, n_floats * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  if (!clear.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_clear, clear.data(), clear.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
-  if (!mark.empty()) NAVGPU_CUDA(cudaMemcpyAsync(L->d_mark, mark.data(), mark.size() * sizeof(DevObs), cudaMemcpyHostToDevice, h->stream));
-  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  // The uploads go through a pinned staging buffer owned by the layer, so they are asynchronous and the call does not
+  // have to wait for the stream: [xyz | clearing table | marking table].  The buffer is reused by the next call once
+  // the copies that read it have completed (event).
+  const size_t xyz_bytes = xyz_host ? n_floats * sizeof(float) : 0, clear_bytes = clear.size() * sizeof(DevObs),
+               mark_bytes = mark.size() * sizeof(DevObs);
+  const size_t stage_bytes = ((xyz_bytes + 15) & ~size_t(15)) + clear_bytes + mark_bytes;
+  if (stage_bytes > 0) {
+    if (!L->ev_stage) NAVGPU_CUDA(cudaEventCreateWithFlags(&L->ev_stage, cudaEventDisableTiming));
+    else NAVGPU_CUDA(cudaEventSynchronize(L->ev_stage));
+    if (stage_bytes > L->stage_capacity) {
+      if (L->h_stage) cudaFreeHost(L->h_stage);
+      L->h_stage = nullptr;
+      NAVGPU_CUDA(cudaMallocHost(&L->h_stage, 2 * stage_bytes));
+      L->stage_capacity = 2 * stage_bytes;
+    }
+    char* st = L->h_stage;
+    char* st_clear = st + ((xyz_bytes + 15) & ~size_t(15));
+    char* st_mark = st_clear + clear_bytes;
+    if (xyz_bytes) {
+      memcpy(st, xyz_host, xyz_bytes);
+      NAVGPU_CUDA(cudaMemcpyAsync(L->d_xyz, st, xyz_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (clear_bytes) {
+      memcpy(st_clear, clear.data(), clear_bytes);
+      NAVGPU_CUDA(cudaMemcpyAsync(L->d_clear, st_clear, clear_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (mark_bytes) {
+      memcpy(st_mark, mark.data(), mark_bytes);
+      NAVGPU_CUDA(cudaMemcpyAsync(L->d_mark, st_mark, mark_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    NAVGPU_CUDA(cudaEventRecord(L->ev_stage, h->stream));
+  }
   L->n_clear = (int)clear.size();
   L->n_mark = (int)mark.size();
   L->h_clear = clear;
