@@ -433,7 +433,9 @@ class Dwa:
         f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
         res = DwaResult()
         costs = np.full(max_samples if want_costs else 1, np.nan)
-        pts = np.zeros((max_points, 3))
+        pts = getattr(self, "_pts", None)  # result buffer kept across calls (a C++ caller owns one, too)
+        if pts is None or pts.shape[0] != max_points:
+            pts = self._pts = np.zeros((max_points, 3))
         self.api.check(self.lib.navgpu_dwa_find_best_path(
             self.h, _p(p, _f64p), _p(v, _f64p), _p(f, _f64p), f.shape[0], C.byref(res),
             _p(costs, _f64p) if want_costs else None, max_samples if want_costs else 0, _p(pts, _f64p), max_points))
