@@ -380,8 +380,13 @@ def run_native_fleet(api, torch, dist, rank, world, local_rank, steps):
 
     step_s = timed(lambda: fleet.step_raw(poses, vels))
 
+    # the raw maps of the e2e loop come from pinned host memory (as the contract asks): same bytes, page-locked
+    raw_pinned_t = torch.empty(raw.shape, dtype=torch.uint8, pin_memory=True)
+    raw_pinned = raw_pinned_t.numpy()
+    raw_pinned[...] = raw
+
     def full():
-        fleet.set_maps(raw, origins)
+        fleet.set_maps(raw_pinned, origins)
         fleet.step_raw(poses, vels)
     e2e_s = timed(full)
     res = fleet.step(poses, vels)
