@@ -302,10 +302,17 @@ __global__ void __launch_bounds__(kMapGridThreads, kWPT == 1 ? 3 : 1) k_mapgrid_
   for (int r = warp; r < (int)g.sy; r += kMapGridThreads / 32) {  // a warp per row, a lane per cell of each word
     for (int w = 0; w < W; ++w) {
       const int wi = r * W + w, c = w * 32 + lane;
+      // un-slice: lane k loads plane k of this word; a 32 x 32 bit transpose across the warp (five butterfly steps)
+      // leaves in lane j the word whose bit k is bit j of plane k, i.e. the level of cell j
+      uint32_t d = lane < planes ? park[(3 + lane) * NW + wi] : 0u;
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        const uint32_t keep_lo = sft == 16 ? 0x0000ffffu : sft == 8 ? 0x00ff00ffu : sft == 4 ? 0x0f0f0f0fu : sft == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, d, sft);
+        d = (lane & sft) ? ((d & ~keep_lo) | ((other & ~keep_lo) >> sft)) : ((d & keep_lo) | ((other & keep_lo) << sft));
+      }
       if (c >= (int)g.sx) continue;
       const uint32_t v = (park[wi] >> lane) & 1u, p = (park[NW + wi] >> lane) & 1u, sd = (park[2 * NW + wi] >> lane) & 1u;
-      uint32_t d = 0;
-      for (int k = 0; k < planes; ++k) d |= ((park[(3 + k) * NW + wi] >> lane) & 1u) << k;
       // seeds 0 (even on an obstacle), untouched cells unreachableCellCosts, touched obstacles obstacleCosts
       job.dist[(size_t)r * g.sx + c] = sd ? 0u : (!v ? n_cells + 1 : (!p ? n_cells : d));
     }
