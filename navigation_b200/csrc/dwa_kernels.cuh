@@ -631,13 +631,18 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
     ddx = ddx * dt;
     ddy = ddy * dt;
     // x / y prefix in the reference's order: pos = float(pos + delta) per step
+    // (the per-step deltas are broadcast through the warp's scratch: one 8-byte shared load instead of two shuffles)
     float x = sx, y = sy, my_x = sx, my_y = sy;
+    warp_scratch[lane] = ddx;
+    warp_scratch[32 + lane] = ddy;
+    __syncwarp();
     for (int l = 0; l < cnt; ++l) {
       if (lane == l) { my_x = x; my_y = y; }
-      const double dxl = __shfl_sync(0xffffffffu, ddx, l), dyl = __shfl_sync(0xffffffffu, ddy, l);
+      const double dxl = warp_scratch[l], dyl = warp_scratch[32 + l];
       x = (float)((double)x + dxl);
       y = (float)((double)y + dyl);
     }
+    __syncwarp();  // the scratch is rewritten below (and by the next round)
     sx = x;
     sy = y;
     sth = th;
@@ -682,9 +687,21 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
       }
       __syncwarp();
     }
+    // the cell of the point itself serves the obstacle critic's centre lookup and the path / goal grids; the point
+    // shifted ahead by xshift serves goal_front / alignment: two worldToMap per point instead of five
+    int cell0_x = 0, cell0_y = 0, cell1_x = 0, cell1_y = 0;
+    bool on_map0 = false, on_map1 = false;
     if (active) {
-      int cx, cy;
-      if (a.nfp == 0 || !dwa_world_to_map(a.g, px, py, cx, cy)) fail = true;  // off-map centre: costmap_model.cpp:57-58
+      on_map0 = dwa_world_to_map(a.g, px, py, cell0_x, cell0_y);
+      if (a.xshift != 0.0) {
+        on_map1 = dwa_world_to_map(a.g, px + a.xshift * c, py + a.xshift * s, cell1_x, cell1_y);
+      } else {
+        on_map1 = on_map0; cell1_x = cell0_x; cell1_y = cell0_y;
+      }
+    }
+    if (active) {
+      const int cx = cell0_x, cy = cell0_y;
+      if (a.nfp == 0 || !on_map0) fail = true;  // off-map centre: costmap_model.cpp:57-58
       else {
         const int centre = a.g.cost[cy * (int)a.g.pitch + cx];
         int f = (int)edge_max[lane];
@@ -709,13 +726,8 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
       const bool stop_on_failure = k < 2;  // path, goal (:126-127 turn it off for the other two)
       double code = 0.0, d = 0.0;
       if (active) {
-        double qx = px, qy = py;
-        if (shifted && a.xshift != 0.0) {
-          qx = qx + a.xshift * c;
-          qy = qy + a.xshift * s;
-        }
-        int cx, cy;
-        if (!dwa_world_to_map(a.g, qx, qy, cx, cy)) code = -4.0;
+        const int cx = shifted ? cell1_x : cell0_x, cy = shifted ? cell1_y : cell0_y;
+        if (!(shifted ? on_map1 : on_map0)) code = -4.0;
         else {
           const uint32_t dd = a.dist[k][cy * (int)a.g.sx + cx];
           const uint32_t n_cells = a.g.sx * a.g.sy;
