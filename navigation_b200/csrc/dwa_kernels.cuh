@@ -622,8 +622,10 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
     sincos(thd, &s, &c);
     double ddx = my_vx * c, ddy = my_vx * s;
     if (my_vy != 0.0f) {
-      ddx = ddx + my_vy * cos(M_PI_2 + thd);
-      ddy = ddy + my_vy * sin(M_PI_2 + thd);
+      double c2, s2;  // cos / sin of the same argument: one range reduction
+      sincos(M_PI_2 + thd, &s2, &c2);
+      ddx = ddx + my_vy * c2;
+      ddy = ddy + my_vy * s2;
     } else {
       ddx = ddx + 0.0;
       ddy = ddy + 0.0;

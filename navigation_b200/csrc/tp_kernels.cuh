@@ -133,8 +133,10 @@ __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, doub
     // computeNewXPosition / computeNewYPosition, trajectory_planner.h:332-347
     double ddx, ddy;
     if (my_vy != 0.0) {
-      ddx = (my_vx * c + my_vy * cos(M_PI_2 + my_th)) * dt;
-      ddy = (my_vx * s + my_vy * sin(M_PI_2 + my_th)) * dt;
+      double c2, s2;
+      sincos(M_PI_2 + my_th, &s2, &c2);
+      ddx = (my_vx * c + my_vy * c2) * dt;
+      ddy = (my_vx * s + my_vy * s2) * dt;
     } else {
       ddx = (my_vx * c + 0.0) * dt;
       ddy = (my_vx * s + 0.0) * dt;
