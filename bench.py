@@ -628,10 +628,9 @@ def run_native(args, rank, world, local_rank):
             if dwa is not None:
                 line["dwa"]["cpu_baseline"] = dwa_cpu_numbers()
                 line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers(), "c5_all_cores": fleet_cpu_parallel_numbers()})
-                if kind == "reference":  # the legacy planner exists in the compiled reference only
-                    ref_api = pyoracle.load(kind)
-                    line["trajectory_planner"]["cpu_baseline"] = dict(
-                        tp_numbers(ref_api, inflate_local(ref_api, local_map_c2()), reps=5), kind=kind, cores=1)
+                ref_api = pyoracle.load(kind)
+                line["trajectory_planner"]["cpu_baseline"] = dict(
+                    tp_numbers(ref_api, inflate_local(ref_api, local_map_c2()), reps=5), kind=kind, cores=1)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

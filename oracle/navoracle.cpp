@@ -13,6 +13,7 @@
 // libstdc++'s std::priority_queue is kept for inflation on purpose: the reference's output depends on its heap tie
 // order, and the same container + push order reproduces it hash-for-hash.
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -689,14 +690,15 @@ struct LineIt {  // line_iterator.h:38-139
 
 // MapGrid::computeTargetDistance (map_grid.cpp:258-310) over explicit seeds; dist pre-filled with "unreachable".
 void mapgrid_bfs(const Grid& cm, bool allow_unknown, std::vector<double>& dist, std::vector<uint8_t>& mark,
-                 std::queue<unsigned>& q) {
+                 std::queue<unsigned>& q, const std::vector<uint8_t>* within_robot = nullptr) {
   const unsigned sx = cm.sx, sy = cm.sy;
   const double obstacle = double(size_t(sx) * sy);
   auto visit = [&](unsigned cur, unsigned chk) {
     if (mark[chk]) return;
     mark[chk] = 1;
     uint8_t cost = cm.c[chk];  // updatePathCell :103-123
-    if (cost == kLethal || cost == kInscribed || (cost == kNoInfo && !allow_unknown)) {
+    if (!(within_robot && (*within_robot)[chk]) &&
+        (cost == kLethal || cost == kInscribed || (cost == kNoInfo && !allow_unknown))) {
       dist[chk] = obstacle;
       return;
     }
@@ -1015,9 +1017,452 @@ std::vector<Pt> to_pts(const double* xy, int n) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Legacy base_local_planner::TrajectoryPlanner (base_local_planner/src/trajectory_planner.cpp), restated.
+struct Tp {
+  navo_tp_config cfg;
+  Grid cm;
+  std::vector<Pt> footprint, plan;
+  std::vector<double> path_dist, goal_dist;  // path_map_ / goal_map_ target_dist
+  bool stuck_left = false, stuck_right = false, stuck_left_strafe = false, stuck_right_strafe = false;
+  bool rotating_left = false, rotating_right = false, strafe_left = false, strafe_right = false;
+  bool escaping = false, final_goal_valid = false;
+  double prev_x = 0, prev_y = 0, escape_x = 0, escape_y = 0, escape_theta = 0, final_goal_x = 0, final_goal_y = 0;
+
+  struct Result {
+    double cost = -1.0, xv = 0, yv = 0, thetav = 0;
+    std::vector<double> x, y, th;
+  };
+
+  // CostmapModel::footprintCost through WorldModel::footprintCost (world_model.h:65-86, costmap_model.cpp:50-142)
+  double footprint_cost(double x, double y, double th) const {
+    const bool allow_unknown = cfg.allow_unknown != 0;
+    const double c = cos(th), s = sin(th);
+    unsigned cx, cy;
+    if (!cm.world_to_map(x, y, cx, cy)) return -1.0;
+    if (footprint.size() < 3) {
+      const uint8_t cost = cm.c[size_t(cy) * cm.sx + cx];
+      if (cost == kLethal || cost == kInscribed || (cost == kNoInfo && !allow_unknown)) return -1.0;
+      return cost;
+    }
+    double fcost = 0.0;
+    const size_t n = footprint.size();
+    for (size_t i = 0; i < n; ++i) {
+      const Pt& a = footprint[i];
+      const Pt& b = footprint[(i + 1) % n];
+      unsigned x0, y0, x1, y1;
+      if (!cm.world_to_map(x + (a.x * c - a.y * s), y + (a.x * s + a.y * c), x0, y0)) return -1.0;
+      if (!cm.world_to_map(x + (b.x * c - b.y * s), y + (b.x * s + b.y * c), x1, y1)) return -1.0;
+      double line_cost = 0.0;
+      for (LineIt l(x0, y0, x1, y1); l.valid(); l.advance()) {
+        const uint8_t cost = cm.c[size_t(l.y) * cm.sx + l.x];
+        if (cost == kLethal || (cost == kNoInfo && !allow_unknown)) return -1.0;
+        if (line_cost < cost) line_cost = cost;
+      }
+      fcost = std::max(line_cost, fcost);
+    }
+    return fcost;
+  }
+
+  // lineCost / pointCost (:389-475): true when no cell of the Bresenham line is LETHAL / INSCRIBED / disallowed unknown
+  bool line_clear(int x0, int x1, int y0, int y1) const {
+    const int dx = abs(x1 - x0), dy = abs(y1 - y0);
+    const int xi = x1 >= x0 ? 1 : -1, yi = y1 >= y0 ? 1 : -1;
+    const bool xmajor = dx >= dy;
+    const int den = xmajor ? dx : dy, numadd = xmajor ? dy : dx;
+    int num = den / 2, x = x0, y = y0;
+    for (int k = 0; k <= den; ++k) {
+      const uint8_t c = cm.c[size_t(y) * cm.sx + x];
+      if (c == kLethal || c == kInscribed || (c == kNoInfo && !cfg.allow_unknown)) return false;
+      num += numadd;
+      if (num >= den) {
+        num -= den;
+        if (xmajor) y += yi; else x += xi;
+      }
+      if (xmajor) x += xi; else y += yi;
+    }
+    return true;
+  }
+
+  double heading_diff(int cell_x, int cell_y, double x, double y, double heading) const {  // :372-387
+    for (int i = (int)plan.size() - 1; i >= 0; --i) {
+      unsigned gx, gy;
+      if (cm.world_to_map(plan[i].x, plan[i].y, gx, gy) && line_clear(cell_x, (int)gx, cell_y, (int)gy)) {
+        double wx, wy;
+        cm.map_to_world(gx, gy, wx, wy);
+        double a = fmod(fmod(atan2(wy - y, wx - x) - heading, 2.0 * M_PI) + 2.0 * M_PI, 2.0 * M_PI);  // angles.h
+        if (a > M_PI) a -= 2.0 * M_PI;
+        return fabs(a);
+      }
+    }
+    return DBL_MAX;
+  }
+
+  static double new_velocity(double vg, double vi, double a_max, double dt) {  // trajectory_planner.h:369-375
+    if ((vg - vi) >= 0) return std::min(vg, vi + a_max * dt);
+    return std::max(vg, vi - a_max * dt);
+  }
+
+  // generateTrajectory (:214-370)
+  void generate(double x, double y, double theta, double vx, double vy, double vtheta, double vx_samp, double vy_samp,
+                double vtheta_samp, double acc_x, double acc_y, double acc_theta, double impossible_cost, Result& t) const {
+    double x_i = x, y_i = y, theta_i = theta, vx_i = vx, vy_i = vy, vtheta_i = vtheta;
+    const double vmag = hypot(vx_samp, vy_samp);
+    int num_steps;
+    if (!cfg.heading_scoring)
+      num_steps = int(std::max((vmag * cfg.sim_time) / cfg.sim_granularity, fabs(vtheta_samp) / cfg.angular_sim_granularity) + 0.5);
+    else
+      num_steps = int(cfg.sim_time / cfg.sim_granularity + 0.5);
+    if (num_steps == 0) num_steps = 1;
+    const double dt = cfg.sim_time / num_steps;
+    double time = 0.0;
+    t.x.clear(); t.y.clear(); t.th.clear();
+    t.xv = vx_samp; t.yv = vy_samp; t.thetav = vtheta_samp;
+    t.cost = -1.0;
+    double path_d = 0.0, goal_d = 0.0, occ_cost = 0.0, hdiff = 0.0;
+    for (int i = 0; i < num_steps; ++i) {
+      unsigned cell_x, cell_y;
+      if (!cm.world_to_map(x_i, y_i, cell_x, cell_y)) { t.cost = -1.0; return; }
+      const double fc = footprint_cost(x_i, y_i, theta_i);
+      if (fc < 0) { t.cost = -1.0; return; }
+      occ_cost = std::max(std::max(occ_cost, fc), double(cm.c[size_t(cell_y) * cm.sx + cell_x]));
+      if (cfg.simple_attractor) {
+        goal_d = (x_i - plan.back().x) * (x_i - plan.back().x) + (y_i - plan.back().y) * (y_i - plan.back().y);
+      } else {
+        bool update = true;
+        if (cfg.heading_scoring) {
+          if (time >= cfg.heading_scoring_timestep && time < cfg.heading_scoring_timestep + dt)
+            hdiff = heading_diff((int)cell_x, (int)cell_y, x_i, y_i, theta_i);
+          else
+            update = false;
+        }
+        if (update) {
+          path_d = path_dist[size_t(cell_y) * cm.sx + cell_x];
+          goal_d = goal_dist[size_t(cell_y) * cm.sx + cell_x];
+          if (impossible_cost <= goal_d || impossible_cost <= path_d) { t.cost = -2.0; return; }
+        }
+      }
+      t.x.push_back(x_i); t.y.push_back(y_i); t.th.push_back(theta_i);
+      vx_i = new_velocity(vx_samp, vx_i, acc_x, dt);
+      vy_i = new_velocity(vy_samp, vy_i, acc_y, dt);
+      vtheta_i = new_velocity(vtheta_samp, vtheta_i, acc_theta, dt);
+      const double nx = x_i + (vx_i * cos(theta_i) + vy_i * cos(M_PI_2 + theta_i)) * dt;  // trajectory_planner.h:332-358
+      const double ny = y_i + (vx_i * sin(theta_i) + vy_i * sin(M_PI_2 + theta_i)) * dt;
+      theta_i = theta_i + vtheta_i * dt;
+      x_i = nx; y_i = ny;
+      time += dt;
+    }
+    if (!cfg.heading_scoring) t.cost = cfg.pdist_scale * path_d + goal_d * cfg.gdist_scale + cfg.occdist_scale * occ_cost;
+    else t.cost = cfg.occdist_scale * occ_cost + cfg.pdist_scale * path_d + 0.3 * hdiff + goal_d * cfg.gdist_scale;
+  }
+
+  // FootprintHelper::getFootprintCells(pos, spec, costmap, fill = true) (footprint_helper.cpp:51-246)
+  std::vector<std::pair<long long, long long>> footprint_cells(double x_i, double y_i, double theta_i) const {
+    std::vector<std::pair<long long, long long>> cells;
+    if (footprint.size() <= 1) {
+      unsigned mx, my;
+      if (cm.world_to_map(x_i, y_i, mx, my)) cells.push_back({mx, my});
+      return cells;
+    }
+    const double cos_th = cos(theta_i), sin_th = sin(theta_i);
+    auto line = [&](int x0, int x1, int y0, int y1) {  // getLineCells :51-120
+      const int dx = abs(x1 - x0), dy = abs(y1 - y0), xi = x1 >= x0 ? 1 : -1, yi = y1 >= y0 ? 1 : -1;
+      const bool xmajor = dx >= dy;
+      const int den = xmajor ? dx : dy, numadd = xmajor ? dy : dx;
+      int num = den / 2, x = x0, y = y0;
+      for (int k = 0; k <= den; ++k) {
+        cells.push_back({x, y});
+        num += numadd;
+        if (num >= den) { num -= den; if (xmajor) y += yi; else x += xi; }
+        if (xmajor) x += xi; else y += yi;
+      }
+    };
+    const size_t n = footprint.size();
+    for (size_t i = 0; i < n; ++i) {
+      const Pt& p = footprint[i];
+      const Pt& q = footprint[(i + 1) % n];
+      unsigned x0, y0, x1, y1;
+      if (!cm.world_to_map(x_i + (p.x * cos_th - p.y * sin_th), y_i + (p.x * sin_th + p.y * cos_th), x0, y0)) return cells;
+      if (!cm.world_to_map(x_i + (q.x * cos_th - q.y * sin_th), y_i + (q.x * sin_th + q.y * cos_th), x1, y1)) return cells;
+      line((int)x0, (int)x1, (int)y0, (int)y1);
+    }
+    // getFillCells :123-178: the swap-adjacent sort (stable by x), then the column walk over the growing vector
+    size_t i = 0;
+    while (i + 1 < cells.size()) {
+      if (cells[i].first > cells[i + 1].first) {
+        std::swap(cells[i], cells[i + 1]);
+        if (i > 0) --i;
+      } else {
+        ++i;
+      }
+    }
+    i = 0;
+    const unsigned min_x = (unsigned)cells.front().first, max_x = (unsigned)cells.back().first;
+    for (unsigned x = min_x; x <= max_x; ++x) {
+      if (i >= cells.size() - 1) break;
+      std::pair<long long, long long> lo, hi;
+      if (cells[i].second < cells[i + 1].second) { lo = cells[i]; hi = cells[i + 1]; }
+      else { lo = cells[i + 1]; hi = cells[i]; }
+      i += 2;
+      while (i < cells.size() && cells[i].first == (long long)x) {
+        if (cells[i].second < lo.second) lo = cells[i];
+        else if (cells[i].second > hi.second) hi = cells[i];
+        ++i;
+      }
+      for (unsigned yy = (unsigned)lo.second; yy < (unsigned)hi.second; ++yy) cells.push_back({(long long)x, (long long)yy});
+    }
+    return cells;
+  }
+
+  // MapGrid::setTargetCells / setLocalGoal (map_grid.cpp:174-254) into `dist`
+  void wavefront(bool local_goal, const std::vector<uint8_t>* within, std::vector<double>& dist) const {
+    const size_t n = size_t(cm.sx) * cm.sy;
+    dist.assign(n, double(n + 1));
+    std::vector<uint8_t> mark(n, 0);
+    std::queue<unsigned> q;
+    std::vector<Pt> adj;
+    adjust_plan_resolution(plan, adj, cm.res);
+    bool started = false;
+    int gx = -1, gy = -1;
+    for (size_t i = 0; i < adj.size(); ++i) {
+      unsigned mx, my;
+      if (cm.world_to_map(adj[i].x, adj[i].y, mx, my) && cm.c[size_t(my) * cm.sx + mx] != kNoInfo) {
+        if (local_goal) { gx = mx; gy = my; }
+        else {
+          const unsigned id = my * cm.sx + mx;
+          dist[id] = 0.0;
+          mark[id] = 1;
+          q.push(id);
+        }
+        started = true;
+      } else if (started) {
+        break;
+      }
+    }
+    if (!started) return;
+    if (local_goal && gx >= 0 && gy >= 0) {
+      const unsigned id = gy * cm.sx + gx;
+      dist[id] = 0.0;
+      mark[id] = 1;
+      q.push(id);
+    }
+    mapgrid_bfs(cm, cfg.allow_unknown != 0, dist, mark, q, within);
+  }
+
+  // createTrajectories (:537-905)
+  Result create(double x, double y, double theta, double vx, double vy, double vtheta) {
+    const double acc_x = cfg.acc_lim_x, acc_y = cfg.acc_lim_y, acc_theta = cfg.acc_lim_theta;
+    double max_vel_x = cfg.max_vel_x, max_vel_theta, min_vel_x, min_vel_theta;
+    if (final_goal_valid) max_vel_x = std::min(max_vel_x, hypot(final_goal_x - x, final_goal_y - y) / cfg.sim_time);
+    const double horizon = cfg.dwa ? cfg.sim_period : cfg.sim_time;
+    max_vel_x = std::max(std::min(max_vel_x, vx + acc_x * horizon), cfg.min_vel_x);
+    min_vel_x = std::max(cfg.min_vel_x, vx - acc_x * horizon);
+    max_vel_theta = std::min(cfg.max_vel_th, vtheta + acc_theta * horizon);
+    min_vel_theta = std::max(cfg.min_vel_th, vtheta - acc_theta * horizon);
+    const double dvx = (max_vel_x - min_vel_x) / (cfg.vx_samples - 1);
+    const double dvtheta = (max_vel_theta - min_vel_theta) / (cfg.vtheta_samples - 1);
+    double vx_samp = min_vel_x, vtheta_samp = min_vel_theta, vy_samp = 0.0;
+    Result one, two;
+    Result* best = &one;
+    Result* comp = &two;
+    best->cost = -1.0;
+    comp->cost = -1.0;
+    const double impossible = double(size_t(cm.sx) * cm.sy);
+    auto gen = [&](double a, double b, double c) { generate(x, y, theta, vx, vy, vtheta, a, b, c, acc_x, acc_y, acc_theta, impossible, *comp); };
+    auto better = [&]() { return comp->cost >= 0 && (comp->cost < best->cost || best->cost < 0); };
+    if (!escaping) {
+      for (int i = 0; i < cfg.vx_samples; ++i) {
+        vtheta_samp = 0;
+        gen(vx_samp, vy_samp, vtheta_samp);
+        if (better()) std::swap(best, comp);
+        vtheta_samp = min_vel_theta;
+        for (int j = 0; j < cfg.vtheta_samples - 1; ++j) {
+          gen(vx_samp, vy_samp, vtheta_samp);
+          if (better()) std::swap(best, comp);
+          vtheta_samp += dvtheta;
+        }
+        vx_samp += dvx;
+      }
+      if (cfg.holonomic_robot) {
+        gen(0.1, 0.1, 0.0);
+        if (better()) std::swap(best, comp);
+        gen(0.1, -0.1, 0.0);
+        if (better()) std::swap(best, comp);
+      }
+    }
+    vtheta_samp = min_vel_theta;
+    vx_samp = 0.0;
+    vy_samp = 0.0;
+    double heading_dist = DBL_MAX;
+    auto ahead = [&](const Result& t, double& out) {  // goal distance one heading_lookahead ahead of the end point
+      const double th_r = t.th.back();
+      unsigned cx, cy;
+      if (!cm.world_to_map(t.x.back() + cfg.heading_lookahead * cos(th_r), t.y.back() + cfg.heading_lookahead * sin(th_r), cx, cy))
+        return false;
+      out = goal_dist[size_t(cy) * cm.sx + cx];
+      return true;
+    };
+    for (int i = 0; i < cfg.vtheta_samples; ++i) {
+      const double limited = vtheta_samp > 0 ? std::max(vtheta_samp, cfg.min_in_place_vel_th)
+                                             : std::min(vtheta_samp, -1.0 * cfg.min_in_place_vel_th);
+      gen(vx_samp, vy_samp, limited);
+      if (comp->cost >= 0 && (comp->cost <= best->cost || best->cost < 0 || best->yv != 0.0) &&
+          (vtheta_samp > dvtheta || vtheta_samp < -1 * dvtheta)) {
+        double ag;
+        if (ahead(*comp, ag) && ag < heading_dist) {
+          if (vtheta_samp < 0 && !stuck_left) { std::swap(best, comp); heading_dist = ag; }
+          else if (vtheta_samp > 0 && !stuck_right) { std::swap(best, comp); heading_dist = ag; }
+        }
+      }
+      vtheta_samp += dvtheta;
+    }
+    auto reset_if_moved = [&]() {
+      if (hypot(x - prev_x, y - prev_y) > cfg.oscillation_reset_dist)
+        rotating_left = rotating_right = strafe_left = strafe_right = stuck_left = stuck_right = stuck_left_strafe =
+            stuck_right_strafe = false;
+    };
+    auto leave_escape = [&]() {
+      double a = fmod(fmod(theta - escape_theta, 2.0 * M_PI) + 2.0 * M_PI, 2.0 * M_PI);
+      if (a > M_PI) a -= 2.0 * M_PI;
+      if (hypot(x - escape_x, y - escape_y) > cfg.escape_reset_dist || fabs(a) > cfg.escape_reset_theta) escaping = false;
+    };
+    if (best->cost >= 0) {  // :700-749
+      if (!(best->xv > 0)) {
+        if (best->thetav < 0) { if (rotating_right) stuck_right = true; rotating_right = true; }
+        else if (best->thetav > 0) { if (rotating_left) stuck_left = true; rotating_left = true; }
+        else if (best->yv > 0) { if (strafe_right) stuck_right_strafe = true; strafe_right = true; }
+        else if (best->yv < 0) { if (strafe_left) stuck_left_strafe = true; strafe_left = true; }
+        prev_x = x;
+        prev_y = y;
+      }
+      reset_if_moved();
+      leave_escape();
+      return *best;
+    }
+    if (cfg.holonomic_robot) {  // :752-797
+      vtheta_samp = min_vel_theta;
+      vx_samp = 0.0;
+      for (int i = 0; i < cfg.n_y_vels; ++i) {
+        vtheta_samp = 0;
+        vy_samp = cfg.y_vels[i];
+        gen(vx_samp, vy_samp, vtheta_samp);
+        if (comp->cost >= 0 && (comp->cost <= best->cost || best->cost < 0)) {
+          double ag;
+          if (ahead(*comp, ag) && ag < heading_dist) {
+            if (vy_samp > 0 && !stuck_left_strafe) { std::swap(best, comp); heading_dist = ag; }
+            else if (vy_samp < 0 && !stuck_right_strafe) { std::swap(best, comp); heading_dist = ag; }
+          }
+        }
+      }
+    }
+    if (best->cost >= 0) {  // :800-848
+      if (!(best->xv > 0)) {
+        if (best->thetav < 0) { if (rotating_right) stuck_right = true; rotating_left = true; }
+        else if (best->thetav > 0) { if (rotating_left) stuck_left = true; rotating_right = true; }
+        else if (best->yv > 0) { if (strafe_right) stuck_right_strafe = true; strafe_left = true; }
+        else if (best->yv < 0) { if (strafe_left) stuck_left_strafe = true; strafe_right = true; }
+        prev_x = x;
+        prev_y = y;
+      }
+      reset_if_moved();
+      leave_escape();
+      return *best;
+    }
+    gen(cfg.backup_vel, 0.0, 0.0);  // :851-903
+    std::swap(best, comp);
+    reset_if_moved();
+    if (!escaping && best->cost > -2.0) {
+      escape_x = x;
+      escape_y = y;
+      escape_theta = theta;
+      escaping = true;
+    }
+    leave_escape();
+    if (best->cost == -1.0) best->cost = 1.0;
+    return *best;
+  }
+
+  // findBestPath (:908-980)
+  Result find_best_path(const double pose[3], const double vel[3]) {
+    const double x = (float)pose[0], y = (float)pose[1], theta = (float)pose[2];  // Eigen::Vector3f pos / vel
+    const double vx = (float)vel[0], vy = (float)vel[1], vtheta = (float)vel[2];
+    std::vector<uint8_t> within(size_t(cm.sx) * cm.sy, 0);
+    for (const auto& c : footprint_cells(x, y, theta)) within[size_t(c.second) * cm.sx + c.first] = 1;
+    wavefront(false, &within, path_dist);
+    wavefront(true, nullptr, goal_dist);
+    return create(x, y, theta, vx, vy, vtheta);
+  }
+};
+
 }  // namespace
 
 extern "C" {
+
+// ---- legacy TrajectoryPlanner (restated above)
+void navo_tp_default_config(navo_tp_config* c) {  // trajectory_planner_ros.cpp:116-213
+  memset(c, 0, sizeof(*c));
+  c->acc_lim_x = 2.5; c->acc_lim_y = 2.5; c->acc_lim_theta = 3.2;
+  c->sim_time = 1.0; c->sim_granularity = 0.025; c->angular_sim_granularity = 0.025; c->sim_period = 0.05;
+  c->pdist_scale = 0.6; c->gdist_scale = 0.8; c->occdist_scale = 0.01;
+  c->heading_lookahead = 0.325; c->oscillation_reset_dist = 0.05; c->escape_reset_dist = 0.10;
+  c->escape_reset_theta = M_PI_4;
+  c->max_vel_x = 0.5; c->min_vel_x = 0.1; c->max_vel_th = 1.0; c->min_vel_th = -1.0; c->min_in_place_vel_th = 0.4;
+  c->backup_vel = -0.1; c->heading_scoring_timestep = 0.8; c->stop_time_buffer = 0.2;
+  c->y_vels[0] = -0.3; c->y_vels[1] = -0.1; c->y_vels[2] = 0.1; c->y_vels[3] = 0.3; c->n_y_vels = 4;
+  c->vx_samples = 3; c->vtheta_samples = 20;
+  c->holonomic_robot = 1; c->dwa = 1; c->heading_scoring = 0; c->simple_attractor = 0; c->allow_unknown = 0;
+}
+void* navo_tp_create(const navo_tp_config* cfg, uint32_t size_x, uint32_t size_y, double resolution,
+                     const double* footprint_xy, int n_footprint) {
+  Tp* t = new Tp;
+  t->cfg = *cfg;
+  t->cm.resize(size_x, size_y, resolution, 0.0, 0.0);
+  for (int i = 0; i < n_footprint; ++i) t->footprint.push_back(Pt{footprint_xy[2 * i], footprint_xy[2 * i + 1]});
+  const size_t n = size_t(size_x) * size_y;
+  t->path_dist.assign(n, double(n + 1));  // MapGrid ctor + resetPathDist: unreachable everywhere
+  t->goal_dist.assign(n, double(n + 1));
+  return t;
+}
+void navo_tp_destroy(void* h) { delete static_cast<Tp*>(h); }
+void navo_tp_set_costmap(void* h, const uint8_t* grid, double origin_x, double origin_y) {
+  Tp* t = static_cast<Tp*>(h);
+  t->cm.ox = origin_x;
+  t->cm.oy = origin_y;
+  memcpy(t->cm.c.data(), grid, t->cm.c.size());
+}
+void navo_tp_update_plan(void* h, const double* plan_xy, int n) {  // updatePlan(plan, false) :477-502
+  Tp* t = static_cast<Tp*>(h);
+  t->plan.clear();
+  for (int i = 0; i < n; ++i) t->plan.push_back(Pt{plan_xy[2 * i], plan_xy[2 * i + 1]});
+  t->final_goal_valid = n > 0;
+  if (n > 0) { t->final_goal_x = t->plan.back().x; t->final_goal_y = t->plan.back().y; }
+}
+int navo_tp_find_best_path(void* h, const double pose[3], const double vel[3], navo_tp_result* result, double* points,
+                           int points_capacity) {
+  Tp* t = static_cast<Tp*>(h);
+  const Tp::Result r = t->find_best_path(pose, vel);
+  result->cost = r.cost; result->xv = r.xv; result->yv = r.yv; result->thetav = r.thetav;
+  result->n_points = (int)r.x.size();
+  result->flags = (t->stuck_left ? 1 : 0) | (t->stuck_right ? 2 : 0) | (t->stuck_left_strafe ? 4 : 0) |
+                  (t->stuck_right_strafe ? 8 : 0) | (t->rotating_left ? 16 : 0) | (t->rotating_right ? 32 : 0) |
+                  (t->strafe_left ? 64 : 0) | (t->strafe_right ? 128 : 0) | (t->escaping ? 256 : 0);
+  for (int i = 0; i < result->n_points && i < points_capacity; ++i) {
+    points[3 * i] = r.x[i]; points[3 * i + 1] = r.y[i]; points[3 * i + 2] = r.th[i];
+  }
+  return 0;
+}
+double navo_tp_score_trajectory(void* h, const double pose[3], const double vel[3], const double vs[3]) {  // :520-535
+  Tp* t = static_cast<Tp*>(h);
+  Tp::Result r;
+  t->generate(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], vs[0], vs[1], vs[2], t->cfg.acc_lim_x, t->cfg.acc_lim_y,
+              t->cfg.acc_lim_theta, double(size_t(t->cm.sx) * t->cm.sy), r);
+  return r.cost;
+}
+void navo_tp_get_grid(void* h, int which, double* out) {
+  Tp* t = static_cast<Tp*>(h);
+  const std::vector<double>& d = which == 0 ? t->path_dist : t->goal_dist;
+  memcpy(out, d.data(), d.size() * sizeof(double));
+}
 
 const char* navo_impl_name(void) { return "port"; }
 

@@ -156,8 +156,9 @@ void navo_mapgrid_bfs(const uint8_t* costs, uint32_t size_x, uint32_t size_y, co
                       int allow_unknown, double* dist_out);
 
 /* ---- legacy base_local_planner::TrajectoryPlanner (base_local_planner/src/trajectory_planner.cpp), SURVEY 8f-4:
- * the second consumer of the rollout scorer.  Implemented by libnavref.so only (the compiled reference); the CUDA
- * path is checked against it directly and against golden fixtures generated from it (tests/golden/tp_*.npz). */
+ * the second consumer of the rollout scorer.  libnavref.so drives the reference's own class; libnavoracle.so restates
+ * it (struct Tp in navoracle.cpp) and is pinned bit-for-bit against libnavref.so, the reference's utest.cpp known
+ * answer and the golden fixtures generated from the reference (tests/golden/tp_*.npz). */
 typedef struct {
   double acc_lim_x, acc_lim_y, acc_lim_theta;
   double sim_time, sim_granularity, angular_sim_granularity, sim_period;

@@ -119,7 +119,7 @@ def _declare(lib, prefix):
         "impl_name": (C.c_char_p, []),
         "project_scan": (i, [C.POINTER(LaserScan), C.POINTER(C.c_float), i, _f64p]),
     }
-    # the legacy TrajectoryPlanner is exported by the compiled reference only
+    # the legacy TrajectoryPlanner (both checkers export it; tolerated as missing for an older prebuilt library)
     optional = {
         "tp_default_config": (None, [C.POINTER(TpConfig)]),
         "tp_create": (vp, [C.POINTER(TpConfig), u, u, d, _f64p, i]),
@@ -326,7 +326,7 @@ class Dwa:
 
 
 class TrajectoryPlanner:
-    """The legacy base_local_planner::TrajectoryPlanner (compiled reference only)."""
+    """The legacy base_local_planner::TrajectoryPlanner."""
 
     def __init__(self, api, size_x, size_y, resolution, footprint_xy, **overrides):
         self.lib = api.lib

@@ -314,7 +314,7 @@ def test_scan_ingest_restatement_known_values(port):
     assert abs(d[0, 0]) < 1e-6 and abs(d[0, 1] - 1.0) < 1e-6
 
 
-def test_tp_utest_footprint_obstacles(ref):
-    """The reference's own TrajectoryPlanner known answer (utest.cpp:86-110) through the compiled reference."""
-    a, b, c = sc.tp_utest_footprint_obstacles(ref)
+def test_tp_utest_footprint_obstacles(port):
+    """The reference's own TrajectoryPlanner known answer (utest.cpp:86-110) through the CPU restatement."""
+    a, b, c = sc.tp_utest_footprint_obstacles(port)
     assert a == -1.0 and b == -1.0 and c >= 0.0
