@@ -352,3 +352,32 @@ def tp_utest_footprint_obstacles(api):
     tp.update_plan([(4.5, 4.5), (4.5, 6.5)])
     out.append(tp.score_trajectory((4.5, 4.5, np.pi / 2), (0.0, 0.0, 0.0), (1.0, 0.0, 0.0)))
     return out
+
+
+def run_tp_edge_cases(api, grid_api):
+    """Corner cases of the legacy TrajectoryPlanner: no plan at all, a degenerate (2-vertex) and an empty footprint,
+    a one-pose plan, a robot outside the map, unknown cells with allow_unknown on and off (allow_unknown is honoured by
+    the CUDA path and the restatement; the reference's own flag is uninitialised, so unknown cells stay out of the way
+    of anything it is compared on)."""
+    rng = np.random.default_rng(77)
+    s = dwa_scenario(rng, style="corridor")
+    grid = local_costmap(grid_api, np.random.default_rng(78), ox=s["origin"][0], oy=s["origin"][1], style="corridor")
+    out = []
+    cases = [
+        dict(fp=PENTAGON, plan=None, pose=s["pose"]),
+        dict(fp=[(-0.2, 0.0), (0.3, 0.0)], plan=s["plan"], pose=s["pose"]),
+        dict(fp=[], plan=s["plan"], pose=s["pose"]),
+        dict(fp=PENTAGON, plan=s["plan"][:1], pose=s["pose"]),
+        dict(fp=PENTAGON, plan=s["plan"], pose=(s["origin"][0] - 1.0, s["origin"][1] + 3.0, 0.0)),
+    ]
+    for c in cases:
+        tp = api.trajectory_planner(120, 120, 0.05, c["fp"], vx_samples=3, vtheta_samples=5)
+        tp.set_costmap(grid, *s["origin"])
+        if c["plan"] is not None:
+            tp.update_plan(c["plan"])
+        for cyc in range(2):
+            r = tp.find_best_path(c["pose"], s["vel"])
+            r["grids"] = [tp.grid(0), tp.grid(1)]
+            r["scores"] = np.array([tp.score_trajectory(c["pose"], s["vel"], (0.2, 0.0, 0.1))])
+            out.append(r)
+    return out

@@ -104,3 +104,30 @@ def test_scan_ingest_known_values(cuda):
     assert a[0, 0] == 1.0 and a[0, 1] == 0.0 and abs(a[1, 0]) < 1e-6 and a[1, 1] == 2.0 and a[2, 0] == -3.0
     assert np.all(a[:, 2] == np.float32(0.2))
     assert b[0, 0] == np.float32(np.float32(4.0) - np.float32(0.0001))
+
+
+def test_scan_ingest_empty_and_all_invalid(cuda, port):
+    """A scan without rays, one whose rays are all out of range, an empty cloud: the layer simply has nothing to do."""
+    base = dict(angle_min=np.float32(-1.0), angle_increment=np.float32(0.01), range_min=np.float32(0.1),
+                range_max=np.float32(4.0), translation=(2.0, 2.0, 0.2), rotation_xyzw=(0, 0, 0, 1),
+                min_obstacle_height=0.0, max_obstacle_height=2.0, obstacle_range=2.5, raytrace_range=3.0)
+    scans = [dict(base, ranges=np.zeros(0, np.float32)), dict(base, ranges=np.full(50, 9.0, np.float32)),
+             dict({k: v for k, v in base.items() if k not in ("angle_min", "angle_increment", "range_min", "range_max")},
+                  points=np.zeros((0, 3), np.float32)),
+             dict(base, ranges=np.full(30, 1.5, np.float32))]
+    cm = cuda.costmap(100, 100, 0.05)
+    o = cm.add_obstacle_layer(1, False, 2.0)
+    cm.add_inflation_layer(0.3, 10.0)
+    cm.set_footprint(sc.square_footprint())
+    cm.set_scans(o, scans)
+    assert [len(cm.get_cloud(o, k)) for k in range(4)] == [0, 0, 0, 30]
+    ref_cm = port.costmap(100, 100, 0.05)
+    ro = ref_cm.add_obstacle_layer(1, False, 2.0)
+    ref_cm.add_inflation_layer(0.3, 10.0)
+    ref_cm.set_footprint(sc.square_footprint())
+    clouds = [port.project_scan(s_) for s_ in scans]
+    ref_cm.set_observations(ro, [dict(origin=org, points=pts, obstacle_range=2.5, raytrace_range=3.0) for org, pts in clouds])
+    assert cm.update_map(2.0, 2.0, 0.0) == ref_cm.update_map(2.0, 2.0, 0.0)
+    assert np.array_equal(cm.get(), ref_cm.get()) and (cm.get() == 254).sum() > 0
+    cm.set_scans(o, [])
+    cm.update_map(2.0, 2.0, 0.0)

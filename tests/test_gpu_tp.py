@@ -49,6 +49,11 @@ def test_tp_boxed_in_matches_checker(cuda, port):
     assert got[-1]["flags"] & 4  # stuck_left_strafe
 
 
+def test_tp_edge_cases_match_checker(cuda, port):
+    """No plan, degenerate and empty footprints, a one-pose plan, the robot outside the map."""
+    assert_cycles_match(sc.run_tp_edge_cases(cuda, port), sc.run_tp_edge_cases(port, port), "edge cases")
+
+
 def test_tp_utest_footprint_obstacles(cuda):
     """base_local_planner/test/utest.cpp:86-110: trajectories that run or rotate the footprint into an obstacle are
     invalid (-1); the same command on a clear map is legal."""
