@@ -836,8 +836,13 @@ __global__ void __launch_bounds__(kObstacleThreads) k_voxel_commit(VoxelArgs a) 
     if (cell < 0) continue;
     const long long off = cell >> 5;
     const unsigned z = (unsigned)(cell & 31);
-    const uint32_t col = atomicOr(&a.vox[off], 0x00010001u << z) | (0x00010001u << z);
-    if (!bits_below_threshold(col >> 16, a.v.mark_threshold)) a.grid[off] = kLethal;
+    if (a.v.mark_threshold == 0) {  // one marked voxel already exceeds the threshold: no need to wait for the old column
+      atomicOr(&a.vox[off], 0x00010001u << z);
+      a.grid[off] = kLethal;
+    } else {
+      const uint32_t col = atomicOr(&a.vox[off], 0x00010001u << z) | (0x00010001u << z);
+      if (!bits_below_threshold(col >> 16, a.v.mark_threshold)) a.grid[off] = kLethal;
+    }
   }
   __syncthreads();
   if (a.do_poly) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
