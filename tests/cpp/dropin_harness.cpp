@@ -14,8 +14,12 @@
 //       constructed with the same arguments on the same Costmap2D and driven through the same public calls
 //       (updatePlan, findBestPath with tf::Stamped<tf::Pose>, scoreTrajectory, checkTrajectory) for 8 cycles,
 //       including cycles where the robot is boxed in and the planner rotates in place / backs up.
+//   D   navgpu_plugins::GpuLayeredCostmap fed with LaserScans (setLaserScans: projection, transform and height filter
+//       on the device) versus the checker's stack (the reference's LayeredCostmap + its own raytraceLine / MarkCell
+//       behind libnavref's C API) fed with the clouds of the restated ingest path: master grids over 3 cycles.
 // Prints one line per check and exits non-zero on any mismatch.  Test infrastructure, not product code.
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstring>
 #include <random>
@@ -328,6 +332,77 @@ void testTrajectoryPlanner() {
   report("C  GpuTrajectoryPlanner vs reference TrajectoryPlanner, 8 cycles", bad, cycles);
 }
 
+void testLaserScanIngest() {
+  const unsigned sx = 240, sy = 200;
+  const double res = 0.05;
+  const std::vector<unsigned char> map = blockMap(sx, sy, 3);
+  navgpu_plugins::GpuLayeredCostmap gpu(sx, sy, res, 0.0, 0.0, false, false);
+  const int gs = gpu.addStaticLayer(false);
+  const int go = gpu.addObstacleLayer(1, true, 2.0);
+  gpu.addInflationLayer(0.55, 10.0);
+  gpu.setFootprint(squareFootprint(0.325));
+  gpu.setLayerCosts(gs, map.data());
+  void* ref = navo_costmap_create(sx, sy, res, 0.0, 0.0, 0, 0);
+  const int rs = navo_costmap_add_grid_layer(ref, NAVO_TRUE_OVERWRITE);
+  const int ro = navo_costmap_add_obstacle_layer(ref, 1, 1, 2.0);
+  navo_costmap_add_inflation_layer(ref, 0.55, 10.0);
+  const double fp[8] = {0.325, 0.325, 0.325, -0.325, -0.325, -0.325, -0.325, 0.325};
+  navo_costmap_set_footprint(ref, fp, 4);
+  navo_grid_layer_set(ref, rs, map.data());
+  std::mt19937 rng(5);
+  std::uniform_real_distribution<float> range(0.05f, 6.0f);
+  long bad = 0, cells = 0;
+  for (int c = 0; c < 3; ++c) {
+    const int n = 360;
+    std::vector<float> ranges(n);
+    for (int i = 0; i < n; ++i) ranges[i] = range(rng);
+    ranges[7] = std::numeric_limits<float>::infinity();
+    ranges[11] = std::numeric_limits<float>::quiet_NaN();
+    const double yaw = 0.4 * c, px = 5.0 + 0.5 * c, py = 4.0 + 0.3 * c;
+    navgpu_laser_scan gsn;
+    memset(&gsn, 0, sizeof(gsn));
+    gsn.ranges = ranges.data(); gsn.n_ranges = n; gsn.inf_is_valid = c & 1;
+    gsn.angle_min = -3.14159f; gsn.angle_increment = 6.28318f / n; gsn.range_min = 0.1f; gsn.range_max = 5.5f;
+    gsn.sensor_to_global_translation[0] = px; gsn.sensor_to_global_translation[1] = py; gsn.sensor_to_global_translation[2] = 0.3;
+    gsn.sensor_to_global_rotation_xyzw[2] = sin(yaw / 2); gsn.sensor_to_global_rotation_xyzw[3] = cos(yaw / 2);
+    gsn.min_obstacle_height = 0.0; gsn.max_obstacle_height = 2.0;
+    gsn.obstacle_range = 2.5; gsn.raytrace_range = 3.0; gsn.marking = 1; gsn.clearing = 1;
+    gpu.setLaserScans(go, std::vector<navgpu_laser_scan>(1, gsn));
+    navo_laser_scan rsn;
+    memset(&rsn, 0, sizeof(rsn));
+    rsn.ranges = ranges.data(); rsn.n_ranges = n; rsn.inf_is_valid = gsn.inf_is_valid;
+    rsn.angle_min = gsn.angle_min; rsn.angle_increment = gsn.angle_increment; rsn.range_min = gsn.range_min; rsn.range_max = gsn.range_max;
+    for (int k = 0; k < 3; ++k) rsn.translation[k] = gsn.sensor_to_global_translation[k];
+    for (int k = 0; k < 4; ++k) rsn.rotation_xyzw[k] = gsn.sensor_to_global_rotation_xyzw[k];
+    rsn.min_obstacle_height = 0.0; rsn.max_obstacle_height = 2.0;
+    std::vector<float> cloud(3 * n);
+    double origin[3];
+    const int np = navo_project_scan(&rsn, cloud.data(), n, origin);
+    navo_observation ob;
+    memset(&ob, 0, sizeof(ob));
+    ob.origin_x = origin[0]; ob.origin_y = origin[1]; ob.origin_z = origin[2];
+    ob.obstacle_range = 2.5; ob.raytrace_range = 3.0; ob.xyz = cloud.data(); ob.n_points = np; ob.marking = 1; ob.clearing = 1;
+    navo_obstacle_set_observations(ref, ro, &ob, 1);
+    int32_t w[4];
+    navo_costmap_update_map(ref, px, py, yaw, w);
+    std::vector<unsigned char> want(size_t(sx) * sy);
+    navo_costmap_get(ref, want.data());
+    const bool ok = gpu.ok() && gpu.updateMap(px, py, yaw);
+    Costmap2D* out = ok ? gpu.getCostmap() : NULL;
+    if (!out) {
+      printf("D GpuLayeredCostmap::setLaserScans failed: %s\n", navgpu_last_error());
+      ++failures;
+      navo_costmap_destroy(ref);
+      return;
+    }
+    // getCostmap() downloads the updated window; outside it both grids still hold the previous cycle's values
+    bad += countDiff(want.data(), out->getCharMap(), want.size());
+    cells += (long)want.size();
+  }
+  navo_costmap_destroy(ref);
+  report("D  GpuLayeredCostmap fed with LaserScans vs the checker's stack, 3 cycles", bad, cells);
+}
+
 }  // namespace
 
 int main() {
@@ -339,6 +414,7 @@ int main() {
   testFusedStack();
   testScoredSamplingPlanner();
   testTrajectoryPlanner();
+  testLaserScanIngest();
   printf("%s\n", failures ? "DROP-IN FAILED" : "DROP-IN OK");
   return failures ? 1 : 0;
 }

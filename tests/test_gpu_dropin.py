@@ -32,7 +32,9 @@ def test_adapters_match_reference_classes(cuda):
     """A1: reference LayeredCostmap with GpuInflationLayer as its plugin == with costmap_2d::InflationLayer (4 cycles);
     A2: GpuLayeredCostmap == reference stack; B: GpuScoredSamplingPlanner through base_local_planner::TrajectorySearch
     == the reference's generator + critics + SimpleScoredSamplingPlanner (best index, cost <= 1e-5 rel, velocities,
-    point count, explored count, oscillation flags) over 6 control cycles."""
+    point count, explored count, oscillation flags) over 6 control cycles; C: GpuTrajectoryPlanner == the reference's
+    TrajectoryPlanner through the same public calls; D: GpuLayeredCostmap fed with LaserScans == the checker's stack fed
+    with the clouds of the restated ingest path."""
     if not os.path.exists(HARNESS):
         if os.path.isdir("/root/reference"):
             build_harness()
