@@ -722,6 +722,8 @@ struct navgpu_fleet {
   std::vector<double> origins;  // n x 2
   std::vector<std::vector<P2>> plan, adj_path, adj_front, adj_align;
   std::vector<char> align_is_path;  // per robot: adj_align == adj_path
+  std::vector<float> h_samples;     // per-step staging of every robot's velocity samples
+  bool grids_dirty = true;          // geometry / plans changed: the robots' MapGrid jobs must reach the device before the wavefronts
   std::vector<double> align_scale;
   std::vector<Oscillation> osc;
   std::vector<double> res_v;  // n x 3 persistent result velocities
@@ -815,6 +817,7 @@ int navgpu_fleet_set_maps(navgpu_fleet* f, const uint8_t* raw_maps, const double
   if (!f || !raw_maps || !origins_xy) return fail(NAVGPU_ERR_INVALID, "bad arguments");
   NAVGPU_CUDA(cudaSetDevice(f->device));
   f->origins.assign(origins_xy, origins_xy + size_t(2) * f->n);
+  f->grids_dirty = true;  // the robots' map origins changed
   // one contiguous H2D copy, then a device-side scatter into the padded stack
   const size_t raw_bytes = size_t(f->n) * f->sy * f->sx;
   NAVGPU_CUDA(cudaMemcpyAsync(f->d_raw, raw_maps, raw_bytes, cudaMemcpyHostToDevice, f->stream));
@@ -860,6 +863,7 @@ int navgpu_fleet_set_plans(navgpu_fleet* f, const double* poses, const double* p
     f->align_is_path[r] = same_plan(f->adj_align[r], f->adj_path[r]);
   }
   f->plans_dirty = true;
+  f->grids_dirty = true;
   return NAVGPU_OK;
 }
 
@@ -906,29 +910,55 @@ int navgpu_fleet_step(navgpu_fleet* f, const double* poses, const double* vels, 
     f->plans_dirty = false;
   }
 
-  // ---- per-robot scalars: samples (SimpleTrajectoryGenerator::initialise), pose, velocity, oscillation mask
-  std::vector<float> samples;
-  int max_samples = 0;
+  // ---- the MapGrid wavefronts only need each robot's geometry and plans, which change with set_maps / set_plans, not
+  // per step: they are launched first, and the per-step host work below (sample enumeration for every robot) runs
+  // while the GPU is busy with the costmap update and the wavefronts
   const size_t cells = size_t(f->sx) * f->sy;
+  if (f->grids_dirty) {
+    for (int r = 0; r < n; ++r) {
+      FleetRobot& R = f->h_robots[r];
+      R.grids.g = DwaGeom{f->d_master + size_t(r) * f->stride * f->pitch, f->sx, f->sy, f->pitch, f->res,
+                          f->origins[2 * r], f->origins[2 * r + 1], 1.0 / f->res};
+      uint32_t* dist = f->d_dist + size_t(r) * 4 * cells;
+      const P2* plans = reinterpret_cast<const P2*>(f->d_plans);
+      R.grids.job[0] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r]), (int)f->adj_path[r].size(), 0, dist};
+      R.grids.job[1] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r]), (int)f->adj_path[r].size(), 1, dist + cells};
+      R.grids.job[2] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 1]), (int)f->adj_front[r].size(), 1, dist + 2 * cells};
+      R.grids.job[3] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 2]), (int)f->adj_align[r].size(), 0, dist + 3 * cells};
+      if (f->align_is_path[r]) {  // the alignment critic holds the path critic's poses: one wavefront serves both
+        R.grids.job[3].dist = dist;
+        R.grids.job[3].skip = 1;
+      }
+    }
+    NAVGPU_CUDA(cudaMemcpyAsync(f->d_robots, f->h_robots.data(), sizeof(FleetRobot) * n, cudaMemcpyHostToDevice, f->stream));
+    NAVGPU_CUDA(cudaStreamSynchronize(f->stream));  // pageable source, rewritten below
+    f->grids_dirty = false;
+  }
+  {  // 4 MapGrid wavefronts per robot, one launch
+    navgpu_dwa tmp;  // geometry carrier for launch_mapgrid
+    tmp.sx = f->sx; tmp.sy = f->sy; tmp.stream = f->stream;
+    MapGridArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.g = DwaGeom{nullptr, f->sx, f->sy, f->pitch, f->res, 0.0, 0.0, 1.0 / f->res};
+    ma.allow_unknown = c.allow_unknown;
+    ma.fleet = f->d_robots;
+    NAVGPU_TRY(launch_mapgrid(&tmp, ma, 4 * n, 4));
+  }
+
+  // ---- per-robot scalars: samples (SimpleTrajectoryGenerator::initialise), pose, velocity, oscillation mask
+  std::vector<float>& samples = f->h_samples;
+  samples.clear();
+  int max_samples = 0;
   for (int r = 0; r < n; ++r) {
     const float pos[3] = {(float)poses[3 * r], (float)poses[3 * r + 1], (float)poses[3 * r + 2]};
     const float vel[3] = {(float)vels[3 * r], (float)vels[3 * r + 1], (float)vels[3 * r + 2]};
     const float goal[2] = {(float)f->plan[r].back().x, (float)f->plan[r].back().y};
     const Samples s = enumerate_samples(c, pos, vel, goal);
-    if (s.v.size() > (size_t)kInlineSamples) return fail(NAVGPU_ERR_UNSUPPORTED, "more than %d per-axis samples per robot", kInlineSamples);
-    FleetRobot& R = f->h_robots[r];
-    R.grids.g = DwaGeom{f->d_master + size_t(r) * f->stride * f->pitch, f->sx, f->sy, f->pitch, f->res,
-                        f->origins[2 * r], f->origins[2 * r + 1], 1.0 / f->res};
-    uint32_t* dist = f->d_dist + size_t(r) * 4 * cells;
-    const P2* plans = reinterpret_cast<const P2*>(f->d_plans);
-    R.grids.job[0] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r]), (int)f->adj_path[r].size(), 0, dist};
-    R.grids.job[1] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r]), (int)f->adj_path[r].size(), 1, dist + cells};
-    R.grids.job[2] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 1]), (int)f->adj_front[r].size(), 1, dist + 2 * cells};
-    R.grids.job[3] = MapGridJob{reinterpret_cast<const double*>(plans + f->plan_off[3 * r + 2]), (int)f->adj_align[r].size(), 0, dist + 3 * cells};
-    if (f->align_is_path[r]) {  // the alignment critic holds the path critic's poses: one wavefront serves both
-      R.grids.job[3].dist = dist;
-      R.grids.job[3].skip = 1;
+    if (s.v.size() > (size_t)kInlineSamples) {
+      cudaStreamSynchronize(f->stream);
+      return fail(NAVGPU_ERR_UNSUPPORTED, "more than %d per-axis samples per robot", kInlineSamples);
     }
+    FleetRobot& R = f->h_robots[r];
     for (int k = 0; k < 3; ++k) { R.pos[k] = pos[k]; R.vel[k] = vel[k]; }
     R.osc_mask = f->osc[r].mask();
     R.scale_alignment = f->align_scale[r];
@@ -957,20 +987,10 @@ int navgpu_fleet_step(navgpu_fleet* f, const double* poses, const double* vels, 
   }
   if (blocks > 0x7fffffffull) return fail(NAVGPU_ERR_UNSUPPORTED, "too many samples in one fleet launch");
 
-  // ---- 4 MapGrid wavefronts per robot, one launch
-  navgpu_dwa tmp;  // geometry carrier for launch_mapgrid
-  tmp.sx = f->sx; tmp.sy = f->sy; tmp.stream = f->stream;
-  MapGridArgs ma;
-  memset(&ma, 0, sizeof(ma));
-  ma.g = DwaGeom{nullptr, f->sx, f->sy, f->pitch, f->res, 0.0, 0.0, 1.0 / f->res};
-  ma.allow_unknown = c.allow_unknown;
-  ma.fleet = f->d_robots;
-  NAVGPU_TRY(launch_mapgrid(&tmp, ma, 4 * n, 4));
-
   // ---- rollouts + critics + per-robot argmin
   DwaScoreArgs base;
   memset(&base, 0, sizeof(base));
-  base.g = ma.g;
+  base.g = DwaGeom{nullptr, f->sx, f->sy, f->pitch, f->res, 0.0, 0.0, 1.0 / f->res};
   base.acc[0] = (float)c.acc_lim_x; base.acc[1] = (float)c.acc_lim_y; base.acc[2] = (float)c.acc_lim_theta;
   base.min_trans_vel = c.min_trans_vel; base.max_trans_vel = c.max_trans_vel; base.min_rot_vel = c.min_rot_vel;
   base.sim_time = c.sim_time; base.sim_granularity = c.sim_granularity; base.angular_sim_granularity = c.angular_sim_granularity;
