@@ -1152,7 +1152,11 @@ __device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const D
                                                  int sxn, int sy0, int syn) {
   const int R = a.R;
   const unsigned sp16 = seed_pitch16(a.pitch);
-  const bool col_any = kInterior || (x + 16 > w.x0 && x < w.xn), col_all = kInterior || (x >= w.x0 && x + 16 <= w.xn);
+  // A window that reaches the map's right edge owns the row padding behind it as well (nothing reads those bytes, and
+  // their seed bits are masked off below), so a group that straddles only that edge keeps the packed 16-cell path
+  // instead of the per-cell one -- every row of a map whose width is not a multiple of 16 has such a group.
+  const int xn_all = w.xn == (int)a.sx ? (int)a.pitch : w.xn;
+  const bool col_any = kInterior || (x + 16 > w.x0 && x < w.xn), col_all = kInterior || (x >= w.x0 && x + 16 <= xn_all);
   const bool col_seed = kInterior ? R > 0 : (R > 0 && x + 16 > sx0 && x < sxn);
 
   // loads of all row iterations first (memory-level parallelism), then the merges
