@@ -1044,4 +1044,4 @@ int navgpu_fleet_get_oscillation_mask(navgpu_fleet* f, int robot, int* mask_out)
 }  // extern "C"
 
 // the legacy TrajectoryPlanner shares this translation unit's kernels (MapGrid wavefront, footprint walks)
-#include "trajectory_planner.inc"
+#include "tp_host.inc"
