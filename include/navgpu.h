@@ -23,6 +23,7 @@
 #ifndef NAVGPU_H_
 #define NAVGPU_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -146,6 +147,14 @@ void* navgpu_costmap_stream(navgpu_costmap* h);
 /* master grid read-back to HOST: whole grid, or a window [x0,xn) x [y0,yn) packed row-major into out */
 int navgpu_costmap_get(navgpu_costmap* h, uint8_t* host_out);
 int navgpu_costmap_get_window(navgpu_costmap* h, int x0, int y0, int xn, int yn, uint8_t* host_out);
+/* the same, written straight into a host grid whose rows are host_pitch bytes apart -- e.g. the buffer of the host
+ * Costmap2D the adapter keeps in sync (host_grid points at cell (0, 0); the window lands at its own place in it) */
+int navgpu_costmap_get_window_into(navgpu_costmap* h, int x0, int y0, int xn, int yn, uint8_t* host_grid,
+                                   uint32_t host_pitch);
+/* page-lock / release a host buffer the caller owns, so that copies from and to it run at full PCIe speed (a pageable
+ * 16 MB download takes about 4x as long); purely an optimisation, every entry point also accepts pageable memory */
+int navgpu_host_register(void* ptr, size_t bytes);
+int navgpu_host_unregister(void* ptr);
 /* the same window as nav_msgs/OccupancyGrid data: Costmap2DPublisher's cost translation table
  * (costmap_2d/src/costmap_2d_publisher.cpp:56-71, 139-152) applied on the device while the window is packed */
 int navgpu_costmap_get_window_occupancy(navgpu_costmap* h, int x0, int y0, int xn, int yn, int8_t* host_out);

@@ -115,6 +115,9 @@ SIGNATURES = {
     "navgpu_costmap_last_timing_split": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "navgpu_costmap_get": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
+    "navgpu_costmap_get_window_into": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_uint32]),
+    "navgpu_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "navgpu_host_unregister": (C.c_int, [C.c_void_p]),
     "navgpu_costmap_get_window_occupancy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _i8p]),
     "navgpu_costmap_set": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_layer_get": (C.c_int, [C.c_void_p, C.c_int, _u8p]),
@@ -351,6 +354,12 @@ class Costmap:
             out = np.empty((yn - y0, xn - x0), dtype=np.uint8)
         self.api.check(self.lib.navgpu_costmap_get_window(self.h, x0, y0, xn, yn, _p(out, _u8p)))
         return out
+
+    def get_window_into(self, x0, y0, xn, yn, host_grid):
+        """Downloads the window straight into its place in a full-size host grid (size_y x size_x uint8)."""
+        assert host_grid.dtype == np.uint8 and host_grid.flags["C_CONTIGUOUS"]
+        self.api.check(self.lib.navgpu_costmap_get_window_into(self.h, x0, y0, xn, yn, _p(host_grid, _u8p),
+                                                               host_grid.shape[1]))
 
     def get_window_occupancy(self, x0, y0, xn, yn):
         out = np.empty((yn - y0, xn - x0), dtype=np.int8)

@@ -1071,6 +1071,31 @@ int navgpu_costmap_get_window(navgpu_costmap* h, int x0, int y0, int xn, int yn,
   return NAVGPU_OK;
 }
 
+int navgpu_costmap_get_window_into(navgpu_costmap* h, int x0, int y0, int xn, int yn, uint8_t* host_grid, uint32_t host_pitch) {
+  if (!h || !host_grid || x0 < 0 || y0 < 0 || xn > (int)h->sx || yn > (int)h->sy || xn < x0 || yn < y0 || host_pitch < h->sx)
+    return fail(NAVGPU_ERR_INVALID, "bad window");
+  if (xn == x0 || yn == y0) return NAVGPU_OK;
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMemcpy2DAsync(host_grid + size_t(y0) * host_pitch + x0, host_pitch,
+                                h->master[h->cur] + size_t(y0) * h->pitch + x0, h->pitch, xn - x0, yn - y0,
+                                cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+int navgpu_host_register(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (navgpu_device_count() <= 0) return fail(NAVGPU_ERR_CUDA, "no CUDA device (libnavgpu has no CPU fallback)");
+  NAVGPU_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return NAVGPU_OK;
+}
+
+int navgpu_host_unregister(void* ptr) {
+  if (!ptr) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_CUDA(cudaHostUnregister(ptr));
+  return NAVGPU_OK;
+}
+
 int navgpu_costmap_get_window_occupancy(navgpu_costmap* h, int x0, int y0, int xn, int yn, int8_t* host_out) {
   if (!h || !host_out || x0 < 0 || y0 < 0 || xn > (int)h->sx || yn > (int)h->sy || xn < x0 || yn < y0)
     return fail(NAVGPU_ERR_INVALID, "bad window");

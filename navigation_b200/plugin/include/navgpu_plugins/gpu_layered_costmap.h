@@ -28,8 +28,11 @@ class GpuLayeredCostmap {
     status_ = navgpu_costmap_create(&handle_, size_x, size_y, resolution, origin_x, origin_y, rolling_window,
                                     track_unknown, device);
     bounds_[0] = bounds_[1] = bounds_[2] = bounds_[3] = 0;
+    // the host copy is page-locked so that window downloads run at PCIe speed (an optimisation: failure is harmless)
+    host_pinned_ = handle_ != NULL && navgpu_host_register(host_.getCharMap(), size_t(size_x) * size_y) == NAVGPU_OK;
   }
   ~GpuLayeredCostmap() {
+    if (host_pinned_) navgpu_host_unregister(host_.getCharMap());
     if (handle_) navgpu_costmap_destroy(handle_);
   }
   GpuLayeredCostmap(const GpuLayeredCostmap&) = delete;
@@ -132,15 +135,15 @@ class GpuLayeredCostmap {
   costmap_2d::Costmap2D* getCostmap() {
     const int w = bounds_[1] - bounds_[0], h = bounds_[3] - bounds_[2];
     if (w > 0 && h > 0) {
-      window_.resize(size_t(w) * h);
-      if (!check(navgpu_costmap_get_window(handle_, bounds_[0], bounds_[2], bounds_[1], bounds_[3], window_.data())))
-        return NULL;
       double origin[2];
       navgpu_costmap_get_origin(handle_, origin);
-      host_.updateOrigin(origin[0], origin[1]);
-      unsigned char* dst = host_.getCharMap();
-      const unsigned int sx = host_.getSizeInCellsX();
-      for (int r = 0; r < h; ++r) memcpy(dst + size_t(bounds_[2] + r) * sx + bounds_[0], window_.data() + size_t(r) * w, w);
+      // Costmap2D::updateOrigin copies the whole grid twice even for a zero shift (costmap_2d.cpp:264-313): only when
+      // the device grid really rolled
+      if (origin[0] != host_.getOriginX() || origin[1] != host_.getOriginY()) host_.updateOrigin(origin[0], origin[1]);
+      // one device-to-host copy, straight into the window's place in the host grid
+      if (!check(navgpu_costmap_get_window_into(handle_, bounds_[0], bounds_[2], bounds_[1], bounds_[3], host_.getCharMap(),
+                                                host_.getSizeInCellsX())))
+        return NULL;
     }
     return &host_;
   }
@@ -152,8 +155,8 @@ class GpuLayeredCostmap {
     return rc == NAVGPU_OK;
   }
   navgpu_costmap* handle_;
+  bool host_pinned_;
   costmap_2d::Costmap2D host_;
-  std::vector<unsigned char> window_;
   int bounds_[4];
   int status_;
 };
