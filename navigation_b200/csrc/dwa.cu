@@ -116,6 +116,26 @@ struct Cycle {
 
 }  // namespace
 
+namespace {
+// Upload of a small host grid (the local costmap a planner scores against) without waiting for the stream: the rows
+// are copied into a pinned staging buffer owned by the handle and go to the device asynchronously; the buffer is
+// reused once the previous upload from it has completed (event).
+int stage_grid_upload(uint8_t** stage, cudaEvent_t* ev, uint8_t* dev, unsigned pitch, const uint8_t* host_grid, unsigned sx,
+                      unsigned sy, cudaStream_t stream) {
+  const size_t bytes = size_t(sx) * sy;
+  if (!*stage) {
+    NAVGPU_CUDA(cudaMallocHost(stage, bytes));
+    NAVGPU_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  } else {
+    NAVGPU_CUDA(cudaEventSynchronize(*ev));
+  }
+  memcpy(*stage, host_grid, bytes);
+  NAVGPU_CUDA(cudaMemcpy2DAsync(dev, pitch, *stage, sx, sx, sy, cudaMemcpyHostToDevice, stream));
+  NAVGPU_CUDA(cudaEventRecord(*ev, stream));
+  return NAVGPU_OK;
+}
+}  // namespace
+
 struct navgpu_dwa {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -125,6 +145,8 @@ struct navgpu_dwa {
   // local costmap: own copy (set_costmap) or a borrowed device grid (set_costmap_device)
   uint8_t* d_cost_own = nullptr;
   const uint8_t* d_cost = nullptr;
+  uint8_t* h_cost_stage = nullptr;  // pinned staging of set_costmap
+  cudaEvent_t ev_cost_stage = nullptr;
   unsigned pitch = 0;
   double ox = 0, oy = 0;
   // plans, already resolution-adjusted: 0 global plan, 1 front plan, 2 what the alignment critic last received
@@ -435,6 +457,8 @@ int navgpu_dwa_destroy(navgpu_dwa* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->d_cost_own);
+  if (h->h_cost_stage) cudaFreeHost(h->h_cost_stage);
+  if (h->ev_cost_stage) cudaEventDestroy(h->ev_cost_stage);
   for (int k = 0; k < 3; ++k) cudaFree(h->d_plan[k]);
   for (int k = 0; k < 4; ++k) cudaFree(h->d_dist[k]);
   cudaFree(h->d_samples); cudaFree(h->d_block_cost); cudaFree(h->d_block_index); cudaFree(h->d_counters);
@@ -458,8 +482,7 @@ int navgpu_dwa_set_costmap(navgpu_dwa* h, const uint8_t* host_grid, double origi
   NAVGPU_TRY(use_device(h));
   const unsigned pitch = grid_pitch(h->sx);
   if (!h->d_cost_own) NAVGPU_CUDA(cudaMalloc(&h->d_cost_own, size_t(pitch) * h->sy));
-  NAVGPU_CUDA(cudaMemcpy2DAsync(h->d_cost_own, pitch, host_grid, h->sx, h->sx, h->sy, cudaMemcpyHostToDevice, h->stream));
-  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  NAVGPU_TRY(stage_grid_upload(&h->h_cost_stage, &h->ev_cost_stage, h->d_cost_own, pitch, host_grid, h->sx, h->sy, h->stream));
   h->d_cost = h->d_cost_own;
   h->pitch = pitch;
   h->ox = origin_x;
