@@ -275,11 +275,19 @@ __global__ void __launch_bounds__(kMapGridThreads, kWPT == 1 ? 3 : 1) k_mapgrid_
       }
       return any;
     };
-    for (uint32_t level = 0;; level += 2) {
-      last_level = level + 1;
-      if (!__syncthreads_or(one_level(F0, F1, level + 1))) break;
-      last_level = level + 2;
-      if (!__syncthreads_or(one_level(F1, F0, level + 2))) break;
+    // plain barriers between levels; the "anything still moving?" vote only every eighth level (a few empty levels
+    // at the end cost less than a reducing barrier per level)
+    for (uint32_t level = 0;; level += 8) {
+      int any = 0;
+#pragma unroll
+      for (uint32_t s2 = 0; s2 < 8; s2 += 2) {
+        any |= one_level(F0, F1, level + s2 + 1);
+        __syncthreads();
+        any |= one_level(F1, F0, level + s2 + 2);
+        if (s2 < 6) __syncthreads();
+      }
+      last_level = level + 8;
+      if (!__syncthreads_or(any)) break;
     }
   }
   __syncthreads();
