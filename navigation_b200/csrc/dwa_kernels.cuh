@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t mapgrid_passable(const DwaGeom& g, int allow
 // wavefront dies out the planes are parked in shared memory and un-sliced by whole warps (one word per warp step,
 // lane = cell) into coalesced uint32 stores.
 template <int kWPT>
-__global__ void __launch_bounds__(kMapGridThreads, kWPT == 1 ? 3 : 1) k_mapgrid_prepare_sliced(MapGridArgs a, int jobs_per_robot, int planes) {
+__global__ void __launch_bounds__(kMapGridThreads, kWPT == 1 ? 2 : 1) k_mapgrid_prepare_sliced(MapGridArgs a, int jobs_per_robot, int planes) {
   extern __shared__ uint32_t mg_smem[];
   cudaTriggerProgrammaticLaunchCompletion();  // the scoring kernel may be scheduled behind us; it waits for our end
   const MapGridJob job = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.job[blockIdx.x % jobs_per_robot]
