@@ -166,14 +166,12 @@ __device__ __forceinline__ uint32_t mapgrid_passable(const DwaGeom& g, int allow
   if (nbits == 32 && ((size_t)row & 3) == 0) {
     const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 8; ++q) {  // four cells per packed compare: obstacle = cost >= 253, minus 255 when unknown is allowed
       const uint32_t v = row4[q];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t c = (v >> (8 * b)) & 0xffu;
-        const bool obstacle = c == kLethal || c == kInscribed || (c == kNoInfo && !allow_unknown);
-        p |= (uint32_t)(!obstacle) << (4 * q + b);
-      }
+      const uint32_t ge = __vcmpgeu4(v, 0xfdfdfdfdu);
+      const uint32_t obs = allow_unknown ? ge & ~__vcmpeq4(v, 0xffffffffu) : ge;
+      const uint32_t bits = ((obs & 0x01010101u) * 0x01020408u) >> 24;  // bit b <-> byte b
+      p |= (~bits & 0xfu) << (4 * q);
     }
     return p;
   }
