@@ -38,11 +38,23 @@ def pick_winner(costs, indices):
     return best_c, best_i
 
 
+_BUFFERS = {}
+
+
 def allgather_minima(dist, torch, cost, index, device):
-    """All-gather of one (cost, index) pair per rank.  The index travels as fp64 (exact below 2^53)."""
+    """All-gather of one (cost, index) pair per rank.  The index travels as fp64 (exact below 2^53).  The send / receive
+    tensors are kept across calls (a sweep is a few hundred microseconds: allocations would show)."""
     world = dist.get_world_size()
-    buf = torch.tensor([cost, float(index)], dtype=torch.float64, device=device)
-    out = torch.zeros(2 * world, dtype=torch.float64, device=device)
+    key = (str(device), world)
+    if key not in _BUFFERS:
+        _BUFFERS[key] = (torch.zeros(2, dtype=torch.float64).pin_memory() if str(device) != "cpu"
+                         else torch.zeros(2, dtype=torch.float64),
+                         torch.zeros(2, dtype=torch.float64, device=device),
+                         torch.zeros(2 * world, dtype=torch.float64, device=device))
+    host, buf, out = _BUFFERS[key]
+    host[0] = cost
+    host[1] = float(index)
+    buf.copy_(host, non_blocking=True)
     dist.all_gather_into_tensor(out, buf)
     g = out.cpu().numpy().reshape(world, 2)
     return g[:, 0].copy(), g[:, 1].astype(np.int64)
