@@ -123,9 +123,21 @@ int navgpu_obstacle_set_scans(navgpu_costmap* h, int layer, const navgpu_laser_s
 int navgpu_obstacle_get_cloud(navgpu_costmap* h, int layer, int index, float* xyz_out, int capacity, int* n_out);
 /* InflationLayer::setInflationParameters (:356-370) */
 int navgpu_inflation_set_params(navgpu_costmap* h, int layer, double inflation_radius, double cost_scaling_factor);
-/* inflation algorithm: 0 = exact windowed nearest-lethal distance (default; equals the reference wherever its
- * priority-queue tie order does not matter), 1 = level-synchronous nearest-source propagation */
+/* Which implementation of InflationLayer::updateCosts (inflation_layer.cpp:172-293) the layer runs.  Both write
+ * max(old, cached cost) with the NO_INFORMATION rule (:249-254), both are tested bit for bit against a CPU
+ * specification (oracle variants 4 / 5), and both equal the reference itself wherever the order in which its priority
+ * queue pops equal-distance entries cannot matter (thick axis-aligned structures).
+ *   0 (default)  exact windowed nearest-seed inflation: every cell within the cached distance R of a LETHAL cell of
+ *                window +- R gets the cost of its NEAREST such cell.  Never lower than the reference; higher on the
+ *                rare cells the reference's propagation reaches only with a farther source.
+ *   1            level-synchronous nearest-source propagation: the reference's loop itself (sources carried through
+ *                4-neighbours, `seen` at pop, distance gate at enqueue), equal distances resolved by a fixed rule
+ *                instead of libstdc++'s heap history -- a legal execution of the reference's code; equals the reference
+ *                on every cell whose value does not depend on that history.  R <= 127.  One persistent kernel with a
+ *                grid barrier per distance level: about 1 ms at 4000 x 4000, R = 20 instead of 0.04 ms for mode 0. */
 int navgpu_inflation_set_mode(navgpu_costmap* h, int layer, int mode);
+/* number of pop rounds (distance levels) of the last mode-1 update of this costmap; synchronises the stream */
+int navgpu_inflation_last_rounds(navgpu_costmap* h, int* rounds_out);
 /* LayeredCostmap::updateMap.  Synchronous: returns after the cycle's kernels finished.
  * window_out = {x0, xn, y0, yn} (LayeredCostmap::getBounds). */
 int navgpu_costmap_update_map(navgpu_costmap* h, double robot_x, double robot_y, double robot_yaw,

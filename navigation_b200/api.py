@@ -105,6 +105,7 @@ SIGNATURES = {
     "navgpu_obstacle_get_cloud": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, _i32p]),
     "navgpu_inflation_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "navgpu_inflation_set_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "navgpu_inflation_last_rounds": (C.c_int, [C.c_void_p, _i32p]),
     "navgpu_costmap_update_map": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, _i32p]),
     "navgpu_costmap_update_map_async": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "navgpu_costmap_synchronize": (C.c_int, [C.c_void_p]),
@@ -311,6 +312,11 @@ class Costmap:
 
     def set_inflation_mode(self, layer, mode):
         self.api.check(self.lib.navgpu_inflation_set_mode(self.h, layer, mode))
+
+    def inflation_last_rounds(self):
+        r = np.zeros(1, dtype=np.int32)
+        self.api.check(self.lib.navgpu_inflation_last_rounds(self.h, _p(r, _i32p)))
+        return int(r[0])
 
     def update_map(self, x=0.0, y=0.0, yaw=0.0):
         w = np.zeros(4, dtype=np.int32)

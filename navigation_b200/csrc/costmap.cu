@@ -5,11 +5,13 @@
 // keeps in its objects (origins, parameters, cached tables, flags) and sequences the kernels of one update cycle.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <limits>
 #include <memory>
 #include <vector>
 
 #include "costmap_kernels.cuh"
+#include "inflate_propagate.cuh"
 
 namespace navgpu {
 
@@ -48,6 +50,7 @@ struct CostTables {
   std::vector<uint8_t> costs;  // (R+2)^2, [dx][dy]
   std::vector<double> dists;
   std::vector<uint8_t> by_d2;  // R*R+1: cost by squared distance
+  std::vector<uint16_t> rank;  // (R+2)^2: dense rank of dists (1 = distance 0), 0xffff where dists > R (mode 1)
   int reach2 = 0;              // largest squared distance with a non-zero cost
   bool ambiguous = false;      // two (dx,dy) with equal dx^2+dy^2 but different cached cost (never seen in practice)
 };
@@ -94,6 +97,16 @@ void build_tables(CostTables& t, unsigned R, double resolution, double inscribed
       }
     }
   t.reach2 = reach_of(t.by_d2);
+  // mode 1 orders pops by the cached double itself (inflation_layer.h:77-80): equal doubles <=> equal ranks
+  std::vector<double> vals;
+  for (double d : t.dists)
+    if (!(d > (double)R)) vals.push_back(d);
+  std::sort(vals.begin(), vals.end());
+  vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+  t.rank.assign(size_t(n) * n, 0xffff);
+  for (size_t i = 0; i < t.dists.size(); ++i)
+    if (!(t.dists[i] > (double)R))
+      t.rank[i] = (uint16_t)(1 + (std::lower_bound(vals.begin(), vals.end(), t.dists[i]) - vals.begin()));
 }
 
 static unsigned cell_distance(double world_dist, double resolution) {  // Costmap2D::cellDistance, costmap_2d.cpp:181-185
@@ -148,6 +161,9 @@ struct Layer {
   CostTables tables;
   uint8_t* d_cost_d2 = nullptr;
   size_t cost_d2_capacity = 0;
+  uint16_t* d_rank = nullptr;   // mode 1: CostTables::rank and ::costs on the device
+  uint8_t* d_cost2d = nullptr;
+  size_t table2d_capacity = 0;
   bool tables_dirty = true;
 };
 
@@ -176,6 +192,11 @@ struct navgpu_costmap {
   size_t occupancy_capacity = 0;
   uint16_t* d_seeds = nullptr;  // seed bitmask of the fast sweep (k_merge_seed -> k_inflate)
   size_t seeds_capacity = 0;
+  // inflation mode 1 (k_inflate_propagate): per-cell state + two frontier lists, barrier / round control
+  uint32_t* d_prop_state = nullptr;
+  PropCtl* d_prop_ctl = nullptr;
+  int prop_max_blocks = 0;
+  size_t prop_smem_set = 0;
   int win[4] = {0, 0, 0, 0};
   bool poly_attr_set = false;
   bool profile = false;
@@ -223,9 +244,25 @@ int upload_tables(navgpu_costmap* h, Layer& L) {
   if (!L.tables_dirty) return NAVGPU_OK;
   const unsigned R = cell_distance(L.radius, h->res);
   build_tables(L.tables, R, h->res, L.inscribed, L.weight);
-  if (L.tables.ambiguous)
+  if (L.mode == 0 && L.tables.ambiguous)
     return fail(NAVGPU_ERR_UNSUPPORTED, "inflation cost table is not a function of squared distance for R=%u", R);
   if (R > 254) return fail(NAVGPU_ERR_UNSUPPORTED, "cell inflation radius %u > 254", R);
+  if (L.mode == 1) {
+    if (R > 127) return fail(NAVGPU_ERR_UNSUPPORTED, "propagation mode carries sources as 8-bit offsets: R=%u > 127", R);
+    for (uint16_t r : L.tables.rank)
+      if (r != 0xffff && r > kPMaxRank) return fail(NAVGPU_ERR_UNSUPPORTED, "too many distinct distances for R=%u", R);
+    const size_t n2 = L.tables.costs.size();
+    if (n2 > L.table2d_capacity) {
+      if (L.d_rank) cudaFree(L.d_rank);
+      if (L.d_cost2d) cudaFree(L.d_cost2d);
+      L.d_rank = nullptr; L.d_cost2d = nullptr;
+      NAVGPU_CUDA(cudaMalloc(&L.d_rank, n2 * sizeof(uint16_t)));
+      NAVGPU_CUDA(cudaMalloc(&L.d_cost2d, n2));
+      L.table2d_capacity = n2;
+    }
+    NAVGPU_CUDA(cudaMemcpyAsync(L.d_rank, L.tables.rank.data(), n2 * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    NAVGPU_CUDA(cudaMemcpyAsync(L.d_cost2d, L.tables.costs.data(), n2, cudaMemcpyHostToDevice, h->stream));
+  }
   size_t n = L.tables.by_d2.size();
   if (n > L.cost_d2_capacity) {
     if (L.d_cost_d2) cudaFree(L.d_cost_d2);
@@ -241,9 +278,61 @@ int upload_tables(navgpu_costmap* h, Layer& L) {
 
 // One sweep over the master grid: the two-kernel fast path (k_merge_seed [+ k_inflate], R <= 31) or the generic
 // fused kernel (any R <= 254).  `seeds` is the handle's seed bitmask (sy x seed_pitch16(pitch) uint16, pads zero).
-int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic, cudaEvent_t ev_mid = nullptr) {
+// everything inflation mode 1 needs besides the sweep's own arguments (buffers sized for the grid of the sweep)
+struct PropBuffers {
+  uint32_t* state = nullptr;
+  uint32_t* list[2] = {nullptr, nullptr};
+  PropCtl* ctl = nullptr;
+  const uint16_t* rank = nullptr;
+  const uint8_t* cost = nullptr;
+  int max_blocks = 0;  // co-resident CTAs of k_inflate_propagate on this device
+};
+
+int propagate_max_blocks(int device, int R, int* out, size_t* smem_set) {
+  const size_t smem = propagate_smem(R);
+  if (smem > 200 * 1024) return fail(NAVGPU_ERR_UNSUPPORTED, "propagation tables for R=%d need %zu B of shared memory", R, smem);
+  if (smem > *smem_set) {
+    NAVGPU_CUDA(cudaFuncSetAttribute(k_inflate_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *smem_set = smem;
+  }
+  int per_sm = 0, sms = 0;
+  NAVGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_propagate, kPThreads, smem));
+  NAVGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (per_sm < 1) return fail(NAVGPU_ERR_UNSUPPORTED, "k_inflate_propagate does not fit an SM for R=%d", R);
+  *out = per_sm * sms;
+  return NAVGPU_OK;
+}
+
+int launch_propagate(const UpdateArgs& a, const uint16_t* seeds, const PropBuffers& pb, cudaStream_t stream) {
+  PropArgs pa;
+  pa.master = a.master;
+  pa.sx = a.sx; pa.sy = a.sy; pa.pitch = a.pitch;
+  pa.win = a.win;
+  pa.R = a.R;
+  pa.seeds = reinterpret_cast<const uint32_t*>(seeds);
+  pa.state = pb.state;
+  pa.rank = pb.rank;
+  pa.cost = pb.cost;
+  pa.ctl = pb.ctl;
+  pa.list[0] = pb.list[0];
+  pa.list[1] = pb.list[1];
+  // a small grid needs few CTAs (the per-round barrier is cheaper), a large one every co-resident CTA
+  const long long cells = (long long)a.pitch * a.sy;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cells / 8192, pb.max_blocks));
+  // barrier counters and list sizes 0, pending-rank slots "none"
+  NAVGPU_CUDA(cudaMemsetAsync(pb.ctl, 0, sizeof(PropCtl), stream));
+  NAVGPU_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(pb.ctl) + offsetof(PropCtl, kmin), 0xff, sizeof(pb.ctl->kmin), stream));
+  void* args[] = {&pa};
+  NAVGPU_CUDA(cudaLaunchCooperativeKernel((const void*)k_inflate_propagate, dim3(blocks), dim3(kPThreads), args,
+                                          propagate_smem(a.R), stream));
+  NAVGPU_LAUNCHED(1);
+  return NAVGPU_OK;
+}
+
+int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic, cudaEvent_t ev_mid = nullptr,
+                 const PropBuffers* prop = nullptr) {
   const int R = a.R;
-  if (R <= 31 && !force_generic) {
+  if ((R <= 31 && !force_generic) || (prop && R > 0)) {
     MergeSeedArgs m;
     m.master = a.master;
     m.sx = a.sx; m.sy = a.sy; m.pitch = a.pitch;
@@ -261,6 +350,7 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
       NAVGPU_LAUNCHED(1);
     }
     if (ev_mid) cudaEventRecord(ev_mid, stream);
+    if (prop && R > 0) return launch_propagate(a, seeds, *prop, stream);
     if (R > 0) {
       InflateArgs ia;
       ia.master = a.master;
@@ -301,7 +391,24 @@ int ensure_seeds(uint16_t** seeds, size_t* cap, unsigned pitch, unsigned sy, cud
   return NAVGPU_OK;
 }
 
-int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2, int reach2 = 0) {
+int ensure_prop(navgpu_costmap* h, const Layer& L, PropBuffers* pb) {
+  if (!h->d_prop_state) {  // per-cell state + the two frontier lists (a cell is listed at most once per list)
+    NAVGPU_CUDA(cudaMalloc(&h->d_prop_state, 3 * h->bytes() * sizeof(uint32_t)));
+    NAVGPU_CUDA(cudaMalloc(&h->d_prop_ctl, sizeof(PropCtl)));
+  }
+  NAVGPU_TRY(propagate_max_blocks(h->device, (int)L.tables.R, &h->prop_max_blocks, &h->prop_smem_set));
+  pb->state = h->d_prop_state;
+  pb->list[0] = h->d_prop_state + h->bytes();
+  pb->list[1] = h->d_prop_state + 2 * h->bytes();
+  pb->ctl = h->d_prop_ctl;
+  pb->rank = L.d_rank;
+  pb->cost = L.d_cost2d;
+  pb->max_blocks = h->prop_max_blocks;
+  return NAVGPU_OK;
+}
+
+int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2, int reach2 = 0,
+                  const Layer* infl = nullptr) {
   UpdateArgs a;
   a.master = h->master[h->cur];
   a.sx = h->sx; a.sy = h->sy; a.pitch = h->pitch;
@@ -312,9 +419,13 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   a.R = R;
   a.cost_d2 = cost_d2;
   a.reach2 = reach2;
-  if (R > 0 && R <= 31) NAVGPU_TRY(ensure_seeds(&h->d_seeds, &h->seeds_capacity, h->pitch, h->sy, h->stream));
+  PropBuffers pb;
+  const bool propagate = infl && infl->mode == 1 && R > 0;
+  if (propagate) NAVGPU_TRY(ensure_prop(h, *infl, &pb));
+  if (R > 0 && (R <= 31 || propagate)) NAVGPU_TRY(ensure_seeds(&h->d_seeds, &h->seeds_capacity, h->pitch, h->sy, h->stream));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[0], h->stream);
-  NAVGPU_TRY(launch_sweep(a, h->d_seeds, h->stream, h->force_generic, h->profile && R > 0 ? h->ev_mid : nullptr));
+  NAVGPU_TRY(launch_sweep(a, h->d_seeds, h->stream, h->force_generic, h->profile && R > 0 ? h->ev_mid : nullptr,
+                          propagate ? &pb : nullptr));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[1], h->stream);
   return NAVGPU_OK;
 }
@@ -520,7 +631,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
         NAVGPU_TRY(launch_update(h, ml, 0, 0, nullptr));
         ml.n = 0;
       }
-      NAVGPU_TRY(launch_update(h, ml, do_reset, (int)L.tables.R, L.d_cost_d2, L.tables.reach2));
+      NAVGPU_TRY(launch_update(h, ml, do_reset, (int)L.tables.R, L.d_cost_d2, L.tables.reach2, &L));
       ml.n = 0;
       do_reset = 0;
       pending = false;
@@ -588,13 +699,14 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   cudaStreamSynchronize(h->stream);
   for (Layer& L : h->layers) {
     cudaFree(L.grid[0]); cudaFree(L.grid[1]);
-    cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_mark_cells); cudaFree(L.d_scan);
+    cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_rank); cudaFree(L.d_cost2d); cudaFree(L.d_mark_cells); cudaFree(L.d_scan);
     if (L.h_stage) cudaFreeHost(L.h_stage);
     if (L.ev_stage) cudaEventDestroy(L.ev_stage);
     cudaFree(L.vox[0]); cudaFree(L.vox[1]);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
   cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
+  cudaFree(h->d_prop_state); cudaFree(h->d_prop_ctl);
   cudaFreeHost(h->h_win);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -984,8 +1096,20 @@ int navgpu_inflation_set_params(navgpu_costmap* h, int layer, double inflation_r
 int navgpu_inflation_set_mode(navgpu_costmap* h, int layer, int mode) {
   Layer* L = get_layer(h, layer, 2);
   if (!L || mode < 0 || mode > 1) return fail(NAVGPU_ERR_INVALID, "bad inflation layer / mode");
-  if (mode == 1) return fail(NAVGPU_ERR_UNSUPPORTED, "propagation mode is not built yet");
+  if (L->mode != mode) L->tables_dirty = true;  // mode 1 keeps the 2-D rank / cost tables on the device
   L->mode = mode;
+  return NAVGPU_OK;
+}
+
+int navgpu_inflation_last_rounds(navgpu_costmap* h, int* rounds_out) {
+  if (!h || !rounds_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  *rounds_out = 0;
+  if (!h->d_prop_ctl) return NAVGPU_OK;
+  NAVGPU_TRY(use_device(h));
+  unsigned r = 0;
+  NAVGPU_CUDA(cudaMemcpyAsync(&r, &h->d_prop_ctl->rounds, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  *rounds_out = (int)r;
   return NAVGPU_OK;
 }
 

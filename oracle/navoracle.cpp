@@ -603,6 +603,17 @@ struct InflationLayer : LayerBase {  // inflation_layer.cpp
       b.maxy = std::max(ty1, b.maxy) + radius;
     }
   }
+  // Tie-policy variants (checker-only; see oracle_api.h navo_inflation_set_variant).  0 = the reference as written.
+  int variant = 0;
+  uint64_t variant_seed = 0;
+  int last_rounds = 0;  // rounds of the level-synchronous variant's last update_costs
+
+  void write_cell(Grid& m, unsigned index, uint8_t cost) const {  // :249-254
+    uint8_t old = m.c[index];
+    if (old == kNoInfo && cost >= kInscribed) m.c[index] = cost;
+    else m.c[index] = std::max(old, cost);
+  }
+
   void update_costs(Costmap& cm, int min_i, int min_j, int max_i, int max_j) override {  // :172-266
     if (!enabled) return;
     Grid& m = cm.master;
@@ -614,6 +625,18 @@ struct InflationLayer : LayerBase {  // inflation_layer.cpp
     min_j = std::max(0, min_j);
     max_i = std::min(int(size_x), max_i);
     max_j = std::min(int(size_y), max_j);
+    if (variant == 4) return update_costs_exact(m, min_i, min_j, max_i, max_j);
+    if (variant == 5) return update_costs_level_sync(m, min_i, min_j, max_i, max_j, nullptr);
+    if (variant == 6) {
+      // certificate that variant 5 is a legal execution: run it on a scratch copy to learn which source every cell
+      // ended up with, then run the reference's SEQUENTIAL priority-queue loop, breaking equal-distance ties in favour
+      // of the entry that carries that source (oldest first otherwise).  The result must equal variant 5's.
+      Grid scratch = m;
+      hint.clear();
+      update_costs_level_sync(scratch, min_i, min_j, max_i, max_j, &hint);
+      std::fill(seen.begin(), seen.end(), 0);
+    }
+    if (variant != 0) return update_costs_tie_variant(m, min_i, min_j, max_i, max_j);
     std::priority_queue<QCell, std::vector<QCell>, QLess> q;
     const unsigned n = R + 2;
     auto enqueue = [&](unsigned index, unsigned mx, unsigned my, unsigned sx, unsigned sy) {  // :277-293
@@ -634,15 +657,175 @@ struct InflationLayer : LayerBase {  // inflation_layer.cpp
       if (seen[cur.index]) continue;
       seen[cur.index] = 1;
       unsigned dx = abs(int(cur.x) - int(cur.sx)), dy = abs(int(cur.y) - int(cur.sy));
-      uint8_t cost = costs[dx * n + dy];
-      uint8_t old = m.c[cur.index];
-      if (old == kNoInfo && cost >= kInscribed) m.c[cur.index] = cost;
-      else m.c[cur.index] = std::max(old, cost);
+      write_cell(m, cur.index, costs[dx * n + dy]);
       if (cur.x > 0) enqueue(cur.index - 1, cur.x - 1, cur.y, cur.sx, cur.sy);
       if (cur.y > 0) enqueue(cur.index - size_x, cur.x, cur.y - 1, cur.sx, cur.sy);
       if (cur.x < size_x - 1) enqueue(cur.index + 1, cur.x + 1, cur.y, cur.sx, cur.sy);
       if (cur.y < size_y - 1) enqueue(cur.index + size_x, cur.x, cur.y + 1, cur.sx, cur.sy);
     }
+  }
+
+  // The same algorithm (:172-293) with the one thing the reference leaves to libstdc++'s heap history made explicit:
+  // which of several queue entries with EQUAL distance is popped first.  variant 1 = oldest first (FIFO), 2 = newest
+  // first (LIFO), 3 = a seeded pseudo-random order.  Every variant is a legal execution of the reference's loop under
+  // some heap implementation; cells whose value differs between variants are the "tie-variant mask".
+  struct TCell {
+    double distance;
+    uint64_t tie;
+    unsigned index, x, y, sx, sy;
+  };
+  struct TLess {
+    bool operator()(const TCell& a, const TCell& b) const {
+      return a.distance > b.distance || (a.distance == b.distance && a.tie > b.tie);
+    }
+  };
+  static uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+  }
+  void update_costs_tie_variant(Grid& m, int min_i, int min_j, int max_i, int max_j) {
+    unsigned size_x = m.sx, size_y = m.sy;
+    std::priority_queue<TCell, std::vector<TCell>, TLess> q;
+    const unsigned n = R + 2;
+    uint64_t seq = 0;
+    auto enqueue = [&](unsigned index, unsigned mx, unsigned my, unsigned sx, unsigned sy) {
+      if (seen[index]) return;
+      unsigned dx = abs(int(mx) - int(sx)), dy = abs(int(my) - int(sy));
+      double d = dists[dx * n + dy];
+      if (d > R) return;
+      uint64_t s = seq++;
+      uint64_t tie = variant == 1 ? s : variant == 2 ? ~s : mix64(s ^ (variant_seed * 0x2545f4914f6cdd1dull));
+      if (variant == 6) tie = s | (hint[index] == int32_t(sy * size_x + sx) ? 0 : (1ull << 63));
+      q.push(TCell{d, tie, index, mx, my, sx, sy});
+    };
+    for (int j = min_j; j < max_j; j++)
+      for (int i = min_i; i < max_i; i++) {
+        unsigned index = j * size_x + i;
+        if (m.c[index] == kLethal) enqueue(index, i, j, i, j);
+      }
+    while (!q.empty()) {
+      TCell cur = q.top();
+      q.pop();
+      if (seen[cur.index]) continue;
+      seen[cur.index] = 1;
+      unsigned dx = abs(int(cur.x) - int(cur.sx)), dy = abs(int(cur.y) - int(cur.sy));
+      write_cell(m, cur.index, costs[dx * n + dy]);
+      if (cur.x > 0) enqueue(cur.index - 1, cur.x - 1, cur.y, cur.sx, cur.sy);
+      if (cur.y > 0) enqueue(cur.index - size_x, cur.x, cur.y - 1, cur.sx, cur.sy);
+      if (cur.x < size_x - 1) enqueue(cur.index + 1, cur.x + 1, cur.y, cur.sx, cur.sy);
+      if (cur.y < size_y - 1) enqueue(cur.index + size_x, cur.x, cur.y + 1, cur.sx, cur.sy);
+    }
+  }
+
+  // variant 4: exact windowed nearest-seed inflation -- every cell within cached distance <= R of a LETHAL cell of
+  // the seed region gets the cached cost of its NEAREST seed (what an unobstructed propagation would deliver).  This is
+  // the specification of the CUDA library's inflation mode 0.  Brute force; checker sizes only.
+  void update_costs_exact(Grid& m, int min_i, int min_j, int max_i, int max_j) {
+    const int size_x = m.sx, size_y = m.sy, r = R;
+    const unsigned n = R + 2;
+    std::vector<std::pair<int, int>> offs;
+    for (int dy = -r; dy <= r; ++dy)
+      for (int dx = -r; dx <= r; ++dx)
+        if (!(dists[unsigned(abs(dx)) * n + unsigned(abs(dy))] > R)) offs.emplace_back(dx, dy);
+    std::vector<uint8_t> best(size_t(size_x) * size_y, 0), hit(size_t(size_x) * size_y, 0);
+    std::vector<double> bd(size_t(size_x) * size_y, 1e300);
+    for (int j = min_j; j < max_j; j++)
+      for (int i = min_i; i < max_i; i++) {
+        if (m.c[size_t(j) * size_x + i] != kLethal) continue;
+        for (auto& o : offs) {
+          int x = i + o.first, y = j + o.second;
+          if (x < 0 || y < 0 || x >= size_x || y >= size_y) continue;
+          unsigned dx = abs(o.first), dy = abs(o.second);
+          double d = dists[dx * n + dy];
+          size_t idx = size_t(y) * size_x + x;
+          if (d < bd[idx]) { bd[idx] = d; best[idx] = costs[dx * n + dy]; hit[idx] = 1; }
+        }
+      }
+    for (size_t idx = 0; idx < hit.size(); ++idx)
+      if (hit[idx]) write_cell(m, unsigned(idx), best[idx]);
+  }
+
+  // variant 5: level-synchronous nearest-source propagation -- the specification of the CUDA library's inflation
+  // mode 1.  The reference's loop (:226-265) with one particular, order-independent choice among equal-distance queue
+  // entries: per round, every unseen cell's best pending entry is the minimum cached distance over the sources carried
+  // by its already-popped 4-neighbours (first of -x, -y, +x, +y on equal distance; an entry exists iff the neighbour
+  // was popped while this cell was unseen and the distance gate :286-287 passed); the round pops ALL cells whose best
+  // entry has the globally smallest distance.  Entries pushed by a pop never have the popped entry's own distance
+  // (dx^2+dy^2 changes parity between 4-neighbours), so a round is a legal sequence of reference pops.
+  std::vector<int32_t> hint;
+  void update_costs_level_sync(Grid& m, int min_i, int min_j, int max_i, int max_j, std::vector<int32_t>* owner_out) {
+    const int size_x = m.sx, size_y = m.sy;
+    const unsigned n = R + 2;
+    const size_t cells = size_t(size_x) * size_y;
+    std::vector<int32_t> owner(cells, -1);
+    std::vector<unsigned> frontier, next;  // unseen cells with at least one popped neighbour
+    std::vector<uint8_t> in_frontier(cells, 0);
+    auto push_frontier = [&](int x, int y) {
+      if (x < 0 || y < 0 || x >= size_x || y >= size_y) return;
+      size_t idx = size_t(y) * size_x + x;
+      if (owner[idx] >= 0 || in_frontier[idx]) return;
+      in_frontier[idx] = 1;
+      frontier.push_back(unsigned(idx));
+    };
+    last_rounds = 0;
+    std::vector<unsigned> popped;
+    for (int j = min_j; j < max_j; j++)
+      for (int i = min_i; i < max_i; i++) {
+        unsigned index = j * size_x + i;
+        if (m.c[index] == kLethal) { owner[index] = int32_t(index); popped.push_back(index); }
+      }
+    if (popped.empty()) {
+      if (owner_out) owner_out->swap(owner);
+      return;
+    }
+    for (unsigned index : popped) write_cell(m, index, costs[0]);
+    struct Best { double d; int32_t src; };
+    auto best_entry = [&](unsigned idx) {
+      int x = idx % size_x, y = idx / size_x;
+      Best b{1e300, -1};
+      const int nx[4] = {x - 1, x, x + 1, x}, ny[4] = {y, y - 1, y, y + 1};
+      for (int k = 0; k < 4; ++k) {
+        if (nx[k] < 0 || ny[k] < 0 || nx[k] >= size_x || ny[k] >= size_y) continue;
+        int32_t s = owner[size_t(ny[k]) * size_x + nx[k]];
+        if (s < 0) continue;
+        unsigned dx = abs(x - int(s % size_x)), dy = abs(y - int(s / size_x));
+        if (dx > R + 1 || dy > R + 1) continue;  // cannot happen (the neighbour is within R of s); table guard
+        double d = dists[dx * n + dy];
+        if (d > R) continue;
+        if (d < b.d) { b.d = d; b.src = s; }
+      }
+      return b;
+    };
+    for (;;) {
+      for (unsigned index : popped) {
+        int x = index % size_x, y = index / size_x;
+        push_frontier(x - 1, y); push_frontier(x, y - 1); push_frontier(x + 1, y); push_frontier(x, y + 1);
+      }
+      popped.clear();
+      double kmin = 1e300;
+      for (unsigned idx : frontier) kmin = std::min(kmin, best_entry(idx).d);
+      if (kmin == 1e300) break;
+      ++last_rounds;
+      next.clear();
+      std::vector<std::pair<unsigned, int32_t>> fin;
+      for (unsigned idx : frontier) {
+        Best b = best_entry(idx);
+        if (b.d == kmin) fin.emplace_back(idx, b.src);
+        else next.push_back(idx);
+      }
+      for (auto& f : fin) {
+        owner[f.first] = f.second;
+        in_frontier[f.first] = 0;
+        popped.push_back(f.first);
+        unsigned dx = abs(int(f.first % size_x) - int(f.second % size_x));
+        unsigned dy = abs(int(f.first / size_x) - int(f.second / size_x));
+        write_cell(m, f.first, costs[dx * n + dy]);
+      }
+      frontier.swap(next);
+    }
+    if (owner_out) owner_out->swap(owner);
   }
 };
 
@@ -1582,6 +1765,16 @@ void navo_obstacle_set_observations(void* h, int layer, const navo_observation* 
 void navo_inflation_set_params(void* h, int layer, double inflation_radius, double cost_scaling_factor) {
   Costmap* cm = static_cast<Costmap*>(h);
   static_cast<InflationLayer*>(cm->layers[layer].get())->set_params(*cm, inflation_radius, cost_scaling_factor);
+}
+int navo_inflation_set_variant(void* h, int layer, int variant, uint64_t seed) {
+  if (variant < 0 || variant > 6) return -1;
+  InflationLayer* il = static_cast<InflationLayer*>(static_cast<Costmap*>(h)->layers[layer].get());
+  il->variant = variant;
+  il->variant_seed = seed;
+  return 0;
+}
+int navo_inflation_last_rounds(void* h, int layer) {
+  return static_cast<InflationLayer*>(static_cast<Costmap*>(h)->layers[layer].get())->last_rounds;
 }
 void navo_costmap_update_map(void* h, double rx, double ry, double ryaw, int32_t w[4]) {
   Costmap* cm = static_cast<Costmap*>(h);

@@ -66,6 +66,19 @@ void navo_layer_set_enabled(void* h, int layer, int enabled);
 /* observations persist until replaced (ObstacleLayer::addStaticObservation, obstacle_layer.cpp:450-464) */
 void navo_obstacle_set_observations(void* h, int layer, const navo_observation* obs, int n_obs);
 void navo_inflation_set_params(void* h, int layer, double inflation_radius, double cost_scaling_factor);
+/* Checker-only: which legal execution of InflationLayer::updateCosts (inflation_layer.cpp:226-265) the checker runs.
+ * The reference pops equal-distance queue entries in whatever order libstdc++'s heap history produces; on diagonal or
+ * point-like obstacle boundaries the result depends on that order.  variant: 0 = the reference as written
+ * (std::priority_queue, same push order: reproduces the compiled reference bit for bit), 1 = oldest entry first
+ * (FIFO), 2 = newest first (LIFO), 3 = seeded pseudo-random order, 4 = exact windowed nearest-seed inflation (the
+ * specification of libnavgpu's inflation mode 0; not a propagation), 5 = level-synchronous propagation (the
+ * specification of libnavgpu's inflation mode 1; a legal execution), 6 = the certificate of that: the reference's
+ * sequential priority-queue loop with equal-distance ties resolved towards variant 5's sources, which must reproduce
+ * variant 5 bit for bit.  Cells that differ between variants 0-3 form the
+ * "tie-variant mask" of a scenario.  Returns 0, or -1 when the library cannot run the variant (libnavref.so: only 0). */
+int navo_inflation_set_variant(void* h, int layer, int variant, uint64_t seed);
+/* rounds (distinct pop levels, incl. repeats after a shorter entry appears) of variant 5's last updateCosts */
+int navo_inflation_last_rounds(void* h, int layer);
 /* LayeredCostmap::updateMap; window_out = {x0, xn, y0, yn} (bx0_, bxn_, by0_, byn_) */
 void navo_costmap_update_map(void* h, double robot_x, double robot_y, double robot_yaw, int32_t window_out[4]);
 void navo_costmap_get(void* h, uint8_t* out);

@@ -93,6 +93,8 @@ def _declare(lib, prefix):
         "layer_set_enabled": (None, [vp, i, i]),
         "obstacle_set_observations": (None, [vp, i, C.POINTER(Observation), i]),
         "inflation_set_params": (None, [vp, i, d, d]),
+        "inflation_set_variant": (i, [vp, i, i, C.c_uint64]),
+        "inflation_last_rounds": (i, [vp, i]),
         "costmap_update_map": (None, [vp, d, d, d, _i32p]),
         "costmap_get": (None, [vp, _u8p]),
         "costmap_set": (None, [vp, _u8p]),
@@ -227,6 +229,14 @@ class Costmap:
 
     def set_inflation_params(self, layer, inflation_radius, cost_scaling_factor):
         self.lib.navo_inflation_set_params(self.h, layer, inflation_radius, cost_scaling_factor)
+
+    def set_inflation_variant(self, layer, variant, seed=0):
+        """0 reference heap order, 1 FIFO, 2 LIFO, 3 seeded random, 4 exact nearest-seed, 5 level-synchronous"""
+        if self.lib.navo_inflation_set_variant(self.h, layer, variant, seed) != 0:
+            raise ValueError(f"inflation variant {variant} is not available in this checker")
+
+    def inflation_last_rounds(self, layer):
+        return int(self.lib.navo_inflation_last_rounds(self.h, layer))
 
     def update_map(self, x=0.0, y=0.0, yaw=0.0):
         w = np.zeros(4, dtype=np.int32)

@@ -544,6 +544,9 @@ void navo_inflation_set_params(void* hv, int layer, double inflation_radius, dou
   static_cast<costmap_2d::InflationLayer*>(static_cast<CostmapHandle*>(hv)->layers[layer])
       ->setInflationParameters(inflation_radius, cost_scaling_factor);
 }
+// the compiled reference has exactly one behaviour: libstdc++'s heap order (variant 0)
+int navo_inflation_set_variant(void*, int, int variant, uint64_t) { return variant == 0 ? 0 : -1; }
+int navo_inflation_last_rounds(void*, int) { return 0; }
 void navo_costmap_update_map(void* hv, double rx, double ry, double ryaw, int32_t w[4]) {
   CostmapHandle* h = static_cast<CostmapHandle*>(hv);
   h->lc->updateMap(rx, ry, ryaw);

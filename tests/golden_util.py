@@ -48,18 +48,26 @@ def load_tp_case(path):
     return out
 
 
-def check_costmap_case(api, tie_free, seed, path, exact=True):
-    """Returns the number of mismatching master cells over all cycles (0 = bit-exact); asserts windows/layers."""
+def check_costmap_case(api, tie_free, seed, path, exact=None, inflation=None, masks=None, one_sided=None):
+    """Runs the scenario of a golden fixture and compares it with the compiled reference's recorded output: windows,
+    origins and obstacle layer grids always ==; the master grid == everywhere (default), == outside the per-cycle
+    `masks` (a scenario's tie-variant mask), or cell by cell through `one_sided(got, reference)`.  Returns the number
+    of differing master cells."""
     g = np.load(path)
-    tr = sc.run_costmap_scenario(api, seed, tie_free=tie_free)
+    tr = sc.run_costmap_scenario(api, seed, tie_free=tie_free, inflation=inflation)
     bad = 0
     for c, (w, m, o, org) in enumerate(tr):
         assert tuple(g[f"w{c}"]) == tuple(w), f"window differs in cycle {c}"
         assert tuple(g[f"org{c}"]) == tuple(org), f"origin differs in cycle {c}"
         assert np.array_equal(g[f"o{c}"], o), f"obstacle layer grid differs in cycle {c}"
-        bad += int((g[f"m{c}"] != m).sum())
-    if exact:
-        assert bad == 0, f"{bad} master cells differ from the reference"
+        diff = g[f"m{c}"] != m
+        bad += int(diff.sum())
+        if masks is not None:
+            assert not (diff & ~masks[c]).any(), f"cycle {c}: {int((diff & ~masks[c]).sum())} cells differ outside the mask"
+        elif one_sided is not None:
+            assert one_sided(m, g[f"m{c}"]), f"cycle {c}: a cell is lower than the reference"
+        else:
+            assert not diff.any(), f"cycle {c}: {int(diff.sum())} master cells differ from the reference"
     return bad
 
 

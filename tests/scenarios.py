@@ -100,8 +100,33 @@ def dwa_scenario(rng, n=120, res=0.05, style=None):
     return dict(style=style, origin=(ox, oy), pose=pose, vel=vel, plan=np.stack([px, py], 1))
 
 
-def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False):
+INFLATION_SEMANTICS = {
+    # name: (checker variant of navo_inflation_set_variant, libnavgpu mode of navgpu_inflation_set_mode)
+    "reference": (0, None),   # libstdc++ heap order, the reference as compiled (checker only)
+    "fifo": (1, None), "lifo": (2, None), "random": (3, None),
+    "exact": (4, 0),          # exact windowed nearest-seed inflation
+    "propagate": (5, 1),      # level-synchronous nearest-source propagation
+    "certificate": (6, None),
+}
+# the sampled tie policies whose disagreement with the reference defines a scenario's tie-variant mask
+TIE_POLICIES = [("fifo", 0), ("lifo", 0)] + [("random", s) for s in range(1, 17)]
+
+
+def select_inflation(cm, layer, which, seed=0):
+    """Pick the inflation semantics on a checker costmap (variant) or a CUDA costmap (mode)."""
+    if which is None:
+        return
+    variant, mode = INFLATION_SEMANTICS[which]
+    if hasattr(cm, "set_inflation_variant"):
+        cm.set_inflation_variant(layer, variant, seed)
+    else:
+        assert mode is not None, f"libnavgpu has no inflation mode for '{which}'"
+        cm.set_inflation_mode(layer, mode)
+
+
+def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False, inflation=None, inflation_seed=0):
     """Multi-cycle LayeredCostmap scenario; returns per cycle (window, master, obstacle-layer grid, origin).
+    `inflation` (a key of INFLATION_SEMANTICS) selects which execution of InflationLayer::updateCosts runs.
 
     `api` is anything shaped like oracle.pyoracle.Api (the oracles and the CUDA binding all are).
     tie_free=True restricts obstacle sources to thick axis-aligned blocks (no marking of single points), the class on
@@ -119,6 +144,7 @@ def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False):
     scaling = float(rng.choice([1.0, 10.0]))
     cm, ids = build_stack(api, rng, sx, sy, res, ox, oy, rolling, tu, kind, radius=radius, scaling=scaling,
                           extra_policy=extra)
+    select_inflation(cm, ids["inflation"], inflation, inflation_seed)
     trace = []
     rx, ry = ox + sx * res / 2, oy + sy * res / 2
     for cyc in range(cycles):
@@ -136,6 +162,18 @@ def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False):
         w = cm.update_map(rx, ry, float(rng.uniform(-3, 3)))
         trace.append((w, cm.get().copy(), cm.get_layer(ids["obstacle"]).copy(), cm.origin()))
     return trace
+
+
+def tie_mask_trace(port, seed, **kw):
+    """Per cycle: the cells of the master grid on which some sampled tie policy of the reference's priority queue
+    (TIE_POLICIES, each a full run of the scenario) disagrees with the reference's own heap order."""
+    base = run_costmap_scenario(port, seed, inflation="reference", **kw)
+    masks = [np.zeros_like(c[1], bool) for c in base]
+    for which, s in TIE_POLICIES:
+        tr = run_costmap_scenario(port, seed, inflation=which, inflation_seed=s, **kw)
+        for m, a, b in zip(masks, tr, base):
+            m |= a[1] != b[1]
+    return base, masks
 
 
 def run_dwa_scenario(api, grid_api, seed, cycles=5):
@@ -187,7 +225,7 @@ def dwa_results_equal(a, b, rtol=0.0):
     return bool(ok)
 
 
-def run_voxel_scenario(api, seed, cycles=4, max_size=70):
+def run_voxel_scenario(api, seed, cycles=4, max_size=70, inflation=None):
     """Multi-cycle LayeredCostmap scenario with a VoxelLayer (3-D ray-trace clearing + marking) [+ inflation];
     returns per cycle (window, master, voxel layer's 2-D grid, voxel columns, origin).  mark_threshold stays 0 (the
     reference's default): with a positive threshold the reference's bounds depend on the order of the cloud points."""
@@ -211,6 +249,7 @@ def run_voxel_scenario(api, seed, cycles=4, max_size=70):
     with_inflation = bool(rng.random() < 0.5)
     if with_inflation:
         ids["inflation"] = cm.add_inflation_layer(0.3, 10.0)
+        select_inflation(cm, ids["inflation"], inflation)
     cm.set_footprint(square_footprint())
     trace = []
     rx, ry = ox + sx * res / 2, oy + sy * res / 2
