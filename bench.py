@@ -299,15 +299,16 @@ def run_native_dwa(api, torch, dist, rank, world, local_rank, steps):
     d4, pose, vel = dwa_setup(api, grid, C4, device=local_rank)
     stream = torch.cuda.ExternalStream(d4.stream(), device=local_rank)
     from navigation_b200 import sharding
-    c, i, total = d4.score_range(pose, vel, PENTAGON, 0, 1)
-    lo, hi = sharding.split_range(total, rank, world)
+    if dist is None:
+        def one_sweep():
+            return d4.find_best_path(pose, vel, PENTAGON, want_costs=False)
+    else:
+        # one-off: the ranks exchange the CUDA IPC handles of their 1 KB exchange buffers; from then on a sweep is one
+        # call per rank and the scoring kernels trade their (cost, index) minima over NVLink themselves
+        sharding.connect_shards(dist, d4)
 
-    def one_sweep():
-        c, i, _ = d4.score_range(pose, vel, PENTAGON, lo, hi)
-        if dist is None:
-            return d4.finish_sharded(pose, [c], [i])
-        costs, indices = sharding.allgather_minima(dist, torch, c, i, dev)  # NCCL, 16 bytes per rank
-        return d4.finish_sharded(pose, costs, indices)
+        def one_sweep():
+            return d4.find_best_path_sharded(pose, vel, PENTAGON)
 
     for _ in range(3):
         r4 = one_sweep()
@@ -328,10 +329,12 @@ def run_native_dwa(api, torch, dist, rank, world, local_rank, steps):
         t = torch.tensor([sweep_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sweep_s = float(t.item())
+    total = int(r4["n_samples"])
     out.update({"c4_samples": int(total), "c4_sweep_ms": 1e3 * sweep_s, "c4_traj_per_s": total / sweep_s,
                 "c4_best_index": int(r4["best_index"]), "c4_best_cost": float(r4["cost"]),
-                "c4_sharding": f"sample range split over {world} rank(s), all_gather of (cost, index)" if world > 1
-                else "single GPU"})
+                "c4_sharding": (f"8-sample blocks dealt round-robin over {world} ranks; (cost, index) minima exchanged "
+                                "by the scoring kernels' last CTAs through peer-mapped buffers (no host step, no "
+                                "collective call)") if world > 1 else "single GPU"})
     return out
 
 

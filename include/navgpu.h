@@ -256,6 +256,36 @@ int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel
  * as simple_scored_sampling_planner.cpp:111-116 would, regenerate its trajectory and update the oscillation flags */
 int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double* costs, const int64_t* indices,
                               int n_ranks, navgpu_dwa_result* result, double* best_points, int points_capacity);
+/* The same with the samples dealt out block-cyclically instead of in contiguous ranges: rank r of `world` scores the
+ * 8-sample blocks r, r + world, r + 2 world, ... of the enumeration.  Trajectory length grows with the outer (vx)
+ * index, so contiguous ranges leave the last rank with 1.6x the mean work at 8 ranks; block-cyclic shares are even.
+ * The (cost, lowest index) winner does not depend on the partition (simple_scored_sampling_planner.cpp:111-116). */
+int navgpu_dwa_score_strided(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                             int n_footprint, int rank, int world, double* best_cost, int64_t* best_index,
+                             int64_t* n_samples_total);
+
+/* ---- multi-GPU sweep with the exchange on the device ----------------------------------
+ * One planner handle per GPU (one process per GPU, or one process driving several).  Every rank scores its
+ * block-cyclic share; the LAST CTA of its scoring kernel stores the rank's 16-byte (cost, index) minimum straight into
+ * every peer's exchange buffer (peer-mapped device memory: the stores cross NVLink / NVSwitch), waits until all `world`
+ * records of the sweep have arrived in its own buffer, picks the reference's winner and regenerates its trajectory --
+ * all inside the one kernel launch.  No host round trip and no collective-library call between scoring and result;
+ * every rank ends with the identical result and oscillation state.
+ * Setup, once: each rank exports its buffer (a cudaIpcMemHandle_t, 64 bytes), the ranks exchange the handles by any
+ * means (MPI, a socket, a file), each rank connects.  In one process: navgpu_dwa_shard_connect_local. */
+#define NAVGPU_IPC_HANDLE_BYTES 64
+int navgpu_dwa_shard_export(navgpu_dwa* h, void* ipc_handle_out /* NAVGPU_IPC_HANDLE_BYTES */);
+int navgpu_dwa_shard_connect(navgpu_dwa* h, int rank, int world, const void* ipc_handles /* world x 64 bytes, rank order */);
+int navgpu_dwa_shard_connect_local(navgpu_dwa* const* handles, int world); /* handles[r] becomes rank r */
+/* DWAPlanner::findBestPath over all ranks; every rank must call it once per cycle with the same inputs (costmap, plan,
+ * pose, velocity, footprint).  A rank whose peers do not answer within two seconds returns cost -7 (nothing valid). */
+int navgpu_dwa_find_best_path_sharded(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                                      int n_footprint, navgpu_dwa_result* result, double* best_points, int points_capacity);
+/* the same split into enqueue and wait, for one host thread that drives several ranks' handles */
+int navgpu_dwa_find_best_path_sharded_async(navgpu_dwa* h, const double pose[3], const double vel[3],
+                                            const double* footprint_xy, int n_footprint);
+int navgpu_dwa_sharded_collect(navgpu_dwa* h, const double pose[3], navgpu_dwa_result* result, double* best_points,
+                               int points_capacity);
 /* the four MapGrid distance fields after prepare(): which = 0 path, 1 goal, 2 goal_front, 3 alignment (fp64, host) */
 int navgpu_dwa_get_grid(navgpu_dwa* h, int which, double* host_out);
 /* enqueue one full scoring cycle without host synchronisation (timing) */

@@ -146,6 +146,15 @@ SIGNATURES = {
                                          _i64p]),
     "navgpu_dwa_finish_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _i64p, C.c_int, C.POINTER(DwaResult), _f64p,
                                             C.c_int]),
+    "navgpu_dwa_score_strided": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "navgpu_dwa_shard_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "navgpu_dwa_shard_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "navgpu_dwa_shard_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "navgpu_dwa_find_best_path_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.POINTER(DwaResult),
+                                                    _f64p, C.c_int]),
+    "navgpu_dwa_find_best_path_sharded_async": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int]),
+    "navgpu_dwa_sharded_collect": (C.c_int, [C.c_void_p, _f64p, C.POINTER(DwaResult), _f64p, C.c_int]),
     "navgpu_dwa_get_grid": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
     "navgpu_dwa_find_best_path_async": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int]),
     "navgpu_dwa_synchronize": (C.c_int, [C.c_void_p]),
@@ -485,6 +494,48 @@ class Dwa:
                                                        begin, end, C.byref(cost), C.byref(idx), C.byref(total)))
         return cost.value, idx.value, total.value
 
+    def score_strided(self, pose, vel, footprint_xy, rank, world):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        cost, idx, total = C.c_double(), C.c_int64(), C.c_int64()
+        self.api.check(self.lib.navgpu_dwa_score_strided(self.h, _p(p, _f64p), _p(v, _f64p), _p(f, _f64p), f.shape[0],
+                                                         rank, world, C.byref(cost), C.byref(idx), C.byref(total)))
+        return cost.value, idx.value, total.value
+
+    def shard_export(self):
+        """This rank's exchange buffer as a 64-byte CUDA IPC handle (bytes)."""
+        buf = (C.c_ubyte * 64)()
+        self.api.check(self.lib.navgpu_dwa_shard_export(self.h, buf))
+        return bytes(buf)
+
+    def shard_connect(self, rank, world, handles):
+        """handles: the `world` exported handles in rank order (bytes each)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self.api.check(self.lib.navgpu_dwa_shard_connect(self.h, rank, world, buf))
+
+    def find_best_path_sharded_async(self, pose, vel, footprint_xy):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        self.api.check(self.lib.navgpu_dwa_find_best_path_sharded_async(self.h, _p(p, _f64p), _p(v, _f64p), _p(f, _f64p),
+                                                                        f.shape[0]))
+
+    def sharded_collect(self, pose, max_points=4096):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        res = DwaResult()
+        pts = np.zeros((max_points, 3))
+        self.api.check(self.lib.navgpu_dwa_sharded_collect(self.h, _p(p, _f64p), C.byref(res), _p(pts, _f64p), max_points))
+        return dict(ok=res.cost >= 0, cost=res.cost, xv=res.xv, yv=res.yv, thetav=res.thetav,
+                    best_index=res.best_index, n_samples=res.n_samples, n_scored=res.n_scored,
+                    points=pts[:res.n_points].copy())
+
+    def find_best_path_sharded(self, pose, vel, footprint_xy, max_points=4096):
+        self.find_best_path_sharded_async(pose, vel, footprint_xy)
+        return self.sharded_collect(pose, max_points)
+
     def finish_sharded(self, pose, costs, indices, max_points=4096):
         p = np.ascontiguousarray(pose, dtype=np.float64)
         c = np.ascontiguousarray(costs, dtype=np.float64)
@@ -667,6 +718,11 @@ class Api:
 
     def dwa(self, *a, **k):
         return Dwa(self, *a, **k)
+
+    def shard_connect_local(self, dwas):
+        """One process driving several planner handles (one per GPU, or several on one GPU): dwas[r] becomes rank r."""
+        arr = (C.c_void_p * len(dwas))(*[d.h for d in dwas])
+        self.check(self.lib.navgpu_dwa_shard_connect_local(arr, len(dwas)))
 
     def fleet(self, *a, **k):
         return Fleet(self, *a, **k)

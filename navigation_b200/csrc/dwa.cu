@@ -180,6 +180,14 @@ struct navgpu_dwa {
   long long n_samples_last = 0;
   bool have_last = false;
   Cycle last;  // arguments of the last score_range launch (for finish_sharded)
+  // sharded sweeps with the device-side exchange (navgpu_dwa_shard_*)
+  ShardExchange* d_shard = nullptr;                 // this rank's exchange buffer
+  ShardExchange* shard_peer[kShardMaxWorld] = {};   // every rank's buffer as mapped here
+  bool shard_ipc[kShardMaxWorld] = {};              // opened with cudaIpcOpenMemHandle (to be closed)
+  int shard_rank = 0, shard_world = 0;
+  unsigned long long shard_seq = 0;
+  Cycle shard_cycle;
+  bool shard_pending = false;
 };
 
 namespace {
@@ -353,6 +361,10 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
   cy.n_samples = (long long)s.nx * s.ny * s.nth;
   a.begin = 0;
   a.end = cy.n_samples;
+  a.stride_rank = 0;
+  a.stride_world = 1;
+  for (int k = 0; k < kShardMaxWorld; ++k) a.shard_peer[k] = nullptr;
+  a.shard_seq = 0;
   for (int k = 0; k < 3; ++k) { a.pos[k] = pos[k]; a.vel[k] = vel[k]; }
   a.acc[0] = (float)c.acc_lim_x; a.acc[1] = (float)c.acc_lim_y; a.acc[2] = (float)c.acc_lim_theta;
   a.min_trans_vel = c.min_trans_vel; a.max_trans_vel = c.max_trans_vel; a.min_rot_vel = c.min_rot_vel;
@@ -382,7 +394,9 @@ int launch_score(navgpu_dwa* h, Cycle& cy, bool finish) {
   DwaScoreArgs& a = cy.args;
   const long long n = a.end - a.begin;
   if (n <= 0) return fail(NAVGPU_ERR_INVALID, "empty sample range");
-  const long long blocks = (n + kDwaWarpsPerBlock - 1) / kDwaWarpsPerBlock;
+  const long long all_blocks = (n + kDwaWarpsPerBlock - 1) / kDwaWarpsPerBlock;
+  // block-cyclic share of this rank (every rank launches at least one CTA so that its exchange step runs)
+  const long long blocks = std::max<long long>(1, (all_blocks - a.stride_rank + a.stride_world - 1) / a.stride_world);
   if (blocks > 0x7fffffffLL) return fail(NAVGPU_ERR_UNSUPPORTED, "too many samples in one launch");
   if ((size_t)blocks > h->block_capacity) {
     if (h->d_block_cost) cudaFree(h->d_block_cost);
@@ -464,6 +478,9 @@ int navgpu_dwa_destroy(navgpu_dwa* h) {
   cudaFree(h->d_samples); cudaFree(h->d_block_cost); cudaFree(h->d_block_index); cudaFree(h->d_counters);
   cudaFree(h->d_best_cost); cudaFree(h->d_best_index);
   cudaFree(h->d_terms); cudaFree(h->d_reported);
+  for (int r = 0; r < kShardMaxWorld; ++r)
+    if (h->shard_ipc[r] && h->shard_peer[r]) cudaIpcCloseMemHandle(h->shard_peer[r]);
+  cudaFree(h->d_shard);
   cudaFreeHost(h->h_result); cudaFreeHost(h->h_points); cudaFreeHost(h->h_best);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -680,6 +697,8 @@ int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double*
     }
   Cycle cy = h->last;
   if (bi < 0) {  // nothing valid anywhere: result_traj_.cost_ = -7, flags untouched
+    // the generated-samples counter is normally read and cleared by the finishing kernel, which does not run here
+    NAVGPU_CUDA(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned int), h->stream));
     if (result) {
       result->cost = -7.0;
       result->xv = h->res_xv; result->yv = h->res_yv; result->thetav = h->res_thv;
@@ -693,6 +712,142 @@ int navgpu_dwa_finish_sharded(navgpu_dwa* h, const double pose[3], const double*
   k_dwa_finish<<<1, 32, 0, h->stream>>>(cy.args, bi, bc, h->h_result, h->h_points, kPointsCapacity);
   NAVGPU_LAUNCHED(1);
   return collect(h, cy, pose, result, best_points, points_capacity);
+}
+
+int navgpu_dwa_score_strided(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                             int n_footprint, int rank, int world, double* best_cost, int64_t* best_index,
+                             int64_t* n_samples_total) {
+  if (!h || !pose || !vel || !best_cost || !best_index || world < 1 || rank < 0 || rank >= world)
+    return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  Cycle cy;
+  NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy));
+  if (n_samples_total) *n_samples_total = cy.n_samples;
+  cy.args.stride_rank = rank;
+  cy.args.stride_world = world;
+  NAVGPU_TRY(launch_score(h, cy, false));
+  NAVGPU_CUDA(cudaGetLastError());
+  h->last = cy;
+  h->have_last = true;
+  NAVGPU_CUDA(cudaMemcpyAsync(&h->h_best[0], h->d_best_cost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(&h->h_best[1], h->d_best_index, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  *best_cost = h->h_best[0];
+  long long idx;
+  memcpy(&idx, &h->h_best[1], sizeof(idx));
+  *best_index = idx;
+  return NAVGPU_OK;
+}
+
+// ---- sharded sweep with the device-side exchange ------------------------------------------------------------------
+static int shard_alloc(navgpu_dwa* h) {
+  if (h->d_shard) return NAVGPU_OK;
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaMalloc(&h->d_shard, sizeof(ShardExchange)));
+  NAVGPU_CUDA(cudaMemset(h->d_shard, 0, sizeof(ShardExchange)));  // seq 0 = "no sweep yet"
+  return NAVGPU_OK;
+}
+
+static void shard_disconnect(navgpu_dwa* h) {
+  for (int r = 0; r < kShardMaxWorld; ++r) {
+    if (h->shard_ipc[r] && h->shard_peer[r]) cudaIpcCloseMemHandle(h->shard_peer[r]);
+    h->shard_peer[r] = nullptr;
+    h->shard_ipc[r] = false;
+  }
+  h->shard_world = 0;
+}
+
+int navgpu_dwa_shard_export(navgpu_dwa* h, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == NAVGPU_IPC_HANDLE_BYTES, "IPC handle size");
+  NAVGPU_TRY(shard_alloc(h));
+  cudaIpcMemHandle_t mh;
+  NAVGPU_CUDA(cudaIpcGetMemHandle(&mh, h->d_shard));
+  memcpy(ipc_handle_out, &mh, sizeof(mh));
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_shard_connect(navgpu_dwa* h, int rank, int world, const void* ipc_handles) {
+  if (!h || !ipc_handles || world < 1 || world > kShardMaxWorld || rank < 0 || rank >= world)
+    return fail(NAVGPU_ERR_INVALID, "bad arguments (world <= %d)", kShardMaxWorld);
+  NAVGPU_TRY(shard_alloc(h));
+  shard_disconnect(h);
+  const char* base = static_cast<const char*>(ipc_handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->shard_peer[r] = h->d_shard;
+      continue;
+    }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, base + size_t(r) * NAVGPU_IPC_HANDLE_BYTES, sizeof(mh));
+    void* p = nullptr;
+    NAVGPU_CUDA(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->shard_peer[r] = static_cast<ShardExchange*>(p);
+    h->shard_ipc[r] = true;
+  }
+  h->shard_rank = rank;
+  h->shard_world = world;
+  h->shard_seq = 0;
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_shard_connect_local(navgpu_dwa* const* handles, int world) {
+  if (!handles || world < 1 || world > kShardMaxWorld) return fail(NAVGPU_ERR_INVALID, "bad arguments (world <= %d)", kShardMaxWorld);
+  for (int r = 0; r < world; ++r) {
+    if (!handles[r]) return fail(NAVGPU_ERR_INVALID, "null handle");
+    NAVGPU_TRY(shard_alloc(handles[r]));
+  }
+  for (int r = 0; r < world; ++r) {
+    navgpu_dwa* h = handles[r];
+    NAVGPU_TRY(use_device(h));
+    shard_disconnect(h);
+    for (int q = 0; q < world; ++q) {
+      if (handles[q]->device != h->device) {
+        int can = 0;
+        NAVGPU_CUDA(cudaDeviceCanAccessPeer(&can, h->device, handles[q]->device));
+        if (!can) return fail(NAVGPU_ERR_UNSUPPORTED, "device %d cannot access device %d", h->device, handles[q]->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(handles[q]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) NAVGPU_CUDA(e);
+        (void)cudaGetLastError();
+      }
+      h->shard_peer[q] = handles[q]->d_shard;
+    }
+    h->shard_rank = r;
+    h->shard_world = world;
+    h->shard_seq = 0;
+  }
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_find_best_path_sharded_async(navgpu_dwa* h, const double pose[3], const double vel[3],
+                                            const double* footprint_xy, int n_footprint) {
+  if (!h || !pose || !vel || (n_footprint > 0 && !footprint_xy)) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (h->shard_world < 1) return fail(NAVGPU_ERR_INVALID, "navgpu_dwa_shard_connect must run first");
+  Cycle cy;
+  NAVGPU_TRY(begin_cycle(h, pose, vel, footprint_xy, n_footprint, cy));
+  cy.args.stride_rank = h->shard_rank;
+  cy.args.stride_world = h->shard_world;
+  for (int r = 0; r < h->shard_world; ++r) cy.args.shard_peer[r] = h->shard_peer[r];
+  cy.args.shard_seq = ++h->shard_seq;
+  NAVGPU_TRY(launch_score(h, cy, true));
+  NAVGPU_CUDA(cudaGetLastError());
+  h->shard_cycle = cy;
+  h->shard_pending = true;
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_sharded_collect(navgpu_dwa* h, const double pose[3], navgpu_dwa_result* result, double* best_points,
+                               int points_capacity) {
+  if (!h || !pose) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (!h->shard_pending) return fail(NAVGPU_ERR_INVALID, "no sharded sweep in flight");
+  NAVGPU_TRY(use_device(h));
+  h->shard_pending = false;
+  return collect(h, h->shard_cycle, pose, result, best_points, points_capacity);
+}
+
+int navgpu_dwa_find_best_path_sharded(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
+                                      int n_footprint, navgpu_dwa_result* result, double* best_points, int points_capacity) {
+  NAVGPU_TRY(navgpu_dwa_find_best_path_sharded_async(h, pose, vel, footprint_xy, n_footprint));
+  return navgpu_dwa_sharded_collect(h, pose, result, best_points, points_capacity);
 }
 
 int navgpu_dwa_get_grid(navgpu_dwa* h, int which, double* host_out) {

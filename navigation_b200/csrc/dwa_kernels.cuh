@@ -452,6 +452,22 @@ struct DwaDeviceResult {
   int n_points, n_scored;
 };
 
+// Multi-GPU sample sweep (config C4): one record per rank and sweep parity in every rank's exchange buffer.  The last
+// CTA of a rank's scoring kernel stores its record into EVERY rank's buffer (peer-mapped device memory: the stores
+// travel over NVLink), then publishes `seq`; whoever finds all `world` records of the current sweep in its own buffer
+// picks the winner.  No host round trip, no collective library call on the path.
+constexpr int kShardMaxWorld = 16;
+struct ShardSlot {
+  double cost;          // the rank's minimum, +inf when it has no valid sample
+  long long index;      // its global sample index, -1 when none
+  unsigned long long seq;  // sweep number this record belongs to (written last, after a system-wide fence)
+  unsigned generated;   // samples the generator accepted on that rank
+  unsigned pad_;
+};
+struct ShardExchange {
+  ShardSlot slot[2][kShardMaxWorld];  // [sweep parity][source rank]
+};
+
 struct DwaScoreArgs {
   DwaGeom g;
   const uint32_t* dist[4];  // 0 path, 1 goal, 2 goal_front, 3 alignment
@@ -462,6 +478,10 @@ struct DwaScoreArgs {
   int inline_samples;  // 1: the samples travel in samples_inline (xs | ys | ths), no upload
   float samples_inline[kInlineSamples];
   long long begin, end;  // sample index range scored by this launch
+  // block-cyclic sharding of that range: CTA b scores the 8-sample block b * stride_world + stride_rank (1 rank: all)
+  int stride_rank, stride_world;
+  ShardExchange* shard_peer[kShardMaxWorld];  // every rank's exchange buffer as mapped on this device; null: no exchange
+  unsigned long long shard_seq;
   float pos[3], vel[3], acc[3];
   double min_trans_vel, max_trans_vel, min_rot_vel;
   double sim_time, sim_granularity, angular_sim_granularity;
@@ -727,7 +747,8 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
     obst_sum += ssum;
     obst_last = __shfl_sync(0xffffffffu, occ, cnt - 1);
     __syncwarp();
-    // ---- the four map-grid critics on my point
+    // ---- the four map-grid critics on my point (the grids come from the kernel launched before this one)
+    cudaGridDependencySynchronize();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const bool shifted = k >= 2;        // goal_front, alignment use xshift (dwa_planner.cpp:80-81)
@@ -835,6 +856,69 @@ __device__ __forceinline__ bool better(double c1, long long i1, double c2, long 
   return c1 < c2 || (c1 == c2 && i1 < i2);
 }
 
+// The exchange step of a sharded sweep, run by warp 0 of the last CTA of every rank's k_dwa_score.  Lane r < world
+// delivers this rank's record to rank r's buffer (a peer-mapped address: the store crosses NVLink), a system-wide fence
+// orders it before the sequence number; then lane r waits for rank r's record of this sweep in the LOCAL buffer.  The
+// winner is the reference's: smallest cost, lowest sample index on equal cost (simple_scored_sampling_planner.cpp:111-116
+// keeps the first strictly smaller one), whatever the partition.  A peer that never answers (its process died) ends
+// the wait after two seconds with "nothing valid" rather than hanging the GPU.
+__device__ __noinline__ void shard_exchange(ShardExchange* peer_of_lane, ShardExchange* mine, int world, int me,
+                                            unsigned long long seq, unsigned* counters, double* cost_io, long long* index_io) {
+  const int lane = threadIdx.x & 31;
+  const int parity = (int)(seq & 1ull);
+  const unsigned generated = counters[1];
+  const double cost = *cost_io;
+  const long long index = *index_io;
+  if (lane < world) {
+    ShardSlot* out = &peer_of_lane->slot[parity][me];
+    out->cost = cost;
+    out->index = index;
+    out->generated = generated;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&out->seq) = seq;
+  }
+  double c = INFINITY;
+  long long ix = -1;
+  unsigned gen = 0;
+  if (lane < world) {
+    const ShardSlot* in = &mine->slot[parity][lane];
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    bool arrived = true;
+    while (*reinterpret_cast<const volatile unsigned long long*>(&in->seq) != seq) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) {
+        arrived = false;
+        break;
+      }
+    }
+    __threadfence_system();
+    if (arrived) {
+      c = *reinterpret_cast<const volatile double*>(&in->cost);
+      ix = *reinterpret_cast<const volatile long long*>(&in->index);
+      gen = *reinterpret_cast<const volatile unsigned*>(&in->generated);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, c, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, ix, o);
+    gen += __shfl_xor_sync(0xffffffffu, gen, o);
+    if (oi >= 0 && (ix < 0 || better(oc, oi, c, ix))) {
+      c = oc;
+      ix = oi;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    *cost_io = c;
+    *index_io = ix;
+    counters[1] = gen;  // n_scored of the whole sweep (finish_winner reports and clears it)
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_dwa_score(DwaScoreArgs a) {
   __shared__ double s_cost[kDwaWarpsPerBlock];
   __shared__ long long s_index[kDwaWarpsPerBlock];
@@ -842,8 +926,10 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_dwa_score(DwaScor
   __shared__ bool s_last;
   __shared__ double s_scratch[kDwaWarpsPerBlock][kWarpScratchDoubles];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long sample = a.begin + (long long)blockIdx.x * kDwaWarpsPerBlock + warp;
-  cudaGridDependencySynchronize();  // launched with programmatic stream serialization behind the MapGrid kernel
+  const long long sample = a.begin + ((long long)blockIdx.x * a.stride_world + a.stride_rank) * kDwaWarpsPerBlock + warp;
+  // Launched with programmatic stream serialization behind the MapGrid kernel, which runs on four SMs for tens of
+  // microseconds: the rollout and the footprint walks (costmap only) start right away, and score_sample waits for the
+  // distance grids (cudaGridDependencySynchronize) just before its first look-up.
   double cost = INFINITY;
   long long index = -1;
   int generated = 0;
@@ -925,8 +1011,11 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_dwa_score(DwaScor
   }
   if (a.finish_out == nullptr) return;
   __syncthreads();
-  if (warp == 0)
-    finish_winner(a, s_index[0], s_cost[0], a.finish_out, a.finish_points, a.finish_capacity, s_scratch[0], &a.counters[1]);
+  if (warp != 0) return;
+  if (a.shard_peer[0] != nullptr)  // multi-GPU sweep: the winner of all ranks
+    shard_exchange(lane < a.stride_world ? a.shard_peer[lane] : nullptr, a.shard_peer[a.stride_rank], a.stride_world,
+                   a.stride_rank, a.shard_seq, a.counters, &s_cost[0], &s_index[0]);
+  finish_winner(a, s_index[0], s_cost[0], a.finish_out, a.finish_points, a.finish_capacity, s_scratch[0], &a.counters[1]);
 }
 
 // DWAPlanner::checkTrajectory: one warp scores sample 0 of a one-sample argument block; a rejected sample leaves an

@@ -9,6 +9,40 @@
 """
 import numpy as np
 
+SAMPLE_BLOCK = 8  # samples per CTA of k_dwa_score: the unit the block-cyclic partition deals out
+
+
+def strided_indices(total, rank, world, block=SAMPLE_BLOCK):
+    """Global sample indices of `rank` under the block-cyclic partition of navgpu_dwa_score_strided /
+    navgpu_dwa_find_best_path_sharded: blocks rank, rank + world, rank + 2 world, ... of `block` samples each.
+    Trajectory length grows with the outer (vx) sample index, so contiguous ranges are unbalanced (the last of 8
+    ranks gets 1.6x the mean number of trajectory points); dealing blocks round-robin evens that out, and the
+    winner rule -- smallest cost, lowest index on ties -- does not depend on the partition."""
+    idx = np.arange(total, dtype=np.int64)
+    return idx[(idx // block) % world == rank]
+
+
+def local_minimum_strided(costs, rank, world, block=SAMPLE_BLOCK):
+    """(cost, global index) of the first strictly smallest valid cost among this rank's block-cyclic share."""
+    c = np.asarray(costs, dtype=np.float64)
+    mine = strided_indices(len(c), rank, world, block)
+    if mine.size == 0:
+        return float("inf"), -1
+    cost, pos = local_minimum(c[mine])
+    return cost, (int(mine[pos]) if pos >= 0 else -1)
+
+
+def connect_shards(dist, dwa):
+    """Device-side exchange setup for one planner handle per rank (one process per GPU): every rank exports its
+    exchange buffer as a CUDA IPC handle, the 64-byte handles travel once over torch.distributed, every rank maps its
+    peers' buffers.  After this the per-cycle data path has no collective call: the scoring kernels exchange their
+    16-byte minima themselves (navgpu_dwa_find_best_path_sharded)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    handles = [None] * world
+    dist.all_gather_object(handles, dwa.shard_export())
+    dwa.shard_connect(rank, world, handles)
+    dist.barrier()
+
 
 def split_range(total, rank, world):
     """Contiguous share [lo, hi) of `total` items for `rank` of `world`."""

@@ -169,3 +169,50 @@ def test_c4_full_sweep_vs_checker(cuda, port):
     same = np.sum((ra["costs"] == rb["costs"]) | (np.isnan(ra["costs"]) & np.isnan(rb["costs"])))
     assert same >= 0.9999 * ra["n_samples"], f"{ra['n_samples'] - same} costs differ in the last bits"
     assert np.array_equal(ra["points"], rb["points"])
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_block_cyclic_shards_give_the_sequential_winner(cuda, port, world):
+    """navgpu_dwa_score_strided: rank r scores the 8-sample blocks r, r + world, ...; the per-rank (cost, index) minima
+    fed to navgpu_dwa_finish_sharded select the very sample (and cost, points, oscillation mask) the unsharded search
+    selects -- on 40 401 samples, a count that is not a multiple of 8 x world."""
+    over = dict(vx_samples=200, vy_samples=1, vth_samples=200, acc_lim_x=20.0, acc_lim_theta=20.0)
+    whole, pose, vel = c2_setup(cuda, port, **over)
+    rw = whole.find_best_path(pose, vel, sc.PENTAGON)
+    d, _, _ = c2_setup(cuda, port, **over)
+    minima = [d.score_strided(pose, vel, sc.PENTAGON, r, world) for r in range(world)]
+    assert all(m[2] == rw["n_samples"] for m in minima)
+    # every rank's minimum comes from one of its own blocks, and exactly one rank holds the overall winner
+    assert all(i < 0 or (i // 8) % world == r for r, (c, i, _) in enumerate(minima))
+    assert sum(i == rw["best_index"] for _, i, _ in minima) == 1
+    rs = d.finish_sharded(pose, [m[0] for m in minima], [m[1] for m in minima])
+    assert rs["best_index"] == rw["best_index"] and rs["cost"] == rw["cost"]
+    assert (rs["xv"], rs["yv"], rs["thetav"]) == (rw["xv"], rw["yv"], rw["thetav"])
+    assert np.array_equal(rs["points"], rw["points"])
+    assert d.oscillation_mask() == whole.oscillation_mask()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_device_side_exchange_on_one_gpu(cuda, port, world):
+    """navgpu_dwa_find_best_path_sharded with `world` planner handles on ONE device (navgpu_dwa_shard_connect_local):
+    the last CTA of every rank's scoring kernel stores its record into every rank's exchange buffer and waits for the
+    others; all ranks return the unsharded search's winner, n_scored and trajectory, over three cycles (oscillation
+    state carried), without any host step between scoring and result."""
+    over = dict(vx_samples=60, vy_samples=3, vth_samples=60, acc_lim_x=20.0, acc_lim_y=20.0, acc_lim_theta=20.0)
+    whole, pose, vel = c2_setup(cuda, port, **over)
+    ranks = [c2_setup(cuda, port, **over)[0] for _ in range(world)]
+    cuda.shard_connect_local(ranks)
+    pose = np.array(pose)
+    vel = np.array(vel)
+    for cyc in range(3):
+        rw = whole.find_best_path(pose, vel, sc.PENTAGON, want_costs=False)
+        for d in ranks:
+            d.find_best_path_sharded_async(pose, vel, sc.PENTAGON)
+        outs = [d.sharded_collect(pose) for d in ranks]
+        for r, o in enumerate(outs):
+            assert o["best_index"] == rw["best_index"] and o["cost"] == rw["cost"], f"cycle {cyc} rank {r}"
+            assert o["n_samples"] == rw["n_samples"] and o["n_scored"] == rw["n_scored"]
+            assert np.array_equal(o["points"], rw["points"])
+        assert all(d.oscillation_mask() == whole.oscillation_mask() for d in ranks)
+        vel = np.array([rw["xv"] * (-1 if cyc % 2 else 1), rw["yv"], -rw["thetav"]])
+        pose = pose + np.array([0.01 * vel[0], 0, 0.01 * vel[2]])

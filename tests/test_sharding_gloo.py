@@ -25,12 +25,15 @@ def free_port():
     return p
 
 
-def worker(rank, world, port, costs, expect, out):
+def worker(rank, world, port, costs, expect, out, strided):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        lo, hi = sharding.split_range(len(costs), rank, world)
-        c, i = sharding.local_minimum(costs[lo:hi], lo)
+        if strided:
+            c, i = sharding.local_minimum_strided(costs, rank, world)
+        else:
+            lo, hi = sharding.split_range(len(costs), rank, world)
+            c, i = sharding.local_minimum(costs[lo:hi], lo)
         cs, idx = sharding.allgather_minima(dist, torch, c, i, "cpu")
         out[rank] = sharding.pick_winner(cs, idx)
         assert out[rank][1] == expect
@@ -38,10 +41,10 @@ def worker(rank, world, port, costs, expect, out):
         dist.destroy_process_group()
 
 
-def run_world(costs, expect, world=2):
+def run_world(costs, expect, world=2, strided=False):
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(worker, args=(world, free_port(), costs, expect, out), nprocs=world, join=True)
+    mp.spawn(worker, args=(world, free_port(), costs, expect, out, strided), nprocs=world, join=True)
     assert len(out) == world and len({v for v in out.values()}) == 1  # every rank agrees
     return out[0]
 
@@ -58,6 +61,11 @@ def test_sharded_argmin_equals_sequential_search(port):
     # the reported costs of losers may be early-exit partial sums (> best), never below the winner's
     cost, index = run_world(np.asarray(r["costs"]), r["best_index"])
     assert index == r["best_index"] and cost == r["cost"]
+    # the block-cyclic partition (blocks of 8 samples dealt round-robin) selects the same sample
+    cost, index = run_world(np.asarray(r["costs"]), r["best_index"], strided=True)
+    assert index == r["best_index"] and cost == r["cost"]
+    cost, index = run_world(np.asarray(r["costs"]), r["best_index"], world=3, strided=True)
+    assert index == r["best_index"] and cost == r["cost"]
 
 
 def test_sharded_argmin_ties_resolve_to_lowest_index():
@@ -67,6 +75,23 @@ def test_sharded_argmin_ties_resolve_to_lowest_index():
     assert run_world(costs, 5) == (4.0, 5)
     costs = np.array([np.nan, -6.0, -2.0, np.nan])  # nobody has anything valid
     assert run_world(costs, -1)[1] == -1
+
+
+def test_strided_ties_resolve_to_lowest_index():
+    costs = np.full(40, 9.0)
+    costs[[3, 11, 19, 35]] = 2.0  # equal minima in blocks 0, 1, 2, 4: ranks 0, 1, 0, 0 of a world of 2
+    assert run_world(costs, 3, strided=True) == (2.0, 3)
+    costs[3] = np.nan
+    assert run_world(costs, 11, strided=True) == (2.0, 11)
+
+
+@pytest.mark.parametrize("n,world", [(844200, 8), (40401, 3), (420, 2), (5, 4)])
+def test_strided_shares_tile_without_overlap(n, world):
+    shares = [sharding.strided_indices(n, r, world) for r in range(world)]
+    assert sum(len(s) for s in shares) == n and len(np.unique(np.concatenate(shares))) == n
+    blocks = -(-n // 8)
+    for r, s in enumerate(shares):  # what launch_score computes: max(1, ceil((blocks - r) / world)) CTAs of 8 samples
+        assert -(-len(s) // 8) == max(0, -(-(blocks - r) // world))
 
 
 @pytest.mark.parametrize("n,world", [(4096, 1), (4096, 2), (4096, 8), (10, 4), (3, 8)])
