@@ -163,6 +163,22 @@ int navgpu_costmap_get_window(navgpu_costmap* h, int x0, int y0, int xn, int yn,
  * Costmap2D the adapter keeps in sync (host_grid points at cell (0, 0); the window lands at its own place in it) */
 int navgpu_costmap_get_window_into(navgpu_costmap* h, int x0, int y0, int xn, int yn, uint8_t* host_grid,
                                    uint32_t host_pitch);
+/* Keeps a HOST mirror of the master grid (the Costmap2D the rest of the stack reads after
+ * LayeredCostmap::updateMap, layered_costmap.cpp:79-150) byte-identical to the device grid while moving only what
+ * changed.  The device holds a shadow of what `host_grid` contains; one kernel compares the master grid with it in
+ * tiles of 128 x 16 cells, writes the tiles that differ -- compacted, through mapped pinned memory -- and the call
+ * scatters them into host_grid (rows host_pitch bytes apart, cell (0, 0) first).  The first call for a given host_grid,
+ * a call after navgpu_costmap_mirror_invalidate, and a cycle that changed more than a quarter of the grid copy the whole
+ * grid instead.  The call synchronises the handle's stream, so `navgpu_costmap_update_map_async` + this is one
+ * complete cycle with a single host wait; the cycle's window is then available from navgpu_costmap_last_window.
+ * rects_out (nullable): x0, y0, xn, yn of every changed tile, up to rects_capacity of them; *n_rects_out: how many
+ * tiles changed (when it exceeds rects_capacity treat the whole grid as changed); *d2h_bytes_out: bytes that crossed
+ * PCIe for this call.  The host must not write host_grid between calls (or must call navgpu_costmap_mirror_invalidate). */
+int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t host_pitch, int32_t* rects_out,
+                               int rects_capacity, int32_t* n_rects_out, uint64_t* d2h_bytes_out);
+int navgpu_costmap_mirror_invalidate(navgpu_costmap* h);
+/* {x0, xn, y0, yn} of the last cycle whose window reached the host (navgpu_costmap_update_map, navgpu_costmap_get_changed) */
+int navgpu_costmap_last_window(navgpu_costmap* h, int32_t window_out[4]);
 /* page-lock / release a host buffer the caller owns, so that copies from and to it run at full PCIe speed (a pageable
  * 16 MB download takes about 4x as long); purely an optimisation, every entry point also accepts pageable memory */
 int navgpu_host_register(void* ptr, size_t bytes);
@@ -247,6 +263,31 @@ int navgpu_dwa_find_best_path(navgpu_dwa* h, const double pose[3], const double 
  * means the trajectory is legal.  A sample the generator rejects scores 0, exactly like the reference. */
 int navgpu_dwa_check_trajectory(navgpu_dwa* h, const double pose[3], const double vel[3], const double vel_samples[3],
                                 const double* footprint_xy, int n_footprint, double* cost_out);
+/* ---- the batched base_local_planner::TrajectoryCostFunction backend (trajectory_cost_function.h:52-82) -----------
+ * For callers that keep the reference's own search (SimpleScoredSamplingPlanner, simple_scored_sampling_planner.cpp
+ * :81-142) and / or their own TrajectorySampleGenerator: the six critics DWAPlanner wires up (dwa_planner.cpp:116-182),
+ * as ONE cost function over trajectories the caller generated.
+ *   navgpu_dwa_prepare             = prepare() of the critics: the four MapGridCostFunction wavefronts on the costmap
+ *                                    and plan the handle holds (map_grid_cost_function.cpp:59-68); no host wait
+ *   navgpu_dwa_score_trajectories  = scoreTrajectory for n_traj trajectories in one launch.  Trajectory t has points
+ *                                    offsets[t] .. offsets[t + 1] - 1 of points_xyth (x, y, theta doubles, what
+ *                                    Trajectory::getPoint returns) and velocities vels[3 t ..] = xv_, yv_, thetav_.
+ *                                    costs_out[t] = what SimpleScoredSamplingPlanner::scoreTrajectory (:50-79) returns
+ *                                    for it with best_traj_cost = -1: the critics' scaled costs summed in DWAPlanner's
+ *                                    order, or the first negative code (-5 oscillation, -6 footprint / off the map,
+ *                                    -9 empty footprint, -4 / -3 / -2 map grid).  terms_out (nullable): the six
+ *                                    per-critic terms of every trajectory.
+ *   navgpu_dwa_update_oscillation  = OscillationCostFunction::updateOscillationFlags (oscillation_cost_function.cpp
+ *                                    :56-68) with the trajectory the caller's search selected. */
+int navgpu_dwa_prepare(navgpu_dwa* h);
+int navgpu_dwa_score_trajectories(navgpu_dwa* h, int n_traj, const int32_t* offsets, const double* points_xyth,
+                                  const double* vels, const double* footprint_xy, int n_footprint, double* costs_out,
+                                  double* terms_out);
+int navgpu_dwa_update_oscillation(navgpu_dwa* h, const double pose[3], double cost, double xv, double yv, double thetav);
+/* the per-axis velocity samples of the last search (SimpleTrajectoryGenerator::initialise,
+ * simple_trajectory_generator.cpp:60-135): counts_out = {nx, ny, nth}; samples_out = xs | ys | ths (float32, exactly
+ * Eigen::Vector3f's values); sample index i = (ix * ny + iy) * nth + ith */
+int navgpu_dwa_get_samples(navgpu_dwa* h, int32_t counts_out[3], float* samples_out, int capacity);
 /* sample-range sharded variant for multi-GPU sweeps: scores enumerated samples [begin, end) only and returns this
  * shard's (cost, global index) minimum without touching the oscillation state; cost = +inf when none valid. */
 int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,

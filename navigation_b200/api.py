@@ -117,6 +117,10 @@ SIGNATURES = {
     "navgpu_costmap_get": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
     "navgpu_costmap_get_window_into": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_uint32]),
+    "navgpu_costmap_get_changed": (C.c_int, [C.c_void_p, _u8p, C.c_uint32, _i32p, C.c_int, C.POINTER(C.c_int32),
+                                             C.POINTER(C.c_uint64)]),
+    "navgpu_costmap_mirror_invalidate": (C.c_int, [C.c_void_p]),
+    "navgpu_costmap_last_window": (C.c_int, [C.c_void_p, _i32p]),
     "navgpu_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "navgpu_host_unregister": (C.c_int, [C.c_void_p]),
     "navgpu_costmap_get_window_occupancy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _i8p]),
@@ -146,6 +150,10 @@ SIGNATURES = {
                                          _i64p]),
     "navgpu_dwa_finish_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _i64p, C.c_int, C.POINTER(DwaResult), _f64p,
                                             C.c_int]),
+    "navgpu_dwa_prepare": (C.c_int, [C.c_void_p]),
+    "navgpu_dwa_score_trajectories": (C.c_int, [C.c_void_p, C.c_int, _i32p, _f64p, _f64p, _f64p, C.c_int, _f64p, _f64p]),
+    "navgpu_dwa_update_oscillation": (C.c_int, [C.c_void_p, _f64p, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "navgpu_dwa_get_samples": (C.c_int, [C.c_void_p, _i32p, C.POINTER(C.c_float), C.c_int]),
     "navgpu_dwa_score_strided": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_int,
                                            C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "navgpu_dwa_shard_export": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -376,6 +384,25 @@ class Costmap:
         self.api.check(self.lib.navgpu_costmap_get_window_into(self.h, x0, y0, xn, yn, _p(host_grid, _u8p),
                                                                host_grid.shape[1]))
 
+    def get_changed(self, host_grid, max_rects=0):
+        """Brings `host_grid` (the full-size host mirror, size_y x size_x uint8, the same array every call) up to date
+        with the device master grid moving only the 128 x 16 tiles that changed; returns (number of changed tiles,
+        bytes that crossed PCIe, rects [n][x0, y0, xn, yn] when max_rects > 0)."""
+        assert host_grid.dtype == np.uint8 and host_grid.flags["C_CONTIGUOUS"]
+        n, nbytes = C.c_int32(), C.c_uint64()
+        rects = np.zeros((max(1, max_rects), 4), dtype=np.int32)
+        self.api.check(self.lib.navgpu_costmap_get_changed(self.h, _p(host_grid, _u8p), host_grid.shape[1],
+                                                           _p(rects, _i32p), max_rects, C.byref(n), C.byref(nbytes)))
+        return int(n.value), int(nbytes.value), rects[:min(int(n.value), max_rects)]
+
+    def mirror_invalidate(self):
+        self.api.check(self.lib.navgpu_costmap_mirror_invalidate(self.h))
+
+    def last_window(self):
+        w = np.zeros(4, dtype=np.int32)
+        self.api.check(self.lib.navgpu_costmap_last_window(self.h, _p(w, _i32p)))
+        return tuple(int(v) for v in w)
+
     def get_window_occupancy(self, x0, y0, xn, yn):
         out = np.empty((yn - y0, xn - x0), dtype=np.int8)
         self.api.check(self.lib.navgpu_costmap_get_window_occupancy(self.h, x0, y0, xn, yn, _p(out, _i8p)))
@@ -493,6 +520,41 @@ class Dwa:
         self.api.check(self.lib.navgpu_dwa_score_range(self.h, _p(p, _f64p), _p(v, _f64p), _p(f, _f64p), f.shape[0],
                                                        begin, end, C.byref(cost), C.byref(idx), C.byref(total)))
         return cost.value, idx.value, total.value
+
+    def prepare(self):
+        """prepare() of the critics: the four MapGrid wavefronts on the current costmap and plan."""
+        self.api.check(self.lib.navgpu_dwa_prepare(self.h))
+
+    def score_trajectories(self, trajectories, vels, footprint_xy, want_terms=False):
+        """The batched TrajectoryCostFunction: `trajectories` = list of [n_i][3] arrays (x, y, theta), vels [n][3]
+        (xv_, yv_, thetav_); returns the total cost per trajectory (and the six per-critic terms)."""
+        n = len(trajectories)
+        offs = np.zeros(n + 1, dtype=np.int32)
+        for i, t in enumerate(trajectories):
+            offs[i + 1] = offs[i] + len(t)
+        pts = (np.concatenate([np.asarray(t, dtype=np.float64).reshape(-1, 3) for t in trajectories])
+               if n and offs[-1] else np.zeros((0, 3)))
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        v = np.ascontiguousarray(vels, dtype=np.float64).reshape(-1, 3)
+        f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        costs = np.zeros(n)
+        terms = np.zeros((n, 6)) if want_terms else None
+        self.api.check(self.lib.navgpu_dwa_score_trajectories(
+            self.h, n, _p(offs, _i32p), _p(pts, _f64p), _p(v, _f64p), _p(f, _f64p), f.shape[0], _p(costs, _f64p),
+            _p(terms, _f64p) if want_terms else None))
+        return (costs, terms) if want_terms else costs
+
+    def update_oscillation(self, pose, cost, xv, yv, thetav):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        self.api.check(self.lib.navgpu_dwa_update_oscillation(self.h, _p(p, _f64p), cost, xv, yv, thetav))
+
+    def samples(self):
+        """Per-axis velocity samples of the last search: (xs, ys, ths) float32 arrays."""
+        counts = np.zeros(3, dtype=np.int32)
+        buf = np.zeros(1 << 16, dtype=np.float32)
+        self.api.check(self.lib.navgpu_dwa_get_samples(self.h, _p(counts, _i32p), _p(buf, C.POINTER(C.c_float)), buf.size))
+        nx, ny, nth = (int(c) for c in counts)
+        return buf[:nx].copy(), buf[nx:nx + ny].copy(), buf[nx + ny:nx + ny + nth].copy()
 
     def score_strided(self, pose, vel, footprint_xy, rank, world):
         p = np.ascontiguousarray(pose, dtype=np.float64)

@@ -6,12 +6,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <limits>
 #include <memory>
 #include <vector>
 
 #include "costmap_kernels.cuh"
 #include "inflate_propagate.cuh"
+#include "mirror_kernels.cuh"
 
 namespace navgpu {
 
@@ -149,6 +151,10 @@ struct Layer {
   cudaEvent_t ev_stage = nullptr;
   size_t scan_capacity = 0;
   int n_clear = 0, n_mark = 0, total_rays = 0, total_marks = 0;
+  // world box of every sensor origin and observation point (rays and marks stay inside it); valid only when the
+  // points were seen on the host (navgpu_obstacle_set_observations)
+  bool touch_box_valid = false;
+  double tbx0 = 0, tby0 = 0, tbx1 = 0, tby1 = 0;
   std::vector<Pt> transformed_footprint;
   // voxel layer (an obstacle layer with columns of 16 voxels, plugins/voxel_layer.cpp)
   bool voxel = false;
@@ -192,6 +198,8 @@ struct navgpu_costmap {
   size_t occupancy_capacity = 0;
   uint16_t* d_seeds = nullptr;  // seed bitmask of the fast sweep (k_merge_seed -> k_inflate)
   size_t seeds_capacity = 0;
+  unsigned* d_tile_ready = nullptr;  // early mode: per k_merge_seed tile, the sweep number that last completed it
+  unsigned sweep_epoch = 0;
   // inflation mode 1 (k_inflate_propagate): per-cell state + two frontier lists, barrier / round control
   uint32_t* d_prop_state = nullptr;
   PropCtl* d_prop_ctl = nullptr;
@@ -204,6 +212,16 @@ struct navgpu_costmap {
   cudaEvent_t ev_sweep[2] = {nullptr, nullptr};
   cudaEvent_t ev_mid = nullptr;  // between k_merge_seed and k_inflate
   cudaEvent_t ev_cycle[2] = {nullptr, nullptr};
+  // host mirror kept in sync by navgpu_costmap_get_changed (mirror_kernels.cuh)
+  uint8_t* d_shadow = nullptr;           // what the host mirror holds
+  const uint8_t* mirror_host = nullptr;  // the host grid the shadow describes
+  uint32_t mirror_host_pitch = 0;
+  bool shadow_valid = false;
+  uint8_t* h_mirror_stage = nullptr;     // mapped pinned: changed tiles, compacted
+  unsigned* h_mirror_tiles = nullptr;    // mapped pinned: their tile numbers
+  MirrorCtl* h_mirror_ctl = nullptr;     // mapped pinned
+  unsigned* d_mirror_counters = nullptr;
+  unsigned mirror_capacity = 0;
 
   size_t bytes() const { return size_t(pitch) * sy; }
   Geom geom(double gox, double goy) const { return Geom{sx, sy, pitch, res, gox, goy}; }
@@ -329,8 +347,13 @@ int launch_propagate(const UpdateArgs& a, const uint16_t* seeds, const PropBuffe
   return NAVGPU_OK;
 }
 
+struct TileFlags {  // early mode: k_merge_seed -> k_inflate per-tile hand-over (MergeSeedArgs::ready)
+  unsigned* ready = nullptr;
+  unsigned epoch = 0;
+};
+
 int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic, cudaEvent_t ev_mid = nullptr,
-                 const PropBuffers* prop = nullptr) {
+                 const PropBuffers* prop = nullptr, const TileFlags* flags = nullptr) {
   const int R = a.R;
   if ((R <= 31 && !force_generic) || (prop && R > 0)) {
     MergeSeedArgs m;
@@ -342,9 +365,12 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
     m.ml = a.ml;
     m.R = R;
     m.seeds = seeds;
+    m.early = a.early; m.ex0 = a.ex0; m.exn = a.exn; m.ey0 = a.ey0; m.eyn = a.eyn;
     if (R > 0 && !seeds) return fail(NAVGPU_ERR_INVALID, "seed bitmask missing");
     dim3 block(kMSGroupsX, kMSRowsY);
     dim3 grid((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16), (a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
+    const bool handover = flags && flags->ready && a.early && R > 0 && !(prop && R > 0) && !ev_mid;
+    if (handover) { m.ready = flags->ready; m.epoch = flags->epoch; }
     if (a.ml.n > 0 || a.do_reset || R > 0) {
       NAVGPU_CUDA(launch_pdl(k_merge_seed, grid, block, 0, stream, m));
       NAVGPU_LAUNCHED(1);
@@ -360,6 +386,7 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
       ia.reach2 = a.reach2;
       ia.cost_d2 = a.cost_d2;
       ia.seeds = reinterpret_cast<const uint32_t*>(seeds);
+      if (handover) { ia.ready = flags->ready; ia.epoch = flags->epoch; ia.ready_pitch = (int)grid.x; }
       dim3 igrid((a.sx + kITX - 1) / kITX, (a.sy + kITY - 1) / kITY);
       // the instantiation whose unrolled row walk just covers the effective reach (what k_inflate calls R)
       const int reach = (int)sqrtf((float)a.reach2 + 0.5f);
@@ -407,9 +434,15 @@ int ensure_prop(navgpu_costmap* h, const Layer& L, PropBuffers* pb) {
   return NAVGPU_OK;
 }
 
+struct EarlyBox {  // see UpdateArgs::early
+  int on = 0, x0 = 0, xn = 0, y0 = 0, yn = 0;
+};
+
 int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2, int reach2 = 0,
-                  const Layer* infl = nullptr) {
+                  const Layer* infl = nullptr, const EarlyBox* early = nullptr) {
   UpdateArgs a;
+  a.early = early && early->on && do_reset ? 1 : 0;
+  a.ex0 = early ? early->x0 : 0; a.exn = early ? early->xn : 0; a.ey0 = early ? early->y0 : 0; a.eyn = early ? early->yn : 0;
   a.master = h->master[h->cur];
   a.sx = h->sx; a.sy = h->sy; a.pitch = h->pitch;
   a.def = h->def;
@@ -424,8 +457,19 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   if (propagate) NAVGPU_TRY(ensure_prop(h, *infl, &pb));
   if (R > 0 && (R <= 31 || propagate)) NAVGPU_TRY(ensure_seeds(&h->d_seeds, &h->seeds_capacity, h->pitch, h->sy, h->stream));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[0], h->stream);
+  TileFlags tf;
+  if (a.early && R > 0 && R <= 31 && !propagate) {
+    const size_t n_tiles = size_t((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16)) *
+                           ((a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
+    if (!h->d_tile_ready) {
+      NAVGPU_CUDA(cudaMalloc(&h->d_tile_ready, n_tiles * sizeof(unsigned)));
+      NAVGPU_CUDA(cudaMemsetAsync(h->d_tile_ready, 0, n_tiles * sizeof(unsigned), h->stream));
+    }
+    tf.ready = h->d_tile_ready;
+    tf.epoch = ++h->sweep_epoch;
+  }
   NAVGPU_TRY(launch_sweep(a, h->d_seeds, h->stream, h->force_generic, h->profile && R > 0 ? h->ev_mid : nullptr,
-                          propagate ? &pb : nullptr));
+                          propagate ? &pb : nullptr, &tf));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[1], h->stream);
   return NAVGPU_OK;
 }
@@ -472,6 +516,11 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   ba.n_layers = (int)h->layers.size();
   ba.master = h->geom(h->ox, h->oy);
   int last_obstacle = -1;
+  // Is this cycle's window the whole map as far as the host can tell (a grid layer updated as a whole, an inflation
+  // layer that must re-inflate), and where can the obstacle kernels write?  Then the merge sweep need not wait for them
+  // outside that box (UpdateArgs::early).
+  bool whole_map = false, box_known = !h->rolling;
+  double ebx0 = 1e300, eby0 = 1e300, ebx1 = -1e300, eby1 = -1e300;
   for (size_t li = 0; li < h->layers.size(); ++li) {
     Layer& L = h->layers[li];
     BoundsLayer& B = ba.layer[li];
@@ -485,6 +534,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
       B.hy0 = L.oy + (L.uy + 0.5) * h->res;
       B.hx1 = L.ox + (L.ux + L.uw + 0.5) * h->res;
       B.hy1 = L.oy + (L.uy + L.uh + 0.5) * h->res;
+      if (L.ux == 0 && L.uy == 0 && L.uw >= h->sx && L.uh >= h->sy && L.ox == h->ox && L.oy == h->oy) whole_map = true;
       L.updated = false;
     } else if (L.kind == 1) {  // ObstacleLayer::updateBounds (obstacle_layer.cpp:340-413)
       if (h->rolling) {
@@ -525,7 +575,17 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
         B.flag = 1;
         B.hx0 = bx0; B.hy0 = by0; B.hx1 = bx1; B.hy1 = by1;
       }
+      if (L.voxel || !L.touch_box_valid || L.ox != h->ox || L.oy != h->oy) box_known = false;
+      if (L.tbx1 >= L.tbx0 && L.tby1 >= L.tby0) {
+        ebx0 = std::min(ebx0, L.tbx0); eby0 = std::min(eby0, L.tby0);
+        ebx1 = std::max(ebx1, L.tbx1); eby1 = std::max(eby1, L.tby1);
+      }
+      for (const Pt& p : L.transformed_footprint) {
+        ebx0 = std::min(ebx0, p.x); eby0 = std::min(eby0, p.y);
+        ebx1 = std::max(ebx1, p.x); eby1 = std::max(eby1, p.y);
+      }
     } else {  // InflationLayer::updateBounds runs on the device (needs the device-accumulated bounds)
+      if (L.need_reinflation) whole_map = true;
       B.flag = L.need_reinflation ? 1 : 0;
       B.hx0 = L.radius;
       L.need_reinflation = false;
@@ -607,6 +667,19 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
 
   // ---- resetMap + updateCosts of every plugin, in order (:137-142), fused into as few sweeps as possible:
   // consecutive cost layers merge in one pass, an inflation layer closes the pass.
+  EarlyBox early;
+  static const bool no_early = getenv("NAVGPU_NO_EARLY_MERGE") != nullptr;  // measurement switch (tools/probe_overlap.py)
+  if (whole_map && box_known && !no_early) {
+    early.on = 1;
+    if (ebx1 >= ebx0 && eby1 >= eby0) {  // cells, two to spare on every side, clamped to the map
+      auto cell = [&](double w, double origin, int size, int pad) {
+        const double c = std::floor((w - origin) / h->res) + pad;
+        return (int)std::min<double>(size, std::max(0.0, c));
+      };
+      early.x0 = cell(ebx0, h->ox, (int)h->sx, -2); early.xn = cell(ebx1, h->ox, (int)h->sx, 3);
+      early.y0 = cell(eby0, h->oy, (int)h->sy, -2); early.yn = cell(eby1, h->oy, (int)h->sy, 3);
+    }
+  }
   MergeLayers ml;
   ml.n = 0;
   int do_reset = 1;
@@ -631,13 +704,13 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
         NAVGPU_TRY(launch_update(h, ml, 0, 0, nullptr));
         ml.n = 0;
       }
-      NAVGPU_TRY(launch_update(h, ml, do_reset, (int)L.tables.R, L.d_cost_d2, L.tables.reach2, &L));
+      NAVGPU_TRY(launch_update(h, ml, do_reset, (int)L.tables.R, L.d_cost_d2, L.tables.reach2, &L, &early));
       ml.n = 0;
       do_reset = 0;
       pending = false;
     }
   }
-  if (pending) NAVGPU_TRY(launch_update(h, ml, do_reset, 0, nullptr));
+  if (pending) NAVGPU_TRY(launch_update(h, ml, do_reset, 0, nullptr, 0, nullptr, &early));
   return NAVGPU_OK;
 }
 
@@ -707,6 +780,10 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   cudaFree(h->master[0]); cudaFree(h->master[1]);
   cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
   cudaFree(h->d_prop_state); cudaFree(h->d_prop_ctl);
+  cudaFree(h->d_shadow); cudaFree(h->d_mirror_counters); cudaFree(h->d_tile_ready);
+  if (h->h_mirror_stage) cudaFreeHost(h->h_mirror_stage);
+  if (h->h_mirror_tiles) cudaFreeHost(h->h_mirror_tiles);
+  if (h->h_mirror_ctl) cudaFreeHost(h->h_mirror_ctl);
   cudaFreeHost(h->h_win);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -917,8 +994,11 @@ static int install_observations(navgpu_costmap* h, Layer* L, const std::vector<D
   // The uploads go through a pinned staging buffer owned by the layer, so they are asynchronous and the call does not
   // have to wait for the stream: [xyz | clearing table | marking table].  The buffer is reused by the next call once
   // the copies that read it have completed (event).
-  const size_t xyz_bytes = xyz_host ? n_floats * sizeof(float) : 0, clear_bytes = clear.size() * sizeof(DevObs),
-               mark_bytes = mark.size() * sizeof(DevObs);
+  // (k_obstacle_update takes tables of up to kInlineObs observations in its kernel parameters: no upload then)
+  const bool tables_inline = !L->voxel && clear.size() <= (size_t)kInlineObs && mark.size() <= (size_t)kInlineObs;
+  const size_t xyz_bytes = xyz_host ? n_floats * sizeof(float) : 0,
+               clear_bytes = tables_inline ? 0 : clear.size() * sizeof(DevObs),
+               mark_bytes = tables_inline ? 0 : mark.size() * sizeof(DevObs);
   const size_t stage_bytes = ((xyz_bytes + 15) & ~size_t(15)) + clear_bytes + mark_bytes;
   if (stage_bytes > 0) {
     if (!L->ev_stage) NAVGPU_CUDA(cudaEventCreateWithFlags(&L->ev_stage, cudaEventDisableTiming));
@@ -963,8 +1043,21 @@ int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_
   std::vector<DevObs> clear, mark;
   L->obs.clear();
   int rays = 0, marks = 0;
+  double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
+  bool finite = true;
   for (int i = 0; i < n_obs; ++i) {
     if (obs[i].n_points < 0 || (obs[i].n_points > 0 && !obs[i].xyz)) return fail(NAVGPU_ERR_INVALID, "bad observation %d", i);
+    bx0 = std::min(bx0, obs[i].origin_x); bx1 = std::max(bx1, obs[i].origin_x);
+    by0 = std::min(by0, obs[i].origin_y); by1 = std::max(by1, obs[i].origin_y);
+    finite = finite && std::isfinite(obs[i].origin_x) && std::isfinite(obs[i].origin_y);
+    float fx0 = INFINITY, fy0 = INFINITY, fx1 = -INFINITY, fy1 = -INFINITY;
+    for (int p = 0; p < obs[i].n_points; ++p) {  // NaN points never win a comparison; the kernels drop them too
+      const float x = obs[i].xyz[3 * p], y = obs[i].xyz[3 * p + 1];
+      fx0 = x < fx0 ? x : fx0; fx1 = x > fx1 ? x : fx1;
+      fy0 = y < fy0 ? y : fy0; fy1 = y > fy1 ? y : fy1;
+    }
+    if (fx1 >= fx0) { bx0 = std::min(bx0, (double)fx0); bx1 = std::max(bx1, (double)fx1); }
+    if (fy1 >= fy0) { by0 = std::min(by0, (double)fy0); by1 = std::max(by1, (double)fy1); }
     DevObs d;
     d.ox = obs[i].origin_x; d.oy = obs[i].origin_y; d.oz = obs[i].origin_z;
     d.obstacle_range = obs[i].obstacle_range;
@@ -986,6 +1079,8 @@ int navgpu_obstacle_set_observations(navgpu_costmap* h, int layer, const navgpu_
       mark.push_back(d);
     }
   }
+  L->touch_box_valid = finite;
+  L->tbx0 = bx0; L->tby0 = by0; L->tbx1 = bx1; L->tby1 = by1;
   return install_observations(h, L, clear, mark, rays, marks, xyz.data(), xyz.size());
 }
 
@@ -995,6 +1090,7 @@ int navgpu_obstacle_set_scans(navgpu_costmap* h, int layer, const navgpu_laser_s
   Layer* L = get_layer(h, layer, 1);
   if (!L || n_scans < 0 || (n_scans > 0 && !scans)) return fail(NAVGPU_ERR_INVALID, "bad obstacle layer / scans");
   NAVGPU_TRY(use_device(h));
+  L->touch_box_valid = false;  // the projected points only ever exist on the device
   std::vector<float> ranges;
   std::vector<ScanRec> recs;
   std::vector<DevObs> clear, mark;
@@ -1204,6 +1300,104 @@ int navgpu_costmap_get_window_into(navgpu_costmap* h, int x0, int y0, int xn, in
                                 h->master[h->cur] + size_t(y0) * h->pitch + x0, h->pitch, xn - x0, yn - y0,
                                 cudaMemcpyDeviceToHost, h->stream));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+// ---- host mirror ---------------------------------------------------------------------------------------------------
+int navgpu_costmap_mirror_invalidate(navgpu_costmap* h) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  h->shadow_valid = false;
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t host_pitch, int32_t* rects_out,
+                               int rects_capacity, int32_t* n_rects_out, uint64_t* d2h_bytes_out) {
+  if (!h || !host_grid || host_pitch < h->sx || rects_capacity < 0 || (rects_capacity > 0 && !rects_out))
+    return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  NAVGPU_TRY(use_device(h));
+  const unsigned tiles_x = (h->sx + kMirrorTileW - 1) / kMirrorTileW, tiles_y = (h->sy + kMirrorTileH - 1) / kMirrorTileH;
+  const unsigned n_tiles = tiles_x * tiles_y;
+  if (!h->d_shadow) {
+    // staging for up to a quarter of the grid (at least 64 tiles, at most 4 MB): beyond that one plain copy is cheaper
+    h->mirror_capacity = std::max(64u, std::min(2048u, n_tiles / 4));
+    NAVGPU_CUDA(cudaMalloc(&h->d_shadow, h->bytes()));
+    NAVGPU_CUDA(cudaMalloc(&h->d_mirror_counters, 2 * sizeof(unsigned)));
+    NAVGPU_CUDA(cudaMemsetAsync(h->d_mirror_counters, 0, 2 * sizeof(unsigned), h->stream));
+    NAVGPU_CUDA(cudaHostAlloc(&h->h_mirror_stage, size_t(h->mirror_capacity) * kMirrorTileBytes, cudaHostAllocMapped));
+    NAVGPU_CUDA(cudaHostAlloc(&h->h_mirror_tiles, size_t(h->mirror_capacity) * sizeof(unsigned), cudaHostAllocMapped));
+    NAVGPU_CUDA(cudaHostAlloc(&h->h_mirror_ctl, sizeof(MirrorCtl), cudaHostAllocMapped));
+    h->shadow_valid = false;
+  }
+  if (host_grid != h->mirror_host || host_pitch != h->mirror_host_pitch) h->shadow_valid = false;
+  auto whole_grid = [&]() -> int {
+    NAVGPU_CUDA(cudaMemcpy2DAsync(host_grid, host_pitch, h->master[h->cur], h->pitch, h->sx, h->sy, cudaMemcpyDeviceToHost,
+                                  h->stream));
+    return NAVGPU_OK;
+  };
+  auto report_whole = [&]() {
+    if (n_rects_out) *n_rects_out = 1;
+    if (rects_capacity > 0) { rects_out[0] = 0; rects_out[1] = 0; rects_out[2] = (int)h->sx; rects_out[3] = (int)h->sy; }
+    if (d2h_bytes_out) *d2h_bytes_out = uint64_t(h->sx) * h->sy;
+  };
+  if (!h->shadow_valid) {
+    NAVGPU_TRY(whole_grid());
+    NAVGPU_CUDA(cudaMemcpyAsync(h->d_shadow, h->master[h->cur], h->bytes(), cudaMemcpyDeviceToDevice, h->stream));
+    if (!h->layers.empty())
+      NAVGPU_CUDA(cudaMemcpyAsync(h->h_win, h->d_win, sizeof(DevWindow), cudaMemcpyDeviceToHost, h->stream));
+    NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+    if (!h->layers.empty()) {
+      h->win[0] = h->h_win->x0; h->win[1] = h->h_win->xn; h->win[2] = h->h_win->y0; h->win[3] = h->h_win->yn;
+    }
+    h->shadow_valid = true;
+    h->mirror_host = host_grid;
+    h->mirror_host_pitch = host_pitch;
+    report_whole();
+    return NAVGPU_OK;
+  }
+  MirrorArgs a;
+  a.master = h->master[h->cur];
+  a.shadow = h->d_shadow;
+  a.sx = h->sx; a.sy = h->sy; a.pitch = h->pitch;
+  a.tiles_x = tiles_x; a.tiles_y = tiles_y;
+  a.capacity = h->mirror_capacity;
+  a.stage = h->h_mirror_stage;
+  a.stage_tile = h->h_mirror_tiles;
+  a.counters = h->d_mirror_counters;
+  a.ctl = h->h_mirror_ctl;
+  a.win = h->layers.empty() ? nullptr : h->d_win;
+  k_mirror_diff<<<(n_tiles + kMirrorWarps - 1) / kMirrorWarps, kMirrorWarps * 32, 0, h->stream>>>(a);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaGetLastError());
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  const MirrorCtl& ctl = *h->h_mirror_ctl;
+  if (a.win) { h->win[0] = ctl.win.x0; h->win[1] = ctl.win.xn; h->win[2] = ctl.win.y0; h->win[3] = ctl.win.yn; }
+  if (ctl.n_changed > h->mirror_capacity) {  // the shadow is up to date already; the host takes the plain copy
+    NAVGPU_TRY(whole_grid());
+    NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+    report_whole();
+    return NAVGPU_OK;
+  }
+  const unsigned n = ctl.n_staged;
+  for (unsigned k = 0; k < n; ++k) {
+    const unsigned t = h->h_mirror_tiles[k], tx = t % tiles_x, ty = t / tiles_x;
+    const unsigned x0 = tx * kMirrorTileW, y0 = ty * kMirrorTileH;
+    const unsigned w = std::min<unsigned>(kMirrorTileW, h->sx - x0), hg = std::min<unsigned>(kMirrorTileH, h->sy - y0);
+    const uint8_t* src = h->h_mirror_stage + size_t(k) * kMirrorTileBytes;
+    uint8_t* dst = host_grid + size_t(y0) * host_pitch + x0;
+    for (unsigned r = 0; r < hg; ++r) memcpy(dst + size_t(r) * host_pitch, src + r * kMirrorTileW, w);
+    if ((int)k < rects_capacity) {
+      rects_out[4 * k] = (int)x0; rects_out[4 * k + 1] = (int)y0;
+      rects_out[4 * k + 2] = (int)(x0 + w); rects_out[4 * k + 3] = (int)(y0 + hg);
+    }
+  }
+  if (n_rects_out) *n_rects_out = (int)n;
+  if (d2h_bytes_out) *d2h_bytes_out = uint64_t(n) * (kMirrorTileBytes + sizeof(unsigned)) + sizeof(MirrorCtl);
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_last_window(navgpu_costmap* h, int32_t window_out[4]) {
+  if (!h || !window_out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  for (int i = 0; i < 4; ++i) window_out[i] = h->win[i];
   return NAVGPU_OK;
 }
 

@@ -901,6 +901,9 @@ struct UpdateArgs {
   int R;                   // 0: no inflation in this pass
   const uint8_t* cost_d2;  // R*R+1 entries: cost by squared cell distance
   int reach2;              // largest squared distance whose cost is not 0 (a cost of 0 never changes a cell)
+  // early != 0: the host knows this cycle's window is the whole map and that the kernel launched just before the sweep
+  // (k_obstacle_update) writes layer cells only inside [ex0, exn) x [ey0, eyn): see k_merge_seed
+  int early = 0, ex0 = 0, exn = 0, ey0 = 0, eyn = 0;
 };
 
 __device__ __forceinline__ uint8_t apply_policy(uint8_t m, uint8_t v, int policy) {
@@ -1087,6 +1090,11 @@ struct MergeSeedArgs {
   MergeLayers ml;
   int R;            // 0: merge only (seeds may be null)
   uint16_t* seeds;  // sy x seed_pitch16(pitch)
+  int early = 0, ex0 = 0, exn = 0, ey0 = 0, eyn = 0;  // see UpdateArgs
+  // early mode with k_inflate behind us: every CTA publishes `epoch` in ready[blockIdx.y * gridDim.x + blockIdx.x] once
+  // its tile (master cells and seed bits) is written, and k_inflate's tiles wait for just the tiles they read
+  unsigned* ready = nullptr;
+  unsigned epoch = 0;
 };
 
 __device__ __forceinline__ uint32_t inc4(uint32_t x) {  // per-byte x + 1 (mod 256), no carry between bytes
@@ -1234,15 +1242,27 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   // launched with programmatic stream serialization: let k_inflate be scheduled as soon as every CTA of this grid
   // is resident, and wait for the kernel before us (window, obstacle grid) before reading anything
   cudaTriggerProgrammaticLaunchCompletion();
-  cudaGridDependencySynchronize();
-  const DevWindow w = *a.win;
+  constexpr int kW = kMSGroupsX * 16, kH = kMSRowsY * kMSRowIters;
+  const int bx0 = blockIdx.x * kW, by0 = blockIdx.y * kH;
+  DevWindow w;
+  if (a.early) {
+    // The window is the whole map whatever the obstacle kernel ahead of us adds to the bounds (they only grow), and that
+    // kernel -- a latency chain of a few thousand rays on a fraction of the SMs -- writes layer cells only inside the
+    // box of its rays, marks and footprint.  Tiles outside that box do not wait for it: the streaming merge of ~95 % of
+    // the map overlaps the ray tracing.  CTA (0, 0) always waits, so that this grid completes after the obstacle
+    // kernel and k_inflate, which waits for this grid, sees everything that kernel wrote (the window record included).
+    w.x0 = 0; w.xn = (int)a.sx; w.y0 = 0; w.yn = (int)a.sy; w.valid = 1;
+    const bool touched = bx0 < a.exn && bx0 + kW > a.ex0 && by0 < a.eyn && by0 + kH > a.ey0;
+    if (touched || (blockIdx.x | blockIdx.y) == 0) cudaGridDependencySynchronize();
+  } else {
+    cudaGridDependencySynchronize();
+    w = *a.win;
+  }
   if (!w.valid) return;
   const int R = a.R;
   // everything k_inflate can read: its tiles intersect window +- 2R, extend up to a tile further, and look R rows /
   // 32 columns beyond their own extent
   const int my = R > 0 ? 3 * R + kITY : 0, mx = R > 0 ? 2 * R + kITX + 32 : 0;
-  constexpr int kW = kMSGroupsX * 16, kH = kMSRowsY * kMSRowIters;
-  const int bx0 = blockIdx.x * kW, by0 = blockIdx.y * kH;
   if (bx0 >= w.xn + mx || bx0 + kW <= w.x0 - mx || by0 >= w.yn + my || by0 + kH <= w.y0 - my) return;
   const int sx0 = max(0, w.x0 - R), sxn = min((int)a.sx, w.xn + R);  // seed region (inflation_layer.cpp:203-211)
   const int sy0 = max(0, w.y0 - R), syn = min((int)a.sy, w.yn + R);
@@ -1251,9 +1271,13 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   const bool interior = bx0 >= w.x0 && bx0 + kW <= w.xn && by0 >= w.y0 && by0 + kH <= w.yn;
   if (interior) {
     merge_seed_items<true>(a, w, x, by0, sx0, sxn, sy0, syn);
-  } else {
-    if (x >= (int)a.pitch) return;
+  } else if (x < (int)a.pitch) {
     merge_seed_items<false>(a, w, x, by0, sx0, sxn, sy0, syn);
+  }
+  if (a.ready) {  // (early mode: the window is the whole map, no CTA left above)
+    __syncthreads();
+    if ((threadIdx.x | threadIdx.y) == 0)  // (release at gpu scope: cumulative over what the barrier made visible here)
+      asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.ready + blockIdx.y * gridDim.x + blockIdx.x), "r"(a.epoch) : "memory");
   }
 }
 
@@ -1265,6 +1289,11 @@ struct InflateArgs {
   int reach2;              // largest squared distance whose cost is not 0: nothing beyond it can change a cell
   const uint8_t* cost_d2;  // R*R+1 entries: cost by squared cell distance
   const uint32_t* seeds;   // the bitmask written by k_merge_seed, viewed as 32-bit words
+  // early mode (see MergeSeedArgs): the window is the whole map and a tile starts as soon as the k_merge_seed tiles it
+  // reads have published `epoch`, instead of waiting for that whole grid (and, through it, for the obstacle kernel)
+  const unsigned* ready = nullptr;
+  unsigned epoch = 0;
+  int ready_pitch = 0;  // k_merge_seed's gridDim.x
 };
 
 // RMAX bounds the effective reach (in cells) this instantiation can handle: the phase-3 walk is unrolled over
@@ -1279,13 +1308,41 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   uint32_t* const sbits = h2;
   __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
+  const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
+  // early mode: the flags of the k_merge_seed tiles this tile reads (seeds: columns tx0 - 32 .. tx0 + 95, rows
+  // ty0 - R .. ty0 + kITY + R - 1; master cells: the tile itself), one per thread, requested before anything else
+  const unsigned* my_flag = nullptr;
+  unsigned flag_seen = 0;
+  if (a.ready) {
+    constexpr int kMW = kMSGroupsX * 16, kMH = kMSRowsY * kMSRowIters;
+    const int mx0 = max(0, tx0 - 32) / kMW, mx1 = min((int)a.pitch - 1, tx0 + kITX + 31) / kMW;
+    const int my0 = max(0, ty0 - a.R) / kMH, my1 = min((int)a.sy - 1, ty0 + kITY + a.R - 1) / kMH;
+    const int nx = mx1 - mx0 + 1, n = nx * (my1 - my0 + 1);  // <= 2 x 7 for R <= 31
+    if ((int)threadIdx.x < n) {
+      my_flag = a.ready + (my0 + (int)threadIdx.x / nx) * a.ready_pitch + mx0 + (int)threadIdx.x % nx;
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(flag_seen) : "l"(my_flag) : "memory");
+    }
+  }
   // the cost table was uploaded long before this cycle: stage it while k_merge_seed is still draining, then wait
   for (int i = threadIdx.x; i <= a.reach2; i += kIThreads) table[i] = a.cost_d2[i];
   if (threadIdx.x == 0) table[a.reach2 + 1] = 0;
-  cudaGridDependencySynchronize();
-  const DevWindow w = *a.win;
+  DevWindow w;
+  if (a.ready) {
+    // Every k_merge_seed CTA is resident or done by the time this grid is scheduled (it triggers the programmatic launch
+    // at its first instruction), so waiting for some of them cannot deadlock.
+    if (my_flag) {
+      while (flag_seen != a.epoch) {
+        __nanosleep(32);
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(flag_seen) : "l"(my_flag) : "memory");
+      }
+    }
+    __syncthreads();
+    w.x0 = 0; w.xn = (int)a.sx; w.y0 = 0; w.yn = (int)a.sy; w.valid = 1;
+  } else {
+    cudaGridDependencySynchronize();
+    w = *a.win;
+  }
   if (!w.valid) return;
-  const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
   {
     const int R = a.R;
     if (tx0 >= w.xn + 2 * R || tx0 + kITX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kITY <= w.y0 - 2 * R) return;
@@ -1302,7 +1359,8 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   for (int i = tid; i < rows * 4; i += kIThreads) {
     const int gy = ty0 - R + (i >> 2);
     uint32_t v = 0;
-    if (gy >= 0 && gy < (int)a.sy) v = a.seeds[(size_t)gy * sp32 + (tx0 >> 5) + (i & 3)];
+    // (read past L1: in early mode a line of the bitmask can hold words of a k_merge_seed tile that is still running)
+    if (gy >= 0 && gy < (int)a.sy) v = __ldcg(&a.seeds[(size_t)gy * sp32 + (tx0 >> 5) + (i & 3)]);
     sbits[i] = v;
     any |= v != 0;
   }

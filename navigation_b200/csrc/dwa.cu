@@ -188,6 +188,11 @@ struct navgpu_dwa {
   unsigned long long shard_seq = 0;
   Cycle shard_cycle;
   bool shard_pending = false;
+  // TrajectoryCostFunction backend (navgpu_dwa_score_trajectories): device copies of the caller's trajectories
+  char* d_traj = nullptr;
+  size_t traj_capacity = 0;
+  std::vector<float> last_samples;  // per-axis samples of the last search (xs | ys | ths), see navgpu_dwa_get_samples
+  int last_nx = 0, last_ny = 0, last_nth = 0;
 };
 
 namespace {
@@ -304,6 +309,47 @@ int launch_mapgrid(navgpu_dwa* h, const MapGridArgs& ma, int n_ctas, int jobs_pe
   return launch_mapgrid(&t, ma, n_ctas, jobs_per_robot);
 }
 
+// prepare() of the critics (simple_scored_sampling_planner.cpp:87-93): the plans reach the device, then four MapGrid
+// wavefronts, one CTA each
+int prepare_grids(navgpu_dwa* h, const DwaGeom& g) {
+  for (int k = 0; k < 3; ++k) NAVGPU_TRY(upload_plan(h, k));
+  MapGridArgs ma;
+  ma.g = g;
+  ma.allow_unknown = h->cfg.allow_unknown;
+  ma.job[0] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 0, h->d_dist[0]};  // path: setTargetCells
+  ma.job[1] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 1, h->d_dist[1]};  // goal: setLocalGoal
+  ma.job[2] = MapGridJob{h->d_plan[1], (int)h->adjusted[1].size(), 1, h->d_dist[2]};  // goal_front
+  ma.job[3] = MapGridJob{h->d_plan[2], (int)h->adjusted[2].size(), 0, h->d_dist[3]};  // alignment
+  if (h->align_is_path) {  // same poses, same mode as the path grid: one wavefront serves both critics
+    ma.job[3].dist = h->d_dist[0];
+    ma.job[3].skip = 1;
+  }
+  ma.fleet = nullptr;
+  NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
+  h->align_aliased = h->align_is_path;
+  return NAVGPU_OK;
+}
+
+// the critics' part of the scoring arguments: geometry, distance grids, scales, footprint, flags
+int critic_args(navgpu_dwa* h, const DwaGeom& g, const double* footprint_xy, int n_footprint, DwaScoreArgs& a) {
+  if (n_footprint < 0 || n_footprint > kMaxFootprint) return fail(NAVGPU_ERR_UNSUPPORTED, "footprint with more than %d vertices", kMaxFootprint);
+  const navgpu_dwa_config& c = h->cfg;
+  a.g = g;
+  for (int k = 0; k < 4; ++k) a.dist[k] = h->d_dist[k];
+  if (h->align_aliased) a.dist[3] = h->d_dist[0];
+  a.sum_scores = c.sum_scores; a.allow_unknown = c.allow_unknown;
+  a.osc_mask = h->osc.mask();
+  a.scale_obstacle = h->obstacle_scale;
+  a.scale_goal_front = h->goal_scale;
+  a.scale_alignment = h->alignment_scale;
+  a.scale_path = h->path_scale;
+  a.scale_goal = h->goal_scale;
+  a.xshift = c.forward_point_distance;
+  a.nfp = n_footprint;
+  for (int k = 0; k < n_footprint; ++k) { a.fpx[k] = footprint_xy[2 * k]; a.fpy[k] = footprint_xy[2 * k + 1]; }
+  return NAVGPU_OK;
+}
+
 // uploads the per-cycle inputs and launches the 4 MapGrid wavefronts; fills the scoring arguments
 int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const double* footprint_xy, int n_footprint,
                 Cycle& cy, bool prepare = true) {
@@ -327,26 +373,11 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
     NAVGPU_CUDA(cudaMemcpyAsync(h->d_samples, s.v.data(), s.v.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // pageable source
   }
-  for (int k = 0; k < 3; ++k) NAVGPU_TRY(upload_plan(h, k));
+  h->last_samples = s.v;
+  h->last_nx = s.nx; h->last_ny = s.ny; h->last_nth = s.nth;
 
   DwaGeom g{h->d_cost, h->sx, h->sy, h->pitch, h->res, h->ox, h->oy, 1.0 / h->res};
-  // prepare() of the critics (simple_scored_sampling_planner.cpp:87-93): four wavefronts, one CTA each
-  MapGridArgs ma;
-  ma.g = g;
-  ma.allow_unknown = c.allow_unknown;
-  ma.job[0] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 0, h->d_dist[0]};  // path: setTargetCells
-  ma.job[1] = MapGridJob{h->d_plan[0], (int)h->adjusted[0].size(), 1, h->d_dist[1]};  // goal: setLocalGoal
-  ma.job[2] = MapGridJob{h->d_plan[1], (int)h->adjusted[1].size(), 1, h->d_dist[2]};  // goal_front
-  ma.job[3] = MapGridJob{h->d_plan[2], (int)h->adjusted[2].size(), 0, h->d_dist[3]};  // alignment
-  if (h->align_is_path) {  // same poses, same mode as the path grid: one wavefront serves both critics
-    ma.job[3].dist = h->d_dist[0];
-    ma.job[3].skip = 1;
-  }
-  ma.fleet = nullptr;
-  if (prepare) {
-    NAVGPU_TRY(launch_mapgrid(h, ma, 4, 4));
-    h->align_aliased = h->align_is_path;
-  }
+  if (prepare) NAVGPU_TRY(prepare_grids(h, g));
 
   DwaScoreArgs& a = cy.args;
   a.g = g;
@@ -481,6 +512,7 @@ int navgpu_dwa_destroy(navgpu_dwa* h) {
   for (int r = 0; r < kShardMaxWorld; ++r)
     if (h->shard_ipc[r] && h->shard_peer[r]) cudaIpcCloseMemHandle(h->shard_peer[r]);
   cudaFree(h->d_shard);
+  cudaFree(h->d_traj);
   cudaFreeHost(h->h_result); cudaFreeHost(h->h_points); cudaFreeHost(h->h_best);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -646,6 +678,78 @@ int navgpu_dwa_check_trajectory(navgpu_dwa* h, const double pose[3], const doubl
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   *cost_out = *out;
   return NAVGPU_OK;
+}
+
+// ---- the batched TrajectoryCostFunction backend ---------------------------------------------------------------------
+int navgpu_dwa_prepare(navgpu_dwa* h) {
+  if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  NAVGPU_TRY(use_device(h));
+  if (!h->d_cost) return fail(NAVGPU_ERR_INVALID, "no costmap set");
+  if (h->plan.empty()) return fail(NAVGPU_ERR_INVALID, "no plan set");
+  const DwaGeom g{h->d_cost, h->sx, h->sy, h->pitch, h->res, h->ox, h->oy, 1.0 / h->res};
+  NAVGPU_TRY(prepare_grids(h, g));
+  NAVGPU_CUDA(cudaGetLastError());
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_score_trajectories(navgpu_dwa* h, int n_traj, const int32_t* offsets, const double* points_xyth,
+                                  const double* vels, const double* footprint_xy, int n_footprint, double* costs_out,
+                                  double* terms_out) {
+  if (!h || n_traj < 0 || (n_traj > 0 && (!offsets || !vels || !costs_out)) || (n_footprint > 0 && !footprint_xy))
+    return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (n_traj == 0) return NAVGPU_OK;
+  NAVGPU_TRY(use_device(h));
+  if (!h->d_cost) return fail(NAVGPU_ERR_INVALID, "no costmap set");
+  const long long n_points = offsets[n_traj];
+  if (offsets[0] != 0 || n_points < 0 || (n_points > 0 && !points_xyth)) return fail(NAVGPU_ERR_INVALID, "bad trajectory offsets");
+  for (int t = 0; t < n_traj; ++t)
+    if (offsets[t + 1] < offsets[t]) return fail(NAVGPU_ERR_INVALID, "trajectory offsets must not decrease");
+  // device copies: [points | vels | costs | terms | offsets]
+  const size_t b_points = size_t(n_points) * 3 * sizeof(double), b_vels = size_t(n_traj) * 3 * sizeof(double),
+               b_costs = size_t(n_traj) * sizeof(double), b_terms = terms_out ? size_t(n_traj) * 6 * sizeof(double) : 0,
+               b_off = size_t(n_traj + 1) * sizeof(int32_t);
+  const size_t need = b_points + b_vels + b_costs + b_terms + b_off;
+  if (need > h->traj_capacity) {
+    if (h->d_traj) cudaFree(h->d_traj);
+    h->d_traj = nullptr;
+    NAVGPU_CUDA(cudaMalloc(&h->d_traj, 2 * need));
+    h->traj_capacity = 2 * need;
+  }
+  double* d_points = reinterpret_cast<double*>(h->d_traj);
+  double* d_vels = reinterpret_cast<double*>(h->d_traj + b_points);
+  double* d_costs = reinterpret_cast<double*>(h->d_traj + b_points + b_vels);
+  double* d_terms = terms_out ? reinterpret_cast<double*>(h->d_traj + b_points + b_vels + b_costs) : nullptr;
+  int* d_off = reinterpret_cast<int*>(h->d_traj + b_points + b_vels + b_costs + b_terms);
+  if (b_points) NAVGPU_CUDA(cudaMemcpyAsync(d_points, points_xyth, b_points, cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(d_vels, vels, b_vels, cudaMemcpyHostToDevice, h->stream));
+  NAVGPU_CUDA(cudaMemcpyAsync(d_off, offsets, b_off, cudaMemcpyHostToDevice, h->stream));
+  DwaScoreArgs a;
+  memset(&a, 0, sizeof(a));
+  const DwaGeom g{h->d_cost, h->sx, h->sy, h->pitch, h->res, h->ox, h->oy, 1.0 / h->res};
+  NAVGPU_TRY(critic_args(h, g, footprint_xy, n_footprint, a));
+  const int blocks = (n_traj + kDwaWarpsPerBlock - 1) / kDwaWarpsPerBlock;
+  k_dwa_score_points<<<blocks, kDwaWarpsPerBlock * 32, 0, h->stream>>>(a, d_off, d_points, d_vels, n_traj, d_costs, d_terms);
+  NAVGPU_LAUNCHED(1);
+  NAVGPU_CUDA(cudaGetLastError());
+  NAVGPU_CUDA(cudaMemcpyAsync(costs_out, d_costs, b_costs, cudaMemcpyDeviceToHost, h->stream));
+  if (terms_out) NAVGPU_CUDA(cudaMemcpyAsync(terms_out, d_terms, b_terms, cudaMemcpyDeviceToHost, h->stream));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_update_oscillation(navgpu_dwa* h, const double pose[3], double cost, double xv, double yv, double thetav) {
+  if (!h || !pose) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  const float pos[3] = {(float)pose[0], (float)pose[1], (float)pose[2]};
+  h->osc.update(pos, cost, xv, yv, thetav, h->cfg.min_trans_vel, h->cfg.oscillation_reset_dist, h->cfg.oscillation_reset_angle);
+  return NAVGPU_OK;
+}
+
+int navgpu_dwa_get_samples(navgpu_dwa* h, int32_t counts_out[3], float* samples_out, int capacity) {
+  if (!h || !counts_out || capacity < 0 || (capacity > 0 && !samples_out)) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  counts_out[0] = h->last_nx; counts_out[1] = h->last_ny; counts_out[2] = h->last_nth;
+  const size_t n = std::min<size_t>(h->last_samples.size(), (size_t)capacity);
+  if (n) memcpy(samples_out, h->last_samples.data(), n * sizeof(float));
+  return h->last_samples.size() > (size_t)capacity ? fail(NAVGPU_ERR_CAPACITY, "samples_out too small") : NAVGPU_OK;
 }
 
 int navgpu_dwa_score_range(navgpu_dwa* h, const double pose[3], const double vel[3], const double* footprint_xy,
@@ -935,6 +1039,11 @@ int navgpu_fleet_create(navgpu_fleet** out, int n_robots, const navgpu_dwa_confi
     return fail(NAVGPU_ERR_INVALID, "bad fleet arguments");
   if (navgpu_device_count() <= device) return fail(NAVGPU_ERR_CUDA, "no CUDA device %d (libnavgpu has no CPU fallback)", device);
   if (size_x > 32767 || size_y > 32767) return fail(NAVGPU_ERR_UNSUPPORTED, "local costmap too large");
+  // the robots' maps are stacked with kFleetPadRows free rows between them: a larger cell inflation radius
+  // (Costmap2D::cellDistance, costmap_2d.cpp:181-185) would inflate one robot's obstacles into its neighbour's map
+  if (inflation_radius > 0 && std::ceil(inflation_radius / resolution) > (double)kFleetPadRows)
+    return fail(NAVGPU_ERR_UNSUPPORTED, "fleet inflation radius of %.0f cells exceeds the %u rows between stacked maps",
+                std::ceil(inflation_radius / resolution), kFleetPadRows);
   std::unique_ptr<navgpu_fleet> f(new navgpu_fleet);
   f->device = device;
   f->n = n_robots;

@@ -568,6 +568,160 @@ __device__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
   return bad ? -1 : best;
 }
 
+// What the critics accumulate over the rounds of 32 points of one trajectory
+struct CriticAcc {
+  bool obst_fail;
+  double obst_sum, obst_last;
+  // per map-grid critic: code of the first failing point (0 = none yet) and the value at the last point
+  double grid_code[4], grid_last[4];
+};
+__device__ __forceinline__ void critic_acc_init(CriticAcc& acc) {
+  acc.obst_fail = false;
+  acc.obst_sum = acc.obst_last = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc.grid_code[k] = acc.grid_last[k] = 0.0;
+}
+
+// The obstacle critic and the four map-grid critics on one round of up to 32 trajectory points: lane l < cnt holds
+// point l -- world position (px, py) and cos / sin of its heading (obstacle_cost_function.cpp:74-142,
+// map_grid_cost_function.cpp:75-129).  Shared by the sample sweep (the points come out of the rollout) and by the
+// TrajectoryCostFunction backend (the points come from the caller's Trajectory).
+__device__ __forceinline__ void score_round(const DwaScoreArgs& a, int lane, int cnt, double px, double py, double c,
+                                            double s, double* warp_scratch, CriticAcc& acc) {
+  const bool active = lane < cnt;
+  // ---- obstacle critic: (point, edge) work items spread over all 32 lanes, so a short tail round costs one edge
+  // per lane instead of a whole footprint per active lane
+  double* pose_s = warp_scratch;              // x, y, cos, sin of the round's points
+  // per point: max edge cost; bit 31 set (the unsigned maximum) once any edge of the point is illegal
+  unsigned* edge_max = reinterpret_cast<unsigned*>(warp_scratch + 128);
+  pose_s[lane] = px;
+  pose_s[32 + lane] = py;
+  pose_s[64 + lane] = c;
+  pose_s[96 + lane] = s;
+  edge_max[lane] = 0;
+  __syncwarp();
+  double occ = 0.0;
+  bool fail = false;
+  if (a.nfp >= 3) {
+    // every (point, vertex) cell once, then every (point, edge) walk between two of them
+    int* vcell = reinterpret_cast<int*>(warp_scratch + 128 + 16);  // [point][kMaxFootprint]
+    const int items = cnt * a.nfp;
+    // it / nfp for it < 512, nfp <= 16 as a multiply by ceil(2^16 / nfp) (error < 512 / 2^16 < 1 / nfp: exact)
+    const unsigned inv_nfp = (65536u + (unsigned)a.nfp - 1u) / (unsigned)a.nfp;
+    for (int it = lane; it < items; it += 32) {
+      const int p = (int)(((unsigned)it * inv_nfp) >> 16), v = it - p * a.nfp;
+      vcell[p * kMaxFootprint + v] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
+    }
+    __syncwarp();
+    for (int it = lane; it < items; it += 32) {
+      const int p = (int)(((unsigned)it * inv_nfp) >> 16), e = it - p * a.nfp;
+      const int e1 = e + 1 < a.nfp ? e + 1 : 0;
+      const int ec = footprint_edge_cost(a, vcell[p * kMaxFootprint + e], vcell[p * kMaxFootprint + e1]);
+      atomicMax(&edge_max[p], ec < 0 ? 0x80000000u : (unsigned)ec);
+    }
+    __syncwarp();
+  }
+  // the cell of the point itself serves the obstacle critic's centre lookup and the path / goal grids; the point
+  // shifted ahead by xshift serves goal_front / alignment: two worldToMap per point instead of five
+  int cell0_x = 0, cell0_y = 0, cell1_x = 0, cell1_y = 0;
+  bool on_map0 = false, on_map1 = false;
+  if (active) {
+    on_map0 = dwa_world_to_map(a.g, px, py, cell0_x, cell0_y);
+    if (a.xshift != 0.0) {
+      on_map1 = dwa_world_to_map(a.g, px + a.xshift * c, py + a.xshift * s, cell1_x, cell1_y);
+    } else {
+      on_map1 = on_map0; cell1_x = cell0_x; cell1_y = cell0_y;
+    }
+  }
+  if (active) {
+    const int cx = cell0_x, cy = cell0_y;
+    if (a.nfp == 0 || !on_map0) fail = true;  // off-map centre: costmap_model.cpp:57-58
+    else {
+      const int centre = a.g.cost[cy * (int)a.g.pitch + cx];
+      int f = (int)edge_max[lane];
+      if (a.nfp < 3) {  // point robot: the centre cell alone (:61-67)
+        f = (centre == kLethal || centre == kInscribed || (centre == kNoInfo && !a.allow_unknown)) ? -1 : centre;
+      }
+      if (f < 0) fail = true;
+      else occ = fmax(fmax(0.0, (double)f), (double)centre);
+    }
+  }
+  acc.obst_fail |= __any_sync(0xffffffffu, fail);
+  double ssum = occ;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);  // small integers: exact
+  acc.obst_sum += ssum;
+  acc.obst_last = __shfl_sync(0xffffffffu, occ, cnt - 1);
+  __syncwarp();
+  // ---- the four map-grid critics on my point (the grids come from the kernel launched before this one)
+  cudaGridDependencySynchronize();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool shifted = k >= 2;        // goal_front, alignment use xshift (dwa_planner.cpp:80-81)
+    const bool stop_on_failure = k < 2;  // path, goal (:126-127 turn it off for the other two)
+    double code = 0.0, d = 0.0;
+    if (active) {
+      const int cx = shifted ? cell1_x : cell0_x, cy = shifted ? cell1_y : cell0_y;
+      if (!(shifted ? on_map1 : on_map0)) code = -4.0;
+      else {
+        const uint32_t dd = a.dist[k][cy * (int)a.g.sx + cx];
+        const uint32_t n_cells = a.g.sx * a.g.sy;
+        d = (double)dd;
+        if (stop_on_failure) {
+          if (dd == n_cells) code = -3.0;
+          else if (dd == n_cells + 1) code = -2.0;
+        }
+      }
+    }
+    const unsigned failing = __ballot_sync(0xffffffffu, code != 0.0);
+    if (failing && acc.grid_code[k] == 0.0) acc.grid_code[k] = __shfl_sync(0xffffffffu, code, __ffs(failing) - 1);
+    acc.grid_last[k] = __shfl_sync(0xffffffffu, d, cnt - 1);
+  }
+}
+
+// SimpleScoredSamplingPlanner::scoreTrajectory with critics in DWAPlanner's order (dwa_planner.cpp:167-173): the
+// total of one trajectory from what the critics found; terms_out (nullable, lane 0 writes) receives the six terms.
+__device__ __forceinline__ double combine_critics(const DwaScoreArgs& a, bool osc_bad, const CriticAcc& acc, double* terms_out,
+                                                  int lane) {
+  const double raw[6] = {osc_bad ? -5.0 : 0.0,
+                         a.nfp == 0 ? -9.0 : (acc.obst_fail ? -6.0 : (a.sum_scores ? acc.obst_sum : acc.obst_last)),
+                         acc.grid_code[2] != 0.0 ? acc.grid_code[2] : acc.grid_last[2],
+                         acc.grid_code[3] != 0.0 ? acc.grid_code[3] : acc.grid_last[3],
+                         acc.grid_code[0] != 0.0 ? acc.grid_code[0] : acc.grid_last[0],
+                         acc.grid_code[1] != 0.0 ? acc.grid_code[1] : acc.grid_last[1]};
+  const double scale[6] = {1.0, a.scale_obstacle, a.scale_goal_front, a.scale_alignment, a.scale_path, a.scale_goal};
+  double total = 0.0;
+  bool done = false;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double term = 0.0;  // what this critic adds; negative = rejecting code; skipped critics add nothing
+    if (scale[k] != 0.0) {
+      double cst = raw[k];
+      if (cst < 0) term = cst;
+      else {
+        if (cst != 0) cst *= scale[k];
+        term = cst;
+      }
+    }
+    if (terms_out && lane == 0) terms_out[k] = scale[k] == 0.0 ? 0.0 : term;
+    if (!done) {
+      if (term < 0) {
+        total = term;
+        done = true;
+      } else {
+        total += term;
+      }
+    }
+  }
+  return total;
+}
+
+// OscillationCostFunction::scoreTrajectory (oscillation_cost_function.cpp:166-176) on the latched-flag mask
+__device__ __forceinline__ bool oscillation_rejects(int m, double xv, double yv, double thv) {
+  return ((m & 1) && xv < 0.0) || ((m & 2) && xv > 0.0) || ((m & 4) && yv < 0.0) || ((m & 8) && yv > 0.0) ||
+         ((m & 16) && thv < 0.0) || ((m & 32) && thv > 0.0);
+}
+
 __device__ __forceinline__ float sample_vx(const DwaScoreArgs& a, int i) { return a.inline_samples ? a.samples_inline[i] : a.vxs[i]; }
 __device__ __forceinline__ float sample_vy(const DwaScoreArgs& a, int i) { return a.inline_samples ? a.samples_inline[a.nx + i] : a.vys[i]; }
 __device__ __forceinline__ float sample_vth(const DwaScoreArgs& a, int i) {
@@ -618,15 +772,11 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
 
   // OscillationCostFunction (scale 1): sign of the sampled velocity against the latched flags
   const double xv = txv, yv = tyv, thv = tthv;
-  const int m = a.osc_mask;
-  const bool osc_bad = ((m & 1) && xv < 0.0) || ((m & 2) && xv > 0.0) || ((m & 4) && yv < 0.0) ||
-                       ((m & 8) && yv > 0.0) || ((m & 16) && thv < 0.0) || ((m & 32) && thv > 0.0);
+  const bool osc_bad = oscillation_rejects(a.osc_mask, xv, yv, thv);
 
   float sx = a.pos[0], sy = a.pos[1], sth = a.pos[2];  // state at the first point of the current round
-  bool obst_fail = false;
-  double obst_sum = 0.0, obst_last = 0.0;
-  // per map-grid critic: code of the first failing point (0 = none yet) and the value at the last point
-  double grid_code[4] = {0, 0, 0, 0}, grid_last[4] = {0, 0, 0, 0};
+  CriticAcc acc;
+  critic_acc_init(acc);
 
   for (int base = 0; base < num_steps; base += 32) {
     const int cnt = min(32, num_steps - base);
@@ -683,129 +833,11 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
       points_out[3 * (base + lane) + 2] = thd;
     }
     if (!kScore) continue;
-    // ---- obstacle critic: (point, edge) work items spread over all 32 lanes, so a short tail round costs one edge
-    // per lane instead of a whole footprint per active lane
-    double* pose_s = warp_scratch;              // x, y, cos, sin of the round's points
-    // per point: max edge cost; bit 31 set (the unsigned maximum) once any edge of the point is illegal
-    unsigned* edge_max = reinterpret_cast<unsigned*>(warp_scratch + 128);
-    pose_s[lane] = px;
-    pose_s[32 + lane] = py;
-    pose_s[64 + lane] = c;
-    pose_s[96 + lane] = s;
-    edge_max[lane] = 0;
-    __syncwarp();
-    double occ = 0.0;
-    bool fail = false;
-    if (a.nfp >= 3) {
-      // every (point, vertex) cell once, then every (point, edge) walk between two of them
-      int* vcell = reinterpret_cast<int*>(warp_scratch + 128 + 16);  // [point][kMaxFootprint]
-      const int items = cnt * a.nfp;
-      // it / nfp for it < 512, nfp <= 16 as a multiply by ceil(2^16 / nfp) (error < 512 / 2^16 < 1 / nfp: exact)
-      const unsigned inv_nfp = (65536u + (unsigned)a.nfp - 1u) / (unsigned)a.nfp;
-      for (int it = lane; it < items; it += 32) {
-        const int p = (int)(((unsigned)it * inv_nfp) >> 16), v = it - p * a.nfp;
-        vcell[p * kMaxFootprint + v] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
-      }
-      __syncwarp();
-      for (int it = lane; it < items; it += 32) {
-        const int p = (int)(((unsigned)it * inv_nfp) >> 16), e = it - p * a.nfp;
-        const int e1 = e + 1 < a.nfp ? e + 1 : 0;
-        const int ec = footprint_edge_cost(a, vcell[p * kMaxFootprint + e], vcell[p * kMaxFootprint + e1]);
-        atomicMax(&edge_max[p], ec < 0 ? 0x80000000u : (unsigned)ec);
-      }
-      __syncwarp();
-    }
-    // the cell of the point itself serves the obstacle critic's centre lookup and the path / goal grids; the point
-    // shifted ahead by xshift serves goal_front / alignment: two worldToMap per point instead of five
-    int cell0_x = 0, cell0_y = 0, cell1_x = 0, cell1_y = 0;
-    bool on_map0 = false, on_map1 = false;
-    if (active) {
-      on_map0 = dwa_world_to_map(a.g, px, py, cell0_x, cell0_y);
-      if (a.xshift != 0.0) {
-        on_map1 = dwa_world_to_map(a.g, px + a.xshift * c, py + a.xshift * s, cell1_x, cell1_y);
-      } else {
-        on_map1 = on_map0; cell1_x = cell0_x; cell1_y = cell0_y;
-      }
-    }
-    if (active) {
-      const int cx = cell0_x, cy = cell0_y;
-      if (a.nfp == 0 || !on_map0) fail = true;  // off-map centre: costmap_model.cpp:57-58
-      else {
-        const int centre = a.g.cost[cy * (int)a.g.pitch + cx];
-        int f = (int)edge_max[lane];
-        if (a.nfp < 3) {  // point robot: the centre cell alone (:61-67)
-          f = (centre == kLethal || centre == kInscribed || (centre == kNoInfo && !a.allow_unknown)) ? -1 : centre;
-        }
-        if (f < 0) fail = true;
-        else occ = fmax(fmax(0.0, (double)f), (double)centre);
-      }
-    }
-    obst_fail |= __any_sync(0xffffffffu, fail);
-    double ssum = occ;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);  // small integers: exact
-    obst_sum += ssum;
-    obst_last = __shfl_sync(0xffffffffu, occ, cnt - 1);
-    __syncwarp();
-    // ---- the four map-grid critics on my point (the grids come from the kernel launched before this one)
-    cudaGridDependencySynchronize();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool shifted = k >= 2;        // goal_front, alignment use xshift (dwa_planner.cpp:80-81)
-      const bool stop_on_failure = k < 2;  // path, goal (:126-127 turn it off for the other two)
-      double code = 0.0, d = 0.0;
-      if (active) {
-        const int cx = shifted ? cell1_x : cell0_x, cy = shifted ? cell1_y : cell0_y;
-        if (!(shifted ? on_map1 : on_map0)) code = -4.0;
-        else {
-          const uint32_t dd = a.dist[k][cy * (int)a.g.sx + cx];
-          const uint32_t n_cells = a.g.sx * a.g.sy;
-          d = (double)dd;
-          if (stop_on_failure) {
-            if (dd == n_cells) code = -3.0;
-            else if (dd == n_cells + 1) code = -2.0;
-          }
-        }
-      }
-      const unsigned failing = __ballot_sync(0xffffffffu, code != 0.0);
-      if (failing && grid_code[k] == 0.0) grid_code[k] = __shfl_sync(0xffffffffu, code, __ffs(failing) - 1);
-      grid_last[k] = __shfl_sync(0xffffffffu, d, cnt - 1);
-    }
+    score_round(a, lane, cnt, px, py, c, s, warp_scratch, acc);
   }
 
   if (!kScore) return res;
-  // SimpleScoredSamplingPlanner::scoreTrajectory with critics in DWAPlanner's order (dwa_planner.cpp:167-173)
-  const double raw[6] = {osc_bad ? -5.0 : 0.0,
-                         a.nfp == 0 ? -9.0 : (obst_fail ? -6.0 : (a.sum_scores ? obst_sum : obst_last)),
-                         grid_code[2] != 0.0 ? grid_code[2] : grid_last[2],
-                         grid_code[3] != 0.0 ? grid_code[3] : grid_last[3],
-                         grid_code[0] != 0.0 ? grid_code[0] : grid_last[0],
-                         grid_code[1] != 0.0 ? grid_code[1] : grid_last[1]};
-  const double scale[6] = {1.0, a.scale_obstacle, a.scale_goal_front, a.scale_alignment, a.scale_path, a.scale_goal};
-  double total = 0.0;
-  bool done = false;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    double term = 0.0;  // what this critic adds; negative = rejecting code; skipped critics add nothing
-    if (scale[k] != 0.0) {
-      double cst = raw[k];
-      if (cst < 0) term = cst;
-      else {
-        if (cst != 0) cst *= scale[k];
-        term = cst;
-      }
-    }
-    if (terms_out && lane == 0) terms_out[k] = scale[k] == 0.0 ? 0.0 : term;
-    if (!done) {
-      if (term < 0) {
-        total = term;
-        done = true;
-      } else {
-        total += term;
-      }
-    }
-  }
-  res.cost = total;
+  res.cost = combine_critics(a, osc_bad, acc, terms_out, lane);
   return res;
 }
 
@@ -1024,6 +1056,41 @@ __global__ void k_dwa_check(DwaScoreArgs a, double* cost_out) {
   __shared__ double s_scratch[kWarpScratchDoubles];
   const TrajResult r = score_sample<true>(a, 0, threadIdx.x & 31, nullptr, nullptr, 0, s_scratch);
   if (threadIdx.x == 0) *cost_out = r.generated ? r.cost : ((a.nfp == 0 && a.scale_obstacle != 0.0) ? -9.0 : 0.0);
+}
+
+// The batched base_local_planner::TrajectoryCostFunction backend (trajectory_cost_function.h:52-82): trajectories the
+// CALLER generated (any TrajectorySampleGenerator) are scored by the six critics DWAPlanner wires up, in its order
+// (dwa_planner.cpp:167-173), with SimpleScoredSamplingPlanner::scoreTrajectory's accumulation (:50-79, no early exit).
+// One warp per trajectory, one lane per point of a round; points = x, y, theta as Trajectory::getPoint returns them
+// (doubles), vels = xv_, yv_, thetav_.  A trajectory without points scores what the reference's critics return for
+// an empty loop: 0 from every grid / obstacle critic (-9 for an empty footprint), -5 from a latched oscillation flag.
+__global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score_points(DwaScoreArgs a, const int* __restrict__ offsets,
+                                                                           const double* __restrict__ points,
+                                                                           const double* __restrict__ vels, int n_traj,
+                                                                           double* __restrict__ costs_out,
+                                                                           double* __restrict__ terms_out) {
+  __shared__ double s_scratch[kDwaWarpsPerBlock][kWarpScratchDoubles];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = blockIdx.x * kDwaWarpsPerBlock + warp;
+  if (t >= n_traj) return;
+  const int first = offsets[t], n = offsets[t + 1] - first;
+  const bool osc_bad = oscillation_rejects(a.osc_mask, vels[3 * t], vels[3 * t + 1], vels[3 * t + 2]);
+  CriticAcc acc;
+  critic_acc_init(acc);
+  for (int base = 0; base < n; base += 32) {
+    const int cnt = min(32, n - base);
+    double px = 0.0, py = 0.0, c = 1.0, s = 0.0;
+    if (lane < cnt) {
+      const double* p = points + 3 * (size_t)(first + base + lane);
+      px = p[0];
+      py = p[1];
+      sincos(p[2], &s, &c);  // WorldModel::footprintCost / MapGridCostFunction take cos, sin of the point's heading
+    }
+    score_round(a, lane, cnt, px, py, c, s, s_scratch[warp], acc);
+    __syncwarp();
+  }
+  const double total = combine_critics(a, osc_bad, acc, terms_out ? terms_out + 6 * (size_t)t : nullptr, lane);
+  if (lane == 0) costs_out[t] = total;
 }
 
 // stand-alone finish for sharded sweeps: the winner was chosen from the all-gathered per-rank minima

@@ -1,0 +1,111 @@
+// mirror_kernels.cuh -- keeping a HOST copy of the master grid in sync without shipping the whole grid every cycle.
+//
+// The reference's consumers (Costmap2DROS, the planners, Costmap2DPublisher) read the master Costmap2D in host memory
+// after LayeredCostmap::updateMap (layered_costmap.cpp:79-150).  A device-resident master grid therefore has to reach the
+// host every cycle, and at 4000 x 4000 that copy (16 MB over PCIe, ~0.3 ms) costs four times the update itself --
+// although all but a few hundred cells keep their value from one cycle to the next.  The device keeps a SHADOW of what
+// the host mirror holds; k_mirror_diff compares the master grid with it tile by tile, writes the tiles that differ
+// straight into mapped pinned host memory (posted writes over PCIe, compacted, with their tile numbers) and brings
+// the shadow up to date.  The host then scatters those tiles into its grid: the mirror is byte-identical to the master
+// grid again, whatever happened in between (skipped cycles, rolled origins, navgpu_costmap_set).
+#pragma once
+
+#include "common.cuh"
+
+namespace navgpu {
+
+constexpr int kMirrorTileW = 128, kMirrorTileH = 16;            // one warp per tile: 8 lanes x 16 B per row, 4 rows per pass
+constexpr int kMirrorTileBytes = kMirrorTileW * kMirrorTileH;  // 2 KB
+constexpr int kMirrorWarps = 8;
+
+struct MirrorCtl {  // mapped pinned host memory: written by the last CTA of k_mirror_diff
+  unsigned n_changed;  // tiles that differ (may exceed the staging capacity: then the host copies the whole grid)
+  unsigned n_staged;   // tiles actually written to the staging buffer = min(n_changed, capacity)
+  DevWindow win;       // the window of the last update cycle, so that one synchronisation serves both
+};
+
+struct MirrorArgs {
+  const uint8_t* master;
+  uint8_t* shadow;
+  unsigned sx, sy, pitch;
+  unsigned tiles_x, tiles_y;
+  unsigned capacity;     // tiles the staging buffer holds
+  uint8_t* stage;        // mapped pinned: capacity x kMirrorTileBytes
+  unsigned* stage_tile;  // mapped pinned: tile number of every staged tile
+  unsigned* counters;    // device: [0] changed tiles, [1] CTAs done
+  MirrorCtl* ctl;        // mapped pinned
+  const DevWindow* win;  // nullable
+};
+
+// bytes of a and b that differ among the first n_valid bytes of the 16-byte group
+__device__ __forceinline__ bool group_differs(const uint4& a, const uint4& b, int n_valid) {
+  if (n_valid >= 16) return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0;
+  const uint32_t d[4] = {a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w};
+  uint32_t any = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int nb = min(4, max(0, n_valid - 4 * k));
+    const uint32_t mask = nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
+    any |= d[k] & mask;
+  }
+  return any != 0;
+}
+
+__global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a) {
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned tile = blockIdx.x * kMirrorWarps + warp;
+  const unsigned n_tiles = a.tiles_x * a.tiles_y;
+  if (tile < n_tiles) {
+    const unsigned tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    const int x = (int)tx * kMirrorTileW + (lane & 7) * 16;
+    const int y0 = (int)ty * kMirrorTileH + (lane >> 3);
+    const int n_valid = min(16, max(0, (int)a.sx - x));  // the row padding is nobody's data
+    uint4 m[4], s[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int y = y0 + 4 * p;
+      m[p] = s[p] = make_uint4(0, 0, 0, 0);
+      if (y < (int)a.sy && n_valid > 0) {
+        const size_t off = (size_t)y * a.pitch + x;
+        m[p] = *reinterpret_cast<const uint4*>(a.master + off);
+        s[p] = *reinterpret_cast<const uint4*>(a.shadow + off);
+      }
+    }
+    bool differs = false;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) differs |= group_differs(m[p], s[p], n_valid);
+    if (__any_sync(0xffffffffu, differs)) {
+      unsigned slot = 0;
+      if (lane == 0) slot = atomicAdd(&a.counters[0], 1u);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      const bool staged = slot < a.capacity;
+      if (staged && lane == 0) a.stage_tile[slot] = tile;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int y = y0 + 4 * p;
+        if (staged)  // rows below the map / columns right of it travel as zeros and are dropped by the host
+          *reinterpret_cast<uint4*>(a.stage + (size_t)slot * kMirrorTileBytes + ((lane >> 3) + 4 * p) * kMirrorTileW +
+                                    (lane & 7) * 16) = m[p];
+        if (y < (int)a.sy && n_valid > 0) *reinterpret_cast<uint4*>(a.shadow + (size_t)y * a.pitch + x) = m[p];
+      }
+    }
+  }
+  // the CTA that finishes last publishes the counts (and the cycle's window) and re-arms the counters
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&a.counters[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  const unsigned n = *reinterpret_cast<volatile unsigned*>(&a.counters[0]);
+  a.ctl->n_changed = n;
+  a.ctl->n_staged = min(n, a.capacity);
+  if (a.win) a.ctl->win = *a.win;
+  a.counters[0] = 0;
+  a.counters[1] = 0;
+}
+
+}  // namespace navgpu

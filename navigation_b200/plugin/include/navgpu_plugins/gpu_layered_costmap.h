@@ -2,7 +2,9 @@
 // layers libnavgpu implements (static-style grid layers, obstacle layers, inflation): one updateMap() runs the whole
 // cycle of costmap_2d/src/layered_costmap.cpp:79-150 on the GPU (bounds of every layer, resetMap, merges in plugin
 // order, ray-trace clearing + marking + footprint clearing, inflation) without the master grid leaving HBM, and
-// getCostmap() brings the updated window back into an ordinary costmap_2d::Costmap2D for host-side consumers.
+// getCostmap() brings an ordinary costmap_2d::Costmap2D for host-side consumers up to date: only the tiles whose cells
+// changed since the last call cross PCIe (navgpu_costmap_get_changed), and the host grid is byte-identical to the
+// device grid afterwards whatever happened in between (several updateMap calls, rolled origins).
 // Header-only RAII over the navgpu_costmap_* C ABI (include/navgpu.h); method names follow LayeredCostmap /
 // Costmap2DROS.  Errors: methods return false and keep navgpu_last_error(); there is no CPU fallback.
 #ifndef NAVGPU_PLUGINS_GPU_LAYERED_COSTMAP_H_
@@ -127,24 +129,38 @@ class GpuLayeredCostmap {
   bool updateMap(double robot_x, double robot_y, double robot_yaw) {
     return check(navgpu_costmap_update_map(handle_, robot_x, robot_y, robot_yaw, bounds_));
   }
+  // the same without waiting for the device: the cycle is complete (and getBounds valid) after the next getCostmap()
+  bool updateMapAsync(double robot_x, double robot_y, double robot_yaw) {
+    return check(navgpu_costmap_update_map_async(handle_, robot_x, robot_y, robot_yaw));
+  }
   // LayeredCostmap::getBounds (layered_costmap.h:129-135)
   void getBounds(unsigned int* x0, unsigned int* xn, unsigned int* y0, unsigned int* yn) const {
     *x0 = bounds_[0]; *xn = bounds_[1]; *y0 = bounds_[2]; *yn = bounds_[3];
   }
-  // LayeredCostmap::getCostmap: refreshes the host copy inside the last update window and returns it
-  costmap_2d::Costmap2D* getCostmap() {
-    const int w = bounds_[1] - bounds_[0], h = bounds_[3] - bounds_[2];
-    if (w > 0 && h > 0) {
-      double origin[2];
-      navgpu_costmap_get_origin(handle_, origin);
-      // Costmap2D::updateOrigin copies the whole grid twice even for a zero shift (costmap_2d.cpp:264-313): only when
-      // the device grid really rolled
-      if (origin[0] != host_.getOriginX() || origin[1] != host_.getOriginY()) host_.updateOrigin(origin[0], origin[1]);
-      // one device-to-host copy, straight into the window's place in the host grid
-      if (!check(navgpu_costmap_get_window_into(handle_, bounds_[0], bounds_[2], bounds_[1], bounds_[3], host_.getCharMap(),
-                                                host_.getSizeInCellsX())))
-        return NULL;
+  // LayeredCostmap::getCostmap: brings the host copy up to date with the device grid and returns it.  changed_rects
+  // (optional) receives x0, y0, xn, yn of every 128 x 16 tile that was rewritten (empty + *whole_grid = true when the
+  // whole grid was copied), e.g. for Costmap2DPublisher's update messages.
+  costmap_2d::Costmap2D* getCostmap(std::vector<int>* changed_rects = NULL, bool* whole_grid = NULL) {
+    double origin[2];
+    navgpu_costmap_get_origin(handle_, origin);
+    // the device grid rolled (Costmap2D::updateOrigin, costmap_2d.cpp:264-313): the host copy only takes the new
+    // origin; the cells that moved are among the tiles the download below rewrites
+    if (origin[0] != host_.getOriginX() || origin[1] != host_.getOriginY()) host_.setOrigin(origin[0], origin[1]);
+    int n = 0;
+    int* rects = NULL;
+    int capacity = 0;
+    if (changed_rects) {
+      changed_rects->resize(4 * kMaxRects);
+      rects = changed_rects->data();
+      capacity = kMaxRects;
     }
+    if (!check(navgpu_costmap_get_changed(handle_, host_.getCharMap(), host_.getSizeInCellsX(), rects, capacity, &n, NULL)))
+      return NULL;
+    const bool whole = n > capacity || (n == 1 && rects && rects[2] - rects[0] == (int)host_.getSizeInCellsX() &&
+                                        rects[3] - rects[1] == (int)host_.getSizeInCellsY());
+    if (changed_rects) changed_rects->resize(whole ? 0 : 4 * size_t(n));
+    if (whole_grid) *whole_grid = whole;
+    navgpu_costmap_last_window(handle_, bounds_);
     return &host_;
   }
   navgpu_costmap* handle() { return handle_; }
@@ -154,9 +170,16 @@ class GpuLayeredCostmap {
     status_ = rc;
     return rc == NAVGPU_OK;
   }
+  // Costmap2D whose origin can follow the device grid without its own copy of updateOrigin's cell shuffle
+  struct HostCostmap : public costmap_2d::Costmap2D {
+    HostCostmap(unsigned int sx, unsigned int sy, double res, double ox, double oy, unsigned char def)
+        : costmap_2d::Costmap2D(sx, sy, res, ox, oy, def) {}
+    void setOrigin(double ox, double oy) { origin_x_ = ox; origin_y_ = oy; }
+  };
+  enum { kMaxRects = 2048 };
   navgpu_costmap* handle_;
   bool host_pinned_;
-  costmap_2d::Costmap2D host_;
+  HostCostmap host_;
   int bounds_[4];
   int status_;
 };

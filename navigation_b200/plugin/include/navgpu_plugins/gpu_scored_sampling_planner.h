@@ -63,6 +63,7 @@ class GpuScoredSamplingPlanner : public base_local_planner::TrajectorySearch {
 
  private:
   bool ensureHandle();
+  void firstLoopVelocity(float v[3]) const;
   navgpu_dwa* handle_;
   navgpu_dwa_config config_;
   costmap_2d::Costmap2D* costmap_;
@@ -72,6 +73,7 @@ class GpuScoredSamplingPlanner : public base_local_planner::TrajectorySearch {
   double pose_[3], vel_[3];
   std::vector<double> footprint_xy_, plan_xy_, plan_pose_;
   std::vector<double> all_costs_, points_;
+  std::vector<float> samples_;
   navgpu_dwa_result result_;
   int last_status_;
 };

@@ -101,6 +101,14 @@ void GpuScoredSamplingPlanner::setState(double x, double y, double yaw, double v
 bool GpuScoredSamplingPlanner::checkTrajectory(double x, double y, double yaw, double vx, double vy, double vyaw,
                                                double sx, double sy, double syaw, double* cost_out) {
   if (!ensureHandle()) return false;
+  // DWAPlanner::checkTrajectory is LatchedStopRotateController's collision check (dwa_planner_ros.cpp:271-288) and runs
+  // on cycles WITHOUT a findBestPath: the critics must see the costmap as it is now (dwa_planner.cpp:118-122), not the
+  // snapshot of the last search.  The MapGrid critics keep their last prepare(), like the reference's.
+  last_status_ = navgpu_dwa_set_costmap(handle_, costmap_->getCharMap(), costmap_->getOriginX(), costmap_->getOriginY());
+  if (last_status_ != NAVGPU_OK) {
+    ROS_ERROR("GpuScoredSamplingPlanner: navgpu_dwa_set_costmap failed (%d): %s", last_status_, navgpu_last_error());
+    return false;
+  }
   const double pose[3] = {x, y, yaw}, vel[3] = {vx, vy, vyaw}, samp[3] = {sx, sy, syaw};
   double cost = -1.0;
   last_status_ = navgpu_dwa_check_trajectory(handle_, pose, vel, samp, footprint_xy_.empty() ? NULL : footprint_xy_.data(),
@@ -112,6 +120,20 @@ bool GpuScoredSamplingPlanner::checkTrajectory(double x, double y, double yaw, d
   if (cost_out) *cost_out = cost;
   if (cost < 0) ROS_WARN("Invalid Trajectory %f, %f, %f, cost: %f", sx, sy, syaw, cost);
   return cost >= 0;
+}
+
+// SimpleTrajectoryGenerator::generateTrajectory's first computeNewVelocities step without use_dwa
+// (simple_trajectory_generator.cpp:203-227, 265-276): float state, double time step
+void GpuScoredSamplingPlanner::firstLoopVelocity(float v[3]) const {
+  const double vmag = hypot((double)v[0], (double)v[1]);
+  const int num_steps = (int)ceil(std::max(vmag * config_.sim_time / config_.sim_granularity,
+                                           fabs((double)v[2]) * config_.sim_time / config_.angular_sim_granularity));
+  if (num_steps <= 0) return;
+  const double dt = config_.sim_time / num_steps;
+  const float cur[3] = {(float)vel_[0], (float)vel_[1], (float)vel_[2]};
+  const float acc[3] = {(float)config_.acc_lim_x, (float)config_.acc_lim_y, (float)config_.acc_lim_theta};
+  for (int k = 0; k < 3; ++k)
+    v[k] = cur[k] < v[k] ? (float)std::min((double)v[k], cur[k] + acc[k] * dt) : (float)std::max((double)v[k], cur[k] - acc[k] * dt);
 }
 
 bool GpuScoredSamplingPlanner::findBestTrajectory(base_local_planner::Trajectory& traj,
@@ -145,10 +167,22 @@ bool GpuScoredSamplingPlanner::findBestTrajectory(base_local_planner::Trajectory
     // the reference copies every generated trajectory with its reported cost (simple_scored_sampling_planner.cpp
     // :106-109); samples its generator rejects do not appear (NaN here).  Points of the losers are not materialised.
     all_explored->clear();
+    int32_t counts[3] = {0, 0, 0};
+    samples_.resize(size_t(nx + 1) + (ny + 1) + (nth + 1));
+    navgpu_dwa_get_samples(handle_, counts, samples_.data(), (int)samples_.size());
+    const float* xs = samples_.data();
+    const float* ys = xs + counts[0];
+    const float* ths = ys + counts[1];
     for (int i = 0; i < result_.n_samples; ++i) {
       if (std::isnan(all_costs_[i])) continue;
       base_local_planner::Trajectory t;
       t.cost_ = all_costs_[i];
+      // traj.xv_, yv_, thetav_ as generateTrajectory sets them (simple_trajectory_generator.cpp:218-227): the sample
+      // itself with use_dwa, else the velocity after the first acceleration step
+      const int ith = i % counts[2], iy = (i / counts[2]) % counts[1], ix = i / (counts[2] * counts[1]);
+      float v[3] = {xs[ix], ys[iy], ths[ith]};
+      if (!config_.use_dwa) firstLoopVelocity(v);
+      t.xv_ = v[0]; t.yv_ = v[1]; t.thetav_ = v[2];
       all_explored->push_back(t);
     }
   }

@@ -3,6 +3,8 @@
 Loads either checker:
     load("port")       -> oracle/libnavoracle.so   (our CPU restatement)
     load("reference")  -> oracle/_ref/libnavref.so (the reference's own compiled sources; may be absent)
+    load("reference_hoisted") -> oracle/_ref/libnavref_hoisted.so (the same with map_grid.cpp:106 reading the default
+                          value without copying the costmap: timing baseline only, see oracle/Makefile)
 Nothing under navigation_b200/ imports this module.
 """
 import ctypes as C
@@ -145,12 +147,13 @@ def _declare(lib, prefix):
 
 
 def build(kind="port"):
-    target = {"port": "oracle", "reference": "ref"}[kind]
+    target = {"port": "oracle", "reference": "ref", "reference_hoisted": "ref_hoisted"}[kind]
     subprocess.check_call(["make", "-s", "-C", HERE, target])
 
 
 def lib_path(kind):
-    return os.path.join(HERE, "libnavoracle.so") if kind == "port" else os.path.join(HERE, "_ref", "libnavref.so")
+    return {"port": os.path.join(HERE, "libnavoracle.so"), "reference": os.path.join(HERE, "_ref", "libnavref.so"),
+            "reference_hoisted": os.path.join(HERE, "_ref", "libnavref_hoisted.so")}[kind]
 
 
 def available(kind):

@@ -7,7 +7,8 @@
 //   A1  costmap_2d::LayeredCostmap (reference) + test grid layer + reference costmap_2d::InflationLayer
 //       versus the same LayeredCostmap + the same grid layer + navgpu_plugins::GpuInflationLayer as the plugin:
 //       master grids must be identical over several cycles (full window, sub-window, parameter change).
-//   A2  navgpu_plugins::GpuLayeredCostmap (whole stack on the device) versus the reference stack.
+//   A2  navgpu_plugins::GpuLayeredCostmap (whole stack on the device) versus the reference stack over several cycles,
+//       the host Costmap2D kept in sync by changed tiles only (updateMapAsync + getCostmap, skipped downloads).
 //   B   navgpu_plugins::GpuScoredSamplingPlanner as a base_local_planner::TrajectorySearch versus the reference's
 //       generator + critics + SimpleScoredSamplingPlanner wired like DWAPlanner (through libnavref's C API).
 //   C   navgpu_plugins::GpuTrajectoryPlanner versus the reference's base_local_planner::TrajectoryPlanner, both
@@ -17,6 +18,10 @@
 //   D   navgpu_plugins::GpuLayeredCostmap fed with LaserScans (setLaserScans: projection, transform and height filter
 //       on the device) versus the checker's stack (the reference's LayeredCostmap + its own raytraceLine / MarkCell
 //       behind libnavref's C API) fed with the clouds of the restated ingest path: master grids over 3 cycles.
+//   E   navgpu_plugins::GpuTrajectoryCostFunction as THE critic of the reference's own SimpleScoredSamplingPlanner fed
+//       by the reference's own SimpleTrajectoryGenerator, versus the same planner with the reference's six critics
+//       wired like DWAPlanner: same winner, same cost; and the batched scoreTrajectories on every explored trajectory
+//       versus the six reference critics' scaled sum.
 // Prints one line per check and exits non-zero on any mismatch.  Test infrastructure, not product code.
 #include <chrono>
 #include <cmath>
@@ -34,9 +39,16 @@
 #include <navgpu_plugins/gpu_inflation_layer.h>
 #include <navgpu_plugins/gpu_layered_costmap.h>
 #include <navgpu_plugins/gpu_scored_sampling_planner.h>
+#include <navgpu_plugins/gpu_trajectory_cost_function.h>
 #include <navgpu_plugins/gpu_trajectory_planner.h>
 
 #include <base_local_planner/costmap_model.h>
+#include <base_local_planner/local_planner_limits.h>
+#include <base_local_planner/map_grid_cost_function.h>
+#include <base_local_planner/obstacle_cost_function.h>
+#include <base_local_planner/oscillation_cost_function.h>
+#include <base_local_planner/simple_scored_sampling_planner.h>
+#include <base_local_planner/simple_trajectory_generator.h>
 #include <base_local_planner/trajectory_planner.h>
 
 #include "oracle_api.h"
@@ -193,6 +205,29 @@ void testFusedStack() {
     return;
   }
   report("A2 GpuLayeredCostmap vs reference LayeredCostmap", countDiff(ref.lc.getCostmap()->getCharMap(), out->getCharMap(), n), n);
+  // further cycles: sub-window changes, the host copy refreshed by changed tiles only -- after every cycle, and after
+  // two cycles without a download in between
+  long bad = 0;
+  std::vector<unsigned char> map2 = map;
+  for (int c = 0; c < 5; ++c) {
+    const unsigned x = 30 + 60 * c, y = 40 + 45 * c;
+    for (unsigned j = y; j < y + 9; ++j) memset(&map2[size_t(j) * sx + x], c % 2 ? 0 : 254, 14);
+    ref.grid->setData(map2);
+    gpu.setLayerCosts(s, map2.data());
+    ref.lc.updateMap(5.0, 5.0, 0.0);
+    if (!gpu.updateMapAsync(5.0, 5.0, 0.0)) ++bad;
+    if (c == 2) continue;  // no getCostmap this cycle: the next one must still bring the host copy up to date
+    std::vector<int> rects;
+    bool whole = false;
+    out = gpu.getCostmap(&rects, &whole);
+    if (!out) { ++bad; continue; }
+    bad += countDiff(ref.lc.getCostmap()->getCharMap(), out->getCharMap(), n);
+    unsigned x0, xn, y0, yn;
+    gpu.getBounds(&x0, &xn, &y0, &yn);
+    if (x0 != 0 || xn != sx || y0 != 0 || yn != sy) ++bad;  // setData touches the whole layer
+    if (whole || rects.size() / 4 > 24) ++bad;               // a 14 x 9 block and its inflation: a handful of tiles
+  }
+  report("A2 five more cycles, host Costmap2D refreshed by changed tiles", bad, 5 * (long)n);
 }
 
 void testScoredSamplingPlanner() {
@@ -261,8 +296,176 @@ void testScoredSamplingPlanner() {
       vel[0] = rr.xv; vel[1] = rr.yv; vel[2] = rr.thetav;
     }
   }
-  navo_dwa_destroy(refp);
   report("B  GpuScoredSamplingPlanner vs reference DWA search, 6 cycles", bad, cycles);
+  // DWAPlanner::checkTrajectory on cycles without a search (LatchedStopRotateController, dwa_planner_ros.cpp:271-288):
+  // the costmap changed since the last findBestTrajectory -- a wall appears right in front of the robot
+  {
+    long bad2 = 0;
+    const double samp[3] = {0.5, 0.0, 0.0};
+    double rc0 = 0, gc0 = 0, rc1 = 0, gc1 = 0;
+    rc0 = navo_dwa_check_trajectory(refp, pose, vel, samp, fp_xy.data(), 4);
+    const bool g0 = gpu.checkTrajectory(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], samp[0], samp[1], samp[2], &gc0);
+    const unsigned wx = (unsigned)((pose[0] + 0.45) / res), wy = (unsigned)(pose[1] / res);
+    for (unsigned y = wy - 8; y < wy + 8; ++y) memset(local->getCharMap() + y * n + wx, 254, 3);
+    navo_dwa_set_costmap(refp, local->getCharMap(), 0.0, 0.0);
+    rc1 = navo_dwa_check_trajectory(refp, pose, vel, samp, fp_xy.data(), 4);
+    const bool g1 = gpu.checkTrajectory(pose[0], pose[1], pose[2], vel[0], vel[1], vel[2], samp[0], samp[1], samp[2], &gc1);
+    if (g0 != (rc0 >= 0) || g1 != (rc1 >= 0) || std::fabs(gc0 - rc0) > 1e-5 * std::fabs(rc0) || gc1 != rc1 || !(rc0 >= 0) || rc1 >= 0) {
+      ++bad2;
+      printf("  checkTrajectory: reference %.9g -> %.9g, gpu %.9g -> %.9g\n", rc0, rc1, gc0, gc1);
+    }
+    report("B  checkTrajectory sees the costmap as it is now", bad2, 2);
+  }
+  navo_dwa_destroy(refp);
+}
+
+// The reference's DWAPlanner wiring (dwa_planner.cpp:116-182, 52-112) with its own classes
+struct RefDwa {
+  base_local_planner::LocalPlannerLimits limits;
+  base_local_planner::ObstacleCostFunction obstacle;
+  base_local_planner::MapGridCostFunction path, goal, goal_front, alignment;
+  base_local_planner::OscillationCostFunction oscillation;
+  base_local_planner::SimpleTrajectoryGenerator generator;
+  std::vector<base_local_planner::TrajectoryCostFunction*> critics;
+  RefDwa(Costmap2D* cm, const navgpu_dwa_config& c)
+      : obstacle(cm), path(cm), goal(cm, 0.0, 0.0, true), goal_front(cm, 0.0, 0.0, true), alignment(cm) {
+    goal_front.setStopOnFailure(false);
+    alignment.setStopOnFailure(false);
+    limits.max_trans_vel = c.max_trans_vel; limits.min_trans_vel = c.min_trans_vel;
+    limits.max_vel_x = c.max_vel_x; limits.min_vel_x = c.min_vel_x;
+    limits.max_vel_y = c.max_vel_y; limits.min_vel_y = c.min_vel_y;
+    limits.max_rot_vel = c.max_rot_vel; limits.min_rot_vel = c.min_rot_vel;
+    limits.acc_lim_x = c.acc_lim_x; limits.acc_lim_y = c.acc_lim_y; limits.acc_lim_theta = c.acc_lim_theta;
+    generator.setParameters(c.sim_time, c.sim_granularity, c.angular_sim_granularity, c.use_dwa != 0, c.sim_period);
+    const double res = cm->getResolution();
+    path.setScale(res * c.path_distance_bias * 0.5);
+    alignment.setScale(res * c.path_distance_bias * 0.5);
+    goal.setScale(res * c.goal_distance_bias * 0.5);
+    goal_front.setScale(res * c.goal_distance_bias * 0.5);
+    obstacle.setScale(res * c.occdist_scale);
+    oscillation.setOscillationResetDist(c.oscillation_reset_dist, c.oscillation_reset_angle);
+    oscillation.resetOscillationFlags();
+    goal_front.setXShift(c.forward_point_distance);
+    alignment.setXShift(c.forward_point_distance);
+    obstacle.setParams(c.max_trans_vel, c.max_scaling_factor, c.scaling_speed);
+    obstacle.setSumScores(c.sum_scores != 0);
+    critics.push_back(&oscillation);
+    critics.push_back(&obstacle);
+    critics.push_back(&goal_front);
+    critics.push_back(&alignment);
+    critics.push_back(&path);
+    critics.push_back(&goal);
+  }
+  // DWAPlanner::updatePlanAndLocalCosts (:240-286)
+  void setPlan(const double pose[3], const std::vector<geometry_msgs::PoseStamped>& plan, double fpd, double cheat, double res,
+               double pdist) {
+    path.setTargetPoses(plan);
+    goal.setTargetPoses(plan);
+    const geometry_msgs::PoseStamped g = plan.back();
+    Eigen::Vector3f pos(pose[0], pose[1], pose[2]);
+    const double sq_dist = (pos[0] - g.pose.position.x) * (pos[0] - g.pose.position.x) +
+                           (pos[1] - g.pose.position.y) * (pos[1] - g.pose.position.y);
+    std::vector<geometry_msgs::PoseStamped> front = plan;
+    const double a = atan2(g.pose.position.y - pos[1], g.pose.position.x - pos[0]);
+    front.back().pose.position.x = front.back().pose.position.x + fpd * cos(a);
+    front.back().pose.position.y = front.back().pose.position.y + fpd * sin(a);
+    goal_front.setTargetPoses(front);
+    if (sq_dist > fpd * fpd * cheat) {
+      alignment.setScale(res * pdist * 0.5);
+      alignment.setTargetPoses(plan);
+    } else {
+      alignment.setScale(0.0);
+    }
+  }
+  // SimpleScoredSamplingPlanner::scoreTrajectory (:50-79) without the early exit
+  double fullScore(base_local_planner::Trajectory& t) {
+    double total = 0.0;
+    for (size_t k = 0; k < critics.size(); ++k) {
+      if (critics[k]->getScale() == 0) continue;
+      double c = critics[k]->scoreTrajectory(t);
+      if (c < 0) return c;
+      if (c != 0) c *= critics[k]->getScale();
+      total += c;
+    }
+    return total;
+  }
+};
+
+void testTrajectoryCostFunction() {
+  const unsigned n = 120;
+  const double res = 0.05;
+  Stack ref(n, n, res, new costmap_2d::InflationLayer);
+  std::vector<unsigned char> g(size_t(n) * n, 0);
+  for (unsigned y = 26; y < 29; ++y) memset(&g[y * n], 254, n);
+  for (unsigned y = 91; y < 94; ++y) memset(&g[y * n], 254, n);
+  for (unsigned y = 52; y < 58; ++y) memset(&g[y * n + 84], 254, 6);
+  ref.grid->setData(g);
+  ref.lc.updateMap(3.0, 3.0, 0.0);
+  Costmap2D* local = ref.lc.getCostmap();
+
+  navgpu_dwa_config gc = navgpu_plugins::GpuScoredSamplingPlanner::defaultConfig();
+  gc.vx_samples = 12; gc.vy_samples = 3; gc.vth_samples = 15;
+  RefDwa rd(local, gc);
+  navgpu_plugins::GpuTrajectoryCostFunction gpu_costs(gc, local);
+  base_local_planner::TrajectoryCostFunction* as_critic = &gpu_costs;  // used through the reference's interface
+
+  std::vector<base_local_planner::TrajectorySampleGenerator*> gens(1, &rd.generator);
+  base_local_planner::SimpleScoredSamplingPlanner ref_planner(gens, rd.critics);
+  std::vector<base_local_planner::TrajectoryCostFunction*> one(1, as_critic);
+  base_local_planner::SimpleScoredSamplingPlanner gpu_planner(gens, one);
+
+  std::vector<geometry_msgs::PoseStamped> plan;
+  for (int i = 0; i < 120; ++i) {
+    geometry_msgs::PoseStamped p;
+    p.pose.position.x = 1.0 + 0.05 * i;
+    p.pose.position.y = 3.0;
+    plan.push_back(p);
+  }
+  const std::vector<geometry_msgs::Point> fp = squareFootprint(0.3);
+  rd.obstacle.setFootprint(fp);
+  gpu_costs.setFootprint(fp);
+  Eigen::Vector3f vsamples(gc.vx_samples, gc.vy_samples, gc.vth_samples);
+
+  double pose[3] = {1.5, 3.0, 0.0}, vel[3] = {0.3, 0.0, 0.0};
+  long bad = 0, cycles = 0, bad_batch = 0, scored = 0;
+  for (int c = 0; c < 6; ++c, ++cycles) {
+    rd.setPlan(pose, plan, gc.forward_point_distance, gc.cheat_factor, res, gc.path_distance_bias);
+    gpu_costs.setPlan(pose[0], pose[1], pose[2], plan);
+    Eigen::Vector3f pos(pose[0], pose[1], pose[2]), v(vel[0], vel[1], vel[2]);
+    Eigen::Vector3f goal(plan.back().pose.position.x, plan.back().pose.position.y, 0.0f);
+    base_local_planner::Trajectory rt, gt;
+    std::vector<base_local_planner::Trajectory> explored;
+    rd.generator.initialise(pos, v, goal, &rd.limits, vsamples);
+    rt.cost_ = -7;
+    ref_planner.findBestTrajectory(rt, &explored);
+    rd.generator.initialise(pos, v, goal, &rd.limits, vsamples);
+    gt.cost_ = -7;
+    gpu_planner.findBestTrajectory(gt, NULL);
+    bool same = rt.cost_ == gt.cost_ && rt.xv_ == gt.xv_ && rt.yv_ == gt.yv_ && rt.thetav_ == gt.thetav_ &&
+                rt.getPointsSize() == gt.getPointsSize();
+    // the batched call on everything the reference explored, against the six critics' full scaled sum
+    std::vector<double> costs;
+    if (!gpu_costs.scoreTrajectories(explored, &costs)) same = false;
+    for (size_t i = 0; i < explored.size() && i < costs.size(); ++i, ++scored) {
+      const double want = rd.fullScore(explored[i]);
+      if (!(costs[i] == want || std::fabs(costs[i] - want) <= 1e-5 * std::fabs(want))) ++bad_batch;
+    }
+    rd.oscillation.updateOscillationFlags(pos, &rt, gc.min_trans_vel);
+    gpu_costs.updateOscillationFlags(pose[0], pose[1], pose[2], &gt);
+    if (!same) {
+      ++bad;
+      printf("  cycle %d: reference cost %.9g v (%.6g %.6g %.6g) %u pts / gpu critic cost %.9g v (%.6g %.6g %.6g) %u pts\n", c,
+             rt.cost_, rt.xv_, rt.yv_, rt.thetav_, rt.getPointsSize(), gt.cost_, gt.xv_, gt.yv_, gt.thetav_, gt.getPointsSize());
+    }
+    if (rt.cost_ >= 0) {  // alternate the direction to exercise the oscillation flags
+      double x, y, th;
+      rt.getPoint(std::min(2u, rt.getPointsSize() - 1), x, y, th);
+      pose[0] = x; pose[1] = y; pose[2] = th;
+      vel[0] = (c % 2 ? 1 : -1) * rt.xv_ * 0.2; vel[1] = rt.yv_; vel[2] = -rt.thetav_;
+    }
+  }
+  report("E  SimpleScoredSamplingPlanner + GpuTrajectoryCostFunction vs + 6 reference critics", bad, cycles);
+  report("E  batched scoreTrajectories vs the reference critics' scaled sum", bad_batch, scored);
 }
 
 void testTrajectoryPlanner() {
@@ -438,6 +641,7 @@ int main() {
   testScoredSamplingPlanner();
   testTrajectoryPlanner();
   testLaserScanIngest();
+  testTrajectoryCostFunction();
   timeFusedStackEndToEnd();
   printf("%s\n", failures ? "DROP-IN FAILED" : "DROP-IN OK");
   return failures ? 1 : 0;

@@ -124,7 +124,8 @@ def select_inflation(cm, layer, which, seed=0):
         cm.set_inflation_mode(layer, mode)
 
 
-def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False, inflation=None, inflation_seed=0):
+def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False, inflation=None, inflation_seed=0,
+                         on_cycle=None):
     """Multi-cycle LayeredCostmap scenario; returns per cycle (window, master, obstacle-layer grid, origin).
     `inflation` (a key of INFLATION_SEMANTICS) selects which execution of InflationLayer::updateCosts runs.
 
@@ -160,6 +161,8 @@ def run_costmap_scenario(api, seed, cycles=4, max_size=90, tie_free=False, infla
         rx += rng.uniform(-0.5, 0.5)
         ry += rng.uniform(-0.5, 0.5)
         w = cm.update_map(rx, ry, float(rng.uniform(-3, 3)))
+        if on_cycle is not None:
+            on_cycle(cm, cyc, w)
         trace.append((w, cm.get().copy(), cm.get_layer(ids["obstacle"]).copy(), cm.origin()))
     return trace
 

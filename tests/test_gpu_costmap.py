@@ -545,3 +545,102 @@ def test_voxel_layer_matches_checker(cuda, port, seed):
             assert diff.sum() <= max(3, 2e-3 * diff.size) and (x[1][diff] > y[1][diff]).all()
         else:
             assert not diff.any(), f"cycle {cyc}: master differs in {diff.sum()} cells"
+
+
+# ---- the host mirror (navgpu_costmap_get_changed): byte-identical to the device master grid after every call ----------
+@pytest.mark.parametrize("seed", list(range(100, 112)) + list(range(0, 8)))
+def test_host_mirror_tracks_the_master_grid(cuda, seed):
+    """Multi-cycle scenarios (rolling and fixed windows, every merge policy, odd map sizes): after each cycle one
+    navgpu_costmap_get_changed leaves the host mirror equal to the device grid, and the window it reports is the
+    cycle's."""
+    state = {}
+
+    def on_cycle(cm, cyc, w):
+        if "m" not in state:  # starts as garbage: the first call must bring everything
+            state["m"] = np.full((cm.size_y, cm.size_x), 7, np.uint8)
+        n, nbytes, rects = cm.get_changed(state["m"], max_rects=8192)
+        assert cm.last_window() == w
+        assert np.array_equal(state["m"], cm.get()), f"mirror differs from the master grid in cycle {cyc}"
+        if cyc > 0:  # whole tiles travel (2 KB + their number each), or the plain grid
+            assert nbytes == cm.size_x * cm.size_y or nbytes <= n * (128 * 16 + 4) + 64
+        # a second call right away finds nothing to move
+        n2, nbytes2, _ = cm.get_changed(state["m"])
+        assert n2 == 0 and nbytes2 <= 64
+
+    sc.run_costmap_scenario(cuda, seed, tie_free=seed >= 100, on_cycle=on_cycle)
+
+
+def test_host_mirror_moves_only_changed_tiles(cuda):
+    """The C3 recipe at 1000^2 with the observation set changing every cycle: the mirror stays identical while only
+    the tiles around the scans cross PCIe; rects cover exactly the cells that changed."""
+    size = 1000
+    sets = [synth.warehouse_c3(size=size, n_obs=4, cycle=c) for c in range(4)]
+    static, _, _, fp = sets[0]
+    cm = cuda.costmap(size, size, 0.05)
+    s = cm.add_grid_layer(0)
+    o = cm.add_obstacle_layer(1, True, 2.0)
+    cm.add_inflation_layer(1.0, 10.0)
+    cm.set_footprint(fp)
+    cm.set_grid_layer(s, static)
+    mirror = np.zeros((size, size), np.uint8)
+    prev = None
+    for cyc in range(6):
+        _, obs, robot, _ = sets[cyc % 4]
+        cm.set_observations(o, obs)
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        cm.update_map_async(*robot)
+        n, nbytes, rects = cm.get_changed(mirror, max_rects=4096)
+        now = cm.get()
+        assert np.array_equal(mirror, now)
+        assert cm.last_window() == (0, size, 0, size)
+        if prev is None:
+            assert nbytes == size * size
+        else:
+            changed = prev != now
+            covered = np.zeros_like(changed)
+            for x0, y0, xn, yn in rects:
+                covered[y0:yn, x0:xn] = True
+                assert changed[y0:yn, x0:xn].any(), "a tile without a changed cell was moved"
+            assert not (changed & ~covered).any()
+            assert 0 < n < 0.25 * (size / 128) * (size / 16)
+            assert nbytes < 0.3 * size * size
+        prev = now
+
+
+def test_host_mirror_whole_grid_paths(cuda):
+    """Everything changes (navgpu_costmap_set with unrelated bytes): more tiles than the staging holds -> plain copy;
+    another host buffer -> plain copy; navgpu_costmap_mirror_invalidate -> plain copy; odd sizes (333 x 77)."""
+    rng = np.random.default_rng(5)
+    sx, sy = 333, 77
+    cm = cuda.costmap(sx, sy, 0.05)
+    a = np.zeros((sy, sx), np.uint8)
+    g = rng.integers(0, 256, (sy, sx), dtype=np.uint8)
+    cm.set(g)
+    assert cm.get_changed(a)[1] == sx * sy and np.array_equal(a, g)
+    g2 = g.copy()
+    g2[5, 300:] = 9          # the last, partial tile column
+    g2[76, 0] = 3            # the last, partial tile row
+    cm.set(g2)
+    n, nbytes, rects = cm.get_changed(a, max_rects=16)
+    assert n == 2 and np.array_equal(a, g2)
+    assert sorted(map(tuple, rects)) == [(0, 64, 128, 77), (256, 0, 333, 16)]
+    g3 = rng.integers(0, 256, (sy, sx), dtype=np.uint8)
+    cm.set(g3)
+    n, nbytes, _ = cm.get_changed(a)
+    assert np.array_equal(a, g3)
+    b = np.zeros((sy, sx), np.uint8)
+    assert cm.get_changed(b)[1] == sx * sy and np.array_equal(b, g3)
+    b[:] = 0
+    cm.mirror_invalidate()
+    assert cm.get_changed(b)[1] == sx * sy and np.array_equal(b, g3)
+    big = cuda.costmap(2000, 1500, 0.05)
+    m = np.zeros((1500, 2000), np.uint8)
+    big.get_changed(m)
+    gb = rng.integers(0, 256, (1500, 2000), dtype=np.uint8)
+    big.set(gb)
+    n, nbytes, _ = big.get_changed(m)   # 1504 tiles changed > staging capacity: whole-grid copy, still exact
+    assert nbytes == 2000 * 1500 and np.array_equal(m, gb)
+    gb[700:710, 900:1000] ^= 1
+    big.set(gb)
+    n, nbytes, _ = big.get_changed(m)
+    assert n <= 4 and np.array_equal(m, gb)

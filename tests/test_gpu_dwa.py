@@ -216,3 +216,50 @@ def test_device_side_exchange_on_one_gpu(cuda, port, world):
         assert all(d.oscillation_mask() == whole.oscillation_mask() for d in ranks)
         vel = np.array([rw["xv"] * (-1 if cyc % 2 else 1), rw["yv"], -rw["thetav"]])
         pose = pose + np.array([0.01 * vel[0], 0, 0.01 * vel[2]])
+
+
+def test_trajectory_cost_function_backend(cuda, port):
+    """navgpu_dwa_prepare + navgpu_dwa_score_trajectories (the batched base_local_planner::TrajectoryCostFunction): the
+    winner of a search, handed back as an explicit trajectory, scores exactly its search cost; the six terms add up in
+    DWAPlanner's critic order; the rejecting codes of the reference's critics come out for off-map / lethal / empty
+    inputs (the C++ adapter is checked against the reference's own critics in tests/cpp/dropin_harness.cpp section E)."""
+    d, pose, vel = c2_setup(cuda, port)
+    r = d.find_best_path(pose, vel, sc.PENTAGON)
+    assert r["ok"]
+    d2, _, _ = c2_setup(cuda, port)
+    d2.prepare()
+    win_v = (r["xv"], r["yv"], r["thetav"])
+    off_map = np.array([[1.5, 3.0, 0.0], [6.5, 3.0, 0.0]])         # second point outside the 6 m map
+    in_wall = np.array([[1.5, 3.0, 0.0], [1.5, 1.35, 0.0]])         # centre on the corridor wall (rows 26..28)
+    empty = np.zeros((0, 3))
+    costs, terms = d2.score_trajectories([r["points"], off_map, in_wall, empty, r["points"][:1]],
+                                         [win_v, win_v, win_v, win_v, win_v], sc.PENTAGON, want_terms=True)
+    assert costs[0] == r["cost"]
+    assert terms[0, 0] == 0 and (terms[0] >= 0).all() and costs[0] == np.add.reduce(terms[0])  # left-to-right sum
+    assert costs[1] == -6.0 and costs[2] == -6.0
+    assert costs[3] == 0.0
+    assert costs[4] >= 0
+    # an empty footprint answers -9 (obstacle_cost_function.cpp:78-82); a point robot (< 3 vertices) looks at the centre
+    assert d2.score_trajectories([r["points"]], [win_v], np.zeros((0, 2)))[0] == -9.0
+    assert d2.score_trajectories([in_wall], [win_v], [(0.0, 0.0)])[0] == -6.0
+    # latched oscillation flags reject by the sign of the trajectory's velocity (oscillation_cost_function.cpp:166-176)
+    d2.update_oscillation(pose, 1.0, 0.3, 0.0, 0.0)    # forward, then backward: forward_neg_only latches (:101-164)
+    d2.update_oscillation(pose, 1.0, -0.2, 0.0, 0.0)
+    assert d2.oscillation_mask() == 2
+    c = d2.score_trajectories([r["points"], r["points"]], [(0.3, 0.0, 0.0), (-0.3, 0.0, 0.0)], sc.PENTAGON)
+    assert c[0] == -5.0 and c[1] == r["cost"]
+    # 1000 trajectories in one launch: every sample's winner-style rescoring is independent of its batch position
+    many = d2.score_trajectories([r["points"]] * 1000, [(-0.3, 0.0, 0.0)] * 1000, sc.PENTAGON)
+    assert (many == r["cost"]).all()
+
+
+def test_all_explored_velocities_available(cuda, port):
+    """navgpu_dwa_get_samples: the per-axis samples behind all_explored's xv_/yv_/thetav_; the winner's velocities are
+    the samples its index names."""
+    d, pose, vel = c2_setup(cuda, port, vy_samples=3, max_vel_y=0.1, min_vel_y=-0.1)
+    r = d.find_best_path(pose, vel, sc.PENTAGON)
+    xs, ys, ths = d.samples()
+    assert len(xs) * len(ys) * len(ths) == r["n_samples"]
+    i = r["best_index"]
+    ith, iy, ix = i % len(ths), (i // len(ths)) % len(ys), i // (len(ths) * len(ys))
+    assert (float(xs[ix]), float(ys[iy]), float(ths[ith])) == (r["xv"], r["yv"], r["thetav"])

@@ -78,3 +78,41 @@ def test_fleet_inflation_does_not_leak_between_robots(cuda):
     fleet.step(np.tile([1.0, 3.0, 0.0], (3, 1)), np.tile([0.2, 0.0, 0.0], (3, 1)))
     assert fleet.costmap(1).max() == 0
     assert fleet.costmap(0)[100, 5] > 0 and fleet.costmap(2)[19, 5] > 0
+
+
+def test_c5_full_fleet_sampled_parity(cuda, port):
+    """The benched configuration itself: 4096 robots with bench.py's inputs (synth.fleet_robot(i), 20 x 1 x 20
+    samples), one navgpu_fleet_step; every 64th robot is replayed through the checker the way the reference would run
+    it (LayeredCostmap inflation, then DWAPlanner::findBestPath): inflated costmap ==, best sample index, sample counts,
+    oscillation mask ==, cost <= 1e-5 relative, velocities ==.  Robots the fleet reports without a valid trajectory
+    must have none in the checker either (the count bench.py prints as c5_valid_robots)."""
+    cfg = dict(vx_samples=20, vy_samples=1, vth_samples=20, max_vel_y=0.0, min_vel_y=0.0)
+    n = 4096
+    robots = [synth.fleet_robot(i) for i in range(n)]
+    fleet = cuda.fleet(n, 120, 120, 0.05, sc.PENTAGON, 0.55, 10.0, **cfg)
+    fleet.set_maps(np.stack([r["raw"] for r in robots]), np.array([r["origin"] for r in robots]))
+    poses = np.array([r["pose"] for r in robots])
+    vels = np.array([r["vel"] for r in robots])
+    fleet.set_plans(poses, [r["plan"] for r in robots])
+    out = fleet.step(poses, vels)
+    invalid = [i for i, g in enumerate(out) if g["cost"] < 0]
+    sample = sorted(set(range(0, n, 64)) | set(invalid[:24]))
+    exact = valid = 0
+    for i in sample:
+        grid, d = checker_robot(port, robots[i], cfg)
+        assert np.array_equal(fleet.costmap(i), grid), f"robot {i}: inflated local costmap differs"
+        d.set_plan(poses[i], robots[i]["plan"])
+        e = d.find_best_path(poses[i], vels[i], sc.PENTAGON)
+        g = out[i]
+        assert (g["best_index"], g["n_samples"], g["n_scored"]) == (e["best_index"], e["n_samples"], e["n_scored"]), \
+            f"robot {i}: {g} vs best {e['best_index']} cost {e['cost']}"
+        assert fleet.oscillation_mask(i) == d.oscillation_mask()
+        assert (g["cost"] >= 0) == bool(e["ok"]), f"robot {i}: fleet cost {g['cost']}, checker cost {e['cost']}"
+        if e["ok"]:
+            assert np.isclose(g["cost"], e["cost"], rtol=RTOL, atol=0)
+            assert (g["xv"], g["yv"], g["thetav"]) == (e["xv"], e["yv"], e["thetav"])
+            exact += g["cost"] == e["cost"]
+            valid += 1
+    assert valid >= 60 and exact >= 0.99 * valid
+    print(f"C5 full fleet: {n - len(invalid)} of {n} robots have a valid trajectory; {len(sample)} replayed through the "
+          f"checker ({min(24, len(invalid))} of them without one), {exact}/{valid} costs bit-equal")
