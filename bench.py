@@ -144,6 +144,174 @@ C4 = dict(n=120, resolution=0.05, vx_samples=200, vy_samples=20, vth_samples=200
 PENTAGON = [(-0.325, -0.325), (-0.325, 0.325), (0.325, 0.325), (0.46, 0.0), (0.325, -0.325)]
 
 
+C1 = dict(size=400, resolution=0.05, inscribed=0.325, inflation_radius=0.55, scaling=10.0)
+SQUARE = [(0.325, 0.325), (0.325, -0.325), (-0.325, -0.325), (-0.325, 0.325)]
+# k_dwa_score at C4: warp-level instructions per sweep from the ncu capture summarised in
+# profiles/ (smsp__inst_executed.sum), used for the issue-slot roofline of the DWA half
+DWA_C4_WARP_INSTRUCTIONS = 2_350_000_000
+DWA_BYTES_PER_TRAJECTORY = 20  # 12 B sample in + 8 B cost out
+
+
+def c1_stack(api, **kw):
+    """BASELINE.json configs[0]: InflationLayer on a synthetic 400x400 @0.05 static map, inscribed 0.325 / inflation
+    0.55 (R = 11), as a layered costmap (static layer + inflation)."""
+    from navigation_b200 import synth
+    g = synth.blocks_c1(C1["size"])
+    cm = api.costmap(C1["size"], C1["size"], C1["resolution"], **kw)
+    s = cm.add_grid_layer(0)
+    cm.add_inflation_layer(C1["inflation_radius"], C1["scaling"])
+    cm.set_footprint(SQUARE)
+    cm.set_grid_layer(s, g)
+    return cm, s, g
+
+
+def seam_numbers(api, master0, radius_m, device, reps):
+    """The costmap_2d::Layer plugin seam: navgpu_inflate_host = the body of GpuInflationLayer::updateCosts on the HOST
+    master grid LayeredCostmap owns (upload of the window +- 2R rows, sweep, download), whole-map window; wall time per
+    call with the master in ordinary pageable memory (what Costmap2D allocates) and page-locked (navgpu_host_register)."""
+    n = master0.shape[0]
+    R, costs, _ = api.build_cost_table(C1["resolution"], C1["inscribed"], radius_m, C1["scaling"])
+    out = {}
+    for name in ("pageable", "registered"):
+        master = master0.copy()
+        if name == "registered":
+            api.host_register(master)
+        for _ in range(2):
+            master[...] = master0
+            api.inflate_host(master, 0, 0, n, n, costs, R, device=device)
+        ts = []
+        for _ in range(reps):
+            master[...] = master0
+            t0 = time.perf_counter()
+            api.inflate_host(master, 0, 0, n, n, costs, R, device=device)
+            ts.append(time.perf_counter() - t0)
+        if name == "registered":
+            api.host_unregister(master)
+        out[f"inflate_host_{name}_ms"] = 1e3 * float(np.median(ts))
+    out["bytes_each_way"] = int(master0.size)
+    out["cell_inflation_radius"] = int(R)
+    return out, master
+
+
+def c1_numbers(api, torch, local_rank, reps):
+    """Config C1 on the device-resident path (static layer + inflation, full window, CUDA events, L2 flushed / hot) and
+    through the plugin seam."""
+    cm, s, g = c1_stack(api, device=local_rank)
+    n = C1["size"]
+    stream = torch.cuda.ExternalStream(cm.stream(), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    for _ in range(3):
+        cm.touch_grid_layer(s, 0, 0, n, n)
+        cm.update_map()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            a.record(stream)
+        cm.touch_grid_layer(s, 0, 0, n, n)
+        cm.update_map_async()
+        b.record(stream)
+    torch.cuda.synchronize()
+    cold = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    a, b = ev[0]
+    a.record(stream)
+    for _ in range(reps):
+        cm.touch_grid_layer(s, 0, 0, n, n)
+        cm.update_map_async()
+    b.record(stream)
+    torch.cuda.synchronize()
+    hot = a.elapsed_time(b) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cm.touch_grid_layer(s, 0, 0, n, n)
+        cm.update_map()
+    sync_ms = 1e3 * (time.perf_counter() - t0) / reps
+    seam, seam_out = seam_numbers(api, g, C1["inflation_radius"], local_rank, reps)
+    same = bool(np.array_equal(seam_out, cm.get()))
+    out = {"what": "BASELINE.json configs[0]: 400x400 @0.05 static map, inscribed 0.325 / inflation 0.55 (R = 11), "
+                   "full-window updateMap (static layer + inflation)",
+           "device_ms_l2_flushed": cold, "device_ms_hot": hot, "update_map_sync_call_ms": sync_ms,
+           "algorithmic_bytes": 2 * n * n, "hbm_frac_hot": 2 * n * n / (hot * 1e-3) / 1e9 / measured_peak_gbs()[0],
+           "plugin_seam": seam, "plugin_seam_equals_device_path": same}
+    return out
+
+
+def c1_cpu_numbers():
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.available("reference") else "port"
+    cm, s, g = c1_stack(pyoracle.load(kind))
+    n = C1["size"]
+    cm.update_map()
+    ts = []
+    for _ in range(5):
+        cm.touch_grid_layer(s, 0, 0, n, n)
+        t0 = time.perf_counter()
+        cm.update_map()
+        ts.append(time.perf_counter() - t0)
+    return {"kind": kind, "cores": 1, "update_map_ms": 1e3 * float(np.median(ts)),
+            "sample": "median of 5 full-window updates of the C1 stack, single thread"}
+
+
+def seam_c3_numbers(api, local_rank, reps=5):
+    """The same seam at C3 size: a 4000x4000 host master holding the static warehouse, R = 20."""
+    from navigation_b200 import synth
+    static, _, _, _ = synth.warehouse_c3(size=C3["size"], n_obs=1)
+    seam, _ = seam_numbers(api, static, C3["inflation_radius"], local_rank, reps)
+    return seam
+
+
+def dwa_prepare_cpu_numbers():
+    """MapGridCostFunction::prepare x 4 of a C2 findBestPath on one host core: as the reference is, and with the one
+    line of map_grid.cpp:106 that copy-constructs the whole Costmap2D per BFS cell replaced by a const_cast (the
+    `reference_hoisted` checker, oracle/Makefile) -- so that the GPU is not compared against that copy only."""
+    from oracle import pyoracle
+    out = {}
+    for kind, key in (("reference", ""), ("reference_hoisted", "_hoisted")):
+        if not pyoracle.available(kind):
+            continue
+        api = pyoracle.load(kind)
+        grid = inflate_local(api, local_map_c2())
+        d, pose, vel = dwa_setup(api, grid, C2)
+        d.find_best_path(pose, vel, PENTAGON)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            d.prepare_only()
+        out[f"prepare{key}_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+        t0 = time.perf_counter()
+        for _ in range(10):
+            d.find_best_path(pose, vel, PENTAGON)
+        out[f"c2_findBestPath{key}_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+    return out
+
+
+def _c4_worker(_):
+    from oracle import pyoracle
+    kind = "reference_hoisted" if pyoracle.available("reference_hoisted") else (
+        "reference" if pyoracle.available("reference") else "port")
+    api = pyoracle.load(kind)
+    grid = inflate_local(api, local_map_c2())
+    d4, pose, vel = dwa_setup(api, grid, dict(C4, vx_samples=C4["vx_samples"] // 4))
+    t0 = time.perf_counter()
+    r = d4.find_best_path(pose, vel, PENTAGON)
+    return time.perf_counter() - t0, int(r["n_samples"]), kind
+
+
+def c4_all_cores_numbers():
+    """C4 on every host core at once: one process per core, each scoring a quarter-size sweep (50 x 20 x 200 samples of
+    the same window) with the reference's code (the hoisted variant: prepare() is negligible either way at this
+    size); aggregate trajectories / s over the slowest process's time."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_c4_worker, range(cores), chunksize=1)
+    dt = max(r[0] for r in res)
+    n = sum(r[1] for r in res)
+    return {"kind": res[0][2], "cores": cores, "c4_traj_per_s": n / dt, "samples": n,
+            "sample": "one 50x20x200-sample sweep per process, one process per host core concurrently; slowest "
+                      "process's time"}
+
+
 def local_map_c2():
     """6 m x 6 m local costmap @0.05: corridor walls + one box, inflated (radius 0.55, scaling 10) by the product's own
     costmap path when a GPU is present, else by the checker (reference arm)."""
@@ -330,6 +498,22 @@ def run_native_dwa(api, torch, dist, rank, world, local_rank, steps):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sweep_s = float(t.item())
     total = int(r4["n_samples"])
+    # roofline of the DWA half: k_dwa_score is bound by instruction issue, not by HBM (its inputs -- a 14.4 KB costmap
+    # and four 57.6 KB distance grids -- live in L1 / L2); both fractions are given
+    peak_gbs, _ = measured_peak_gbs()
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_hz = 1e6 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"]) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1.965e9
+    issue_peak = sms * 4 * sm_hz * world  # one warp instruction per scheduler and cycle, 4 schedulers per SM
+    out["roofline"] = {
+        "kernel": "k_dwa_score (C4 sweep)", "bound": "issue",
+        "achieved": DWA_C4_WARP_INSTRUCTIONS / sweep_s / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s",
+        "frac": DWA_C4_WARP_INSTRUCTIONS / sweep_s / issue_peak,
+        "warp_instructions_per_sweep": DWA_C4_WARP_INSTRUCTIONS,
+        "warp_instructions_source": "ncu smsp__inst_executed.sum of the same sweep (profiles/), not re-measured in this run",
+        "hbm": {"algorithmic_bytes": DWA_BYTES_PER_TRAJECTORY * total,
+                "achieved_gbs": DWA_BYTES_PER_TRAJECTORY * total / sweep_s / 1e9, "peak_gbs": peak_gbs * world,
+                "frac": DWA_BYTES_PER_TRAJECTORY * total / sweep_s / 1e9 / (peak_gbs * world)}}
     out.update({"c4_samples": int(total), "c4_sweep_ms": 1e3 * sweep_s, "c4_traj_per_s": total / sweep_s,
                 "c4_best_index": int(r4["best_index"]), "c4_best_cost": float(r4["cost"]),
                 "c4_sharding": (f"8-sample blocks dealt round-robin over {world} ranks; (cost, index) minima exchanged "
@@ -609,6 +793,8 @@ def run_native(args, rank, world, local_rank):
     else:
         sweep, merge, inflate = float(np.mean(sweep_ms)), float(np.mean(merge_ms)), float(np.mean(inflate_ms))
 
+    c1 = c1_numbers(api, torch, local_rank, max(10, args.steps)) if rank == 0 else None
+    seam_c3 = seam_c3_numbers(api, local_rank) if rank == 0 else None
     voxel_ms = voxel_numbers(lambda *a: api.costmap(*a, device=local_rank), max(5, args.steps), torch.cuda.synchronize)
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -619,6 +805,8 @@ def run_native(args, rank, world, local_rank):
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "l2": "flushed (256 MiB memset) before every timed cycle",
+                       "value_excludes": "the 35 KB upload of the cycle's observations (resident when the timed region "
+                                         "starts); e2e includes it",
                        "multi_gpu": "replicas only for the costmap path" if world > 1 else "single GPU",
                        "hot_l2_ms_per_step": hot_ms},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -636,6 +824,8 @@ def run_native(args, rank, world, local_rank):
         line["voxel_layer"] = {"c3_with_voxel_layer_update_map_ms": voxel_ms,
                                "what": "C3 with costmap_2d::VoxelLayer (10 x 0.2 m voxels) instead of ObstacleLayer, "
                                        "synchronous navgpu_costmap_update_map, hot L2"}
+        line["c1"] = c1
+        line["plugin_seam_c3"] = seam_c3
         if dwa is not None:
             line["dwa"] = dwa
             line["trajectory_planner"] = tp_numbers(api, inflate_local(api, local_map_c2(), device=local_rank),
@@ -646,9 +836,12 @@ def run_native(args, rank, world, local_rank):
             kind = "reference" if pyoracle.available("reference") else "port"
             line["voxel_layer"]["cpu_ms"] = voxel_numbers(pyoracle.load(kind).costmap, 1)
             line["voxel_layer"]["cpu_kind"] = kind
+            line["c1"]["cpu_baseline"] = c1_cpu_numbers()
             if dwa is not None:
                 line["dwa"]["cpu_baseline"] = dwa_cpu_numbers()
-                line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers(), "c5_all_cores": fleet_cpu_parallel_numbers()})
+                line["dwa"]["cpu_baseline"].update(dwa_prepare_cpu_numbers())
+                line["dwa"]["cpu_baseline"].update({"c5": fleet_cpu_numbers(), "c5_all_cores": fleet_cpu_parallel_numbers(),
+                                                    "c4_all_cores": c4_all_cores_numbers()})
                 ref_api = pyoracle.load(kind)
                 line["trajectory_planner"]["cpu_baseline"] = dict(
                     tp_numbers(ref_api, inflate_local(ref_api, local_map_c2()), reps=5), kind=kind, cores=1)

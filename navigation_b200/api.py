@@ -803,6 +803,13 @@ class Api:
         n = R.value + 2
         return R.value, costs[:n * n].reshape(n, n).copy(), dists[:n * n].reshape(n, n).copy()
 
+    def host_register(self, array):
+        """Page-locks a numpy array's buffer (navgpu_host_register); undo with host_unregister."""
+        self.check(self.lib.navgpu_host_register(C.c_void_p(array.ctypes.data), array.nbytes))
+
+    def host_unregister(self, array):
+        self.check(self.lib.navgpu_host_unregister(C.c_void_p(array.ctypes.data)))
+
     def inflate_host(self, master, min_i, min_j, max_i, max_j, cost_table, radius, device=0):
         assert master.dtype == np.uint8 and master.flags.c_contiguous
         t = np.ascontiguousarray(cost_table, dtype=np.uint8)

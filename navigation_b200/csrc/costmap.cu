@@ -1426,7 +1426,8 @@ int navgpu_costmap_get_window_occupancy(navgpu_costmap* h, int x0, int y0, int x
     NAVGPU_CUDA(cudaMalloc(&h->d_occupancy, n));
     h->occupancy_capacity = n;
   }
-  dim3 block(256), grid((xn - x0 + 255) / 256, yn - y0);
+  const int groups = ((xn + 15) >> 4) - (x0 >> 4);  // 16-cell groups of a master row that the window touches
+  dim3 block(256), grid((groups + 255) / 256, yn - y0);
   k_translate_window<<<grid, block, 0, h->stream>>>(h->master[h->cur], h->pitch, x0, y0, xn - x0, yn - y0, h->d_occupancy);
   NAVGPU_LAUNCHED(1);
   NAVGPU_CUDA(cudaMemcpyAsync(host_out, h->d_occupancy, n, cudaMemcpyDeviceToHost, h->stream));

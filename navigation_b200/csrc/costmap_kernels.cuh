@@ -599,18 +599,43 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
 // Costmap2DPublisher's cost -> occupancy translation (src/costmap_2d_publisher.cpp:56-71, applied per cell in
 // prepareGrid :95-113 and publishCostmap :139-152), fused with the packing of a window for the download:
 // 0 -> 0, 253 -> 99, 254 -> 100, 255 -> -1, 1..252 -> 1 + 97 * (v - 1) / 251.
-__global__ void k_translate_window(const uint8_t* __restrict__ master, unsigned pitch, int x0, int y0, int w, int h,
-                                   int8_t* __restrict__ out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w || y >= h) return;
-  const int v = master[(size_t)(y0 + y) * pitch + x0 + x];
-  int o;
-  if (v == 0) o = 0;
-  else if (v == kInscribed) o = 99;
-  else if (v == kLethal) o = 100;
-  else if (v == kNoInfo) o = -1;
-  else o = 1 + (97 * (v - 1)) / 251;
-  out[(size_t)y * w + x] = (int8_t)o;
+// Sixteen cells per thread: one aligned 16-byte load of the master row, a 256-entry table in shared memory, one
+// 16-byte store when the packed output is aligned there (always for whole-row windows of maps whose width is a multiple
+// of 16), byte stores at the window's edges otherwise.
+__global__ void __launch_bounds__(256) k_translate_window(const uint8_t* __restrict__ master, unsigned pitch, int x0, int y0,
+                                                           int w, int h, int8_t* __restrict__ out) {
+  __shared__ uint8_t lut[256];
+  {
+    const int v = threadIdx.x;
+    int o;
+    if (v == 0) o = 0;
+    else if (v == kInscribed) o = 99;
+    else if (v == kLethal) o = 100;
+    else if (v == kNoInfo) o = -1;
+    else o = 1 + (97 * (v - 1)) / 251;
+    lut[v] = (uint8_t)(int8_t)o;
+  }
+  __syncthreads();
+  const int y = blockIdx.y;
+  const int gx = ((x0 >> 4) + blockIdx.x * blockDim.x + threadIdx.x) << 4;  // first cell of my 16-cell group of the row
+  if (y >= h || gx >= x0 + w) return;
+  const uint4 v = *reinterpret_cast<const uint4*>(master + (size_t)(y0 + y) * pitch + gx);
+  const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    o[k] = (uint32_t)lut[in[k] & 0xffu] | ((uint32_t)lut[(in[k] >> 8) & 0xffu] << 8) |
+           ((uint32_t)lut[(in[k] >> 16) & 0xffu] << 16) | ((uint32_t)lut[in[k] >> 24] << 24);
+  int8_t* dst = out + (size_t)y * w + (gx - x0);  // (may point before `out` for the first group: guarded below)
+  if (gx >= x0 && gx + 16 <= x0 + w && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int cx = gx + i;
+      if (cx >= x0 && cx < x0 + w) out[(size_t)y * w + (cx - x0)] = (int8_t)(o[i >> 2] >> (8 * (i & 3)));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1306,7 +1331,8 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   // the unpruned seed words only live until the pruning pass has read them: they borrow the start of h2, which phase 2
   // fills afterwards (and only for seeded rows; phase 3 never reads another row)
   uint32_t* const sbits = h2;
-  __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
+  __shared__ uint32_t rowmask[kIMaskWords];   // bit (r + 32) <-> region row r has seeds
+  __shared__ uint32_t fullmask[kIMaskWords];  // bit (r + 32) <-> region row r is seeded in all 64 columns of the tile
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
   // early mode: the flags of the k_merge_seed tiles this tile reads (seeds: columns tx0 - 32 .. tx0 + 95, rows
@@ -1364,7 +1390,7 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     sbits[i] = v;
     any |= v != 0;
   }
-  if (tid < kIMaskWords) rowmask[tid] = 0;
+  if (tid < kIMaskWords) rowmask[tid] = fullmask[tid] = 0;
   if (!__syncthreads_or(any)) return;
 
   // ---- interior seeds cannot be the nearest seed of any other cell: a seed whose four neighbours are seeds too has,
@@ -1389,6 +1415,10 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     if (keep) atomicOr(&rowmask[(r >> 5) + 1], 1u << (r & 31));
   }
   __syncthreads();
+  // rows whose seeds cover every column of the tile (the long side of a wall or shelf): such a row hides every seeded
+  // row behind it from the cells in front of it -- (j' - k)^2 > (j - k)^2 + 0 -- which phase 3 uses to shorten its walk
+  for (int r = tid; r < rows; r += kIThreads)
+    if ((pbits[4 * r + 1] & pbits[4 * r + 2]) == 0xffffffffu) atomicOr(&fullmask[(r >> 5) + 1], 1u << (r & 31));
 
   // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row; warp w takes the
   // seeded rows r = w mod 8, straight from the row mask)
@@ -1449,6 +1479,38 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
         nrows += __popc(mw[q]);
       }
       if (anyrow == 0) continue;  // no seeded row anywhere near these eight rows: nothing to inflate
+      {
+        // window bit b <-> j = b - RMAX; the eight output rows are bits RMAX .. RMAX + 7.  Above them only the rows up
+        // to (and including) the nearest full row can matter, below them likewise.
+        auto below = [](int n) -> uint32_t { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : (1u << n) - 1u); };
+        uint32_t fw[NW];
+        uint32_t anyfull = 0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+          fw[q] = __funnelshift_r(fullmask[wi + q], fullmask[wi + q + 1], sh) & mw[q];
+          anyfull |= fw[q];
+        }
+        if (anyfull) {
+          int bt = -1, bb = -1;
+#pragma unroll
+          for (int q = NW - 1; q >= 0; --q) {
+            const uint32_t am = fw[q] & below(RMAX - 32 * q);
+            if (bt < 0 && am) bt = 32 * q + 31 - __clz(am);
+          }
+#pragma unroll
+          for (int q = 0; q < NW; ++q) {
+            const uint32_t bm = fw[q] & ~below(RMAX + 8 - 32 * q);
+            if (bb < 0 && bm) bb = 32 * q + __ffs(bm) - 1;
+          }
+          nrows = 0;
+#pragma unroll
+          for (int q = 0; q < NW; ++q) {
+            if (bt > 0) mw[q] &= ~below(bt - 32 * q);
+            if (bb >= 0) mw[q] &= below(bb + 1 - 32 * q);
+            nrows += __popc(mw[q]);
+          }
+        }
+      }
       if (nrows <= kISparseRows) {
 #pragma unroll
         for (int q = 0; q < NW; ++q) {

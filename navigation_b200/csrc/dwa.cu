@@ -6,6 +6,7 @@
 // the per-axis velocity samples (VelocityIterator is a 20-entry fp64 accumulation) and the oscillation flags.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <memory>
 #include <vector>

@@ -525,8 +525,9 @@ __device__ __forceinline__ int footprint_vertex_cell(const Args& a, double x, do
 // One footprint edge of one pose: CostmapModel::lineCost over the LineIterator cells between the map cells of two
 // consecutive oriented footprint vertices (costmap_model.cpp:75-131, line_iterator.h:38-139).  Returns the maximum
 // cell cost along the edge, or -1 when a vertex is off the map or a cell is LETHAL / (NO_INFORMATION && !allow_unknown).
+// `cost` is the grid the cells are read from: a.g.cost, or the CTA's shared-memory copy of it
 template <class Args>
-__device__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
+__device__ int footprint_edge_cost(const Args& a, const uint8_t* __restrict__ cost, int cell_p, int cell_q) {
   const DwaGeom& g = a.g;
   if ((cell_p | cell_q) < 0) return -1;  // a vertex off the map (costmap_model.cpp:79-90)
   const int px = cell_p & 0xffff, py = cell_p >> 16, qx = cell_q & 0xffff, qy = cell_q >> 16;
@@ -543,7 +544,7 @@ __device__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
   int best = 0, lethal_probe = 0xff;
   if (a.allow_unknown) {
     for (int k = 0; k <= den; ++k) {
-      const int c = g.cost[off];
+      const int c = cost[off];
       best = max(best, c);
       lethal_probe = min(lethal_probe, c ^ 0xfe);
       num += numadd;
@@ -555,7 +556,7 @@ __device__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
     }
   } else {
     for (int k = 0; k <= den; ++k) {
-      best = max(best, (int)g.cost[off]);
+      best = max(best, (int)cost[off]);
       num += numadd;
       if (num >= den) {
         num -= den;
@@ -566,6 +567,10 @@ __device__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
   }
   const bool bad = a.allow_unknown ? lethal_probe == 0 : best >= kLethal;
   return bad ? -1 : best;
+}
+template <class Args>
+__device__ __forceinline__ int footprint_edge_cost(const Args& a, int cell_p, int cell_q) {
+  return footprint_edge_cost(a, a.g.cost, cell_p, cell_q);
 }
 
 // What the critics accumulate over the rounds of 32 points of one trajectory
@@ -586,8 +591,9 @@ __device__ __forceinline__ void critic_acc_init(CriticAcc& acc) {
 // point l -- world position (px, py) and cos / sin of its heading (obstacle_cost_function.cpp:74-142,
 // map_grid_cost_function.cpp:75-129).  Shared by the sample sweep (the points come out of the rollout) and by the
 // TrajectoryCostFunction backend (the points come from the caller's Trajectory).
-__device__ __forceinline__ void score_round(const DwaScoreArgs& a, int lane, int cnt, double px, double py, double c,
-                                            double s, double* warp_scratch, CriticAcc& acc) {
+__device__ __forceinline__ void score_round(const DwaScoreArgs& a, const uint8_t* __restrict__ cost, int lane, int cnt,
+                                            double px, double py, double c, double s, double* warp_scratch,
+                                            CriticAcc& acc) {
   const bool active = lane < cnt;
   // ---- obstacle critic: (point, edge) work items spread over all 32 lanes, so a short tail round costs one edge
   // per lane instead of a whole footprint per active lane
@@ -604,19 +610,22 @@ __device__ __forceinline__ void score_round(const DwaScoreArgs& a, int lane, int
   bool fail = false;
   if (a.nfp >= 3) {
     // every (point, vertex) cell once, then every (point, edge) walk between two of them
-    int* vcell = reinterpret_cast<int*>(warp_scratch + 128 + 16);  // [point][kMaxFootprint]
+    // [point][vertex], packed with a row length of nfp: item `it` of the loops below owns word `it`, so the lanes of
+    // a pass read and write 32 consecutive words (a row length of kMaxFootprint = 16 put every second point on the
+    // same banks)
+    int* vcell = reinterpret_cast<int*>(warp_scratch + 128 + 16);
     const int items = cnt * a.nfp;
     // it / nfp for it < 512, nfp <= 16 as a multiply by ceil(2^16 / nfp) (error < 512 / 2^16 < 1 / nfp: exact)
     const unsigned inv_nfp = (65536u + (unsigned)a.nfp - 1u) / (unsigned)a.nfp;
     for (int it = lane; it < items; it += 32) {
       const int p = (int)(((unsigned)it * inv_nfp) >> 16), v = it - p * a.nfp;
-      vcell[p * kMaxFootprint + v] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
+      vcell[it] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
     }
     __syncwarp();
     for (int it = lane; it < items; it += 32) {
       const int p = (int)(((unsigned)it * inv_nfp) >> 16), e = it - p * a.nfp;
-      const int e1 = e + 1 < a.nfp ? e + 1 : 0;
-      const int ec = footprint_edge_cost(a, vcell[p * kMaxFootprint + e], vcell[p * kMaxFootprint + e1]);
+      const int next = e + 1 < a.nfp ? it + 1 : it - e;  // the closing edge returns to the point's first vertex
+      const int ec = footprint_edge_cost(a, cost, vcell[it], vcell[next]);
       atomicMax(&edge_max[p], ec < 0 ? 0x80000000u : (unsigned)ec);
     }
     __syncwarp();
@@ -637,7 +646,7 @@ __device__ __forceinline__ void score_round(const DwaScoreArgs& a, int lane, int
     const int cx = cell0_x, cy = cell0_y;
     if (a.nfp == 0 || !on_map0) fail = true;  // off-map centre: costmap_model.cpp:57-58
     else {
-      const int centre = a.g.cost[cy * (int)a.g.pitch + cx];
+      const int centre = cost[cy * (int)a.g.pitch + cx];
       int f = (int)edge_max[lane];
       if (a.nfp < 3) {  // point robot: the centre cell alone (:61-67)
         f = (centre == kLethal || centre == kInscribed || (centre == kNoInfo && !a.allow_unknown)) ? -1 : centre;
@@ -733,7 +742,8 @@ __device__ __forceinline__ float sample_vth(const DwaScoreArgs& a, int i) {
 constexpr int kWarpScratchDoubles = 128 + 16 + 16 * kMaxFootprint;  // 4 x 32 pose doubles, 32 ints, 32 x kMaxFootprint vertex cells
 template <bool kScore>
 __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int lane, double* terms_out,
-                                   double* points_out, int points_capacity, double* warp_scratch) {
+                                   double* points_out, int points_capacity, double* warp_scratch,
+                                   const uint8_t* __restrict__ cost) {
   TrajResult res;
   res.cost = nan_quiet();
   res.generated = false;
@@ -833,7 +843,7 @@ __device__ TrajResult score_sample(const DwaScoreArgs& a, long long sample, int 
       points_out[3 * (base + lane) + 2] = thd;
     }
     if (!kScore) continue;
-    score_round(a, lane, cnt, px, py, c, s, warp_scratch, acc);
+    score_round(a, cost, lane, cnt, px, py, c, s, warp_scratch, acc);
   }
 
   if (!kScore) return res;
@@ -850,7 +860,7 @@ __device__ void finish_winner(const DwaScoreArgs& a, long long idx, double cost,
   TrajResult r;
   r.generated = false;
   r.num_steps = 0;
-  if (idx >= 0) r = score_sample<false>(a, idx, lane, nullptr, points, points_capacity, warp_scratch);
+  if (idx >= 0) r = score_sample<false>(a, idx, lane, nullptr, points, points_capacity, warp_scratch, a.g.cost);
   if (lane == 0) {
     out->n_scored = (int)*n_generated;  // samples the generator accepted; re-armed for the next search
     *n_generated = 0;
@@ -952,6 +962,8 @@ __device__ __noinline__ void shard_exchange(ShardExchange* peer_of_lane, ShardEx
 }
 
 __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_dwa_score(DwaScoreArgs a) {
+  // (the 14.4 KB local costmap is read through L1: a per-CTA copy in shared memory measured 3-5 % slower)
+  const uint8_t* costmap = a.g.cost;
   __shared__ double s_cost[kDwaWarpsPerBlock];
   __shared__ long long s_index[kDwaWarpsPerBlock];
   __shared__ int s_generated[kDwaWarpsPerBlock];
@@ -967,7 +979,7 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_dwa_score(DwaScor
   int generated = 0;
   if (sample < a.end) {
     double* terms = a.all_terms ? a.all_terms + 6 * (sample - a.begin) : nullptr;
-    const TrajResult r = score_sample<true>(a, sample, lane, terms, nullptr, 0, s_scratch[warp]);
+    const TrajResult r = score_sample<true>(a, sample, lane, terms, nullptr, 0, s_scratch[warp], costmap);
     generated = r.generated;
     if (terms && !r.generated && lane == 0)
       for (int k = 0; k < 6; ++k) terms[k] = nan_quiet();
@@ -1054,7 +1066,7 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_dwa_score(DwaScor
 // empty trajectory, which every critic scores as 0 (an empty footprint still answers -9)
 __global__ void k_dwa_check(DwaScoreArgs a, double* cost_out) {
   __shared__ double s_scratch[kWarpScratchDoubles];
-  const TrajResult r = score_sample<true>(a, 0, threadIdx.x & 31, nullptr, nullptr, 0, s_scratch);
+  const TrajResult r = score_sample<true>(a, 0, threadIdx.x & 31, nullptr, nullptr, 0, s_scratch, a.g.cost);
   if (threadIdx.x == 0) *cost_out = r.generated ? r.cost : ((a.nfp == 0 && a.scale_obstacle != 0.0) ? -9.0 : 0.0);
 }
 
@@ -1086,7 +1098,7 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32) k_dwa_score_points(Dwa
       py = p[1];
       sincos(p[2], &s, &c);  // WorldModel::footprintCost / MapGridCostFunction take cos, sin of the point's heading
     }
-    score_round(a, lane, cnt, px, py, c, s, s_scratch[warp], acc);
+    score_round(a, a.g.cost, lane, cnt, px, py, c, s, s_scratch[warp], acc);
     __syncwarp();
   }
   const double total = combine_critics(a, osc_bad, acc, terms_out ? terms_out + 6 * (size_t)t : nullptr, lane);
@@ -1210,13 +1222,14 @@ __global__ void __launch_bounds__(kDwaWarpsPerBlock * 32, 4) k_fleet_score(DwaSc
     return;
   }
   fleet_patch_args(s_a, base, r, samples);
+  const uint8_t* costmap = s_a.g.cost;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long sample = (long long)local * kDwaWarpsPerBlock + warp;
   double cost = INFINITY;
   long long index = -1;
   int gen = 0;
   if (sample < s_a.end) {
-    const TrajResult t = score_sample<true>(s_a, sample, lane, nullptr, nullptr, 0, s_scratch[warp]);
+    const TrajResult t = score_sample<true>(s_a, sample, lane, nullptr, nullptr, 0, s_scratch[warp], costmap);
     gen = t.generated;
     if (t.generated && t.cost >= 0) {
       cost = t.cost;

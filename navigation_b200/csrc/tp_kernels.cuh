@@ -167,13 +167,13 @@ __device__ void tp_score_sample(const TpScoreArgs& a, int sample, int lane, doub
       const unsigned inv_nfp = (65536u + (unsigned)a.nfp - 1u) / (unsigned)a.nfp;  // exact for it < 512, nfp <= 16
       for (int it = lane; it < items; it += 32) {
         const int p = (int)(((unsigned)it * inv_nfp) >> 16), v = it - p * a.nfp;
-        vcell[p * kMaxFootprint + v] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
+        vcell[it] = footprint_vertex_cell(a, pose_s[p], pose_s[32 + p], pose_s[64 + p], pose_s[96 + p], v);
       }
       __syncwarp();
       for (int it = lane; it < items; it += 32) {
         const int p = (int)(((unsigned)it * inv_nfp) >> 16), e = it - p * a.nfp;
-        const int e1 = e + 1 < a.nfp ? e + 1 : 0;
-        const int ec = footprint_edge_cost(a, vcell[p * kMaxFootprint + e], vcell[p * kMaxFootprint + e1]);
+        const int next = e + 1 < a.nfp ? it + 1 : it - e;  // packed [point][vertex] rows of nfp words
+        const int ec = footprint_edge_cost(a, vcell[it], vcell[next]);
         atomicMax(&edge_max[p], ec < 0 ? 0x80000000u : (unsigned)ec);
       }
       __syncwarp();

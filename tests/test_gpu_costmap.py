@@ -499,6 +499,12 @@ def test_publisher_translation_fused_into_the_download(cuda):
     cm.set(grid)
     assert np.array_equal(cm.get_window_occupancy(0, 0, sx, sy), table[grid])
     assert np.array_equal(cm.get_window_occupancy(13, 5, 290, 71), table[grid[5:71, 13:290]])
+    assert np.array_equal(cm.get_window_occupancy(16, 0, 272, 9), table[grid[0:9, 16:272]])   # aligned 16-byte stores
+    assert np.array_equal(cm.get_window_occupancy(299, 70, 301, 77), table[grid[70:77, 299:301]])  # inside one group
+    big = cuda.costmap(640, 33, 0.05)                                                       # whole rows, width % 16 == 0
+    g2 = (np.arange(640 * 33, dtype=np.uint32).reshape(33, 640) * 11 % 256).astype(np.uint8)
+    big.set(g2)
+    assert np.array_equal(big.get_window_occupancy(0, 0, 640, 33), table[g2])
 
 
 def test_c3_full_size_bit_exact_vs_checker(cuda, port):
