@@ -152,6 +152,10 @@ int navgpu_costmap_set_profiling(navgpu_costmap* h, int enabled);
 /* test hook: use the generic (any-R) fused sweep kernel even where the R <= 31 two-kernel fast path applies */
 int navgpu_costmap_force_generic_sweep(navgpu_costmap* h, int enabled);
 int navgpu_costmap_last_timing(navgpu_costmap* h, float* cycle_ms, float* sweep_ms);
+/* measurement hook (process started with NAVGPU_TRACE set): first start / last end of the cycle's kernels on the device's
+ * global timer in ns -- out[0..1] obstacle kernel, [2..3] k_merge_seed, [4..5] k_inflate, [6] last merge tile in the
+ * obstacle box, [7] / [8] first / last inflate tile released by its flags (tools/probe_trace.py) */
+int navgpu_costmap_last_trace(navgpu_costmap* h, uint64_t out[16]);
 /* the sweep's two kernels separately: streaming merge + seed bitmask (k_merge_seed), inflation (k_inflate) */
 int navgpu_costmap_last_timing_split(navgpu_costmap* h, float* merge_ms, float* inflate_ms);
 /* the CUDA stream of this handle (cudaStream_t) so callers can record events on it */
@@ -334,6 +338,29 @@ int navgpu_dwa_find_best_path_async(navgpu_dwa* h, const double pose[3], const d
                                     const double* footprint_xy, int n_footprint);
 int navgpu_dwa_synchronize(navgpu_dwa* h);
 void* navgpu_dwa_stream(navgpu_dwa* h);
+
+/* ---- Plan preprocessing of the local planners, batched ------------------------------------------
+ * base_local_planner::transformGlobalPlan (base_local_planner/src/goal_functions.cpp:86-174) and prunePlan (:68-84) for
+ * n_plans independent plans in one launch (one warp per plan).  Plans are concatenated: plan p owns poses
+ * offsets[p] .. offsets[p + 1] - 1 of plan_xyz (x, y, z of pose.position, doubles).  tf's part stays with the caller
+ * (tf is not in the reference tree): per plan the robot position expressed in the PLAN's frame (tf.transformPose,
+ * :110-111) and plan_to_global_transform (:103-107) as a rigid transform.
+ *   navgpu_plans_transform: first_out[p] = index of the first pose within dist_threshold[p] of the robot (the plan's
+ *       size when there is none), count_out[p] = number of poses kept from there -- every pose up to and including the
+ *       first one beyond the threshold, exactly the reference's two loops (:122-149); transformed_xyz[offsets[p] + k] =
+ *       plan_to_global * (kept pose k).  The reference's dist_threshold is max(size_x, size_y) * resolution / 2 of the
+ *       local costmap (:114-115).  Orientations are not transformed: the critics of this path read positions only.
+ *   navgpu_plans_prune: erase_count_out[p] = number of way-points prunePlan erases from the front of plan p (and of
+ *       the global plan): all before the first one closer than 1 m to the robot. */
+typedef struct {
+  double m[9]; /* rotation (tf::Matrix3x3 of the transform's basis), row-major */
+  double t[3]; /* origin */
+} navgpu_rigid_transform;
+int navgpu_plans_transform(int n_plans, const int32_t* offsets, const double* plan_xyz, const double* robot_xy,
+                           const navgpu_rigid_transform* plan_to_global, const double* dist_threshold,
+                           int32_t* first_out, int32_t* count_out, double* transformed_xyz, int device);
+int navgpu_plans_prune(int n_plans, const int32_t* offsets, const double* plan_xyz, const double* robot_xy,
+                       int32_t* erase_count_out, int device);
 
 /* ---- Fleet mode: N independent robots per control cycle (config C5) ------------------------------------------
  * Every robot has its own local costmap (raw obstacles in, inflated on the device exactly like a layered costmap

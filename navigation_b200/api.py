@@ -117,6 +117,7 @@ SIGNATURES = {
     "navgpu_costmap_get": (C.c_int, [C.c_void_p, _u8p]),
     "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
     "navgpu_costmap_get_window_into": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_uint32]),
+    "navgpu_costmap_last_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "navgpu_costmap_get_changed": (C.c_int, [C.c_void_p, _u8p, C.c_uint32, _i32p, C.c_int, C.POINTER(C.c_int32),
                                              C.POINTER(C.c_uint64)]),
     "navgpu_costmap_mirror_invalidate": (C.c_int, [C.c_void_p]),
@@ -150,6 +151,8 @@ SIGNATURES = {
                                          _i64p]),
     "navgpu_dwa_finish_sharded": (C.c_int, [C.c_void_p, _f64p, _f64p, _i64p, C.c_int, C.POINTER(DwaResult), _f64p,
                                             C.c_int]),
+    "navgpu_plans_transform": (C.c_int, [C.c_int, _i32p, _f64p, _f64p, C.c_void_p, _f64p, _i32p, _i32p, _f64p, C.c_int]),
+    "navgpu_plans_prune": (C.c_int, [C.c_int, _i32p, _f64p, _f64p, _i32p, C.c_int]),
     "navgpu_dwa_prepare": (C.c_int, [C.c_void_p]),
     "navgpu_dwa_score_trajectories": (C.c_int, [C.c_void_p, C.c_int, _i32p, _f64p, _f64p, _f64p, C.c_int, _f64p, _f64p]),
     "navgpu_dwa_update_oscillation": (C.c_int, [C.c_void_p, _f64p, C.c_double, C.c_double, C.c_double, C.c_double]),
@@ -383,6 +386,11 @@ class Costmap:
         assert host_grid.dtype == np.uint8 and host_grid.flags["C_CONTIGUOUS"]
         self.api.check(self.lib.navgpu_costmap_get_window_into(self.h, x0, y0, xn, yn, _p(host_grid, _u8p),
                                                                host_grid.shape[1]))
+
+    def last_trace(self):
+        out = np.zeros(16, dtype=np.uint64)
+        self.api.check(self.lib.navgpu_costmap_last_trace(self.h, _p(out, C.POINTER(C.c_uint64))))
+        return out
 
     def get_changed(self, host_grid, max_rects=0):
         """Brings `host_grid` (the full-size host mirror, size_y x size_x uint8, the same array every call) up to date
@@ -802,6 +810,42 @@ class Api:
                                                     C.byref(R)))
         n = R.value + 2
         return R.value, costs[:n * n].reshape(n, n).copy(), dists[:n * n].reshape(n, n).copy()
+
+    @staticmethod
+    def _pack_plans(plans):
+        offs = np.zeros(len(plans) + 1, dtype=np.int32)
+        for i, p in enumerate(plans):
+            offs[i + 1] = offs[i] + len(p)
+        xyz = np.zeros((int(offs[-1]), 3))
+        for i, p in enumerate(plans):
+            a = np.asarray(p, dtype=np.float64).reshape(len(p), -1) if len(p) else np.zeros((0, 3))
+            xyz[offs[i]:offs[i + 1], :a.shape[1]] = a
+        return offs, np.ascontiguousarray(xyz)
+
+    def plans_transform(self, plans, robot_xy, transforms, thresholds, device=0):
+        """Batched base_local_planner::transformGlobalPlan: plans = list of [n_i][2 or 3] arrays, robot_xy [n][2] in the
+        plans' frames, transforms [n][12] (3x3 rotation row-major, then the origin), thresholds [n]; returns
+        (first index, list of transformed [count_i][3] arrays)."""
+        n = len(plans)
+        offs, xyz = self._pack_plans(plans)
+        rob = np.ascontiguousarray(robot_xy, dtype=np.float64).reshape(n, 2)
+        tf = np.ascontiguousarray(transforms, dtype=np.float64).reshape(n, 12)
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64).reshape(n)
+        first, count = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        out = np.zeros_like(xyz)
+        self.check(self.lib.navgpu_plans_transform(n, _p(offs, _i32p), _p(xyz, _f64p), _p(rob, _f64p),
+                                                   C.c_void_p(tf.ctypes.data), _p(thr, _f64p), _p(first, _i32p),
+                                                   _p(count, _i32p), _p(out, _f64p), device))
+        return first, [out[offs[i]:offs[i] + count[i]].copy() for i in range(n)]
+
+    def plans_prune(self, plans, robot_xy, device=0):
+        """Batched base_local_planner::prunePlan: how many way-points are erased from the front of every plan."""
+        n = len(plans)
+        offs, xyz = self._pack_plans(plans)
+        rob = np.ascontiguousarray(robot_xy, dtype=np.float64).reshape(n, 2)
+        erase = np.zeros(n, dtype=np.int32)
+        self.check(self.lib.navgpu_plans_prune(n, _p(offs, _i32p), _p(xyz, _f64p), _p(rob, _f64p), _p(erase, _i32p), device))
+        return erase
 
     def host_register(self, array):
         """Page-locks a numpy array's buffer (navgpu_host_register); undo with host_unregister."""

@@ -200,6 +200,8 @@ struct navgpu_costmap {
   size_t seeds_capacity = 0;
   unsigned* d_tile_ready = nullptr;  // early mode: per k_merge_seed tile, the sweep number that last completed it
   unsigned sweep_epoch = 0;
+  int sm_count = 0;
+  unsigned long long* d_trace = nullptr;  // NAVGPU_TRACE: kernel start / end stamps of the last cycle (measurement)
   // inflation mode 1 (k_inflate_propagate): per-cell state + two frontier lists, barrier / round control
   uint32_t* d_prop_state = nullptr;
   PropCtl* d_prop_ctl = nullptr;
@@ -350,6 +352,7 @@ int launch_propagate(const UpdateArgs& a, const uint16_t* seeds, const PropBuffe
 struct TileFlags {  // early mode: k_merge_seed -> k_inflate per-tile hand-over (MergeSeedArgs::ready)
   unsigned* ready = nullptr;
   unsigned epoch = 0;
+  unsigned long long* trace = nullptr;
 };
 
 int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic, cudaEvent_t ev_mid = nullptr,
@@ -366,6 +369,7 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
     m.R = R;
     m.seeds = seeds;
     m.early = a.early; m.ex0 = a.ex0; m.exn = a.exn; m.ey0 = a.ey0; m.eyn = a.eyn;
+    m.trace = flags ? flags->trace : nullptr;
     if (R > 0 && !seeds) return fail(NAVGPU_ERR_INVALID, "seed bitmask missing");
     dim3 block(kMSGroupsX, kMSRowsY);
     dim3 grid((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16), (a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
@@ -387,9 +391,11 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
       ia.cost_d2 = a.cost_d2;
       ia.seeds = reinterpret_cast<const uint32_t*>(seeds);
       if (handover) { ia.ready = flags->ready; ia.epoch = flags->epoch; ia.ready_pitch = (int)grid.x; }
+      ia.trace = flags ? flags->trace : nullptr;
       dim3 igrid((a.sx + kITX - 1) / kITX, (a.sy + kITY - 1) / kITY);
       // the instantiation whose unrolled row walk just covers the effective reach (what k_inflate calls R)
       const int reach = (int)sqrtf((float)a.reach2 + 0.5f);
+      ia.reach = reach;
       if (reach <= 12) NAVGPU_CUDA(launch_pdl(k_inflate<12>, igrid, dim3(kIThreads), 0, stream, ia));
       else if (reach <= 20) NAVGPU_CUDA(launch_pdl(k_inflate<20>, igrid, dim3(kIThreads), 0, stream, ia));
       else NAVGPU_CUDA(launch_pdl(k_inflate<31>, igrid, dim3(kIThreads), 0, stream, ia));
@@ -458,6 +464,7 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   if (R > 0 && (R <= 31 || propagate)) NAVGPU_TRY(ensure_seeds(&h->d_seeds, &h->seeds_capacity, h->pitch, h->sy, h->stream));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[0], h->stream);
   TileFlags tf;
+  tf.trace = h->d_trace;
   if (a.early && R > 0 && R <= 31 && !propagate) {
     const size_t n_tiles = size_t((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16)) *
                            ((a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
@@ -506,6 +513,12 @@ int footprint_polygon(navgpu_costmap* h, const Layer& L, PolyArgs& pa, int* mode
 // One LayeredCostmap::updateMap cycle (layered_costmap.cpp:79-150), enqueued on the handle's stream.
 int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   NAVGPU_TRY(use_device(h));
+  static const bool tracing = getenv("NAVGPU_TRACE") != nullptr;
+  if (tracing) {
+    if (!h->d_trace) NAVGPU_CUDA(cudaMalloc(&h->d_trace, 16 * sizeof(unsigned long long)));
+    static const unsigned long long init[16] = {~0ull, 0, ~0ull, 0, ~0ull, 0, 0, ~0ull, 0, 0, 0, 0, 0, 0, 0, 0};
+    NAVGPU_CUDA(cudaMemcpyAsync(h->d_trace, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  }
   // rolling window: master origin follows the robot (:86-91)
   if (h->rolling)
     NAVGPU_TRY(roll_grid(h, h->master, h->cur, h->ox, h->oy, h->def, rx - h->size_m_x() / 2, ry - h->size_m_y() / 2));
@@ -592,6 +605,19 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     }
   }
 
+  EarlyBox early;
+  static const bool no_early = getenv("NAVGPU_NO_EARLY_MERGE") != nullptr;  // measurement switch (tools/probe_overlap.py)
+  if (whole_map && box_known && !no_early) {
+    early.on = 1;
+    if (ebx1 >= ebx0 && eby1 >= eby0) {  // cells, two to spare on every side, clamped to the map
+      auto cell = [&](double w, double origin, int size, int pad) {
+        const double c = std::floor((w - origin) / h->res) + pad;
+        return (int)std::min<double>(size, std::max(0.0, c));
+      };
+      early.x0 = cell(ebx0, h->ox, (int)h->sx, -2); early.xn = cell(ebx1, h->ox, (int)h->sx, 3);
+      early.y0 = cell(eby0, h->oy, (int)h->sy, -2); early.yn = cell(eby1, h->oy, (int)h->sy, 3);
+    }
+  }
   // ---- device part: one k_obstacle_update per enabled obstacle layer (ray-trace clearing, then marking, then the
   // footprint polygon of updateCosts); the last one also finalises the bounds into the cycle's window
   for (size_t li = 0; li < h->layers.size(); ++li) {
@@ -646,6 +672,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     oa.do_poly = mode == 1;
     oa.do_finalize = (int)li == last_obstacle;
     if (oa.do_finalize) oa.ba = ba;
+    oa.trace = h->d_trace;
     oa.boxes = h->d_boxes; oa.infl = h->d_infl; oa.win = h->d_win;
     const int blocks = std::max(1, (L.total_rays * 32 + kObstacleThreads - 1) / kObstacleThreads);
     k_obstacle_update<<<blocks, kObstacleThreads, 0, h->stream>>>(oa);
@@ -667,19 +694,6 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
 
   // ---- resetMap + updateCosts of every plugin, in order (:137-142), fused into as few sweeps as possible:
   // consecutive cost layers merge in one pass, an inflation layer closes the pass.
-  EarlyBox early;
-  static const bool no_early = getenv("NAVGPU_NO_EARLY_MERGE") != nullptr;  // measurement switch (tools/probe_overlap.py)
-  if (whole_map && box_known && !no_early) {
-    early.on = 1;
-    if (ebx1 >= ebx0 && eby1 >= eby0) {  // cells, two to spare on every side, clamped to the map
-      auto cell = [&](double w, double origin, int size, int pad) {
-        const double c = std::floor((w - origin) / h->res) + pad;
-        return (int)std::min<double>(size, std::max(0.0, c));
-      };
-      early.x0 = cell(ebx0, h->ox, (int)h->sx, -2); early.xn = cell(ebx1, h->ox, (int)h->sx, 3);
-      early.y0 = cell(eby0, h->oy, (int)h->sy, -2); early.yn = cell(eby1, h->oy, (int)h->sy, 3);
-    }
-  }
   MergeLayers ml;
   ml.n = 0;
   int do_reset = 1;
@@ -780,7 +794,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   cudaFree(h->master[0]); cudaFree(h->master[1]);
   cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
   cudaFree(h->d_prop_state); cudaFree(h->d_prop_ctl);
-  cudaFree(h->d_shadow); cudaFree(h->d_mirror_counters); cudaFree(h->d_tile_ready);
+  cudaFree(h->d_shadow); cudaFree(h->d_mirror_counters); cudaFree(h->d_tile_ready); cudaFree(h->d_trace);
   if (h->h_mirror_stage) cudaFreeHost(h->h_mirror_stage);
   if (h->h_mirror_tiles) cudaFreeHost(h->h_mirror_tiles);
   if (h->h_mirror_ctl) cudaFreeHost(h->h_mirror_ctl);
@@ -1266,6 +1280,15 @@ int navgpu_costmap_update_map(navgpu_costmap* h, double rx, double ry, double ry
   }
   if (window_out)
     for (int i = 0; i < 4; ++i) window_out[i] = h->win[i];
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_last_trace(navgpu_costmap* h, uint64_t out[16]) {
+  if (!h || !out) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (!h->d_trace) return fail(NAVGPU_ERR_INVALID, "tracing is off (set NAVGPU_TRACE before the first update)");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  NAVGPU_CUDA(cudaMemcpy(out, h->d_trace, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return NAVGPU_OK;
 }
 

@@ -8,6 +8,22 @@
 
 namespace navgpu {
 
+// measurement only (NAVGPU_TRACE, tools/probe_trace.py): first start / last end of every kernel of a cycle on the
+// device's global timer, so that the overlap of the three kernels can be read off.  [2k] = min start, [2k + 1] = max end
+// for k = 0 obstacle, 1 merge, 2 inflate; [6] = last end of a merge tile in the obstacle box, [7] = first start of
+// actual work (after the flag wait) of an inflate tile, [8] = last flag wait end of an inflate tile.
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_start(unsigned long long* tr, int k) {
+  if (tr && (threadIdx.x | threadIdx.y) == 0) atomicMin(&tr[2 * k], trace_now());
+}
+__device__ __forceinline__ void trace_end(unsigned long long* tr, int k) {
+  if (tr && (threadIdx.x | threadIdx.y) == 0) atomicMax(&tr[2 * k + 1], trace_now());
+}
+
 struct Geom {
   unsigned sx, sy, pitch;
   double res, ox, oy;
@@ -551,6 +567,7 @@ struct ObstacleArgs {
   DevBox* boxes;
   InflationBoundsState* infl;
   DevWindow* win;
+  unsigned long long* trace = nullptr;
 };
 constexpr int kObstacleThreads = 256;
 
@@ -561,6 +578,7 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * kObstacleThreads + threadIdx.x) >> 5;
   cudaTriggerProgrammaticLaunchCompletion();  // k_merge_seed may be scheduled behind us; it waits for our completion
+  if (a.trace && threadIdx.x == 0) atomicMin(&a.trace[0], trace_now());
   // the observation tables travel in the kernel parameters when they fit (no dependent global loads to find a ray's
   // observation), else they are read from device memory
   const DevObs* clear_tab = a.n_clear <= kInlineObs ? a.clear_inline : a.clear;
@@ -594,6 +612,7 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
       finalize_bounds(a.ba, a.boxes, a.infl, a.win);
     }
   }
+  if (a.trace && threadIdx.x == 0) atomicMax(&a.trace[1], trace_now());
 }
 
 // Costmap2DPublisher's cost -> occupancy translation (src/costmap_2d_publisher.cpp:56-71, applied per cell in
@@ -1120,6 +1139,7 @@ struct MergeSeedArgs {
   // its tile (master cells and seed bits) is written, and k_inflate's tiles wait for just the tiles they read
   unsigned* ready = nullptr;
   unsigned epoch = 0;
+  unsigned long long* trace = nullptr;
 };
 
 __device__ __forceinline__ uint32_t inc4(uint32_t x) {  // per-byte x + 1 (mod 256), no carry between bytes
@@ -1267,6 +1287,7 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   // launched with programmatic stream serialization: let k_inflate be scheduled as soon as every CTA of this grid
   // is resident, and wait for the kernel before us (window, obstacle grid) before reading anything
   cudaTriggerProgrammaticLaunchCompletion();
+  trace_start(a.trace, 1);
   constexpr int kW = kMSGroupsX * 16, kH = kMSRowsY * kMSRowIters;
   const int bx0 = blockIdx.x * kW, by0 = blockIdx.y * kH;
   DevWindow w;
@@ -1299,6 +1320,9 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   } else if (x < (int)a.pitch) {
     merge_seed_items<false>(a, w, x, by0, sx0, sxn, sy0, syn);
   }
+  trace_end(a.trace, 1);
+  if (a.trace && a.early && bx0 < a.exn && bx0 + kW > a.ex0 && by0 < a.eyn && by0 + kH > a.ey0 && (threadIdx.x | threadIdx.y) == 0)
+    atomicMax(&a.trace[6], trace_now());
   if (a.ready) {  // (early mode: the window is the whole map, no CTA left above)
     __syncthreads();
     if ((threadIdx.x | threadIdx.y) == 0)  // (release at gpu scope: cumulative over what the barrier made visible here)
@@ -1312,6 +1336,7 @@ struct InflateArgs {
   const DevWindow* win;
   int R;
   int reach2;              // largest squared distance whose cost is not 0: nothing beyond it can change a cell
+  int reach;               // floor(sqrt(reach2)): the effective radius in cells
   const uint8_t* cost_d2;  // R*R+1 entries: cost by squared cell distance
   const uint32_t* seeds;   // the bitmask written by k_merge_seed, viewed as 32-bit words
   // early mode (see MergeSeedArgs): the window is the whole map and a tile starts as soon as the k_merge_seed tiles it
@@ -1319,26 +1344,29 @@ struct InflateArgs {
   const unsigned* ready = nullptr;
   unsigned epoch = 0;
   int ready_pitch = 0;  // k_merge_seed's gridDim.x
+  unsigned long long* trace = nullptr;
 };
 
 // RMAX bounds the effective reach (in cells) this instantiation can handle: the phase-3 walk is unrolled over
 // 8 + 2 * RMAX region rows, so a small RMAX keeps the kernel's code (and its instruction-cache footprint) small.
 template <int RMAX>
-__global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
+__global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   constexpr int kRows = kITY + 2 * RMAX;       // region rows this instantiation can hold
   __shared__ uint32_t pbits[kRows * 4];        // seed words W0..W3 of each region row (columns tx0-32 .. tx0+95), pruned
   __shared__ uint32_t h2[kRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
   // the unpruned seed words only live until the pruning pass has read them: they borrow the start of h2, which phase 2
   // fills afterwards (and only for seeded rows; phase 3 never reads another row)
   uint32_t* const sbits = h2;
-  __shared__ uint32_t rowmask[kIMaskWords];   // bit (r + 32) <-> region row r has seeds
-  __shared__ uint32_t fullmask[kIMaskWords];  // bit (r + 32) <-> region row r is seeded in all 64 columns of the tile
+  __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
+  __shared__ uint8_t rowlist[kRows];         // the same rows as a list (any order), n_seeded of them
+  __shared__ int n_seeded;
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
   // early mode: the flags of the k_merge_seed tiles this tile reads (seeds: columns tx0 - 32 .. tx0 + 95, rows
   // ty0 - R .. ty0 + kITY + R - 1; master cells: the tile itself), one per thread, requested before anything else
   const unsigned* my_flag = nullptr;
   unsigned flag_seen = 0;
+  trace_start(a.trace, 2);
   if (a.ready) {
     constexpr int kMW = kMSGroupsX * 16, kMH = kMSRowsY * kMSRowIters;
     const int mx0 = max(0, tx0 - 32) / kMW, mx1 = min((int)a.pitch - 1, tx0 + kITX + 31) / kMW;
@@ -1364,6 +1392,10 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     }
     __syncthreads();
     w.x0 = 0; w.xn = (int)a.sx; w.y0 = 0; w.yn = (int)a.sy; w.valid = 1;
+    if (a.trace && threadIdx.x == 0) {
+      atomicMin(&a.trace[7], trace_now());
+      atomicMax(&a.trace[8], trace_now());
+    }
   } else {
     cudaGridDependencySynchronize();
     w = *a.win;
@@ -1375,7 +1407,7 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
   }
   // from here on R is the effective reach: seeds further than sqrt(reach2) cells away only ever contribute cost 0,
   // and max(old, 0) / the NO_INFORMATION rule leave the cell as it is
-  const int R = (int)sqrtf((float)a.reach2 + 0.5f);
+  const int R = a.reach;
   const int rows = kITY + 2 * R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned sp32 = seed_pitch16(a.pitch) / 2;
@@ -1390,8 +1422,12 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     sbits[i] = v;
     any |= v != 0;
   }
-  if (tid < kIMaskWords) rowmask[tid] = fullmask[tid] = 0;
-  if (!__syncthreads_or(any)) return;
+  if (tid < kIMaskWords) rowmask[tid] = 0;
+  if (tid == 0) n_seeded = 0;
+  if (!__syncthreads_or(any)) {
+    trace_end(a.trace, 2);
+    return;
+  }
 
   // ---- interior seeds cannot be the nearest seed of any other cell: a seed whose four neighbours are seeds too has,
   // for every non-seed cell p, a neighbouring seed strictly closer to p (step along the larger coordinate difference),
@@ -1412,21 +1448,18 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
     if (wq == 0) keep &= ~(0xffffffffu >> R);
     if (wq == 3) keep &= (1u << R) - 1u;
     pbits[i] = keep;
-    if (keep) atomicOr(&rowmask[(r >> 5) + 1], 1u << (r & 31));
+    if (keep) {  // whoever sets the row's bit first also lists the row
+      const uint32_t bit = 1u << (r & 31);
+      if (!(atomicOr(&rowmask[(r >> 5) + 1], bit) & bit)) rowlist[atomicAdd(&n_seeded, 1)] = (uint8_t)r;
+    }
   }
   __syncthreads();
-  // rows whose seeds cover every column of the tile (the long side of a wall or shelf): such a row hides every seeded
-  // row behind it from the cells in front of it -- (j' - k)^2 > (j - k)^2 + 0 -- which phase 3 uses to shorten its walk
-  for (int r = tid; r < rows; r += kIThreads)
-    if ((pbits[4 * r + 1] & pbits[4 * r + 2]) == 0xffffffffu) atomicOr(&fullmask[(r >> 5) + 1], 1u << (r & 31));
 
-  // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row; warp w takes the
-  // seeded rows r = w mod 8, straight from the row mask)
-  for (int wi = 0; wi * 32 < rows; ++wi) {
-    uint32_t m = rowmask[wi + 1] & (0x01010101u << warp);
-    while (m) {
-      const int r = wi * 32 + __ffs(m) - 1;
-      m &= m - 1;
+  // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row, straight from the list)
+  {
+    const int n_rows_seeded = n_seeded;
+    for (int li = warp; li < n_rows_seeded; li += kIThreads / 32) {
+      const int r = rowlist[li];
       const uint32_t W0 = pbits[4 * r], W1 = pbits[4 * r + 1], W2 = pbits[4 * r + 2], W3 = pbits[4 * r + 3];
       const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
       uint32_t packed = 0;
@@ -1479,38 +1512,6 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
         nrows += __popc(mw[q]);
       }
       if (anyrow == 0) continue;  // no seeded row anywhere near these eight rows: nothing to inflate
-      {
-        // window bit b <-> j = b - RMAX; the eight output rows are bits RMAX .. RMAX + 7.  Above them only the rows up
-        // to (and including) the nearest full row can matter, below them likewise.
-        auto below = [](int n) -> uint32_t { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : (1u << n) - 1u); };
-        uint32_t fw[NW];
-        uint32_t anyfull = 0;
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-          fw[q] = __funnelshift_r(fullmask[wi + q], fullmask[wi + q + 1], sh) & mw[q];
-          anyfull |= fw[q];
-        }
-        if (anyfull) {
-          int bt = -1, bb = -1;
-#pragma unroll
-          for (int q = NW - 1; q >= 0; --q) {
-            const uint32_t am = fw[q] & below(RMAX - 32 * q);
-            if (bt < 0 && am) bt = 32 * q + 31 - __clz(am);
-          }
-#pragma unroll
-          for (int q = 0; q < NW; ++q) {
-            const uint32_t bm = fw[q] & ~below(RMAX + 8 - 32 * q);
-            if (bb < 0 && bm) bb = 32 * q + __ffs(bm) - 1;
-          }
-          nrows = 0;
-#pragma unroll
-          for (int q = 0; q < NW; ++q) {
-            if (bt > 0) mw[q] &= ~below(bt - 32 * q);
-            if (bb >= 0) mw[q] &= below(bb + 1 - 32 * q);
-            nrows += __popc(mw[q]);
-          }
-        }
-      }
       if (nrows <= kISparseRows) {
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
@@ -1592,6 +1593,7 @@ __global__ void __launch_bounds__(kIThreads) k_inflate(InflateArgs a) {
       }
     }
   }
+  trace_end(a.trace, 2);
 }
 
 inline size_t update_costs_smem(int R) {

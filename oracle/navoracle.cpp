@@ -24,6 +24,7 @@
 
 #include "oracle_api.h"
 #include "scan_ingest_restated.h"
+#include "plan_restated.h"
 
 namespace {
 

@@ -206,6 +206,11 @@ double navo_tp_score_trajectory(void* h, const double pose[3], const double vel[
 /* path_map_ (0) / goal_map_ (1) target_dist after the last findBestPath */
 void navo_tp_get_grid(void* h, int which, double* out);
 
+/* plan preprocessing, restated in oracle/plan_restated.h (see its header: tf is not in the tree) */
+int navo_plan_transform(const double* plan_xyz, int n, const double robot_xy[2], const double m[9], const double t[3],
+                        double dist_threshold, int* first_out, double* out_xyz);
+int navo_plan_prune(const double* plan_xyz, int n, const double robot_xy[2]);
+
 const char* navo_impl_name(void);
 
 #ifdef __cplusplus

@@ -133,6 +133,8 @@ def _declare(lib, prefix):
         "tp_find_best_path": (i, [vp, _f64p, _f64p, C.POINTER(TpResult), _f64p, i]),
         "tp_score_trajectory": (d, [vp, _f64p, _f64p, _f64p]),
         "tp_get_grid": (None, [vp, i, _f64p]),
+        "plan_transform": (i, [_f64p, i, _f64p, _f64p, _f64p, d, _i32p, _f64p]),
+        "plan_prune": (i, [_f64p, i, _f64p]),
     }
     for name, (res, args) in sig.items():
         f = g(name)
@@ -407,6 +409,36 @@ class Api:
 
     def trajectory_planner(self, *a, **k):
         return TrajectoryPlanner(self, *a, **k)
+
+    def plans_transform(self, plans, robot_xy, transforms, thresholds):
+        """transformGlobalPlan plan by plan (same shape as navigation_b200.api.Api.plans_transform)."""
+        first, outs = [], []
+        for k, p in enumerate(plans):
+            a = np.zeros((len(p), 3))
+            q = np.asarray(p, dtype=np.float64).reshape(len(p), -1) if len(p) else np.zeros((0, 3))
+            a[:, :q.shape[1]] = q
+            a = np.ascontiguousarray(a)
+            rob = np.ascontiguousarray(robot_xy[k], dtype=np.float64)
+            tf = np.ascontiguousarray(transforms[k], dtype=np.float64).reshape(12)
+            m, t = np.ascontiguousarray(tf[:9]), np.ascontiguousarray(tf[9:])
+            f = np.zeros(1, dtype=np.int32)
+            out = np.zeros_like(a)
+            n = self.lib.navo_plan_transform(_p(a, _f64p), len(a), _p(rob, _f64p), _p(m, _f64p), _p(t, _f64p),
+                                             float(thresholds[k]), _p(f, _i32p), _p(out, _f64p))
+            first.append(int(f[0]))
+            outs.append(out[:n].copy())
+        return np.array(first, dtype=np.int32), outs
+
+    def plans_prune(self, plans, robot_xy):
+        out = []
+        for k, p in enumerate(plans):
+            a = np.zeros((len(p), 3))
+            q = np.asarray(p, dtype=np.float64).reshape(len(p), -1) if len(p) else np.zeros((0, 3))
+            a[:, :q.shape[1]] = q
+            a = np.ascontiguousarray(a)
+            rob = np.ascontiguousarray(robot_xy[k], dtype=np.float64)
+            out.append(self.lib.navo_plan_prune(_p(a, _f64p), len(a), _p(rob, _f64p)))
+        return np.array(out, dtype=np.int32)
 
     def interpret_values(self, values, track_unknown=True, unknown_cost_value=255, lethal_threshold=100,
                          trinary=True):

@@ -48,6 +48,7 @@
 
 #include "oracle_api.h"
 #include "scan_ingest_restated.h"
+#include "plan_restated.h"
 
 // ---- footprint.cpp needs boost::tokenizer/XmlRpc; its two pure functions are restated (footprint.cpp:41-67,106-120)
 namespace costmap_2d {

@@ -23,7 +23,7 @@ def measure(label):
     for _ in range(5):
         cm.touch_grid_layer(s, 0, 0, size, size)
         cm.update_map(*robot)
-    n = 30
+    n = 100
     e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
     for k in range(n):
@@ -34,7 +34,7 @@ def measure(label):
         cm.update_map_async(*robot)
         e1[k].record(stream)
     torch.cuda.synchronize()
-    cold = np.median([a.elapsed_time(b) for a, b in zip(e0, e1)])
+    cold = np.mean([a.elapsed_time(b) for a, b in zip(e0, e1)])
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
     for k in range(n):
