@@ -602,6 +602,12 @@ class Dwa:
                     best_index=res.best_index, n_samples=res.n_samples, n_scored=res.n_scored,
                     points=pts[:res.n_points].copy())
 
+    def prepared(self, pose, vel, footprint_xy, max_points=256):
+        """The arguments of a search marshalled once, the way a C++ caller holds them (plain arrays and a result
+        struct): repeated calls then cost the C-ABI call only.  Returns an object with find_best_path() and
+        find_best_path_sharded()."""
+        return _PreparedSearch(self, pose, vel, footprint_xy, max_points)
+
     def find_best_path_sharded(self, pose, vel, footprint_xy, max_points=4096):
         self.find_best_path_sharded_async(pose, vel, footprint_xy)
         return self.sharded_collect(pose, max_points)
@@ -694,6 +700,32 @@ class TrajectoryPlanner:
         n = C.c_int32()
         self.api.check(self.lib.navgpu_tp_last_sample_count(self.h, C.byref(n)))
         return int(n.value)
+
+
+class _PreparedSearch:
+    def __init__(self, dwa, pose, vel, footprint_xy, max_points):
+        self.dwa, self.lib, self.check = dwa, dwa.lib, dwa.api.check
+        self.p = np.ascontiguousarray(pose, dtype=np.float64)
+        self.v = np.ascontiguousarray(vel, dtype=np.float64)
+        self.f = np.ascontiguousarray(footprint_xy, dtype=np.float64).reshape(-1, 2)
+        self.res = DwaResult()
+        self.pts = np.zeros((max_points, 3))
+        self.max_points = max_points
+        self._a = (_p(self.p, _f64p), _p(self.v, _f64p), _p(self.f, _f64p), self.f.shape[0])
+        self._r = (C.byref(self.res), _p(self.pts, _f64p), max_points)
+
+    def _result(self):
+        r = self.res
+        return dict(ok=r.cost >= 0, cost=r.cost, xv=r.xv, yv=r.yv, thetav=r.thetav, best_index=r.best_index,
+                    n_samples=r.n_samples, n_scored=r.n_scored, points=self.pts[:min(r.n_points, self.max_points)])
+
+    def find_best_path(self):
+        self.check(self.lib.navgpu_dwa_find_best_path(self.dwa.h, *self._a, self._r[0], None, 0, self._r[1], self._r[2]))
+        return self._result()
+
+    def find_best_path_sharded(self):
+        self.check(self.lib.navgpu_dwa_find_best_path_sharded(self.dwa.h, *self._a, *self._r))
+        return self._result()
 
 
 class Fleet:

@@ -151,6 +151,7 @@ struct Layer {
   cudaEvent_t ev_stage = nullptr;
   size_t scan_capacity = 0;
   int n_clear = 0, n_mark = 0, total_rays = 0, total_marks = 0;
+  uint8_t* d_tile_used = nullptr;  // MergeLayers::used (plain obstacle layers of non-rolling, FREE_SPACE-default costmaps)
   // world box of every sensor origin and observation point (rays and marks stay inside it); valid only when the
   // points were seen on the host (navgpu_obstacle_set_observations)
   bool touch_box_valid = false;
@@ -673,6 +674,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     oa.do_finalize = (int)li == last_obstacle;
     if (oa.do_finalize) oa.ba = ba;
     oa.trace = h->d_trace;
+    oa.tile_used = L.d_tile_used;
     oa.boxes = h->d_boxes; oa.infl = h->d_infl; oa.win = h->d_win;
     const int blocks = std::max(1, (L.total_rays * 32 + kObstacleThreads - 1) / kObstacleThreads);
     k_obstacle_update<<<blocks, kObstacleThreads, 0, h->stream>>>(oa);
@@ -708,6 +710,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
       if (policy == NAVGPU_NOTHING) continue;
       ml.grid[ml.n] = L.grid[L.cur];
       ml.policy[ml.n] = policy;
+      ml.used[ml.n] = L.d_tile_used;
       ++ml.n;
       pending = true;
     } else {
@@ -789,7 +792,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
     cudaFree(L.d_clear); cudaFree(L.d_mark); cudaFree(L.d_xyz); cudaFree(L.d_cost_d2); cudaFree(L.d_rank); cudaFree(L.d_cost2d); cudaFree(L.d_mark_cells); cudaFree(L.d_scan);
     if (L.h_stage) cudaFreeHost(L.h_stage);
     if (L.ev_stage) cudaEventDestroy(L.ev_stage);
-    cudaFree(L.vox[0]); cudaFree(L.vox[1]);
+    cudaFree(L.vox[0]); cudaFree(L.vox[1]); cudaFree(L.d_tile_used);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
   cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
@@ -837,6 +840,15 @@ int navgpu_costmap_add_obstacle_layer(navgpu_costmap* h, int combination_method,
   L.footprint_clearing = footprint_clearing != 0;
   L.max_obstacle_height = max_obstacle_height;
   NAVGPU_TRY(add_cost_layer(h, L));
+  // The only writers of such a layer's grid are its own kernel's clears (FREE_SPACE) and marks: the tiles without a mark
+  // are known to hold the default value.  Not for rolling maps (the grid shifts) or NO_INFORMATION defaults.
+  static const bool no_summary = getenv("NAVGPU_NO_LAYER_SUMMARY") != nullptr;  // measurement switch
+  if (!h->rolling && L.def == kFree && !no_summary) {
+    const size_t n_tiles = size_t((h->pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16)) *
+                           ((h->sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
+    NAVGPU_CUDA(cudaMalloc(&L.d_tile_used, n_tiles));
+    NAVGPU_CUDA(cudaMemsetAsync(L.d_tile_used, 0, n_tiles, h->stream));
+  }
   h->layers.push_back(L);
   if (layer_out) *layer_out = (int)h->layers.size() - 1;
   return NAVGPU_OK;

@@ -318,7 +318,9 @@ __device__ __forceinline__ void mark_prepare(const Geom& g, const DevObs* __rest
   cells[t] = cell;
 }
 
-__device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, const long long* cells, int total_points) {
+constexpr unsigned kMarkTileW = 256, kMarkTileH = 32;  // = k_merge_seed's tile (static_assert next to that kernel)
+__device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, const long long* cells, int total_points,
+                                                uint8_t* __restrict__ tile_used = nullptr, unsigned pitch = 1) {
   const int nt = blockDim.x;
   for (int base = threadIdx.x; base < total_points; base += 4 * nt) {  // four loads in flight per thread
     long long cell[4];
@@ -329,7 +331,13 @@ __device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, cons
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (cell[u] >= 0) grid[cell[u]] = kLethal;
+      if (cell[u] >= 0) {
+        grid[cell[u]] = kLethal;
+        if (tile_used) {  // MergeLayers::used: this tile no longer is all FREE_SPACE
+          const unsigned y = (unsigned)(cell[u] / pitch), x = (unsigned)(cell[u] - (long long)y * pitch);
+          tile_used[(y / (kMarkTileH)) * ((pitch + kMarkTileW - 1) / kMarkTileW) + x / kMarkTileW] = 1;
+        }
+      }
   }
 }
 
@@ -568,6 +576,7 @@ struct ObstacleArgs {
   InflationBoundsState* infl;
   DevWindow* win;
   unsigned long long* trace = nullptr;
+  uint8_t* tile_used = nullptr;  // MergeLayers::used of this layer (nullable)
 };
 constexpr int kObstacleThreads = 256;
 
@@ -602,7 +611,7 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  mark_commit_cta(a.grid, a.mark_cells, a.total_marks);
+  mark_commit_cta(a.grid, a.mark_cells, a.total_marks, a.tile_used, a.g.pitch);
   __syncthreads();
   if (a.do_poly) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
   if (threadIdx.x == 0) {
@@ -934,6 +943,10 @@ struct MergeLayers {
   int n;
   const uint8_t* grid[kMaxLayers];
   int policy[kMaxLayers];
+  // Per layer, nullable: one byte per k_merge_seed tile (256 x 32 cells, row-major over ceil(pitch / 256) columns), 0 as
+  // long as every cell of the tile still holds FREE_SPACE.  An obstacle layer is FREE_SPACE almost everywhere (marks
+  // exist where scans ever ended): the merge takes zeros for such a tile instead of reading 8 KB of them from HBM.
+  const uint8_t* used[kMaxLayers] = {};
 };
 struct UpdateArgs {
   uint8_t* master;
@@ -1117,6 +1130,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 //                  InflationLayer's max / NO_INFORMATION rule directly on the master grid, touching only rows that
 //                  inflation reaches.  A tile whose seed words are all zero exits after the load.
 constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2;  // k_merge_seed: CTA = 256 columns x 32 rows
+static_assert(kMSGroupsX * 16 == (int)kMarkTileW && kMSRowsY * kMSRowIters == (int)kMarkTileH, "MergeLayers::used tile");
 constexpr int kITX = 64, kITY = 128, kIThreads = 256, kIMaxRows = kITY + 2 * 31;
 constexpr int kIMaskWords = (kIMaxRows + 32 + 70 + 31) / 32 + 1;
 constexpr int kISparseRows = 12;  // k_inflate phase 3: up to this many seeded rows per window take the set-bit walk
@@ -1202,7 +1216,7 @@ __device__ __forceinline__ uint32_t lethal_bits4(uint32_t v) {  // one bit per b
 // CTA tile lies inside the window, the seed region and the map, so every per-group edge test folds away.
 template <bool kInterior>
 __device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const DevWindow& w, int x, int by0, int sx0,
-                                                 int sxn, int sy0, int syn) {
+                                                 int sxn, int sy0, int syn, unsigned used_mask) {
   const int R = a.R;
   const unsigned sp16 = seed_pitch16(a.pitch);
   // A window that reaches the map's right edge owns the row padding behind it as well (nothing reads those bytes, and
@@ -1227,8 +1241,8 @@ __device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const D
     const bool need_master = any_in ? !(all_in && a.do_reset) : (col_seed && y >= sy0 && y < syn);
     if (need_master) mv[it] = *reinterpret_cast<const uint4*>(a.master + off);
     if (any_in) {
-      if (a.ml.n > 0) lv[it][0] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off);
-      if (a.ml.n > 1) lv[it][1] = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off);
+      if (a.ml.n > 0 && (used_mask & 1u)) lv[it][0] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off);
+      if (a.ml.n > 1 && (used_mask & 2u)) lv[it][1] = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off);
     }
   }
 #pragma unroll
@@ -1247,14 +1261,15 @@ __device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const D
       if (a.ml.n > 0) v = merge16(v, lv[it][0], a.ml.policy[0]);
       if (a.ml.n > 1) v = merge16(v, lv[it][1], a.ml.policy[1]);
       for (int l = 2; l < a.ml.n; ++l)
-        v = merge16(v, *reinterpret_cast<const uint4*>(a.ml.grid[l] + off), a.ml.policy[l]);
+        v = merge16(v, (used_mask >> l) & 1u ? *reinterpret_cast<const uint4*>(a.ml.grid[l] + off) : make_uint4(0, 0, 0, 0),
+                    a.ml.policy[l]);
     } else if (any_in) {  // group straddles the window edge: per-cell path
       uint32_t vv[4] = {v.x, v.y, v.z, v.w};
       for (int l = -1; l < a.ml.n; ++l) {
         uint4 lv4 = make_uint4(0, 0, 0, 0);
         if (l == 0) lv4 = lv[it][0];
         else if (l == 1) lv4 = lv[it][1];
-        else if (l >= 2) lv4 = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
+        else if (l >= 2 && ((used_mask >> l) & 1u)) lv4 = *reinterpret_cast<const uint4*>(a.ml.grid[l] + off);
         const uint32_t lw[4] = {lv4.x, lv4.y, lv4.z, lv4.w};
         for (int i = 0; i < 16; ++i) {
           const int cx = x + i;
@@ -1315,10 +1330,15 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   const int x = bx0 + threadIdx.x * 16;
   // the window lies inside the map, the seed region contains the window: a tile inside the window is interior
   const bool interior = bx0 >= w.x0 && bx0 + kW <= w.xn && by0 >= w.y0 && by0 + kH <= w.yn;
+  // layers whose tile summary says "all FREE_SPACE here" are not read (after the wait above: the obstacle kernel sets
+  // the bytes of the tiles it marks)
+  unsigned used_mask = 0xffffffffu;
+  for (int l = 0; l < a.ml.n; ++l)
+    if (a.ml.used[l] && a.ml.used[l][blockIdx.y * gridDim.x + blockIdx.x] == 0) used_mask &= ~(1u << l);
   if (interior) {
-    merge_seed_items<true>(a, w, x, by0, sx0, sxn, sy0, syn);
+    merge_seed_items<true>(a, w, x, by0, sx0, sxn, sy0, syn, used_mask);
   } else if (x < (int)a.pitch) {
-    merge_seed_items<false>(a, w, x, by0, sx0, sxn, sy0, syn);
+    merge_seed_items<false>(a, w, x, by0, sx0, sxn, sy0, syn, used_mask);
   }
   trace_end(a.trace, 1);
   if (a.trace && a.early && bx0 < a.exn && bx0 + kW > a.ex0 && by0 < a.eyn && by0 + kH > a.ey0 && (threadIdx.x | threadIdx.y) == 0)

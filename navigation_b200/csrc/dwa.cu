@@ -162,6 +162,10 @@ struct navgpu_dwa {
   uint32_t* d_dist[4] = {nullptr, nullptr, nullptr, nullptr};
   float* d_samples = nullptr;
   size_t samples_capacity = 0;
+  float* h_samples_stage = nullptr;  // pinned staging of the per-axis samples
+  size_t samples_stage_capacity = 0;
+  cudaEvent_t ev_samples_stage = nullptr;
+  bool samples_on_device = false;  // d_samples holds last_samples
   double* d_block_cost = nullptr;
   long long* d_block_index = nullptr;
   size_t block_capacity = 0;
@@ -370,9 +374,27 @@ int begin_cycle(navgpu_dwa* h, const double pose[3], const double velv[3], const
       h->d_samples = nullptr;
       NAVGPU_CUDA(cudaMalloc(&h->d_samples, s.v.size() * 2 * sizeof(float)));
       h->samples_capacity = s.v.size() * 2;
+      h->samples_on_device = false;
     }
-    NAVGPU_CUDA(cudaMemcpyAsync(h->d_samples, s.v.data(), s.v.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    NAVGPU_CUDA(cudaStreamSynchronize(h->stream));  // pageable source
+    // the samples only change with the robot's velocity and the limits: an identical set is already on the device; a new
+    // one goes through a pinned staging buffer (no wait for the stream)
+    if (!h->samples_on_device || s.v != h->last_samples) {
+      const size_t bytes = s.v.size() * sizeof(float);
+      if (bytes > h->samples_stage_capacity) {
+        if (h->h_samples_stage) cudaFreeHost(h->h_samples_stage);
+        h->h_samples_stage = nullptr;
+        NAVGPU_CUDA(cudaMallocHost(&h->h_samples_stage, 2 * bytes));
+        h->samples_stage_capacity = 2 * bytes;
+      }
+      if (!h->ev_samples_stage) NAVGPU_CUDA(cudaEventCreateWithFlags(&h->ev_samples_stage, cudaEventDisableTiming));
+      else NAVGPU_CUDA(cudaEventSynchronize(h->ev_samples_stage));
+      memcpy(h->h_samples_stage, s.v.data(), bytes);
+      NAVGPU_CUDA(cudaMemcpyAsync(h->d_samples, h->h_samples_stage, bytes, cudaMemcpyHostToDevice, h->stream));
+      NAVGPU_CUDA(cudaEventRecord(h->ev_samples_stage, h->stream));
+      h->samples_on_device = true;
+    }
+  } else {
+    h->samples_on_device = false;
   }
   h->last_samples = s.v;
   h->last_nx = s.nx; h->last_ny = s.ny; h->last_nth = s.nth;
@@ -504,6 +526,8 @@ int navgpu_dwa_destroy(navgpu_dwa* h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->d_cost_own);
   if (h->h_cost_stage) cudaFreeHost(h->h_cost_stage);
+  if (h->h_samples_stage) cudaFreeHost(h->h_samples_stage);
+  if (h->ev_samples_stage) cudaEventDestroy(h->ev_samples_stage);
   if (h->ev_cost_stage) cudaEventDestroy(h->ev_cost_stage);
   for (int k = 0; k < 3; ++k) cudaFree(h->d_plan[k]);
   for (int k = 0; k < 4; ++k) cudaFree(h->d_dist[k]);
