@@ -403,6 +403,26 @@ class Costmap:
                                                            _p(rects, _i32p), max_rects, C.byref(n), C.byref(nbytes)))
         return int(n.value), int(nbytes.value), rects[:min(int(n.value), max_rects)]
 
+    def prepared_cycle(self, obstacle_layer, grid_layer, mirror):
+        """One end-to-end update cycle with its arguments marshalled once, the way a C++ caller holds them:
+        cycle(packed_observations, robot) = navgpu_obstacle_set_observations + navgpu_grid_layer_touch (whole layer) +
+        navgpu_costmap_update_map_async + navgpu_costmap_get_changed into `mirror`; returns the bytes that crossed
+        PCIe on the way back."""
+        assert mirror.dtype == np.uint8 and mirror.flags["C_CONTIGUOUS"]
+        lib, h, check = self.lib, self.h, self.api.check
+        mptr, pitch = _p(mirror, _u8p), mirror.shape[1]
+        n, nbytes = C.c_int32(), C.c_uint64()
+        nref, bref = C.byref(n), C.byref(nbytes)
+        sx, sy = self.size_x, self.size_y
+
+        def cycle(packed, robot):
+            check(lib.navgpu_obstacle_set_observations(h, obstacle_layer, packed[0], packed[1]))
+            check(lib.navgpu_grid_layer_touch(h, grid_layer, 0, 0, sx, sy))
+            check(lib.navgpu_costmap_update_map_async(h, robot[0], robot[1], robot[2]))
+            check(lib.navgpu_costmap_get_changed(h, mptr, pitch, None, 0, nref, bref))
+            return nbytes.value
+        return cycle
+
     def mirror_invalidate(self):
         self.api.check(self.lib.navgpu_costmap_mirror_invalidate(self.h))
 

@@ -225,6 +225,13 @@ struct navgpu_costmap {
   MirrorCtl* h_mirror_ctl = nullptr;     // mapped pinned
   unsigned* d_mirror_counters = nullptr;
   unsigned mirror_capacity = 0;
+  // where the master grid can differ from the shadow (MirrorArgs::dirty / all / hx0..):
+  DevWindow* d_mirror_dirty = nullptr;  // accumulated by finalize_bounds, emptied by k_mirror_diff
+  bool mirror_all = true;               // something other than an update cycle wrote the master grid (upload, roll)
+  bool content_changed = true;          // layer contents / parameters changed by a call since the last update cycle
+  bool master_clean = false;            // the last cycle recomputed the whole map: the grid is a pure function of the layers
+  bool refine_valid = false;            // every cycle since the last get_changed changed cells only inside refine box
+  int refine[4] = {0, 0, 0, 0};         // x0, xn, y0, yn (empty: xn <= x0)
 
   size_t bytes() const { return size_t(pitch) * sy; }
   Geom geom(double gox, double goy) const { return Geom{sx, sy, pitch, res, gox, goy}; }
@@ -529,6 +536,15 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   BoundsArgs ba;
   ba.n_layers = (int)h->layers.size();
   ba.master = h->geom(h->ox, h->oy);
+  unsigned max_cell_radius = 0;
+  for (const Layer& L : h->layers)
+    if (L.kind == 2) max_cell_radius = std::max(max_cell_radius, cell_distance(L.radius, h->res));
+  ba.mirror_dirty = h->d_mirror_dirty;
+  ba.mirror_pad = 2 * (int)max_cell_radius + 2;
+  if (h->rolling) {  // the grid may shift under the shadow
+    h->mirror_all = true;
+    h->master_clean = false;
+  }
   int last_obstacle = -1;
   // Is this cycle's window the whole map as far as the host can tell (a grid layer updated as a whole, an inflation
   // layer that must re-inflate), and where can the obstacle kernels write?  Then the merge sweep need not wait for them
@@ -696,6 +712,25 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
 
   // ---- resetMap + updateCosts of every plugin, in order (:137-142), fused into as few sweeps as possible:
   // consecutive cost layers merge in one pass, an inflation layer closes the pass.
+  // host mirror: a whole-map cycle on a grid that was a pure function of the layers, with layers that changed only inside
+  // the obstacle kernels' box, changes master cells only within that box grown by the inflation radius
+  if (early.on && h->master_clean && !h->content_changed) {
+    if (early.xn > early.x0 && early.yn > early.y0) {
+      const int pad = (int)max_cell_radius + 1;
+      const int x0 = std::max(0, early.x0 - pad), xn = std::min((int)h->sx, early.xn + pad);
+      const int y0 = std::max(0, early.y0 - pad), yn = std::min((int)h->sy, early.yn + pad);
+      if (h->refine[1] > h->refine[0]) {
+        h->refine[0] = std::min(h->refine[0], x0); h->refine[1] = std::max(h->refine[1], xn);
+        h->refine[2] = std::min(h->refine[2], y0); h->refine[3] = std::max(h->refine[3], yn);
+      } else {
+        h->refine[0] = x0; h->refine[1] = xn; h->refine[2] = y0; h->refine[3] = yn;
+      }
+    }
+  } else {
+    h->refine_valid = false;
+  }
+  h->master_clean = whole_map && !h->rolling;
+  h->content_changed = false;
   MergeLayers ml;
   ml.n = 0;
   int do_reset = 1;
@@ -778,6 +813,8 @@ int navgpu_costmap_create(navgpu_costmap** out, uint32_t size_x, uint32_t size_y
   NAVGPU_CUDA(cudaMemcpy(h->d_boxes, boxes, sizeof(boxes), cudaMemcpyHostToDevice));
   NAVGPU_CUDA(cudaMemcpy(h->d_infl, infl, sizeof(infl), cudaMemcpyHostToDevice));
   NAVGPU_CUDA(cudaMemset(h->d_win, 0, sizeof(DevWindow)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_mirror_dirty, sizeof(DevWindow)));
+  NAVGPU_CUDA(cudaMemset(h->d_mirror_dirty, 0, sizeof(DevWindow)));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   *out = h.release();
   return NAVGPU_OK;
@@ -797,7 +834,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
   cudaFree(h->master[0]); cudaFree(h->master[1]);
   cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
   cudaFree(h->d_prop_state); cudaFree(h->d_prop_ctl);
-  cudaFree(h->d_shadow); cudaFree(h->d_mirror_counters); cudaFree(h->d_tile_ready); cudaFree(h->d_trace);
+  cudaFree(h->d_shadow); cudaFree(h->d_mirror_counters); cudaFree(h->d_mirror_dirty); cudaFree(h->d_tile_ready); cudaFree(h->d_trace);
   if (h->h_mirror_stage) cudaFreeHost(h->h_mirror_stage);
   if (h->h_mirror_tiles) cudaFreeHost(h->h_mirror_tiles);
   if (h->h_mirror_ctl) cudaFreeHost(h->h_mirror_ctl);
@@ -808,6 +845,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
 }
 
 static int add_cost_layer(navgpu_costmap* h, Layer& L) {
+  h->content_changed = true;
   // CostmapLayer::matchSize (costmap_layer.cpp:14-19): same geometry as the master, filled with the default value
   L.def = h->track_unknown ? kNoInfo : kFree;
   L.ox = h->ox;
@@ -913,6 +951,7 @@ int navgpu_costmap_add_inflation_layer(navgpu_costmap* h, double inflation_radiu
 
 int navgpu_costmap_set_footprint(navgpu_costmap* h, const double* xy, int n) {  // layered_costmap.cpp:163-173
   if (!h || n < 0 || (n > 0 && !xy)) return fail(NAVGPU_ERR_INVALID, "bad footprint");
+  h->content_changed = true;
   h->footprint.clear();
   for (int i = 0; i < n; ++i) h->footprint.push_back(Pt{xy[2 * i], xy[2 * i + 1]});
   footprint_radii(h->footprint, h->inscribed, h->circumscribed);
@@ -933,6 +972,7 @@ static Layer* get_layer(navgpu_costmap* h, int layer, int kind) {
 }
 
 static void mark_whole(navgpu_costmap* h, Layer* L) {
+  h->content_changed = true;  // (navgpu_grid_layer_set*: the layer's cells changed, not just its "updated" box)
   L->ux = L->uy = 0;
   L->uw = h->sx;
   L->uh = h->sy;
@@ -942,6 +982,7 @@ static void mark_whole(navgpu_costmap* h, Layer* L) {
 int navgpu_grid_layer_set(navgpu_costmap* h, int layer, const uint8_t* host_data) {
   Layer* L = get_layer(h, layer, 0);
   if (!L || !host_data) return fail(NAVGPU_ERR_INVALID, "bad grid layer");
+  h->content_changed = true;
   NAVGPU_TRY(use_device(h));
   NAVGPU_CUDA(cudaMemcpy2DAsync(L->grid[L->cur], h->pitch, host_data, h->sx, h->sx, h->sy, cudaMemcpyHostToDevice, h->stream));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
@@ -987,6 +1028,7 @@ int navgpu_grid_layer_touch(navgpu_costmap* h, int layer, uint32_t x, uint32_t y
 
 int navgpu_layer_set_enabled(navgpu_costmap* h, int layer, int enabled) {
   Layer* L = get_layer(h, layer, -1);
+  if (h) h->content_changed = true;
   if (!L) return fail(NAVGPU_ERR_INVALID, "bad layer");
   if (L->kind == 2 && L->enabled != (enabled != 0)) L->need_reinflation = true;  // reconfigureCB :104-107
   L->enabled = enabled != 0;
@@ -1205,6 +1247,7 @@ int navgpu_obstacle_get_cloud(navgpu_costmap* h, int layer, int index, float* xy
 
 int navgpu_inflation_set_params(navgpu_costmap* h, int layer, double inflation_radius, double cost_scaling_factor) {
   Layer* L = get_layer(h, layer, 2);
+  if (h) h->content_changed = true;
   if (!L) return fail(NAVGPU_ERR_INVALID, "bad inflation layer");
   if (L->weight != cost_scaling_factor || L->radius != inflation_radius) {  // inflation_layer.cpp:356-370
     L->radius = inflation_radius;
@@ -1217,6 +1260,7 @@ int navgpu_inflation_set_params(navgpu_costmap* h, int layer, double inflation_r
 
 int navgpu_inflation_set_mode(navgpu_costmap* h, int layer, int mode) {
   Layer* L = get_layer(h, layer, 2);
+  if (h) h->content_changed = true;
   if (!L || mode < 0 || mode > 1) return fail(NAVGPU_ERR_INVALID, "bad inflation layer / mode");
   if (L->mode != mode) L->tables_dirty = true;  // mode 1 keeps the 2-D rank / cost tables on the device
   L->mode = mode;
@@ -1237,6 +1281,7 @@ int navgpu_inflation_last_rounds(navgpu_costmap* h, int* rounds_out) {
 
 int navgpu_costmap_force_generic_sweep(navgpu_costmap* h, int enabled) {
   if (!h) return fail(NAVGPU_ERR_INVALID, "null handle");
+  h->content_changed = true;
   h->force_generic = enabled != 0;
   return NAVGPU_OK;
 }
@@ -1386,6 +1431,10 @@ int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t h
     h->shadow_valid = true;
     h->mirror_host = host_grid;
     h->mirror_host_pitch = host_pitch;
+    NAVGPU_CUDA(cudaMemsetAsync(h->d_mirror_dirty, 0, sizeof(DevWindow), h->stream));
+    h->mirror_all = false;
+    h->refine_valid = true;
+    h->refine[0] = h->refine[1] = h->refine[2] = h->refine[3] = 0;
     report_whole();
     return NAVGPU_OK;
   }
@@ -1400,16 +1449,57 @@ int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t h
   a.counters = h->d_mirror_counters;
   a.ctl = h->h_mirror_ctl;
   a.win = h->layers.empty() ? nullptr : h->d_win;
-  k_mirror_diff<<<(n_tiles + kMirrorWarps - 1) / kMirrorWarps, kMirrorWarps * 32, 0, h->stream>>>(a);
+  a.dirty = h->d_mirror_dirty;
+  a.all = h->mirror_all ? 1 : 0;
+  if (h->refine_valid) {
+    a.hx0 = h->refine[0]; a.hxn = h->refine[1]; a.hy0 = h->refine[2]; a.hyn = h->refine[3];
+  } else {
+    a.hx0 = 0; a.hxn = (int)h->sx; a.hy0 = 0; a.hyn = (int)h->sy;
+  }
+  // a page-locked, mapped mirror (navgpu_host_register, cudaHostAlloc) takes the tiles directly; asked every call, since
+  // the caller may have released the registration in between
+  a.host_direct = nullptr;
+  a.host_pitch = host_pitch;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_grid) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+      void* last = nullptr;  // the whole grid must lie inside the registered range: probe its last byte as well
+      cudaPointerAttributes attr_end;
+      const uint8_t* end_byte = host_grid + size_t(h->sy - 1) * host_pitch + (h->sx - 1);
+      if (cudaPointerGetAttributes(&attr_end, end_byte) == cudaSuccess && attr_end.type == cudaMemoryTypeHost && attr_end.devicePointer)
+        last = attr_end.devicePointer;
+      if (last == static_cast<uint8_t*>(attr.devicePointer) + (end_byte - host_grid)) a.host_direct = static_cast<uint8_t*>(attr.devicePointer);
+    } else {
+      cudaGetLastError();  // an ordinary pageable pointer is not an error here
+    }
+  }
+  a.tx0 = 0; a.ty0 = 0; a.tw = tiles_x; a.th = tiles_y;
+  if (!a.all && h->refine_valid) {  // the host's box bounds the work: launch only the tiles it touches (possibly none)
+    a.tx0 = (unsigned)a.hx0 / kMirrorTileW;
+    a.ty0 = (unsigned)a.hy0 / kMirrorTileH;
+    a.tw = a.hxn > a.hx0 ? ((unsigned)a.hxn + kMirrorTileW - 1) / kMirrorTileW - a.tx0 : 0u;
+    a.th = a.hyn > a.hy0 ? ((unsigned)a.hyn + kMirrorTileH - 1) / kMirrorTileH - a.ty0 : 0u;
+  }
+  h->mirror_all = false;
+  h->refine_valid = true;  // from here on: until a cycle that is not of the refinable kind
+  h->refine[0] = h->refine[1] = h->refine[2] = h->refine[3] = 0;
+  const unsigned launched_tiles = std::max(1u, a.tw * a.th);  // (one CTA at least: it publishes the counts and the window)
+  k_mirror_diff<<<(launched_tiles + kMirrorWarps - 1) / kMirrorWarps, kMirrorWarps * 32, 0, h->stream>>>(a);
   NAVGPU_LAUNCHED(1);
   NAVGPU_CUDA(cudaGetLastError());
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   const MirrorCtl& ctl = *h->h_mirror_ctl;
   if (a.win) { h->win[0] = ctl.win.x0; h->win[1] = ctl.win.xn; h->win[2] = ctl.win.y0; h->win[3] = ctl.win.yn; }
-  if (ctl.n_changed > h->mirror_capacity) {  // the shadow is up to date already; the host takes the plain copy
+  if (ctl.n_changed > h->mirror_capacity && !a.host_direct) {  // the shadow is up to date already; the host takes the plain copy
     NAVGPU_TRY(whole_grid());
     NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
     report_whole();
+    return NAVGPU_OK;
+  }
+  if (ctl.n_changed > h->mirror_capacity) {  // direct mode: the data is in place, only the tile list overflowed
+    if (n_rects_out) *n_rects_out = std::max((int)ctl.n_changed, rects_capacity + 1);  // "treat the whole grid as changed"
+    if (rects_capacity > 0) { rects_out[0] = 0; rects_out[1] = 0; rects_out[2] = (int)h->sx; rects_out[3] = (int)h->sy; }
+    if (d2h_bytes_out) *d2h_bytes_out = uint64_t(ctl.n_changed) * kMirrorTileBytes + sizeof(MirrorCtl);
     return NAVGPU_OK;
   }
   const unsigned n = ctl.n_staged;
@@ -1417,9 +1507,11 @@ int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t h
     const unsigned t = h->h_mirror_tiles[k], tx = t % tiles_x, ty = t / tiles_x;
     const unsigned x0 = tx * kMirrorTileW, y0 = ty * kMirrorTileH;
     const unsigned w = std::min<unsigned>(kMirrorTileW, h->sx - x0), hg = std::min<unsigned>(kMirrorTileH, h->sy - y0);
-    const uint8_t* src = h->h_mirror_stage + size_t(k) * kMirrorTileBytes;
-    uint8_t* dst = host_grid + size_t(y0) * host_pitch + x0;
-    for (unsigned r = 0; r < hg; ++r) memcpy(dst + size_t(r) * host_pitch, src + r * kMirrorTileW, w);
+    if (!a.host_direct) {
+      const uint8_t* src = h->h_mirror_stage + size_t(k) * kMirrorTileBytes;
+      uint8_t* dst = host_grid + size_t(y0) * host_pitch + x0;
+      for (unsigned r = 0; r < hg; ++r) memcpy(dst + size_t(r) * host_pitch, src + r * kMirrorTileW, w);
+    }
     if ((int)k < rects_capacity) {
       rects_out[4 * k] = (int)x0; rects_out[4 * k + 1] = (int)y0;
       rects_out[4 * k + 2] = (int)(x0 + w); rects_out[4 * k + 3] = (int)(y0 + hg);
@@ -1477,6 +1569,8 @@ int navgpu_costmap_get(navgpu_costmap* h, uint8_t* host_out) {
 
 int navgpu_costmap_set(navgpu_costmap* h, const uint8_t* host_in) {
   if (!h || !host_in) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  h->mirror_all = true;  // the master grid is written behind the update cycles' back
+  h->master_clean = false;
   NAVGPU_TRY(use_device(h));
   NAVGPU_CUDA(cudaMemcpy2DAsync(h->master[h->cur], h->pitch, host_in, h->sx, h->sx, h->sy, cudaMemcpyHostToDevice, h->stream));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));

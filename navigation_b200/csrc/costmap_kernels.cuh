@@ -484,6 +484,10 @@ struct BoundsArgs {
   int n_layers;
   BoundsLayer layer[kMaxLayers];
   Geom master;
+  // host mirror (mirror_kernels.cuh): every cycle adds its window, grown by what inflation can write beyond it, to the
+  // box of cells the master grid may have changed in since the mirror was last brought up to date
+  DevWindow* mirror_dirty = nullptr;
+  int mirror_pad = 0;  // cells: 2 x the largest cell inflation radius of the stack (writes reach window +- 2R)
 };
 struct InflationBoundsState {
   double last_min_x, last_min_y, last_max_x, last_max_y;
@@ -537,6 +541,17 @@ __device__ __forceinline__ void finalize_bounds(const BoundsArgs& a, DevBox* box
   yn = min((int)g.sy, yn + 1);
   win->x0 = x0; win->xn = xn; win->y0 = y0; win->yn = yn;
   win->valid = !(xn < x0 || yn < y0);
+  if (a.mirror_dirty && win->valid) {
+    DevWindow& d = *a.mirror_dirty;
+    const int p = a.mirror_pad;
+    const int dx0 = max(0, x0 - p), dxn = min((int)g.sx, xn + p), dy0 = max(0, y0 - p), dyn = min((int)g.sy, yn + p);
+    if (d.valid) {
+      d.x0 = min(d.x0, dx0); d.xn = max(d.xn, dxn); d.y0 = min(d.y0, dy0); d.yn = max(d.yn, dyn);
+    } else {
+      d.x0 = dx0; d.xn = dxn; d.y0 = dy0; d.yn = dyn;
+      d.valid = 1;
+    }
+  }
 }
 
 __global__ void k_finalize_bounds(BoundsArgs a, DevBox* boxes, InflationBoundsState* infl, DevWindow* win) {
@@ -1380,6 +1395,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
   __shared__ uint8_t rowlist[kRows];         // the same rows as a list (any order), n_seeded of them
   __shared__ int n_seeded;
+  __shared__ int next_group;                 // phase 3: the next 8-row group nobody has taken yet
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
   // early mode: the flags of the k_merge_seed tiles this tile reads (seeds: columns tx0 - 32 .. tx0 + 95, rows
@@ -1443,7 +1459,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     any |= v != 0;
   }
   if (tid < kIMaskWords) rowmask[tid] = 0;
-  if (tid == 0) n_seeded = 0;
+  if (tid == 0) n_seeded = next_group = 0;
   if (!__syncthreads_or(any)) {
     trace_end(a.trace, 2);
     return;
@@ -1499,12 +1515,18 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   }
   __syncthreads();
 
-  // ---- phase 3 + epilogue: each warp owns 64 columns x 8 rows at a time
+  // ---- phase 3 + epilogue: a warp takes 64 columns x 8 rows at a time
   const uint32_t R2x2 = (uint32_t)a.reach2 * 0x10001u;
   const int x = tx0 + 2 * lane;
   const bool xok = x < (int)a.sx;
   const uint32_t keep_hi = x + 1 >= (int)a.sx ? 0xff00u : 0u;
-  for (int g = warp; g < kITY / 8; g += kIThreads / 32) {
+  // (the groups are handed out as warps become free: a group far from every seed costs a few instructions, one next to a
+  // shelf several hundred -- a fixed assignment leaves warps idle at the end of the tile)
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(&next_group, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= kITY / 8) break;
     const int yr0 = g * 8;  // first tile row of this group; region rows yr0 .. yr0 + 7 + 2R
     uint32_t acc[8];
 #pragma unroll

@@ -5,9 +5,10 @@
 // host every cycle, and at 4000 x 4000 that copy (16 MB over PCIe, ~0.3 ms) costs four times the update itself --
 // although all but a few hundred cells keep their value from one cycle to the next.  The device keeps a SHADOW of what
 // the host mirror holds; k_mirror_diff compares the master grid with it tile by tile, writes the tiles that differ
-// straight into mapped pinned host memory (posted writes over PCIe, compacted, with their tile numbers) and brings
-// the shadow up to date.  The host then scatters those tiles into its grid: the mirror is byte-identical to the master
-// grid again, whatever happened in between (skipped cycles, rolled origins, navgpu_costmap_set).
+// straight into mapped pinned host memory (posted writes over PCIe) and brings the shadow up to date: into their own
+// place in the host mirror when that buffer is page-locked (navgpu_host_register), else compacted into a staging area
+// from which the call scatters them.  Either way the mirror is byte-identical to the master grid again, whatever
+// happened in between (skipped cycles, rolled origins, navgpu_costmap_set).
 #pragma once
 
 #include "common.cuh"
@@ -35,6 +36,19 @@ struct MirrorArgs {
   unsigned* counters;    // device: [0] changed tiles, [1] CTAs done
   MirrorCtl* ctl;        // mapped pinned
   const DevWindow* win;  // nullable
+  // Where the master grid can differ from the shadow: the box the update cycles accumulated on the device since the
+  // last call (finalize_bounds: every window grown by 2R), cut down to `hx0..hyn` when the host knows better (cycles that
+  // recomputed the whole map from layers that only changed inside the obstacle kernels' boxes), or everything when
+  // `all` is set (first call, uploads, rolled origins).  The last CTA empties the device box.
+  DevWindow* dirty;
+  int all;
+  int hx0, hxn, hy0, hyn;
+  // the grid covers the tiles [tx0, tx0 + tw) x [ty0, ty0 + th) only (all of them unless the host's box is smaller)
+  unsigned tx0, ty0, tw, th;
+  // non-null: the host mirror itself is page-locked and mapped (its address as this device sees it, rows host_pitch
+  // bytes apart) -- changed tiles are written straight to their place in it and only their numbers are staged
+  uint8_t* host_direct;
+  unsigned host_pitch;
 };
 
 // bytes of a and b that differ among the first n_valid bytes of the 16-byte group
@@ -54,10 +68,23 @@ __device__ __forceinline__ bool group_differs(const uint4& a, const uint4& b, in
 __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a) {
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned tile = blockIdx.x * kMirrorWarps + warp;
+  const unsigned local = blockIdx.x * kMirrorWarps + warp;  // index within the launched rectangle of tiles
   const unsigned n_tiles = a.tiles_x * a.tiles_y;
-  if (tile < n_tiles) {
-    const unsigned tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  const unsigned tile = local < a.tw * a.th ? (a.ty0 + local / a.tw) * a.tiles_x + a.tx0 + local % a.tw : n_tiles;
+  int rx0 = 0, rxn = (int)a.sx, ry0 = 0, ryn = (int)a.sy;
+  if (!a.all) {
+    const DevWindow d = *a.dirty;  // (read by every CTA before the last one resets it: the reset follows the ticket)
+    if (d.valid) {
+      rx0 = max(d.x0, a.hx0); rxn = min(d.xn, a.hxn); ry0 = max(d.y0, a.hy0); ryn = min(d.yn, a.hyn);
+    } else {
+      rxn = ryn = 0;  // no update cycle since the last call
+    }
+  }
+  const unsigned tx_ = tile % a.tiles_x, ty_ = tile / a.tiles_x;
+  const bool in_region = (int)(tx_ * kMirrorTileW) < rxn && (int)((tx_ + 1) * kMirrorTileW) > rx0 &&
+                         (int)(ty_ * kMirrorTileH) < ryn && (int)((ty_ + 1) * kMirrorTileH) > ry0;
+  if (tile < n_tiles && in_region) {
+    const unsigned tx = tx_, ty = ty_;
     const int x = (int)tx * kMirrorTileW + (lane & 7) * 16;
     const int y0 = (int)ty * kMirrorTileH + (lane >> 3);
     const int n_valid = min(16, max(0, (int)a.sx - x));  // the row padding is nobody's data
@@ -84,10 +111,22 @@ __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a)
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int y = y0 + 4 * p;
-        if (staged)  // rows below the map / columns right of it travel as zeros and are dropped by the host
+        const bool in_map = y < (int)a.sy && n_valid > 0;
+        if (a.host_direct) {
+          if (in_map) {
+            uint8_t* dst = a.host_direct + (size_t)y * a.host_pitch + x;
+            if (n_valid == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              *reinterpret_cast<uint4*>(dst) = m[p];
+            } else {
+              const uint32_t w4[4] = {m[p].x, m[p].y, m[p].z, m[p].w};
+              for (int b = 0; b < n_valid; ++b) dst[b] = (uint8_t)(w4[b >> 2] >> (8 * (b & 3)));
+            }
+          }
+        } else if (staged) {  // rows below the map / columns right of it travel as zeros and are dropped by the host
           *reinterpret_cast<uint4*>(a.stage + (size_t)slot * kMirrorTileBytes + ((lane >> 3) + 4 * p) * kMirrorTileW +
                                     (lane & 7) * 16) = m[p];
-        if (y < (int)a.sy && n_valid > 0) *reinterpret_cast<uint4*>(a.shadow + (size_t)y * a.pitch + x) = m[p];
+        }
+        if (in_map) *reinterpret_cast<uint4*>(a.shadow + (size_t)y * a.pitch + x) = m[p];
       }
     }
   }
@@ -106,6 +145,7 @@ __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a)
   if (a.win) a.ctl->win = *a.win;
   a.counters[0] = 0;
   a.counters[1] = 0;
+  a.dirty->valid = 0;
 }
 
 }  // namespace navgpu

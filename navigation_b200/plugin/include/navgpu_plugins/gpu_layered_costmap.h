@@ -88,6 +88,11 @@ class GpuLayeredCostmap {
                                                  lethal_threshold, trinary));
   }
   bool setLayerCosts(int layer, const unsigned char* costs) { return check(navgpu_grid_layer_set(handle_, layer, costs)); }
+  // StaticLayer's has_updated_data_ without new data (static_layer.cpp:263-285): the next updateMap covers the layer's
+  // whole extent again
+  bool markLayerUpdated(int layer) {
+    return check(navgpu_grid_layer_touch(handle_, layer, 0, 0, host_.getSizeInCellsX(), host_.getSizeInCellsY()));
+  }
   // ObstacleLayer's marking / clearing observations for the coming cycles (obstacle_layer.cpp:340-365, 450-464);
   // cloud points are float32 x, y, z exactly as pcl::PointXYZ stores them
   bool setObservations(int layer, const std::vector<costmap_2d::Observation>& marking_and_clearing) {

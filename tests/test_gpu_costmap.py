@@ -554,16 +554,20 @@ def test_voxel_layer_matches_checker(cuda, port, seed):
 
 
 # ---- the host mirror (navgpu_costmap_get_changed): byte-identical to the device master grid after every call ----------
+@pytest.mark.parametrize("registered", [False, True], ids=["pageable", "page-locked"])
 @pytest.mark.parametrize("seed", list(range(100, 112)) + list(range(0, 8)))
-def test_host_mirror_tracks_the_master_grid(cuda, seed):
+def test_host_mirror_tracks_the_master_grid(cuda, seed, registered):
     """Multi-cycle scenarios (rolling and fixed windows, every merge policy, odd map sizes): after each cycle one
     navgpu_costmap_get_changed leaves the host mirror equal to the device grid, and the window it reports is the
-    cycle's."""
+    cycle's.  A pageable mirror is filled from the staging area by the call, a page-locked one (navgpu_host_register)
+    directly by the kernel."""
     state = {}
 
     def on_cycle(cm, cyc, w):
         if "m" not in state:  # starts as garbage: the first call must bring everything
             state["m"] = np.full((cm.size_y, cm.size_x), 7, np.uint8)
+            if registered:
+                cuda.host_register(state["m"])
         n, nbytes, rects = cm.get_changed(state["m"], max_rects=8192)
         assert cm.last_window() == w
         assert np.array_equal(state["m"], cm.get()), f"mirror differs from the master grid in cycle {cyc}"
@@ -573,10 +577,15 @@ def test_host_mirror_tracks_the_master_grid(cuda, seed):
         n2, nbytes2, _ = cm.get_changed(state["m"])
         assert n2 == 0 and nbytes2 <= 64
 
-    sc.run_costmap_scenario(cuda, seed, tie_free=seed >= 100, on_cycle=on_cycle)
+    try:
+        sc.run_costmap_scenario(cuda, seed, tie_free=seed >= 100, on_cycle=on_cycle)
+    finally:
+        if registered and "m" in state:
+            cuda.host_unregister(state["m"])
 
 
-def test_host_mirror_moves_only_changed_tiles(cuda):
+@pytest.mark.parametrize("registered", [False, True], ids=["pageable", "page-locked"])
+def test_host_mirror_moves_only_changed_tiles(cuda, registered):
     """The C3 recipe at 1000^2 with the observation set changing every cycle: the mirror stays identical while only
     the tiles around the scans cross PCIe; rects cover exactly the cells that changed."""
     size = 1000
@@ -589,6 +598,8 @@ def test_host_mirror_moves_only_changed_tiles(cuda):
     cm.set_footprint(fp)
     cm.set_grid_layer(s, static)
     mirror = np.zeros((size, size), np.uint8)
+    if registered:
+        cuda.host_register(mirror)
     prev = None
     for cyc in range(6):
         _, obs, robot, _ = sets[cyc % 4]
@@ -611,6 +622,44 @@ def test_host_mirror_moves_only_changed_tiles(cuda):
             assert 0 < n < 0.25 * (size / 128) * (size / 16)
             assert nbytes < 0.3 * size * size
         prev = now
+    # things that change cells far from the scans -- behind the back of the "only the scans' box can change" shortcut
+    il = 2
+    cm.set_inflation_params(il, 0.8, 5.0)                       # every inflated cell changes
+    cm.update_map_async(*robot)
+    cm.get_changed(mirror)
+    assert np.array_equal(mirror, cm.get())
+    static2 = static.copy()
+    static2[900:910, 40:60] = 254                               # a new block in a far corner ...
+    cm.set_grid_layer(s, static2)
+    cm.update_map_async(*robot)                                 # ... in a cycle whose result is NOT fetched
+    cm.set_observations(o, sets[1][1])
+    cm.touch_grid_layer(s, 0, 0, size, size)
+    cm.update_map_async(*sets[1][2])
+    cm.get_changed(mirror)
+    assert np.array_equal(mirror, cm.get())
+    cm.set_footprint([(0.5, 0.4), (0.5, -0.4), (-0.5, -0.4), (-0.5, 0.4)])   # another inscribed radius: another cost table
+    cm.touch_grid_layer(s, 0, 0, size, size)
+    cm.update_map_async(*robot)
+    cm.get_changed(mirror)
+    assert np.array_equal(mirror, cm.get())
+    cm.set_enabled(o, False)                                    # the marks disappear everywhere
+    cm.touch_grid_layer(s, 0, 0, size, size)
+    cm.update_map_async(*robot)
+    n, nbytes, _ = cm.get_changed(mirror)
+    assert n > 0 and np.array_equal(mirror, cm.get())
+    for cyc in range(3):                                        # and back to quiet cycles: few tiles again
+        cm.touch_grid_layer(s, 0, 0, size, size)
+        cm.update_map_async(*robot)
+        n, nbytes, _ = cm.get_changed(mirror)
+        assert np.array_equal(mirror, cm.get())
+    assert n == 0
+    if registered:
+        cuda.host_unregister(mirror)
+        cm.touch_grid_layer(s, 0, 0, size, size)   # the registration is gone: the next call stages again
+        cm.set_observations(o, sets[2][1])
+        cm.update_map_async(*sets[2][2])
+        cm.get_changed(mirror)
+        assert np.array_equal(mirror, cm.get())
 
 
 def test_host_mirror_whole_grid_paths(cuda):
