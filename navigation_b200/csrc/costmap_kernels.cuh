@@ -1396,6 +1396,9 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   __shared__ uint8_t rowlist[kRows];         // the same rows as a list (any order), n_seeded of them
   __shared__ int n_seeded;
   __shared__ int next_group;                 // phase 3: the next 8-row group nobody has taken yet
+  // phase 3: dy^2 of window row j against the eight output rows k of a group, (j - k)^2 in both 16-bit halves:
+  // dy2tab[j + RMAX][k / 4] component k % 4 -- two broadcast 16-byte loads per seeded row instead of an add chain
+  __shared__ uint4 dy2tab[8 + 2 * RMAX][2];
   __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
   // early mode: the flags of the k_merge_seed tiles this tile reads (seeds: columns tx0 - 32 .. tx0 + 95, rows
@@ -1460,6 +1463,10 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   }
   if (tid < kIMaskWords) rowmask[tid] = 0;
   if (tid == 0) n_seeded = next_group = 0;
+  for (int i = tid; i < (8 + 2 * RMAX) * 8; i += kIThreads) {
+    const int d = (i >> 3) - RMAX - (i & 7);
+    reinterpret_cast<uint32_t*>(dy2tab)[i] = (uint32_t)(d * d) * 0x10001u;
+  }
   if (!__syncthreads_or(any)) {
     trace_end(a.trace, 2);
     return;
@@ -1535,7 +1542,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     // +-R only ever add candidates above the reach, which changes nothing.  Two walks over the row mask of
     // j in [-RMAX, 7 + RMAX] (warp-uniform either way):
     //  * few seeded rows (the usual case: walls, shelves): visit the set bits only; dy^2 = (j - k)^2 for k = 0..7
-    //    comes from one three-input add per k, (j-k)^2 = (j-k+1)^2 - (2j+1) + 2k, on both 16-bit halves at once;
+    //    comes from a small shared table, two broadcast 16-byte loads per row;
     //  * many seeded rows: the walk unrolled over j, so that dy^2 is an immediate operand of VIADDMNMX and the row's
     //    address an immediate offset; rows without seeds cost one bit test, eight such rows one byte test.
     {
@@ -1562,14 +1569,15 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
             const int j = __ffs(m) - 1 + 32 * q - RMAX;
             m &= m - 1;
             const uint32_t hh = hb[j * (kITX / 2)];
-            uint32_t q2 = (uint32_t)(j * j) * 0x10001u;                // dy^2 for k = 0, in both halves
-            const uint32_t nstep = (uint32_t)(-(2 * j + 1)) * 0x10001u;  // -(2j + 1), likewise (mod 2^32: exact)
-            acc[0] = __viaddmin_u16x2(hh, q2, acc[0]);
-#pragma unroll
-            for (int k = 1; k < 8; ++k) {
-              q2 = q2 + nstep + (uint32_t)(2 * k) * 0x10001u;
-              acc[k] = __viaddmin_u16x2(hh, q2, acc[k]);
-            }
+            const uint4 qa = dy2tab[j + RMAX][0], qb = dy2tab[j + RMAX][1];
+            acc[0] = __viaddmin_u16x2(hh, qa.x, acc[0]);
+            acc[1] = __viaddmin_u16x2(hh, qa.y, acc[1]);
+            acc[2] = __viaddmin_u16x2(hh, qa.z, acc[2]);
+            acc[3] = __viaddmin_u16x2(hh, qa.w, acc[3]);
+            acc[4] = __viaddmin_u16x2(hh, qb.x, acc[4]);
+            acc[5] = __viaddmin_u16x2(hh, qb.y, acc[5]);
+            acc[6] = __viaddmin_u16x2(hh, qb.z, acc[6]);
+            acc[7] = __viaddmin_u16x2(hh, qb.w, acc[7]);
           }
         }
       } else {
