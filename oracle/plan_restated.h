@@ -2,12 +2,13 @@
  * plan_restated.h -- CPU restatement of the local planners' plan preprocessing.  TEST INFRASTRUCTURE ONLY.
  *
  * The loops are the reference's own (base_local_planner/src/goal_functions.cpp): prunePlan :68-84 and the two loops of
- * transformGlobalPlan :118-149.  goal_functions.cpp itself cannot be compiled here: it needs tf::TransformListener
- * (lookupTransform, transformPose) and the tf <-> message conversions, and tf is NOT part of the reference tree
- * (package.xml dependency `tf`).  PARITY UNPINNED for that third-party part: what is restated from tf's published
- * source (tf/LinearMath/Transform.h, Matrix3x3.h, Vector3.h, geometry 1.11.x) is Transform::operator()(Vector3) =
- * (basis row . v) + origin with Vector3::dot evaluated x*x' + y*y' + z*z' left to right in double.  The reference has
- * no unit test or golden vector for either function.
+ * transformGlobalPlan :118-149.  PINNED against the reference itself: goal_functions.cpp compiles unmodified against
+ * the tf stand-in of oracle/shim_tf into oracle/_ref/libgoalref.so (oracle/goal_harness.cpp, `make goalref`), and
+ * tests/test_plan_preprocessing.py checks this restatement bit for bit against those functions and against golden
+ * vectors generated from them (tests/golden/plan_*.npz).  What stays PARITY UNPINNED is tf's own arithmetic -- tf is NOT
+ * part of the reference tree (package.xml dependency `tf`): the stand-in restates, from tf's published source
+ * (tf/LinearMath/Transform.h, Matrix3x3.h, Vector3.h, geometry 1.11.x), Transform::operator()(Vector3) =
+ * (basis row . v) + origin with Vector3::dot evaluated x*x' + y*y' + z*z' left to right in double.
  * Included by both checker libraries so that they export the same symbols.
  */
 #ifndef NAV_ORACLE_PLAN_RESTATED_H_

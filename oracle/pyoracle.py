@@ -515,6 +515,52 @@ class Api:
         return out
 
 
+class GoalRef:
+    """The reference's own transformGlobalPlan / prunePlan (oracle/_ref/libgoalref.so, `make -C oracle goalref`); same
+    call shapes as Api.plans_transform / plans_prune.  Thresholds must be multiples of 0.5 (the harness expresses them
+    as a costmap size)."""
+
+    PATH = os.path.join(HERE, "_ref", "libgoalref.so")
+
+    def __init__(self):
+        self.lib = C.CDLL(self.PATH)
+        self.lib.navref_plan_transform.restype = C.c_int
+        self.lib.navref_plan_transform.argtypes = [_f64p, C.c_int, _f64p, _f64p, _f64p, C.c_double, _i32p, _f64p]
+        self.lib.navref_plan_prune.restype = C.c_int
+        self.lib.navref_plan_prune.argtypes = [_f64p, C.c_int, _f64p]
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
+
+    @staticmethod
+    def _xyz(p):
+        a = np.zeros((len(p), 3))
+        q = np.asarray(p, dtype=np.float64).reshape(len(p), -1) if len(p) else np.zeros((0, 3))
+        a[:, :q.shape[1]] = q
+        return np.ascontiguousarray(a)
+
+    def plans_transform(self, plans, robot_xy, transforms, thresholds):
+        outs = []
+        for k, p in enumerate(plans):
+            a = self._xyz(p)
+            rob = np.ascontiguousarray(robot_xy[k], dtype=np.float64)
+            tf = np.ascontiguousarray(transforms[k], dtype=np.float64).reshape(12)
+            m, t = np.ascontiguousarray(tf[:9]), np.ascontiguousarray(tf[9:])
+            f = np.zeros(1, dtype=np.int32)
+            out = np.zeros_like(a)
+            n = self.lib.navref_plan_transform(_p(a, _f64p), len(a), _p(rob, _f64p), _p(m, _f64p), _p(t, _f64p),
+                                               float(thresholds[k]), _p(f, _i32p), _p(out, _f64p))
+            assert n >= 0 or len(a) == 0, f"navref_plan_transform failed ({n})"
+            outs.append(out[:max(n, 0)].copy())
+        return outs
+
+    def plans_prune(self, plans, robot_xy):
+        return np.array([self.lib.navref_plan_prune(_p(self._xyz(p), _f64p), len(p),
+                                                    _p(np.ascontiguousarray(robot_xy[k], dtype=np.float64), _f64p))
+                         for k, p in enumerate(plans)], dtype=np.int32)
+
+
 _cache = {}
 
 

@@ -56,6 +56,14 @@ def main():
             for k in range(2):
                 d[f"grid{c}_{k}"] = r["grids"][k].astype(np.int32)
         np.savez_compressed(os.path.join(HERE, f"tp_{seed}.npz"), **d)
+    # plan preprocessing: the reference's own transformGlobalPlan / prunePlan (oracle/_ref/libgoalref.so)
+    import test_plan_preprocessing as tpp
+    goal = po.GoalRef()
+    for seed in tpp.GOLDEN_PLAN_SEEDS:
+        plans, robots, tfs, thr = tpp.random_batch(np.random.default_rng(seed), 64)
+        outs = goal.plans_transform(plans, robots, tfs, thr)
+        np.savez_compressed(os.path.join(HERE, f"plan_{seed}.npz"), counts=np.array([len(o) for o in outs]),
+                            xyz=np.concatenate(outs), pruned=goal.plans_prune(plans, robots))
     print("golden fixtures written to", HERE)
 
 

@@ -1,9 +1,10 @@
 """Plan preprocessing: base_local_planner::transformGlobalPlan / prunePlan
 (base_local_planner/src/goal_functions.cpp:68-174).
 
-CPU part: the checker's restatement (oracle/plan_restated.h) on hand-worked cases -- the reference has no unit test for
-these functions, and tf is not in the tree, so this path is "parity unpinned" beyond the loops' own logic (see the
-restatement's header).  GPU part: the batched kernels (navgpu_plans_transform / navgpu_plans_prune, one warp per plan)
+CPU part: the checker's restatement (oracle/plan_restated.h) on hand-worked cases and against the REFERENCE'S OWN
+functions -- goal_functions.cpp compiled unmodified into oracle/_ref/libgoalref.so against a tf stand-in
+(oracle/shim_tf; tf is not in the reference tree, so the transform arithmetic itself stays "parity unpinned", the loops
+do not) -- plus golden vectors generated from it (tests/golden/plan_*.npz).  GPU part: the batched kernels (navgpu_plans_transform / navgpu_plans_prune, one warp per plan)
 against the restatement on random batches, bit for bit."""
 import numpy as np
 import pytest
@@ -110,3 +111,57 @@ def test_batched_kernels_edge_cases(cuda, port):
     for a, b in zip(o_gpu, o_ref):
         assert np.array_equal(a, b, equal_nan=True)
     assert np.array_equal(cuda.plans_prune(plans, robots), port.plans_prune(plans, robots))
+
+
+def reference_goal_functions():
+    from oracle import pyoracle
+    import os
+    if not pyoracle.GoalRef.available():
+        if os.path.isdir("/root/reference"):
+            import subprocess
+            subprocess.check_call(["make", "-s", "-C", os.path.dirname(pyoracle.__file__), "goalref"])
+        else:
+            pytest.skip("oracle/_ref/libgoalref.so not present (needs /root/reference to build)")
+    return pyoracle.GoalRef()
+
+
+@pytest.mark.parametrize("seed,n", [(11, 50), (12, 400)])
+def test_restatement_equals_the_reference_functions(port, seed, n):
+    """The restated loops against base_local_planner::transformGlobalPlan / prunePlan themselves: the kept poses (which
+    poses, how many, their transformed positions) and the number of pruned way-points, bit for bit."""
+    ref = reference_goal_functions()
+    rng = np.random.default_rng(seed)
+    plans, robots, tfs, thr = random_batch(rng, n)
+    _, o_port = port.plans_transform(plans, robots, tfs, thr)
+    o_ref = ref.plans_transform(plans, robots, tfs, thr)
+    for k, (a, b) in enumerate(zip(o_port, o_ref)):
+        assert a.shape == b.shape and np.array_equal(a, b), f"plan {k}: {a.shape} vs {b.shape}"
+    assert np.array_equal(port.plans_prune(plans, robots), ref.plans_prune(plans, robots))
+    assert sum(len(o) for o in o_ref) > 0
+
+
+GOLDEN_PLAN_SEEDS = [21, 22, 23]
+
+
+@pytest.mark.parametrize("seed", GOLDEN_PLAN_SEEDS)
+def test_restatement_equals_the_golden_vectors(port, seed):
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"plan_{seed}.npz")
+    g = np.load(path)
+    plans, robots, tfs, thr = random_batch(np.random.default_rng(seed), 64)
+    first, outs = port.plans_transform(plans, robots, tfs, thr)
+    assert np.array_equal(np.array([len(o) for o in outs]), g["counts"])
+    assert np.array_equal(np.concatenate(outs) if sum(map(len, outs)) else np.zeros((0, 3)), g["xyz"])
+    assert np.array_equal(port.plans_prune(plans, robots), g["pruned"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", GOLDEN_PLAN_SEEDS)
+def test_batched_kernels_equal_the_golden_vectors(cuda, seed):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"plan_{seed}.npz"))
+    plans, robots, tfs, thr = random_batch(np.random.default_rng(seed), 64)
+    first, outs = cuda.plans_transform(plans, robots, tfs, thr)
+    assert np.array_equal(np.array([len(o) for o in outs]), g["counts"])
+    assert np.array_equal(np.concatenate(outs), g["xyz"])
+    assert np.array_equal(cuda.plans_prune(plans, robots), g["pruned"])
