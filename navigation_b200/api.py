@@ -118,6 +118,7 @@ SIGNATURES = {
     "navgpu_costmap_get_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
     "navgpu_costmap_get_window_into": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_uint32]),
     "navgpu_costmap_last_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "navgpu_costmap_last_cta_trace": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_int]),
     "navgpu_costmap_get_changed": (C.c_int, [C.c_void_p, _u8p, C.c_uint32, _i32p, C.c_int, C.POINTER(C.c_int32),
                                              C.POINTER(C.c_uint64)]),
     "navgpu_costmap_mirror_invalidate": (C.c_int, [C.c_void_p]),
@@ -390,6 +391,11 @@ class Costmap:
     def last_trace(self):
         out = np.zeros(16, dtype=np.uint64)
         self.api.check(self.lib.navgpu_costmap_last_trace(self.h, _p(out, C.POINTER(C.c_uint64))))
+        return out
+
+    def last_cta_trace(self, kernel, n_ctas):
+        out = np.zeros((n_ctas, 8), dtype=np.uint64)
+        self.api.check(self.lib.navgpu_costmap_last_cta_trace(self.h, kernel, _p(out, C.POINTER(C.c_uint64)), n_ctas))
         return out
 
     def get_changed(self, host_grid, max_rects=0):

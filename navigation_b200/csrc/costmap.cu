@@ -378,6 +378,8 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
     m.seeds = seeds;
     m.early = a.early; m.ex0 = a.ex0; m.exn = a.exn; m.ey0 = a.ey0; m.eyn = a.eyn;
     m.trace = flags ? flags->trace : nullptr;
+    m.lean = a.ml.n >= 1 && a.ml.n <= 2 && a.ml.policy[0] == NAVGPU_TRUE_OVERWRITE &&
+             (a.ml.n == 1 || a.ml.policy[1] == NAVGPU_MAX || a.ml.policy[1] == NAVGPU_OVERWRITE) && !getenv("NAVGPU_NO_LEAN_MERGE");
     if (R > 0 && !seeds) return fail(NAVGPU_ERR_INVALID, "seed bitmask missing");
     dim3 block(kMSGroupsX, kMSRowsY);
     dim3 grid((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16), (a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
@@ -523,8 +525,11 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   NAVGPU_TRY(use_device(h));
   static const bool tracing = getenv("NAVGPU_TRACE") != nullptr;
   if (tracing) {
-    if (!h->d_trace) NAVGPU_CUDA(cudaMalloc(&h->d_trace, 16 * sizeof(unsigned long long)));
-    static const unsigned long long init[16] = {~0ull, 0, ~0ull, 0, ~0ull, 0, 0, ~0ull, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (!h->d_trace) {
+      NAVGPU_CUDA(cudaMalloc(&h->d_trace, (16 + 16 * (size_t)kCtaTraceMax) * sizeof(unsigned long long)));
+      NAVGPU_CUDA(cudaMemsetAsync(h->d_trace, 0, (16 + 16 * (size_t)kCtaTraceMax) * sizeof(unsigned long long), h->stream));
+    }
+    static const unsigned long long init[16] = {~0ull, 0, ~0ull, 0, ~0ull, 0, 0, ~0ull, 0, 0, 0, 0, 0, 0, ~0ull, 0};
     NAVGPU_CUDA(cudaMemcpyAsync(h->d_trace, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   }
   // rolling window: master origin follows the robot (:86-91)
@@ -1346,6 +1351,16 @@ int navgpu_costmap_last_trace(navgpu_costmap* h, uint64_t out[16]) {
   NAVGPU_TRY(use_device(h));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
   NAVGPU_CUDA(cudaMemcpy(out, h->d_trace, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return NAVGPU_OK;
+}
+
+int navgpu_costmap_last_cta_trace(navgpu_costmap* h, int kernel, uint64_t* out, int n_ctas) {
+  if (!h || !out || kernel < 0 || kernel > 1 || n_ctas < 0 || n_ctas > kCtaTraceMax) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (!h->d_trace) return fail(NAVGPU_ERR_INVALID, "tracing is off (set NAVGPU_TRACE before the first update)");
+  NAVGPU_TRY(use_device(h));
+  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  NAVGPU_CUDA(cudaMemcpy(out, h->d_trace + 16 + 8 * (size_t)kernel * kCtaTraceMax, 8 * (size_t)n_ctas * sizeof(uint64_t),
+                         cudaMemcpyDeviceToHost));
   return NAVGPU_OK;
 }
 

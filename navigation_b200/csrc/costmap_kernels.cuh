@@ -23,6 +23,21 @@ __device__ __forceinline__ void trace_start(unsigned long long* tr, int k) {
 __device__ __forceinline__ void trace_end(unsigned long long* tr, int k) {
   if (tr && (threadIdx.x | threadIdx.y) == 0) atomicMax(&tr[2 * k + 1], trace_now());
 }
+// per-CTA records behind the 16 summary words (tools/probe_cta_trace.py): 8 words per CTA -- start, start of the
+// actual work (after the flag / dependency wait), end, SM id, and for k_inflate the ends of its seed-word, pruning and
+// phase-2 stages -- k_merge_seed's CTAs first, k_inflate's from kCtaTraceMax
+constexpr int kCtaTraceMax = 4096;
+__device__ __forceinline__ void trace_cta(unsigned long long* tr, int kernel, int cta, int slot) {
+  if (tr && (threadIdx.x | threadIdx.y) == 0 && cta < kCtaTraceMax) {
+    unsigned long long* rec = tr + 16 + 8 * ((size_t)kernel * kCtaTraceMax + cta);
+    rec[slot] = trace_now();
+    if (slot == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      rec[3] = smid;
+    }
+  }
+}
 
 struct Geom {
   unsigned sx, sy, pitch;
@@ -622,13 +637,19 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   if (threadIdx.x == 0) {
     __threadfence();
     s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    if (a.trace) {  // [14] first / [9] last CTA through with its rays; [10] marks stored, [11] polygon cleared
+      atomicMin(&a.trace[14], trace_now());
+      atomicMax(&a.trace[9], trace_now());
+    }
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   mark_commit_cta(a.grid, a.mark_cells, a.total_marks, a.tile_used, a.g.pitch);
   __syncthreads();
+  if (a.trace && threadIdx.x == 0) a.trace[10] = trace_now();
   if (a.do_poly) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
+  if (a.trace && threadIdx.x == 0) a.trace[11] = trace_now();
   if (threadIdx.x == 0) {
     *a.ticket = 0;  // re-armed for the next cycle
     if (a.do_finalize) {
@@ -1145,6 +1166,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 //                  InflationLayer's max / NO_INFORMATION rule directly on the master grid, touching only rows that
 //                  inflation reaches.  A tile whose seed words are all zero exits after the load.
 constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2;  // k_merge_seed: CTA = 256 columns x 32 rows
+static_assert(128 + 2 * 31 <= 256, "k_inflate: one thread per region row");
 static_assert(kMSGroupsX * 16 == (int)kMarkTileW && kMSRowsY * kMSRowIters == (int)kMarkTileH, "MergeLayers::used tile");
 constexpr int kITX = 64, kITY = 128, kIThreads = 256, kIMaxRows = kITY + 2 * 31;
 constexpr int kIMaskWords = (kIMaxRows + 32 + 70 + 31) / 32 + 1;
@@ -1169,6 +1191,7 @@ struct MergeSeedArgs {
   unsigned* ready = nullptr;
   unsigned epoch = 0;
   unsigned long long* trace = nullptr;
+  int lean = 0;  // the stack is "TrueOverwrite, then at most one Max / Overwrite layer": interior tiles take merge_seed_lean
 };
 
 __device__ __forceinline__ uint32_t inc4(uint32_t x) {  // per-byte x + 1 (mod 256), no carry between bytes
@@ -1222,9 +1245,68 @@ __device__ __forceinline__ uint4 merge16(uint4 m, uint4 v, int policy) {
   }
 }
 
+// bit 7 of every byte of x that equals 255 (the low seven bits carry into bit 7 exactly when they are all set)
+__device__ __forceinline__ uint32_t is255_4(uint32_t x) { return ((x & 0x7f7f7f7fu) + 0x01010101u) & x & 0x80808080u; }
+
 __device__ __forceinline__ uint32_t lethal_bits4(uint32_t v) {  // one bit per byte that equals LETHAL_OBSTACLE
-  const uint32_t e = __vcmpeq4(v, 0xfefefefeu) & 0x01010101u;
+  const uint32_t e = is255_4(v ^ 0x01010101u) >> 7;
   return (e * 0x01020408u) >> 24;
+}
+
+// k_merge_seed on an interior tile of the usual stack: layer 0 merged with TrueOverwrite (StaticLayer on a non-rolling
+// map, plugins/static_layer.cpp:318-326 -- whatever resetMap left is overwritten), optionally one more layer merged
+// with Max or Overwrite (ObstacleLayer, plugins/obstacle_layer.cpp:431-443).  Same results as merge_seed_items<true>;
+// what differs is the instruction count: 16-cell groups without a byte >= 128 (free space and low costs: almost all of
+// a map) hold neither NO_INFORMATION nor LETHAL_OBSTACLE, so merging an all-FREE_SPACE group into them changes
+// nothing and they seed nothing, and the tile summary byte of the second layer is fetched behind the first layer's
+// loads instead of in front of them.
+template <bool kEdge>
+__device__ __forceinline__ void merge_seed_lean(const MergeSeedArgs& a, int x, int by0) {
+  // kEdge: the tile reaches beyond the map's last row or column (the window being the whole map there): rows past the
+  // map are skipped, the row padding behind the last column is written like cells (nothing reads it) and seeds nothing
+  if (kEdge && x >= (int)a.pitch) return;
+  const int y0 = by0 + threadIdx.y;
+  const size_t off = (size_t)y0 * a.pitch + x, rs = (size_t)kMSRowsY * a.pitch;
+  uint4 v[kMSRowIters], o[kMSRowIters];
+#pragma unroll
+  for (int it = 0; it < kMSRowIters; ++it) {
+    v[it] = make_uint4(0, 0, 0, 0);
+    if (!kEdge || y0 + it * kMSRowsY < (int)a.sy) v[it] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off + it * rs);
+  }
+  const bool two = a.ml.n > 1;
+  bool use1 = two;
+  if (two && a.ml.used[1]) use1 = a.ml.used[1][blockIdx.y * gridDim.x + blockIdx.x] != 0;
+#pragma unroll
+  for (int it = 0; it < kMSRowIters; ++it) {
+    o[it] = make_uint4(0, 0, 0, 0);
+    if (use1 && (!kEdge || y0 + it * kMSRowsY < (int)a.sy)) o[it] = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off + it * rs);
+  }
+  const int pol1 = a.ml.policy[1];
+  const unsigned sp16 = seed_pitch16(a.pitch);
+  uint16_t* srow = a.seeds + (size_t)y0 * sp16 + 2 + (x >> 4);
+  uint32_t colmask = 0xffffu;
+  if (kEdge && x + 16 > (int)a.sx) colmask = x >= (int)a.sx ? 0u : (1u << ((int)a.sx - x)) - 1u;
+#pragma unroll
+  for (int it = 0; it < kMSRowIters; ++it) {
+    if (kEdge && y0 + it * kMSRowsY >= (int)a.sy) continue;
+    uint4 m = v[it];
+    uint32_t hi = (m.x | m.y | m.z | m.w) & 0x80808080u;  // some byte >= 128: the group may hold 254 / 255
+    if (two) {
+      if ((o[it].x | o[it].y | o[it].z | o[it].w) != 0 || pol1 != NAVGPU_MAX) {
+        m = merge16(m, o[it], pol1);
+        hi = (m.x | m.y | m.z | m.w) & 0x80808080u;
+      } else if (hi) {  // Max with an all-FREE_SPACE group only turns NO_INFORMATION into 0
+        m.x &= ~((is255_4(m.x) >> 7) * 0xffu); m.y &= ~((is255_4(m.y) >> 7) * 0xffu);
+        m.z &= ~((is255_4(m.z) >> 7) * 0xffu); m.w &= ~((is255_4(m.w) >> 7) * 0xffu);
+      }
+    }
+    *reinterpret_cast<uint4*>(a.master + off + it * rs) = m;
+    if (a.R > 0) {
+      uint32_t seed16 = 0;
+      if (hi) seed16 = lethal_bits4(m.x) | (lethal_bits4(m.y) << 4) | (lethal_bits4(m.z) << 8) | (lethal_bits4(m.w) << 12);
+      srow[(size_t)it * kMSRowsY * sp16] = (uint16_t)(seed16 & colmask);
+    }
+  }
 }
 
 // body of k_merge_seed for one thread: kMSRowIters groups of 16 cells in one column of groups.  kInterior: the whole
@@ -1318,6 +1400,7 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   // is resident, and wait for the kernel before us (window, obstacle grid) before reading anything
   cudaTriggerProgrammaticLaunchCompletion();
   trace_start(a.trace, 1);
+  trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 0);
   constexpr int kW = kMSGroupsX * 16, kH = kMSRowsY * kMSRowIters;
   const int bx0 = blockIdx.x * kW, by0 = blockIdx.y * kH;
   DevWindow w;
@@ -1330,10 +1413,25 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
     w.x0 = 0; w.xn = (int)a.sx; w.y0 = 0; w.yn = (int)a.sy; w.valid = 1;
     const bool touched = bx0 < a.exn && bx0 + kW > a.ex0 && by0 < a.eyn && by0 + kH > a.ey0;
     if (touched || (blockIdx.x | blockIdx.y) == 0) cudaGridDependencySynchronize();
+    if (a.lean) {  // every tile: the window is the whole map
+      trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 1);
+      if (bx0 + kW <= (int)a.sx && by0 + kH <= (int)a.sy) merge_seed_lean<false>(a, bx0 + threadIdx.x * 16, by0);
+      else merge_seed_lean<true>(a, bx0 + threadIdx.x * 16, by0);
+      trace_end(a.trace, 1);
+      trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 2);
+      if (a.trace && touched && (threadIdx.x | threadIdx.y) == 0) atomicMax(&a.trace[6], trace_now());
+      if (a.ready) {
+        __syncthreads();
+        if ((threadIdx.x | threadIdx.y) == 0)
+          asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.ready + blockIdx.y * gridDim.x + blockIdx.x), "r"(a.epoch) : "memory");
+      }
+      return;
+    }
   } else {
     cudaGridDependencySynchronize();
     w = *a.win;
   }
+  trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 1);
   if (!w.valid) return;
   const int R = a.R;
   // everything k_inflate can read: its tiles intersect window +- 2R, extend up to a tile further, and look R rows /
@@ -1350,12 +1448,15 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   unsigned used_mask = 0xffffffffu;
   for (int l = 0; l < a.ml.n; ++l)
     if (a.ml.used[l] && a.ml.used[l][blockIdx.y * gridDim.x + blockIdx.x] == 0) used_mask &= ~(1u << l);
-  if (interior) {
+  if (interior && a.lean) {
+    merge_seed_lean<false>(a, x, by0);
+  } else if (interior) {
     merge_seed_items<true>(a, w, x, by0, sx0, sxn, sy0, syn, used_mask);
   } else if (x < (int)a.pitch) {
     merge_seed_items<false>(a, w, x, by0, sx0, sxn, sy0, syn, used_mask);
   }
   trace_end(a.trace, 1);
+  trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 2);
   if (a.trace && a.early && bx0 < a.exn && bx0 + kW > a.ex0 && by0 < a.eyn && by0 + kH > a.ey0 && (threadIdx.x | threadIdx.y) == 0)
     atomicMax(&a.trace[6], trace_now());
   if (a.ready) {  // (early mode: the window is the whole map, no CTA left above)
@@ -1387,25 +1488,33 @@ struct InflateArgs {
 template <int RMAX>
 __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   constexpr int kRows = kITY + 2 * RMAX;       // region rows this instantiation can hold
-  __shared__ uint32_t pbits[kRows * 4];        // seed words W0..W3 of each region row (columns tx0-32 .. tx0+95), pruned
-  __shared__ uint32_t h2[kRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
+  __shared__ __align__(16) uint32_t pbits[kRows * 4];  // seed words W0..W3 of each region row (columns tx0-32 .. tx0+95), pruned
+  __shared__ __align__(16) uint32_t h2[kRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
   // the unpruned seed words only live until the pruning pass has read them: they borrow the start of h2, which phase 2
   // fills afterwards (and only for seeded rows; phase 3 never reads another row)
   uint32_t* const sbits = h2;
   __shared__ uint32_t rowmask[kIMaskWords];  // bit (r + 32) <-> region row r has seeds
+  // bit (r + 32) <-> region row r repeats row r - 1: same (non-zero) pruned seed words, hence the same horizontal
+  // distances in every column of the tile.  Of a run of repeated rows only the row nearest to an output row can win
+  // there (same hx^2, smaller dy^2): phase 2 computes the first row of a run only (canon[r] names it), phase 3 skips
+  // the repeats further from its eight output rows.  A vertical wall costs one row instead of one per map row.
+  __shared__ uint32_t dupmask[kIMaskWords];
+  __shared__ __align__(4) uint8_t canon[(kRows + 3) & ~3];
   __shared__ uint8_t rowlist[kRows];         // the same rows as a list (any order), n_seeded of them
   __shared__ int n_seeded;
   __shared__ int next_group;                 // phase 3: the next 8-row group nobody has taken yet
   // phase 3: dy^2 of window row j against the eight output rows k of a group, (j - k)^2 in both 16-bit halves:
   // dy2tab[j + RMAX][k / 4] component k % 4 -- two broadcast 16-byte loads per seeded row instead of an add chain
   __shared__ uint4 dy2tab[8 + 2 * RMAX][2];
-  __shared__ uint8_t table[1024];  // cost by d^2, table[R*R+1] = 0 ("out of reach")
+  // cost by d^2, table[reach2 + 1] = 0 ("out of reach"); reach <= RMAX bounds reach2 by (RMAX + 1)^2 - 1
+  __shared__ uint8_t table[((RMAX + 1) * (RMAX + 1) + 1 + 15) & ~15];
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
   // early mode: the flags of the k_merge_seed tiles this tile reads (seeds: columns tx0 - 32 .. tx0 + 95, rows
   // ty0 - R .. ty0 + kITY + R - 1; master cells: the tile itself), one per thread, requested before anything else
   const unsigned* my_flag = nullptr;
   unsigned flag_seen = 0;
   trace_start(a.trace, 2);
+  trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 0);
   if (a.ready) {
     constexpr int kMW = kMSGroupsX * 16, kMH = kMSRowsY * kMSRowIters;
     const int mx0 = max(0, tx0 - 32) / kMW, mx1 = min((int)a.pitch - 1, tx0 + kITX + 31) / kMW;
@@ -1439,6 +1548,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     cudaGridDependencySynchronize();
     w = *a.win;
   }
+  trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 1);
   if (!w.valid) return;
   {
     const int R = a.R;
@@ -1451,26 +1561,37 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned sp32 = seed_pitch16(a.pitch) / 2;
 
-  // ---- seed words of the region; leave when there is nothing to inflate from
+  // ---- seed words of the region (every load in flight before the first use); leave when there is nothing to inflate from
   int any = 0;
-  for (int i = tid; i < rows * 4; i += kIThreads) {
-    const int gy = ty0 - R + (i >> 2);
-    uint32_t v = 0;
-    // (read past L1: in early mode a line of the bitmask can hold words of a k_merge_seed tile that is still running)
-    if (gy >= 0 && gy < (int)a.sy) v = __ldcg(&a.seeds[(size_t)gy * sp32 + (tx0 >> 5) + (i & 3)]);
-    sbits[i] = v;
-    any |= v != 0;
-  }
-  if (tid < kIMaskWords) rowmask[tid] = 0;
-  if (tid == 0) n_seeded = next_group = 0;
-  for (int i = tid; i < (8 + 2 * RMAX) * 8; i += kIThreads) {
-    const int d = (i >> 3) - RMAX - (i & 7);
-    reinterpret_cast<uint32_t*>(dy2tab)[i] = (uint32_t)(d * d) * 0x10001u;
+  {
+    constexpr int NI = (kRows * 4 + kIThreads - 1) / kIThreads;
+    uint32_t v[NI];
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * kIThreads, gy = ty0 - R + (i >> 2);
+      v[k] = 0;
+      // (read past L1: in early mode a line of the bitmask can hold words of a k_merge_seed tile that is still running)
+      if (i < rows * 4 && gy >= 0 && gy < (int)a.sy) v[k] = __ldcg(&a.seeds[(size_t)gy * sp32 + (tx0 >> 5) + (i & 3)]);
+    }
+    if (tid < kIMaskWords) rowmask[tid] = dupmask[tid] = 0;
+    if (tid == 0) n_seeded = next_group = 0;
+    for (int i = tid; i < (8 + 2 * RMAX) * 8; i += kIThreads) {
+      const int d = (i >> 3) - RMAX - (i & 7);
+      reinterpret_cast<uint32_t*>(dy2tab)[i] = (uint32_t)(d * d) * 0x10001u;
+    }
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * kIThreads;
+      if (i < rows * 4) sbits[i] = v[k];
+      any |= v[k] != 0;
+    }
   }
   if (!__syncthreads_or(any)) {
     trace_end(a.trace, 2);
+    trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 2);
     return;
   }
+  trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 4);
 
   // ---- interior seeds cannot be the nearest seed of any other cell: a seed whose four neighbours are seeds too has,
   // for every non-seed cell p, a neighbouring seed strictly closer to p (step along the larger coordinate difference),
@@ -1478,33 +1599,64 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   // which max() keeps.  Dropping them empties most rows of thick structures for phases 2 and 3.  Seeds on the rim
   // of the loaded region (unknown neighbours) are kept.
   // Only seeds within R columns of the tile can matter (the top R bits of W0, the low R bits of W3): pbits holds the
-  // words already masked that way, and rowmask gets a bit for every row that still has one.
-  for (int i = tid; i < rows * 4; i += kIThreads) {
-    const int r = i >> 2, wq = i & 3;
-    const uint32_t c = sbits[i];
-    uint32_t keep = c;
-    if (c != 0 && r > 0 && r + 1 < rows) {
-      const uint32_t left = (c << 1) | (wq > 0 ? sbits[i - 1] >> 31 : 0u);
-      const uint32_t right = (c >> 1) | (wq < 3 ? sbits[i + 1] << 31 : 0u);
-      keep = c & ~(left & right & sbits[i - 4] & sbits[i + 4]);
+  // words already masked that way.  One thread per region row: it also finds out whether its row repeats the row above
+  // (whose pruned words it recomputes rather than wait for), and the warp's ballots become the row masks and the list
+  // of rows phase 2 has to compute.
+  {
+    const uint4* sb4 = reinterpret_cast<const uint4*>(sbits);
+    auto pruned = [&](int r) -> uint4 {
+      uint4 c = sb4[r];
+      if ((c.x | c.y | c.z | c.w) != 0 && r > 0 && r + 1 < rows) {
+        const uint4 u = sb4[r - 1], d = sb4[r + 1];
+        const uint32_t kx = (c.x << 1) & ((c.x >> 1) | (c.y << 31)) & u.x & d.x;
+        const uint32_t ky = ((c.y << 1) | (c.x >> 31)) & ((c.y >> 1) | (c.z << 31)) & u.y & d.y;
+        const uint32_t kz = ((c.z << 1) | (c.y >> 31)) & ((c.z >> 1) | (c.w << 31)) & u.z & d.z;
+        const uint32_t kw = ((c.w << 1) | (c.z >> 31)) & (c.w >> 1) & u.w & d.w;
+        c.x &= ~kx; c.y &= ~ky; c.z &= ~kz; c.w &= ~kw;
+      }
+      c.x &= ~(0xffffffffu >> R);
+      c.w &= (1u << R) - 1u;
+      return c;
+    };
+    const int r = tid;  // (kRows <= 190 < kIThreads)
+    bool seeded = false, dup = false;
+    if (r < rows) {
+      const uint4 k = pruned(r);
+      reinterpret_cast<uint4*>(pbits)[r] = k;
+      seeded = (k.x | k.y | k.z | k.w) != 0;
+      if (seeded && r > 0) {
+        const uint4 p = pruned(r - 1);
+        dup = k.x == p.x && k.y == p.y && k.z == p.z && k.w == p.w;
+      }
     }
-    if (wq == 0) keep &= ~(0xffffffffu >> R);
-    if (wq == 3) keep &= (1u << R) - 1u;
-    pbits[i] = keep;
-    if (keep) {  // whoever sets the row's bit first also lists the row
-      const uint32_t bit = 1u << (r & 31);
-      if (!(atomicOr(&rowmask[(r >> 5) + 1], bit) & bit)) rowlist[atomicAdd(&n_seeded, 1)] = (uint8_t)r;
+    const uint32_t sm = __ballot_sync(0xffffffffu, seeded), dm = __ballot_sync(0xffffffffu, dup);
+    const uint32_t lm = sm & ~dm;  // rows whose distances phase 2 computes
+    int base = 0;
+    if (lane == 0 && sm) {
+      rowmask[warp + 1] = sm;
+      dupmask[warp + 1] = dm;
+      if (lm) base = atomicAdd(&n_seeded, __popc(lm));
     }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (seeded && !dup) rowlist[base + __popc(lm & ((1u << lane) - 1u))] = (uint8_t)r;
   }
   __syncthreads();
+  trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 5);
 
-  // ---- phase 2: squared horizontal distances for the rows that have seeds (one warp per row, straight from the list)
+  // ---- phase 2: squared horizontal distances for the listed rows (one warp per row); before that every row learns
+  // canon[r], the nearest row at or above it that does not repeat its predecessor
   {
-    const int n_rows_seeded = n_seeded;
-    for (int li = warp; li < n_rows_seeded; li += kIThreads / 32) {
+    if (tid < rows) {
+      int qq = warp;
+      uint32_t z = ~dupmask[warp + 1] & (0xffffffffu >> (31 - lane));
+      while (z == 0) z = ~dupmask[--qq + 1];  // (row 0 never repeats anything: the walk ends there at the latest)
+      canon[tid] = (uint8_t)(32 * qq + 31 - __clz(z));
+    }
+    const int n_rows_listed = n_seeded;
+    for (int li = warp; li < n_rows_listed; li += kIThreads / 32) {
       const int r = rowlist[li];
-      const uint32_t W0 = pbits[4 * r], W1 = pbits[4 * r + 1], W2 = pbits[4 * r + 2], W3 = pbits[4 * r + 3];
-      const uint32_t A = lane < 16 ? W0 : W1, B = lane < 16 ? W1 : W2, C = lane < 16 ? W2 : W3;
+      const uint4 W = reinterpret_cast<const uint4*>(pbits)[r];
+      const uint32_t A = lane < 16 ? W.x : W.y, B = lane < 16 ? W.y : W.z, C = lane < 16 ? W.z : W.w;
       uint32_t packed = 0;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -1521,6 +1673,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     }
   }
   __syncthreads();
+  trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 6);
 
   // ---- phase 3 + epilogue: a warp takes 64 columns x 8 rows at a time
   const uint32_t R2x2 = (uint32_t)a.reach2 * 0x10001u;
@@ -1547,7 +1700,8 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     //    address an immediate offset; rows without seeds cost one bit test, eight such rows one byte test.
     {
       constexpr int NJ = 8 + 2 * RMAX, NW = (NJ + 31) / 32, NB = (NJ + 7) / 8;
-      const uint32_t* hb = h2 + (yr0 + R) * (kITX / 2) + lane;
+      const uint32_t* hb = h2 + lane;
+      const uint8_t* cn = canon + yr0 + R;  // cn[j]: the row whose distances row j shares
       const int p0 = yr0 + R - RMAX + 32;  // position of j = -RMAX in rowmask (which is stored with a 32-row offset)
       const int wi = p0 >> 5, sh = p0 & 31;
       uint32_t mw[NW];
@@ -1557,6 +1711,14 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
       for (int q = 0; q < NW; ++q) {
         mw[q] = __funnelshift_r(rowmask[wi + q], rowmask[wi + q + 1], sh);
         if (q == NW - 1 && (NJ & 31) != 0) mw[q] &= (1u << (NJ & 31)) - 1u;
+        // repeats: above the eight output rows (j < 0) a row whose successor repeats it loses to that successor,
+        // below them (j > 7) a row that repeats its predecessor loses to that predecessor; window position p = j + RMAX
+        const uint32_t dw = __funnelshift_r(dupmask[wi + q], dupmask[wi + q + 1], sh);
+        constexpr int kBelow = RMAX + 8;  // first window position below the output rows
+        const uint32_t below = 32 * q >= kBelow ? 0xffffffffu : (32 * q + 32 <= kBelow ? 0u : 0xffffffffu << (kBelow & 31));
+        uint32_t drop = below & dw;
+        if (q == 0) drop |= ((1u << RMAX) - 1u) & (dw >> 1);
+        mw[q] &= ~drop;
         anyrow |= mw[q];
         nrows += __popc(mw[q]);
       }
@@ -1568,7 +1730,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
           while (m) {
             const int j = __ffs(m) - 1 + 32 * q - RMAX;
             m &= m - 1;
-            const uint32_t hh = hb[j * (kITX / 2)];
+            const uint32_t hh = hb[cn[j] * (kITX / 2)];
             const uint4 qa = dy2tab[j + RMAX][0], qb = dy2tab[j + RMAX][1];
             acc[0] = __viaddmin_u16x2(hh, qa.x, acc[0]);
             acc[1] = __viaddmin_u16x2(hh, qa.y, acc[1]);
@@ -1590,7 +1752,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
             const int j = 8 * c + b - RMAX;
             if (j > 7 + RMAX) continue;
             if (bits8 & (1u << b)) {
-              const uint32_t hh = hb[j * (kITX / 2)];
+              const uint32_t hh = hb[cn[j] * (kITX / 2)];
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int dy = j - k;
@@ -1644,6 +1806,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     }
   }
   trace_end(a.trace, 2);
+  trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 2);
 }
 
 inline size_t update_costs_smem(int R) {
