@@ -1764,44 +1764,40 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
       }
     }
     // rows that inflation reaches somewhere in these 64 columns: read, combine (inflation_layer.cpp:249-254), write.
-    // Both cells of the pair are handled in one 32-bit word: byte k of `cost2` / `cur` belongs to cell k.
+    // Two rows at a time: the lane's 2 x 2 cells travel in one 32-bit word (bytes 0-1 row k, bytes 2-3 row k + 1), so
+    // the byte maximum, the NO_INFORMATION test and the "did anything change" test are paid once per four cells.  A
+    // cell out of reach looks up table[reach2 + 1] = 0 and a row that is not read counts as 0: max(0, 0) stores nothing.
     const int kmax = xok ? min(8, (int)a.sy - (ty0 + yr0)) : 0;
-    uint8_t* prow = a.master + (size_t)(ty0 + yr0) * a.pitch + x;
+    const uint32_t out_of_reach = R2x2 + 0x10001u;
+    const uint32_t cell0 = (uint32_t)(ty0 + yr0) * a.pitch + (uint32_t)x;  // (sy * pitch < 2^32: sizes are < 65536)
+    const uint32_t keep_hi4 = keep_hi * 0x10001u;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {  // four rows at a time keeps the loads in flight within 32 registers
-      uint32_t cur[4];
+      uint32_t d2[4], cur[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int k = 4 * half + q;
-        // bit 15 of every half whose squared distance is within reach (no borrow crosses the halves)
-        const uint32_t hit = k < kmax ? ((R2x2 | 0x80008000u) - acc[k]) & 0x80008000u : 0u;
-        cur[q] = 0xffffffffu;  // "row not reached" (a uint16 load never produces it)
-        if (hit) cur[q] = *reinterpret_cast<const uint16_t*>(prow + (size_t)k * a.pitch);
+        d2[q] = k < kmax ? __vminu2(acc[k], out_of_reach) : out_of_reach;
+        cur[q] = 0;
+        if (d2[q] != out_of_reach) cur[q] = *reinterpret_cast<const uint16_t*>(a.master + (cell0 + (uint32_t)k * a.pitch));
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = 4 * half + q;
-        if (cur[q] == 0xffffffffu) continue;
-        const uint32_t d2 = __vminu2(acc[k], R2x2 + 0x10001u);  // out of reach -> table[reach2 + 1] = 0
-        const uint32_t old2 = cur[q];
-        if (__vcmpeq4(old2, 0xffffffffu) == 0) {  // (a uint16 load: the upper bytes are 0)
-          // neither cell is NO_INFORMATION (the usual case): a plain byte maximum (inflation_layer.cpp:253-254)
-          const uint32_t c8 = ((uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 8)) & ~keep_hi;
-          const uint32_t out = __vmaxu4(old2, c8);
-          if (out != old2) *reinterpret_cast<uint16_t*>(prow + (size_t)k * a.pitch) = (uint16_t)out;
-          continue;
+      for (int pr = 0; pr < 2; ++pr) {
+        const int k = 4 * half + 2 * pr;
+        const uint32_t da = d2[2 * pr], db = d2[2 * pr + 1];
+        if (da == out_of_reach && db == out_of_reach) continue;
+        const uint32_t c = ((uint32_t)table[da & 0xffffu] | ((uint32_t)table[da >> 16] << 8) |
+                            ((uint32_t)table[db & 0xffffu] << 16) | ((uint32_t)table[db >> 16] << 24)) & ~keep_hi4;
+        const uint32_t old4 = cur[2 * pr] | (cur[2 * pr + 1] << 16);
+        uint32_t out = __vmaxu4(old4, c);  // neither cell NO_INFORMATION (the usual case): a plain maximum (:253-254)
+        const uint32_t noinfo = __vcmpeq4(old4, 0xffffffffu);
+        if (noinfo) {  // NO_INFORMATION is replaced only by costs >= INSCRIBED_INFLATED_OBSTACLE, and then by the cost (:249-252)
+          const uint32_t ge = __vcmpgeu4(c, 0xfdfdfdfdu);
+          out = (noinfo & ((ge & c) | (~ge & old4))) | (~noinfo & out);
         }
-        const uint32_t c16 = (uint32_t)table[d2 & 0xffffu] | ((uint32_t)table[d2 >> 16] << 16);
-        const uint32_t o16 = __byte_perm(old2, 0, 0x4140);  // the two cells' bytes, one per 16-bit lane
-        uint32_t r16 = __vmaxu2(o16, c16);
-        // NO_INFORMATION is replaced only by costs >= INSCRIBED
-        const uint32_t keep = __vminu2(__vmaxu2(c16, 0x00fc00fcu), 0x00fd00fdu) - 0x00fc00fcu;  // 1 where cost >= 253
-        const uint32_t noinfo = ((o16 + 0x00010001u) >> 8) & 0x00010001u;                       // 1 where old == 255
-        const uint32_t repl = (noinfo & keep) * 0xffffu;                                        // 0xffff per such half
-        r16 = (c16 & repl) | (r16 & ~repl);
-        uint32_t out = __byte_perm(r16, 0, 0x4420);
-        out = (out & ~keep_hi) | (old2 & keep_hi);  // padding column: left as it is
-        if (out != old2) *reinterpret_cast<uint16_t*>(prow + (size_t)k * a.pitch) = (uint16_t)out;
+        const uint32_t diff = out ^ old4;
+        if (diff & 0xffffu) *reinterpret_cast<uint16_t*>(a.master + (cell0 + (uint32_t)k * a.pitch)) = (uint16_t)out;
+        if (diff >> 16) *reinterpret_cast<uint16_t*>(a.master + (cell0 + (uint32_t)(k + 1) * a.pitch)) = (uint16_t)(out >> 16);
       }
     }
   }
