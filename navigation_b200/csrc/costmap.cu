@@ -195,6 +195,8 @@ struct navgpu_costmap {
   DevWindow* d_win = nullptr;
   DevWindow* h_win = nullptr;  // pinned
   unsigned* d_ticket = nullptr;  // k_obstacle_update's "last CTA" counter
+  unsigned* d_obst_done = nullptr;  // ObstacleArgs::done_flag
+  unsigned obst_epoch = 0;
   int8_t* d_occupancy = nullptr;  // packed window for navgpu_costmap_get_window_occupancy
   size_t occupancy_capacity = 0;
   uint16_t* d_seeds = nullptr;  // seed bitmask of the fast sweep (k_merge_seed -> k_inflate)
@@ -377,6 +379,7 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
     m.R = R;
     m.seeds = seeds;
     m.early = a.early; m.ex0 = a.ex0; m.exn = a.exn; m.ey0 = a.ey0; m.eyn = a.eyn;
+    m.obst_flag = a.obst_flag; m.obst_epoch = a.obst_epoch;
     m.trace = flags ? flags->trace : nullptr;
     m.lean = a.ml.n >= 1 && a.ml.n <= 2 && a.ml.policy[0] == NAVGPU_TRUE_OVERWRITE &&
              (a.ml.n == 1 || a.ml.policy[1] == NAVGPU_MAX || a.ml.policy[1] == NAVGPU_OVERWRITE) && !getenv("NAVGPU_NO_LEAN_MERGE");
@@ -452,6 +455,8 @@ int ensure_prop(navgpu_costmap* h, const Layer& L, PropBuffers* pb) {
 
 struct EarlyBox {  // see UpdateArgs::early
   int on = 0, x0 = 0, xn = 0, y0 = 0, yn = 0;
+  const unsigned* flag = nullptr;  // UpdateArgs::obst_flag
+  unsigned epoch = 0;
 };
 
 int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R, const uint8_t* cost_d2, int reach2 = 0,
@@ -459,6 +464,7 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   UpdateArgs a;
   a.early = early && early->on && do_reset ? 1 : 0;
   a.ex0 = early ? early->x0 : 0; a.exn = early ? early->xn : 0; a.ey0 = early ? early->y0 : 0; a.eyn = early ? early->yn : 0;
+  if (a.early && early->flag) { a.obst_flag = early->flag; a.obst_epoch = early->epoch; }
   a.master = h->master[h->cur];
   a.sx = h->sx; a.sy = h->sy; a.pitch = h->pitch;
   a.def = h->def;
@@ -642,6 +648,7 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   }
   // ---- device part: one k_obstacle_update per enabled obstacle layer (ray-trace clearing, then marking, then the
   // footprint polygon of updateCosts); the last one also finalises the bounds into the cycle's window
+  bool standalone_polygon = false;  // a k_polygon_clear launch follows some obstacle kernel: no early "grids done" flag
   for (size_t li = 0; li < h->layers.size(); ++li) {
     Layer& L = h->layers[li];
     if (L.kind != 1 || !L.enabled) continue;
@@ -696,6 +703,13 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
     if (oa.do_finalize) oa.ba = ba;
     oa.trace = h->d_trace;
     oa.tile_used = L.d_tile_used;
+    if (mode == 2) standalone_polygon = true;
+    if (early.on && (int)li == last_obstacle && !standalone_polygon) {
+      oa.done_flag = h->d_obst_done;
+      oa.done_epoch = ++h->obst_epoch;
+      early.flag = h->d_obst_done;
+      early.epoch = oa.done_epoch;
+    }
     oa.boxes = h->d_boxes; oa.infl = h->d_infl; oa.win = h->d_win;
     const int blocks = std::max(1, (L.total_rays * 32 + kObstacleThreads - 1) / kObstacleThreads);
     k_obstacle_update<<<blocks, kObstacleThreads, 0, h->stream>>>(oa);
@@ -807,6 +821,8 @@ int navgpu_costmap_create(navgpu_costmap** out, uint32_t size_x, uint32_t size_y
   NAVGPU_CUDA(cudaMalloc(&h->d_win, sizeof(DevWindow)));
   NAVGPU_CUDA(cudaMalloc(&h->d_ticket, sizeof(unsigned)));
   NAVGPU_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
+  NAVGPU_CUDA(cudaMalloc(&h->d_obst_done, sizeof(unsigned)));
+  NAVGPU_CUDA(cudaMemset(h->d_obst_done, 0, sizeof(unsigned)));
   NAVGPU_CUDA(cudaMallocHost(&h->h_win, sizeof(DevWindow)));
   DevBox boxes[kMaxLayers];
   InflationBoundsState infl[kMaxLayers];
@@ -837,7 +853,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
     cudaFree(L.vox[0]); cudaFree(L.vox[1]); cudaFree(L.d_tile_used);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
-  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_occupancy);
+  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_obst_done); cudaFree(h->d_occupancy);
   cudaFree(h->d_prop_state); cudaFree(h->d_prop_ctl);
   cudaFree(h->d_shadow); cudaFree(h->d_mirror_counters); cudaFree(h->d_mirror_dirty); cudaFree(h->d_tile_ready); cudaFree(h->d_trace);
   if (h->h_mirror_stage) cudaFreeHost(h->h_mirror_stage);

@@ -337,15 +337,16 @@ constexpr unsigned kMarkTileW = 256, kMarkTileH = 32;  // = k_merge_seed's tile 
 __device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, const long long* cells, int total_points,
                                                 uint8_t* __restrict__ tile_used = nullptr, unsigned pitch = 1) {
   const int nt = blockDim.x;
-  for (int base = threadIdx.x; base < total_points; base += 4 * nt) {  // four loads in flight per thread
-    long long cell[4];
+  constexpr int kU = 12;  // loads in flight per thread: a few thousand marks are one round trip for 256 threads
+  for (int base = threadIdx.x; base < total_points; base += kU * nt) {
+    long long cell[kU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const int t = base + u * nt;
       cell[u] = t < total_points ? __ldcg(cells + t) : -1;  // written by other CTAs of this launch: read past L1
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < kU; ++u)
       if (cell[u] >= 0) {
         grid[cell[u]] = kLethal;
         if (tile_used) {  // MergeLayers::used: this tile no longer is all FREE_SPACE
@@ -607,6 +608,11 @@ struct ObstacleArgs {
   DevWindow* win;
   unsigned long long* trace = nullptr;
   uint8_t* tile_used = nullptr;  // MergeLayers::used of this layer (nullable)
+  // set to done_epoch (release, gpu scope) by the last CTA as soon as the layer grid is complete (rays cleared, marks
+  // stored, footprint cleared), before the bounds pass: early-mode k_merge_seed tiles in the rays' box wait for this
+  // word instead of for the end of the kernel
+  unsigned* done_flag = nullptr;
+  unsigned done_epoch = 0;
 };
 constexpr int kObstacleThreads = 256;
 
@@ -650,6 +656,13 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   if (a.trace && threadIdx.x == 0) a.trace[10] = trace_now();
   if (a.do_poly) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
   if (a.trace && threadIdx.x == 0) a.trace[11] = trace_now();
+  if (a.done_flag) {
+    __syncthreads();  // every thread's mark / polygon stores are ordered before the release below
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.done_flag), "r"(a.done_epoch) : "memory");
+    }
+  }
   if (threadIdx.x == 0) {
     *a.ticket = 0;  // re-armed for the next cycle
     if (a.do_finalize) {
@@ -997,6 +1010,10 @@ struct UpdateArgs {
   // early != 0: the host knows this cycle's window is the whole map and that the kernel launched just before the sweep
   // (k_obstacle_update) writes layer cells only inside [ex0, exn) x [ey0, eyn): see k_merge_seed
   int early = 0, ex0 = 0, exn = 0, ey0 = 0, eyn = 0;
+  // early mode: the word the last k_obstacle_update sets to obst_epoch once the layer grids hold everything this cycle
+  // writes to them (marks and footprint included) -- before it finalises the bounds; null: wait for the whole kernel
+  const unsigned* obst_flag = nullptr;
+  unsigned obst_epoch = 0;
 };
 
 __device__ __forceinline__ uint8_t apply_policy(uint8_t m, uint8_t v, int policy) {
@@ -1186,6 +1203,8 @@ struct MergeSeedArgs {
   int R;            // 0: merge only (seeds may be null)
   uint16_t* seeds;  // sy x seed_pitch16(pitch)
   int early = 0, ex0 = 0, exn = 0, ey0 = 0, eyn = 0;  // see UpdateArgs
+  const unsigned* obst_flag = nullptr;                // see UpdateArgs
+  unsigned obst_epoch = 0;
   // early mode with k_inflate behind us: every CTA publishes `epoch` in ready[blockIdx.y * gridDim.x + blockIdx.x] once
   // its tile (master cells and seed bits) is written, and k_inflate's tiles wait for just the tiles they read
   unsigned* ready = nullptr;
@@ -1412,7 +1431,20 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
     // kernel and k_inflate, which waits for this grid, sees everything that kernel wrote (the window record included).
     w.x0 = 0; w.xn = (int)a.sx; w.y0 = 0; w.yn = (int)a.sy; w.valid = 1;
     const bool touched = bx0 < a.exn && bx0 + kW > a.ex0 && by0 < a.eyn && by0 + kH > a.ey0;
-    if (touched || (blockIdx.x | blockIdx.y) == 0) cudaGridDependencySynchronize();
+    if ((blockIdx.x | blockIdx.y) == 0 || (touched && !a.obst_flag)) cudaGridDependencySynchronize();
+    if (touched && a.obst_flag) {
+      // (every CTA of the obstacle kernel is resident or done before this grid is scheduled: it triggers the programmatic
+      // launch at its first instruction, so waiting for its last CTA cannot deadlock)
+      if ((threadIdx.x | threadIdx.y) == 0) {
+        unsigned seen;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(a.obst_flag) : "memory");
+          if (seen == a.obst_epoch) break;
+          __nanosleep(64);
+        }
+      }
+      __syncthreads();
+    }
     if (a.lean) {  // every tile: the window is the whole map
       trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 1);
       if (bx0 + kW <= (int)a.sx && by0 + kH <= (int)a.sy) merge_seed_lean<false>(a, bx0 + threadIdx.x * 16, by0);
