@@ -156,7 +156,7 @@ int navgpu_costmap_last_timing(navgpu_costmap* h, float* cycle_ms, float* sweep_
  * global timer in ns -- out[0..1] obstacle kernel, [2..3] k_merge_seed, [4..5] k_inflate, [6] last merge tile in the
  * obstacle box, [7] / [8] first / last inflate tile released by its flags (tools/probe_trace.py) */
 int navgpu_costmap_last_trace(navgpu_costmap* h, uint64_t out[16]);
-/* same hook, per CTA of the last cycle: kernel 0 = k_merge_seed, 1 = k_inflate; out[8 * cta + 0..6] = start, start of the
+/* same hook, per CTA of the last cycle: kernel 0 = k_merge_seed, 1 = k_inflate, 2 = k_obstacle_update; out[8 * cta + 0..6] = start, start of the
  * work proper (after the dependency / flag wait), end (global timer, ns), SM id, k_inflate's stage ends; n_ctas <= 4096
  * (tools/probe_cta_trace.py) */
 int navgpu_costmap_last_cta_trace(navgpu_costmap* h, int kernel, uint64_t* out, int n_ctas);

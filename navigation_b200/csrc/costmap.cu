@@ -532,8 +532,8 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
   static const bool tracing = getenv("NAVGPU_TRACE") != nullptr;
   if (tracing) {
     if (!h->d_trace) {
-      NAVGPU_CUDA(cudaMalloc(&h->d_trace, (16 + 16 * (size_t)kCtaTraceMax) * sizeof(unsigned long long)));
-      NAVGPU_CUDA(cudaMemsetAsync(h->d_trace, 0, (16 + 16 * (size_t)kCtaTraceMax) * sizeof(unsigned long long), h->stream));
+      NAVGPU_CUDA(cudaMalloc(&h->d_trace, (16 + 24 * (size_t)kCtaTraceMax) * sizeof(unsigned long long)));
+      NAVGPU_CUDA(cudaMemsetAsync(h->d_trace, 0, (16 + 24 * (size_t)kCtaTraceMax) * sizeof(unsigned long long), h->stream));
     }
     static const unsigned long long init[16] = {~0ull, 0, ~0ull, 0, ~0ull, 0, 0, ~0ull, 0, 0, 0, 0, 0, 0, ~0ull, 0};
     NAVGPU_CUDA(cudaMemcpyAsync(h->d_trace, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
@@ -1371,7 +1371,7 @@ int navgpu_costmap_last_trace(navgpu_costmap* h, uint64_t out[16]) {
 }
 
 int navgpu_costmap_last_cta_trace(navgpu_costmap* h, int kernel, uint64_t* out, int n_ctas) {
-  if (!h || !out || kernel < 0 || kernel > 1 || n_ctas < 0 || n_ctas > kCtaTraceMax) return fail(NAVGPU_ERR_INVALID, "bad arguments");
+  if (!h || !out || kernel < 0 || kernel > 2 || n_ctas < 0 || n_ctas > kCtaTraceMax) return fail(NAVGPU_ERR_INVALID, "bad arguments");
   if (!h->d_trace) return fail(NAVGPU_ERR_INVALID, "tracing is off (set NAVGPU_TRACE before the first update)");
   NAVGPU_TRY(use_device(h));
   NAVGPU_CUDA(cudaStreamSynchronize(h->stream));

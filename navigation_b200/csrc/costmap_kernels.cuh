@@ -629,7 +629,9 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   const DevObs* clear_tab = a.n_clear <= kInlineObs ? a.clear_inline : a.clear;
   const DevObs* mark_tab = a.n_mark <= kInlineObs ? a.mark_inline : a.mark;
   BoxAcc acc;
+  trace_cta(a.trace, 2, blockIdx.x, 0);
   raytrace_ray(a.grid, a.g, clear_tab, a.n_clear, a.xyz, a.total_rays, acc, warp, lane);
+  trace_cta(a.trace, 2, blockIdx.x, 4);
   {  // this CTA's share of the marking tests
     const int per_cta = (a.total_marks + gridDim.x - 1) / gridDim.x;
     for (int i = threadIdx.x; i < per_cta; i += kObstacleThreads) {
@@ -638,11 +640,14 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
         mark_prepare(a.g, mark_tab, a.n_mark, a.xyz, a.max_obstacle_height, acc, a.mark_cells, t);
     }
   }
+  trace_cta(a.trace, 2, blockIdx.x, 5);
   acc.flush_cta(a.box, s_box);
   __syncthreads();
+  trace_cta(a.trace, 2, blockIdx.x, 6);
   if (threadIdx.x == 0) {
     __threadfence();
     s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    trace_cta(a.trace, 2, blockIdx.x, 2);
     if (a.trace) {  // [14] first / [9] last CTA through with its rays; [10] marks stored, [11] polygon cleared
       atomicMin(&a.trace[14], trace_now());
       atomicMax(&a.trace[9], trace_now());

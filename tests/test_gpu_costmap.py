@@ -252,6 +252,63 @@ def test_tie_worlds_both_modes(cuda, port, kind, n, radius):
         assert outside == 0
 
 
+def repeated_row_world(kind, sx, sy, seed):
+    """Worlds whose rows repeat: what k_inflate's repeated-row pruning (dupmask / canon) has to get right."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros((sy, sx), np.uint8)
+    if kind == "walls":  # vertical walls 1..4 cells thick, some with gaps, some ending inside a tile
+        for _ in range(sx // 25):
+            x, t = int(rng.integers(0, sx - 4)), int(rng.integers(1, 5))
+            y0, y1 = sorted(int(v) for v in rng.integers(0, sy, 2))
+            g[y0:y1 + 1, x:x + t] = 254
+            if rng.random() < 0.5 and y1 - y0 > 6:
+                gap = int(rng.integers(y0 + 1, y1 - 2))
+                g[gap:gap + int(rng.integers(1, 4)), x:x + t] = 0
+    elif kind == "border":  # the 1-cell map border of the warehouse world plus full-height and full-width lines
+        g[0, :] = g[-1, :] = 254
+        g[:, 0] = g[:, -1] = 254
+        g[:, sx // 3] = 254
+        g[sy // 2, :] = 254
+    elif kind == "period2":  # rows alternate between two patterns: no two consecutive rows repeat
+        a, b = rng.random(sx) < 0.03, rng.random(sx) < 0.03
+        g[0::2, :][:, a] = 254
+        g[1::2, :][:, b] = 254
+    elif kind == "blocks":  # runs of identical rows of random length, separated by different or empty rows
+        y = 0
+        while y < sy:
+            h = int(rng.integers(1, 40))
+            if rng.random() < 0.7:
+                g[y:y + h, rng.random(sx) < 0.02] = 254
+            y += h
+    elif kind == "comb":  # a horizontal bar with vertical teeth: repeated rows next to a thick structure
+        for y0 in range(10, sy - 40, 70):
+            g[y0:y0 + 4, 5:sx - 5] = 254
+            for x in range(8, sx - 8, 13):
+                g[y0 + 4:y0 + 30, x:x + 2] = 254
+    return g
+
+
+@pytest.mark.parametrize("radius", [0.3, 0.55, 1.0, 1.5])
+@pytest.mark.parametrize("kind", ["walls", "border", "period2", "blocks", "comb"])
+def test_repeated_rows_exact_mode(cuda, port, kind, radius):
+    """k_inflate computes horizontal distances once per run of identical (pruned) seed rows and lets only the row of a
+    run nearest to an output row compete: same grid as the checker's exact nearest-seed variant, on sizes that leave
+    partial tiles at both edges."""
+    sx, sy = 333, 517
+    g = repeated_row_world(kind, sx, sy, 11)
+    outs = []
+    for api in (cuda, port):
+        cm = api.costmap(sx, sy, 0.05)
+        s = cm.add_grid_layer(0)
+        il = cm.add_inflation_layer(radius, 10.0)
+        cm.set_footprint(sc.square_footprint())
+        cm.set_grid_layer(s, g)
+        sc.select_inflation(cm, il, "exact", 0)
+        cm.update_map()
+        outs.append(cm.get())
+    assert np.array_equal(outs[0], outs[1]), f"{int((outs[0] != outs[1]).sum())} cells differ"
+
+
 def test_blocked_propagation_three_seeds(cuda, port):
     """A tie-INDEPENDENT difference between nearest-seed and propagated inflation: lethal cells at (3,3), (4,1), (0,5)
     (relative), R = 10, cost_scaling_factor 3: the compiled reference writes 158 one cell left of the first column's

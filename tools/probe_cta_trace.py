@@ -73,6 +73,14 @@ def report(name, r):
     print("  slowest: " + ", ".join("cta %d %.1f us (start %.1f)" % (np.flatnonzero(r[:, 0] > 0)[i] if False else i, (en - wk)[i], st[i]) for i in order))
 
 
+ob = cm.last_cta_trace(2, 360).astype(np.float64)
+ob = ob[ob[:, 0] > 0]
+if len(ob):
+    rel = lambda c: (ob[:, c] - t0) / 1e3
+    print("k_obstacle_update ray CTAs (us, mean / max): start %.1f / %.1f, rays traced %.1f / %.1f, marks tested %.1f / %.1f, "
+          "box flushed %.1f / %.1f, ticket taken %.1f / %.1f" %
+          (rel(0).mean(), rel(0).max(), rel(4).mean(), rel(4).max(), rel(5).mean(), rel(5).max(), rel(6).mean(),
+           rel(6).max(), rel(2).mean(), rel(2).max()))
 report("k_merge_seed", m)
 report("k_inflate", f)
 # k_inflate's stages per tile column class (us): seed words, pruning, phase 2, phase 3 + epilogue
