@@ -296,7 +296,7 @@ int upload_tables(navgpu_costmap* h, Layer& L) {
   size_t n = L.tables.by_d2.size();
   if (n > L.cost_d2_capacity) {
     if (L.d_cost_d2) cudaFree(L.d_cost_d2);
-    NAVGPU_CUDA(cudaMalloc(&L.d_cost_d2, n));
+    NAVGPU_CUDA(cudaMalloc(&L.d_cost_d2, n + 8));  // (k_inflate stages the table by 32-bit words)
     L.cost_d2_capacity = n;
   }
   NAVGPU_CUDA(cudaMemcpyAsync(L.d_cost_d2, L.tables.by_d2.data(), n, cudaMemcpyHostToDevice, h->stream));
@@ -1725,7 +1725,7 @@ int seam_run(uint8_t* master, const uint8_t* layer, uint32_t size_x, uint32_t si
     ml.policy[0] = policy;
   }
   if (R > 0) {
-    NAVGPU_TRY(ensure(&c->d_table, &c->cap_table, size_t(R) * R + 1));
+    NAVGPU_TRY(ensure(&c->d_table, &c->cap_table, size_t(R) * R + 1 + 8));  // (staged by 32-bit words)
     NAVGPU_CUDA(cudaMemcpyAsync(c->d_table, by_d2, size_t(R) * R + 1, cudaMemcpyHostToDevice, c->stream));
   }
   k_set_window<<<1, 32, 0, c->stream>>>(c->d_win, min_i, max_i, min_j - y_lo, max_j - y_lo);

@@ -1503,6 +1503,35 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   }
 }
 
+// k_inflate phase 3: dy^2 of window row j against the eight output rows k of a group, (j - k)^2 in both 16-bit halves:
+// c_dy2.v[j + 31][k] for j in [-31, 38] -- two broadcast 16-byte constant loads per seeded row instead of an add chain
+struct Dy2Table {
+  uint32_t v[8 + 2 * 31][8];
+  constexpr Dy2Table() : v() {
+    for (int p = 0; p < 8 + 2 * 31; ++p)
+      for (int k = 0; k < 8; ++k) v[p][k] = (uint32_t)((p - 31 - k) * (p - 31 - k)) * 0x10001u;
+  }
+};
+__constant__ Dy2Table c_dy2 = Dy2Table();
+
+// (lane 0 of a warp takes a number: a plain shared-memory atomic, without the warp-aggregation code the compiler wraps
+// around atomicAdd)
+__device__ __forceinline__ int smem_fetch_add(int* p, int v) {
+  int old;
+  asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
+}
+
+// 16-bit global accesses through an address held in one 64-bit register pair (k_inflate's epilogue)
+__device__ __forceinline__ uint32_t ldg_u16(unsigned long long addr) {
+  uint32_t v;
+  asm volatile("ld.global.u16 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg_u16(unsigned long long addr, uint32_t v) {
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
 struct InflateArgs {
   uint8_t* master;
   unsigned sx, sy, pitch;
@@ -1540,11 +1569,8 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   __shared__ uint8_t rowlist[kRows];         // the same rows as a list (any order), n_seeded of them
   __shared__ int n_seeded;
   __shared__ int next_group;                 // phase 3: the next 8-row group nobody has taken yet
-  // phase 3: dy^2 of window row j against the eight output rows k of a group, (j - k)^2 in both 16-bit halves:
-  // dy2tab[j + RMAX][k / 4] component k % 4 -- two broadcast 16-byte loads per seeded row instead of an add chain
-  __shared__ uint4 dy2tab[8 + 2 * RMAX][2];
   // cost by d^2, table[reach2 + 1] = 0 ("out of reach"); reach <= RMAX bounds reach2 by (RMAX + 1)^2 - 1
-  __shared__ uint8_t table[((RMAX + 1) * (RMAX + 1) + 1 + 15) & ~15];
+  __shared__ __align__(16) uint8_t table[((RMAX + 1) * (RMAX + 1) + 1 + 15) & ~15];
   const int tx0 = blockIdx.x * kITX, ty0 = blockIdx.y * kITY;
   // early mode: the flags of the k_merge_seed tiles this tile reads (seeds: columns tx0 - 32 .. tx0 + 95, rows
   // ty0 - R .. ty0 + kITY + R - 1; master cells: the tile itself), one per thread, requested before anything else
@@ -1563,8 +1589,14 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     }
   }
   // the cost table was uploaded long before this cycle: stage it while k_merge_seed is still draining, then wait
-  for (int i = threadIdx.x; i <= a.reach2; i += kIThreads) table[i] = a.cost_d2[i];
-  if (threadIdx.x == 0) table[a.reach2 + 1] = 0;
+  {  // (by 32-bit words; the word that holds entry reach2 + 1 gets its zero on the way)
+    const int zw = (a.reach2 + 1) >> 2;
+    for (int i = threadIdx.x; i <= zw; i += kIThreads) {
+      uint32_t v = reinterpret_cast<const uint32_t*>(a.cost_d2)[i];
+      if (i == zw) v &= ~(0xffu << (8 * ((a.reach2 + 1) & 3)));
+      reinterpret_cast<uint32_t*>(table)[i] = v;
+    }
+  }
   DevWindow w;
   if (a.ready) {
     // Every k_merge_seed CTA is resident or done by the time this grid is scheduled (it triggers the programmatic launch
@@ -1612,10 +1644,6 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     }
     if (tid < kIMaskWords) rowmask[tid] = dupmask[tid] = 0;
     if (tid == 0) n_seeded = next_group = 0;
-    for (int i = tid; i < (8 + 2 * RMAX) * 8; i += kIThreads) {
-      const int d = (i >> 3) - RMAX - (i & 7);
-      reinterpret_cast<uint32_t*>(dy2tab)[i] = (uint32_t)(d * d) * 0x10001u;
-    }
 #pragma unroll
     for (int k = 0; k < NI; ++k) {
       const int i = tid + k * kIThreads;
@@ -1672,7 +1700,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     if (lane == 0 && sm) {
       rowmask[warp + 1] = sm;
       dupmask[warp + 1] = dm;
-      if (lm) base = atomicAdd(&n_seeded, __popc(lm));
+      if (lm) base = smem_fetch_add(&n_seeded, __popc(lm));
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (seeded && !dup) rowlist[base + __popc(lm & ((1u << lane) - 1u))] = (uint8_t)r;
@@ -1717,11 +1745,12 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   const int x = tx0 + 2 * lane;
   const bool xok = x < (int)a.sx;
   const uint32_t keep_hi = x + 1 >= (int)a.sx ? 0xff00u : 0u;
+  const bool edge_tile = tx0 + kITX > (int)a.sx || ty0 + kITY > (int)a.sy;
   // (the groups are handed out as warps become free: a group far from every seed costs a few instructions, one next to a
   // shelf several hundred -- a fixed assignment leaves warps idle at the end of the tile)
   for (;;) {
     int g = 0;
-    if (lane == 0) g = atomicAdd(&next_group, 1);
+    if (lane == 0) g = smem_fetch_add(&next_group, 1);
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g >= kITY / 8) break;
     const int yr0 = g * 8;  // first tile row of this group; region rows yr0 .. yr0 + 7 + 2R
@@ -1768,7 +1797,8 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
             const int j = __ffs(m) - 1 + 32 * q - RMAX;
             m &= m - 1;
             const uint32_t hh = hb[cn[j] * (kITX / 2)];
-            const uint4 qa = dy2tab[j + RMAX][0], qb = dy2tab[j + RMAX][1];
+            const uint4* dq = reinterpret_cast<const uint4*>(c_dy2.v[j + 31]);
+            const uint4 qa = dq[0], qb = dq[1];
             acc[0] = __viaddmin_u16x2(hh, qa.x, acc[0]);
             acc[1] = __viaddmin_u16x2(hh, qa.y, acc[1]);
             acc[2] = __viaddmin_u16x2(hh, qa.z, acc[2]);
@@ -1804,9 +1834,16 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
     // Two rows at a time: the lane's 2 x 2 cells travel in one 32-bit word (bytes 0-1 row k, bytes 2-3 row k + 1), so
     // the byte maximum, the NO_INFORMATION test and the "did anything change" test are paid once per four cells.  A
     // cell out of reach looks up table[reach2 + 1] = 0 and a row that is not read counts as 0: max(0, 0) stores nothing.
-    const int kmax = xok ? min(8, (int)a.sy - (ty0 + yr0)) : 0;
     const uint32_t out_of_reach = R2x2 + 0x10001u;
-    const uint32_t cell0 = (uint32_t)(ty0 + yr0) * a.pitch + (uint32_t)x;  // (sy * pitch < 2^32: sizes are < 65536)
+    if (edge_tile) {  // (block-uniform) rows below the map and lanes right of it: out of reach, nothing is read or written
+      const int kmax = xok ? min(8, (int)a.sy - (ty0 + yr0)) : 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k >= kmax) acc[k] = 0x7fff7fffu;
+    }
+    // (the group's first cell as one 64-bit register pair: a row's address is then a single 32 x 32 + 64 multiply-add)
+    unsigned long long prow = (unsigned long long)__cvta_generic_to_global(a.master + ((size_t)(ty0 + yr0) * a.pitch + x));
+    asm volatile("" : "+l"(prow));
     const uint32_t keep_hi4 = keep_hi * 0x10001u;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {  // four rows at a time keeps the loads in flight within 32 registers
@@ -1814,9 +1851,9 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int k = 4 * half + q;
-        d2[q] = k < kmax ? __vminu2(acc[k], out_of_reach) : out_of_reach;
+        d2[q] = __vminu2(acc[k], out_of_reach);
         cur[q] = 0;
-        if (d2[q] != out_of_reach) cur[q] = *reinterpret_cast<const uint16_t*>(a.master + (cell0 + (uint32_t)k * a.pitch));
+        if (d2[q] != out_of_reach) cur[q] = ldg_u16(prow + (unsigned long long)((uint32_t)k * a.pitch));
       }
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr) {
@@ -1833,8 +1870,8 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
           out = (noinfo & ((ge & c) | (~ge & old4))) | (~noinfo & out);
         }
         const uint32_t diff = out ^ old4;
-        if (diff & 0xffffu) *reinterpret_cast<uint16_t*>(a.master + (cell0 + (uint32_t)k * a.pitch)) = (uint16_t)out;
-        if (diff >> 16) *reinterpret_cast<uint16_t*>(a.master + (cell0 + (uint32_t)(k + 1) * a.pitch)) = (uint16_t)(out >> 16);
+        if (diff & 0xffffu) stg_u16(prow + (unsigned long long)((uint32_t)k * a.pitch), out);
+        if (diff >> 16) stg_u16(prow + (unsigned long long)((uint32_t)(k + 1) * a.pitch), out >> 16);
       }
     }
   }
