@@ -711,8 +711,8 @@ int enqueue_update(navgpu_costmap* h, double rx, double ry, double ryaw) {
       early.epoch = oa.done_epoch;
     }
     oa.boxes = h->d_boxes; oa.infl = h->d_infl; oa.win = h->d_win;
-    const int blocks = std::max(1, (L.total_rays * 32 + kObstacleThreads - 1) / kObstacleThreads);
-    k_obstacle_update<<<blocks, kObstacleThreads, 0, h->stream>>>(oa);
+    const int blocks = std::max(1, (L.total_rays + kObstacleRayWarps - 1) / kObstacleRayWarps);
+    k_obstacle_update<<<blocks, kObstacleUpdateThreads, 0, h->stream>>>(oa);
     NAVGPU_LAUNCHED(1);
     if (mode == 2) {  // large footprint: stand-alone rasteriser with dynamic shared memory
       size_t smem = 2 * kPolyMaxCells * sizeof(uint32_t);

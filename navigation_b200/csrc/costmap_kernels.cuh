@@ -93,6 +93,32 @@ struct BoxAcc {
       }
     }
   }
+  __device__ __forceinline__ void reduce_warp() {  // all 32 lanes must call; every lane ends up with the warp's box
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+      maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+      miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+      maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    }
+  }
+  // s_box holds one box per warp (written before the barrier in front of this call): threads 0..3 fold them into the
+  // layer's device box, one atomic per coordinate and CTA
+  static __device__ __forceinline__ void flush_rows(DevBox* box, unsigned long long (*s_box)[4], int n_rows) {
+    if (threadIdx.x < 4) {
+      const bool is_min = threadIdx.x < 2;
+      unsigned long long v = s_box[0][threadIdx.x], any = s_box[0][2];
+      for (int w = 1; w < n_rows; ++w) {
+        v = is_min ? min(v, s_box[w][threadIdx.x]) : max(v, s_box[w][threadIdx.x]);
+        any = max(any, s_box[w][2]);
+      }
+      if (any != 0ull) {
+        unsigned long long* dst = threadIdx.x == 0 ? &box->minx : threadIdx.x == 1 ? &box->miny : threadIdx.x == 2 ? &box->maxx : &box->maxy;
+        if (is_min) atomicMin(dst, v);
+        else atomicMax(dst, v);
+      }
+    }
+  }
   __device__ __forceinline__ void flush_warp(DevBox* box) {  // all 32 lanes must call
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -334,9 +360,10 @@ __device__ __forceinline__ void mark_prepare(const Geom& g, const DevObs* __rest
 }
 
 constexpr unsigned kMarkTileW = 256, kMarkTileH = 32;  // = k_merge_seed's tile (static_assert next to that kernel)
+// (called by the first `nt` threads of the CTA; nt = 0: all of them)
 __device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, const long long* cells, int total_points,
-                                                uint8_t* __restrict__ tile_used = nullptr, unsigned pitch = 1) {
-  const int nt = blockDim.x;
+                                                uint8_t* __restrict__ tile_used = nullptr, unsigned pitch = 1, int nt = 0) {
+  if (nt == 0) nt = blockDim.x;
   constexpr int kU = 12;  // loads in flight per thread: a few thousand marks are one round trip for 256 threads
   for (int base = threadIdx.x; base < total_points; base += kU * nt) {
     long long cell[kU];
@@ -370,11 +397,17 @@ struct PolyArgs {
 };
 // cells / sorted: `capacity` packed (x | y << 16) entries each: the outline in order, and the vector convexFillCells
 // works on.  Called by every thread of one CTA.
-__device__ __forceinline__ void polygon_clear_cta(uint8_t* __restrict__ grid, unsigned pitch, const PolyArgs& poly,
-                                                  uint8_t value, uint32_t* cells, uint32_t* sorted, int capacity) {
+// First stage, by one warp (kWarp: lanes of the calling warp, warp-level barriers) or by the whole CTA: the outline
+// cells, and for regular outlines -- every column between the extreme vertices holds at least two outline cells, which
+// is what a closed outline gives -- per-column [min_y, max_y) in `sorted` (colmin | colmax | colcnt, W entries each):
+// the reference's column walk (costmap_2d.cpp:391-427) is then a per-column fill, the first two sorted entries of a
+// column seed min / max and the rest extend them.  Returns whether the outline is regular (uniform over the callers).
+template <bool kWarp>
+__device__ __forceinline__ bool polygon_prepare(const PolyArgs& poly, uint32_t* cells, uint32_t* sorted, int capacity) {
   __shared__ int edge_first[33];
-  __shared__ int n_total;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int s_irregular;
+  const int tid = kWarp ? (int)(threadIdx.x & 31) : (int)threadIdx.x, nt = kWarp ? 32 : (int)blockDim.x;
+  auto sync = [] { if (kWarp) __syncwarp(); else __syncthreads(); };
   if (tid == 0) {
     int acc = 0;
     for (int k = 0; k < poly.n; ++k) {
@@ -383,8 +416,9 @@ __device__ __forceinline__ void polygon_clear_cta(uint8_t* __restrict__ grid, un
       acc += max(abs(poly.vx[k1] - poly.vx[k]), abs(poly.vy[k1] - poly.vy[k])) + 1;
     }
     edge_first[poly.n] = acc;
+    s_irregular = 1;
   }
-  __syncthreads();
+  sync();
   const int n_outline = edge_first[poly.n];
   for (int j = tid; j < n_outline; j += nt) {
     int k = 0;
@@ -406,46 +440,62 @@ __device__ __forceinline__ void polygon_clear_cta(uint8_t* __restrict__ grid, un
     }
     cells[j] = (uint32_t)x | ((uint32_t)y << 16);
   }
-  __syncthreads();
-  // Regular outlines -- every column between the extreme vertices holds at least two outline cells, which is what a
-  // closed outline gives -- make the reference's column walk (costmap_2d.cpp:391-427) a per-column [min_y, max_y)
-  // fill: the first two sorted entries of a column seed min/max, the rest extend them.  That case runs in parallel;
-  // anything else (degenerate footprints) replays the walk verbatim below.
-  {
-    __shared__ int s_irregular;
-    int min_x = poly.vx[0], max_x = poly.vx[0], min_y = poly.vy[0], max_y = poly.vy[0];
-    for (int k = 1; k < poly.n; ++k) {
-      min_x = min(min_x, poly.vx[k]); max_x = max(max_x, poly.vx[k]);
-      min_y = min(min_y, poly.vy[k]); max_y = max(max_y, poly.vy[k]);
+  sync();
+  int min_x = poly.vx[0], max_x = poly.vx[0];
+  for (int k = 1; k < poly.n; ++k) { min_x = min(min_x, poly.vx[k]); max_x = max(max_x, poly.vx[k]); }
+  const int W = max_x - min_x + 1;
+  if (W >= 2 && 3 * W <= capacity) {  // uniform
+    int* colmin = reinterpret_cast<int*>(sorted);
+    int* colmax = colmin + W;
+    int* colcnt = colmax + W;
+    for (int c = tid; c < W; c += nt) { colmin[c] = 0x7fffffff; colmax[c] = -1; colcnt[c] = 0; }
+    if (tid == 0) s_irregular = 0;
+    sync();
+    for (int j = tid; j < n_outline; j += nt) {
+      const int c = (int)(cells[j] & 0xffffu) - min_x, y = (int)(cells[j] >> 16);
+      atomicMin(&colmin[c], y);
+      atomicMax(&colmax[c], y);
+      atomicAdd(&colcnt[c], 1);
     }
-    const int W = max_x - min_x + 1, H = max_y - min_y + 1;
-    if (W >= 2 && 3 * W <= capacity) {  // block-uniform
-      int* colmin = reinterpret_cast<int*>(sorted);
-      int* colmax = colmin + W;
-      int* colcnt = colmax + W;
-      for (int c = tid; c < W; c += nt) { colmin[c] = 0x7fffffff; colmax[c] = -1; colcnt[c] = 0; }
-      if (tid == 0) s_irregular = 0;
-      __syncthreads();
-      for (int j = tid; j < n_outline; j += nt) {
-        const int c = (int)(cells[j] & 0xffffu) - min_x, y = (int)(cells[j] >> 16);
-        atomicMin(&colmin[c], y);
-        atomicMax(&colmax[c], y);
-        atomicAdd(&colcnt[c], 1);
-      }
-      __syncthreads();
-      for (int c = tid; c < W; c += nt)
-        if (colcnt[c] < 2) s_irregular = 1;
-      __syncthreads();
-      if (!s_irregular) {
-        for (int j = tid; j < n_outline; j += nt) grid[(size_t)(cells[j] >> 16) * pitch + (cells[j] & 0xffffu)] = value;
-        for (int j = tid; j < W * H; j += nt) {
-          const int c = j % W, y = min_y + j / W;
-          if (y >= colmin[c] && y < colmax[c]) grid[(size_t)y * pitch + (min_x + c)] = value;
-        }
-        return;
-      }
-      __syncthreads();  // the scratch is reused by the walk
-    }
+    sync();
+    for (int c = tid; c < W; c += nt)
+      if (colcnt[c] < 2) s_irregular = 1;
+    sync();
+  }
+  return s_irregular == 0;
+}
+
+// Second stage for regular outlines, by every thread of the CTA (behind a barrier after polygon_prepare)
+__device__ __forceinline__ void polygon_fill_regular(uint8_t* __restrict__ grid, unsigned pitch, const PolyArgs& poly,
+                                                     uint8_t value, const uint32_t* cells, const uint32_t* sorted) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int min_x = poly.vx[0], max_x = poly.vx[0], min_y = poly.vy[0], max_y = poly.vy[0], n_outline = 0;
+  for (int k = 0; k < poly.n; ++k) {
+    const int k1 = (k + 1) % poly.n;
+    min_x = min(min_x, poly.vx[k]); max_x = max(max_x, poly.vx[k]);
+    min_y = min(min_y, poly.vy[k]); max_y = max(max_y, poly.vy[k]);
+    n_outline += max(abs(poly.vx[k1] - poly.vx[k]), abs(poly.vy[k1] - poly.vy[k])) + 1;
+  }
+  const int W = max_x - min_x + 1, H = max_y - min_y + 1;
+  const int* colmin = reinterpret_cast<const int*>(sorted);
+  const int* colmax = colmin + W;
+  for (int j = tid; j < n_outline; j += nt) grid[(size_t)(cells[j] >> 16) * pitch + (cells[j] & 0xffffu)] = value;
+  for (int j = tid; j < W * H; j += nt) {
+    const int c = j % W, y = min_y + j / W;
+    if (y >= colmin[c] && y < colmax[c]) grid[(size_t)y * pitch + (min_x + c)] = value;
+  }
+}
+
+// What is left for outlines that are not regular (degenerate footprints): the reference's walk replayed verbatim.
+// `cells` holds the outline (polygon_prepare); every thread of the CTA calls.
+__device__ __forceinline__ void polygon_fill_irregular(uint8_t* __restrict__ grid, unsigned pitch, const PolyArgs& poly,
+                                                       uint8_t value, uint32_t* cells, uint32_t* sorted, int capacity) {
+  __shared__ int n_total;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int n_outline = 0;
+  for (int k = 0; k < poly.n; ++k) {
+    const int k1 = (k + 1) % poly.n;
+    n_outline += max(abs(poly.vx[k1] - poly.vx[k]), abs(poly.vy[k1] - poly.vy[k])) + 1;
   }
   for (int j = tid; j < n_outline; j += nt) {  // stable rank by x
     const uint32_t xj = cells[j] & 0xffffu;
@@ -483,6 +533,17 @@ __device__ __forceinline__ void polygon_clear_cta(uint8_t* __restrict__ grid, un
     const uint32_t c = sorted[j];
     grid[(size_t)(c >> 16) * pitch + (c & 0xffffu)] = value;
   }
+}
+
+// The whole thing by one CTA (cells / sorted: `capacity` entries each)
+__device__ __forceinline__ void polygon_clear_cta(uint8_t* __restrict__ grid, unsigned pitch, const PolyArgs& poly,
+                                                  uint8_t value, uint32_t* cells, uint32_t* sorted, int capacity) {
+  if (polygon_prepare<false>(poly, cells, sorted, capacity)) {
+    polygon_fill_regular(grid, pitch, poly, value, cells, sorted);
+    return;
+  }
+  __syncthreads();  // the scratch is reused by the walk
+  polygon_fill_irregular(grid, pitch, poly, value, cells, sorted, capacity);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -615,13 +676,15 @@ struct ObstacleArgs {
   unsigned done_epoch = 0;
 };
 constexpr int kObstacleThreads = 256;
+// k_obstacle_update: eight ray warps and one more warp that runs this CTA's share of the marking tests next to them
+// (two cold instruction streams side by side instead of one after the other)
+constexpr int kObstacleRayWarps = 8, kObstacleUpdateThreads = 32 * (kObstacleRayWarps + 1);
 
-__global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleArgs a) {
+__global__ void __maxnreg__(48) k_obstacle_update(ObstacleArgs a) {
   __shared__ uint32_t poly_cells[kPolySmallCells], poly_sorted[kPolySmallCells];
-  __shared__ unsigned long long s_box[kObstacleThreads / 32][4];
+  __shared__ unsigned long long s_box[kObstacleRayWarps + 1][4];
   __shared__ bool s_last;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * kObstacleThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, cta_warp = threadIdx.x >> 5;
   cudaTriggerProgrammaticLaunchCompletion();  // k_merge_seed may be scheduled behind us; it waits for our completion
   if (a.trace && threadIdx.x == 0) atomicMin(&a.trace[0], trace_now());
   // the observation tables travel in the kernel parameters when they fit (no dependent global loads to find a ray's
@@ -630,18 +693,24 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   const DevObs* mark_tab = a.n_mark <= kInlineObs ? a.mark_inline : a.mark;
   BoxAcc acc;
   trace_cta(a.trace, 2, blockIdx.x, 0);
-  raytrace_ray(a.grid, a.g, clear_tab, a.n_clear, a.xyz, a.total_rays, acc, warp, lane);
-  trace_cta(a.trace, 2, blockIdx.x, 4);
-  {  // this CTA's share of the marking tests
+  if (cta_warp < kObstacleRayWarps) {
+    raytrace_ray(a.grid, a.g, clear_tab, a.n_clear, a.xyz, a.total_rays, acc, blockIdx.x * kObstacleRayWarps + cta_warp, lane);
+    trace_cta(a.trace, 2, blockIdx.x, 4);
+    // (a ray touches its end point from lane 0 only: nothing to reduce within the warp)
+    if (lane == 0) { s_box[cta_warp][0] = acc.minx; s_box[cta_warp][1] = acc.miny; s_box[cta_warp][2] = acc.maxx; s_box[cta_warp][3] = acc.maxy; }
+  } else {  // this CTA's share of the marking tests
     const int per_cta = (a.total_marks + gridDim.x - 1) / gridDim.x;
-    for (int i = threadIdx.x; i < per_cta; i += kObstacleThreads) {
+    for (int i = lane; i < per_cta; i += 32) {
       const int t = blockIdx.x * per_cta + i;
       if (t < a.total_marks)
         mark_prepare(a.g, mark_tab, a.n_mark, a.xyz, a.max_obstacle_height, acc, a.mark_cells, t);
     }
+    if (a.trace && lane == 0 && blockIdx.x < kCtaTraceMax) a.trace[16 + 8 * (2 * (size_t)kCtaTraceMax + blockIdx.x) + 5] = trace_now();
+    acc.reduce_warp();
+    if (lane == 0) { s_box[cta_warp][0] = acc.minx; s_box[cta_warp][1] = acc.miny; s_box[cta_warp][2] = acc.maxx; s_box[cta_warp][3] = acc.maxy; }
   }
-  trace_cta(a.trace, 2, blockIdx.x, 5);
-  acc.flush_cta(a.box, s_box);
+  __syncthreads();
+  BoxAcc::flush_rows(a.box, s_box, kObstacleRayWarps + 1);
   __syncthreads();
   trace_cta(a.trace, 2, blockIdx.x, 6);
   if (threadIdx.x == 0) {
@@ -656,10 +725,20 @@ __global__ void __launch_bounds__(kObstacleThreads) k_obstacle_update(ObstacleAr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  mark_commit_cta(a.grid, a.mark_cells, a.total_marks, a.tile_used, a.g.pitch);
+  // the ray warps store the marks while the ninth warp prepares the footprint polygon; its stores follow the marks
+  __shared__ bool s_regular;
+  if (cta_warp < kObstacleRayWarps) {
+    mark_commit_cta(a.grid, a.mark_cells, a.total_marks, a.tile_used, a.g.pitch, 32 * kObstacleRayWarps);
+  } else if (a.do_poly) {
+    const bool regular = polygon_prepare<true>(a.poly, poly_cells, poly_sorted, kPolySmallCells);
+    if (lane == 0) s_regular = regular;
+  }
   __syncthreads();
   if (a.trace && threadIdx.x == 0) a.trace[10] = trace_now();
-  if (a.do_poly) polygon_clear_cta(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
+  if (a.do_poly) {
+    if (s_regular) polygon_fill_regular(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted);
+    else polygon_fill_irregular(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
+  }
   if (a.trace && threadIdx.x == 0) a.trace[11] = trace_now();
   if (a.done_flag) {
     __syncthreads();  // every thread's mark / polygon stores are ordered before the release below

@@ -20,13 +20,16 @@ obs, robot = sets[0]
 cm.set_observations(o, obs if os.environ.get("PROBE_NO_OBS") is None else [])
 stream = torch.cuda.ExternalStream(cm.stream())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush64 = flush.view(torch.int64)
 n_merge = ((size + 255) // 256) * ((size + 31) // 32)
 n_infl = ((size + 63) // 64) * ((size + 127) // 128)
 n_merge, n_infl = min(n_merge, 4096), min(n_infl, 4096)
 for k in range(8):
-    if os.environ.get("PROBE_FLUSH", "1") == "1":
+    if os.environ.get("PROBE_FLUSH", "1") in ("1", "2"):
         with torch.cuda.stream(stream):
             flush.zero_()
+            if os.environ.get("PROBE_FLUSH") == "2":  # a read pass behind the write: the L2 ends up full of CLEAN lines
+                flush64.sum()
     cm.touch_grid_layer(s, 0, 0, size, size)
     cm.update_map_async(*robot)
     t = cm.last_trace().astype(np.int64)
