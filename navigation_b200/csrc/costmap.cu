@@ -385,7 +385,7 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
              (a.ml.n == 1 || a.ml.policy[1] == NAVGPU_MAX || a.ml.policy[1] == NAVGPU_OVERWRITE) && !getenv("NAVGPU_NO_LEAN_MERGE");
     if (R > 0 && !seeds) return fail(NAVGPU_ERR_INVALID, "seed bitmask missing");
     dim3 block(kMSGroupsX, kMSRowsY);
-    dim3 grid((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16), (a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
+    dim3 grid((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16), (a.sy + kMSTileH - 1) / kMSTileH);
     const bool handover = flags && flags->ready && a.early && R > 0 && !(prop && R > 0) && !ev_mid;
     if (handover) { m.ready = flags->ready; m.epoch = flags->epoch; }
     if (a.ml.n > 0 || a.do_reset || R > 0) {
@@ -482,8 +482,7 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
   TileFlags tf;
   tf.trace = h->d_trace;
   if (a.early && R > 0 && R <= 31 && !propagate) {
-    const size_t n_tiles = size_t((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16)) *
-                           ((a.sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
+    const size_t n_tiles = size_t((a.pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16)) * ((a.sy + kMSTileH - 1) / kMSTileH);
     if (!h->d_tile_ready) {
       NAVGPU_CUDA(cudaMalloc(&h->d_tile_ready, n_tiles * sizeof(unsigned)));
       NAVGPU_CUDA(cudaMemsetAsync(h->d_tile_ready, 0, n_tiles * sizeof(unsigned), h->stream));
@@ -903,8 +902,7 @@ int navgpu_costmap_add_obstacle_layer(navgpu_costmap* h, int combination_method,
   // are known to hold the default value.  Not for rolling maps (the grid shifts) or NO_INFORMATION defaults.
   static const bool no_summary = getenv("NAVGPU_NO_LAYER_SUMMARY") != nullptr;  // measurement switch
   if (!h->rolling && L.def == kFree && !no_summary) {
-    const size_t n_tiles = size_t((h->pitch + kMSGroupsX * 16 - 1) / (kMSGroupsX * 16)) *
-                           ((h->sy + kMSRowsY * kMSRowIters - 1) / (kMSRowsY * kMSRowIters));
+    const size_t n_tiles = size_t((h->pitch + kMarkTileW - 1) / kMarkTileW) * ((h->sy + kMarkTileH - 1) / kMarkTileH);
     NAVGPU_CUDA(cudaMalloc(&L.d_tile_used, n_tiles));
     NAVGPU_CUDA(cudaMemsetAsync(L.d_tile_used, 0, n_tiles, h->stream));
   }

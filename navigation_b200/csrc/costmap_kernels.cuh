@@ -1076,7 +1076,7 @@ struct MergeLayers {
   int n;
   const uint8_t* grid[kMaxLayers];
   int policy[kMaxLayers];
-  // Per layer, nullable: one byte per k_merge_seed tile (256 x 32 cells, row-major over ceil(pitch / 256) columns), 0 as
+  // Per layer, nullable: one byte per k_merge_seed sub-tile (256 x 32 cells, row-major over ceil(pitch / 256) columns), 0 as
   // long as every cell of the tile still holds FREE_SPACE.  An obstacle layer is FREE_SPACE almost everywhere (marks
   // exist where scans ever ended): the merge takes zeros for such a tile instead of reading 8 KB of them from HBM.
   const uint8_t* used[kMaxLayers] = {};
@@ -1266,7 +1266,12 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 //                  VIADDMNMX.U16x2 per row and cell pair; the epilogue looks the cost up by d^2 and applies
 //                  InflationLayer's max / NO_INFORMATION rule directly on the master grid, touching only rows that
 //                  inflation reaches.  A tile whose seed words are all zero exits after the load.
-constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2;  // k_merge_seed: CTA = 256 columns x 32 rows
+// k_merge_seed: a CTA walks kMSSubTiles sub-tiles of 256 columns x 32 rows (what MergeLayers::used summarises) top to
+// bottom: 256 x 128 cells per CTA.  (CTAs of one sub-tile live ~1.7 us and a freed slot stays empty for about a
+// microsecond before its next CTA runs -- tools/probe_cta_trace.py --; four times the work per CTA makes the 4000^2 pass
+// a single wave of 500 CTAs.)
+constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2, kMSSubTiles = 4;
+constexpr int kMSTileH = kMSRowsY * kMSRowIters * kMSSubTiles;
 static_assert(128 + 2 * 31 <= 256, "k_inflate: one thread per region row");
 static_assert(kMSGroupsX * 16 == (int)kMarkTileW && kMSRowsY * kMSRowIters == (int)kMarkTileH, "MergeLayers::used tile");
 constexpr int kITX = 64, kITY = 128, kIThreads = 256, kIMaxRows = kITY + 2 * 31;
@@ -1369,45 +1374,58 @@ __device__ __forceinline__ void merge_seed_lean(const MergeSeedArgs& a, int x, i
   // map are skipped, the row padding behind the last column is written like cells (nothing reads it) and seeds nothing
   if (kEdge && x >= (int)a.pitch) return;
   const int y0 = by0 + threadIdx.y;
-  const size_t off = (size_t)y0 * a.pitch + x, rs = (size_t)kMSRowsY * a.pitch;
-  uint4 v[kMSRowIters], o[kMSRowIters];
-#pragma unroll
-  for (int it = 0; it < kMSRowIters; ++it) {
-    v[it] = make_uint4(0, 0, 0, 0);
-    if (!kEdge || y0 + it * kMSRowsY < (int)a.sy) v[it] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off + it * rs);
-  }
+  const size_t off = (size_t)y0 * a.pitch + x, rs = (size_t)kMSRowsY * a.pitch;  // this thread's rows: y0 + 16 i
   const bool two = a.ml.n > 1;
-  bool use1 = two;
-  if (two && a.ml.used[1]) use1 = a.ml.used[1][blockIdx.y * gridDim.x + blockIdx.x] != 0;
-#pragma unroll
-  for (int it = 0; it < kMSRowIters; ++it) {
-    o[it] = make_uint4(0, 0, 0, 0);
-    if (use1 && (!kEdge || y0 + it * kMSRowsY < (int)a.sy)) o[it] = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off + it * rs);
-  }
   const int pol1 = a.ml.policy[1];
   const unsigned sp16 = seed_pitch16(a.pitch);
   uint16_t* srow = a.seeds + (size_t)y0 * sp16 + 2 + (x >> 4);
   uint32_t colmask = 0xffffu;
   if (kEdge && x + 16 > (int)a.sx) colmask = x >= (int)a.sx ? 0u : (1u << ((int)a.sx - x)) - 1u;
+  auto load = [&](int sub, uint4* dst) {  // first layer, the two rows of sub-tile `sub`
 #pragma unroll
-  for (int it = 0; it < kMSRowIters; ++it) {
-    if (kEdge && y0 + it * kMSRowsY >= (int)a.sy) continue;
-    uint4 m = v[it];
-    uint32_t hi = (m.x | m.y | m.z | m.w) & 0x80808080u;  // some byte >= 128: the group may hold 254 / 255
-    if (two) {
-      if ((o[it].x | o[it].y | o[it].z | o[it].w) != 0 || pol1 != NAVGPU_MAX) {
-        m = merge16(m, o[it], pol1);
-        hi = (m.x | m.y | m.z | m.w) & 0x80808080u;
-      } else if (hi) {  // Max with an all-FREE_SPACE group only turns NO_INFORMATION into 0
-        m.x &= ~((is255_4(m.x) >> 7) * 0xffu); m.y &= ~((is255_4(m.y) >> 7) * 0xffu);
-        m.z &= ~((is255_4(m.z) >> 7) * 0xffu); m.w &= ~((is255_4(m.w) >> 7) * 0xffu);
-      }
+    for (int it = 0; it < kMSRowIters; ++it) {
+      const int row = kMSRowIters * sub + it;
+      dst[it] = make_uint4(0, 0, 0, 0);
+      if (!kEdge || y0 + row * kMSRowsY < (int)a.sy) dst[it] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off + row * rs);
     }
-    *reinterpret_cast<uint4*>(a.master + off + it * rs) = m;
-    if (a.R > 0) {
-      uint32_t seed16 = 0;
-      if (hi) seed16 = lethal_bits4(m.x) | (lethal_bits4(m.y) << 4) | (lethal_bits4(m.z) << 8) | (lethal_bits4(m.w) << 12);
-      srow[(size_t)it * kMSRowsY * sp16] = (uint16_t)(seed16 & colmask);
+  };
+  uint4 v[2][kMSRowIters];
+  load(0, v[0]);
+  // the second layer's summary bytes of the sub-tiles, behind the first loads
+  uint32_t use1 = two ? (1u << kMSSubTiles) - 1u : 0u;
+  if (two && a.ml.used[1]) {
+    use1 = 0;
+#pragma unroll
+    for (int sub = 0; sub < kMSSubTiles; ++sub)
+      if (!kEdge || by0 + sub * (kMSRowsY * kMSRowIters) < (int)a.sy)
+        use1 |= (a.ml.used[1][(blockIdx.y * kMSSubTiles + sub) * gridDim.x + blockIdx.x] != 0 ? 1u : 0u) << sub;
+  }
+#pragma unroll
+  for (int sub = 0; sub < kMSSubTiles; ++sub) {
+    if (sub + 1 < kMSSubTiles) load(sub + 1, v[(sub + 1) & 1]);  // (one sub-tile ahead)
+#pragma unroll
+    for (int it = 0; it < kMSRowIters; ++it) {
+      const int row = kMSRowIters * sub + it;
+      if (kEdge && y0 + row * kMSRowsY >= (int)a.sy) continue;
+      uint4 m = v[sub & 1][it];
+      uint32_t hi = (m.x | m.y | m.z | m.w) & 0x80808080u;  // some byte >= 128: the group may hold 254 / 255
+      if (two) {
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if ((use1 >> sub) & 1u) o = *reinterpret_cast<const uint4*>(a.ml.grid[1] + off + row * rs);
+        if ((o.x | o.y | o.z | o.w) != 0 || pol1 != NAVGPU_MAX) {
+          m = merge16(m, o, pol1);
+          hi = (m.x | m.y | m.z | m.w) & 0x80808080u;
+        } else if (hi) {  // Max with an all-FREE_SPACE group only turns NO_INFORMATION into 0
+          m.x &= ~((is255_4(m.x) >> 7) * 0xffu); m.y &= ~((is255_4(m.y) >> 7) * 0xffu);
+          m.z &= ~((is255_4(m.z) >> 7) * 0xffu); m.w &= ~((is255_4(m.w) >> 7) * 0xffu);
+        }
+      }
+      *reinterpret_cast<uint4*>(a.master + off + row * rs) = m;
+      if (a.R > 0) {
+        uint32_t seed16 = 0;
+        if (hi) seed16 = lethal_bits4(m.x) | (lethal_bits4(m.y) << 4) | (lethal_bits4(m.z) << 8) | (lethal_bits4(m.w) << 12);
+        srow[(size_t)row * kMSRowsY * sp16] = (uint16_t)(seed16 & colmask);
+      }
     }
   }
 }
@@ -1504,7 +1522,7 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   cudaTriggerProgrammaticLaunchCompletion();
   trace_start(a.trace, 1);
   trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 0);
-  constexpr int kW = kMSGroupsX * 16, kH = kMSRowsY * kMSRowIters;
+  constexpr int kW = kMSGroupsX * 16, kH = kMSTileH;
   const int bx0 = blockIdx.x * kW, by0 = blockIdx.y * kH;
   DevWindow w;
   if (a.early) {
@@ -1558,18 +1576,25 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSe
   const int sy0 = max(0, w.y0 - R), syn = min((int)a.sy, w.yn + R);
   const int x = bx0 + threadIdx.x * 16;
   // the window lies inside the map, the seed region contains the window: a tile inside the window is interior
-  const bool interior = bx0 >= w.x0 && bx0 + kW <= w.xn && by0 >= w.y0 && by0 + kH <= w.yn;
-  // layers whose tile summary says "all FREE_SPACE here" are not read (after the wait above: the obstacle kernel sets
-  // the bytes of the tiles it marks)
-  unsigned used_mask = 0xffffffffu;
-  for (int l = 0; l < a.ml.n; ++l)
-    if (a.ml.used[l] && a.ml.used[l][blockIdx.y * gridDim.x + blockIdx.x] == 0) used_mask &= ~(1u << l);
-  if (interior && a.lean) {
+  if (a.lean && bx0 >= w.x0 && bx0 + kW <= w.xn && by0 >= w.y0 && by0 + kH <= w.yn) {
     merge_seed_lean<false>(a, x, by0);
-  } else if (interior) {
-    merge_seed_items<true>(a, w, x, by0, sx0, sxn, sy0, syn, used_mask);
-  } else if (x < (int)a.pitch) {
-    merge_seed_items<false>(a, w, x, by0, sx0, sxn, sy0, syn, used_mask);
+  } else {
+    for (int sub = 0; sub < kMSSubTiles; ++sub) {  // sub-tile by sub-tile
+      constexpr int kSH = kMSRowsY * kMSRowIters;
+      const int sy_0 = by0 + sub * kSH;
+      if (sy_0 >= (int)a.sy || sy_0 >= w.yn + my || sy_0 + kSH <= w.y0 - my) continue;
+      const bool interior = bx0 >= w.x0 && bx0 + kW <= w.xn && sy_0 >= w.y0 && sy_0 + kSH <= w.yn;
+      // layers whose tile summary says "all FREE_SPACE here" are not read (after the wait above: the obstacle kernel
+      // sets the bytes of the tiles it marks)
+      unsigned used_mask = 0xffffffffu;
+      for (int l = 0; l < a.ml.n; ++l)
+        if (a.ml.used[l] && a.ml.used[l][(blockIdx.y * kMSSubTiles + sub) * gridDim.x + blockIdx.x] == 0) used_mask &= ~(1u << l);
+      if (interior) {
+        merge_seed_items<true>(a, w, x, sy_0, sx0, sxn, sy0, syn, used_mask);
+      } else if (x < (int)a.pitch) {
+        merge_seed_items<false>(a, w, x, sy_0, sx0, sxn, sy0, syn, used_mask);
+      }
+    }
   }
   trace_end(a.trace, 1);
   trace_cta(a.trace, 0, blockIdx.y * gridDim.x + blockIdx.x, 2);
@@ -1658,10 +1683,10 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   trace_start(a.trace, 2);
   trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 0);
   if (a.ready) {
-    constexpr int kMW = kMSGroupsX * 16, kMH = kMSRowsY * kMSRowIters;
+    constexpr int kMW = kMSGroupsX * 16, kMH = kMSTileH;
     const int mx0 = max(0, tx0 - 32) / kMW, mx1 = min((int)a.pitch - 1, tx0 + kITX + 31) / kMW;
     const int my0 = max(0, ty0 - a.R) / kMH, my1 = min((int)a.sy - 1, ty0 + kITY + a.R - 1) / kMH;
-    const int nx = mx1 - mx0 + 1, n = nx * (my1 - my0 + 1);  // <= 2 x 7 for R <= 31
+    const int nx = mx1 - mx0 + 1, n = nx * (my1 - my0 + 1);  // <= 2 x 3 for R <= 31
     if ((int)threadIdx.x < n) {
       my_flag = a.ready + (my0 + (int)threadIdx.x / nx) * a.ready_pitch + mx0 + (int)threadIdx.x % nx;
       asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(flag_seen) : "l"(my_flag) : "memory");
