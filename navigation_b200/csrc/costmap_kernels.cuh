@@ -1270,7 +1270,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_update_costs(UpdateArgs a) {
 // bottom: 256 x 128 cells per CTA.  (CTAs of one sub-tile live ~1.7 us and a freed slot stays empty for about a
 // microsecond before its next CTA runs -- tools/probe_cta_trace.py --; four times the work per CTA makes the 4000^2 pass
 // a single wave of 500 CTAs.)
-constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2, kMSSubTiles = 4;
+constexpr int kMSGroupsX = 16, kMSRowsY = 16, kMSRowIters = 2, kMSSubTiles = 2;
 constexpr int kMSTileH = kMSRowsY * kMSRowIters * kMSSubTiles;
 static_assert(128 + 2 * 31 <= 256, "k_inflate: one thread per region row");
 static_assert(kMSGroupsX * 16 == (int)kMarkTileW && kMSRowsY * kMSRowIters == (int)kMarkTileH, "MergeLayers::used tile");
@@ -1389,8 +1389,9 @@ __device__ __forceinline__ void merge_seed_lean(const MergeSeedArgs& a, int x, i
       if (!kEdge || y0 + row * kMSRowsY < (int)a.sy) dst[it] = *reinterpret_cast<const uint4*>(a.ml.grid[0] + off + row * rs);
     }
   };
-  uint4 v[2][kMSRowIters];
-  load(0, v[0]);
+  uint4 v[kMSSubTiles][kMSRowIters];  // every row of the thread in flight before the first is used
+#pragma unroll
+  for (int sub = 0; sub < kMSSubTiles; ++sub) load(sub, v[sub]);
   // the second layer's summary bytes of the sub-tiles, behind the first loads
   uint32_t use1 = two ? (1u << kMSSubTiles) - 1u : 0u;
   if (two && a.ml.used[1]) {
@@ -1402,12 +1403,11 @@ __device__ __forceinline__ void merge_seed_lean(const MergeSeedArgs& a, int x, i
   }
 #pragma unroll
   for (int sub = 0; sub < kMSSubTiles; ++sub) {
-    if (sub + 1 < kMSSubTiles) load(sub + 1, v[(sub + 1) & 1]);  // (one sub-tile ahead)
 #pragma unroll
     for (int it = 0; it < kMSRowIters; ++it) {
       const int row = kMSRowIters * sub + it;
       if (kEdge && y0 + row * kMSRowsY >= (int)a.sy) continue;
-      uint4 m = v[sub & 1][it];
+      uint4 m = v[sub][it];
       uint32_t hi = (m.x | m.y | m.z | m.w) & 0x80808080u;  // some byte >= 128: the group may hold 254 / 255
       if (two) {
         uint4 o = make_uint4(0, 0, 0, 0);
@@ -1516,7 +1516,7 @@ __device__ __forceinline__ void merge_seed_items(const MergeSeedArgs& a, const D
   }
 }
 
-__global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 6) k_merge_seed(MergeSeedArgs a) {
+__global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 5) k_merge_seed(MergeSeedArgs a) {
   // launched with programmatic stream serialization: let k_inflate be scheduled as soon as every CTA of this grid
   // is resident, and wait for the kernel before us (window, obstacle grid) before reading anything
   cudaTriggerProgrammaticLaunchCompletion();

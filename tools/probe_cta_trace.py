@@ -21,7 +21,7 @@ cm.set_observations(o, obs if os.environ.get("PROBE_NO_OBS") is None else [])
 stream = torch.cuda.ExternalStream(cm.stream())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 flush64 = flush.view(torch.int64)
-n_merge = ((size + 255) // 256) * ((size + 127) // 128)
+n_merge = ((size + 255) // 256) * ((size + 63) // 64)
 n_infl = ((size + 63) // 64) * ((size + 127) // 128)
 n_merge, n_infl = min(n_merge, 4096), min(n_infl, 4096)
 for k in range(8):
