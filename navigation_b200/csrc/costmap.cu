@@ -4,9 +4,11 @@
 // touches grid cells runs in the kernels of costmap_kernels.cuh; the host keeps only the scalar state the reference
 // keeps in its objects (origins, parameters, cached tables, flags) and sequences the kernels of one update cycle.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <memory>
 #include <vector>
@@ -225,6 +227,7 @@ struct navgpu_costmap {
   uint8_t* h_mirror_stage = nullptr;     // mapped pinned: changed tiles, compacted
   unsigned* h_mirror_tiles = nullptr;    // mapped pinned: their tile numbers
   MirrorCtl* h_mirror_ctl = nullptr;     // mapped pinned
+  unsigned mirror_seq = 0;               // MirrorCtl::seq of the last k_mirror_diff
   unsigned* d_mirror_counters = nullptr;
   unsigned mirror_capacity = 0;
   // where the master grid can differ from the shadow (MirrorArgs::dirty / all / hx0..):
@@ -1435,6 +1438,7 @@ int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t h
     NAVGPU_CUDA(cudaHostAlloc(&h->h_mirror_stage, size_t(h->mirror_capacity) * kMirrorTileBytes, cudaHostAllocMapped));
     NAVGPU_CUDA(cudaHostAlloc(&h->h_mirror_tiles, size_t(h->mirror_capacity) * sizeof(unsigned), cudaHostAllocMapped));
     NAVGPU_CUDA(cudaHostAlloc(&h->h_mirror_ctl, sizeof(MirrorCtl), cudaHostAllocMapped));
+    memset(h->h_mirror_ctl, 0, sizeof(MirrorCtl));
     h->shadow_valid = false;
   }
   if (host_grid != h->mirror_host || host_pitch != h->mirror_host_pitch) h->shadow_valid = false;
@@ -1513,10 +1517,28 @@ int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t h
   h->refine_valid = true;  // from here on: until a cycle that is not of the refinable kind
   h->refine[0] = h->refine[1] = h->refine[2] = h->refine[3] = 0;
   const unsigned launched_tiles = std::max(1u, a.tw * a.th);  // (one CTA at least: it publishes the counts and the window)
-  k_mirror_diff<<<(launched_tiles + kMirrorWarps - 1) / kMirrorWarps, kMirrorWarps * 32, 0, h->stream>>>(a);
+  a.seq = ++h->mirror_seq;
+  NAVGPU_CUDA(launch_pdl(k_mirror_diff, dim3((launched_tiles + kMirrorWarps - 1) / kMirrorWarps), dim3(kMirrorWarps * 32), 0,
+                         h->stream, a));
   NAVGPU_LAUNCHED(1);
   NAVGPU_CUDA(cudaGetLastError());
-  NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  {  // wait for the kernel's last word in mapped memory; a stream synchronisation backs the poll up (errors, hangs)
+    static const bool no_poll = getenv("NAVGPU_NO_MIRROR_POLL") != nullptr;
+    const volatile unsigned* seq = &h->h_mirror_ctl->seq;
+    bool seen = false;
+    if (!no_poll) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (unsigned spin = 0;; ++spin) {
+        if (*seq == a.seq) { seen = true; break; }
+        if ((spin & 1023u) == 1023u && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!seen) NAVGPU_CUDA(cudaStreamSynchronize(h->stream));
+  }
   const MirrorCtl& ctl = *h->h_mirror_ctl;
   if (a.win) { h->win[0] = ctl.win.x0; h->win[1] = ctl.win.xn; h->win[2] = ctl.win.y0; h->win[3] = ctl.win.yn; }
   if (ctl.n_changed > h->mirror_capacity && !a.host_direct) {  // the shadow is up to date already; the host takes the plain copy

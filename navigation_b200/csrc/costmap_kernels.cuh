@@ -1680,6 +1680,7 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   // ty0 - R .. ty0 + kITY + R - 1; master cells: the tile itself), one per thread, requested before anything else
   const unsigned* my_flag = nullptr;
   unsigned flag_seen = 0;
+  cudaTriggerProgrammaticLaunchCompletion();  // (a k_mirror_diff behind us may become resident; it waits for our end)
   trace_start(a.trace, 2);
   trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 0);
   if (a.ready) {

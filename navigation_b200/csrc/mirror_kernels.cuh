@@ -23,6 +23,10 @@ struct MirrorCtl {  // mapped pinned host memory: written by the last CTA of k_m
   unsigned n_changed;  // tiles that differ (may exceed the staging capacity: then the host copies the whole grid)
   unsigned n_staged;   // tiles actually written to the staging buffer = min(n_changed, capacity)
   DevWindow win;       // the window of the last update cycle, so that one synchronisation serves both
+  // written last, behind a system-scope fence: the call's number.  The host polls this word instead of synchronising the
+  // stream (the documented mapped-memory signalling pattern: data, __threadfence_system(), flag), which takes the
+  // stream-synchronisation wake-up out of every cycle.
+  unsigned seq;
 };
 
 struct MirrorArgs {
@@ -49,6 +53,7 @@ struct MirrorArgs {
   // bytes apart) -- changed tiles are written straight to their place in it and only their numbers are staged
   uint8_t* host_direct;
   unsigned host_pitch;
+  unsigned seq;  // MirrorCtl::seq of this call
 };
 
 // bytes of a and b that differ among the first n_valid bytes of the 16-byte group
@@ -68,6 +73,9 @@ __device__ __forceinline__ bool group_differs(const uint4& a, const uint4& b, in
 __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a) {
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // launched with programmatic stream serialization behind the cycle's last kernel: resident while that kernel drains,
+  // reading nothing before it has completed
+  cudaGridDependencySynchronize();
   const unsigned local = blockIdx.x * kMirrorWarps + warp;  // index within the launched rectangle of tiles
   const unsigned n_tiles = a.tiles_x * a.tiles_y;
   const unsigned tile = local < a.tw * a.th ? (a.ty0 + local / a.tw) * a.tiles_x + a.tx0 + local % a.tw : n_tiles;
@@ -133,12 +141,12 @@ __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a)
   // the CTA that finishes last publishes the counts (and the cycle's window) and re-arms the counters
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    __threadfence_system();  // (this CTA's tiles are in host memory before its ticket counts)
     s_last = atomicAdd(&a.counters[1], 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
-  __threadfence();
+  __threadfence_system();
   const unsigned n = *reinterpret_cast<volatile unsigned*>(&a.counters[0]);
   a.ctl->n_changed = n;
   a.ctl->n_staged = min(n, a.capacity);
@@ -146,6 +154,8 @@ __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a)
   a.counters[0] = 0;
   a.counters[1] = 0;
   a.dirty->valid = 0;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned*>(&a.ctl->seq) = a.seq;
 }
 
 }  // namespace navgpu
