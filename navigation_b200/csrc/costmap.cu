@@ -228,6 +228,11 @@ struct navgpu_costmap {
   unsigned* h_mirror_tiles = nullptr;    // mapped pinned: their tile numbers
   MirrorCtl* h_mirror_ctl = nullptr;     // mapped pinned
   unsigned mirror_seq = 0;               // MirrorCtl::seq of the last k_mirror_diff
+  // InflateArgs::done of the sweep that was enqueued last, if it publishes per-tile completion (0: it does not)
+  unsigned* d_inflate_done = nullptr;
+  size_t inflate_done_capacity = 0;
+  unsigned inflate_done_epoch = 0;
+  int inflate_done_pitch = 0;
   unsigned* d_mirror_counters = nullptr;
   unsigned mirror_capacity = 0;
   // where the master grid can differ from the shadow (MirrorArgs::dirty / all / hx0..):
@@ -366,7 +371,10 @@ struct TileFlags {  // early mode: k_merge_seed -> k_inflate per-tile hand-over 
   unsigned* ready = nullptr;
   unsigned epoch = 0;
   unsigned long long* trace = nullptr;
+  unsigned* done = nullptr;        // InflateArgs::done
+  bool* handed_over = nullptr;     // out: the sweep used the per-tile flags (and published `done`)
 };
+static_assert(kMirrorInflateTileW == kITX && kMirrorInflateTileH == kITY, "k_mirror_diff waits for k_inflate's tiles");
 
 int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool force_generic, cudaEvent_t ev_mid = nullptr,
                  const PropBuffers* prop = nullptr, const TileFlags* flags = nullptr) {
@@ -406,7 +414,11 @@ int launch_sweep(const UpdateArgs& a, uint16_t* seeds, cudaStream_t stream, bool
       ia.reach2 = a.reach2;
       ia.cost_d2 = a.cost_d2;
       ia.seeds = reinterpret_cast<const uint32_t*>(seeds);
-      if (handover) { ia.ready = flags->ready; ia.epoch = flags->epoch; ia.ready_pitch = (int)grid.x; }
+      if (handover) {
+        ia.ready = flags->ready; ia.epoch = flags->epoch; ia.ready_pitch = (int)grid.x;
+        ia.done = flags->done;
+        if (flags->handed_over) *flags->handed_over = flags->done != nullptr;
+      }
       ia.trace = flags ? flags->trace : nullptr;
       dim3 igrid((a.sx + kITX - 1) / kITX, (a.sy + kITY - 1) / kITY);
       // the instantiation whose unrolled row walk just covers the effective reach (what k_inflate calls R)
@@ -492,10 +504,25 @@ int launch_update(navgpu_costmap* h, const MergeLayers& ml, int do_reset, int R,
     }
     tf.ready = h->d_tile_ready;
     tf.epoch = ++h->sweep_epoch;
+    const size_t n_itiles = size_t((a.sx + kITX - 1) / kITX) * ((a.sy + kITY - 1) / kITY);
+    if (n_itiles > h->inflate_done_capacity) {
+      if (h->d_inflate_done) cudaFree(h->d_inflate_done);
+      NAVGPU_CUDA(cudaMalloc(&h->d_inflate_done, n_itiles * sizeof(unsigned)));
+      NAVGPU_CUDA(cudaMemsetAsync(h->d_inflate_done, 0, n_itiles * sizeof(unsigned), h->stream));
+      h->inflate_done_capacity = n_itiles;
+    }
+    tf.done = h->d_inflate_done;
   }
+  bool handed_over = false;
+  tf.handed_over = &handed_over;
+  h->inflate_done_epoch = 0;  // (whatever sweep ran before is no longer the last one)
   NAVGPU_TRY(launch_sweep(a, h->d_seeds, h->stream, h->force_generic, h->profile && R > 0 ? h->ev_mid : nullptr,
                           propagate ? &pb : nullptr, &tf));
   if (h->profile && R > 0) cudaEventRecord(h->ev_sweep[1], h->stream);
+  if (handed_over) {
+    h->inflate_done_epoch = tf.epoch;
+    h->inflate_done_pitch = (int)((a.sx + kITX - 1) / kITX);
+  }
   return NAVGPU_OK;
 }
 
@@ -855,7 +882,7 @@ int navgpu_costmap_destroy(navgpu_costmap* h) {
     cudaFree(L.vox[0]); cudaFree(L.vox[1]); cudaFree(L.d_tile_used);
   }
   cudaFree(h->master[0]); cudaFree(h->master[1]);
-  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_obst_done); cudaFree(h->d_occupancy);
+  cudaFree(h->d_boxes); cudaFree(h->d_infl); cudaFree(h->d_win); cudaFree(h->d_seeds); cudaFree(h->d_ticket); cudaFree(h->d_obst_done); cudaFree(h->d_inflate_done); cudaFree(h->d_occupancy);
   cudaFree(h->d_prop_state); cudaFree(h->d_prop_ctl);
   cudaFree(h->d_shadow); cudaFree(h->d_mirror_counters); cudaFree(h->d_mirror_dirty); cudaFree(h->d_tile_ready); cudaFree(h->d_trace);
   if (h->h_mirror_stage) cudaFreeHost(h->h_mirror_stage);
@@ -1507,6 +1534,9 @@ int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t h
     }
   }
   a.tx0 = 0; a.ty0 = 0; a.tw = tiles_x; a.th = tiles_y;
+  // (every cycle since the last call was a whole-map cycle on a clean grid: the sweep enqueued last is the only work in
+  // flight that writes the cells this call compares)
+  const bool mirror_refinable = !a.all && h->refine_valid;
   if (!a.all && h->refine_valid) {  // the host's box bounds the work: launch only the tiles it touches (possibly none)
     a.tx0 = (unsigned)a.hx0 / kMirrorTileW;
     a.ty0 = (unsigned)a.hy0 / kMirrorTileH;
@@ -1517,6 +1547,12 @@ int navgpu_costmap_get_changed(navgpu_costmap* h, uint8_t* host_grid, uint32_t h
   h->refine_valid = true;  // from here on: until a cycle that is not of the refinable kind
   h->refine[0] = h->refine[1] = h->refine[2] = h->refine[3] = 0;
   const unsigned launched_tiles = std::max(1u, a.tw * a.th);  // (one CTA at least: it publishes the counts and the window)
+  static const bool no_tile_wait = getenv("NAVGPU_NO_MIRROR_TILE_WAIT") != nullptr;
+  if (mirror_refinable && h->inflate_done_epoch != 0 && !no_tile_wait) {
+    a.inflate_done = h->d_inflate_done;
+    a.inflate_epoch = h->inflate_done_epoch;
+    a.inflate_pitch = h->inflate_done_pitch;
+  }
   a.seq = ++h->mirror_seq;
   NAVGPU_CUDA(launch_pdl(k_mirror_diff, dim3((launched_tiles + kMirrorWarps - 1) / kMirrorWarps), dim3(kMirrorWarps * 32), 0,
                          h->stream, a));

@@ -1650,13 +1650,14 @@ struct InflateArgs {
   const unsigned* ready = nullptr;
   unsigned epoch = 0;
   int ready_pitch = 0;  // k_merge_seed's gridDim.x
+  unsigned* done = nullptr;  // nullable: one word per tile of this grid, set to `epoch` when the tile's cells are final
   unsigned long long* trace = nullptr;
 };
 
 // RMAX bounds the effective reach (in cells) this instantiation can handle: the phase-3 walk is unrolled over
 // 8 + 2 * RMAX region rows, so a small RMAX keeps the kernel's code (and its instruction-cache footprint) small.
 template <int RMAX>
-__global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
+__device__ __forceinline__ void inflate_tile(const InflateArgs& a) {
   constexpr int kRows = kITY + 2 * RMAX;       // region rows this instantiation can hold
   __shared__ __align__(16) uint32_t pbits[kRows * 4];  // seed words W0..W3 of each region row (columns tx0-32 .. tx0+95), pruned
   __shared__ __align__(16) uint32_t h2[kRows * (kITX / 2)];  // packed u16x2 squared horizontal distances
@@ -1982,6 +1983,18 @@ __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   }
   trace_end(a.trace, 2);
   trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 2);
+}
+
+template <int RMAX>
+__global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
+  inflate_tile<RMAX>(a);
+  // whichever way the tile ended: its master cells are final.  k_mirror_diff (the host mirror) starts on the tiles it
+  // compares as soon as the inflate tiles that write them say so, instead of after the whole grid
+  if (a.done) {
+    __syncthreads();
+    if (threadIdx.x == 0)
+      asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.done + blockIdx.y * gridDim.x + blockIdx.x), "r"(a.epoch) : "memory");
+  }
 }
 
 inline size_t update_costs_smem(int R) {

@@ -54,7 +54,23 @@ struct MirrorArgs {
   uint8_t* host_direct;
   unsigned host_pitch;
   unsigned seq;  // MirrorCtl::seq of this call
+  // non-null: the sweep in front of this kernel was a whole-map cycle whose k_inflate publishes `inflate_epoch` per
+  // 64 x 128 tile (inflate_pitch tiles per row) when the tile's cells are final: a tile is compared as soon as the
+  // (at most two) inflate tiles that write it are done, while the rest of that kernel is still running
+  const unsigned* inflate_done = nullptr;
+  unsigned inflate_epoch = 0;
+  int inflate_pitch = 0;
 };
+constexpr int kMirrorInflateTileW = 64, kMirrorInflateTileH = 128;  // = k_inflate's tile (static_assert in costmap.cu)
+
+__device__ __forceinline__ void mirror_wait_word(const unsigned* p, unsigned want) {
+  unsigned seen;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(p) : "memory");
+    if (seen == want) break;
+    __nanosleep(100);
+  }
+}
 
 // bytes of a and b that differ among the first n_valid bytes of the 16-byte group
 __device__ __forceinline__ bool group_differs(const uint4& a, const uint4& b, int n_valid) {
@@ -75,7 +91,15 @@ __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // launched with programmatic stream serialization behind the cycle's last kernel: resident while that kernel drains,
   // reading nothing before it has completed
-  cudaGridDependencySynchronize();
+  if (a.inflate_done) {
+    // Every CTA of the k_inflate grid in front is resident or done by now (it triggers the programmatic launch at its
+    // first instruction).  Its tile (0, 0) depends on k_merge_seed's tile (0, 0), which waits for the END of the
+    // obstacle kernel: behind this word the cycle's window and the dirty box are final.
+    if (lane == 0) mirror_wait_word(a.inflate_done, a.inflate_epoch);
+    __syncwarp();
+  } else {
+    cudaGridDependencySynchronize();
+  }
   const unsigned local = blockIdx.x * kMirrorWarps + warp;  // index within the launched rectangle of tiles
   const unsigned n_tiles = a.tiles_x * a.tiles_y;
   const unsigned tile = local < a.tw * a.th ? (a.ty0 + local / a.tw) * a.tiles_x + a.tx0 + local % a.tw : n_tiles;
@@ -93,6 +117,13 @@ __global__ void __launch_bounds__(kMirrorWarps * 32) k_mirror_diff(MirrorArgs a)
                          (int)(ty_ * kMirrorTileH) < ryn && (int)((ty_ + 1) * kMirrorTileH) > ry0;
   if (tile < n_tiles && in_region) {
     const unsigned tx = tx_, ty = ty_;
+    if (a.inflate_done) {  // the two inflate tiles that cover this 128 x 16 tile
+      if (lane < kMirrorTileW / kMirrorInflateTileW) {
+        const int ix = (int)(tx * kMirrorTileW) / kMirrorInflateTileW + lane, iy = (int)(ty * kMirrorTileH) / kMirrorInflateTileH;
+        if (ix < a.inflate_pitch) mirror_wait_word(a.inflate_done + iy * a.inflate_pitch + ix, a.inflate_epoch);
+      }
+      __syncwarp();
+    }
     const int x = (int)tx * kMirrorTileW + (lane & 7) * 16;
     const int y0 = (int)ty * kMirrorTileH + (lane >> 3);
     const int n_valid = min(16, max(0, (int)a.sx - x));  // the row padding is nobody's data
