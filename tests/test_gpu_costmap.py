@@ -309,6 +309,65 @@ def test_repeated_rows_exact_mode(cuda, port, kind, radius):
     assert np.array_equal(outs[0], outs[1]), f"{int((outs[0] != outs[1]).sum())} cells differ"
 
 
+def moving_scans(static, res, cycle, n_obs, n_beams=180, rng_seed=5):
+    """Observations ray-cast through the static world plus a few boxes that exist only in the scans, from sensor poses
+    that move with `cycle`; returns (observations, robot pose)."""
+    sy, sx = static.shape
+    rng = np.random.default_rng(rng_seed)
+    cx, cy = sx // 2 - 60 + 9 * cycle, (sy // 160) * 80 + 83
+    centers = [(cx + int(rng.integers(-50, 120)), cy + int(rng.integers(-18, 18))) for _ in range(5)]
+    world = (static == 254) | synth.pallets(sx, sy, centers)
+    obs = []
+    for k in range(n_obs):
+        sensor = ((cx + 11 * k + 0.5) * res, (cy + 0.5) * res)
+        while world[int(sensor[1] / res), int(sensor[0] / res)]:
+            sensor = (sensor[0] + 5 * res, sensor[1])
+        pts = synth.raycast_scan(world, res, (0.0, 0.0), sensor, n_beams, 8.0, phase=0.002 * k)
+        obs.append(dict(origin=(sensor[0], sensor[1], 0.3), points=pts, obstacle_range=8.0, raytrace_range=8.0,
+                        marking=True, clearing=True))
+    return obs, (obs[-1]["origin"][0], obs[-1]["origin"][1], 0.1 * cycle)
+
+
+@pytest.mark.parametrize("stack", ["max", "overwrite", "two_obstacle_layers", "static_max", "large_footprint", "no_clearing"])
+def test_whole_map_cycles_on_layer_stacks(cuda, port, stack):
+    """Whole-map cycles (the static layer touched as a whole every cycle, scans moving) on the stacks that take the
+    different paths of the early-mode sweep: the lean merge with Max / Overwrite as the second policy, the generic merge
+    behind two obstacle kernels (the last one releases the "layer grids complete" word), a first layer merged with Max,
+    a footprint too large for the obstacle kernel's rasteriser (stand-alone polygon kernel: no early release), no
+    footprint clearing at all -- on a map that leaves partial tiles on both edges, three cycles each, the host mirror
+    brought up to date after every cycle.  Master grid, obstacle layers and mirror: bit-exact."""
+    sx, sy, res = 777, 1000, 0.05
+    static = synth.warehouse_static(sx, sy)
+    n_layers = 2 if stack == "two_obstacle_layers" else 1
+    fp = sc.square_footprint(1.6) if stack == "large_footprint" else sc.square_footprint()
+    cms = []
+    for api in (cuda, port):
+        cm = api.costmap(sx, sy, res)
+        s = cm.add_grid_layer(2 if stack == "static_max" else 0)
+        layers = [cm.add_obstacle_layer(0 if stack == "overwrite" else 1, stack != "no_clearing", 2.0) for _ in range(n_layers)]
+        il = cm.add_inflation_layer(0.8, 10.0)
+        cm.set_footprint(fp)
+        cm.set_grid_layer(s, static)
+        sc.select_inflation(cm, il, "exact", 0)
+        cms.append((cm, s, layers))
+    mirror = np.zeros((sy, sx), np.uint8)
+    for cycle in range(3):
+        outs = []
+        for cm, s, layers in cms:
+            for li, o in enumerate(layers):
+                obs, robot = moving_scans(static, res, cycle + 2 * li, 3, rng_seed=5 + li)
+                cm.set_observations(o, obs)
+            cm.touch_grid_layer(s, 0, 0, sx, sy)
+            w = cm.update_map(*robot)
+            outs.append((w, cm.get(), [cm.get_layer(o) for o in layers]))
+        assert outs[0][0] == outs[1][0] == (0, sx, 0, sy)
+        for a, b in zip(outs[0][2], outs[1][2]):
+            assert np.array_equal(a, b), f"cycle {cycle}: an obstacle layer differs on {int((a != b).sum())} cells"
+        assert np.array_equal(outs[0][1], outs[1][1]), f"cycle {cycle}: {int((outs[0][1] != outs[1][1]).sum())} master cells differ"
+        cms[0][0].get_changed(mirror)
+        assert np.array_equal(mirror, outs[0][1]), f"cycle {cycle}: the host mirror differs from the device grid"
+
+
 def test_blocked_propagation_three_seeds(cuda, port):
     """A tie-INDEPENDENT difference between nearest-seed and propagated inflation: lethal cells at (3,3), (4,1), (0,5)
     (relative), R = 10, cost_scaling_factor 3: the compiled reference writes 158 one cell left of the first column's
