@@ -1703,7 +1703,6 @@ __device__ __forceinline__ void inflate_tile(const InflateArgs& a) {
       reinterpret_cast<uint32_t*>(table)[i] = v;
     }
   }
-  DevWindow w;
   if (a.ready) {
     // Every k_merge_seed CTA is resident or done by the time this grid is scheduled (it triggers the programmatic launch
     // at its first instruction), so waiting for some of them cannot deadlock.
@@ -1713,19 +1712,17 @@ __device__ __forceinline__ void inflate_tile(const InflateArgs& a) {
         asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(flag_seen) : "l"(my_flag) : "memory");
       }
     }
-    __syncthreads();
-    w.x0 = 0; w.xn = (int)a.sx; w.y0 = 0; w.yn = (int)a.sy; w.valid = 1;
+    __syncthreads();  // (the window is the whole map: every tile of the grid is in it)
     if (a.trace && threadIdx.x == 0) {
       atomicMin(&a.trace[7], trace_now());
       atomicMax(&a.trace[8], trace_now());
     }
+    trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 1);
   } else {
     cudaGridDependencySynchronize();
-    w = *a.win;
-  }
-  trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 1);
-  if (!w.valid) return;
-  {
+    const DevWindow w = *a.win;
+    trace_cta(a.trace, 1, blockIdx.y * gridDim.x + blockIdx.x, 1);
+    if (!w.valid) return;
     const int R = a.R;
     if (tx0 >= w.xn + 2 * R || tx0 + kITX <= w.x0 - 2 * R || ty0 >= w.yn + 2 * R || ty0 + kITY <= w.y0 - 2 * R) return;
   }
@@ -1961,23 +1958,32 @@ __device__ __forceinline__ void inflate_tile(const InflateArgs& a) {
         cur[q] = 0;
         if (d2[q] != out_of_reach) cur[q] = ldg_u16(prow + (unsigned long long)((uint32_t)k * a.pitch));
       }
+      if (d2[0] == out_of_reach && d2[1] == out_of_reach && d2[2] == out_of_reach && d2[3] == out_of_reach) continue;
+      uint32_t old4[2], out[2];
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        const uint32_t da = d2[2 * pr], db = d2[2 * pr + 1];
+        const uint32_t c = ((uint32_t)table[da & 0xffffu] | ((uint32_t)table[da >> 16] << 8) |
+                            ((uint32_t)table[db & 0xffffu] << 16) | ((uint32_t)table[db >> 16] << 24)) & ~keep_hi4;
+        old4[pr] = cur[2 * pr] | (cur[2 * pr + 1] << 16);
+        out[pr] = __vmaxu4(old4[pr], c);  // no cell NO_INFORMATION (the usual case): a plain maximum (:253-254)
+        d2[2 * pr] = c;                   // (kept for the NO_INFORMATION rule below)
+      }
+      // NO_INFORMATION is replaced only by costs >= INSCRIBED_INFLATED_OBSTACLE, and then by the cost (:249-252): where
+      // old == 255 the maximum is 255, and 255 - (255 - c) = c
+      if ((__vcmpeq4(old4[0], 0xffffffffu) | __vcmpeq4(old4[1], 0xffffffffu)) != 0) {
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const uint32_t c = d2[2 * pr];
+          out[pr] -= __vcmpeq4(old4[pr], 0xffffffffu) & __vcmpgeu4(c, 0xfdfdfdfdu) & ~c;
+        }
+      }
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr) {
         const int k = 4 * half + 2 * pr;
-        const uint32_t da = d2[2 * pr], db = d2[2 * pr + 1];
-        if (da == out_of_reach && db == out_of_reach) continue;
-        const uint32_t c = ((uint32_t)table[da & 0xffffu] | ((uint32_t)table[da >> 16] << 8) |
-                            ((uint32_t)table[db & 0xffffu] << 16) | ((uint32_t)table[db >> 16] << 24)) & ~keep_hi4;
-        const uint32_t old4 = cur[2 * pr] | (cur[2 * pr + 1] << 16);
-        uint32_t out = __vmaxu4(old4, c);  // neither cell NO_INFORMATION (the usual case): a plain maximum (:253-254)
-        const uint32_t noinfo = __vcmpeq4(old4, 0xffffffffu);
-        if (noinfo) {  // NO_INFORMATION is replaced only by costs >= INSCRIBED_INFLATED_OBSTACLE, and then by the cost (:249-252)
-          const uint32_t ge = __vcmpgeu4(c, 0xfdfdfdfdu);
-          out = (noinfo & ((ge & c) | (~ge & old4))) | (~noinfo & out);
-        }
-        const uint32_t diff = out ^ old4;
-        if (diff & 0xffffu) stg_u16(prow + (unsigned long long)((uint32_t)k * a.pitch), out);
-        if (diff >> 16) stg_u16(prow + (unsigned long long)((uint32_t)(k + 1) * a.pitch), out >> 16);
+        const uint32_t diff = out[pr] ^ old4[pr];
+        if (diff & 0xffffu) stg_u16(prow + (unsigned long long)((uint32_t)k * a.pitch), out[pr]);
+        if (diff >> 16) stg_u16(prow + (unsigned long long)((uint32_t)(k + 1) * a.pitch), out[pr] >> 16);
       }
     }
   }
