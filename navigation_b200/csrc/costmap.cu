@@ -850,6 +850,25 @@ int navgpu_costmap_create(navgpu_costmap** out, uint32_t size_x, uint32_t size_y
   NAVGPU_CUDA(cudaMalloc(&h->d_win, sizeof(DevWindow)));
   NAVGPU_CUDA(cudaMalloc(&h->d_ticket, sizeof(unsigned)));
   NAVGPU_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
+  {
+    // One L1 / shared-memory split (the largest shared-memory carve-out, which k_inflate's 8 x 26 KB need anyway) for the
+    // three kernels of a cycle: CTAs of two kernels share an SM only if its split suits both, and an SM must drain to
+    // change it.  With the same split k_inflate's CTAs move in as k_merge_seed's leave instead of waiting for the SM to
+    // empty -- also on the SMs that hold the merge CTAs waiting for the obstacle kernel, or that kernel's last CTA.
+    // (k_merge_seed streams and k_obstacle_update scatters single bytes: neither misses the L1 it gives up.)
+    static bool done_for_device[64] = {};
+    static const bool separate = getenv("NAVGPU_SEPARATE_CARVEOUTS") != nullptr;  // measurement switch
+    if (!separate && h->device >= 0 && h->device < 64 && !done_for_device[h->device]) {
+      done_for_device[h->device] = true;
+      const int c = cudaSharedmemCarveoutMaxShared;
+      NAVGPU_CUDA(cudaFuncSetAttribute(k_obstacle_update, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+      NAVGPU_CUDA(cudaFuncSetAttribute(k_merge_seed, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+      NAVGPU_CUDA(cudaFuncSetAttribute(k_inflate<12>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+      NAVGPU_CUDA(cudaFuncSetAttribute(k_inflate<20>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+      NAVGPU_CUDA(cudaFuncSetAttribute(k_inflate<31>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+      NAVGPU_CUDA(cudaFuncSetAttribute(k_mirror_diff, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+    }
+  }
   NAVGPU_CUDA(cudaMalloc(&h->d_obst_done, sizeof(unsigned)));
   NAVGPU_CUDA(cudaMemset(h->d_obst_done, 0, sizeof(unsigned)));
   NAVGPU_CUDA(cudaMallocHost(&h->h_win, sizeof(DevWindow)));
