@@ -364,7 +364,7 @@ constexpr unsigned kMarkTileW = 256, kMarkTileH = 32;  // = k_merge_seed's tile 
 __device__ __forceinline__ void mark_commit_cta(uint8_t* __restrict__ grid, const long long* cells, int total_points,
                                                 uint8_t* __restrict__ tile_used = nullptr, unsigned pitch = 1, int nt = 0) {
   if (nt == 0) nt = blockDim.x;
-  constexpr int kU = 12;  // loads in flight per thread: a few thousand marks are one round trip for 256 threads
+  constexpr int kU = 13;  // loads in flight per thread: a few thousand marks are one round trip for 224 threads
   for (int base = threadIdx.x; base < total_points; base += kU * nt) {
     long long cell[kU];
 #pragma unroll
@@ -466,9 +466,11 @@ __device__ __forceinline__ bool polygon_prepare(const PolyArgs& poly, uint32_t* 
 }
 
 // Second stage for regular outlines, by every thread of the CTA (behind a barrier after polygon_prepare)
+// (tid of nt threads call; nt < 0: every thread of the CTA)
 __device__ __forceinline__ void polygon_fill_regular(uint8_t* __restrict__ grid, unsigned pitch, const PolyArgs& poly,
-                                                     uint8_t value, const uint32_t* cells, const uint32_t* sorted) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+                                                     uint8_t value, const uint32_t* cells, const uint32_t* sorted,
+                                                     int tid = -1, int nt = -1) {
+  if (nt < 0) { tid = threadIdx.x; nt = blockDim.x; }
   int min_x = poly.vx[0], max_x = poly.vx[0], min_y = poly.vy[0], max_y = poly.vy[0], n_outline = 0;
   for (int k = 0; k < poly.n; ++k) {
     const int k1 = (k + 1) % poly.n;
@@ -488,10 +490,17 @@ __device__ __forceinline__ void polygon_fill_regular(uint8_t* __restrict__ grid,
 
 // What is left for outlines that are not regular (degenerate footprints): the reference's walk replayed verbatim.
 // `cells` holds the outline (polygon_prepare); every thread of the CTA calls.
+// (tid of nt threads call, synchronising on named barrier 1 with nt participants; nt < 0: every thread of the CTA)
 __device__ __forceinline__ void polygon_fill_irregular(uint8_t* __restrict__ grid, unsigned pitch, const PolyArgs& poly,
-                                                       uint8_t value, uint32_t* cells, uint32_t* sorted, int capacity) {
+                                                       uint8_t value, uint32_t* cells, uint32_t* sorted, int capacity,
+                                                       int tid = -1, int nt = -1) {
   __shared__ int n_total;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool named = nt >= 0;
+  if (nt < 0) { tid = threadIdx.x; nt = blockDim.x; }
+  auto sync = [&] {
+    if (named) asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
+    else __syncthreads();
+  };
   int n_outline = 0;
   for (int k = 0; k < poly.n; ++k) {
     const int k1 = (k + 1) % poly.n;
@@ -506,7 +515,7 @@ __device__ __forceinline__ void polygon_fill_irregular(uint8_t* __restrict__ gri
     }
     sorted[rank] = cells[j];
   }
-  __syncthreads();
+  sync();
   if (tid == 0) {
     int size = n_outline;
     auto X = [&](int i) { return (int)(sorted[i] & 0xffffu); };
@@ -528,7 +537,7 @@ __device__ __forceinline__ void polygon_fill_irregular(uint8_t* __restrict__ gri
     }
     n_total = size;
   }
-  __syncthreads();
+  sync();
   for (int j = tid; j < n_total; j += nt) {
     const uint32_t c = sorted[j];
     grid[(size_t)(c >> 16) * pitch + (c & 0xffffu)] = value;
@@ -725,35 +734,41 @@ __global__ void __maxnreg__(48) k_obstacle_update(ObstacleArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // the ray warps store the marks while the ninth warp prepares the footprint polygon; its stores follow the marks
+  // The last CTA: ray warps 0..6 store the marks, the ninth warp prepares the footprint polygon meanwhile, both then
+  // store the polygon (behind the marks: named barrier 1 over those eight warps) and release the "layer grids complete"
+  // word; ray warp 7 runs the bounds pass next to all that (it only reads the layers' boxes, complete since the last
+  // ticket) -- a single thread's ~1500 dependent instructions that would otherwise end the kernel 9 us later.
+  constexpr int kTailThreads = 32 * kObstacleRayWarps;  // warps 0..6 and 8
   __shared__ bool s_regular;
+  if (cta_warp == kObstacleRayWarps - 1) {
+    if (lane == 0) {
+      if (a.do_finalize) finalize_bounds(a.ba, a.boxes, a.infl, a.win);
+      if (a.trace) atomicMax(&a.trace[1], trace_now());
+    }
+    return;
+  }
+  const int ttid = cta_warp < kObstacleRayWarps ? (int)threadIdx.x : (int)threadIdx.x - 32;  // 0 .. kTailThreads - 1
   if (cta_warp < kObstacleRayWarps) {
-    mark_commit_cta(a.grid, a.mark_cells, a.total_marks, a.tile_used, a.g.pitch, 32 * kObstacleRayWarps);
+    mark_commit_cta(a.grid, a.mark_cells, a.total_marks, a.tile_used, a.g.pitch, 32 * (kObstacleRayWarps - 1));
   } else if (a.do_poly) {
     const bool regular = polygon_prepare<true>(a.poly, poly_cells, poly_sorted, kPolySmallCells);
     if (lane == 0) s_regular = regular;
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(kTailThreads) : "memory");
   if (a.trace && threadIdx.x == 0) a.trace[10] = trace_now();
   if (a.do_poly) {
-    if (s_regular) polygon_fill_regular(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted);
-    else polygon_fill_irregular(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells);
+    if (s_regular) polygon_fill_regular(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, ttid, kTailThreads);
+    else polygon_fill_irregular(a.grid, a.g.pitch, a.poly, kFree, poly_cells, poly_sorted, kPolySmallCells, ttid, kTailThreads);
   }
   if (a.trace && threadIdx.x == 0) a.trace[11] = trace_now();
   if (a.done_flag) {
-    __syncthreads();  // every thread's mark / polygon stores are ordered before the release below
+    asm volatile("bar.sync 1, %0;" ::"n"(kTailThreads) : "memory");  // every mark / polygon store before the release
     if (threadIdx.x == 0) {
       __threadfence();
       asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.done_flag), "r"(a.done_epoch) : "memory");
     }
   }
-  if (threadIdx.x == 0) {
-    *a.ticket = 0;  // re-armed for the next cycle
-    if (a.do_finalize) {
-      __threadfence();
-      finalize_bounds(a.ba, a.boxes, a.infl, a.win);
-    }
-  }
+  if (threadIdx.x == 0) *a.ticket = 0;  // re-armed for the next cycle
   if (a.trace && threadIdx.x == 0) atomicMax(&a.trace[1], trace_now());
 }
 
@@ -1529,11 +1544,13 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 5) k_merge_seed(MergeSe
     // The window is the whole map whatever the obstacle kernel ahead of us adds to the bounds (they only grow), and that
     // kernel -- a latency chain of a few thousand rays on a fraction of the SMs -- writes layer cells only inside the
     // box of its rays, marks and footprint.  Tiles outside that box do not wait for it: the streaming merge of ~95 % of
-    // the map overlaps the ray tracing.  CTA (0, 0) always waits, so that this grid completes after the obstacle
-    // kernel and k_inflate, which waits for this grid, sees everything that kernel wrote (the window record included).
+    // the map overlaps the ray tracing.  CTA (0, 0) always waits for all of that kernel at its END, so that this grid
+    // completes after it and a k_inflate that waits for this grid sees everything that kernel wrote (the window record
+    // included) -- not in front of its own tile, which five inflation tiles need.
     w.x0 = 0; w.xn = (int)a.sx; w.y0 = 0; w.yn = (int)a.sy; w.valid = 1;
     const bool touched = bx0 < a.exn && bx0 + kW > a.ex0 && by0 < a.eyn && by0 + kH > a.ey0;
-    if ((blockIdx.x | blockIdx.y) == 0 || (touched && !a.obst_flag)) cudaGridDependencySynchronize();
+    // (CTA (0, 0) waits for the END of the obstacle kernel -- but behind its own work, see below)
+    if (touched && !a.obst_flag) cudaGridDependencySynchronize();
     if (touched && a.obst_flag) {
       // (every CTA of the obstacle kernel is resident or done before this grid is scheduled: it triggers the programmatic
       // launch at its first instruction, so waiting for its last CTA cannot deadlock)
@@ -1559,6 +1576,7 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 5) k_merge_seed(MergeSe
         if ((threadIdx.x | threadIdx.y) == 0)
           asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.ready + blockIdx.y * gridDim.x + blockIdx.x), "r"(a.epoch) : "memory");
       }
+      if ((blockIdx.x | blockIdx.y) == 0) cudaGridDependencySynchronize();  // this grid completes after the obstacle kernel
       return;
     }
   } else {
@@ -1605,6 +1623,7 @@ __global__ void __launch_bounds__(kMSGroupsX * kMSRowsY, 5) k_merge_seed(MergeSe
     if ((threadIdx.x | threadIdx.y) == 0)  // (release at gpu scope: cumulative over what the barrier made visible here)
       asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.ready + blockIdx.y * gridDim.x + blockIdx.x), "r"(a.epoch) : "memory");
   }
+  if (a.early && (blockIdx.x | blockIdx.y) == 0) cudaGridDependencySynchronize();  // (see the early-mode comment above)
 }
 
 // k_inflate phase 3: dy^2 of window row j against the eight output rows k of a group, (j - k)^2 in both 16-bit halves:
@@ -1994,6 +2013,9 @@ __device__ __forceinline__ void inflate_tile(const InflateArgs& a) {
 template <int RMAX>
 __global__ void __launch_bounds__(kIThreads, 8) k_inflate(InflateArgs a) {
   inflate_tile<RMAX>(a);
+  // tile (0, 0) of a sweep that runs on per-tile flags: behind the whole k_merge_seed grid, which completes behind the
+  // obstacle kernel -- done[0] tells k_mirror_diff that the cycle's window record and dirty box are final
+  if (a.ready && (blockIdx.x | blockIdx.y) == 0) cudaGridDependencySynchronize();
   // whichever way the tile ended: its master cells are final.  k_mirror_diff (the host mirror) starts on the tiles it
   // compares as soon as the inflate tiles that write them say so, instead of after the whole grid
   if (a.done) {
