@@ -285,7 +285,18 @@ int launch_mapgrid(const MapGridTarget* h, const MapGridArgs& ma, int n_ctas, in
   while ((1ull << planes) <= (unsigned long long)h->sx * h->sy + 1) ++planes;  // levels go up to n_cells
   const size_t sliced_smem = (size_t(3 + planes) * NW + 2) * sizeof(uint32_t);
   const int wpt = (NW + kMapGridThreads - 1) / kMapGridThreads;
-  if (wpt <= 4 && planes <= kMapGridMaxPlanes && sliced_smem <= 200 * 1024) {
+  // maps of at most 128 x 128 cells: the row kernel (registers + warp shuffles, a barrier per 16 levels).  A
+  // planner's few grids run with 512 threads per CTA -- the warps beyond the search warps help with the passable bits,
+  // the seeds and the epilogue; a fleet's thousands of grids run the search warps only.
+  // NAVGPU_MAPGRID=sliced | rows and NAVGPU_MAPGRID_HELPERS=0 | 1 force a variant (tests, measurements).
+  const char* force = getenv("NAVGPU_MAPGRID");
+  const char* force_helpers = getenv("NAVGPU_MAPGRID_HELPERS");
+  const bool rows_fit = h->sx <= 128 && h->sy <= 128;
+  if (rows_fit && !(force && !strcmp(force, "sliced"))) {
+    const bool helpers = force_helpers ? atoi(force_helpers) != 0 : n_ctas < 1024;
+    const size_t smem = size_t(15) * NW * sizeof(uint32_t);
+    k_mapgrid_prepare_rows<4, 2, 8><<<n_ctas, helpers ? 512 : 128, smem, h->stream>>>(ma, jobs_per_robot);
+  } else if (wpt <= 4 && planes <= kMapGridMaxPlanes && sliced_smem <= 200 * 1024) {
     auto launch = [&](auto kernel) -> int {
       if (sliced_smem > 48 * 1024)
         NAVGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sliced_smem));

@@ -106,7 +106,7 @@ constexpr int kMapGridMaxPlanes = 18;
 // Returns false when no plan point is on the map (every cell stays unreachable).
 __device__ __forceinline__ bool mapgrid_seed(const MapGridJob& job, const DwaGeom& g, uint32_t* F0, int W) {
   __shared__ int s_first, s_end;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;  // (512 threads in the sliced kernels, 32 .. 128 in the row kernel)
   if (tid == 0) {
     s_first = 0x7fffffff;
     s_end = job.n_points;
@@ -126,30 +126,30 @@ __device__ __forceinline__ bool mapgrid_seed(const MapGridJob& job, const DwaGeo
   int cached[kCached];
 #pragma unroll
   for (int q = 0; q < kCached; ++q) {
-    const int i = tid + q * kMapGridThreads;
+    const int i = tid + q * nt;
     cached[q] = i < job.n_points ? point_cell(i) : -1;
     if (cached[q] >= 0) atomicMin(&s_first, i);
   }
-  for (int i = tid + kCached * kMapGridThreads; i < job.n_points; i += kMapGridThreads)
+  for (int i = tid + kCached * nt; i < job.n_points; i += nt)
     if (point_cell(i) >= 0) atomicMin(&s_first, i);
   __syncthreads();
   const int first = s_first;
   if (first == 0x7fffffff) return false;
 #pragma unroll
   for (int q = 0; q < kCached; ++q) {
-    const int i = tid + q * kMapGridThreads;
+    const int i = tid + q * nt;
     if (i > first && i < job.n_points && cached[q] < 0) atomicMin(&s_end, i);
   }
-  for (int i = tid + kCached * kMapGridThreads; i < job.n_points; i += kMapGridThreads)
+  for (int i = tid + kCached * nt; i < job.n_points; i += nt)
     if (i > first && point_cell(i) < 0) atomicMin(&s_end, i);
   __syncthreads();
   const int end = s_end, lo = job.local_goal ? end - 1 : first;
 #pragma unroll
   for (int q = 0; q < kCached; ++q) {
-    const int i = tid + q * kMapGridThreads;
+    const int i = tid + q * nt;
     if (i >= lo && i < end) atomicOr(&F0[(cached[q] >> 16) * W + ((cached[q] & 0xffff) >> 5)], 1u << (cached[q] & 31));
   }
-  for (int i = tid + kCached * kMapGridThreads; i < end; i += kMapGridThreads) {
+  for (int i = tid + kCached * nt; i < end; i += nt) {
     if (i < lo) continue;
     const int c = point_cell(i);
     atomicOr(&F0[(c >> 16) * W + ((c & 0xffff) >> 5)], 1u << (c & 31));
@@ -321,6 +321,292 @@ __global__ void __launch_bounds__(kMapGridThreads, kWPT == 1 ? 2 : 1) k_mapgrid_
       const uint32_t v = (park[wi] >> lane) & 1u, p = (park[NW + wi] >> lane) & 1u, sd = (park[2 * NW + wi] >> lane) & 1u;
       // seeds 0 (even on an obstacle), untouched cells unreachableCellCosts, touched obstacles obstacleCosts
       job.dist[(size_t)r * g.sx + c] = sd ? 0u : (!v ? n_cells + 1 : (!p ? n_cells : d));
+    }
+  }
+}
+
+// Row variant for local maps of at most 128 x 128 cells (the usual 6 m window is 120 x 120): NO barrier and NO shared
+// memory inside a level.  A lane of a search warp owns kRPL consecutive rows of 4 words (128 cells) each -- frontier,
+// "passable and not yet visited" bits and the eight low bit planes of the level all live in its registers; the row
+// above / below the lane's rows comes through two warp shuffles per word, the left / right cell through funnel shifts:
+//     next = (F<<1 | F>>1 | F(up) | F(down)) & A;   A ^= next;   low planes |= next by the level's (static) low bits
+// and once per kTrip levels the planes above take T = A(before) ^ A(after) by the bits those levels share: ~7
+// instructions per word and level against five shared loads, a store and a CTA barrier in the sliced kernel.
+// Search warp w owns rows [w * own, (w + 1) * own) and carries `halo` more rows on either side; rows at distance t from
+// the window's edge go stale after t levels (their outer neighbours are missing), so the warps run `halo` levels on
+// their own, then publish their own rows (F, A) in shared memory and refresh their halo rows: one (named) barrier per
+// `halo` levels -- 16 at 120 rows and 4 warps -- instead of one per level.
+// Touched-but-not-expanded cells (obstacles next to an expanded cell) are derived once at the end as the neighbours
+// of the expanded set, instead of being tracked per level.  Levels >= 256 (mazes) leave the planes: those cells are
+// written to the grid as they are reached and flagged in a ninth plane (shared memory), which the epilogue skips.
+// A planner's launch has 512 threads: the warps beyond the search warps compute passable bits and seeds with them,
+// sleep at the CTA barrier during the search and share the epilogue (planes parked in shared memory; four cells per
+// lane spread into the bytes of one word by nibble * 0x204081 & 0x01010101; uint4 stores).  A fleet's launch has the
+// search warps only (thousands of grids: occupancy instead of latency).
+// Measured (C2, 144 levels): 42 us sliced -> 28 us; the search is bound by the ALU pipe of the four schedulers (one
+// warp instruction per two cycles each, B300_MICROARCH "pipe rates"), ~55 instructions per level and warp.
+template <int kWarps, int kRPL, int kTrip>
+__global__ void __launch_bounds__(512) k_mapgrid_prepare_rows(MapGridArgs a, int jobs_per_robot) {
+  extern __shared__ uint32_t mg_smem[];
+  cudaTriggerProgrammaticLaunchCompletion();  // the scoring kernel may be scheduled behind us; it waits for our end
+  const MapGridJob job = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.job[blockIdx.x % jobs_per_robot]
+                                 : a.job[blockIdx.x % jobs_per_robot];
+  if (job.skip) return;
+  const DwaGeom g = a.fleet ? a.fleet[blockIdx.x / jobs_per_robot].grids.g : a.g;
+  static_assert(kWarps > 1 && (kTrip == 4 || kTrip == 8), "search warps exchange halo rows; trips of 4 or 8 levels");
+  constexpr int kWin = 32 * kRPL, kSearchThreads = 32 * kWarps;
+  constexpr uint32_t kFull = 0xffffffffu;
+  const int nt = blockDim.x;  // 32 * kWarps, or 512: the extra warps help before and after the search
+  const int W = (g.sx + 31) / 32, sy = (int)g.sy, NW = W * sy;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_cells = g.sx * g.sy;
+  uint32_t* Psm = mg_smem;      // passable bits, [row][W]
+  uint32_t* Ssm = Psm + NW;     // seed bits
+  uint32_t* Dsm = Ssm + NW;     // cells of level >= 256 (written to the grid as they were reached)
+  uint32_t* XF = Dsm + NW;      // published rows, two buffers of F | A; the touched bits at the end
+  uint32_t* Pl = XF + 4 * NW;   // the eight planes, parked for the epilogue
+  for (int wi = tid; wi < NW; wi += nt) {
+    Psm[wi] = mapgrid_passable(g, a.allow_unknown, wi / W, wi % W) | (job.within_robot ? job.within_robot[wi] : 0u);
+    Ssm[wi] = 0;
+    Dsm[wi] = 0;
+  }
+  __syncthreads();
+  mapgrid_seed(job, g, Ssm, W);  // (no seed: every bit stays 0, every cell unreachable)
+
+  if (warp < kWarps) {  // ---- the search, by the first kWarps warps (barrier 1 is theirs; the others wait below)
+  auto search_barrier_or = [&](bool pred) -> bool {
+    uint32_t r;
+    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "r"((uint32_t)pred), "n"(kSearchThreads) : "memory");
+    return r != 0;
+  };
+  // rows of this lane: row0 + j; own rows of the warp [own_lo, own_hi).  The first row of lane 0 and the last row of
+  // lane 31 are never rows whose bits matter (off the map, or the outermost halo rows), so the shuffles at the warp's
+  // ends need no masking: whatever they deliver lands in rows that are empty or stale by design.
+  const int own = (sy + kWarps - 1) / kWarps;
+  const int margin = (kWin - own) / 2;
+  const int halo = margin & ~7;  // levels between exchanges (>= 8 for every map the host sends here)
+  const int own_lo = warp * own, own_hi = min(own_lo + own, sy);
+  const int row0 = own_lo - margin + lane * kRPL;
+  uint32_t F[kRPL][4], G[kRPL][4], A[kRPL][4], T[kRPL][4], D[8][kRPL][4];
+#pragma unroll
+  for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int r = row0 + j;
+      const bool in = r >= 0 && r < sy && w < W;
+      const uint32_t p = in ? Psm[r * W + w] : 0u, sd = in ? Ssm[r * W + w] : 0u;
+      F[j][w] = sd;
+      A[j][w] = p & ~sd;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) D[k][j][w] = 0;
+    }
+  // the four neighbours of the bits of X, into Y (every row of the window; the outermost rows get whatever the
+  // shuffle delivers at the warp's ends)
+  auto neighbours = [&](const uint32_t (&X)[kRPL][4], uint32_t (&Y)[kRPL][4]) {
+    uint32_t up[4], dn[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      up[w] = __shfl_up_sync(kFull, X[kRPL - 1][w], 1);
+      dn[w] = __shfl_down_sync(kFull, X[0][w], 1);
+    }
+#pragma unroll
+    for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t f = X[j][w], l = w ? X[j][w - 1] : 0u, r = w < 3 ? X[j][w + 1] : 0u;
+        const uint32_t u = j ? X[j - 1][w] : up[w], d = j < kRPL - 1 ? X[j + 1][w] : dn[w];
+        Y[j][w] = __funnelshift_l(l, f, 1) | __funnelshift_r(f, r, 1) | u | d;
+      }
+  };
+  // level `base + i` (i < kTrip at compile time): the low planes take the new cells of the levels whose bit is set.
+  // kDeep (levels >= 256, a maze: rare) is a separate instantiation so that the usual loop stays a few hundred
+  // instructions of straight-line code -- a lone warp per scheduler has nothing to hide instruction fetches behind.
+  auto one_level = [&](const uint32_t (&X)[kRPL][4], uint32_t (&Y)[kRPL][4], uint32_t base, auto ic, auto deep) {
+    constexpr int i = decltype(ic)::value;
+    neighbours(X, Y);
+#pragma unroll
+    for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        Y[j][w] &= A[j][w];
+        A[j][w] ^= Y[j][w];
+        if (i & 1) D[0][j][w] |= Y[j][w];
+        if (i & 2) D[1][j][w] |= Y[j][w];
+        if (i & 4) D[2][j][w] |= Y[j][w];
+      }
+    if (decltype(deep)::value) {  // the level no longer fits the planes: the cells are written as they are reached
+#pragma unroll 1
+      for (int j = 0; j < kRPL; ++j) {
+        const int r = row0 + j;
+        if (r < own_lo || r >= own_hi) continue;
+#pragma unroll 1
+        for (int w = 0; w < W; ++w) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int jj = 0; jj < kRPL; ++jj)
+#pragma unroll
+            for (int ww = 0; ww < 4; ++ww)
+              if (jj == j && ww == w) m = Y[jj][ww];
+          if (m) Dsm[r * W + w] |= m;  // (the word belongs to this lane)
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            job.dist[(size_t)r * g.sx + w * 32 + b] = base + i;
+          }
+        }
+      }
+    }
+  };
+  // levels base .. base + kTrip - 1 (base a multiple of kTrip): the cells reached in them share the level's bits from
+  // log2(kTrip) up, which are set once per trip from T = A(before) ^ A(after)
+  auto trip = [&](uint32_t base, auto deep) {
+#pragma unroll
+    for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) T[j][w] = A[j][w];
+    if (base) one_level(F, G, base, std::integral_constant<int, 0>(), deep);  // (level 0 is the seeds themselves)
+    else {
+#pragma unroll
+      for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) G[j][w] = F[j][w];
+    }
+    one_level(G, F, base, std::integral_constant<int, 1>(), deep);
+    one_level(F, G, base, std::integral_constant<int, 2>(), deep);
+    one_level(G, F, base, std::integral_constant<int, 3>(), deep);
+    if (kTrip == 8) {
+      one_level(F, G, base, std::integral_constant<int, 4>(), deep);
+      one_level(G, F, base, std::integral_constant<int, 5>(), deep);
+      one_level(F, G, base, std::integral_constant<int, 6>(), deep);
+      one_level(G, F, base, std::integral_constant<int, 7>(), deep);
+    }
+#pragma unroll
+    for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) T[j][w] ^= A[j][w];
+#pragma unroll
+    for (int k = (kTrip == 8 ? 3 : 2); k < 8; ++k)
+      if ((base >> k) & 1u) {
+#pragma unroll
+        for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) D[k][j][w] |= T[j][w];
+      }
+  };
+  auto trips = [&](uint32_t base) {
+    if (base < 256) trip(base, std::false_type());
+    else trip(base, std::true_type());
+  };
+  auto own_rows_or = [&](const uint32_t (&X)[kRPL][4]) -> uint32_t {
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < kRPL; ++j) {
+      const int r = row0 + j;
+      if (r >= own_lo && r < own_hi) any |= X[j][0] | X[j][1] | X[j][2] | X[j][3];
+    }
+    return any;
+  };
+  // publish the own rows of X / refresh the rows of the window that other warps own
+  auto publish = [&](uint32_t* buf, const uint32_t (&X)[kRPL][4]) {
+#pragma unroll
+    for (int j = 0; j < kRPL; ++j) {
+      const int r = row0 + j;
+      if (r < own_lo || r >= own_hi) continue;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (w < W) buf[r * W + w] = X[j][w];
+    }
+  };
+  auto refresh = [&](const uint32_t* buf, uint32_t (&X)[kRPL][4]) {
+#pragma unroll
+    for (int j = 0; j < kRPL; ++j) {
+      const int r = row0 + j;
+      if (r < 0 || r >= sy || (r >= own_lo && r < own_hi)) continue;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (w < W) X[j][w] = buf[r * W + w];
+    }
+  };
+
+  uint32_t lv = 0;  // levels done (a multiple of kTrip); the frontier of level lv - 1 (the seeds at first) is in F
+  {
+    for (uint32_t e = 0;; ++e) {
+#pragma unroll 1
+      for (int t = 0; t < halo; t += kTrip) {
+        trips(lv);
+        lv += kTrip;
+      }
+      uint32_t* buf = XF + (e & 1u) * 2 * NW;
+      publish(buf, F);
+      publish(buf + NW, A);
+      if (!search_barrier_or(own_rows_or(F) != 0)) break;  // exact rows only: an empty frontier everywhere ends the search
+      refresh(buf, F);
+      refresh(buf + NW, A);
+    }
+  }
+
+  // expanded cells E = seeds | visited passable cells; touched = E | neighbours(E)
+#pragma unroll
+  for (int j = 0; j < kRPL; ++j)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int r = row0 + j;
+      const bool in = r >= 0 && r < sy && w < W;
+      F[j][w] = in ? (Ssm[r * W + w] | (Psm[r * W + w] & ~A[j][w])) : 0u;
+    }
+  search_barrier_or(false);  // (everyone has left the loop: the exchange buffers are free)
+  publish(XF, F);
+  search_barrier_or(false);
+  refresh(XF, F);
+  search_barrier_or(false);  // (... and read, before the touched bits overwrite them)
+  neighbours(F, G);
+  // park what the epilogue needs of the own rows: touched bits and the planes
+#pragma unroll
+  for (int j = 0; j < kRPL; ++j) {
+    const int r = row0 + j;
+    if (r < own_lo || r >= own_hi) continue;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      if (w >= W) continue;
+      XF[r * W + w] = F[j][w] | G[j][w];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) Pl[k * NW + r * W + w] = D[k][j][w];
+    }
+  }
+  }  // ---- end of the search warps' part
+  __syncthreads();
+  // Epilogue, every warp of the CTA: a warp per row, a lane per four cells.  The planes of four cells are spread into
+  // the bytes of one word (nibble * 0x204081 & 0x01010101 puts bit b into byte b); seeds 0 (even on an obstacle),
+  // untouched cells unreachableCellCosts, touched obstacles obstacleCosts; uint4 stores.
+  const bool vec = (g.sx & 3u) == 0 && ((size_t)job.dist & 15u) == 0;
+  const int w = lane >> 3, c = (lane & 7) * 4;
+  const int ncols = min(32, (int)g.sx - w * 32);
+  for (int r = warp; r < sy; r += nt >> 5) {
+    if (w >= W || c >= ncols) continue;
+    const int wi = r * W + w;
+    const uint32_t touched = XF[wi], pw = Psm[wi], sw = Ssm[wi];
+    const uint32_t unreached = ~touched >> c, obstacle = (touched & ~pw & ~sw) >> c, seed = sw >> c;
+    const uint32_t dn = (Dsm[wi] >> c) & 0xfu;  // cells written during the search keep their value
+    uint32_t lo = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lo |= ((((Pl[k * NW + wi] >> c) & 0xfu) * 0x00204081u) & 0x01010101u) << k;
+    uint32_t out[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint32_t v = (lo >> (8 * b)) & 0xffu;
+      v = ((seed >> b) & 1u) ? 0u : v;
+      v = ((obstacle >> b) & 1u) ? n_cells : v;
+      v = ((unreached >> b) & 1u) ? n_cells + 1 : v;
+      out[b] = v;
+    }
+    uint32_t* dst = job.dist + (size_t)r * g.sx + w * 32 + c;
+    if (vec && dn == 0) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (c + b < ncols && !((dn >> b) & 1u)) dst[b] = out[b];
     }
   }
 }
