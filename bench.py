@@ -469,6 +469,16 @@ def run_native_dwa(api, torch, dist, rank, world, local_rank, steps):
     out["c2_samples"] = int(r2["n_samples"])
     out["c2_best_index"] = int(r2["best_index"])
     out["c2_traj_per_s"] = r2["n_samples"] / (out["c2_findBestPath_us"] * 1e-6)
+    # MapGridCostFunction::prepare x 4 alone (navgpu_dwa_prepare: the MapGrid wavefront kernel), CUDA events on the
+    # planner's stream -- the device-side counterpart of cpu_baseline.prepare_ms
+    s2 = torch.cuda.ExternalStream(d2.stream(), device=local_rank)
+    pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in pe:
+        a.record(s2)
+        d2.prepare()
+        b.record(s2)
+        d2.synchronize()
+    out["c2_prepare_device_us"] = 1e3 * float(np.mean([a.elapsed_time(b) for a, b in pe]))
 
     d4, pose, vel = dwa_setup(api, grid, C4, device=local_rank)
     stream = torch.cuda.ExternalStream(d4.stream(), device=local_rank)
